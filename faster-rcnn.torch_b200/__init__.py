@@ -1,0 +1,12 @@
+"""B200-native Faster R-CNN detection hot path behind the reference's Lua surface.
+
+Host mirror (Python, because this image has no Lua toolchain) of the names the reference exposes on the path:
+Rect, Localizer, Anchors, nms, Detector, extract_roi_pooling_input and the vgg_small / vgg_large model factories.
+All arithmetic runs in libfrcnn_b200.so (hand-written CUDA for sm_100a) through the C ABI of include/frcnn_b200.h;
+PyTorch is used for device memory only.  There is no CPU fallback."""
+from ._lib import FrcnnError, declared_functions, ffi, lib  # noqa: F401
+from .rect import Rect  # noqa: F401
+from .geometry import Anchors, Localizer  # noqa: F401
+from .nms import nms, nms_segmented, nms_segmented_dev  # noqa: F401
+from .models import Model, create_model, duplo_cfg, imgnet_cfg, vgg_large, vgg_small  # noqa: F401
+from .detector import Detector, extract_roi_pooling_input  # noqa: F401

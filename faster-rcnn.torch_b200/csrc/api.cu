@@ -1,0 +1,1255 @@
+// C ABI of the library (include/frcnn_b200.h): context, model plan, weight packing, pnet / cnet forward and the
+// fused Detector:detect pipeline.  Host orchestration only -- every arithmetic step is a kernel of this library.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <array>
+#include <memory>
+
+#include "common.h"
+#include "detect.h"
+#include "nms.h"
+
+namespace frcnn {
+
+static std::string g_last_error;
+void set_global_error(const std::string& msg) { g_last_error = msg; }
+
+struct ParamInfo {
+  std::string name;
+  int64_t numel;
+};
+
+struct ConvLayer {
+  int cin, cout, k, pad;
+  bool first;       // 3-channel first layer: im2col + 1x1 GEMM over 64-wide patches
+  float scale;      // SpatialDropout evaluate-mode factor (1 if no dropout follows)
+  int p_w, p_b, p_prelu;
+  bf16* w_packed = nullptr;
+  int block;        // trunk block index, or -1 for an anchor-head conv
+  // per-shape state
+  int hin = 0, win = 0, hout = 0, wout = 0;
+  bf16* in = nullptr;
+  bf16* out = nullptr;
+  ConvLaunch launch;
+};
+
+struct Head {
+  int kW, n, input;
+  ConvLayer conv;
+  int p_w2, p_b2;
+  float* acc = nullptr;      // [N][hh][hw][n] fp32 split-K sums
+  float* out = nullptr;      // [N][18][hh][hw] fp32
+  int hh = 0, hw = 0;
+};
+
+struct FcLayer {
+  int nin, nout;
+  bool bn;
+  int p_w, p_b, p_bn_w, p_bn_b, p_bn_mean, p_bn_var, p_prelu;
+  bf16* w_packed = nullptr;
+  float* acc = nullptr;      // [R_cap][nout] fp32
+  bf16* out_bf16 = nullptr;  // [R_cap][nout]
+  float* out_f32 = nullptr;  // last layer only
+  ConvLaunch launch;
+};
+
+}  // namespace frcnn
+
+using namespace frcnn;
+
+struct frcnn_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  int cc_major = 0, cc_minor = 0;
+  std::string err;
+  int64_t launches = 0;
+
+  // plan
+  bool planned = false;
+  std::vector<frcnn_block_desc> blocks;
+  std::vector<frcnn_head_desc> head_desc;
+  std::vector<frcnn_fc_desc> fc_desc;
+  int class_count = 0, roi_kh = 6, roi_kw = 6;
+  std::vector<double> scales;
+  std::vector<ParamInfo> params;
+  std::vector<const float*> bound;
+  bool packed = false;
+  std::vector<ConvLayer> trunk;
+  std::vector<Head> heads;
+  std::vector<FcLayer> fcs;
+  int p_reg_w = -1, p_reg_b = -1, p_cls_w = -1, p_cls_b = -1;
+  int feat_c = 0;
+  std::vector<std::vector<std::array<int, 6>>> loc;  // heads..., ROI
+  std::vector<float> w_lut, h_lut;
+  float* d_w_lut = nullptr;
+  float* d_h_lut = nullptr;
+  LocalizerDev roi_loc;
+
+  // thresholds (Detector.lua:54,81,115,133)
+  double thr_fg = 0.95, thr_class = 0.2;
+  float thr_nms1 = 0.25f, thr_nms2 = 0.1f;
+
+  // activation workspace for (N, H, W)
+  int ws_n = 0, ws_h = 0, ws_w = 0;
+  std::vector<void*> ws_allocs;
+  bf16* patches = nullptr;
+  std::vector<bf16*> pool_out;   // per block
+  std::vector<int> pool_h, pool_w;
+  int feat_h = 0, feat_w = 0;
+
+  // detector workspace
+  int cand_cap = 4096;
+  int det_n = 0;             // batch size the detector buffers were sized for
+  int roi_cap = 0;           // total ROI rows
+  std::vector<void*> det_allocs;
+  double* cand_r = nullptr;
+  float4* cand_box = nullptr;
+  float* cand_logp = nullptr;
+  int4* cand_anchor = nullptr;
+  int* cand_count = nullptr;
+  int* flags = nullptr;      // [0] candidate overflow, [1] degenerate ROIs, [2] roi_total, [3] n_det
+  int* ticket = nullptr;
+  unsigned long long* status = nullptr;
+  int status_blocks = 0;
+  unsigned epoch = 0;
+  int* pick1 = nullptr;
+  int* count1 = nullptr;
+  int* roi_base = nullptr;
+  bf16* roi_out = nullptr;
+  int* roi_img = nullptr;
+  int* roi_cand = nullptr;
+  float* reg_out = nullptr;
+  float* cls_out = nullptr;
+  double* fin_r2 = nullptr;
+  float4* fin_box = nullptr;
+  int* fin_cls = nullptr;
+  float* fin_conf = nullptr;
+  float4* gbox = nullptr;
+  int* grow = nullptr;
+  int* n_pass = nullptr;
+  frcnn_detection* det_dev = nullptr;
+  int det_cap = 0;
+  void* nms_mem = nullptr;
+  size_t nms_bytes = 0;
+  NmsWorkspace nms;
+  int nms_cap_total = 0, nms_cap_seg = 0;
+  // pinned host staging
+  int* h_ints = nullptr;           // [16]
+  frcnn_detection* h_det = nullptr;
+  int h_det_cap = 0;
+  float* h_img = nullptr;
+  size_t h_img_bytes = 0;
+  float* d_img = nullptr;
+  size_t d_img_bytes = 0;
+  int64_t stats[4] = {0, 0, 0, 0};
+  bool profiling = false;
+  cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float timings[6] = {0, 0, 0, 0, 0, 0};
+  // scratch for API-level calls
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+};
+
+namespace frcnn {
+
+static void* dev_alloc(std::vector<void*>& list, size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 256;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) throw Error{FRCNN_E_NOMEM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e)};
+  list.push_back(p);
+  return p;
+}
+static void free_all(std::vector<void*>& list) {
+  for (void* p : list) cudaFree(p);
+  list.clear();
+}
+static void* ensure_scratch(frcnn_ctx* c, size_t bytes) {
+  if (bytes > c->scratch_bytes) {
+    if (c->scratch) {
+      FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+      cudaFree(c->scratch);
+      c->scratch = nullptr;
+      c->scratch_bytes = 0;
+    }
+    cudaError_t e = cudaMalloc(&c->scratch, bytes);
+    if (e != cudaSuccess) throw Error{FRCNN_E_NOMEM, std::string("cudaMalloc scratch: ") + cudaGetErrorString(e)};
+    c->scratch_bytes = bytes;
+  }
+  return c->scratch;
+}
+
+// small utility kernels --------------------------------------------------------------------------------------
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+// fp32 [R][C*bins] in the reference's flatten order (c*bins + b) -> bf16 [R][bins][C]
+__global__ void pack_roi_rows_kernel(const float* __restrict__ x, bf16* __restrict__ out, long R, int C, int bins) {
+  long total = R * C * bins;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i / ((long)C * bins);
+    int k = i - r * (long)C * bins;
+    int b = k / C, c = k - b * C;
+    out[i] = __float2bfloat16_rn(x[r * (long)C * bins + (long)c * bins + b]);
+  }
+}
+// split-K sums -> prelu(acc + bias) * scale -> bf16 (test entry frcnn_conv_bf16 with splits > 1)
+__global__ void acc_tail_kernel(const float* __restrict__ acc, const float* __restrict__ bias, const float* __restrict__ prelu,
+                                float scale, bf16* __restrict__ out, long total, int n) {
+  const bool hp = prelu != nullptr;
+  const float slope = hp ? prelu[0] : 1.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float x = acc[i] + (bias ? bias[i % n] : 0.f);
+    if (hp) x = x > 0.f ? x : x * slope;
+    out[i] = __float2bfloat16_rn(x * scale);
+  }
+}
+
+// geometry (host) ------------------------------------------------------------------------------------------
+static double lua_mod_h(double a, double b) { return a - floor(a / b) * b; }
+
+// Localizer:inputToFeatureRect (Localizer.lua:41-67)
+static void input_to_feature(const std::vector<std::array<int, 6>>& L, const double in[4], double out[4]) {
+  double minX = in[0], minY = in[1], maxX = in[2], maxY = in[3];
+  for (const auto& l : L) {
+    const double kW = l[0], kH = l[1], dW = l[2], dH = l[3], pW = l[4], pH = l[5];
+    if (dW < kW) {
+      minX -= (kW - dW); maxX += (kW - dW);
+      minY -= (kH - dH); maxY += (kH - dH);
+    }
+    minX += pW; maxX += pW; minY += pH; maxY += pH;
+    minX = minX / dH;
+    minY = minY / dH;
+    if (lua_mod_h(maxX - kW, dW) == 0.0) maxX = std::max((maxX - kW) / dW + 1.0, minX + 1.0);
+    else maxX = std::max(ceil((maxX - kW) / dW) + 1.0, minX + 1.0);
+    if (lua_mod_h(maxY - kH, dH) == 0.0) maxY = std::max((maxY - kH) / dW + 1.0, minY + 1.0);
+    else maxY = std::max(ceil((maxY - kH) / dH) + 1.0, minY + 1.0);
+  }
+  out[0] = floor(minX); out[1] = floor(minY); out[2] = ceil(maxX); out[3] = ceil(maxY);
+}
+// Localizer:featureToInputRect (Localizer.lua:69-79)
+static void feature_to_input(const std::vector<std::array<int, 6>>& L, const double in[4], double out[4]) {
+  double minX = in[0], minY = in[1], maxX = in[2], maxY = in[3];
+  for (int i = (int)L.size() - 1; i >= 0; --i) {
+    const auto& l = L[i];
+    minX = minX * l[2] - l[4];
+    minY = minY * l[3] - l[4];               // sic: padW (Localizer.lua:74)
+    maxX = maxX * l[2] - l[5] + l[0] - l[2]; // sic: padH (Localizer.lua:75)
+    maxY = maxY * l[3] - l[5] + l[1] - l[3];
+  }
+  out[0] = minX; out[1] = minY; out[2] = maxX; out[3] = maxY;
+}
+// Anchors.__init (Anchors.lua:15-57)
+static void build_luts(frcnn_ctx* c) {
+  const int S = (int)c->scales.size();
+  c->w_lut.assign((size_t)S * 3 * LUT_EXTENT * 2, 0.f);
+  c->h_lut.assign((size_t)S * 3 * LUT_EXTENT * 2, 0.f);
+  for (int i = 0; i < S; ++i) {
+    const double s = c->scales[i];
+    const double a = s / sqrt(2.0);
+    const double asp[3][2] = {{s, s}, {2 * a, a}, {a, 2 * a}};
+    for (int j = 0; j < 3; ++j) {
+      for (int y = 1; y <= LUT_EXTENT; ++y) {
+        double in[4] = {0, (double)(y - 1), 0, (double)y}, r[4];
+        feature_to_input(c->loc[i], in, r);
+        const double cy = (r[1] + r[3]) / 2;
+        const double mn = cy - asp[j][1] * 0.5;  // Rect.fromCenterWidthHeight (Rect.lua:30-36)
+        c->h_lut[(((size_t)i * 3 + j) * LUT_EXTENT + (y - 1)) * 2 + 0] = (float)mn;
+        c->h_lut[(((size_t)i * 3 + j) * LUT_EXTENT + (y - 1)) * 2 + 1] = (float)(mn + asp[j][1]);
+      }
+      for (int x = 1; x <= LUT_EXTENT; ++x) {
+        double in[4] = {(double)(x - 1), 0, (double)x, 0}, r[4];
+        feature_to_input(c->loc[i], in, r);
+        const double cx = (r[0] + r[2]) / 2;
+        const double mn = cx - asp[j][0] * 0.5;
+        c->w_lut[(((size_t)i * 3 + j) * LUT_EXTENT + (x - 1)) * 2 + 0] = (float)mn;
+        c->w_lut[(((size_t)i * 3 + j) * LUT_EXTENT + (x - 1)) * 2 + 1] = (float)(mn + asp[j][0]);
+      }
+    }
+  }
+}
+
+static int add_param(frcnn_ctx* c, const std::string& name, int64_t numel) {
+  c->params.push_back({name, numel});
+  return (int)c->params.size() - 1;
+}
+
+static void do_plan(frcnn_ctx* c, const frcnn_block_desc* blocks, int n_blocks, const frcnn_head_desc* heads, int n_heads,
+                    const frcnn_fc_desc* fcs, int n_fcs, int class_count, int roi_kh, int roi_kw, const double* scales,
+                    int n_scales, float dropout_eval_scale) {
+  FRCNN_REQUIRE(!c->planned, FRCNN_E_STATE, "model plan already set on this ctx");
+  FRCNN_REQUIRE(n_blocks >= 1 && n_blocks <= 8 && n_fcs >= 1 && class_count >= 1, FRCNN_E_INVALID, "bad model description");
+  FRCNN_REQUIRE(n_heads == MAX_HEADS && n_scales == MAX_HEADS, FRCNN_E_INVALID,
+                "the reference hard-codes 4 anchor layers (Detector.lua:38, Anchors.lua:108)");
+  c->blocks.assign(blocks, blocks + n_blocks);
+  c->head_desc.assign(heads, heads + n_heads);
+  c->fc_desc.assign(fcs, fcs + n_fcs);
+  c->class_count = class_count;
+  c->roi_kh = roi_kh;
+  c->roi_kw = roi_kw;
+  c->scales.assign(scales, scales + n_scales);
+  int cin = 3;
+  for (int b = 0; b < n_blocks; ++b) {
+    const auto& l = blocks[b];
+    FRCNN_REQUIRE(l.kW == l.kH && l.padW == l.padH && l.conv_steps >= 1, FRCNN_E_INVALID, "square kernels / symmetric pads only");
+    FRCNN_REQUIRE(l.filters % 64 == 0, FRCNN_E_INVALID, "block filters must be a multiple of 64");
+    for (int s = 0; s < l.conv_steps; ++s) {
+      ConvLayer cv;
+      cv.cin = cin; cv.cout = l.filters; cv.k = l.kW; cv.pad = l.padW;
+      cv.first = (cin == 3);
+      cv.block = b;
+      cv.scale = 1.0f;
+      if (s == 0 && l.dropout > 0.f) cv.scale = dropout_eval_scale < 0.f ? 1.0f - l.dropout : dropout_eval_scale;  // Q5
+      std::string n = "b" + std::to_string(b + 1) + "_c" + std::to_string(s + 1);
+      cv.p_w = add_param(c, n + ".weight", (int64_t)l.filters * cin * l.kH * l.kW);
+      cv.p_b = add_param(c, n + ".bias", l.filters);
+      cv.p_prelu = add_param(c, n + ".prelu", 1);
+      c->trunk.push_back(cv);
+      cin = l.filters;
+    }
+  }
+  c->feat_c = cin;
+  for (int h = 0; h < n_heads; ++h) {
+    const auto& a = heads[h];
+    FRCNN_REQUIRE(a.input >= 1 && a.input <= n_blocks, FRCNN_E_INVALID, "anchor net input out of range");
+    FRCNN_REQUIRE(a.n % 128 == 0, FRCNN_E_INVALID, "anchor net width must be a multiple of 128");
+    Head hd;
+    hd.kW = a.kW; hd.n = a.n; hd.input = a.input;
+    hd.conv.cin = blocks[a.input - 1].filters; hd.conv.cout = a.n; hd.conv.k = a.kW; hd.conv.pad = 0;
+    hd.conv.first = false; hd.conv.block = -1; hd.conv.scale = 1.f;
+    std::string n = "h" + std::to_string(h + 1);
+    hd.conv.p_w = add_param(c, n + "_conv.weight", (int64_t)a.n * hd.conv.cin * a.kW * a.kW);
+    hd.conv.p_b = add_param(c, n + "_conv.bias", a.n);
+    hd.conv.p_prelu = add_param(c, n + "_conv.prelu", 1);
+    hd.p_w2 = add_param(c, n + "_out.weight", 18 * a.n);
+    hd.p_b2 = add_param(c, n + "_out.bias", 18);
+    c->heads.push_back(hd);
+  }
+  int fin = roi_kh * roi_kw * c->feat_c;
+  for (int i = 0; i < n_fcs; ++i) {
+    FRCNN_REQUIRE(fcs[i].n % 64 == 0, FRCNN_E_INVALID, "class layer width must be a multiple of 64");
+    FcLayer f;
+    f.nin = fin; f.nout = fcs[i].n; f.bn = fcs[i].batch_norm != 0;
+    std::string n = "fc" + std::to_string(i + 1);
+    f.p_w = add_param(c, n + ".weight", (int64_t)f.nout * fin);
+    f.p_b = add_param(c, n + ".bias", f.nout);
+    f.p_bn_w = f.p_bn_b = f.p_bn_mean = f.p_bn_var = -1;
+    if (f.bn) {
+      f.p_bn_w = add_param(c, n + ".bn_weight", f.nout);
+      f.p_bn_b = add_param(c, n + ".bn_bias", f.nout);
+      f.p_bn_mean = add_param(c, n + ".bn_mean", f.nout);
+      f.p_bn_var = add_param(c, n + ".bn_var", f.nout);
+    }
+    f.p_prelu = add_param(c, n + ".prelu", 1);
+    c->fcs.push_back(f);
+    fin = f.nout;
+  }
+  c->p_reg_w = add_param(c, "reg.weight", 4 * (int64_t)fin);
+  c->p_reg_b = add_param(c, "reg.bias", 4);
+  c->p_cls_w = add_param(c, "cls.weight", (int64_t)(class_count + 1) * fin);
+  c->p_cls_b = add_param(c, "cls.bias", class_count + 1);
+
+  // Localizer layer lists (Localizer.lua:8-38): convs and max-pools in forward order
+  auto trunk_layers = [&](int upto) {
+    std::vector<std::array<int, 6>> L;
+    for (int b = 0; b < upto; ++b) {
+      for (int s = 0; s < blocks[b].conv_steps; ++s)
+        L.push_back({blocks[b].kW, blocks[b].kH, 1, 1, blocks[b].padW, blocks[b].padH});
+      L.push_back({2, 2, 2, 2, 0, 0});
+    }
+    return L;
+  };
+  c->loc.clear();
+  for (int h = 0; h < n_heads; ++h) {
+    auto L = trunk_layers(heads[h].input);
+    L.push_back({heads[h].kW, heads[h].kW, 1, 1, 0, 0});
+    L.push_back({1, 1, 1, 1, 0, 0});
+    c->loc.push_back(L);
+  }
+  c->loc.push_back(trunk_layers(n_blocks));
+  FRCNN_REQUIRE((int)c->loc.back().size() <= MAX_LOC_LAYERS, FRCNN_E_INVALID, "too many layers for the ROI localizer");
+  c->roi_loc.n = (int)c->loc.back().size();
+  for (int i = 0; i < c->roi_loc.n; ++i)
+    for (int e = 0; e < 6; ++e) c->roi_loc.l[i][e] = c->loc.back()[i][e];
+  build_luts(c);
+  c->bound.assign(c->params.size(), nullptr);
+  c->planned = true;
+}
+
+static const float* P(frcnn_ctx* c, int idx) { return idx >= 0 ? c->bound[idx] : nullptr; }
+
+#define REQUIRE_DEVICE(c) FRCNN_REQUIRE((c)->device >= 0, FRCNN_E_CUDA, "host-only context: no CUDA device (there is no CPU fallback)")
+
+static void do_pack(frcnn_ctx* c) {
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(c->planned, FRCNN_E_STATE, "frcnn_model_plan must be called first");
+  for (auto p : c->bound) FRCNN_REQUIRE(p != nullptr, FRCNN_E_STATE, "frcnn_bind_params must be called before packing");
+  auto alloc_w = [&](size_t elems) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, elems * sizeof(bf16));
+    if (e != cudaSuccess) throw Error{FRCNN_E_NOMEM, "cudaMalloc(packed weights) failed"};
+    return (bf16*)p;
+  };
+  for (auto& cv : c->trunk) {
+    if (cv.first) {
+      FRCNN_REQUIRE(cv.cin * cv.k * cv.k <= 64, FRCNN_E_INVALID, "first-layer im2col K exceeds 64");
+      if (!cv.w_packed) cv.w_packed = alloc_w((size_t)cv.cout * 64);
+      launch_pack_first_conv_weight(P(c, cv.p_w), cv.w_packed, cv.cout, cv.cin, cv.k, cv.k, c->stream);
+    } else {
+      if (!cv.w_packed) cv.w_packed = alloc_w((size_t)cv.cout * cv.cin * cv.k * cv.k);
+      launch_pack_conv_weight(P(c, cv.p_w), cv.w_packed, cv.cout, cv.cin, cv.k, cv.k, c->stream);
+    }
+    ++c->launches;
+  }
+  for (auto& h : c->heads) {
+    auto& cv = h.conv;
+    if (!cv.w_packed) cv.w_packed = alloc_w((size_t)cv.cout * cv.cin * cv.k * cv.k);
+    launch_pack_conv_weight(P(c, cv.p_w), cv.w_packed, cv.cout, cv.cin, cv.k, cv.k, c->stream);
+    ++c->launches;
+  }
+  for (size_t i = 0; i < c->fcs.size(); ++i) {
+    auto& f = c->fcs[i];
+    if (!f.w_packed) f.w_packed = alloc_w((size_t)f.nout * f.nin);
+    if (i == 0) launch_pack_fc_weight(P(c, f.p_w), f.w_packed, f.nout, c->feat_c, c->roi_kh * c->roi_kw, 1, c->stream);
+    else launch_pack_fc_weight(P(c, f.p_w), f.w_packed, f.nout, f.nin, 1, 0, c->stream);
+    ++c->launches;
+  }
+  if (!c->d_w_lut) {
+    FRCNN_CUDA_TRY(cudaMalloc(&c->d_w_lut, c->w_lut.size() * sizeof(float)));
+    FRCNN_CUDA_TRY(cudaMalloc(&c->d_h_lut, c->h_lut.size() * sizeof(float)));
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_w_lut, c->w_lut.data(), c->w_lut.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_h_lut, c->h_lut.data(), c->h_lut.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  }
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));  // the LUT host vectors / caller buffers may change afterwards
+  c->packed = true;
+}
+
+// (re)builds the activation workspace and the prepared conv launches for an (N, H, W) input
+static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
+  if (c->ws_n == N && c->ws_h == H && c->ws_w == W) return;
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  free_all(c->ws_allocs);
+  c->ws_n = c->ws_h = c->ws_w = 0;
+  const int nb = (int)c->blocks.size();
+  c->pool_out.assign(nb, nullptr);
+  c->pool_h.assign(nb, 0);
+  c->pool_w.assign(nb, 0);
+  c->patches = (bf16*)dev_alloc(c->ws_allocs, (size_t)N * H * W * 64 * sizeof(bf16));
+  int h = H, w = W;
+  bf16* cur = nullptr;
+  size_t li = 0;
+  for (int b = 0; b < nb; ++b) {
+    for (int s = 0; s < c->blocks[b].conv_steps; ++s, ++li) {
+      ConvLayer& cv = c->trunk[li];
+      cv.hin = h; cv.win = w;
+      cv.hout = h + 2 * cv.pad - cv.k + 1;
+      cv.wout = w + 2 * cv.pad - cv.k + 1;
+      cv.out = (bf16*)dev_alloc(c->ws_allocs, (size_t)N * cv.hout * cv.wout * cv.cout * sizeof(bf16));
+      if (cv.first) {
+        cv.in = c->patches;
+        conv_prepare(&cv.launch, c->patches, cv.w_packed, N, cv.hout, cv.wout, 64, cv.cout, 1, 1, 0, 0, EPI_BF16_NHWC,
+                     c->sm_count, 0, 0);
+      } else {
+        cv.in = cur;
+        conv_prepare(&cv.launch, cur, cv.w_packed, N, h, w, cv.cin, cv.cout, cv.k, cv.k, cv.pad, cv.pad, EPI_BF16_NHWC,
+                     c->sm_count, 0, 0);
+      }
+      cv.launch.p.out_bf16 = cv.out;
+      cv.launch.p.scale = cv.scale;
+      cur = cv.out;
+      h = cv.hout; w = cv.wout;
+    }
+    const int ph = (h + 1) / 2, pw = (w + 1) / 2;  // :ceil() pooling (model_utilities.lua:23)
+    c->pool_out[b] = (bf16*)dev_alloc(c->ws_allocs, (size_t)N * ph * pw * c->blocks[b].filters * sizeof(bf16));
+    c->pool_h[b] = ph; c->pool_w[b] = pw;
+    cur = c->pool_out[b];
+    h = ph; w = pw;
+  }
+  c->feat_h = h; c->feat_w = w;
+  for (auto& hd : c->heads) {
+    const int ih = c->pool_h[hd.input - 1], iw = c->pool_w[hd.input - 1];
+    FRCNN_REQUIRE(ih >= hd.kW && iw >= hd.kW, FRCNN_E_INVALID, "image too small for the anchor networks");
+    hd.hh = ih - hd.kW + 1; hd.hw = iw - hd.kW + 1;
+    FRCNN_REQUIRE(hd.hh <= LUT_EXTENT && hd.hw <= LUT_EXTENT, FRCNN_E_INVALID,
+                  "feature map exceeds the 200-cell anchor LUT (Anchors.lua:15)");
+    hd.acc = (float*)dev_alloc(c->ws_allocs, (size_t)N * hd.hh * hd.hw * hd.n * sizeof(float));
+    hd.out = (float*)dev_alloc(c->ws_allocs, (size_t)N * 18 * hd.hh * hd.hw * sizeof(float));
+    hd.conv.hin = ih; hd.conv.win = iw; hd.conv.hout = hd.hh; hd.conv.wout = hd.hw;
+    conv_prepare(&hd.conv.launch, c->pool_out[hd.input - 1], hd.conv.w_packed, N, ih, iw, hd.conv.cin, hd.conv.cout, hd.kW,
+                 hd.kW, 0, 0, EPI_F32_ATOMIC, c->sm_count, 0, 0);
+    hd.conv.launch.p.out_f32 = hd.acc;
+  }
+  c->ws_n = N; c->ws_h = H; c->ws_w = W;
+}
+
+static void run_conv(frcnn_ctx* c, ConvLayer& cv) {
+  cv.launch.p.bias = P(c, cv.p_b);
+  cv.launch.p.prelu = P(c, cv.p_prelu);
+  conv_launch(cv.launch, c->stream);
+  ++c->launches;
+}
+
+static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, int W) {
+  FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called before the forward pass");
+  FRCNN_REQUIRE(N >= 1 && H >= 16 && W >= 16, FRCNN_E_INVALID, "bad input size");
+  ensure_pnet_workspace(c, N, H, W);
+  size_t li = 0;
+  int h = H, w = W;
+  for (size_t b = 0; b < c->blocks.size(); ++b) {
+    for (int s = 0; s < c->blocks[b].conv_steps; ++s, ++li) {
+      ConvLayer& cv = c->trunk[li];
+      if (cv.first) {
+        launch_im2col_first(img_dev, c->patches, N, cv.cin, H, W, cv.k, cv.k, cv.pad, cv.pad, c->stream);
+        ++c->launches;
+      }
+      run_conv(c, cv);
+      h = cv.hout; w = cv.wout;
+    }
+    launch_maxpool2x2(c->trunk[li - 1].out, c->pool_out[b], N, h, w, c->blocks[b].filters, c->stream);
+    ++c->launches;
+    h = c->pool_h[b]; w = c->pool_w[b];
+    for (auto& hd : c->heads) {
+      if (hd.input != (int)b + 1) continue;
+      FRCNN_CUDA_TRY(cudaMemsetAsync(hd.acc, 0, (size_t)N * hd.hh * hd.hw * hd.n * sizeof(float), c->stream));
+      hd.conv.launch.p.bias = nullptr;
+      hd.conv.launch.p.prelu = nullptr;
+      conv_launch(hd.conv.launch, c->stream);
+      launch_head_tail(hd.acc, P(c, hd.conv.p_b), P(c, hd.conv.p_prelu), P(c, hd.p_w2), P(c, hd.p_b2), hd.out, N, hd.hh, hd.hw,
+                       hd.n, 18, c->stream);
+      c->launches += 2;
+    }
+  }
+  FRCNN_CUDA_TRY(cudaGetLastError());
+}
+
+// detector / cnet workspace for a batch of N images
+static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
+  int want_rows = std::max(N * c->cand_cap, min_rows);
+  if (c->det_n >= N && c->roi_cap >= want_rows) return;
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  free_all(c->det_allocs);
+  if (c->nms_mem) { cudaFree(c->nms_mem); c->nms_mem = nullptr; }
+  c->det_n = 0;
+  auto& A = c->det_allocs;
+  const int cap = c->cand_cap;
+  const size_t NC = (size_t)N * cap;
+  c->cand_r = (double*)dev_alloc(A, NC * 4 * sizeof(double));
+  c->cand_box = (float4*)dev_alloc(A, NC * sizeof(float4));
+  c->cand_logp = (float*)dev_alloc(A, NC * sizeof(float));
+  c->cand_anchor = (int4*)dev_alloc(A, NC * sizeof(int4));
+  c->cand_count = (int*)dev_alloc(A, N * sizeof(int));
+  c->flags = (int*)dev_alloc(A, 16 * sizeof(int));
+  c->ticket = (int*)dev_alloc(A, N * sizeof(int));
+  c->status_blocks = 4096;
+  c->status = (unsigned long long*)dev_alloc(A, (size_t)N * c->status_blocks * sizeof(unsigned long long));
+  FRCNN_CUDA_TRY(cudaMemsetAsync(c->ticket, 0, N * sizeof(int), c->stream));
+  FRCNN_CUDA_TRY(cudaMemsetAsync(c->status, 0, (size_t)N * c->status_blocks * sizeof(unsigned long long), c->stream));
+  FRCNN_CUDA_TRY(cudaMemsetAsync(c->flags, 0, 16 * sizeof(int), c->stream));
+  c->epoch = 0;
+  c->pick1 = (int*)dev_alloc(A, NC * sizeof(int));
+  c->count1 = (int*)dev_alloc(A, N * sizeof(int));
+  c->roi_base = (int*)dev_alloc(A, N * sizeof(int));
+  const int R = want_rows;
+  const int bins = c->roi_kh * c->roi_kw;
+  c->roi_out = (bf16*)dev_alloc(A, (size_t)R * bins * c->feat_c * sizeof(bf16));
+  c->roi_img = (int*)dev_alloc(A, (size_t)R * sizeof(int));
+  c->roi_cand = (int*)dev_alloc(A, (size_t)R * sizeof(int));
+  const int ncls = c->class_count + 1;
+  c->reg_out = (float*)dev_alloc(A, (size_t)R * 4 * sizeof(float));
+  c->cls_out = (float*)dev_alloc(A, (size_t)R * ncls * sizeof(float));
+  c->fin_r2 = (double*)dev_alloc(A, (size_t)R * 4 * sizeof(double));
+  c->fin_box = (float4*)dev_alloc(A, (size_t)R * sizeof(float4));
+  c->fin_cls = (int*)dev_alloc(A, (size_t)R * sizeof(int));
+  c->fin_conf = (float*)dev_alloc(A, (size_t)R * sizeof(float));
+  c->gbox = (float4*)dev_alloc(A, NC * sizeof(float4));
+  c->grow = (int*)dev_alloc(A, NC * sizeof(int));
+  c->n_pass = (int*)dev_alloc(A, N * sizeof(int));
+  c->det_cap = (int)NC;
+  c->det_dev = (frcnn_detection*)dev_alloc(A, (size_t)c->det_cap * sizeof(frcnn_detection));
+  // cnet layers: GEMM rows = R
+  const bf16* in = c->roi_out;
+  for (size_t i = 0; i < c->fcs.size(); ++i) {
+    FcLayer& f = c->fcs[i];
+    f.acc = (float*)dev_alloc(A, (size_t)R * f.nout * sizeof(float));
+    const bool last = i + 1 == c->fcs.size();
+    f.out_bf16 = last ? nullptr : (bf16*)dev_alloc(A, (size_t)R * f.nout * sizeof(bf16));
+    f.out_f32 = last ? (float*)dev_alloc(A, (size_t)R * f.nout * sizeof(float)) : nullptr;
+    // split-K sized for the detector's typical few hundred ROIs: 8 K-iterations per split
+    int k_iters = f.nin / 64;
+    int splits = std::max(1, k_iters / 8);
+    conv_prepare(&f.launch, in, f.w_packed, 1, 1, R, f.nin, f.nout, 1, 1, 0, 0, EPI_F32_ATOMIC, c->sm_count, splits, 0);
+    f.launch.p.out_f32 = f.acc;
+    f.launch.p.m_limit = c->flags + 2;  // roi_total
+    in = f.out_bf16;
+  }
+  // NMS workspace: segments = max(N images, N * classes)
+  c->nms_cap_total = (int)NC;
+  c->nms_cap_seg = N * std::max(1, c->class_count);
+  c->nms_bytes = nms_workspace_bytes(c->nms_cap_total, c->nms_cap_seg);
+  FRCNN_CUDA_TRY(cudaMalloc(&c->nms_mem, c->nms_bytes));
+  nms_workspace_init(&c->nms, c->nms_mem, c->nms_bytes, c->nms_cap_total, c->nms_cap_seg);
+  if (!c->h_ints) FRCNN_CUDA_TRY(cudaMallocHost(&c->h_ints, 64 * sizeof(int)));
+  if (c->h_det_cap < c->det_cap) {
+    if (c->h_det) cudaFreeHost(c->h_det);
+    FRCNN_CUDA_TRY(cudaMallocHost(&c->h_det, (size_t)c->det_cap * sizeof(frcnn_detection)));
+    c->h_det_cap = c->det_cap;
+  }
+  c->det_n = N;
+  c->roi_cap = R;
+}
+
+// cnet on rows [0, *roi_total) of roi_out (bf16, [bins][C] order)
+static void run_cnet(frcnn_ctx* c, int rows_max) {
+  for (size_t i = 0; i < c->fcs.size(); ++i) {
+    FcLayer& f = c->fcs[i];
+    FRCNN_CUDA_TRY(cudaMemsetAsync(f.acc, 0, (size_t)rows_max * f.nout * sizeof(float), c->stream));
+    conv_launch(f.launch, c->stream);
+    launch_fc_tail(f.acc, P(c, f.p_b), P(c, f.p_bn_w), P(c, f.p_bn_b), P(c, f.p_bn_mean), P(c, f.p_bn_var), P(c, f.p_prelu),
+                   f.out_bf16, f.out_f32, rows_max, c->flags + 2, f.nout, c->stream);
+    c->launches += 2;
+  }
+  const FcLayer& last = c->fcs.back();
+  launch_cnet_out(last.out_f32, P(c, c->p_reg_w), P(c, c->p_reg_b), P(c, c->p_cls_w), P(c, c->p_cls_b), c->reg_out, c->cls_out,
+                  rows_max, c->flags + 2, last.nout, c->class_count + 1, c->stream);
+  ++c->launches;
+  FRCNN_CUDA_TRY(cudaGetLastError());
+}
+
+static void run_decode(frcnn_ctx* c, const float* const* heads_dev, int N, int H, int W, double threshold) {
+  DecodeParams p;
+  int off = 0;
+  for (int i = 0; i < MAX_HEADS; ++i) {
+    p.head[i] = heads_dev[i];
+    p.hh[i] = c->heads[i].hh;
+    p.hw[i] = c->heads[i].hw;
+    p.offs[i] = off;
+    off += p.hh[i] * p.hw[i] * 3;
+  }
+  p.offs[MAX_HEADS] = off;
+  p.total = off;
+  p.w_lut = c->d_w_lut;
+  p.h_lut = c->d_h_lut;
+  p.img_w = W; p.img_h = H; p.threshold = threshold;
+  p.cap = c->cand_cap;
+  p.cand_r = c->cand_r; p.cand_box = c->cand_box; p.cand_logp = c->cand_logp; p.cand_anchor = c->cand_anchor;
+  p.cand_count = c->cand_count;
+  p.cand_overflow = c->flags + 0;
+  p.ticket = c->ticket;
+  p.status = c->status;
+  p.nblocks = (off + 255) / 256;
+  FRCNN_REQUIRE(p.nblocks <= c->status_blocks, FRCNN_E_INVALID, "too many anchors for the decode scan state");
+  // status words are laid out with the per-image stride nblocks; epoch tags make stale words harmless
+  p.epoch = ++c->epoch;
+  launch_rpn_decode(p, N, c->stream);
+  ++c->launches;
+}
+
+static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, frcnn_detection* det_host, int cap, int* n_det) {
+  FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called before detect");
+  FRCNN_REQUIRE(det_host != nullptr && n_det != nullptr && cap >= 0, FRCNN_E_INVALID, "bad output buffer");
+  ensure_pnet_workspace(c, N, H, W);
+  ensure_det_workspace(c, N, 0);
+  cudaStream_t st = c->stream;
+  const bool prof = c->profiling;
+  if (prof) for (int i = 0; i < 7; ++i) if (!c->ev[i]) FRCNN_CUDA_TRY(cudaEventCreate(&c->ev[i]));
+  if (prof) cudaEventRecord(c->ev[0], st);
+  do_pnet_forward(c, img_dev, N, H, W);
+  if (prof) cudaEventRecord(c->ev[1], st);
+  // --- Detector.lua:36-66
+  const float* heads_dev[MAX_HEADS];
+  for (int i = 0; i < MAX_HEADS; ++i) heads_dev[i] = c->heads[i].out;
+  run_decode(c, heads_dev, N, H, W, c->thr_fg);
+  // --- Detector.lua:68-85: nms(bb, 0.25, score) -- the score tensor is ignored, order key = y2 (nms.lua:41-42)
+  nms_set_segments_from_counts(&c->nms, c->cand_count, N, c->cand_cap, st);
+  c->launches += 1 + nms_run(&c->nms, reinterpret_cast<const float*>(c->cand_box), 4, N, N * c->cand_cap, c->cand_cap, c->thr_nms1,
+                             FRCNN_NMS_ORDER_Y2, 0, st, nullptr);
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->pick1, c->nms.st.pick, (size_t)N * c->cand_cap * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->count1, c->nms.st.counts, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (prof) cudaEventRecord(c->ev[2], st);
+  // --- Detector.lua:91-98: ROI pooling of every candidate
+  launch_roi_base(c->count1, N, c->roi_base, c->flags + 2, c->roi_cap, st);
+  RoiParams rp;
+  rp.fmap = c->pool_out.back(); rp.FH = c->feat_h; rp.FW = c->feat_w; rp.C = c->feat_c; rp.kh = c->roi_kh; rp.kw = c->roi_kw;
+  rp.loc = c->roi_loc;
+  rp.cand_r = c->cand_r; rp.pick = c->pick1; rp.pick_count = c->count1; rp.roi_base = c->roi_base; rp.cap = c->cand_cap;
+  rp.out = c->roi_out; rp.roi_img = c->roi_img; rp.roi_cand = c->roi_cand; rp.status = c->flags + 1;
+  launch_roi_pool_nhwc(rp, N, st);
+  c->launches += 2;
+  if (prof) cudaEventRecord(c->ev[3], st);
+  // --- Detector.lua:101: cnet
+  run_cnet(c, c->roi_cap);
+  if (prof) cudaEventRecord(c->ev[4], st);
+  // --- Detector.lua:106-122
+  FinalizeParams fp;
+  fp.cand_r = c->cand_r; fp.cand_logp = c->cand_logp; fp.cand_anchor = c->cand_anchor; fp.cap = c->cand_cap;
+  fp.roi_img = c->roi_img; fp.roi_cand = c->roi_cand; fp.roi_total = c->flags + 2; fp.reg = c->reg_out; fp.cls = c->cls_out;
+  fp.ncls = c->class_count + 1; fp.class_prob = c->thr_class;
+  fp.fin_r2 = c->fin_r2; fp.fin_box = c->fin_box; fp.fin_cls = c->fin_cls; fp.fin_conf = c->fin_conf;
+  launch_finalize(fp, c->roi_cap, st);
+  GroupParams gp;
+  gp.roi_base = c->roi_base; gp.pick_count = c->count1; gp.fin_cls = c->fin_cls; gp.fin_box = c->fin_box;
+  gp.cap = c->cand_cap; gp.n_classes = c->class_count; gp.gbox = c->gbox; gp.grow = c->grow; gp.n_pass = c->n_pass;
+  launch_group_by_class(gp, &c->nms, N, st);
+  c->launches += 2;
+  // --- Detector.lua:125-136: per-class nms(bb, 0.1, bb[{{},5}]) -- order key again y2
+  const int n_seg = N * c->class_count;
+  c->launches += nms_run(&c->nms, reinterpret_cast<const float*>(c->gbox), 4, n_seg, N * c->cand_cap, c->cand_cap, c->thr_nms2,
+                         FRCNN_NMS_ORDER_Y2, 0, st, nullptr);
+  AssembleParams ap;
+  ap.grow = c->grow; ap.cand_r = c->cand_r; ap.cand_logp = c->cand_logp; ap.cand_anchor = c->cand_anchor;
+  ap.roi_img = c->roi_img; ap.roi_cand = c->roi_cand; ap.fin_r2 = c->fin_r2; ap.fin_cls = c->fin_cls; ap.fin_conf = c->fin_conf;
+  ap.cap = c->cand_cap; ap.n_classes = c->class_count; ap.det = c->det_dev; ap.det_cap = c->det_cap; ap.n_det = c->flags + 3;
+  launch_assemble(ap, &c->nms, n_seg, st);
+  ++c->launches;
+  if (prof) cudaEventRecord(c->ev[5], st);
+  // --- results to the host: flags + per-image counts, then the winners
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_ints, c->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  const int NS = std::min(N, 16);
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_ints + 4, c->cand_count, NS * sizeof(int), cudaMemcpyDeviceToHost, st));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_ints + 20, c->n_pass, NS * sizeof(int), cudaMemcpyDeviceToHost, st));
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
+  const int overflow = c->h_ints[0], degenerate = c->h_ints[1], roi_total = c->h_ints[2], ndet = c->h_ints[3];
+  if (overflow || degenerate) FRCNN_CUDA_TRY(cudaMemsetAsync(c->flags, 0, 2 * sizeof(int), st));
+  c->stats[0] = c->stats[2] = 0;
+  for (int i = 0; i < NS; ++i) { c->stats[0] += c->h_ints[4 + i]; c->stats[2] += c->h_ints[20 + i]; }
+  c->stats[1] = roi_total;
+  c->stats[3] = ndet;
+  if (prof) {
+    for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&c->timings[i], c->ev[i], c->ev[i + 1]);
+    cudaEventElapsedTime(&c->timings[5], c->ev[0], c->ev[5]);
+  }
+  FRCNN_REQUIRE(!overflow, FRCNN_E_OVERFLOW, "more RPN matches than the candidate capacity (" + std::to_string(c->cand_cap) + " per image)");
+  FRCNN_REQUIRE(!degenerate, FRCNN_E_ROI_EMPTY,
+                "an ROI clipped to max == 0; the reference raises an index error here (objective.lua:11)");
+  const int ncopy = std::min(ndet, std::min(cap, c->det_cap));
+  if (ncopy > 0) {
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_det, c->det_dev, (size_t)ncopy * sizeof(frcnn_detection), cudaMemcpyDeviceToHost, st));
+    FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(det_host, c->h_det, (size_t)ncopy * sizeof(frcnn_detection));
+  }
+  *n_det = ncopy;
+  FRCNN_REQUIRE(ndet <= cap, FRCNN_E_OVERFLOW, "more winners than the output capacity");
+}
+
+}  // namespace frcnn
+
+// =============================================================================================== C ABI
+#define API_BEGIN(ctx)                                                     \
+  if (!(ctx)) {                                                            \
+    frcnn::set_global_error("null ctx");                                   \
+    return FRCNN_E_INVALID;                                                \
+  }                                                                        \
+  try {                                                                    \
+    if ((ctx)->device >= 0) {                                              \
+      cudaError_t _sd = cudaSetDevice((ctx)->device);                      \
+      if (_sd != cudaSuccess) throw frcnn::Error{FRCNN_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(_sd)}; \
+    }
+
+#define API_END(ctx)                                  \
+    return FRCNN_OK;                                  \
+  } catch (const frcnn::Error& e) {                   \
+    (ctx)->err = e.msg;                               \
+    return e.code;                                    \
+  } catch (const std::exception& e) {                 \
+    (ctx)->err = e.what();                            \
+    return FRCNN_E_INVALID;                           \
+  } catch (...) {                                     \
+    (ctx)->err = "unknown error";                     \
+    return FRCNN_E_INVALID;                           \
+  }
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int frcnn_version(void) { return 100; }
+
+int frcnn_create(frcnn_ctx** out, int device, void* stream) {
+  if (!out) return FRCNN_E_INVALID;
+  *out = nullptr;
+  if (device == -1) {  // host-only context: model plan + Localizer / Anchors geometry, no compute entry point works
+    frcnn_ctx* c = new frcnn_ctx();
+    c->device = -1;
+    *out = c;
+    return FRCNN_OK;
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    frcnn::set_global_error(std::string("no CUDA device available: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                            " (this library has no CPU fallback)");
+    cudaGetLastError();
+    return FRCNN_E_CUDA;
+  }
+  if (device < 0 || device >= count) {
+    frcnn::set_global_error("device index out of range");
+    return FRCNN_E_INVALID;
+  }
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) {
+    frcnn::set_global_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return FRCNN_E_CUDA;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    frcnn::set_global_error(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    return FRCNN_E_CUDA;
+  }
+  if (prop.major != 10) {
+    frcnn::set_global_error("this library is built for sm_100a (B200) only; found compute capability " + std::to_string(prop.major) +
+                            "." + std::to_string(prop.minor));
+    return FRCNN_E_CUDA;
+  }
+  frcnn_ctx* c = new frcnn_ctx();
+  c->device = device;
+  c->stream = (cudaStream_t)stream;
+  c->sm_count = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  *out = c;
+  return FRCNN_OK;
+}
+
+int frcnn_destroy(frcnn_ctx* c) {
+  if (!c) return FRCNN_E_INVALID;
+  if (c->device < 0) {
+    delete c;
+    return FRCNN_OK;
+  }
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  frcnn::free_all(c->ws_allocs);
+  frcnn::free_all(c->det_allocs);
+  if (c->nms_mem) cudaFree(c->nms_mem);
+  for (auto& cv : c->trunk) if (cv.w_packed) cudaFree(cv.w_packed);
+  for (auto& h : c->heads) if (h.conv.w_packed) cudaFree(h.conv.w_packed);
+  for (auto& f : c->fcs) if (f.w_packed) cudaFree(f.w_packed);
+  if (c->d_w_lut) cudaFree(c->d_w_lut);
+  if (c->d_h_lut) cudaFree(c->d_h_lut);
+  if (c->scratch) cudaFree(c->scratch);
+  if (c->d_img) cudaFree(c->d_img);
+  if (c->h_ints) cudaFreeHost(c->h_ints);
+  if (c->h_det) cudaFreeHost(c->h_det);
+  if (c->h_img) cudaFreeHost(c->h_img);
+  for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  delete c;
+  return FRCNN_OK;
+}
+
+const char* frcnn_last_error(const frcnn_ctx* c) { return c ? c->err.c_str() : frcnn::g_last_error.c_str(); }
+
+int frcnn_device_info(frcnn_ctx* c, int* sm_count, int* cc_major, int* cc_minor) {
+  API_BEGIN(c)
+  if (sm_count) *sm_count = c->sm_count;
+  if (cc_major) *cc_major = c->cc_major;
+  if (cc_minor) *cc_minor = c->cc_minor;
+  API_END(c)
+}
+
+int64_t frcnn_launch_count(const frcnn_ctx* c) { return c ? c->launches : 0; }
+
+int frcnn_model_plan(frcnn_ctx* c, const frcnn_block_desc* blocks, int n_blocks, const frcnn_head_desc* heads, int n_heads,
+                     const frcnn_fc_desc* fcs, int n_fcs, int class_count, int roi_kh, int roi_kw, const double* scales,
+                     int n_scales, float dropout_eval_scale) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(blocks && heads && fcs && scales, FRCNN_E_INVALID, "null model description");
+  frcnn::do_plan(c, blocks, n_blocks, heads, n_heads, fcs, n_fcs, class_count, roi_kh, roi_kw, scales, n_scales, dropout_eval_scale);
+  API_END(c)
+}
+
+int frcnn_param_count(const frcnn_ctx* c) { return c ? (int)c->params.size() : 0; }
+
+int frcnn_param_info(const frcnn_ctx* c, int index, char* name, int name_cap, int64_t* numel) {
+  if (!c || index < 0 || index >= (int)c->params.size()) return FRCNN_E_INVALID;
+  if (name && name_cap > 0) {
+    strncpy(name, c->params[index].name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (numel) *numel = c->params[index].numel;
+  return FRCNN_OK;
+}
+
+int frcnn_bind_params(frcnn_ctx* c, const float* const* params_dev, int n) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(c->planned, FRCNN_E_STATE, "frcnn_model_plan must be called first");
+  FRCNN_REQUIRE(params_dev && n == (int)c->params.size(), FRCNN_E_INVALID,
+                "expected " + std::to_string(c->params.size()) + " parameter pointers");
+  for (int i = 0; i < n; ++i) {
+    FRCNN_REQUIRE(params_dev[i] != nullptr, FRCNN_E_INVALID, "null parameter pointer: " + c->params[i].name);
+    c->bound[i] = params_dev[i];
+  }
+  c->packed = false;
+  API_END(c)
+}
+
+int frcnn_pack_weights(frcnn_ctx* c) {
+  API_BEGIN(c)
+  frcnn::do_pack(c);
+  API_END(c)
+}
+
+int frcnn_localizer_layers(const frcnn_ctx* cc, int which, int* layers6, int cap_layers, int* n_layers) {
+  frcnn_ctx* c = const_cast<frcnn_ctx*>(cc);
+  if (!c) return FRCNN_E_INVALID;
+  try {
+    FRCNN_REQUIRE(c->planned && which >= 0 && which < (int)c->loc.size(), FRCNN_E_INVALID, "bad localizer index");
+    const auto& L = c->loc[which];
+    FRCNN_REQUIRE(n_layers != nullptr, FRCNN_E_INVALID, "null n_layers");
+    *n_layers = (int)L.size();
+    if (layers6) {
+      FRCNN_REQUIRE(cap_layers >= (int)L.size(), FRCNN_E_INVALID, "layer buffer too small");
+      for (size_t i = 0; i < L.size(); ++i)
+        for (int e = 0; e < 6; ++e) layers6[i * 6 + e] = L[i][e];
+    }
+    return FRCNN_OK;
+  } catch (const frcnn::Error& e) {
+    c->err = e.msg;
+    return e.code;
+  }
+}
+
+int frcnn_input_to_feature_rect(const frcnn_ctx* cc, int which, const double rect[4], double out[4]) {
+  frcnn_ctx* c = const_cast<frcnn_ctx*>(cc);
+  if (!c || !c->planned || which < 0 || which >= (int)c->loc.size() || !rect || !out) return FRCNN_E_INVALID;
+  frcnn::input_to_feature(c->loc[which], rect, out);
+  return FRCNN_OK;
+}
+
+int frcnn_feature_to_input_rect(const frcnn_ctx* cc, int which, const double rect[4], double out[4]) {
+  frcnn_ctx* c = const_cast<frcnn_ctx*>(cc);
+  if (!c || !c->planned || which < 0 || which >= (int)c->loc.size() || !rect || !out) return FRCNN_E_INVALID;
+  frcnn::feature_to_input(c->loc[which], rect, out);
+  return FRCNN_OK;
+}
+
+int frcnn_anchors_build(frcnn_ctx* c, float* w_lut_host, float* h_lut_host) {
+  if (!c || !c->planned || !w_lut_host || !h_lut_host) return FRCNN_E_INVALID;
+  memcpy(w_lut_host, c->w_lut.data(), c->w_lut.size() * sizeof(float));
+  memcpy(h_lut_host, c->h_lut.data(), c->h_lut.size() * sizeof(float));
+  return FRCNN_OK;
+}
+
+int frcnn_pnet_output_dims(const frcnn_ctx* cc, int h, int w, int* dims3) {
+  frcnn_ctx* c = const_cast<frcnn_ctx*>(cc);
+  if (!c || !c->planned || !dims3) return FRCNN_E_INVALID;
+  std::vector<int> ph, pw;
+  int ch = h, cw = w;
+  for (auto& b : c->blocks) {
+    for (int s = 0; s < b.conv_steps; ++s) {
+      ch = ch + 2 * b.padH - b.kH + 1;
+      cw = cw + 2 * b.padW - b.kW + 1;
+    }
+    ch = (ch + 1) / 2;
+    cw = (cw + 1) / 2;
+    ph.push_back(ch);
+    pw.push_back(cw);
+  }
+  for (size_t i = 0; i < c->heads.size(); ++i) {
+    dims3[i * 3 + 0] = 18;
+    dims3[i * 3 + 1] = ph[c->heads[i].input - 1] - c->heads[i].kW + 1;
+    dims3[i * 3 + 2] = pw[c->heads[i].input - 1] - c->heads[i].kW + 1;
+  }
+  dims3[c->heads.size() * 3 + 0] = c->feat_c;
+  dims3[c->heads.size() * 3 + 1] = ch;
+  dims3[c->heads.size() * 3 + 2] = cw;
+  return FRCNN_OK;
+}
+
+int frcnn_pnet_forward(frcnn_ctx* c, const float* img_dev, int n, int h, int w, float* const* out_dev) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(img_dev != nullptr, FRCNN_E_INVALID, "null image");
+  frcnn::do_pnet_forward(c, img_dev, n, h, w);
+  if (out_dev) {
+    for (size_t i = 0; i < c->heads.size(); ++i)
+      if (out_dev[i])
+        FRCNN_CUDA_TRY(cudaMemcpyAsync(out_dev[i], c->heads[i].out, (size_t)n * 18 * c->heads[i].hh * c->heads[i].hw * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, c->stream));
+    if (out_dev[c->heads.size()]) {
+      frcnn::launch_nhwc_bf16_to_chw_f32(c->pool_out.back(), out_dev[c->heads.size()], n, c->feat_h, c->feat_w, c->feat_c, c->stream);
+      ++c->launches;
+    }
+  }
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  API_END(c)
+}
+
+int frcnn_rpn_decode(frcnn_ctx* c, const float* const* heads_dev, int h, int w, double threshold, frcnn_candidate* cand_host, int cap,
+                     int* n_cand) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called first (uploads the anchor LUTs)");
+  FRCNN_REQUIRE(heads_dev && cand_host && n_cand, FRCNN_E_INVALID, "null argument");
+  // head sizes follow from the image size
+  std::vector<int> dims((c->heads.size() + 1) * 3);
+  frcnn_pnet_output_dims(c, h, w, dims.data());
+  for (size_t i = 0; i < c->heads.size(); ++i) {
+    c->heads[i].hh = dims[i * 3 + 1];
+    c->heads[i].hw = dims[i * 3 + 2];
+    FRCNN_REQUIRE(c->heads[i].hh <= frcnn::LUT_EXTENT && c->heads[i].hw <= frcnn::LUT_EXTENT, FRCNN_E_INVALID,
+                  "feature map exceeds the 200-cell anchor LUT (Anchors.lua:15)");
+  }
+  if (c->ws_h != h || c->ws_w != w) c->ws_n = 0;  // head sizes were overwritten: force a workspace rebuild later
+  frcnn::ensure_det_workspace(c, 1, 0);
+  frcnn::run_decode(c, heads_dev, 1, h, w, threshold);
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_ints, c->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_ints + 4, c->cand_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  const int overflow = c->h_ints[0];
+  const int n = c->h_ints[4];
+  if (overflow) FRCNN_CUDA_TRY(cudaMemsetAsync(c->flags, 0, sizeof(int), c->stream));
+  FRCNN_REQUIRE(!overflow, FRCNN_E_OVERFLOW, "more RPN matches than the candidate capacity");
+  FRCNN_REQUIRE(n <= cap, FRCNN_E_OVERFLOW, "more RPN matches than the output capacity");
+  std::vector<double> r((size_t)n * 4);
+  std::vector<float> box((size_t)n * 4), lp(n);
+  std::vector<int> an((size_t)n * 4);
+  if (n > 0) {
+    FRCNN_CUDA_TRY(cudaMemcpy(r.data(), c->cand_r, r.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    FRCNN_CUDA_TRY(cudaMemcpy(box.data(), c->cand_box, box.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    FRCNN_CUDA_TRY(cudaMemcpy(lp.data(), c->cand_logp, lp.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    FRCNN_CUDA_TRY(cudaMemcpy(an.data(), c->cand_anchor, an.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  for (int i = 0; i < n; ++i) {
+    frcnn_candidate& o = cand_host[i];
+    for (int e = 0; e < 4; ++e) { o.r[e] = r[i * 4 + e]; o.box[e] = box[i * 4 + e]; }
+    o.logp = lp[i];
+    o.layer = an[i * 4]; o.aspect = an[i * 4 + 1]; o.y = an[i * 4 + 2]; o.x = an[i * 4 + 3];
+    o.pad_ = 0;
+  }
+  *n_cand = n;
+  API_END(c)
+}
+
+static void nms_dev_impl(frcnn_ctx* c, const float* boxes_dev, int64_t n_total, int64_t row_stride, const int64_t* seg_offsets_host,
+                         int n_seg, float overlap, int order_mode, int order_col, int64_t* pick_dev, int64_t* counts_dev) {
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(n_total >= 0 && n_total < (1ll << 31) && n_seg >= 1 && row_stride >= 4, FRCNN_E_INVALID, "bad NMS sizes");
+  FRCNN_REQUIRE(order_mode >= 0 && order_mode <= 2 && (order_mode != FRCNN_NMS_ORDER_COLUMN || (order_col >= 0 && order_col < row_stride)),
+                FRCNN_E_INVALID, "bad NMS order mode");
+  // a private workspace sized for this call (kept until a larger one is needed)
+  std::vector<int> beg(n_seg), len(n_seg);
+  int max_len = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    int64_t a = seg_offsets_host ? seg_offsets_host[s] : 0, b = seg_offsets_host ? seg_offsets_host[s + 1] : n_total;
+    FRCNN_REQUIRE(a >= 0 && b >= a && b <= n_total, FRCNN_E_INVALID, "bad segment offsets");
+    beg[s] = (int)a;
+    len[s] = (int)(b - a);
+    max_len = std::max(max_len, len[s]);
+  }
+  if (n_total == 0 || max_len == 0) {
+    FRCNN_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, n_seg * sizeof(int64_t), c->stream));
+    return;
+  }
+  const int cap_total = (int)n_total, cap_seg = n_seg;
+  size_t need = frcnn::nms_workspace_bytes(cap_total, cap_seg);
+  void* mem = frcnn::ensure_scratch(c, need);
+  frcnn::NmsWorkspace ws;
+  frcnn::nms_workspace_init(&ws, mem, need, cap_total, cap_seg);
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(ws.st.seg_beg, beg.data(), n_seg * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(ws.st.seg_len, len.data(), n_seg * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));  // beg/len are stack vectors
+  if (!c->h_ints) FRCNN_CUDA_TRY(cudaMallocHost(&c->h_ints, 64 * sizeof(int)));
+  int* h_rem = max_len > 8192 ? c->h_ints + 40 : nullptr;
+  c->launches += frcnn::nms_run(&ws, boxes_dev, (int)row_stride, n_seg, cap_total, max_len, overlap, order_mode, order_col, c->stream, h_rem);
+  frcnn::nms_export(&ws, n_seg, max_len, pick_dev, counts_dev, c->stream);
+  ++c->launches;
+  FRCNN_CUDA_TRY(cudaGetLastError());
+}
+
+int frcnn_nms_segmented_dev(frcnn_ctx* c, const float* boxes_dev, int64_t n_total, int64_t row_stride, const int64_t* seg_offsets_host,
+                            int n_seg, float overlap, int order_mode, int order_col, int64_t* pick_dev, int64_t* counts_dev) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(boxes_dev && seg_offsets_host && pick_dev && counts_dev, FRCNN_E_INVALID, "null argument");
+  nms_dev_impl(c, boxes_dev, n_total, row_stride, seg_offsets_host, n_seg, overlap, order_mode, order_col, pick_dev, counts_dev);
+  API_END(c)
+}
+
+int frcnn_nms_dev(frcnn_ctx* c, const float* boxes_dev, int64_t n, int64_t row_stride, float overlap, int order_mode, int order_col,
+                  int64_t* pick_dev, int64_t* n_pick_dev) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(pick_dev && n_pick_dev && (boxes_dev || n == 0), FRCNN_E_INVALID, "null argument");
+  nms_dev_impl(c, boxes_dev, n, row_stride, nullptr, 1, overlap, order_mode, order_col, pick_dev, n_pick_dev);
+  API_END(c)
+}
+
+int frcnn_nms_segmented(frcnn_ctx* c, const float* boxes_host, int64_t row_stride, const int64_t* seg_offsets_host, int n_seg,
+                        float overlap, int order_mode, int order_col, int64_t* pick_host, int64_t* counts_host) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(seg_offsets_host && pick_host && counts_host && n_seg >= 1, FRCNN_E_INVALID, "null argument");
+  const int64_t n = seg_offsets_host[n_seg];
+  FRCNN_REQUIRE(n >= 0 && (boxes_host || n == 0), FRCNN_E_INVALID, "null boxes");
+  if (n == 0) {
+    for (int s = 0; s < n_seg; ++s) counts_host[s] = 0;
+    return FRCNN_OK;
+  }
+  // staging buffers: boxes | picks | counts
+  std::vector<void*> tmp;
+  struct Guard { std::vector<void*>& v; ~Guard() { for (void* p : v) cudaFree(p); } } guard{tmp};
+  float* d_boxes = (float*)frcnn::dev_alloc(tmp, (size_t)n * row_stride * sizeof(float));
+  int64_t* d_pick = (int64_t*)frcnn::dev_alloc(tmp, (size_t)n * sizeof(int64_t));
+  int64_t* d_counts = (int64_t*)frcnn::dev_alloc(tmp, (size_t)n_seg * sizeof(int64_t));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(d_boxes, boxes_host, (size_t)n * row_stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  nms_dev_impl(c, d_boxes, n, row_stride, seg_offsets_host, n_seg, overlap, order_mode, order_col, d_pick, d_counts);
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(counts_host, d_counts, n_seg * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(pick_host, d_pick, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  API_END(c)
+}
+
+int frcnn_nms(frcnn_ctx* c, const float* boxes_host, int64_t n, int64_t row_stride, float overlap, int order_mode, int order_col,
+              int64_t* pick_host, int64_t* n_pick) {
+  if (!n_pick) return FRCNN_E_INVALID;
+  if (n == 0) {  // nms.lua:26-28
+    *n_pick = 0;
+    return FRCNN_OK;
+  }
+  int64_t seg[2] = {0, n};
+  return frcnn_nms_segmented(c, boxes_host, row_stride, seg, 1, overlap, order_mode, order_col, pick_host, n_pick);
+}
+
+int frcnn_roi_pool_forward(frcnn_ctx* c, const float* fmap_dev, int C, int H, int W, const double* rects_host, int R, float* out_dev,
+                           int32_t* argmax_dev) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(c->planned, FRCNN_E_STATE, "frcnn_model_plan must be called first");
+  FRCNN_REQUIRE(fmap_dev && rects_host && out_dev && R >= 0, FRCNN_E_INVALID, "null argument");
+  if (R == 0) return FRCNN_OK;
+  uint8_t* mem = (uint8_t*)frcnn::ensure_scratch(c, (size_t)R * 4 * sizeof(double) + 256);
+  int* status = (int*)mem;
+  double* rects_dev = (double*)(mem + 256);
+  FRCNN_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int), c->stream));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(rects_dev, rects_host, (size_t)R * 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  frcnn::launch_roi_pool_chw(fmap_dev, C, H, W, c->roi_loc, rects_dev, R, c->roi_kh, c->roi_kw, out_dev, argmax_dev, status, c->stream);
+  ++c->launches;
+  int h_status = 0;
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(&h_status, status, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  FRCNN_REQUIRE(h_status == 0, FRCNN_E_ROI_EMPTY, "an ROI clipped to max == 0; the reference raises an index error here (objective.lua:11)");
+  API_END(c)
+}
+
+int frcnn_cnet_forward(frcnn_ctx* c, const float* x_dev, int R, float* reg_dev, float* cls_dev) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called first");
+  FRCNN_REQUIRE(x_dev && reg_dev && cls_dev && R >= 0, FRCNN_E_INVALID, "null argument");
+  if (R == 0) return FRCNN_OK;
+  frcnn::ensure_det_workspace(c, 1, R);
+  const int bins = c->roi_kh * c->roi_kw;
+  long total = (long)R * bins * c->feat_c;
+  int blocks = (int)std::min<long>((total + 255) / 256, 148 * 16);
+  frcnn::pack_roi_rows_kernel<<<blocks, 256, 0, c->stream>>>(x_dev, c->roi_out, R, c->feat_c, bins);
+  frcnn::set_int_kernel<<<1, 1, 0, c->stream>>>(c->flags + 2, R);
+  c->launches += 2;
+  frcnn::run_cnet(c, R);
+  const int ncls = c->class_count + 1;
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(reg_dev, c->reg_out, (size_t)R * 4 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(cls_dev, c->cls_out, (size_t)R * ncls * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  API_END(c)
+}
+
+int frcnn_detect_dev(frcnn_ctx* c, const float* img_dev, int n, int h, int w, frcnn_detection* det_host, int cap, int* n_det) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(img_dev != nullptr, FRCNN_E_INVALID, "null image");
+  frcnn::do_detect(c, img_dev, n, h, w, det_host, cap, n_det);
+  API_END(c)
+}
+
+int frcnn_detect(frcnn_ctx* c, const float* img_host, int n, int h, int w, frcnn_detection* det_host, int cap, int* n_det) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(img_host != nullptr && n >= 1 && h >= 1 && w >= 1, FRCNN_E_INVALID, "null image");
+  const size_t bytes = (size_t)n * 3 * h * w * sizeof(float);
+  if (bytes > c->d_img_bytes) {
+    FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->d_img) cudaFree(c->d_img);
+    if (c->h_img) cudaFreeHost(c->h_img);
+    c->d_img = nullptr; c->h_img = nullptr; c->d_img_bytes = 0;
+    FRCNN_CUDA_TRY(cudaMalloc(&c->d_img, bytes));
+    FRCNN_CUDA_TRY(cudaMallocHost(&c->h_img, bytes));
+    c->d_img_bytes = bytes;
+  }
+  // Input:cuda() (Detector.lua:32): stage through pinned memory so the copy is a true async DMA
+  memcpy(c->h_img, img_host, bytes);
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_img, c->h_img, bytes, cudaMemcpyHostToDevice, c->stream));
+  frcnn::do_detect(c, c->d_img, n, h, w, det_host, cap, n_det);
+  API_END(c)
+}
+
+int frcnn_detect_stats(const frcnn_ctx* c, int64_t stats[4]) {
+  if (!c || !stats) return FRCNN_E_INVALID;
+  for (int i = 0; i < 4; ++i) stats[i] = c->stats[i];
+  return FRCNN_OK;
+}
+
+int frcnn_set_detect_thresholds(frcnn_ctx* c, double fg_prob, float nms_proposals, double class_prob, float nms_classes) {
+  if (!c) return FRCNN_E_INVALID;
+  c->thr_fg = fg_prob; c->thr_nms1 = nms_proposals; c->thr_class = class_prob; c->thr_nms2 = nms_classes;
+  return FRCNN_OK;
+}
+
+int frcnn_set_profiling(frcnn_ctx* c, int enable) {
+  if (!c) return FRCNN_E_INVALID;
+  c->profiling = enable != 0;
+  return FRCNN_OK;
+}
+
+int frcnn_last_timings(const frcnn_ctx* c, float ms[6]) {
+  if (!c || !ms) return FRCNN_E_INVALID;
+  for (int i = 0; i < 6; ++i) ms[i] = c->timings[i];
+  return FRCNN_OK;
+}
+
+int frcnn_conv_bf16(frcnn_ctx* c, const uint16_t* x_dev, const float* w_dev, const float* bias_dev, const float* prelu_dev, float scale,
+                    int n, int h, int w, int cin, int cout, int k, int pad, int splits, int bn, uint16_t* out_dev, int iters,
+                    float* elapsed_ms) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(x_dev && w_dev && out_dev, FRCNN_E_INVALID, "null argument");
+  FRCNN_REQUIRE(bn == 0 || bn == 64 || bn == 128 || bn == 192 || bn == 256, FRCNN_E_INVALID, "bn must be 0, 64, 128, 192 or 256");
+  const int ho = h + 2 * pad - k + 1, wo = w + 2 * pad - k + 1;
+  FRCNN_REQUIRE(ho > 0 && wo > 0, FRCNN_E_INVALID, "input smaller than the kernel");
+  const size_t wbytes = ((size_t)cout * cin * k * k * sizeof(frcnn::bf16) + 255) & ~size_t(255);
+  const size_t abytes = (size_t)n * ho * wo * cout * sizeof(float);
+  uint8_t* mem = (uint8_t*)frcnn::ensure_scratch(c, wbytes + abytes + 256);
+  frcnn::bf16* wp = (frcnn::bf16*)mem;
+  float* acc = (float*)(mem + wbytes);
+  frcnn::launch_pack_conv_weight(w_dev, wp, cout, cin, k, k, c->stream);
+  frcnn::ConvLaunch L;
+  const bool split = splits > 1;
+  frcnn::conv_prepare(&L, (const frcnn::bf16*)x_dev, wp, n, h, w, cin, cout, k, k, pad, pad, split ? frcnn::EPI_F32_ATOMIC : frcnn::EPI_BF16_NHWC,
+                      c->sm_count, split ? splits : 0, bn);
+  L.p.bias = split ? nullptr : bias_dev;
+  L.p.prelu = split ? nullptr : prelu_dev;
+  L.p.scale = scale;
+  L.p.out_bf16 = (frcnn::bf16*)out_dev;
+  L.p.out_f32 = acc;
+  if (iters < 1) iters = 1;
+  cudaEvent_t e0, e1;
+  FRCNN_CUDA_TRY(cudaEventCreate(&e0));
+  FRCNN_CUDA_TRY(cudaEventCreate(&e1));
+  if (split) FRCNN_CUDA_TRY(cudaMemsetAsync(acc, 0, abytes, c->stream));
+  FRCNN_CUDA_TRY(cudaEventRecord(e0, c->stream));
+  for (int i = 0; i < iters; ++i) {
+    frcnn::conv_launch(L, c->stream);
+    ++c->launches;
+  }
+  FRCNN_CUDA_TRY(cudaEventRecord(e1, c->stream));
+  if (split) {
+    if (iters > 1) {  // the timing loop accumulated `iters` times: redo once for the result
+      FRCNN_CUDA_TRY(cudaMemsetAsync(acc, 0, abytes, c->stream));
+      frcnn::conv_launch(L, c->stream);
+    }
+    long total = (long)n * ho * wo * cout;
+    int blocks = (int)std::min<long>((total + 255) / 256, 148 * 16);
+    frcnn::acc_tail_kernel<<<blocks, 256, 0, c->stream>>>(acc, bias_dev, prelu_dev, scale, (frcnn::bf16*)out_dev, total, cout);
+  }
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (elapsed_ms) FRCNN_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  API_END(c)
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

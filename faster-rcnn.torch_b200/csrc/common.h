@@ -1,0 +1,102 @@
+// Shared declarations of the B200-native Faster R-CNN hot-path library (internal; the public surface is
+// include/frcnn_b200.h).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/frcnn_b200.h"
+
+namespace frcnn {
+
+typedef __nv_bfloat16 bf16;
+
+struct Error {
+  int code;
+  std::string msg;
+};
+
+void set_global_error(const std::string& msg);
+
+#define FRCNN_CUDA_TRY(expr)                                                                            \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      throw ::frcnn::Error{FRCNN_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e) + " at " + \
+                                             __FILE__ + ":" + std::to_string(__LINE__)};                \
+    }                                                                                                   \
+  } while (0)
+
+#define FRCNN_REQUIRE(cond, code, text)                   \
+  do {                                                    \
+    if (!(cond)) throw ::frcnn::Error{(code), (text)};    \
+  } while (0)
+
+// ------------------------------------------------------------------ conv / GEMM kernel interface
+enum ConvEpilogue {
+  EPI_BF16_NHWC = 0,   // y = prelu(acc + bias) * scale  -> bf16 NHWC
+  EPI_F32_ATOMIC = 1,  // split-K partial sums, red.global.add.f32 into a zeroed fp32 [pixels][Cout] workspace
+};
+
+struct ConvParams {
+  int N, Hin, Win, Cin;     // input NHWC (Cin % 64 == 0)
+  int Hout, Wout, Cout;     // output
+  int KH, KW, padH, padW;   // stride 1
+  int BW, BH, bw_shift;     // spatial shape of the 128-pixel M tile (BW * BH == 128)
+  int tiles_w, tiles_h;     // ceil(Wout / BW), ceil(Hout / BH)
+  int n_tiles_m, n_tiles_n; // N * tiles_h * tiles_w, ceil(Cout / BN)
+  int cchunks;              // Cin / 64
+  int k_iters;              // KH * KW * cchunks
+  int splits, k_per_split;  // split-K
+  int mode;                 // ConvEpilogue
+  const float* bias;        // [Cout] or null
+  const float* prelu;       // device pointer to the shared slope, or null (identity)
+  float scale;              // post-activation scale (SpatialDropout eval factor), 1 if none
+  bf16* out_bf16;           // EPI_BF16_NHWC
+  float* out_f32;           // EPI_F32_ATOMIC
+  const int* m_limit;       // optional device int: tiles whose first row >= *m_limit are skipped (GEMM rows)
+};
+
+struct TensorMapCache;
+
+struct ConvLaunch {
+  ConvParams p;
+  int BN;
+  CUtensorMap tmA, tmB;
+  int grid;
+};
+
+// Host helpers (conv_igemm.cu)
+void conv_choose_tile(int Hout, int Wout, int* BW, int* BH);
+void make_tmap_act(CUtensorMap* m, const bf16* base, int N, int H, int W, int C, int BW, int BH);
+void make_tmap_weight(CUtensorMap* m, const bf16* base, int Cout, int K, int BN);
+void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
+                  int KH, int KW, int padH, int padW, int mode, int num_sms, int force_splits, int force_bn);
+void conv_launch(const ConvLaunch& L, cudaStream_t st);
+int conv_smem_bytes(int BN);
+
+// ------------------------------------------------------------------ element kernels (elementwise.cu)
+void launch_pack_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st);
+void launch_pack_first_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st);
+void launch_pack_fc_weight(const float* w, bf16* out, int nout, int C, int bins, int permute, cudaStream_t st);
+void launch_im2col_first(const float* img, bf16* patches, int N, int C, int H, int W, int KH, int KW, int padH,
+                         int padW, cudaStream_t st);
+void launch_maxpool2x2(const bf16* in, bf16* out, int N, int H, int W, int C, cudaStream_t st);
+void launch_head_tail(const float* acc, const float* bias, const float* prelu, const float* w2, const float* b2,
+                      float* out_chw, int N, int H, int W, int Cmid, int Cout2, cudaStream_t st);
+void launch_nhwc_bf16_to_chw_f32(const bf16* in, float* out, int N, int H, int W, int C, cudaStream_t st);
+void launch_chw_f32_to_nhwc_bf16(const float* in, bf16* out, int N, int H, int W, int C, cudaStream_t st);
+void launch_fc_tail(const float* acc, const float* bias, const float* bn_w, const float* bn_b, const float* bn_mean,
+                    const float* bn_var, const float* prelu, bf16* out_bf16, float* out_f32, int rows_max,
+                    const int* rows_dev, int n, cudaStream_t st);
+void launch_cnet_out(const float* hidden, const float* w_reg, const float* b_reg, const float* w_cls,
+                     const float* b_cls, float* reg_out, float* cls_out, int rows_max, const int* rows_dev, int nin,
+                     int ncls, cudaStream_t st);
+
+}  // namespace frcnn

@@ -1,0 +1,168 @@
+"""Host mirror of models/model_utilities.lua, models/vgg_small.lua, models/vgg_large.lua and config/*.lua:
+the same description tables, turned into a plan of the CUDA library (frcnn_model_plan) instead of nn modules.
+
+The returned `Model` plays the role of the reference's model table {cfg, layers, pnet, cnet}
+(model_utilities.lua:128-134): `model.pnet.forward(img)` and `model.cnet.forward(x)` keep the Lua call shapes."""
+import math
+
+import numpy as np
+import torch
+
+from ._lib import check, ffi, lib
+
+# config/duplo.lua, config/imagenet.lua (the parameters the detection path reads)
+duplo_cfg = dict(class_count=16, target_smaller_side=450, scales=[32, 64, 128, 256], max_pixel_size=1000,
+                 roi_pooling=dict(kw=6, kh=6), batch_size=256, positive_threshold=0.5, negative_threshold=0.25,
+                 best_match=True, nearby_aversion=True)
+imgnet_cfg = dict(class_count=200, target_smaller_side=480, scales=[48, 96, 192, 384], max_pixel_size=1000,
+                  roi_pooling=dict(kw=6, kh=6), batch_size=300, positive_threshold=0.6, negative_threshold=0.25,
+                  best_match=True, nearby_aversion=True)
+
+
+class _Net:
+    """Stands in for an nn.gModule: forward()/evaluate()/training() with the reference's call shapes."""
+
+    def __init__(self, fwd):
+        self._fwd = fwd
+        self.train = False
+
+    def forward(self, *a, **k):
+        return self._fwd(*a, **k)
+
+    __call__ = forward
+
+    def evaluate(self):
+        self.train = False
+
+    def training(self):
+        raise NotImplementedError("training-mode forward/backward is not built yet (SURVEY 8a rows P2, O1)")
+
+
+class Model:
+    def __init__(self, cfg, layers, anchor_nets, class_layers, device=0, dropout_eval_scale=-1.0, stream=None):
+        self.cfg, self.layers, self.anchor_nets, self.class_layers = cfg, layers, anchor_nets, class_layers
+        self.host_only = device == -1  # plan + Localizer / Anchors geometry only; no compute entry point works
+        if not self.host_only and not torch.cuda.is_available():
+            # fail loudly: the product has no CPU path
+            raise RuntimeError("frcnn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = None if self.host_only else torch.device("cuda", device)
+        L = lib()
+        pctx = ffi.new("frcnn_ctx**")
+        check(None, L.frcnn_create(pctx, device, ffi.cast("void*", stream or 0)))
+        self.ctx = pctx[0]
+        blocks = ffi.new("frcnn_block_desc[]", len(layers))
+        for i, l in enumerate(layers):
+            blocks[i].filters, blocks[i].kW, blocks[i].kH = l["filters"], l["kW"], l["kH"]
+            blocks[i].padW, blocks[i].padH, blocks[i].conv_steps = l["padW"], l["padH"], l["conv_steps"]
+            blocks[i].dropout = l.get("dropout") or 0.0
+        heads = ffi.new("frcnn_head_desc[]", len(anchor_nets))
+        for i, a in enumerate(anchor_nets):
+            heads[i].kW, heads[i].n, heads[i].input = a["kW"], a["n"], a["input"]
+        fcs = ffi.new("frcnn_fc_desc[]", len(class_layers))
+        for i, l in enumerate(class_layers):
+            fcs[i].n, fcs[i].dropout, fcs[i].batch_norm = l["n"], l.get("dropout") or 0.0, 1 if l.get("batch_norm") else 0
+        scales = ffi.new("double[]", [float(s) for s in cfg["scales"]])
+        check(self.ctx, L.frcnn_model_plan(self.ctx, blocks, len(layers), heads, len(anchor_nets), fcs, len(class_layers),
+                                           cfg["class_count"], cfg["roi_pooling"]["kh"], cfg["roi_pooling"]["kw"], scales,
+                                           len(cfg["scales"]), dropout_eval_scale))
+        self.param_names, self.param_numel = [], []
+        name = ffi.new("char[64]")
+        numel = ffi.new("int64_t*")
+        for i in range(L.frcnn_param_count(self.ctx)):
+            check(self.ctx, L.frcnn_param_info(self.ctx, i, name, 64, numel))
+            self.param_names.append(ffi.string(name).decode())
+            self.param_numel.append(int(numel[0]))
+        self.pnet = _Net(self._pnet_forward)
+        self.cnet = _Net(self._cnet_forward)
+        self.n_heads = len(anchor_nets)
+        if self.host_only:
+            return
+        # one flat fp32 buffer, like nn.Module.flatten (utilities.lua:136-147); params are views into it
+        self.weights = torch.zeros(sum(self.param_numel), dtype=torch.float32, device=self.device)
+        self.params, off = {}, 0
+        for n, k in zip(self.param_names, self.param_numel):
+            self.params[n] = self.weights[off:off + k]
+            off += k
+        ptrs = ffi.new("const float*[]", [ffi.cast("const float*", self.params[n].data_ptr()) for n in self.param_names])
+        check(self.ctx, L.frcnn_bind_params(self.ctx, ptrs, len(self.param_names)))
+
+    def close(self):
+        if getattr(self, "ctx", None) is not None:
+            lib().frcnn_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- parameters -------------------------------------------------------------------------------------------
+    def load_params(self, params):
+        """params: dict name -> array/tensor in Torch layouts (conv [Cout][Cin][kH][kW], linear [out][in])."""
+        for n in self.param_names:
+            v = params[n]
+            v = torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v, dtype=torch.float32)
+            self.params[n].copy_(v.reshape(-1).to(self.device))
+        self.pack_weights()
+
+    def pack_weights(self):
+        """Re-packs the flat fp32 weights into the tensor-core layouts; call after every change of `weights`."""
+        torch.cuda.synchronize(self.device)
+        check(self.ctx, lib().frcnn_pack_weights(self.ctx))
+
+    # -- forward passes ---------------------------------------------------------------------------------------
+    def output_dims(self, h, w):
+        dims = ffi.new("int[]", 3 * (self.n_heads + 1))
+        check(self.ctx, lib().frcnn_pnet_output_dims(self.ctx, h, w, dims))
+        return [tuple(dims[3 * i + j] for j in range(3)) for i in range(self.n_heads + 1)]
+
+    def _pnet_forward(self, img):
+        """pnet:forward(img) (Detector.lua:33): img [3][H][W] (or [N][3][H][W]) fp32 CUDA tensor -> list of the
+        4 anchor-head maps [18][h][w] and the last conv-block map [C][h][w] (leading N if batched)."""
+        batched = img.dim() == 4
+        x = (img if batched else img.unsqueeze(0)).to(self.device, torch.float32).contiguous()
+        n, _, h, w = x.shape
+        outs = [torch.empty((n,) + d, dtype=torch.float32, device=self.device) for d in self.output_dims(h, w)]
+        ptrs = ffi.new("float*[]", [ffi.cast("float*", o.data_ptr()) for o in outs])
+        check(self.ctx, lib().frcnn_pnet_forward(self.ctx, ffi.cast("const float*", x.data_ptr()), n, h, w, ptrs))
+        return outs if batched else [o[0] for o in outs]
+
+    def _cnet_forward(self, x):
+        """cnet:forward(cinput) (Detector.lua:101): x [R][kh*kw*C] fp32 -> (bbox [R][4], log-softmax [R][classes+1])."""
+        x = x.to(self.device, torch.float32).contiguous()
+        R = x.shape[0]
+        reg = torch.empty((R, 4), dtype=torch.float32, device=self.device)
+        cls = torch.empty((R, self.cfg["class_count"] + 1), dtype=torch.float32, device=self.device)
+        check(self.ctx, lib().frcnn_cnet_forward(self.ctx, ffi.cast("const float*", x.data_ptr()), R,
+                                                 ffi.cast("float*", reg.data_ptr()), ffi.cast("float*", cls.data_ptr())))
+        return reg, cls
+
+    def launch_count(self):
+        return int(lib().frcnn_launch_count(self.ctx))
+
+
+def create_model(cfg, layers, anchor_nets, class_layers, **kw):  # model_utilities.lua:126-136
+    return Model(cfg, layers, anchor_nets, class_layers, **kw)
+
+
+def vgg_small(cfg, **kw):  # models/vgg_small.lua:3-25
+    layers = [dict(filters=64, kW=3, kH=3, padW=1, padH=1, dropout=0.0, conv_steps=1),
+              dict(filters=128, kW=3, kH=3, padW=1, padH=1, dropout=0.4, conv_steps=2),
+              dict(filters=256, kW=3, kH=3, padW=1, padH=1, dropout=0.4, conv_steps=2),
+              dict(filters=384, kW=3, kH=3, padW=1, padH=1, dropout=0.4, conv_steps=2)]
+    anchor_nets = [dict(kW=3, n=256, input=3), dict(kW=3, n=256, input=4), dict(kW=5, n=256, input=4),
+                   dict(kW=7, n=256, input=4)]
+    class_layers = [dict(n=1024, dropout=0.5, batch_norm=True), dict(n=512, dropout=0.5)]
+    return create_model(cfg, layers, anchor_nets, class_layers, **kw)
+
+
+def vgg_large(cfg, **kw):  # models/vgg_large.lua:3-25
+    layers = [dict(filters=64, kW=3, kH=3, padW=1, padH=1, dropout=0.0, conv_steps=2),
+              dict(filters=128, kW=3, kH=3, padW=1, padH=1, dropout=0.4, conv_steps=2),
+              dict(filters=256, kW=3, kH=3, padW=1, padH=1, dropout=0.4, conv_steps=3),
+              dict(filters=512, kW=3, kH=3, padW=1, padH=1, dropout=0.4, conv_steps=3)]
+    anchor_nets = [dict(kW=3, n=256, input=3), dict(kW=3, n=256, input=4), dict(kW=5, n=256, input=4),
+                   dict(kW=7, n=256, input=4)]
+    class_layers = [dict(n=1024, dropout=0.5, batch_norm=True), dict(n=512, dropout=0.5)]
+    return create_model(cfg, layers, anchor_nets, class_layers, **kw)

@@ -1,0 +1,189 @@
+/* frcnn_b200.h -- C ABI of the B200-native Faster R-CNN detection hot path.
+ *
+ * Drop-in boundary for andreaskoepf/faster-rcnn.torch.  The reference has no FFI of its own (pure Lua on top
+ * of Torch7 nn/cunn); each entry point below names the reference interface (file:line) it replaces.  The Lua
+ * glue (faster-rcnn.torch_b200/lua/) binds exactly these symbols through LuaJIT FFI; the
+ * Python host mirror binds the same symbols through ctypes.
+ *
+ * The declarations are cdef-clean: after removing lines that start with '#' and the extern "C" braces the file
+ * can be passed verbatim to LuaJIT ffi.cdef / Python cffi.
+ *
+ * Conventions
+ *   - every function returns an int status (FRCNN_OK == 0); the message of the last failure is available from
+ *     frcnn_last_error(ctx) (ctx may be NULL for failures of frcnn_create).  No C++ exception and no exit()
+ *     crosses this boundary.
+ *   - "_dev" pointers are CUDA device pointers borrowed for the duration of the call (Torch / the caller owns
+ *     every tensor); "_host" pointers are ordinary host memory.  Plain pointers and sizes only.
+ *   - all work is enqueued on the stream given to frcnn_create (NULL = legacy default stream, which keeps the
+ *     ordering with surrounding cutorch work).  Entry points that return host data synchronise that stream.
+ *   - a ctx is bound to one device and is not re-entrant.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with FRCNN_E_CUDA.
+ */
+#ifndef FRCNN_B200_H
+#define FRCNN_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct frcnn_ctx frcnn_ctx;
+
+enum {
+  FRCNN_OK = 0,
+  FRCNN_E_INVALID = 1,   /* bad argument */
+  FRCNN_E_CUDA = 2,      /* CUDA runtime / driver failure (including: no device) */
+  FRCNN_E_NOMEM = 3,
+  FRCNN_E_STATE = 4,     /* call order violated (e.g. forward before bind_params) */
+  FRCNN_E_ROI_EMPTY = 5, /* an ROI clipped to max == 0: the reference raises here (objective.lua:11) */
+  FRCNN_E_OVERFLOW = 6,  /* more candidates than the capacity given */
+  FRCNN_E_NCCL = 7
+};
+
+/* nms.lua:37-43 -- what the `scores` argument selects.  A tensor argument falls through to Y2 (sic). */
+enum { FRCNN_NMS_ORDER_Y2 = 0, FRCNN_NMS_ORDER_AREA = 1, FRCNN_NMS_ORDER_COLUMN = 2 };
+
+/* models/vgg_small.lua:5-10 `layers` entries */
+typedef struct frcnn_block_desc {
+  int filters, kW, kH, padW, padH, conv_steps;
+  float dropout;
+} frcnn_block_desc;
+/* models/vgg_small.lua:12-17 `anchor_nets` entries (input is 1-based, as in Lua) */
+typedef struct frcnn_head_desc {
+  int kW, n, input;
+} frcnn_head_desc;
+/* models/vgg_small.lua:19-22 `class_layers` entries */
+typedef struct frcnn_fc_desc {
+  int n;
+  float dropout;
+  int batch_norm;
+} frcnn_fc_desc;
+
+/* One entry of the match list built by Detector.lua:36-66 ({p, a, r, l}) */
+typedef struct frcnn_candidate {
+  double r[4];   /* decoded rect, Lua doubles {minX, minY, maxX, maxY} (Anchors.lua:245-252) */
+  float box[4];  /* r:totensor(), fp32 (Rect.lua:143-145) */
+  float logp;    /* c[1], foreground log-probability (Detector.lua:52) */
+  int layer, aspect, y, x; /* 1-based anchor coordinates (Anchors.lua:60-67) */
+  int pad_;
+} frcnn_candidate;
+
+/* One winner of Detector.lua:140 ({p, a, r, l, r2, class, confidence}) */
+typedef struct frcnn_detection {
+  double r[4];    /* proposal rect */
+  double r2[4];   /* refined rect (Detector.lua:107) */
+  float p;        /* RPN foreground log-probability */
+  float confidence; /* class log-probability (Detector.lua:112) */
+  int cls;        /* 1-based class index (Detector.lua:111) */
+  int layer, aspect, y, x; /* anchor a */
+  int image;      /* 0-based index of the frame inside the batch */
+} frcnn_detection;
+
+/* ---- lifetime -------------------------------------------------------------------------------------------- */
+int frcnn_version(void);
+/* replaces cutorch.setDevice + :cuda() setup (main.lua:52, Detector.lua:13-14).  stream: cudaStream_t or NULL. */
+int frcnn_create(frcnn_ctx** out, int device, void* stream);
+int frcnn_destroy(frcnn_ctx* ctx);
+const char* frcnn_last_error(const frcnn_ctx* ctx);
+int frcnn_device_info(frcnn_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor);
+/* number of kernels this library has launched on ctx so far (bench.py's gpu_launches) */
+int64_t frcnn_launch_count(const frcnn_ctx* ctx);
+
+/* ---- model plan: replaces create_model (models/model_utilities.lua:126-136) -------------------------------- */
+/* dropout_eval_scale < 0 selects the Torch7 SpatialDropout v1 default (1 - p). */
+int frcnn_model_plan(frcnn_ctx* ctx, const frcnn_block_desc* blocks, int n_blocks, const frcnn_head_desc* heads,
+                     int n_heads, const frcnn_fc_desc* fcs, int n_fcs, int class_count, int roi_kh, int roi_kw,
+                     const double* scales, int n_scales, float dropout_eval_scale);
+/* Parameter tensors in bind order.  Shapes are Torch's: conv [Cout][Cin][kH][kW], linear [out][in]. */
+int frcnn_param_count(const frcnn_ctx* ctx);
+int frcnn_param_info(const frcnn_ctx* ctx, int index, char* name, int name_cap, int64_t* numel);
+/* Borrows device pointers into Torch's flat weight buffer (utilities.lua:136-147); fp32. */
+int frcnn_bind_params(frcnn_ctx* ctx, const float* const* params_dev, int n);
+/* Re-packs the bound fp32 weights into the bf16 tensor-core layouts; call after every optimiser step
+ * (main.lua:133) or restore (main.lua:97). */
+int frcnn_pack_weights(frcnn_ctx* ctx);
+
+/* ---- geometry: Localizer.lua / Anchors.lua (host-side, exact double arithmetic) ---------------------------- */
+/* which: 0..n_heads-1 = Localizer.new(pnet.outnode.children[which+1]) (Anchors.lua:11); n_heads = the ROI
+ * localizer (Detector.lua:12, objective.lua:22).  layers6: rows {kW,kH,dW,dH,padW,padH} (Localizer.lua:28-36). */
+int frcnn_localizer_layers(const frcnn_ctx* ctx, int which, int* layers6, int cap_layers, int* n_layers);
+/* Localizer:inputToFeatureRect (Localizer.lua:41-67) */
+int frcnn_input_to_feature_rect(const frcnn_ctx* ctx, int which, const double rect[4], double out[4]);
+/* Localizer:featureToInputRect (Localizer.lua:69-79) */
+int frcnn_feature_to_input_rect(const frcnn_ctx* ctx, int which, const double rect[4], double out[4]);
+/* Anchors.__init LUTs (Anchors.lua:15-57): w_lut/h_lut are [n_scales][3][200][2] fp32 */
+int frcnn_anchors_build(frcnn_ctx* ctx, float* w_lut_host, float* h_lut_host);
+
+/* ---- pnet: replaces pnet:forward (Detector.lua:33, objective.lua:71) --------------------------------------- */
+/* img_dev: [n][3][h][w] fp32.  out_dev[0..n_heads-1]: [n][18][hi][wi] fp32; out_dev[n_heads]: [n][C][hf][wf] fp32
+ * (Torch layouts).  Any out_dev entry may be NULL to skip that export.  Evaluate mode. */
+int frcnn_pnet_forward(frcnn_ctx* ctx, const float* img_dev, int n, int h, int w, float* const* out_dev);
+/* Shapes of the outputs above for an h x w input: dims[i] = {channels, height, width}, i = 0..n_heads */
+int frcnn_pnet_output_dims(const frcnn_ctx* ctx, int h, int w, int* dims3);
+
+/* ---- RPN decode: replaces the per-anchor Lua loop Detector.lua:36-66 ------------------------------------- */
+/* heads_dev[i]: [18][hi][wi] fp32 of ONE image.  Writes the ordered match list (layer, y, x, aspect order) to
+ * cand_host and its length to n_cand.  threshold = 0.95 in the reference (Detector.lua:54). */
+int frcnn_rpn_decode(frcnn_ctx* ctx, const float* const* heads_dev, int h, int w, double threshold,
+                     frcnn_candidate* cand_host, int cap, int* n_cand);
+
+/* ---- NMS: replaces the global nms(boxes, overlap, scores) (nms.lua:23-102) ---------------------------------- */
+/* boxes_host: n rows of row_stride floats {minX,minY,maxX,maxY,...}.  pick_host receives 0-based indices in pick
+ * order (the Lua shim adds 1), n_pick their number.  order_col is 0-based. */
+int frcnn_nms(frcnn_ctx* ctx, const float* boxes_host, int64_t n, int64_t row_stride, float overlap, int order_mode,
+              int order_col, int64_t* pick_host, int64_t* n_pick);
+/* Same on device buffers (boxes_dev fp32 row-major, pick_dev int64[n], n_pick_dev int64[1]). Asynchronous. */
+int frcnn_nms_dev(frcnn_ctx* ctx, const float* boxes_dev, int64_t n, int64_t row_stride, float overlap,
+                  int order_mode, int order_col, int64_t* pick_dev, int64_t* n_pick_dev);
+/* Per-class NMS of Detector.lua:125-136 in one call: segment s is rows seg_offsets[s]..seg_offsets[s+1]-1.
+ * pick (segment-local 0-based indices, pick order) is written at pick[seg_offsets[s]...]; counts[s] = #picks. */
+int frcnn_nms_segmented(frcnn_ctx* ctx, const float* boxes_host, int64_t row_stride, const int64_t* seg_offsets_host,
+                        int n_seg, float overlap, int order_mode, int order_col, int64_t* pick_host,
+                        int64_t* counts_host);
+int frcnn_nms_segmented_dev(frcnn_ctx* ctx, const float* boxes_dev, int64_t n_total, int64_t row_stride,
+                            const int64_t* seg_offsets_host, int n_seg, float overlap, int order_mode, int order_col,
+                            int64_t* pick_dev, int64_t* counts_dev);
+
+/* ---- ROI pooling: replaces extract_roi_pooling_input + nn.SpatialAdaptiveMaxPooling (objective.lua:5-13,30;
+ *      Detector.lua:96-97) ------------------------------------------------------------------------------------ */
+/* fmap_dev: [C][H][W] fp32 (Torch layout); rects_host: R input-space rects (doubles).  out_dev: [R][C*kh*kw] fp32,
+ * element c*kh*kw + by*kw + bx; argmax_dev (optional): flat index y*W + x into the feature plane (0-based). */
+int frcnn_roi_pool_forward(frcnn_ctx* ctx, const float* fmap_dev, int C, int H, int W, const double* rects_host, int R,
+                           float* out_dev, int32_t* argmax_dev);
+
+/* ---- cnet: replaces cnet:forward (Detector.lua:101, objective.lua:164), evaluate mode ---------------------- */
+/* x_dev: [R][kh*kw*C] fp32 (reference ordering).  reg_dev: [R][4]; cls_dev: [R][class_count+1] log-softmax. */
+int frcnn_cnet_forward(frcnn_ctx* ctx, const float* x_dev, int R, float* reg_dev, float* cls_dev);
+
+/* ---- whole pipeline: replaces Detector:detect (Detector.lua:17-141) ------------------------------------- */
+/* img_host: [n][3][h][w] fp32 in host memory (copied to the device inside the call).  det_host receives the
+ * winners of all frames grouped by (image, class ascending) and, inside a class, in pick order. */
+int frcnn_detect(frcnn_ctx* ctx, const float* img_host, int n, int h, int w, frcnn_detection* det_host, int cap,
+                 int* n_det);
+/* Same with the frames already resident in device memory. */
+int frcnn_detect_dev(frcnn_ctx* ctx, const float* img_dev, int n, int h, int w, frcnn_detection* det_host, int cap,
+                     int* n_det);
+/* Stage statistics of the last detect call: {matches, candidates after NMS, classified (non-bg, conf>0.2),
+ * winners} summed over the batch. */
+int frcnn_detect_stats(const frcnn_ctx* ctx, int64_t stats[4]);
+/* Thresholds of Detector.lua:54,81,115,133; defaults 0.95, 0.25, 0.2, 0.1. */
+int frcnn_set_detect_thresholds(frcnn_ctx* ctx, double fg_prob, float nms_proposals, double class_prob,
+                                float nms_classes);
+/* Device-side time of the kernel groups of the last detect call when profiling was enabled with
+ * frcnn_set_profiling(ctx, 1): ms[0]=trunk+heads convs, [1]=decode+nms, [2]=roi pool, [3]=cnet, [4]=final nms,
+ * [5]=total. */
+int frcnn_set_profiling(frcnn_ctx* ctx, int enable);
+int frcnn_last_timings(const frcnn_ctx* ctx, float ms[6]);
+
+/* ---- low-level conv / GEMM entry (tests, roofline measurement) ---------------------------------------- */
+/* y = prelu(conv(x, w) + bias) * scale on NHWC bf16 activations (passed as uint16 bit patterns).
+ * x_dev: [n][h][w][cin]; w_dev: fp32 Torch layout [cout][cin][k][k]; out_dev: [n][ho][wo][cout] bf16.
+ * splits > 1 exercises the split-K fp32-atomic path; bn in {0 (auto), 64, 128, 192, 256}.
+ * elapsed_ms (optional) receives the device time of `iters` back-to-back launches of the conv kernel alone. */
+int frcnn_conv_bf16(frcnn_ctx* ctx, const uint16_t* x_dev, const float* w_dev, const float* bias_dev,
+                    const float* prelu_dev, float scale, int n, int h, int w, int cin, int cout, int k, int pad,
+                    int splits, int bn, uint16_t* out_dev, int iters, float* elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FRCNN_B200_H */
