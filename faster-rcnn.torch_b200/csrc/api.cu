@@ -148,6 +148,13 @@ struct frcnn_ctx {
   bool profiling = false;
   cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float timings[6] = {0, 0, 0, 0, 0, 0};
+  // per-launch timing of the tcgen05 conv/GEMM kernel (profiling mode): event pairs around every launch
+  std::vector<cudaEvent_t> conv_ev;
+  int conv_ev_used = 0;
+  double conv_flops = 0.0;
+  float conv_ms = 0.f;
+  int conv_launches = 0;
+  long prof_rows = 0;  // ROI rows of the previous profiled detect call (FLOP accounting of the cnet GEMMs)
   // scratch for API-level calls
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -484,11 +491,47 @@ static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
   c->ws_n = N; c->ws_h = H; c->ws_w = W;
 }
 
+// Launches the conv/GEMM kernel; in profiling mode brackets it with an event pair and adds its algorithmic FLOPs
+// (2 * M * N * K of the un-padded problem; `rows` overrides M for the m_limit-ed cnet GEMMs).
+static void conv_launch_timed(frcnn_ctx* c, const ConvLaunch& L, long rows = -1) {
+  if (c->profiling) {
+    if ((int)c->conv_ev.size() < c->conv_ev_used + 2) {
+      cudaEvent_t a, b;
+      FRCNN_CUDA_TRY(cudaEventCreate(&a));
+      FRCNN_CUDA_TRY(cudaEventCreate(&b));
+      c->conv_ev.push_back(a);
+      c->conv_ev.push_back(b);
+    }
+    cudaEventRecord(c->conv_ev[c->conv_ev_used], c->stream);
+  }
+  conv_launch(L, c->stream);
+  ++c->launches;
+  if (c->profiling) {
+    cudaEventRecord(c->conv_ev[c->conv_ev_used + 1], c->stream);
+    c->conv_ev_used += 2;
+    const double M = rows >= 0 ? (double)rows : (double)L.p.N * L.p.Hout * L.p.Wout;
+    c->conv_flops += 2.0 * M * L.p.Cout * (double)L.p.KH * L.p.KW * L.p.Cin;
+  }
+}
+static void conv_profile_begin(frcnn_ctx* c) {
+  c->conv_ev_used = 0;
+  c->conv_flops = 0.0;
+}
+// after a stream synchronisation
+static void conv_profile_end(frcnn_ctx* c) {
+  c->conv_ms = 0.f;
+  c->conv_launches = c->conv_ev_used / 2;
+  for (int i = 0; i + 1 < c->conv_ev_used; i += 2) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->conv_ev[i], c->conv_ev[i + 1]);
+    c->conv_ms += ms;
+  }
+}
+
 static void run_conv(frcnn_ctx* c, ConvLayer& cv) {
   cv.launch.p.bias = P(c, cv.p_b);
   cv.launch.p.prelu = P(c, cv.p_prelu);
-  conv_launch(cv.launch, c->stream);
-  ++c->launches;
+  conv_launch_timed(c, cv.launch);
 }
 
 static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, int W) {
@@ -515,10 +558,10 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
       FRCNN_CUDA_TRY(cudaMemsetAsync(hd.acc, 0, (size_t)N * hd.hh * hd.hw * hd.n * sizeof(float), c->stream));
       hd.conv.launch.p.bias = nullptr;
       hd.conv.launch.p.prelu = nullptr;
-      conv_launch(hd.conv.launch, c->stream);
+      conv_launch_timed(c, hd.conv.launch);
       launch_head_tail(hd.acc, P(c, hd.conv.p_b), P(c, hd.conv.p_prelu), P(c, hd.p_w2), P(c, hd.p_b2), hd.out, N, hd.hh, hd.hw,
                        hd.n, 18, c->stream);
-      c->launches += 2;
+      ++c->launches;
     }
   }
   FRCNN_CUDA_TRY(cudaGetLastError());
@@ -605,10 +648,10 @@ static void run_cnet(frcnn_ctx* c, int rows_max) {
   for (size_t i = 0; i < c->fcs.size(); ++i) {
     FcLayer& f = c->fcs[i];
     FRCNN_CUDA_TRY(cudaMemsetAsync(f.acc, 0, (size_t)rows_max * f.nout * sizeof(float), c->stream));
-    conv_launch(f.launch, c->stream);
+    conv_launch_timed(c, f.launch, c->profiling ? c->prof_rows : -1);
     launch_fc_tail(f.acc, P(c, f.p_b), P(c, f.p_bn_w), P(c, f.p_bn_b), P(c, f.p_bn_mean), P(c, f.p_bn_var), P(c, f.p_prelu),
                    f.out_bf16, f.out_f32, rows_max, c->flags + 2, f.nout, c->stream);
-    c->launches += 2;
+    ++c->launches;
   }
   const FcLayer& last = c->fcs.back();
   launch_cnet_out(last.out_f32, P(c, c->p_reg_w), P(c, c->p_reg_b), P(c, c->p_cls_w), P(c, c->p_cls_b), c->reg_out, c->cls_out,
@@ -654,7 +697,10 @@ static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, f
   cudaStream_t st = c->stream;
   const bool prof = c->profiling;
   if (prof) for (int i = 0; i < 7; ++i) if (!c->ev[i]) FRCNN_CUDA_TRY(cudaEventCreate(&c->ev[i]));
-  if (prof) cudaEventRecord(c->ev[0], st);
+  if (prof) {
+    conv_profile_begin(c);
+    cudaEventRecord(c->ev[0], st);
+  }
   do_pnet_forward(c, img_dev, N, H, W);
   if (prof) cudaEventRecord(c->ev[1], st);
   // --- Detector.lua:36-66
@@ -719,6 +765,8 @@ static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, f
   if (prof) {
     for (int i = 0; i < 5; ++i) cudaEventElapsedTime(&c->timings[i], c->ev[i], c->ev[i + 1]);
     cudaEventElapsedTime(&c->timings[5], c->ev[0], c->ev[5]);
+    conv_profile_end(c);
+    c->prof_rows = roi_total;
   }
   FRCNN_REQUIRE(!overflow, FRCNN_E_OVERFLOW, "more RPN matches than the candidate capacity (" + std::to_string(c->cand_cap) + " per image)");
   FRCNN_REQUIRE(!degenerate, FRCNN_E_ROI_EMPTY,
@@ -834,6 +882,7 @@ int frcnn_destroy(frcnn_ctx* c) {
   if (c->h_det) cudaFreeHost(c->h_det);
   if (c->h_img) cudaFreeHost(c->h_img);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+  for (auto& e : c->conv_ev) cudaEventDestroy(e);
   delete c;
   return FRCNN_OK;
 }
@@ -960,6 +1009,7 @@ int frcnn_pnet_output_dims(const frcnn_ctx* cc, int h, int w, int* dims3) {
 int frcnn_pnet_forward(frcnn_ctx* c, const float* img_dev, int n, int h, int w, float* const* out_dev) {
   API_BEGIN(c)
   FRCNN_REQUIRE(img_dev != nullptr, FRCNN_E_INVALID, "null image");
+  frcnn::conv_profile_begin(c);
   frcnn::do_pnet_forward(c, img_dev, n, h, w);
   if (out_dev) {
     for (size_t i = 0; i < c->heads.size(); ++i)
@@ -1036,6 +1086,8 @@ static void nms_dev_impl(frcnn_ctx* c, const float* boxes_dev, int64_t n_total, 
     len[s] = (int)(b - a);
     max_len = std::max(max_len, len[s]);
   }
+  FRCNN_REQUIRE(!seg_offsets_host || (seg_offsets_host[0] == 0 && seg_offsets_host[n_seg] == n_total), FRCNN_E_INVALID,
+                "segment offsets must partition [0, n_total)");
   if (n_total == 0 || max_len == 0) {
     FRCNN_CUDA_TRY(cudaMemsetAsync(counts_dev, 0, n_seg * sizeof(int64_t), c->stream));
     return;
@@ -1134,6 +1186,7 @@ int frcnn_cnet_forward(frcnn_ctx* c, const float* x_dev, int R, float* reg_dev, 
   FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called first");
   FRCNN_REQUIRE(x_dev && reg_dev && cls_dev && R >= 0, FRCNN_E_INVALID, "null argument");
   if (R == 0) return FRCNN_OK;
+  frcnn::conv_profile_begin(c);
   frcnn::ensure_det_workspace(c, 1, R);
   const int bins = c->roi_kh * c->roi_kw;
   long total = (long)R * bins * c->feat_c;
@@ -1196,6 +1249,14 @@ int frcnn_set_profiling(frcnn_ctx* c, int enable) {
 int frcnn_last_timings(const frcnn_ctx* c, float ms[6]) {
   if (!c || !ms) return FRCNN_E_INVALID;
   for (int i = 0; i < 6; ++i) ms[i] = c->timings[i];
+  return FRCNN_OK;
+}
+
+int frcnn_last_conv_profile(const frcnn_ctx* c, float* ms, double* flops, int* launches) {
+  if (!c) return FRCNN_E_INVALID;
+  if (ms) *ms = c->conv_ms;
+  if (flops) *flops = c->conv_flops;
+  if (launches) *launches = c->conv_launches;
   return FRCNN_OK;
 }
 

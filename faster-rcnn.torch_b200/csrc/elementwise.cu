@@ -151,8 +151,12 @@ template <int COUT2>
 __global__ void head_tail_kernel(const float* __restrict__ acc, const float* __restrict__ bias, const float* __restrict__ prelu,
                                  const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ out,
                                  long npix, int HW, int Cmid) {
-  extern __shared__ float sw[];  // [COUT2][Cmid]
+  // parameter pointers are views into Torch's flat weight buffer (utilities.lua:136-147) at arbitrary 4-byte
+  // offsets: read them scalar-wise into shared memory, never with vector loads
+  extern __shared__ float sw[];  // [COUT2][Cmid] weights, then [Cmid] bias
+  float* sbias = sw + COUT2 * Cmid;
   for (int i = threadIdx.x; i < COUT2 * Cmid; i += blockDim.x) sw[i] = w2[i];
+  for (int i = threadIdx.x; i < Cmid; i += blockDim.x) sbias[i] = bias[i];
   __syncthreads();
   const float slope = prelu[0];
   int lane = threadIdx.x & 31;
@@ -164,7 +168,7 @@ __global__ void head_tail_kernel(const float* __restrict__ acc, const float* __r
     for (int o = 0; o < COUT2; ++o) part[o] = 0.f;
     for (int c = lane * 4; c < Cmid; c += 128) {
       float4 a = *reinterpret_cast<const float4*>(acc + pix * Cmid + c);
-      float4 b = *reinterpret_cast<const float4*>(bias + c);
+      float4 b = *reinterpret_cast<const float4*>(sbias + c);
       float h[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) h[e] = h[e] > 0.f ? h[e] : h[e] * slope;
@@ -195,7 +199,7 @@ void launch_head_tail(const float* acc, const float* bias, const float* prelu, c
   FRCNN_REQUIRE(Cout2 == 18, FRCNN_E_INVALID, "anchor head must have 18 outputs (model_utilities.lua:33)");
   FRCNN_REQUIRE(Cmid % 128 == 0, FRCNN_E_INVALID, "anchor head width must be a multiple of 128");
   long npix = (long)N * H * W;
-  int smem = 18 * Cmid * sizeof(float);
+  int smem = 19 * Cmid * sizeof(float);
   int blocks = min(cdiv(npix, 8), 148 * 4);
   head_tail_kernel<18><<<blocks, 256, smem, st>>>(acc, bias, prelu, w2, b2, out_chw, npix, H * W, Cmid);
 }

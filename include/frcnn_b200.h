@@ -173,6 +173,10 @@ int frcnn_set_detect_thresholds(frcnn_ctx* ctx, double fg_prob, float nms_propos
  * [5]=total. */
 int frcnn_set_profiling(frcnn_ctx* ctx, int enable);
 int frcnn_last_timings(const frcnn_ctx* ctx, float ms[6]);
+/* Profiling mode also brackets every launch of the tcgen05 conv/GEMM kernel with a CUDA event pair on the ctx
+ * stream: summed device time, summed algorithmic FLOPs (2*M*N*K of the un-padded problems) and launch count of
+ * the last detect call (bench.py's roofline figure). */
+int frcnn_last_conv_profile(const frcnn_ctx* ctx, float* ms, double* flops, int* launches);
 
 /* ---- low-level conv / GEMM entry (tests, roofline measurement) ---------------------------------------- */
 /* y = prelu(conv(x, w) + bias) * scale on NHWC bf16 activations (passed as uint16 bit patterns).

@@ -63,12 +63,13 @@ def decode(outputs, anchors, input_rect, threshold=0.95):
 
 
 class Detector:
-    def __init__(self, desc, cfg, params, dropout_eval_scale=None, quant=None):  # Detector.lua:8-15
+    def __init__(self, desc, cfg, params, dropout_eval_scale=None, quant=None, quant_heads="same"):  # Detector.lua:8-15
         self.desc, self.cfg, self.p = desc, cfg, params
         self.anchors = Anchors(desc["layers"], desc["anchor_nets"], cfg["scales"])
         self.localizer = Localizer(trunk_layer_info(desc["layers"], len(desc["layers"])))
         self.dropout_eval_scale = dropout_eval_scale
         self.quant = quant
+        self.quant_heads = quant_heads
 
     def detect(self, img, outputs=None, return_intermediates=False):  # Detector.lua:17-141
         cfg = self.cfg
@@ -88,7 +89,7 @@ class Detector:
                 candidates = [matches[i] for i in pick]
                 fmap = outputs[4]
                 cinput = torch.stack([roi_pool(fmap, v["r"], self.localizer, kh, kw)[0] for v in candidates])
-                bbox_out, cls_out = M.cnet_forward(self.desc, self.p, cinput, quant=self.quant)
+                bbox_out, cls_out = M.cnet_forward(self.desc, self.p, cinput, quant=self.quant, quant_heads=self.quant_heads)
                 inter.update(candidates=candidates, cinput=cinput, coutputs=(bbox_out, cls_out), pick=pick)
                 yclass = {}
                 for i, x in enumerate(candidates):  # Detector.lua:106-122

@@ -142,10 +142,12 @@ def pnet_forward(desc, p, img, train=False, dropout_masks=None, dropout_eval_sca
     return outs
 
 
-def cnet_forward(desc, p, x, train=False, dropout_masks=None, quant=None):
+def cnet_forward(desc, p, x, train=False, dropout_masks=None, quant=None, quant_heads="same"):
     """create_classification_net forward (model_utilities.lua:76-108). x: [R][kh*kw*C].
-    Returns (R x 4 bbox, R x (C+1) log-softmax)."""
+    Returns (R x 4 bbox, R x (C+1) log-softmax).  `quant` as in pnet_forward; `quant_heads` overrides it for the
+    two small output Linear layers (the CUDA path keeps those in fp32: pass None)."""
     q = quant or (lambda t: t)
+    qh = q if quant_heads == "same" else (quant_heads or (lambda t: t))
     for li, l in enumerate(desc["class_layers"]):
         n = "fc%d" % (li + 1)
         x = F.linear(q(x), q(p[n + ".weight"]), p[n + ".bias"])
@@ -158,8 +160,8 @@ def cnet_forward(desc, p, x, train=False, dropout_masks=None, quant=None):
         x = prelu(x, p[n + ".prelu"])
         if train and l.get("dropout"):
             x = x * dropout_masks[n] / (1 - l["dropout"])
-    reg = F.linear(q(x), q(p["reg.weight"]), p["reg.bias"])
-    cls = F.log_softmax(F.linear(q(x), q(p["cls.weight"]), p["cls.bias"]), dim=1)
+    reg = F.linear(qh(x), qh(p["reg.weight"]), p["reg.bias"])
+    cls = F.log_softmax(F.linear(qh(x), qh(p["cls.weight"]), p["cls.bias"]), dim=1)
     return reg, cls
 
 

@@ -1,0 +1,118 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol include/frcnn_b200.h declares,
+its host-side geometry (Localizer / Anchors, exact double math) equals the oracle, and every compute entry point
+fails loudly without a GPU (there is no CPU fallback).  No kernel is launched here."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import anchors as OA, localizer as OL, model as OM
+from oracle.rect import Rect as ORect
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_library_exports_every_declared_symbol(F):
+    names = F.declared_functions()
+    assert len(names) >= 30 and "frcnn_detect" in names and "frcnn_nms" in names
+    path = os.path.join(os.path.dirname(F.__file__), "libfrcnn_b200.so")
+    so = ctypes.CDLL(path)
+    for n in names:
+        assert hasattr(so, n), "library does not export " + n
+    assert F.lib().frcnn_version() == 100
+
+
+def test_header_is_cdef_clean(F):
+    # the header, minus preprocessor lines, is what LuaJIT ffi.cdef / cffi consume verbatim
+    from frcnn_b200._lib import header_cdef
+    src = header_cdef()
+    assert "#" not in src and "extern" not in src
+    for t in ("frcnn_block_desc", "frcnn_head_desc", "frcnn_fc_desc", "frcnn_candidate", "frcnn_detection"):
+        assert t in src
+    assert F.ffi.sizeof("frcnn_candidate") == 72 and F.ffi.sizeof("frcnn_detection") == 96
+
+
+def test_no_cpu_fallback(F):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    ctx = F.ffi.new("frcnn_ctx**")
+    assert F.lib().frcnn_create(ctx, 0, F.ffi.NULL) == 2  # FRCNN_E_CUDA
+    assert b"no CPU fallback" in F.ffi.string(F.lib().frcnn_last_error(F.ffi.NULL))
+    with pytest.raises(RuntimeError):
+        F.vgg_small(F.duplo_cfg)
+    m = F.vgg_small(F.duplo_cfg, device=-1)  # host-only context: geometry works, compute does not
+    b = np.zeros((4, 4), np.float32)
+    with pytest.raises(F.FrcnnError) as e:
+        F.nms(b, 0.5, model=m)
+    assert e.value.code == 2
+    assert F.lib().frcnn_pack_weights(m.ctx) == 2
+
+
+@pytest.mark.parametrize("which", ["small", "large"])
+def test_host_geometry_equals_oracle(F, which):
+    desc, cfg, fac, fcfg = (OM.VGG_SMALL, OM.CFG_DUPLO, F.vgg_small, F.duplo_cfg) if which == "small" else \
+                           (OM.VGG_LARGE, OM.CFG_IMAGENET, F.vgg_large, F.imgnet_cfg)
+    m = fac(fcfg, device=-1)
+    # parameter table = oracle's param_specs (bind order is the flat-buffer order)
+    specs = OM.param_specs(desc, cfg)
+    assert m.param_names == [n for n, _ in specs]
+    assert m.param_numel == [int(np.prod(s)) for _, s in specs]
+    a = F.Anchors(m)
+    oa = OA.Anchors(desc["layers"], desc["anchor_nets"], cfg["scales"])
+    assert np.array_equal(a.w, oa.w) and np.array_equal(a.h, oa.h)  # bit-exact fp32 LUTs
+    for i in range(4):
+        assert a.localizers[i].layers == oa.localizers[i].layers
+    loc = F.Localizer(m, 5)
+    oloc = OL.Localizer(OL.trunk_layer_info(desc["layers"], 4))
+    assert loc.layers == oloc.layers
+    g = np.load(os.path.join(GOLD, "geometry_nms.npz"))
+    want = g["roi_out_small"] if which == "small" else g["roi_out_large"]
+    got = np.array([loc.inputToFeatureRect(F.Rect(*r)).unpack() for r in g["roi_in"]])
+    assert np.array_equal(got, want)
+    rng = np.random.default_rng(1)
+    for _ in range(200):
+        x0, y0 = rng.uniform(-100, 900), rng.uniform(-100, 500)
+        r = (x0, y0, x0 + rng.uniform(0.5, 500), y0 + rng.uniform(0.5, 400))
+        assert loc.inputToFeatureRect(F.Rect(*r)).unpack() == oloc.inputToFeatureRect(ORect(*r)).unpack()
+        q = tuple(float(v) for v in rng.integers(0, 60, 4))
+        assert loc.featureToInputRect(*q).unpack() == oloc.featureToInputRect(*q).unpack()
+    r = a.get(2, 3, 4, 5)
+    o = oa.get(2, 3, 4, 5)
+    assert r.unpack() == o.unpack() and r.index == o.index
+    assert m.output_dims(450, 800)[:2] == ([(18, 55, 98), (18, 27, 48)] if which == "small" else
+                                           [(18, 55, 98), (18, 27, 48)])
+    m.close()
+
+
+def test_pnet_output_dims(F):
+    m = F.vgg_small(F.duplo_cfg, device=-1)
+    assert m.output_dims(450, 800) == [(18, 55, 98), (18, 27, 48), (18, 25, 46), (18, 23, 44), (384, 29, 50)]
+    assert m.output_dims(122, 192) == [(18, 14, 22), (18, 6, 10), (18, 4, 8), (18, 2, 6), (384, 8, 12)]
+    m.close()
+    m = F.vgg_large(F.imgnet_cfg, device=-1)
+    assert m.output_dims(600, 1000) == [(18, 73, 123), (18, 36, 61), (18, 34, 59), (18, 32, 57), (512, 38, 63)]
+    m.close()
+
+
+def test_plan_validation(F):
+    m = F.vgg_small(F.duplo_cfg, device=-1)
+    L, ffi = F.lib(), F.ffi
+    # a second plan on the same ctx is a state error; bad localizer index is invalid
+    scales = ffi.new("double[]", [32., 64., 128., 256.])
+    blocks = ffi.new("frcnn_block_desc[]", 1)
+    heads = ffi.new("frcnn_head_desc[]", 4)
+    fcs = ffi.new("frcnn_fc_desc[]", 1)
+    assert L.frcnn_model_plan(m.ctx, blocks, 1, heads, 4, fcs, 1, 16, 6, 6, scales, 4, -1.0) == 4
+    n = ffi.new("int*")
+    assert L.frcnn_localizer_layers(m.ctx, 9, ffi.NULL, 0, n) == 1
+    m.close()
+
+
+def test_nms_order_dispatch(F):
+    # nms.lua:37-43: number -> column, 'area' -> area, anything else (incl. a score tensor) -> y2
+    from frcnn_b200.nms import _order, ORDER_AREA, ORDER_COLUMN, ORDER_Y2
+    assert _order(5) == (ORDER_COLUMN, 4)
+    assert _order("area") == (ORDER_AREA, 0)
+    assert _order(np.zeros(3)) == (ORDER_Y2, 0) and _order(None) == (ORDER_Y2, 0) and _order("score") == (ORDER_Y2, 0)

@@ -1,0 +1,137 @@
+"""GPU tests of the tcgen05 implicit-GEMM convolution (csrc/conv_igemm.cu) and of pnet:forward built on it.
+
+Floating point: the tensor cores take bf16 operands and accumulate in fp32.  Kernel-level tests compare with a
+PyTorch fp32 convolution of the SAME bf16-rounded operands (difference = accumulation order + one bf16 rounding of
+the output: rtol 1e-2 / atol scaled to the output magnitude).  pnet tests compare with the fp32 oracle, with the
+tolerance stated per test."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as TF
+
+from oracle import model as OM
+
+pytestmark = pytest.mark.gpu
+
+
+def _conv_case(F, model, n, h, w, cin, cout, k, pad, splits=0, bn=0, prelu=True, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    bias = torch.randn(cout, generator=g) * 0.1
+    slope = torch.tensor([0.2])
+    xq, wq = OM.bf16_round(x), OM.bf16_round(wt)
+    ref = TF.conv2d(xq, wq, bias, padding=pad)
+    if prelu:
+        ref = torch.where(ref > 0, ref, ref * slope)
+    ref = ref * scale
+    x_nhwc = xq.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
+    out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device="cuda")
+    wd, bd, sd = wt.cuda(), bias.cuda(), slope.cuda()
+    ffi, L = F.ffi, F.lib()
+    ms = ffi.new("float*")
+    rc = L.frcnn_conv_bf16(model.ctx, ffi.cast("const uint16_t*", x_nhwc.data_ptr()), ffi.cast("const float*", wd.data_ptr()),
+                           ffi.cast("const float*", bd.data_ptr()),
+                           ffi.cast("const float*", sd.data_ptr()) if prelu else ffi.NULL, scale, n, h, w, cin, cout, k, pad,
+                           splits, bn, ffi.cast("uint16_t*", out.data_ptr()), 1, ms)
+    assert rc == 0, ffi.string(L.frcnn_last_error(model.ctx))
+    got = out.float().cpu().permute(0, 3, 1, 2)
+    err = (got - ref).abs()
+    tol = 1e-2 * ref.abs() + 1e-2 * ref.abs().max()
+    assert bool((err <= tol).all()), "max err %g at ref max %g" % (err.max(), ref.abs().max())
+    return got, ref
+
+
+@pytest.mark.parametrize("case", [
+    # n, h, w, cin, cout, k, pad
+    (1, 16, 16, 64, 64, 3, 1), (1, 20, 37, 64, 128, 3, 1), (2, 29, 50, 128, 128, 3, 1), (1, 57, 100, 128, 256, 3, 1),
+    (1, 29, 50, 256, 384, 3, 1), (1, 29, 50, 384, 384, 3, 1), (1, 57, 100, 256, 256, 3, 0), (1, 29, 50, 384, 256, 5, 0),
+    (1, 29, 50, 384, 256, 7, 0), (1, 1, 300, 512, 256, 1, 0), (3, 9, 7, 64, 192, 3, 1), (1, 113, 200, 64, 128, 3, 1),
+])
+def test_conv_shapes(F, small_model, case):
+    _conv_case(F, small_model, *case, seed=sum(case))
+
+
+@pytest.mark.parametrize("bn", [64, 128, 192, 256])
+def test_conv_tile_widths(F, small_model, bn):
+    cout = {64: 64, 128: 256, 192: 384, 256: 512}[bn]
+    _conv_case(F, small_model, 1, 30, 41, 128, cout, 3, 1, bn=bn, seed=bn)
+
+
+@pytest.mark.parametrize("splits", [2, 3, 9])
+def test_conv_split_k(F, small_model, splits):
+    _conv_case(F, small_model, 1, 27, 48, 384, 256, 3, 0, splits=splits, seed=splits)
+
+
+def test_conv_epilogue_variants(F, small_model):
+    _conv_case(F, small_model, 1, 24, 24, 64, 64, 3, 1, prelu=False)
+    _conv_case(F, small_model, 1, 24, 24, 64, 64, 3, 1, scale=0.6)
+
+
+def test_conv_exact_integers(F, small_model):
+    """Small-integer operands are exact in bf16 and in fp32 accumulation: the result must be bit-identical to the
+    reference convolution -- catches any tap / channel / swizzle mis-addressing that tolerances could hide."""
+    g = torch.Generator().manual_seed(1)
+    n, h, w, cin, cout, k, pad = 1, 23, 35, 128, 128, 3, 1
+    x = torch.randint(-2, 3, (n, cin, h, w), generator=g).float()
+    wt = torch.randint(-2, 3, (cout, cin, k, k), generator=g).float()
+    bias = torch.randint(-3, 4, (cout,), generator=g).float()
+    ref = TF.conv2d(x, wt, bias, padding=pad)
+    ref = ref.clamp(-256, 256)  # keep outputs exactly representable in bf16
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
+    out = torch.empty(n, h, w, cout, dtype=torch.bfloat16, device="cuda")
+    wd, bd = wt.cuda(), bias.cuda()
+    ffi, L = F.ffi, F.lib()
+    rc = L.frcnn_conv_bf16(small_model.ctx, ffi.cast("const uint16_t*", x_nhwc.data_ptr()), ffi.cast("const float*", wd.data_ptr()),
+                           ffi.cast("const float*", bd.data_ptr()), ffi.NULL, 1.0, n, h, w, cin, cout, k, pad, 0, 0,
+                           ffi.cast("uint16_t*", out.data_ptr()), 1, ffi.NULL)
+    assert rc == 0
+    got = out.float().cpu().permute(0, 3, 1, 2)
+    mask = (TF.conv2d(x, wt, bias, padding=pad).abs() <= 256)
+    assert torch.equal(got[mask], ref[mask])
+
+
+@pytest.mark.parametrize("h,w", [(122, 192), (450, 800)])
+def test_pnet_forward_vs_oracle(F, small_model, h, w):
+    """pnet:forward (model_utilities.lua:3-58) against the oracle.  Stated tolerance: against the oracle run with
+    bf16-rounded conv operands, 3 % of the per-map max magnitude (bf16 storage of the intermediate activations adds
+    one extra rounding per layer); against the pure fp32 oracle, 6 %."""
+    img = OM.synthetic_frame(h, w, seed=1)
+    outs = small_model.pnet.forward(img.cuda())
+    with torch.no_grad():
+        want_q = OM.pnet_forward(OM.VGG_SMALL, small_model.oracle_params, img, quant=OM.bf16_round)
+        want_f = OM.pnet_forward(OM.VGG_SMALL, small_model.oracle_params, img) if h < 200 else None
+    for i, (o, q) in enumerate(zip(outs, want_q)):
+        assert tuple(o.shape) == tuple(q.shape)
+        scale = q.abs().max().item()
+        assert (o.cpu() - q).abs().max().item() <= 0.03 * scale, "output %d" % i
+        if want_f is not None:
+            assert (o.cpu() - want_f[i]).abs().max().item() <= 0.06 * want_f[i].abs().max().item()
+
+
+def test_pnet_batch_equals_single(F, small_model):
+    """Images of a batch are independent (objective.lua:65): batched forward == per-image forward -- bit for bit on
+    the trunk (deterministic kernels); the anchor-head maps come from split-K fp32 atomics whose summation order
+    is not reproducible, so they agree to fp32 rounding (1e-5 of the map magnitude)."""
+    imgs = torch.stack([OM.synthetic_frame(122, 192, seed=s) for s in range(3)]).cuda()
+    outs = small_model.pnet.forward(imgs)
+    for s in range(3):
+        single = small_model.pnet.forward(imgs[s])
+        assert torch.equal(outs[4][s], single[4])
+        for a, b in zip(outs[:4], single[:4]):
+            assert (a[s] - b).abs().max().item() <= 1e-5 * b.abs().max().item()
+
+
+def test_vgg_large_forward(F):
+    m = F.vgg_large(F.imgnet_cfg)
+    p = OM.init_params(OM.VGG_LARGE, OM.CFG_IMAGENET, seed=2, randomize_aux=True)
+    m.load_params(p)
+    img = OM.synthetic_frame(150, 200, seed=4)
+    outs = m.pnet.forward(img.cuda())
+    with torch.no_grad():
+        want = OM.pnet_forward(OM.VGG_LARGE, p, img, quant=OM.bf16_round)
+    for o, q in zip(outs, want):
+        assert tuple(o.shape) == tuple(q.shape)
+        assert (o.cpu() - q).abs().max().item() <= 0.03 * q.abs().max().item()
+    m.close()
