@@ -1,0 +1,144 @@
+-- frcnn_b200.lua -- LuaJIT-FFI glue between the reference's Lua surface and libfrcnn_b200.so.
+--
+-- NOT RUN IN THIS REPOSITORY'S CI: the build image has no Lua / LuaJIT / Torch7 (SURVEY.md section 0.4).  The file is
+-- the reference-side binding a maintainer adds (INTEGRATION.md); it is kept thin and mechanical: every numeric
+-- step happens inside the C library, whose ABI (include/frcnn_b200.h) is exercised by the Python cffi tests with
+-- the very same cdef text.
+--
+-- Usage (main.lua stays unchanged except for three lines, see INTEGRATION.md):
+--   local b200 = require 'frcnn_b200'
+--   local model = load_model(cfg, opt.model, opt.restore, true)     -- main.lua:80-101, unchanged
+--   b200.accelerate(model)                                          -- binds the flat weights, builds the plan
+--   local d = Detector(model)                                       -- lua/Detector.lua of this directory
+local ffi = require 'ffi'
+local M = {}
+
+-- The header is cdef-clean: strip the preprocessor lines and the extern "C" braces, pass the rest verbatim.
+local function read_header(path)
+  local f = assert(io.open(path, 'r'))
+  local out = {}
+  for line in f:lines() do
+    local s = line:match('^%s*(.-)%s*$')
+    if s:sub(1, 1) ~= '#' and s ~= 'extern "C" {' and s ~= '}' then out[#out + 1] = line end
+  end
+  f:close()
+  return table.concat(out, '\n')
+end
+
+local root = os.getenv('FRCNN_B200_ROOT') or '.'
+ffi.cdef(read_header(root .. '/include/frcnn_b200.h'))
+local C = ffi.load(root .. '/faster-rcnn.torch_b200/libfrcnn_b200.so')
+M.C = C
+
+local function check(ctx, rc)
+  if rc ~= 0 then
+    error(string.format('frcnn_b200 error %d: %s', rc, ffi.string(C.frcnn_last_error(ctx))), 3)
+  end
+end
+M.check = check
+
+-- One context per device (cutorch.setDevice(opt.gpuid + 1), main.lua:52).  stream nil = legacy default stream, which
+-- keeps the ordering with surrounding cutorch work.
+function M.create(device)
+  local p = ffi.new('frcnn_ctx*[1]')
+  check(nil, C.frcnn_create(p, device or (cutorch.getDevice() - 1), nil))
+  return ffi.gc(p[0], C.frcnn_destroy)
+end
+
+-- Walks the nngraph exactly like Localizer.lua:19-24 does: output node -> children[1] -> ... collecting the
+-- nn.Sequential of every conv block (model_utilities.lua:41-49), in forward order.
+local function trunk_blocks(pnet, n_heads)
+  local blocks, node = {}, pnet.outnode.children[n_heads + 1]
+  while node and node.data.module do
+    if torch.typename(node.data.module) == 'nn.Sequential' then table.insert(blocks, 1, node.data.module) end
+    node = node.children[1]
+  end
+  return blocks
+end
+
+local function dev_ptr(t) return ffi.cast('const float*', t:data()) end
+
+-- Builds the plan from the model's own description tables (models/vgg_*.lua) and binds device pointers of the
+-- learnable tensors -- views into the flat CudaTensor created by combine_and_flatten_parameters
+-- (utilities.lua:136-147), so optimiser updates (main.lua:133) are seen after the next M.pack(model).
+function M.accelerate(model, anchor_nets, class_layers)
+  local cfg, layers = model.cfg, model.layers
+  anchor_nets = anchor_nets or model.anchor_nets
+  class_layers = class_layers or model.class_layers
+  assert(anchor_nets and class_layers, 'pass the anchor_nets / class_layers tables of models/vgg_*.lua')
+  local ctx = M.create()
+  local nb, nh, nf = #layers, #anchor_nets, #class_layers
+  local blocks = ffi.new('frcnn_block_desc[?]', nb)
+  for i, l in ipairs(layers) do
+    local b = blocks[i - 1]
+    b.filters, b.kW, b.kH, b.padW, b.padH, b.conv_steps, b.dropout = l.filters, l.kW, l.kH, l.padW, l.padH, l.conv_steps, l.dropout or 0
+  end
+  local heads = ffi.new('frcnn_head_desc[?]', nh)
+  for i, a in ipairs(anchor_nets) do heads[i - 1].kW, heads[i - 1].n, heads[i - 1].input = a.kW, a.n, a.input end
+  local fcs = ffi.new('frcnn_fc_desc[?]', nf)
+  for i, l in ipairs(class_layers) do
+    fcs[i - 1].n, fcs[i - 1].dropout, fcs[i - 1].batch_norm = l.n, l.dropout or 0, l.batch_norm and 1 or 0
+  end
+  local scales = ffi.new('double[?]', #cfg.scales, cfg.scales)
+  check(ctx, C.frcnn_model_plan(ctx, blocks, nb, heads, nh, fcs, nf, cfg.class_count, cfg.roi_pooling.kh, cfg.roi_pooling.kw,
+                                scales, #cfg.scales, -1))
+  -- parameter pointers in the library's bind order (frcnn_param_info): trunk convs, heads, cnet
+  local ptrs = {}
+  for _, seq in ipairs(trunk_blocks(model.pnet, nh)) do
+    local convs, prelus = seq:findModules('nn.SpatialConvolution'), seq:findModules('nn.PReLU')
+    for i = 1, #convs do
+      ptrs[#ptrs + 1] = dev_ptr(convs[i].weight); ptrs[#ptrs + 1] = dev_ptr(convs[i].bias); ptrs[#ptrs + 1] = dev_ptr(prelus[i].weight)
+    end
+  end
+  for i = 1, nh do
+    local seq = model.pnet.outnode.children[i].data.module   -- AnchorNetwork Sequential (model_utilities.lua:29-35)
+    local c1, pr, c2 = seq.modules[1], seq.modules[2], seq.modules[3]
+    for _, t in ipairs{c1.weight, c1.bias, pr.weight, c2.weight, c2.bias} do ptrs[#ptrs + 1] = dev_ptr(t) end
+  end
+  local lin = model.cnet:findModules('nn.Linear')
+  local bns = model.cnet:findModules('nn.BatchNormalization')
+  local prs = model.cnet:findModules('nn.PReLU')
+  local bi = 0
+  for i, l in ipairs(class_layers) do
+    ptrs[#ptrs + 1] = dev_ptr(lin[i].weight); ptrs[#ptrs + 1] = dev_ptr(lin[i].bias)
+    if l.batch_norm then
+      bi = bi + 1
+      local bn = bns[bi]
+      for _, t in ipairs{bn.weight, bn.bias, bn.running_mean, bn.running_var} do ptrs[#ptrs + 1] = dev_ptr(t) end
+    end
+    ptrs[#ptrs + 1] = dev_ptr(prs[i].weight)
+  end
+  -- the two output branches: Linear(n, 4) and Linear(n, classes) (model_utilities.lua:96-104)
+  local reg, cls = lin[nf + 1], lin[nf + 2]
+  if reg.weight:size(1) ~= 4 then reg, cls = cls, reg end
+  for _, t in ipairs{reg.weight, reg.bias, cls.weight, cls.bias} do ptrs[#ptrs + 1] = dev_ptr(t) end
+  assert(#ptrs == C.frcnn_param_count(ctx), 'parameter walk does not match the plan')
+  local arr = ffi.new('const float*[?]', #ptrs, ptrs)
+  check(ctx, C.frcnn_bind_params(ctx, arr, #ptrs))
+  model.b200 = { ctx = ctx, n_heads = nh }
+  M.pack(model)
+  return model
+end
+
+-- Call after every optimiser step / weights:copy (main.lua:97,133): re-packs fp32 -> bf16 tensor-core layouts.
+function M.pack(model)
+  cutorch.synchronize()
+  check(model.b200.ctx, C.frcnn_pack_weights(model.b200.ctx))
+end
+
+-- pnet:forward(img) drop-in (Detector.lua:33): returns the 5-entry output table of CudaTensors.
+function M.pnet_forward(model, img)
+  local ctx, nh = model.b200.ctx, model.b200.n_heads
+  local h, w = img:size(2), img:size(3)
+  local dims = ffi.new('int[?]', 3 * (nh + 1))
+  check(ctx, C.frcnn_pnet_output_dims(ctx, h, w, dims))
+  local outs, ptrs = {}, ffi.new('float*[?]', nh + 1)
+  for i = 0, nh do
+    outs[i + 1] = torch.CudaTensor(dims[3 * i], dims[3 * i + 1], dims[3 * i + 2])
+    ptrs[i] = outs[i + 1]:data()
+  end
+  check(ctx, C.frcnn_pnet_forward(ctx, img:data(), 1, h, w, ptrs))
+  return outs
+end
+
+return M
