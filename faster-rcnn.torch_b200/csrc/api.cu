@@ -23,7 +23,8 @@ struct ParamInfo {
 
 struct ConvLayer {
   int cin, cout, k, pad;
-  bool first;       // 3-channel first layer: im2col + 1x1 GEMM over 64-wide patches
+  bool first;       // 3-channel first layer: fused in-kernel im2col (conv_first_kernel)
+  bool pooled;      // last conv of a block: the 2x2 ceil max pool is fused into its epilogue
   float scale;      // SpatialDropout evaluate-mode factor (1 if no dropout follows)
   int p_w, p_b, p_prelu;
   bf16* w_packed = nullptr;
@@ -95,7 +96,6 @@ struct frcnn_ctx {
   // activation workspace for (N, H, W)
   int ws_n = 0, ws_h = 0, ws_w = 0;
   std::vector<void*> ws_allocs;
-  bf16* patches = nullptr;
   std::vector<bf16*> pool_out;   // per block
   std::vector<int> pool_h, pool_w;
   int feat_h = 0, feat_w = 0;
@@ -400,8 +400,8 @@ static void do_pack(frcnn_ctx* c) {
   };
   for (auto& cv : c->trunk) {
     if (cv.first) {
-      FRCNN_REQUIRE(cv.cin * cv.k * cv.k <= 64, FRCNN_E_INVALID, "first-layer im2col K exceeds 64");
-      if (!cv.w_packed) cv.w_packed = alloc_w((size_t)cv.cout * 64);
+      FRCNN_REQUIRE(cv.cin * cv.k * cv.k <= 32, FRCNN_E_INVALID, "first-layer im2col K exceeds 32");
+      if (!cv.w_packed) cv.w_packed = alloc_w((size_t)cv.cout * 32);
       launch_pack_first_conv_weight(P(c, cv.p_w), cv.w_packed, cv.cout, cv.cin, cv.k, cv.k, c->stream);
     } else {
       if (!cv.w_packed) cv.w_packed = alloc_w((size_t)cv.cout * cv.cin * cv.k * cv.k);
@@ -443,36 +443,33 @@ static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
   c->pool_out.assign(nb, nullptr);
   c->pool_h.assign(nb, 0);
   c->pool_w.assign(nb, 0);
-  c->patches = (bf16*)dev_alloc(c->ws_allocs, (size_t)N * H * W * 64 * sizeof(bf16));
   int h = H, w = W;
   bf16* cur = nullptr;
   size_t li = 0;
   for (int b = 0; b < nb; ++b) {
     for (int s = 0; s < c->blocks[b].conv_steps; ++s, ++li) {
       ConvLayer& cv = c->trunk[li];
+      cv.pooled = (s + 1 == c->blocks[b].conv_steps);  // model_utilities.lua:23: the pool follows the block's last conv
       cv.hin = h; cv.win = w;
       cv.hout = h + 2 * cv.pad - cv.k + 1;
       cv.wout = w + 2 * cv.pad - cv.k + 1;
-      cv.out = (bf16*)dev_alloc(c->ws_allocs, (size_t)N * cv.hout * cv.wout * cv.cout * sizeof(bf16));
+      const int oh = cv.pooled ? (cv.hout + 1) / 2 : cv.hout, ow = cv.pooled ? (cv.wout + 1) / 2 : cv.wout;  // :ceil()
+      cv.out = (bf16*)dev_alloc(c->ws_allocs, (size_t)N * oh * ow * cv.cout * sizeof(bf16));
+      const int mode = cv.pooled ? EPI_POOL : EPI_STORE;
       if (cv.first) {
-        cv.in = c->patches;
-        conv_prepare(&cv.launch, c->patches, cv.w_packed, N, cv.hout, cv.wout, 64, cv.cout, 1, 1, 0, 0, EPI_BF16_NHWC,
-                     c->sm_count, 0, 0);
+        cv.in = nullptr;
+        conv_first_prepare(&cv.launch, cv.w_packed, N, h, w, cv.cin, cv.cout, cv.k, cv.k, cv.pad, cv.pad, mode, cv.out, c->sm_count);
       } else {
         cv.in = cur;
-        conv_prepare(&cv.launch, cur, cv.w_packed, N, h, w, cv.cin, cv.cout, cv.k, cv.k, cv.pad, cv.pad, EPI_BF16_NHWC,
-                     c->sm_count, 0, 0);
+        conv_prepare(&cv.launch, cur, cv.w_packed, N, h, w, cv.cin, cv.cout, cv.k, cv.k, cv.pad, cv.pad, mode, cv.out,
+                     c->sm_count, 0, 0, 0);
       }
-      cv.launch.p.out_bf16 = cv.out;
       cv.launch.p.scale = cv.scale;
       cur = cv.out;
-      h = cv.hout; w = cv.wout;
+      h = oh; w = ow;
     }
-    const int ph = (h + 1) / 2, pw = (w + 1) / 2;  // :ceil() pooling (model_utilities.lua:23)
-    c->pool_out[b] = (bf16*)dev_alloc(c->ws_allocs, (size_t)N * ph * pw * c->blocks[b].filters * sizeof(bf16));
-    c->pool_h[b] = ph; c->pool_w[b] = pw;
-    cur = c->pool_out[b];
-    h = ph; w = pw;
+    c->pool_out[b] = cur;
+    c->pool_h[b] = h; c->pool_w[b] = w;
   }
   c->feat_h = h; c->feat_w = w;
   for (auto& hd : c->heads) {
@@ -485,7 +482,7 @@ static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
     hd.out = (float*)dev_alloc(c->ws_allocs, (size_t)N * 18 * hd.hh * hd.hw * sizeof(float));
     hd.conv.hin = ih; hd.conv.win = iw; hd.conv.hout = hd.hh; hd.conv.wout = hd.hw;
     conv_prepare(&hd.conv.launch, c->pool_out[hd.input - 1], hd.conv.w_packed, N, ih, iw, hd.conv.cin, hd.conv.cout, hd.kW,
-                 hd.kW, 0, 0, EPI_F32_ATOMIC, c->sm_count, 0, 0);
+                 hd.kW, 0, 0, EPI_F32_ATOMIC, nullptr, c->sm_count, 0, 0, 0);
     hd.conv.launch.p.out_f32 = hd.acc;
   }
   c->ws_n = N; c->ws_h = H; c->ws_w = W;
@@ -539,20 +536,12 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
   FRCNN_REQUIRE(N >= 1 && H >= 16 && W >= 16, FRCNN_E_INVALID, "bad input size");
   ensure_pnet_workspace(c, N, H, W);
   size_t li = 0;
-  int h = H, w = W;
   for (size_t b = 0; b < c->blocks.size(); ++b) {
     for (int s = 0; s < c->blocks[b].conv_steps; ++s, ++li) {
       ConvLayer& cv = c->trunk[li];
-      if (cv.first) {
-        launch_im2col_first(img_dev, c->patches, N, cv.cin, H, W, cv.k, cv.k, cv.pad, cv.pad, c->stream);
-        ++c->launches;
-      }
+      if (cv.first) cv.launch.p.img = img_dev;
       run_conv(c, cv);
-      h = cv.hout; w = cv.wout;
     }
-    launch_maxpool2x2(c->trunk[li - 1].out, c->pool_out[b], N, h, w, c->blocks[b].filters, c->stream);
-    ++c->launches;
-    h = c->pool_h[b]; w = c->pool_w[b];
     for (auto& hd : c->heads) {
       if (hd.input != (int)b + 1) continue;
       FRCNN_CUDA_TRY(cudaMemsetAsync(hd.acc, 0, (size_t)N * hd.hh * hd.hw * hd.n * sizeof(float), c->stream));
@@ -622,7 +611,7 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
     // split-K sized for the detector's typical few hundred ROIs: 8 K-iterations per split
     int k_iters = f.nin / 64;
     int splits = std::max(1, k_iters / 8);
-    conv_prepare(&f.launch, in, f.w_packed, 1, 1, R, f.nin, f.nout, 1, 1, 0, 0, EPI_F32_ATOMIC, c->sm_count, splits, 0);
+    conv_prepare(&f.launch, in, f.w_packed, 1, 1, R, f.nin, f.nout, 1, 1, 0, 0, EPI_F32_ATOMIC, nullptr, c->sm_count, splits, 0, 0);
     f.launch.p.out_f32 = f.acc;
     f.launch.p.m_limit = c->flags + 2;  // roi_total
     in = f.out_bf16;
@@ -1260,13 +1249,47 @@ int frcnn_last_conv_profile(const frcnn_ctx* c, float* ms, double* flops, int* l
   return FRCNN_OK;
 }
 
+int frcnn_conv_first(frcnn_ctx* c, const float* img_dev, const float* w_dev, const float* bias_dev, const float* prelu_dev,
+                     float scale, int n, int h, int w, int cout, int pad, int pool, uint16_t* out_dev, int iters, float* elapsed_ms) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(img_dev && w_dev && out_dev, FRCNN_E_INVALID, "null argument");
+  uint8_t* mem = (uint8_t*)frcnn::ensure_scratch(c, (size_t)cout * 32 * sizeof(frcnn::bf16) + 256);
+  frcnn::bf16* wp = (frcnn::bf16*)mem;
+  frcnn::launch_pack_first_conv_weight(w_dev, wp, cout, 3, 3, 3, c->stream);
+  frcnn::ConvLaunch L;
+  frcnn::conv_first_prepare(&L, wp, n, h, w, 3, cout, 3, 3, pad, pad, pool ? frcnn::EPI_POOL : frcnn::EPI_STORE, (frcnn::bf16*)out_dev,
+                            c->sm_count);
+  L.p.bias = bias_dev;
+  L.p.prelu = prelu_dev;
+  L.p.scale = scale;
+  L.p.img = img_dev;
+  if (iters < 1) iters = 1;
+  cudaEvent_t e0, e1;
+  FRCNN_CUDA_TRY(cudaEventCreate(&e0));
+  FRCNN_CUDA_TRY(cudaEventCreate(&e1));
+  FRCNN_CUDA_TRY(cudaEventRecord(e0, c->stream));
+  for (int i = 0; i < iters; ++i) {
+    frcnn::conv_launch(L, c->stream);
+    ++c->launches;
+  }
+  FRCNN_CUDA_TRY(cudaEventRecord(e1, c->stream));
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  if (elapsed_ms) FRCNN_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  API_END(c)
+}
+
 int frcnn_conv_bf16(frcnn_ctx* c, const uint16_t* x_dev, const float* w_dev, const float* bias_dev, const float* prelu_dev, float scale,
-                    int n, int h, int w, int cin, int cout, int k, int pad, int splits, int bn, uint16_t* out_dev, int iters,
-                    float* elapsed_ms) {
+                    int n, int h, int w, int cin, int cout, int k, int pad, int splits, int bn, int mt, int pool, uint16_t* out_dev,
+                    int iters, float* elapsed_ms) {
   API_BEGIN(c)
   REQUIRE_DEVICE(c);
   FRCNN_REQUIRE(x_dev && w_dev && out_dev, FRCNN_E_INVALID, "null argument");
   FRCNN_REQUIRE(bn == 0 || bn == 64 || bn == 128 || bn == 192 || bn == 256, FRCNN_E_INVALID, "bn must be 0, 64, 128, 192 or 256");
+  FRCNN_REQUIRE(mt >= 0 && mt <= 2 && !(pool && splits > 1), FRCNN_E_INVALID, "bad mt / pool");
   const int ho = h + 2 * pad - k + 1, wo = w + 2 * pad - k + 1;
   FRCNN_REQUIRE(ho > 0 && wo > 0, FRCNN_E_INVALID, "input smaller than the kernel");
   const size_t wbytes = ((size_t)cout * cin * k * k * sizeof(frcnn::bf16) + 255) & ~size_t(255);
@@ -1277,12 +1300,12 @@ int frcnn_conv_bf16(frcnn_ctx* c, const uint16_t* x_dev, const float* w_dev, con
   frcnn::launch_pack_conv_weight(w_dev, wp, cout, cin, k, k, c->stream);
   frcnn::ConvLaunch L;
   const bool split = splits > 1;
-  frcnn::conv_prepare(&L, (const frcnn::bf16*)x_dev, wp, n, h, w, cin, cout, k, k, pad, pad, split ? frcnn::EPI_F32_ATOMIC : frcnn::EPI_BF16_NHWC,
-                      c->sm_count, split ? splits : 0, bn);
+  frcnn::conv_prepare(&L, (const frcnn::bf16*)x_dev, wp, n, h, w, cin, cout, k, k, pad, pad,
+                      split ? frcnn::EPI_F32_ATOMIC : (pool ? frcnn::EPI_POOL : frcnn::EPI_STORE), (frcnn::bf16*)out_dev, c->sm_count,
+                      split ? splits : 0, bn, mt);
   L.p.bias = split ? nullptr : bias_dev;
   L.p.prelu = split ? nullptr : prelu_dev;
   L.p.scale = scale;
-  L.p.out_bf16 = (frcnn::bf16*)out_dev;
   L.p.out_f32 = acc;
   if (iters < 1) iters = 1;
   cudaEvent_t e0, e1;

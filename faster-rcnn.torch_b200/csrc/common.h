@@ -40,16 +40,19 @@ void set_global_error(const std::string& msg);
 
 // ------------------------------------------------------------------ conv / GEMM kernel interface
 enum ConvEpilogue {
-  EPI_BF16_NHWC = 0,   // y = prelu(acc + bias) * scale  -> bf16 NHWC
+  EPI_STORE = 0,       // y = prelu(acc + bias) * scale -> bf16 NHWC, staged in shared memory, written by TMA store
   EPI_F32_ATOMIC = 1,  // split-K partial sums, red.global.add.f32 into a zeroed fp32 [pixels][Cout] workspace
+  EPI_POOL = 2,        // as EPI_STORE followed by the 2x2 stride-2 ceil-mode max pool (model_utilities.lua:23):
+                       // only the pooled map is written
 };
 
 struct ConvParams {
   int N, Hin, Win, Cin;     // input NHWC (Cin % 64 == 0)
   int Hout, Wout, Cout;     // output
   int KH, KW, padH, padW;   // stride 1
-  int BW, BH, bw_shift;     // spatial shape of the 128-pixel M tile (BW * BH == 128)
-  int tiles_w, tiles_h;     // ceil(Wout / BW), ceil(Hout / BH)
+  int BW, BH, bw_shift;     // spatial shape of one 128-pixel M sub-tile (BW * BH == 128)
+  int MT;                   // 128-row sub-tiles per CTA tile (1 or 2), stacked along H: the CTA tile is BW x (BH * MT)
+  int tiles_w, tiles_h;     // ceil(Wout / BW), ceil(Hout / (BH * MT))
   int n_tiles_m, n_tiles_n; // N * tiles_h * tiles_w, ceil(Cout / BN)
   int cchunks;              // Cin / 64
   int k_iters;              // KH * KW * cchunks
@@ -58,9 +61,10 @@ struct ConvParams {
   const float* bias;        // [Cout] or null
   const float* prelu;       // device pointer to the shared slope, or null (identity)
   float scale;              // post-activation scale (SpatialDropout eval factor), 1 if none
-  bf16* out_bf16;           // EPI_BF16_NHWC
   float* out_f32;           // EPI_F32_ATOMIC
   const int* m_limit;       // optional device int: tiles whose first row >= *m_limit are skipped (GEMM rows)
+  const float* img;         // first-layer kernel only: [N][Cimg][Hin][Win] fp32 input frames (Torch layout)
+  int Cimg;                 // first-layer kernel only: image channels (3); K = Cimg * KH * KW <= 32
 };
 
 struct TensorMapCache;
@@ -68,7 +72,9 @@ struct TensorMapCache;
 struct ConvLaunch {
   ConvParams p;
   int BN;
-  CUtensorMap tmA, tmB;
+  bool first;               // fused first-layer kernel (in-kernel im2col of the fp32 image)
+  CUtensorMap tmA, tmB, tmOut;
+  const bf16* w_first;      // first-layer kernel: packed [Cout][32] bf16 weights
   int grid;
 };
 
@@ -77,7 +83,11 @@ void conv_choose_tile(int Hout, int Wout, int* BW, int* BH);
 void make_tmap_act(CUtensorMap* m, const bf16* base, int N, int H, int W, int C, int BW, int BH);
 void make_tmap_weight(CUtensorMap* m, const bf16* base, int Cout, int K, int BN);
 void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
-                  int KH, int KW, int padH, int padW, int mode, int num_sms, int force_splits, int force_bn);
+                  int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int force_splits, int force_bn,
+                  int force_mt);
+// First layer (Cin = 3): reads the fp32 NCHW frames directly; w_packed32: [Cout][32] bf16 (K = Cin*KH*KW padded).
+void conv_first_prepare(ConvLaunch* L, const bf16* w_packed32, int N, int Hin, int Win, int Cimg, int Cout, int KH,
+                        int KW, int padH, int padW, int mode, bf16* out, int num_sms);
 void conv_launch(const ConvLaunch& L, cudaStream_t st);
 int conv_smem_bytes(int BN);
 
@@ -85,8 +95,6 @@ int conv_smem_bytes(int BN);
 void launch_pack_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st);
 void launch_pack_first_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st);
 void launch_pack_fc_weight(const float* w, bf16* out, int nout, int C, int bins, int permute, cudaStream_t st);
-void launch_im2col_first(const float* img, bf16* patches, int N, int C, int H, int W, int KH, int KW, int padH,
-                         int padW, cudaStream_t st);
 void launch_maxpool2x2(const bf16* in, bf16* out, int N, int H, int W, int C, cudaStream_t st);
 void launch_head_tail(const float* acc, const float* bias, const float* prelu, const float* w2, const float* b2,
                       float* out_chw, int N, int H, int W, int Cmid, int Cout2, cudaStream_t st);

@@ -1,24 +1,32 @@
-// Implicit-GEMM convolution / GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue.
+// Implicit-GEMM convolution / GEMM for sm_100a: TMA -> shared memory -> tcgen05.mma -> TMEM -> epilogue -> TMA store.
 //
 // Replaces nn.SpatialConvolution forward as pnet uses it (models/model_utilities.lua:8,31; stride 1, square or
-// rectangular kernels, symmetric zero padding) and nn.Linear forward as cnet uses it (model_utilities.lua:82).
+// rectangular kernels, symmetric zero padding) fused with the nn.PReLU, the evaluate-mode nn.SpatialDropout scale
+// and -- for the last conv of a block -- the nn.SpatialMaxPooling(2,2,2,2):ceil() that follow it
+// (model_utilities.lua:9-12,23), and nn.Linear forward as cnet uses it (model_utilities.lua:82).
 //
 // Data layout in HBM
 //   activations  NHWC bf16, C % 64 == 0          (a GEMM operand [rows][K] is the case H = 1, W = rows)
 //   weights      [Cout][KH][KW][Cin] bf16        (K-major rows of K = KH*KW*Cin)
 // GEMM view      M = N*Hout*Wout output pixels, N = Cout, K = KH*KW*Cin.
 //
-// One M tile is a BH x BW rectangle of 128 output pixels of one image, so that the A operand of filter tap
-// (kh, kw) and channel chunk c is ONE 4-D TMA box {64 ch, BW, BH, 1} at (c, w0 + kw - padW, h0 + kh - padH, n):
+// One CTA tile is a (BH*MT) x BW rectangle of 128*MT output pixels of one image, so that the A operand of filter tap
+// (kh, kw) and channel chunk c is ONE 4-D TMA box {64 ch, BW, BH*MT, 1} at (c, w0 + kw - padW, h0 + kh - padH, n):
 // zero padding and image borders are the TMA unit's out-of-bounds zero fill, no im2col buffer exists.  The box
-// lands in shared memory as 128 rows of 128 bytes with the 128-byte swizzle -- the canonical K-major UMMA
-// operand layout -- and is consumed by four tcgen05.mma (M=128, N=BN, K=16) per 64-channel chunk.
+// lands in shared memory as rows of 128 bytes with the 128-byte swizzle -- the canonical K-major UMMA operand
+// layout -- and is consumed by four tcgen05.mma (M=128, N=BN, K=16) per 64-channel chunk and 128-row sub-tile.
+// MT = 2 halves the weight traffic per MAC for the narrow (Cout <= 128) layers, which are L2->SM bandwidth bound.
 //
 // Kernel structure (persistent, warp-specialised, 256 threads, 1 CTA / SM):
 //   warp 0   TMA producer   (one elected lane)        smem ring: full[s] / empty[s] mbarriers
 //   warp 1   MMA issuer     (one elected lane)        TMEM accumulators double-buffered: tmem_full / tmem_empty
 //   warp 2   TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld 32x32b -> bias + PReLU + scale -> bf16 NHWC   (or fp32 red.add for split-K)
+//   warps 4-7 epilogue: tcgen05.ld 32x32b -> bias (smem) + PReLU + scale -> bf16 -> swizzled smem tile
+//             [-> 2x2 max pool in smem] -> one TMA tensor store per 64-channel group (coalesced, clips borders);
+//             or fp32 red.add for split-K (cnet, anchor heads).
+//
+// conv_first_kernel: the 3-channel first layer.  Same MMA / epilogue, but the A operand (K = 27 padded to 32) is
+// built in shared memory by four producer warps straight from the fp32 NCHW frame -- no im2col buffer in HBM.
 #include <stdio.h>
 
 #include "common.h"
@@ -27,14 +35,23 @@
 namespace frcnn {
 
 static constexpr int BLOCK_M = 128;
-static constexpr int BLOCK_K = 64;                         // bf16 elements = 128 bytes = one swizzle row
-static constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-static constexpr int SMEM_BUDGET = 200 * 1024;
+static constexpr int BLOCK_K = 64;                           // bf16 elements = 128 bytes = one swizzle row
+static constexpr int A_SUB_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB per 128-row sub-tile
+static constexpr int STAGE_TILE_BYTES = 128 * 128;           // epilogue staging: 128 px x 64 ch bf16
+static constexpr int STAGE_POOL_BYTES = 32 * 128;            // pooled 32 px x 64 ch
+static constexpr int MAX_BIAS = 512;
+static constexpr int SMEM_LIMIT = 227 * 1024;
+static constexpr int SMEM_FIXED = STAGE_TILE_BYTES + STAGE_POOL_BYTES + MAX_BIAS * 4 + 256 + 1024;
 
-__host__ __device__ constexpr int conv_stages(int BN) { return SMEM_BUDGET / (A_STAGE_BYTES + BN * BLOCK_K * 2); }
-__host__ __device__ constexpr int tmem_cols(int BN) { return 2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512); }
-
-int conv_smem_bytes(int BN) { return conv_stages(BN) * (A_STAGE_BYTES + BN * BLOCK_K * 2) + 1024 + 256; }
+__host__ __device__ constexpr int stage_bytes(int BN, int MT) { return MT * A_SUB_BYTES + BN * BLOCK_K * 2; }
+__host__ __device__ constexpr int conv_stages(int BN, int MT) {
+  return (SMEM_LIMIT - SMEM_FIXED) / stage_bytes(BN, MT) > 8 ? 8 : (SMEM_LIMIT - SMEM_FIXED) / stage_bytes(BN, MT);
+}
+__host__ __device__ constexpr int tmem_cols(int BN, int MT) {
+  return 2 * BN * MT <= 64 ? 64 : (2 * BN * MT <= 128 ? 128 : (2 * BN * MT <= 256 ? 256 : 512));
+}
+static int conv_smem_bytes_mt(int BN, int MT) { return conv_stages(BN, MT) * stage_bytes(BN, MT) + SMEM_FIXED; }
+int conv_smem_bytes(int BN) { return conv_smem_bytes_mt(BN, 1); }
 
 struct TileCoord {
   int n_img, h0, w0, n0, k_begin, k_end, m0;
@@ -50,7 +67,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
   int r2 = mt / p.tiles_w;
   int th = r2 % p.tiles_h;
   t.n_img = r2 / p.tiles_h;
-  t.h0 = th * p.BH;
+  t.h0 = th * p.BH * p.MT;
   t.w0 = tw * p.BW;
   t.n0 = nt * BN;
   t.k_begin = ks * p.k_per_split;
@@ -59,20 +76,150 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
   return t;
 }
 
-template <int BN>
+// ------------------------------------------------------------------------------------------------- epilogue
+// Runs on the four epilogue warps (warp & 3 = TMEM lane quarter).  tile_buf / pool_buf: 1024-byte aligned staging.
+template <int BN, int MT>
+__device__ __forceinline__ void epilogue_loop(const ConvParams& p, const CUtensorMap* tmOut, uint8_t* tile_buf,
+                                              uint8_t* pool_buf, const float* sbias, uint32_t tmem_base, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty, int total_tiles, int m_limit, int warp, int lane) {
+  const int q = warp & 3;
+  const int row = q * 32 + lane;  // TMEM lane == pixel row of the sub-tile
+  const int dy = row >> p.bw_shift;
+  const int dx = row & (p.BW - 1);
+  const float slope = p.prelu ? __ldg(p.prelu) : 1.0f;
+  const bool has_prelu = p.prelu != nullptr;
+  const bool store_thread = (row == 0);
+  const uint32_t tile_addr = ptx::smem_u32(tile_buf);
+  const uint32_t pool_addr = ptx::smem_u32(pool_buf);
+  const uint32_t my_row_addr = tile_addr + row * 128;
+  const int sw = row & 7;
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    TileCoord t = decode_tile(p, tile, BN);
+    if (t.m0 >= m_limit) continue;
+    ptx::mbar_wait(&tmem_full[acc], acc_phase);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int hbase = t.h0 + mt * p.BH;
+      const int h = hbase + dy, w = t.w0 + dx;
+      const bool valid = (h < p.Hout) && (w < p.Wout);
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN * MT + mt * BN) + ((uint32_t)(q * 32) << 16);
+      if (p.mode == EPI_F32_ATOMIC) {
+        const size_t pix = ((size_t)t.n_img * p.Hout + h) * p.Wout + w;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(taddr + c0, v);
+          ptx::tmem_ld_wait();
+          const int cbase = t.n0 + c0;
+          if (valid && cbase < p.Cout) {
+            float* dst = p.out_f32 + pix * p.Cout + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int g = 0; g < BN / 64; ++g) {
+          const int cbase = t.n0 + g * 64;
+          uint32_t o[32];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(taddr + g * 64 + half * 32, v);
+            ptx::tmem_ld_wait();
+            const float4* b4 = reinterpret_cast<const float4*>(sbias + cbase + half * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = b4[j];
+              float x0 = __uint_as_float(v[4 * j]) + b.x, x1 = __uint_as_float(v[4 * j + 1]) + b.y;
+              float x2 = __uint_as_float(v[4 * j + 2]) + b.z, x3 = __uint_as_float(v[4 * j + 3]) + b.w;
+              if (has_prelu) {
+                x0 = x0 > 0.f ? x0 : x0 * slope;
+                x1 = x1 > 0.f ? x1 : x1 * slope;
+                x2 = x2 > 0.f ? x2 : x2 * slope;
+                x3 = x3 > 0.f ? x3 : x3 * slope;
+              }
+              o[half * 16 + 2 * j] = ptx::pack_bf16x2(x0 * p.scale, x1 * p.scale);
+              o[half * 16 + 2 * j + 1] = ptx::pack_bf16x2(x2 * p.scale, x3 * p.scale);
+            }
+          }
+          if (p.mode == EPI_POOL && !valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = 0xFF80FF80u;  // -inf: outside the map, never wins a ceil-mode window
+          }
+          // the previous TMA store must have finished reading the staging buffers before they are overwritten
+          if (store_thread) ptx::tma_store_wait_read();
+          ptx::named_bar_sync(1, 128);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            ptx::st_shared_v4(my_row_addr + ((c ^ sw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+          if (p.mode == EPI_POOL) {
+            ptx::named_bar_sync(1, 128);
+            const int pw_shift = p.bw_shift - 1;  // pooled tile width BW / 2
+#pragma unroll
+            for (int it = 0; it < 2; ++it) {
+              const int item = row + it * 128;
+              const int pp = item >> 3, c = item & 7;
+              const int ppy = pp >> pw_shift, ppx = pp & ((p.BW >> 1) - 1);
+              const int r00 = (2 * ppy) * p.BW + 2 * ppx;
+              const int r01 = r00 + 1, r10 = r00 + p.BW, r11 = r10 + 1;
+              uint4 a = ptx::ld_shared_v4(tile_addr + r00 * 128 + ((c ^ (r00 & 7)) << 4));
+              const uint4 b = ptx::ld_shared_v4(tile_addr + r01 * 128 + ((c ^ (r01 & 7)) << 4));
+              const uint4 cc = ptx::ld_shared_v4(tile_addr + r10 * 128 + ((c ^ (r10 & 7)) << 4));
+              const uint4 d = ptx::ld_shared_v4(tile_addr + r11 * 128 + ((c ^ (r11 & 7)) << 4));
+              __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
+              const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+              const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&cc);
+              const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pa[j] = __hmax2(__hmax2(pa[j], pb[j]), __hmax2(pc[j], pd[j]));
+              ptx::st_shared_v4(pool_addr + pp * 128 + ((c ^ (pp & 7)) << 4), a.x, a.y, a.z, a.w);
+            }
+          }
+          ptx::fence_proxy_async();
+          ptx::named_bar_sync(1, 128);
+          if (store_thread) {
+            if (p.mode == EPI_POOL) ptx::tma_store_4d(tmOut, pool_buf, cbase, t.w0 >> 1, hbase >> 1, t.n_img);
+            else ptx::tma_store_4d(tmOut, tile_buf, cbase, t.w0, hbase, t.n_img);
+            ptx::tma_store_commit();
+          }
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+    if (++acc == 2) {
+      acc = 0;
+      acc_phase ^= 1;
+    }
+  }
+  if (store_thread) ptx::tma_store_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------------- main kernel
+template <int BN, int MT>
 __global__ void __launch_bounds__(256, 1)
-    conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
-  constexpr int STAGES = conv_stages(BN);
+    conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
+  constexpr int STAGES = conv_stages(BN, MT);
+  constexpr int A_STAGE_BYTES = MT * A_SUB_BYTES;
   constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   constexpr uint32_t TX_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BN);
-  constexpr int TMEM_COLS = tmem_cols(BN);
+  constexpr int TMEM_COLS = tmem_cols(BN, MT);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint8_t* tile_buf = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  uint8_t* pool_buf = tile_buf + STAGE_TILE_BYTES;
+  float* sbias = reinterpret_cast<float*>(pool_buf + STAGE_POOL_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -86,6 +233,7 @@ __global__ void __launch_bounds__(256, 1)
   if (warp == 0 && lane == 0) {
     ptx::tma_prefetch_desc(&tmA);
     ptx::tma_prefetch_desc(&tmB);
+    if (p.mode != EPI_F32_ATOMIC) ptx::tma_prefetch_desc(&tmOut);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -101,6 +249,10 @@ __global__ void __launch_bounds__(256, 1)
   if (warp == 2) {
     ptx::tmem_alloc(tmem_base_slot, TMEM_COLS);
     ptx::tmem_relinquish();
+  }
+  if (p.mode != EPI_F32_ATOMIC) {
+    // parameter pointers are views into Torch's flat weight buffer at arbitrary 4-byte offsets: scalar loads
+    for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -144,7 +296,7 @@ __global__ void __launch_bounds__(256, 1)
         if (t.m0 >= m_limit) continue;
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tmem_base + acc * BN * MT;
         for (int k = t.k_begin; k < t.k_end; ++k) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
@@ -152,8 +304,13 @@ __global__ void __launch_bounds__(256, 1)
           const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
 #pragma unroll
           for (int j = 0; j < BLOCK_K / 16; ++j) {
-            // advance 16 bf16 = 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            ptx::mma_bf16_ss(d_tmem, da + 2 * j, db + 2 * j, IDESC, (k > t.k_begin || j > 0) ? 1u : 0u);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) {
+              // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field; the second
+              // 128-row sub-tile starts 16 KB further
+              ptx::mma_bf16_ss(d_tmem + mt * BN, da + 2 * j + mt * (A_SUB_BYTES >> 4), db + 2 * j, IDESC,
+                               (k > t.k_begin || j > 0) ? 1u : 0u);
+            }
           }
           ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           if (k == t.k_end - 1) ptx::mma_commit(&tmem_full[acc]);
@@ -169,71 +326,149 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (warps 4..7 <-> TMEM lanes 0..127)
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const int dy = row >> p.bw_shift;
-    const int dx = row & (p.BW - 1);
-    const float slope = p.prelu ? __ldg(p.prelu) : 1.0f;
-    const bool has_prelu = p.prelu != nullptr;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      TileCoord t = decode_tile(p, tile, BN);
-      if (t.m0 >= m_limit) continue;
-      ptx::mbar_wait(&tmem_full[acc], acc_phase);
-      ptx::tc_fence_after();
-      const int h = t.h0 + dy, w = t.w0 + dx;
-      const bool valid = (h < p.Hout) && (w < p.Wout);
-      const size_t pix = ((size_t)t.n_img * p.Hout + h) * p.Wout + w;
-      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(taddr + c0, v);
-        ptx::tmem_ld_wait();
-        const int cbase = t.n0 + c0;
-        if (valid && cbase < p.Cout) {
-          if (p.mode == EPI_BF16_NHWC) {
-            uint32_t o[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float x0 = __uint_as_float(v[2 * j]), x1 = __uint_as_float(v[2 * j + 1]);
-              if (p.bias) {
-                x0 += __ldg(p.bias + cbase + 2 * j);
-                x1 += __ldg(p.bias + cbase + 2 * j + 1);
-              }
-              if (has_prelu) {
-                x0 = x0 > 0.f ? x0 : x0 * slope;
-                x1 = x1 > 0.f ? x1 : x1 * slope;
-              }
-              x0 *= p.scale;
-              x1 *= p.scale;
-              o[j] = ptx::pack_bf16x2(x0, x1);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(p.out_bf16 + pix * p.Cout + cbase);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-          } else {
-            float* dst = p.out_f32 + pix * p.Cout + cbase;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
-          }
-        }
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
-      }
-    }
+    epilogue_loop<BN, MT>(p, &tmOut, tile_buf, pool_buf, sbias, tmem_base, tmem_full, tmem_empty, total_tiles, m_limit, warp, lane);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- first layer
+// 3 x (3x3) first convolution on the fp32 NCHW frame (Detector.lua:32-33 uploads exactly this tensor).
+// 384 threads: warps 0-3 build the im2col rows (K = 27 -> 32, 64 bytes of each 128-byte swizzled row), warp 4 issues
+// two tcgen05.mma (M128 x N64 x K16) per tile, warp 5 owns TMEM, warps 8-11 run the shared epilogue.
+static constexpr int FIRST_STAGES = 6;
+static constexpr int FIRST_BN = 64;
+static constexpr int FIRST_SMEM = FIRST_STAGES * A_SUB_BYTES + FIRST_BN * 128 + SMEM_FIXED;
+
+__global__ void __launch_bounds__(384, 1)
+    conv_first_kernel(const __grid_constant__ CUtensorMap tmOut, const ConvParams p, const bf16* __restrict__ w32) {
+  constexpr int BN = FIRST_BN;
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BN);
+  constexpr int TMEM_COLS = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + FIRST_STAGES * A_SUB_BYTES;
+  uint8_t* tile_buf = smem_b + BN * 128;
+  uint8_t* pool_buf = tile_buf + STAGE_TILE_BYTES;
+  float* sbias = reinterpret_cast<float*>(pool_buf + STAGE_POOL_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
+  uint64_t* empty_bar = full_bar + FIRST_STAGES;
+  uint64_t* tmem_full = empty_bar + FIRST_STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.n_tiles_m;
+
+  if (warp == 4 && lane == 0) {
+    ptx::tma_prefetch_desc(&tmOut);
+    for (int s = 0; s < FIRST_STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 128);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 5) {
+    ptx::tmem_alloc(tmem_base_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+  // weights [64][32] bf16 -> K-major 128-byte-swizzled rows (chunks 0..3 of every row)
+  for (int i = threadIdx.x; i < BN * 4; i += blockDim.x) {
+    const int n = i >> 2, c = i & 3;
+    const uint4 v = reinterpret_cast<const uint4*>(w32)[i];
+    *reinterpret_cast<uint4*>(smem_b + n * 128 + ((c ^ (n & 7)) << 4)) = v;
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------ im2col producers: thread <-> pixel row
+    const int row = threadIdx.x;
+    const int dy = row >> p.bw_shift, dx = row & (p.BW - 1);
+    const int sw = row & 7;
+    const size_t plane = (size_t)p.Hin * p.Win;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TileCoord t = decode_tile(p, tile, BN);
+      const int h = t.h0 + dy - p.padH, w = t.w0 + dx - p.padW;  // top-left tap in input coordinates
+      const float* base = p.img + (size_t)t.n_img * 3 * plane;
+      float v[27];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int yy = h + kh, xx = w + kw;
+            const bool in = yy >= 0 && yy < p.Hin && xx >= 0 && xx < p.Win;
+            v[c * 9 + kh * 3 + kw] = in ? __ldg(base + c * plane + (size_t)yy * p.Win + xx) : 0.f;
+          }
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 13; ++j) o[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      o[13] = ptx::pack_bf16x2(v[26], 0.f);
+      o[14] = 0u;
+      o[15] = 0u;
+      ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+      const uint32_t dst = ptx::smem_u32(smem_a + stage * A_SUB_BYTES) + row * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ptx::st_shared_v4(dst + ((c ^ sw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+      ptx::fence_proxy_async();
+      ptx::mbar_arrive(&full_bar[stage]);
+      if (++stage == FIRST_STAGES) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp == 4) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b));
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + stage * A_SUB_BYTES));
+        ptx::mma_bf16_ss(tmem_base + acc * BN, da, db, IDESC, 0u);
+        ptx::mma_bf16_ss(tmem_base + acc * BN, da + 2, db + 2, IDESC, 1u);
+        ptx::mma_commit(&empty_bar[stage]);
+        ptx::mma_commit(&tmem_full[acc]);
+        if (++stage == FIRST_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    epilogue_loop<BN, 1>(p, &tmOut, tile_buf, pool_buf, sbias, tmem_base, tmem_full, tmem_empty, total_tiles, 0x7fffffff, warp, lane);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -257,6 +492,7 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// NHWC bf16 tensor [N][H][W][C], box {64 ch, BW, BH, 1}, 128-byte swizzle: used for loads (A operand) and stores
 void make_tmap_act(CUtensorMap* m, const bf16* base, int N, int H, int W, int C, int BW, int BH) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
@@ -267,7 +503,8 @@ void make_tmap_act(CUtensorMap* m, const bf16* base, int N, int H, int W, int C,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FRCNN_REQUIRE(r == CUDA_SUCCESS, FRCNN_E_CUDA,
                 "cuTensorMapEncodeTiled(activation) failed, CUresult " + std::to_string((int)r) + " dims " +
-                    std::to_string(C) + "x" + std::to_string(W) + "x" + std::to_string(H) + "x" + std::to_string(N));
+                    std::to_string(C) + "x" + std::to_string(W) + "x" + std::to_string(H) + "x" + std::to_string(N) + " box " +
+                    std::to_string(BW) + "x" + std::to_string(BH));
 }
 
 void make_tmap_weight(CUtensorMap* m, const bf16* base, int Cout, int K, int BN) {
@@ -282,12 +519,14 @@ void make_tmap_weight(CUtensorMap* m, const bf16* base, int Cout, int K, int BN)
                 "cuTensorMapEncodeTiled(weight) failed, CUresult " + std::to_string((int)r));
 }
 
-// Pick the BW x BH (= 128) rectangle that wastes the fewest padded pixels.
-void conv_choose_tile(int Hout, int Wout, int* BW, int* BH) {
+// Pick the BW x BH (= 128) rectangle that wastes the fewest padded pixels.  mt: sub-tiles stacked along H;
+// even: both sides even (needed by the fused 2x2 pool).
+static void choose_tile(int Hout, int Wout, int mt, bool even, int* BW, int* BH) {
   long best = -1;
-  for (int bw = 128; bw >= 1; bw >>= 1) {
+  for (int bw = even ? 64 : 128; bw >= (even ? 2 : 1); bw >>= 1) {
     int bh = 128 / bw;
-    long padded = (long)((Wout + bw - 1) / bw) * bw * (long)((Hout + bh - 1) / bh) * bh;
+    long th = (long)bh * mt;
+    long padded = (long)((Wout + bw - 1) / bw) * bw * (long)((Hout + th - 1) / th) * th;
     if (best < 0 || padded < best) {
       best = padded;
       *BW = bw;
@@ -295,6 +534,7 @@ void conv_choose_tile(int Hout, int Wout, int* BW, int* BH) {
     }
   }
 }
+void conv_choose_tile(int Hout, int Wout, int* BW, int* BH) { choose_tile(Hout, Wout, 1, false, BW, BH); }
 
 static int choose_bn(int Cout) {
   if (Cout % 256 == 0) return 256;
@@ -304,25 +544,55 @@ static int choose_bn(int Cout) {
   return 128;
 }
 
-void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
-                  int KH, int KW, int padH, int padW, int mode, int num_sms, int force_splits, int force_bn) {
-  FRCNN_REQUIRE(Cin % 64 == 0, FRCNN_E_INVALID, "conv: Cin must be a multiple of 64");
-  FRCNN_REQUIRE(Cout % 32 == 0, FRCNN_E_INVALID, "conv: Cout must be a multiple of 32");
-  ConvParams& p = L->p;
+static void fill_geometry(ConvParams& p, int N, int Hin, int Win, int Cin, int Cout, int KH, int KW, int padH, int padW,
+                          int mode, int MT) {
   p = ConvParams();
   p.N = N; p.Hin = Hin; p.Win = Win; p.Cin = Cin;
   p.Hout = Hin + 2 * padH - KH + 1;
   p.Wout = Win + 2 * padW - KW + 1;
   FRCNN_REQUIRE(p.Hout > 0 && p.Wout > 0, FRCNN_E_INVALID, "conv: input smaller than the kernel");
   p.Cout = Cout; p.KH = KH; p.KW = KW; p.padH = padH; p.padW = padW;
-  conv_choose_tile(p.Hout, p.Wout, &p.BW, &p.BH);
+  p.MT = MT;
+  choose_tile(p.Hout, p.Wout, MT, mode == EPI_POOL, &p.BW, &p.BH);
   p.bw_shift = 0;
   while ((1 << p.bw_shift) < p.BW) ++p.bw_shift;
   p.tiles_w = (p.Wout + p.BW - 1) / p.BW;
-  p.tiles_h = (p.Hout + p.BH - 1) / p.BH;
+  p.tiles_h = (p.Hout + p.BH * MT - 1) / (p.BH * MT);
   p.n_tiles_m = N * p.tiles_h * p.tiles_w;
+  p.mode = mode;
+  p.scale = 1.0f;
+}
+
+static void make_out_map(ConvLaunch* L, bf16* out) {
+  const ConvParams& p = L->p;
+  if (p.mode == EPI_STORE) make_tmap_act(&L->tmOut, out, p.N, p.Hout, p.Wout, p.Cout, p.BW, p.BH);
+  else if (p.mode == EPI_POOL)
+    make_tmap_act(&L->tmOut, out, p.N, (p.Hout + 1) / 2, (p.Wout + 1) / 2, p.Cout, p.BW / 2, p.BH / 2);
+  else L->tmOut = L->tmB;  // unused
+}
+
+void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
+                  int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int force_splits, int force_bn,
+                  int force_mt) {
+  FRCNN_REQUIRE(Cin % 64 == 0, FRCNN_E_INVALID, "conv: Cin must be a multiple of 64");
+  FRCNN_REQUIRE(mode == EPI_F32_ATOMIC ? Cout % 32 == 0 : (Cout % 64 == 0 && Cout <= MAX_BIAS), FRCNN_E_INVALID,
+                "conv: Cout must be a multiple of 64 (<= 512) for the bf16 epilogues, of 32 for split-K");
+  FRCNN_REQUIRE(mode == EPI_F32_ATOMIC || out != nullptr, FRCNN_E_INVALID, "conv: null output");
   int BN = force_bn > 0 ? force_bn : choose_bn(Cout);
   L->BN = BN;
+  L->first = false;
+  L->w_first = nullptr;
+  // two 128-row sub-tiles per CTA for the narrow layers (halves the weight traffic per MAC) when there are enough
+  // tiles left to fill the machine at least twice
+  int MT = 1;
+  if (force_mt > 0) MT = force_mt;
+  else if (mode != EPI_F32_ATOMIC && BN <= 128) {
+    long px = (long)N * (Hin + 2 * padH - KH + 1) * (Win + 2 * padW - KW + 1);
+    if (px / 256 * ((Cout + BN - 1) / BN) >= 2L * num_sms) MT = 2;
+  }
+  FRCNN_REQUIRE(MT == 1 || (MT == 2 && BN <= 128), FRCNN_E_INVALID, "conv: MT = 2 needs BN <= 128 (TMEM columns)");
+  fill_geometry(L->p, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, MT);
+  ConvParams& p = L->p;
   p.n_tiles_n = (Cout + BN - 1) / BN;
   p.cchunks = Cin / 64;
   p.k_iters = KH * KW * p.cchunks;
@@ -342,33 +612,68 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
   if (splits > p.k_iters) splits = p.k_iters;
   p.k_per_split = (p.k_iters + splits - 1) / splits;
   p.splits = (p.k_iters + p.k_per_split - 1) / p.k_per_split;
-  p.mode = mode;
-  p.scale = 1.0f;
-  make_tmap_act(&L->tmA, in, N, Hin, Win, Cin, p.BW, p.BH);
+  make_tmap_act(&L->tmA, in, N, Hin, Win, Cin, p.BW, p.BH * MT);
   make_tmap_weight(&L->tmB, w_packed, Cout, KH * KW * Cin, BN);
+  make_out_map(L, out);
   int total = p.n_tiles_m * p.n_tiles_n * p.splits;
   L->grid = total < num_sms ? total : num_sms;
 }
 
-template <int BN>
-static void launch_bn(const ConvLaunch& L, cudaStream_t st) {
+void conv_first_prepare(ConvLaunch* L, const bf16* w_packed32, int N, int Hin, int Win, int Cimg, int Cout, int KH,
+                        int KW, int padH, int padW, int mode, bf16* out, int num_sms) {
+  FRCNN_REQUIRE(Cimg == 3 && KH == 3 && KW == 3 && Cout == FIRST_BN, FRCNN_E_INVALID,
+                "first-layer kernel: 3 input planes, 3x3 filters, 64 outputs (models/vgg_*.lua)");
+  FRCNN_REQUIRE(mode == EPI_STORE || mode == EPI_POOL, FRCNN_E_INVALID, "first-layer kernel: bf16 epilogues only");
+  L->BN = FIRST_BN;
+  L->first = true;
+  L->w_first = w_packed32;
+  fill_geometry(L->p, N, Hin, Win, 64, Cout, KH, KW, padH, padW, mode, 1);
+  ConvParams& p = L->p;
+  p.Cimg = Cimg;
+  p.n_tiles_n = 1;
+  p.cchunks = 1;
+  p.k_iters = 1;
+  p.splits = 1;
+  p.k_per_split = 1;
+  make_out_map(L, out);
+  L->tmA = L->tmOut;
+  L->tmB = L->tmOut;
+  L->grid = p.n_tiles_m < num_sms ? p.n_tiles_m : num_sms;
+}
+
+template <int BN, int MT>
+static void launch_cfg(const ConvLaunch& L, cudaStream_t st) {
   static bool configured = false;
-  int smem = conv_smem_bytes(BN);
+  int smem = conv_smem_bytes_mt(BN, MT);
   if (!configured) {
-    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  conv_igemm_kernel<BN><<<L.grid, 256, smem, st>>>(L.tmA, L.tmB, L.p);
+  conv_igemm_kernel<BN, MT><<<L.grid, 256, smem, st>>>(L.tmA, L.tmB, L.tmOut, L.p);
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
 void conv_launch(const ConvLaunch& L, cudaStream_t st) {
-  switch (L.BN) {
-    case 64: launch_bn<64>(L, st); break;
-    case 128: launch_bn<128>(L, st); break;
-    case 192: launch_bn<192>(L, st); break;
-    case 256: launch_bn<256>(L, st); break;
-    default: throw Error{FRCNN_E_INVALID, "conv: unsupported BN"};
+  if (L.first) {
+    static bool configured = false;
+    if (!configured) {
+      FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_SMEM));
+      configured = true;
+    }
+    FRCNN_REQUIRE(L.p.img != nullptr, FRCNN_E_STATE, "first-layer kernel: image pointer not set");
+    conv_first_kernel<<<L.grid, 384, FIRST_SMEM, st>>>(L.tmOut, L.p, L.w_first);
+    FRCNN_CUDA_TRY(cudaGetLastError());
+    return;
+  }
+  const int key = L.BN * 10 + L.p.MT;
+  switch (key) {
+    case 641: launch_cfg<64, 1>(L, st); break;
+    case 642: launch_cfg<64, 2>(L, st); break;
+    case 1281: launch_cfg<128, 1>(L, st); break;
+    case 1282: launch_cfg<128, 2>(L, st); break;
+    case 1921: launch_cfg<192, 1>(L, st); break;
+    case 2561: launch_cfg<256, 1>(L, st); break;
+    default: throw Error{FRCNN_E_INVALID, "conv: unsupported (BN, MT)"};
   }
 }
 

@@ -1,5 +1,5 @@
-// HBM-bound helper kernels around the tensor-core conv: weight re-packing, the im2col of the 3-channel first
-// layer, 2x2 ceil-mode max pooling, anchor-head tail (bias + PReLU + 1x1 conv), cnet tails and layout converters.
+// HBM-bound helper kernels around the tensor-core conv: weight re-packing, 2x2 ceil-mode max pooling (standalone
+// variant; the trunk uses the pool fused into the conv epilogue), anchor-head tail (bias + PReLU + 1x1 conv), cnet tails and layout converters.
 // All are coalesced / 16-byte vectorised streaming kernels; none has data reuse worth staging in shared memory
 // except the small weight matrices of the tails.
 #include "common.h"
@@ -28,15 +28,15 @@ void launch_pack_conv_weight(const float* w, bf16* out, int Cout, int Cin, int K
   pack_conv_weight_kernel<<<min(cdiv(total, 256), 148 * 8), 256, 0, st>>>(w, out, Cout, Cin, KH, KW);
 }
 
-// First layer (Cin = 3): the flat Torch weight row [Cin*KH*KW] is already the im2col K order; pad K to 64.
+// First layer (Cin = 3): the flat Torch weight row [Cin*KH*KW] is already the im2col K order; pad K to 32.
 __global__ void pack_first_conv_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int K) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Cout * 64) return;
-  int k = i & 63, o = i >> 6;
+  if (i >= Cout * 32) return;
+  int k = i & 31, o = i >> 5;
   out[i] = __float2bfloat16_rn(k < K ? w[o * K + k] : 0.f);
 }
 void launch_pack_first_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st) {
-  pack_first_conv_weight_kernel<<<cdiv(Cout * 64, 256), 256, 0, st>>>(w, out, Cout, Cin * KH * KW);
+  pack_first_conv_weight_kernel<<<cdiv(Cout * 32, 256), 256, 0, st>>>(w, out, Cout, Cin * KH * KW);
 }
 
 // Linear weight [nout][K] fp32 -> bf16.  With permute: K index c*bins + b (reference ROI-pool flatten order,
@@ -59,49 +59,6 @@ __global__ void pack_fc_weight_kernel(const float* __restrict__ w, bf16* __restr
 void launch_pack_fc_weight(const float* w, bf16* out, int nout, int C, int bins, int permute, cudaStream_t st) {
   long total = (long)nout * C * bins;
   pack_fc_weight_kernel<<<min(cdiv(total, 256), 148 * 8), 256, 0, st>>>(w, out, nout, C, bins, permute);
-}
-
-// ------------------------------------------------------------------------------------------ first-layer im2col
-// img [N][C][H][W] fp32 -> patches [N][H][W][64] bf16, k = c*KH*KW + kh*KW + kw (zero for k >= C*KH*KW and for
-// taps outside the image).  One thread writes 8 consecutive k (16 bytes).
-__global__ void im2col_first_kernel(const float* __restrict__ img, bf16* __restrict__ patches, int N, int C, int H, int W,
-                                    int KH, int KW, int padH, int padW) {
-  long total = (long)N * H * W * 8;
-  int K = C * KH * KW;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    int g = i & 7;
-    long pix = i >> 3;
-    int x = pix % W;
-    long r = pix / W;
-    int y = r % H;
-    int n = r / H;
-    uint32_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float v[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        int k = g * 8 + j * 2 + e;
-        float val = 0.f;
-        if (k < K) {
-          int c = k / (KH * KW);
-          int t = k - c * KH * KW;
-          int kh = t / KW, kw = t - kh * KW;
-          int yy = y + kh - padH, xx = x + kw - padW;
-          if (yy >= 0 && yy < H && xx >= 0 && xx < W) val = __ldg(img + (((long)n * C + c) * H + yy) * W + xx);
-        }
-        v[e] = val;
-      }
-      __nv_bfloat162 t2 = __floats2bfloat162_rn(v[0], v[1]);
-      o[j] = *reinterpret_cast<uint32_t*>(&t2);
-    }
-    reinterpret_cast<uint4*>(patches)[i] = make_uint4(o[0], o[1], o[2], o[3]);
-  }
-}
-void launch_im2col_first(const float* img, bf16* patches, int N, int C, int H, int W, int KH, int KW, int padH, int padW,
-                         cudaStream_t st) {
-  long total = (long)N * H * W * 8;
-  im2col_first_kernel<<<min(cdiv(total, 256), 148 * 16), 256, 0, st>>>(img, patches, N, C, H, W, KH, KW, padH, padW);
 }
 
 // ------------------------------------------------------------------------------------------ 2x2 ceil max pool

@@ -180,12 +180,18 @@ int frcnn_last_conv_profile(const frcnn_ctx* ctx, float* ms, double* flops, int*
 
 /* ---- low-level conv / GEMM entry (tests, roofline measurement) ---------------------------------------- */
 /* y = prelu(conv(x, w) + bias) * scale on NHWC bf16 activations (passed as uint16 bit patterns).
- * x_dev: [n][h][w][cin]; w_dev: fp32 Torch layout [cout][cin][k][k]; out_dev: [n][ho][wo][cout] bf16.
- * splits > 1 exercises the split-K fp32-atomic path; bn in {0 (auto), 64, 128, 192, 256}.
- * elapsed_ms (optional) receives the device time of `iters` back-to-back launches of the conv kernel alone. */
+ * x_dev: [n][h][w][cin]; w_dev: fp32 Torch layout [cout][cin][k][k]; out_dev: [n][ho][wo][cout] bf16, or with
+ * pool != 0 the 2x2 stride-2 ceil-mode max-pooled map [n][ceil(ho/2)][ceil(wo/2)][cout] (model_utilities.lua:23).
+ * splits > 1 exercises the split-K fp32-atomic path; bn in {0 (auto), 64, 128, 192, 256}; mt in {0 (auto), 1, 2} =
+ * 128-row sub-tiles per CTA.  elapsed_ms (optional) receives the device time of `iters` back-to-back launches of
+ * the conv kernel alone. */
 int frcnn_conv_bf16(frcnn_ctx* ctx, const uint16_t* x_dev, const float* w_dev, const float* bias_dev,
                     const float* prelu_dev, float scale, int n, int h, int w, int cin, int cout, int k, int pad,
-                    int splits, int bn, uint16_t* out_dev, int iters, float* elapsed_ms);
+                    int splits, int bn, int mt, int pool, uint16_t* out_dev, int iters, float* elapsed_ms);
+/* The fused first layer: img_dev [n][3][h][w] fp32 (Torch layout), w_dev [cout = 64][3][3][3] fp32; output as above. */
+int frcnn_conv_first(frcnn_ctx* ctx, const float* img_dev, const float* w_dev, const float* bias_dev,
+                     const float* prelu_dev, float scale, int n, int h, int w, int cout, int pad, int pool,
+                     uint16_t* out_dev, int iters, float* elapsed_ms);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ from oracle import model as OM
 pytestmark = pytest.mark.gpu
 
 
-def _conv_case(F, model, n, h, w, cin, cout, k, pad, splits=0, bn=0, prelu=True, scale=1.0, seed=0):
+def _conv_case(F, model, n, h, w, cin, cout, k, pad, splits=0, bn=0, prelu=True, scale=1.0, seed=0, mt=0, pool=False):
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(n, cin, h, w, generator=g)
     wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
@@ -27,14 +27,17 @@ def _conv_case(F, model, n, h, w, cin, cout, k, pad, splits=0, bn=0, prelu=True,
     ref = ref * scale
     x_nhwc = xq.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16).cuda()
     ho, wo = h + 2 * pad - k + 1, w + 2 * pad - k + 1
-    out = torch.empty(n, ho, wo, cout, dtype=torch.bfloat16, device="cuda")
+    if pool:  # nn.SpatialMaxPooling(2,2,2,2):ceil() fused into the epilogue
+        ref = TF.max_pool2d(ref, 2, 2, ceil_mode=True)
+        ho, wo = (ho + 1) // 2, (wo + 1) // 2
+    out = torch.full((n, ho, wo, cout), float("nan"), dtype=torch.bfloat16, device="cuda")
     wd, bd, sd = wt.cuda(), bias.cuda(), slope.cuda()
     ffi, L = F.ffi, F.lib()
     ms = ffi.new("float*")
     rc = L.frcnn_conv_bf16(model.ctx, ffi.cast("const uint16_t*", x_nhwc.data_ptr()), ffi.cast("const float*", wd.data_ptr()),
                            ffi.cast("const float*", bd.data_ptr()),
                            ffi.cast("const float*", sd.data_ptr()) if prelu else ffi.NULL, scale, n, h, w, cin, cout, k, pad,
-                           splits, bn, ffi.cast("uint16_t*", out.data_ptr()), 1, ms)
+                           splits, bn, mt, 1 if pool else 0, ffi.cast("uint16_t*", out.data_ptr()), 1, ms)
     assert rc == 0, ffi.string(L.frcnn_last_error(model.ctx))
     got = out.float().cpu().permute(0, 3, 1, 2)
     err = (got - ref).abs()
@@ -69,6 +72,51 @@ def test_conv_epilogue_variants(F, small_model):
     _conv_case(F, small_model, 1, 24, 24, 64, 64, 3, 1, scale=0.6)
 
 
+@pytest.mark.parametrize("case", [
+    # n, h, w, cin, cout, k, pad  -- even / odd map sizes (ceil-mode windows clipped at the border), all tile widths
+    (1, 16, 16, 64, 64, 3, 1), (1, 29, 51, 128, 128, 3, 1), (2, 57, 100, 128, 256, 3, 1), (1, 113, 200, 64, 128, 3, 1),
+    (1, 57, 99, 256, 384, 3, 1), (1, 225, 400, 64, 128, 3, 1), (3, 9, 7, 64, 192, 3, 1), (1, 75, 125, 256, 512, 3, 1),
+])
+def test_conv_fused_pool(F, small_model, case):
+    _conv_case(F, small_model, *case, seed=sum(case), pool=True)
+
+
+@pytest.mark.parametrize("pool", [False, True])
+@pytest.mark.parametrize("case", [(1, 64, 64, 64, 128, 3, 1), (2, 113, 200, 128, 128, 3, 1), (1, 45, 77, 64, 64, 3, 1)])
+def test_conv_two_subtiles_per_cta(F, small_model, case, pool):
+    """MT = 2: CTA tiles of 256 pixels sharing one weight tile (the narrow, L2-bound layers)."""
+    _conv_case(F, small_model, *case, seed=sum(case) + 1, mt=2, pool=pool)
+
+
+@pytest.mark.parametrize("pool", [False, True])
+@pytest.mark.parametrize("n,h,w", [(1, 16, 16), (1, 450, 800), (2, 123, 77), (1, 61, 96)])
+def test_conv_first_layer(F, small_model, n, h, w, pool):
+    """The fused first layer (in-kernel im2col of the fp32 NCHW frame, K = 27) against conv2d on bf16-rounded
+    operands."""
+    g = torch.Generator().manual_seed(h + w + n)
+    x = torch.randn(n, 3, h, w, generator=g)
+    wt = torch.randn(64, 3, 3, 3, generator=g) * (2.0 / 27) ** 0.5
+    bias = torch.randn(64, generator=g) * 0.1
+    slope = torch.tensor([0.2])
+    ref = TF.conv2d(OM.bf16_round(x), OM.bf16_round(wt), bias, padding=1)
+    ref = torch.where(ref > 0, ref, ref * slope)
+    ho, wo = h, w
+    if pool:
+        ref = TF.max_pool2d(ref, 2, 2, ceil_mode=True)
+        ho, wo = (h + 1) // 2, (w + 1) // 2
+    out = torch.full((n, ho, wo, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    xd, wd, bd, sd = x.cuda(), wt.cuda(), bias.cuda(), slope.cuda()
+    ffi, L = F.ffi, F.lib()
+    rc = L.frcnn_conv_first(small_model.ctx, ffi.cast("const float*", xd.data_ptr()), ffi.cast("const float*", wd.data_ptr()),
+                            ffi.cast("const float*", bd.data_ptr()), ffi.cast("const float*", sd.data_ptr()), 1.0, n, h, w, 64, 1,
+                            1 if pool else 0, ffi.cast("uint16_t*", out.data_ptr()), 1, ffi.NULL)
+    assert rc == 0, ffi.string(L.frcnn_last_error(small_model.ctx))
+    got = out.float().cpu().permute(0, 3, 1, 2)
+    err = (got - ref).abs()
+    tol = 1e-2 * ref.abs() + 1e-2 * ref.abs().max()
+    assert bool((err <= tol).all()), "max err %g at ref max %g" % (err.max(), ref.abs().max())
+
+
 def test_conv_exact_integers(F, small_model):
     """Small-integer operands are exact in bf16 and in fp32 accumulation: the result must be bit-identical to the
     reference convolution -- catches any tap / channel / swizzle mis-addressing that tolerances could hide."""
@@ -84,7 +132,7 @@ def test_conv_exact_integers(F, small_model):
     wd, bd = wt.cuda(), bias.cuda()
     ffi, L = F.ffi, F.lib()
     rc = L.frcnn_conv_bf16(small_model.ctx, ffi.cast("const uint16_t*", x_nhwc.data_ptr()), ffi.cast("const float*", wd.data_ptr()),
-                           ffi.cast("const float*", bd.data_ptr()), ffi.NULL, 1.0, n, h, w, cin, cout, k, pad, 0, 0,
+                           ffi.cast("const float*", bd.data_ptr()), ffi.NULL, 1.0, n, h, w, cin, cout, k, pad, 0, 0, 0, 0,
                            ffi.cast("uint16_t*", out.data_ptr()), 1, ffi.NULL)
     assert rc == 0
     got = out.float().cpu().permute(0, 3, 1, 2)
