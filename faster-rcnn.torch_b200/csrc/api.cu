@@ -40,7 +40,7 @@ struct Head {
   int kW, n, input;
   ConvLayer conv;
   int p_w2, p_b2;
-  float* acc = nullptr;      // [N][hh][hw][n] fp32 split-K sums
+  float* acc = nullptr;      // [splits * N][hh][hw][n] fp32 split-K slices
   float* out = nullptr;      // [N][18][hh][hw] fp32
   int hh = 0, hw = 0;
 };
@@ -472,18 +472,32 @@ static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
     c->pool_h[b] = h; c->pool_w[b] = w;
   }
   c->feat_h = h; c->feat_w = w;
+  // anchor heads: ONE grouped conv launch with deterministic split-K slices, sized so that all work units of all
+  // heads have similar K length and there are about two units per SM
+  long total_k = 0;
   for (auto& hd : c->heads) {
     const int ih = c->pool_h[hd.input - 1], iw = c->pool_w[hd.input - 1];
     FRCNN_REQUIRE(ih >= hd.kW && iw >= hd.kW, FRCNN_E_INVALID, "image too small for the anchor networks");
     hd.hh = ih - hd.kW + 1; hd.hw = iw - hd.kW + 1;
     FRCNN_REQUIRE(hd.hh <= LUT_EXTENT && hd.hw <= LUT_EXTENT, FRCNN_E_INVALID,
                   "feature map exceeds the 200-cell anchor LUT (Anchors.lua:15)");
-    hd.acc = (float*)dev_alloc(c->ws_allocs, (size_t)N * hd.hh * hd.hw * hd.n * sizeof(float));
-    hd.out = (float*)dev_alloc(c->ws_allocs, (size_t)N * 18 * hd.hh * hd.hw * sizeof(float));
+    FRCNN_REQUIRE(hd.n == 256, FRCNN_E_INVALID, "anchor net width must be 256 (models/vgg_*.lua)");
+    const long tiles = (long)N * ((hd.hh * hd.hw + 127) / 128);
+    total_k += tiles * hd.kW * hd.kW * (hd.conv.cin / 64);
+  }
+  const long k_target = std::max<long>(16, (total_k + 2L * c->sm_count - 1) / (2L * c->sm_count));
+  for (auto& hd : c->heads) {
+    const int ih = c->pool_h[hd.input - 1], iw = c->pool_w[hd.input - 1];
+    const int k_iters = hd.kW * hd.kW * (hd.conv.cin / 64);
+    int splits = (int)((k_iters + k_target / 2) / k_target);
+    splits = std::max(1, std::min(splits, std::max(1, k_iters / 8)));
     hd.conv.hin = ih; hd.conv.win = iw; hd.conv.hout = hd.hh; hd.conv.wout = hd.hw;
     conv_prepare(&hd.conv.launch, c->pool_out[hd.input - 1], hd.conv.w_packed, N, ih, iw, hd.conv.cin, hd.conv.cout, hd.kW,
-                 hd.kW, 0, 0, EPI_F32_ATOMIC, nullptr, c->sm_count, 0, 0, 0);
-    hd.conv.launch.p.out_f32 = hd.acc;
+                 hd.kW, 0, 0, EPI_F32_SLICES, nullptr, c->sm_count, splits, 256, 1);
+    const size_t slices = (size_t)hd.conv.launch.p.splits * N;
+    hd.acc = (float*)dev_alloc(c->ws_allocs, slices * hd.hh * hd.hw * hd.n * sizeof(float));
+    hd.out = (float*)dev_alloc(c->ws_allocs, (size_t)N * 18 * hd.hh * hd.hw * sizeof(float));
+    conv_set_f32_output(&hd.conv.launch, hd.acc);
   }
   c->ws_n = N; c->ws_h = H; c->ws_w = W;
 }
@@ -507,7 +521,30 @@ static void conv_launch_timed(frcnn_ctx* c, const ConvLaunch& L, long rows = -1)
     cudaEventRecord(c->conv_ev[c->conv_ev_used + 1], c->stream);
     c->conv_ev_used += 2;
     const double M = rows >= 0 ? (double)rows : (double)L.p.N * L.p.Hout * L.p.Wout;
-    c->conv_flops += 2.0 * M * L.p.Cout * (double)L.p.KH * L.p.KW * L.p.Cin;
+    c->conv_flops += 2.0 * M * L.p.Cout * (double)L.p.KH * L.p.KW * (L.first ? L.p.Cimg : L.p.Cin);
+  }
+}
+static void conv_group_launch_timed(frcnn_ctx* c, const ConvLaunch* const* Ls, int n) {
+  const bool prof = c->profiling;
+  if (prof) {
+    if ((int)c->conv_ev.size() < c->conv_ev_used + 2) {
+      cudaEvent_t a, b;
+      FRCNN_CUDA_TRY(cudaEventCreate(&a));
+      FRCNN_CUDA_TRY(cudaEventCreate(&b));
+      c->conv_ev.push_back(a);
+      c->conv_ev.push_back(b);
+    }
+    cudaEventRecord(c->conv_ev[c->conv_ev_used], c->stream);
+  }
+  conv_launch_group(Ls, n, c->sm_count, c->stream);
+  ++c->launches;
+  if (prof) {
+    cudaEventRecord(c->conv_ev[c->conv_ev_used + 1], c->stream);
+    c->conv_ev_used += 2;
+    for (int i = 0; i < n; ++i) {
+      const ConvParams& p = Ls[i]->p;
+      c->conv_flops += 2.0 * (double)p.N * p.Hout * p.Wout * p.Cout * (double)p.KH * p.KW * p.Cin;
+    }
   }
 }
 static void conv_profile_begin(frcnn_ctx* c) {
@@ -542,16 +579,35 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
       if (cv.first) cv.launch.p.img = img_dev;
       run_conv(c, cv);
     }
+  }
+  // anchor heads (model_utilities.lua:29-35,51-54): one grouped split-K conv launch, heaviest units first, then one
+  // grouped tail launch
+  {
+    std::vector<const ConvLaunch*> order;
     for (auto& hd : c->heads) {
-      if (hd.input != (int)b + 1) continue;
-      FRCNN_CUDA_TRY(cudaMemsetAsync(hd.acc, 0, (size_t)N * hd.hh * hd.hw * hd.n * sizeof(float), c->stream));
       hd.conv.launch.p.bias = nullptr;
       hd.conv.launch.p.prelu = nullptr;
-      conv_launch_timed(c, hd.conv.launch);
-      launch_head_tail(hd.acc, P(c, hd.conv.p_b), P(c, hd.conv.p_prelu), P(c, hd.p_w2), P(c, hd.p_b2), hd.out, N, hd.hh, hd.hw,
-                       hd.n, 18, c->stream);
-      ++c->launches;
+      order.push_back(&hd.conv.launch);
     }
+    std::stable_sort(order.begin(), order.end(),
+                     [](const ConvLaunch* a, const ConvLaunch* b) { return a->p.k_per_split > b->p.k_per_split; });
+    conv_group_launch_timed(c, order.data(), (int)order.size());
+    HeadTailGroup tg;
+    tg.n = (int)c->heads.size();
+    for (int i = 0; i < tg.n; ++i) {
+      Head& hd = c->heads[i];
+      HeadTail& t = tg.h[i];
+      t.ws = hd.acc;
+      t.splits = hd.conv.launch.p.splits;
+      t.npix = (long)N * hd.hh * hd.hw;
+      t.slice_stride = t.npix * hd.n;
+      t.HW = hd.hh * hd.hw;
+      t.bias = P(c, hd.conv.p_b); t.prelu = P(c, hd.conv.p_prelu); t.w2 = P(c, hd.p_w2); t.b2 = P(c, hd.p_b2);
+      t.out = hd.out;
+      t.block_end = 0;
+    }
+    launch_head_tail_group(tg, c->sm_count, c->stream);
+    ++c->launches;
   }
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
@@ -611,9 +667,10 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
     // split-K sized for the detector's typical few hundred ROIs: 8 K-iterations per split
     int k_iters = f.nin / 64;
     int splits = std::max(1, k_iters / 8);
-    conv_prepare(&f.launch, in, f.w_packed, 1, 1, R, f.nin, f.nout, 1, 1, 0, 0, EPI_F32_ATOMIC, nullptr, c->sm_count, splits, 0, 0);
-    f.launch.p.out_f32 = f.acc;
+    conv_prepare(&f.launch, in, f.w_packed, 1, 1, R, f.nin, f.nout, 1, 1, 0, 0, EPI_F32_REDUCE, nullptr, c->sm_count, splits, 0, 0);
+    conv_set_f32_output(&f.launch, f.acc);
     f.launch.p.m_limit = c->flags + 2;  // roi_total
+    f.launch.p.dyn_ctas = c->sm_count;  // split-K factor chosen on the device from the live row count
     in = f.out_bf16;
   }
   // NMS workspace: segments = max(N images, N * classes)
@@ -1301,12 +1358,12 @@ int frcnn_conv_bf16(frcnn_ctx* c, const uint16_t* x_dev, const float* w_dev, con
   frcnn::ConvLaunch L;
   const bool split = splits > 1;
   frcnn::conv_prepare(&L, (const frcnn::bf16*)x_dev, wp, n, h, w, cin, cout, k, k, pad, pad,
-                      split ? frcnn::EPI_F32_ATOMIC : (pool ? frcnn::EPI_POOL : frcnn::EPI_STORE), (frcnn::bf16*)out_dev, c->sm_count,
+                      split ? frcnn::EPI_F32_REDUCE : (pool ? frcnn::EPI_POOL : frcnn::EPI_STORE), (frcnn::bf16*)out_dev, c->sm_count,
                       split ? splits : 0, bn, mt);
   L.p.bias = split ? nullptr : bias_dev;
   L.p.prelu = split ? nullptr : prelu_dev;
   L.p.scale = scale;
-  L.p.out_f32 = acc;
+  if (split) frcnn::conv_set_f32_output(&L, acc);
   if (iters < 1) iters = 1;
   cudaEvent_t e0, e1;
   FRCNN_CUDA_TRY(cudaEventCreate(&e0));

@@ -41,9 +41,12 @@ void set_global_error(const std::string& msg);
 // ------------------------------------------------------------------ conv / GEMM kernel interface
 enum ConvEpilogue {
   EPI_STORE = 0,       // y = prelu(acc + bias) * scale -> bf16 NHWC, staged in shared memory, written by TMA store
-  EPI_F32_ATOMIC = 1,  // split-K partial sums, red.global.add.f32 into a zeroed fp32 [pixels][Cout] workspace
+  EPI_F32_REDUCE = 1,  // split-K partial sums added into a zeroed fp32 NHWC buffer [N][Hout][Wout][Cout] by TMA
+                       // tensor reductions (cp.reduce.async.bulk.tensor .add); summation order not reproducible
   EPI_POOL = 2,        // as EPI_STORE followed by the 2x2 stride-2 ceil-mode max pool (model_utilities.lua:23):
                        // only the pooled map is written
+  EPI_F32_SLICES = 3,  // deterministic split-K: raw fp32 partial sums, split s of image n -> slice [s * N + n] of an
+                       // fp32 NHWC workspace [splits * N][Hout][Wout][Cout] (TMA store); summed by the consumer
 };
 
 struct ConvParams {
@@ -61,8 +64,9 @@ struct ConvParams {
   const float* bias;        // [Cout] or null
   const float* prelu;       // device pointer to the shared slope, or null (identity)
   float scale;              // post-activation scale (SpatialDropout eval factor), 1 if none
-  float* out_f32;           // EPI_F32_ATOMIC
   const int* m_limit;       // optional device int: tiles whose first row >= *m_limit are skipped (GEMM rows)
+  int dyn_ctas;             // with m_limit: > 0 = choose the split-K factor on the device so that the tiles of the
+                            // *m_limit live rows fill dyn_ctas CTAs (host `splits` is then the upper bound)
   const float* img;         // first-layer kernel only: [N][Cimg][Hin][Win] fp32 input frames (Torch layout)
   int Cimg;                 // first-layer kernel only: image channels (3); K = Cimg * KH * KW <= 32
 };
@@ -78,6 +82,18 @@ struct ConvLaunch {
   int grid;
 };
 
+// Several independent convolutions executed by ONE launch of the conv kernel (the four anchor heads): work units
+// (conv g, tile, split) are enumerated conv by conv and dealt round-robin to the persistent CTAs.
+static constexpr int MAX_GROUP = 4;
+struct ConvGroup {
+  ConvParams p[MAX_GROUP];
+  int unit_end[MAX_GROUP];  // exclusive prefix of the unit counts
+  int n;
+};
+struct ConvMaps {
+  CUtensorMap a[MAX_GROUP], b[MAX_GROUP], o[MAX_GROUP];
+};
+
 // Host helpers (conv_igemm.cu)
 void conv_choose_tile(int Hout, int Wout, int* BW, int* BH);
 void make_tmap_act(CUtensorMap* m, const bf16* base, int N, int H, int W, int C, int BW, int BH);
@@ -89,6 +105,10 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
 void conv_first_prepare(ConvLaunch* L, const bf16* w_packed32, int N, int Hin, int Win, int Cimg, int Cout, int KH,
                         int KW, int padH, int padW, int mode, bf16* out, int num_sms);
 void conv_launch(const ConvLaunch& L, cudaStream_t st);
+// all members: same BN, MT == 1, not the first-layer kernel; pass them heaviest (longest K per unit) first
+void conv_launch_group(const ConvLaunch* const* Ls, int n, int num_sms, cudaStream_t st);
+// fp32 output map: EPI_F32_SLICES: ws is [splits * N][Hout][Wout][Cout]; EPI_F32_REDUCE: [N][Hout][Wout][Cout]
+void conv_set_f32_output(ConvLaunch* L, float* ws);
 int conv_smem_bytes(int BN);
 
 // ------------------------------------------------------------------ element kernels (elementwise.cu)
@@ -96,8 +116,22 @@ void launch_pack_conv_weight(const float* w, bf16* out, int Cout, int Cin, int K
 void launch_pack_first_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st);
 void launch_pack_fc_weight(const float* w, bf16* out, int nout, int C, int bins, int permute, cudaStream_t st);
 void launch_maxpool2x2(const bf16* in, bf16* out, int N, int H, int W, int C, cudaStream_t st);
-void launch_head_tail(const float* acc, const float* bias, const float* prelu, const float* w2, const float* b2,
-                      float* out_chw, int N, int H, int W, int Cmid, int Cout2, cudaStream_t st);
+// AnchorNetwork tails of all heads in one launch (mid width 256, 18 outputs: model_utilities.lua:29-35)
+struct HeadTail {
+  const float* ws;      // [splits][npix][256] fp32 split-K slices of the k x k conv
+  int splits;
+  long slice_stride;    // npix * 256
+  long npix;            // N * H * W
+  int HW;
+  const float *bias, *prelu, *w2, *b2;
+  float* out;           // [N][18][H][W] fp32
+  int block_end;        // filled by the launcher
+};
+struct HeadTailGroup {
+  HeadTail h[4];
+  int n;
+};
+void launch_head_tail_group(const HeadTailGroup& g, int num_sms, cudaStream_t st);
 void launch_nhwc_bf16_to_chw_f32(const bf16* in, float* out, int N, int H, int W, int C, cudaStream_t st);
 void launch_chw_f32_to_nhwc_bf16(const float* in, bf16* out, int N, int H, int W, int C, cudaStream_t st);
 void launch_fc_tail(const float* acc, const float* bias, const float* bn_w, const float* bn_b, const float* bn_mean,

@@ -57,10 +57,10 @@ struct TileCoord {
   int n_img, h0, w0, n0, k_begin, k_end, m0;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int BN) {
+__device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, int BN, int splits, int k_per_split) {
   TileCoord t;
-  int ks = tile % p.splits;
-  int r = tile / p.splits;
+  int ks = tile % splits;
+  int r = tile / splits;
   int nt = r % p.n_tiles_n;
   int mt = r / p.n_tiles_n;
   int tw = mt % p.tiles_w;
@@ -70,34 +70,74 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
   t.h0 = th * p.BH * p.MT;
   t.w0 = tw * p.BW;
   t.n0 = nt * BN;
-  t.k_begin = ks * p.k_per_split;
-  t.k_end = min(p.k_iters, t.k_begin + p.k_per_split);
+  t.k_begin = ks * k_per_split;
+  t.k_end = min(p.k_iters, t.k_begin + k_per_split);
   t.m0 = t.w0;  // first GEMM row of the tile; only used with m_limit (GEMM use: BH == 1, N == 1, tiles_h == 1)
   return t;
+}
+
+// Per-conv schedule values every warp role derives identically at kernel start.
+struct GroupSched {
+  int m_limit[MAX_GROUP];
+  int splits[MAX_GROUP];
+  int kps[MAX_GROUP];
+};
+__device__ __forceinline__ void make_sched(const ConvGroup& grp, int BN, GroupSched& sc) {
+#pragma unroll
+  for (int g = 0; g < MAX_GROUP; ++g) {
+    const ConvParams& p = grp.p[g];
+    const bool live = g < grp.n;
+    sc.m_limit[g] = (live && p.m_limit) ? *p.m_limit : 0x7fffffff;
+    sc.splits[g] = p.splits;
+    sc.kps[g] = p.k_per_split;
+    if (live && p.m_limit && p.dyn_ctas > 0) {
+      const int m_tiles = max(1, (sc.m_limit[g] + BLOCK_M - 1) / BLOCK_M);
+      int want = p.dyn_ctas / (m_tiles * p.n_tiles_n);
+      want = max(1, min(want, p.splits));
+      const int kps = (p.k_iters + want - 1) / want;
+      sc.kps[g] = kps;
+      sc.splits[g] = (p.k_iters + kps - 1) / kps;
+    }
+  }
+}
+// unit -> (conv index, tile coordinates); units of conv g are enumerated with its HOST split count (upper bound):
+// unit indices beyond the device-chosen count decode to tiles at or beyond m_limit and are skipped by every role
+__device__ __forceinline__ bool next_unit(const ConvGroup& grp, const GroupSched& sc, int unit, int BN, int& gi, TileCoord& t) {
+  gi = 0;
+  while (unit >= grp.unit_end[gi]) ++gi;
+  const int local = unit - (gi ? grp.unit_end[gi - 1] : 0);
+  const ConvParams& p = grp.p[gi];
+  if (local >= p.n_tiles_m * p.n_tiles_n * sc.splits[gi]) return false;
+  t = decode_tile(p, local, BN, sc.splits[gi], sc.kps[gi]);
+  return t.m0 < sc.m_limit[gi];
 }
 
 // ------------------------------------------------------------------------------------------------- epilogue
 // Runs on the four epilogue warps (warp & 3 = TMEM lane quarter).  tile_buf / pool_buf: 1024-byte aligned staging.
 template <int BN, int MT>
-__device__ __forceinline__ void epilogue_loop(const ConvParams& p, const CUtensorMap* tmOut, uint8_t* tile_buf,
+__device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtensorMap* tmOuts, uint8_t* tile_buf,
                                               uint8_t* pool_buf, const float* sbias, uint32_t tmem_base, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty, int total_tiles, int m_limit, int warp, int lane) {
+                                              uint64_t* tmem_empty, const GroupSched& sc, int warp, int lane) {
   const int q = warp & 3;
   const int row = q * 32 + lane;  // TMEM lane == pixel row of the sub-tile
-  const int dy = row >> p.bw_shift;
-  const int dx = row & (p.BW - 1);
-  const float slope = p.prelu ? __ldg(p.prelu) : 1.0f;
-  const bool has_prelu = p.prelu != nullptr;
   const bool store_thread = (row == 0);
   const uint32_t tile_addr = ptx::smem_u32(tile_buf);
   const uint32_t pool_addr = ptx::smem_u32(pool_buf);
   const uint32_t my_row_addr = tile_addr + row * 128;
   const int sw = row & 7;
+  const int total_units = grp.unit_end[grp.n - 1];
   int acc = 0;
   uint32_t acc_phase = 0;
-  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    TileCoord t = decode_tile(p, tile, BN);
-    if (t.m0 >= m_limit) continue;
+  for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    int gi;
+    TileCoord t;
+    if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+    const ConvParams& p = grp.p[gi];
+    const CUtensorMap* tmOut = tmOuts + gi;
+    const int dy = row >> p.bw_shift;
+    const int dx = row & (p.BW - 1);
+    const float slope = p.prelu ? __ldg(p.prelu) : 1.0f;
+    const bool has_prelu = p.prelu != nullptr;
     ptx::mbar_wait(&tmem_full[acc], acc_phase);
     ptx::tc_fence_after();
 #pragma unroll 1
@@ -106,18 +146,26 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, const CUtenso
       const int h = hbase + dy, w = t.w0 + dx;
       const bool valid = (h < p.Hout) && (w < p.Wout);
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN * MT + mt * BN) + ((uint32_t)(q * 32) << 16);
-      if (p.mode == EPI_F32_ATOMIC) {
-        const size_t pix = ((size_t)t.n_img * p.Hout + h) * p.Wout + w;
+      if (p.mode == EPI_F32_SLICES || p.mode == EPI_F32_REDUCE) {
+        // raw fp32 partial sums: 32 columns = one 128-byte staging row.  SLICES: plain store into slice
+        // split * N + image (deterministic); REDUCE: TMA tensor reduction (add) into the image's map
+        const int slice = p.mode == EPI_F32_SLICES ? (t.k_begin / sc.kps[gi]) * p.N + t.n_img : t.n_img;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(taddr + c0, v);
           ptx::tmem_ld_wait();
-          const int cbase = t.n0 + c0;
-          if (valid && cbase < p.Cout) {
-            float* dst = p.out_f32 + pix * p.Cout + cbase;
+          if (store_thread) ptx::tma_store_wait_read();
+          ptx::named_bar_sync(1, 128);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+          for (int c = 0; c < 8; ++c)
+            ptx::st_shared_v4(my_row_addr + ((c ^ sw) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          ptx::fence_proxy_async();
+          ptx::named_bar_sync(1, 128);
+          if (store_thread) {
+            if (p.mode == EPI_F32_SLICES) ptx::tma_store_4d(tmOut, tile_buf, t.n0 + c0, t.w0, hbase, slice);
+            else ptx::tma_reduce_add_4d(tmOut, tile_buf, t.n0 + c0, t.w0, hbase, slice);
+            ptx::tma_store_commit();
           }
         }
       } else {
@@ -203,8 +251,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvParams& p, const CUtenso
 // ------------------------------------------------------------------------------------------------- main kernel
 template <int BN, int MT>
 __global__ void __launch_bounds__(256, 1)
-    conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const __grid_constant__ CUtensorMap tmOut, const ConvParams p) {
+    conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGroup grp) {
   constexpr int STAGES = conv_stages(BN, MT);
   constexpr int A_STAGE_BYTES = MT * A_SUB_BYTES;
   constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
@@ -227,13 +274,17 @@ __global__ void __launch_bounds__(256, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.n_tiles_m * p.n_tiles_n * p.splits;
-  const int m_limit = p.m_limit ? *p.m_limit : 0x7fffffff;
+  const int total_units = grp.unit_end[grp.n - 1];
+  GroupSched sc;
+  make_sched(grp, BN, sc);
+  const ConvParams& p0 = grp.p[0];
 
   if (warp == 0 && lane == 0) {
-    ptx::tma_prefetch_desc(&tmA);
-    ptx::tma_prefetch_desc(&tmB);
-    if (p.mode != EPI_F32_ATOMIC) ptx::tma_prefetch_desc(&tmOut);
+    for (int g = 0; g < grp.n; ++g) {
+      ptx::tma_prefetch_desc(&maps.a[g]);
+      ptx::tma_prefetch_desc(&maps.b[g]);
+      ptx::tma_prefetch_desc(&maps.o[g]);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -250,9 +301,10 @@ __global__ void __launch_bounds__(256, 1)
     ptx::tmem_alloc(tmem_base_slot, TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  if (p.mode != EPI_F32_ATOMIC) {
-    // parameter pointers are views into Torch's flat weight buffer at arbitrary 4-byte offsets: scalar loads
-    for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+  if (p0.mode == EPI_STORE || p0.mode == EPI_POOL) {
+    // (single-conv launches only) parameter pointers are views into Torch's flat weight buffer at arbitrary
+    // 4-byte offsets: scalar loads
+    for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (p0.bias && i < p0.Cout) ? p0.bias[i] : 0.f;
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -264,9 +316,13 @@ __global__ void __launch_bounds__(256, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        TileCoord t = decode_tile(p, tile, BN);
-        if (t.m0 >= m_limit) continue;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        int gi;
+        TileCoord t;
+        if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+        const ConvParams& p = grp.p[gi];
+        const CUtensorMap& tmA = maps.a[gi];
+        const CUtensorMap& tmB = maps.b[gi];
         for (int k = t.k_begin; k < t.k_end; ++k) {
           int tap = k / p.cchunks;
           int cc = k - tap * p.cchunks;
@@ -291,9 +347,10 @@ __global__ void __launch_bounds__(256, 1)
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        TileCoord t = decode_tile(p, tile, BN);
-        if (t.m0 >= m_limit) continue;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        int gi;
+        TileCoord t;
+        if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN * MT;
@@ -326,7 +383,7 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
   } else if (warp >= 4) {
-    epilogue_loop<BN, MT>(p, &tmOut, tile_buf, pool_buf, sbias, tmem_base, tmem_full, tmem_empty, total_tiles, m_limit, warp, lane);
+    epilogue_loop<BN, MT>(grp, maps.o, tile_buf, pool_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp, lane);
   }
 
   ptx::tc_fence_before();
@@ -346,8 +403,10 @@ static constexpr int FIRST_BN = 64;
 static constexpr int FIRST_SMEM = FIRST_STAGES * A_SUB_BYTES + FIRST_BN * 128 + SMEM_FIXED;
 
 __global__ void __launch_bounds__(384, 1)
-    conv_first_kernel(const __grid_constant__ CUtensorMap tmOut, const ConvParams p, const bf16* __restrict__ w32) {
+    conv_first_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvGroup grp,
+                      const bf16* __restrict__ w32) {
   constexpr int BN = FIRST_BN;
+  const ConvParams& p = grp.p[0];
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BN);
   constexpr int TMEM_COLS = 128;
   extern __shared__ uint8_t smem_raw[];
@@ -405,7 +464,7 @@ __global__ void __launch_bounds__(384, 1)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      TileCoord t = decode_tile(p, tile, BN);
+      TileCoord t = decode_tile(p, tile, BN, 1, 1);
       const int h = t.h0 + dy - p.padH, w = t.w0 + dx - p.padW;  // top-left tap in input coordinates
       const float* base = p.img + (size_t)t.n_img * 3 * plane;
       float v[27];
@@ -463,7 +522,9 @@ __global__ void __launch_bounds__(384, 1)
       }
     }
   } else if (warp >= 8) {
-    epilogue_loop<BN, 1>(p, &tmOut, tile_buf, pool_buf, sbias, tmem_base, tmem_full, tmem_empty, total_tiles, 0x7fffffff, warp, lane);
+    GroupSched sc;
+    make_sched(grp, BN, sc);
+    epilogue_loop<BN, 1>(grp, &tmOut, tile_buf, pool_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp, lane);
   }
 
   ptx::tc_fence_before();
@@ -568,16 +629,31 @@ static void make_out_map(ConvLaunch* L, bf16* out) {
   if (p.mode == EPI_STORE) make_tmap_act(&L->tmOut, out, p.N, p.Hout, p.Wout, p.Cout, p.BW, p.BH);
   else if (p.mode == EPI_POOL)
     make_tmap_act(&L->tmOut, out, p.N, (p.Hout + 1) / 2, (p.Wout + 1) / 2, p.Cout, p.BW / 2, p.BH / 2);
-  else L->tmOut = L->tmB;  // unused
+  else L->tmOut = L->tmB;  // unused (EPI_F32_REDUCE) or set later by conv_set_slices_output (EPI_F32_SLICES)
+}
+
+void conv_set_f32_output(ConvLaunch* L, float* ws) {
+  const ConvParams& p = L->p;
+  FRCNN_REQUIRE((p.mode == EPI_F32_SLICES || p.mode == EPI_F32_REDUCE) && ws != nullptr, FRCNN_E_INVALID,
+                "conv: not an fp32 split-K launch");
+  const int S = p.mode == EPI_F32_SLICES ? p.splits * p.N : p.N;
+  cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wout, (cuuint64_t)p.Hout, (cuuint64_t)S};
+  cuuint64_t strides[3] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)p.Wout * p.Cout * 4, (cuuint64_t)p.Hout * p.Wout * p.Cout * 4};
+  cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_encode()(&L->tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ws, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FRCNN_REQUIRE(r == CUDA_SUCCESS, FRCNN_E_CUDA, "cuTensorMapEncodeTiled(fp32 slices) failed, CUresult " + std::to_string((int)r));
 }
 
 void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
                   int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int force_splits, int force_bn,
                   int force_mt) {
   FRCNN_REQUIRE(Cin % 64 == 0, FRCNN_E_INVALID, "conv: Cin must be a multiple of 64");
-  FRCNN_REQUIRE(mode == EPI_F32_ATOMIC ? Cout % 32 == 0 : (Cout % 64 == 0 && Cout <= MAX_BIAS), FRCNN_E_INVALID,
+  const bool f32 = mode == EPI_F32_REDUCE || mode == EPI_F32_SLICES;
+  FRCNN_REQUIRE(f32 ? Cout % 32 == 0 : (Cout % 64 == 0 && Cout <= MAX_BIAS), FRCNN_E_INVALID,
                 "conv: Cout must be a multiple of 64 (<= 512) for the bf16 epilogues, of 32 for split-K");
-  FRCNN_REQUIRE(mode == EPI_F32_ATOMIC || out != nullptr, FRCNN_E_INVALID, "conv: null output");
+  FRCNN_REQUIRE(f32 || out != nullptr, FRCNN_E_INVALID, "conv: null output");
   int BN = force_bn > 0 ? force_bn : choose_bn(Cout);
   L->BN = BN;
   L->first = false;
@@ -586,7 +662,7 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
   // tiles left to fill the machine at least twice
   int MT = 1;
   if (force_mt > 0) MT = force_mt;
-  else if (mode != EPI_F32_ATOMIC && BN <= 128) {
+  else if (!f32 && BN <= 128) {
     long px = (long)N * (Hin + 2 * padH - KH + 1) * (Win + 2 * padW - KW + 1);
     if (px / 256 * ((Cout + BN - 1) / BN) >= 2L * num_sms) MT = 2;
   }
@@ -597,7 +673,7 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
   p.cchunks = Cin / 64;
   p.k_iters = KH * KW * p.cchunks;
   int splits = 1;
-  if (mode == EPI_F32_ATOMIC) {
+  if (mode == EPI_F32_REDUCE || mode == EPI_F32_SLICES) {
     if (force_splits > 0) {
       splits = force_splits;
     } else {
@@ -642,18 +718,38 @@ void conv_first_prepare(ConvLaunch* L, const bf16* w_packed32, int N, int Hin, i
 }
 
 template <int BN, int MT>
-static void launch_cfg(const ConvLaunch& L, cudaStream_t st) {
+static void launch_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
   static bool configured = false;
   int smem = conv_smem_bytes_mt(BN, MT);
   if (!configured) {
     FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  conv_igemm_kernel<BN, MT><<<L.grid, 256, smem, st>>>(L.tmA, L.tmB, L.tmOut, L.p);
+  conv_igemm_kernel<BN, MT><<<grid, 256, smem, st>>>(maps, grp);
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
+static void launch_key(int BN, int MT, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+  switch (BN * 10 + MT) {
+    case 641: launch_cfg<64, 1>(maps, grp, grid, st); break;
+    case 642: launch_cfg<64, 2>(maps, grp, grid, st); break;
+    case 1281: launch_cfg<128, 1>(maps, grp, grid, st); break;
+    case 1282: launch_cfg<128, 2>(maps, grp, grid, st); break;
+    case 1921: launch_cfg<192, 1>(maps, grp, grid, st); break;
+    case 2561: launch_cfg<256, 1>(maps, grp, grid, st); break;
+    default: throw Error{FRCNN_E_INVALID, "conv: unsupported (BN, MT)"};
+  }
+}
+
 void conv_launch(const ConvLaunch& L, cudaStream_t st) {
+  ConvGroup grp;
+  grp.n = 1;
+  grp.p[0] = L.p;
+  grp.unit_end[0] = L.p.n_tiles_m * L.p.n_tiles_n * L.p.splits;
+  for (int g = 1; g < MAX_GROUP; ++g) {
+    grp.p[g] = L.p;
+    grp.unit_end[g] = grp.unit_end[0];
+  }
   if (L.first) {
     static bool configured = false;
     if (!configured) {
@@ -661,20 +757,37 @@ void conv_launch(const ConvLaunch& L, cudaStream_t st) {
       configured = true;
     }
     FRCNN_REQUIRE(L.p.img != nullptr, FRCNN_E_STATE, "first-layer kernel: image pointer not set");
-    conv_first_kernel<<<L.grid, 384, FIRST_SMEM, st>>>(L.tmOut, L.p, L.w_first);
+    conv_first_kernel<<<L.grid, 384, FIRST_SMEM, st>>>(L.tmOut, grp, L.w_first);
     FRCNN_CUDA_TRY(cudaGetLastError());
     return;
   }
-  const int key = L.BN * 10 + L.p.MT;
-  switch (key) {
-    case 641: launch_cfg<64, 1>(L, st); break;
-    case 642: launch_cfg<64, 2>(L, st); break;
-    case 1281: launch_cfg<128, 1>(L, st); break;
-    case 1282: launch_cfg<128, 2>(L, st); break;
-    case 1921: launch_cfg<192, 1>(L, st); break;
-    case 2561: launch_cfg<256, 1>(L, st); break;
-    default: throw Error{FRCNN_E_INVALID, "conv: unsupported (BN, MT)"};
+  ConvMaps maps;
+  for (int g = 0; g < MAX_GROUP; ++g) {
+    maps.a[g] = L.tmA;
+    maps.b[g] = L.tmB;
+    maps.o[g] = L.tmOut;
   }
+  launch_key(L.BN, L.p.MT, maps, grp, L.grid, st);
+}
+
+void conv_launch_group(const ConvLaunch* const* Ls, int n, int num_sms, cudaStream_t st) {
+  FRCNN_REQUIRE(n >= 1 && n <= MAX_GROUP, FRCNN_E_INVALID, "conv group: 1..4 members");
+  ConvGroup grp;
+  ConvMaps maps;
+  grp.n = n;
+  int total = 0;
+  for (int g = 0; g < MAX_GROUP; ++g) {
+    const ConvLaunch& L = *Ls[g < n ? g : n - 1];
+    FRCNN_REQUIRE(!L.first && L.p.MT == 1 && L.BN == Ls[0]->BN, FRCNN_E_INVALID, "conv group: members must share BN, MT = 1");
+    FRCNN_REQUIRE(L.p.mode == EPI_F32_SLICES || L.p.mode == EPI_F32_REDUCE, FRCNN_E_INVALID, "conv group: fp32 epilogues only");
+    grp.p[g] = L.p;
+    maps.a[g] = L.tmA;
+    maps.b[g] = L.tmB;
+    maps.o[g] = L.tmOut;
+    if (g < n) total += L.p.n_tiles_m * L.p.n_tiles_n * L.p.splits;
+    grp.unit_end[g] = total;
+  }
+  launch_key(Ls[0]->BN, 1, maps, grp, total < num_sms ? total : num_sms, st);
 }
 
 }  // namespace frcnn

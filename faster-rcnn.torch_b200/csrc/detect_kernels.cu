@@ -63,18 +63,29 @@ __global__ void __launch_bounds__(256) rpn_decode_kernel(DecodeParams p) {
     if (w < warp) before += c;
     block_total += c;
   }
+  // Parallel look-back: every block publishes its own count (tagged with this launch's epoch) as soon as it is
+  // known; block `bid` sums the counts of blocks 0..bid-1, each thread polling a strided subset.  Blocks with a
+  // smaller ticket are already running (tickets are handed out in start order), so the waits terminate.
+  volatile unsigned long long* status = p.status + (long)img * p.nblocks;
+  if (threadIdx.x == 0) status[bid] = ((unsigned long long)p.epoch << 32) | (unsigned)block_total;
+  unsigned part = 0;
+  for (int b = threadIdx.x; b < bid; b += 256) {
+    unsigned long long v;
+    do {
+      v = status[b];
+    } while ((unsigned)(v >> 32) != p.epoch);
+    part += (unsigned)v;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+  __shared__ unsigned s_part[8];
+  if (lane == 0) s_part[warp] = part;
+  __syncthreads();
   if (threadIdx.x == 0) {
     unsigned excl = 0;
-    volatile unsigned long long* status = p.status + (long)img * p.nblocks;
-    if (bid > 0) {
-      unsigned long long v;
-      do {
-        v = status[bid - 1];
-      } while ((unsigned)(v >> 32) != p.epoch);
-      excl = (unsigned)v;
-    }
+#pragma unroll
+    for (int w = 0; w < 8; ++w) excl += s_part[w];
     const unsigned incl = excl + (unsigned)block_total;
-    status[bid] = ((unsigned long long)p.epoch << 32) | incl;
     s_excl = (int)excl;
     if (bid == p.nblocks - 1) {
       p.cand_count[img] = min((int)incl, p.cap);
@@ -357,56 +368,50 @@ void launch_group_by_class(const GroupParams& p, NmsWorkspace* ws, int N, cudaSt
 // ------------------------------------------------------------------------------------------------ winners
 // Detector.lua:125-136: winners = for each class, the picks of its NMS, in pick order.  Segments are ordered
 // (image, class), so an exclusive scan of the pick counts gives every winner its output slot.
-__global__ void __launch_bounds__(1024) assemble_kernel(AssembleParams p, NmsState st, int n_seg) {
-  __shared__ int s_off[1025];
-  __shared__ int s_carry;
-  if (threadIdx.x == 0) s_carry = 0;
+// One CTA per (image, class) segment: its output offset is the sum of the pick counts of all earlier segments.
+__global__ void __launch_bounds__(256) assemble_kernel(AssembleParams p, NmsState st, int n_seg) {
+  __shared__ int s_part[8];
+  __shared__ int s_start;
+  const int s = blockIdx.x;
+  int local = 0;
+  for (int i = threadIdx.x; i < s; i += blockDim.x) local += st.counts[i];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) local += __shfl_xor_sync(0xffffffffu, local, d);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = local;
   __syncthreads();
-  for (int s0 = 0; s0 < n_seg; s0 += 1024) {
-    const int s = s0 + threadIdx.x;
-    const int cnt = s < n_seg ? st.counts[s] : 0;
-    // inclusive scan over the chunk (Hillis-Steele in shared memory)
-    s_off[threadIdx.x] = cnt;
-    __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-      int v = threadIdx.x >= off ? s_off[threadIdx.x - off] : 0;
-      __syncthreads();
-      s_off[threadIdx.x] += v;
-      __syncthreads();
-    }
-    const int start = s_carry + s_off[threadIdx.x] - cnt;
-    const int chunk_total = s_off[1023];
-    if (s < n_seg) {
-      const int beg = st.seg_beg[s];
-      for (int k = 0; k < cnt; ++k) {
-        const int slot = start + k;
-        if (slot >= p.det_cap) break;
-        const int g = beg + st.pick[beg + k];
-        const int row = p.grow[g];
-        const int img = p.roi_img[row], cand = p.roi_cand[row];
-        const long ci = (long)img * p.cap + cand;
-        frcnn_detection d;
-        for (int e = 0; e < 4; ++e) {
-          d.r[e] = p.cand_r[ci * 4 + e];
-          d.r2[e] = p.fin_r2[(long)row * 4 + e];
-        }
-        d.p = p.cand_logp[ci];
-        d.confidence = p.fin_conf[row];
-        d.cls = p.fin_cls[row];
-        const int4 a = p.cand_anchor[ci];
-        d.layer = a.x; d.aspect = a.y; d.y = a.z; d.x = a.w;
-        d.image = img;
-        p.det[slot] = d;
-      }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) s_carry += chunk_total;
-    __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < 8; ++w) t += s_part[w];
+    s_start = t;
   }
-  if (threadIdx.x == 0) *p.n_det = s_carry;
+  __syncthreads();
+  const int start = s_start;
+  const int cnt = st.counts[s];
+  const int beg = st.seg_beg[s];
+  if (s == n_seg - 1 && threadIdx.x == 0) *p.n_det = start + cnt;
+  for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+    const int slot = start + k;
+    if (slot >= p.det_cap) break;
+    const int g = beg + st.pick[beg + k];
+    const int row = p.grow[g];
+    const int img = p.roi_img[row], cand = p.roi_cand[row];
+    const long ci = (long)img * p.cap + cand;
+    frcnn_detection d;
+    for (int e = 0; e < 4; ++e) {
+      d.r[e] = p.cand_r[ci * 4 + e];
+      d.r2[e] = p.fin_r2[(long)row * 4 + e];
+    }
+    d.p = p.cand_logp[ci];
+    d.confidence = p.fin_conf[row];
+    d.cls = p.fin_cls[row];
+    const int4 a = p.cand_anchor[ci];
+    d.layer = a.x; d.aspect = a.y; d.y = a.z; d.x = a.w;
+    d.image = img;
+    p.det[slot] = d;
+  }
 }
 void launch_assemble(const AssembleParams& p, NmsWorkspace* ws, int n_seg, cudaStream_t st) {
-  assemble_kernel<<<1, 1024, 0, st>>>(p, ws->st, n_seg);
+  assemble_kernel<<<n_seg, 256, 0, st>>>(p, ws->st, n_seg);
 }
 
 }  // namespace frcnn

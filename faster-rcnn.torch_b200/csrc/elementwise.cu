@@ -101,64 +101,115 @@ void launch_maxpool2x2(const bf16* in, bf16* out, int N, int H, int W, int C, cu
 }
 
 // ------------------------------------------------------------------------------------------ anchor-head tail
-// AnchorNetwork tail (model_utilities.lua:32-33): PReLU(acc + bias) followed by the 1x1 conv to 3*(2+4) = 18
-// channels, written in Torch layout [N][18][H][W] fp32.  acc: fp32 [N*H*W][Cmid] split-K sums.  One warp per
-// pixel; the 18 x Cmid matrix lives in shared memory; fp32 throughout.
-template <int COUT2>
-__global__ void head_tail_kernel(const float* __restrict__ acc, const float* __restrict__ bias, const float* __restrict__ prelu,
-                                 const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ out,
-                                 long npix, int HW, int Cmid) {
-  // parameter pointers are views into Torch's flat weight buffer (utilities.lua:136-147) at arbitrary 4-byte
-  // offsets: read them scalar-wise into shared memory, never with vector loads
-  extern __shared__ float sw[];  // [COUT2][Cmid] weights, then [Cmid] bias
-  float* sbias = sw + COUT2 * Cmid;
-  for (int i = threadIdx.x; i < COUT2 * Cmid; i += blockDim.x) sw[i] = w2[i];
-  for (int i = threadIdx.x; i < Cmid; i += blockDim.x) sbias[i] = bias[i];
+// AnchorNetwork tail (model_utilities.lua:32-33) for all anchor heads in one launch: sum of the split-K slices of
+// the k x k conv + bias -> PReLU -> 1x1 conv to 3*(2+4) = 18 channels, written in Torch layout [N][18][H][W] fp32.
+// fp32 throughout, fixed summation order (deterministic).  A warp handles 4 pixels at a time: every lane owns 8 of
+// the 256 mid channels, the 18 x 256 weights are read from shared memory once per 4 pixels, and the 72 partial
+// sums are reduced across the warp with a transposing butterfly (31 shuffles per 32 values).
+template <int NV>
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+  // after the loop lane l holds the warp-wide total of v[l]
+#pragma unroll
+  for (int off = 16, cnt = 16; off >= 1; off >>= 1, cnt >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt; ++i) {
+      const float send = upper ? v[i] : v[i + cnt];
+      const float keep = upper ? v[i + cnt] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(256) head_tail_group_kernel(HeadTailGroup g) {
+  constexpr int CO = 18, CM = 256;
+  extern __shared__ float sw[];  // [18][256] weights, [256] bias
+  float* sbias = sw + CO * CM;
+  int hi = 0;
+  while (hi + 1 < g.n && (int)blockIdx.x >= g.h[hi].block_end) ++hi;
+  const HeadTail& H = g.h[hi];
+  const int block0 = hi ? g.h[hi - 1].block_end : 0;
+  // parameter pointers are views into Torch's flat buffer at arbitrary 4-byte offsets: scalar loads
+  for (int i = threadIdx.x; i < CO * CM; i += blockDim.x) sw[i] = H.w2[i];
+  for (int i = threadIdx.x; i < CM; i += blockDim.x) sbias[i] = H.bias[i];
   __syncthreads();
-  const float slope = prelu[0];
-  int lane = threadIdx.x & 31;
-  long warp_global = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-  long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
-  for (long pix = warp_global; pix < npix; pix += nwarps) {
-    float part[COUT2];
+  const float slope = H.prelu[0];
+  const int lane = threadIdx.x & 31;
+  const long warp_idx = ((long)(blockIdx.x - block0) * blockDim.x + threadIdx.x) >> 5;
+  const long nwarps = ((long)(H.block_end - block0) * blockDim.x) >> 5;
+  for (long base = warp_idx * 4; base < H.npix; base += nwarps * 4) {
+    float part[CO][4];
 #pragma unroll
-    for (int o = 0; o < COUT2; ++o) part[o] = 0.f;
-    for (int c = lane * 4; c < Cmid; c += 128) {
-      float4 a = *reinterpret_cast<const float4*>(acc + pix * Cmid + c);
-      float4 b = *reinterpret_cast<const float4*>(sbias + c);
-      float h[4] = {a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w};
+    for (int o = 0; o < CO; ++o)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) h[e] = h[e] > 0.f ? h[e] : h[e] * slope;
+      for (int q = 0; q < 4; ++q) part[o][q] = 0.f;
 #pragma unroll
-      for (int o = 0; o < COUT2; ++o) {
-        const float* wr = sw + o * Cmid + c;
-        part[o] += h[0] * wr[0] + h[1] * wr[1] + h[2] * wr[2] + h[3] * wr[3];
+    for (int half = 0; half < 2; ++half) {
+      const int c = half * 128 + lane * 4;
+      const float4 b = *reinterpret_cast<const float4*>(sbias + c);
+      float4 hv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (base + q < H.npix) {
+          const float* src = H.ws + (base + q) * CM + c;
+          for (int s = 0; s < H.splits; ++s) {  // fixed order: deterministic
+            const float4 t = *reinterpret_cast<const float4*>(src + (size_t)s * H.slice_stride);
+            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+          }
+          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          a.x = a.x > 0.f ? a.x : a.x * slope;
+          a.y = a.y > 0.f ? a.y : a.y * slope;
+          a.z = a.z > 0.f ? a.z : a.z * slope;
+          a.w = a.w > 0.f ? a.w : a.w * slope;
+        }
+        hv[q] = a;
+      }
+#pragma unroll
+      for (int o = 0; o < CO; ++o) {
+        const float4 w = *reinterpret_cast<const float4*>(sw + o * CM + c);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) part[o][q] += hv[q].x * w.x + hv[q].y * w.y + hv[q].z * w.z + hv[q].w * w.w;
       }
     }
 #pragma unroll
-    for (int o = 0; o < COUT2; ++o) {
+    for (int grp = 0; grp < 3; ++grp) {
+      float v[32];
 #pragma unroll
-      for (int s = 16; s > 0; s >>= 1) part[o] += __shfl_xor_sync(0xffffffffu, part[o], s);
-    }
-    long n = pix / HW;
-    long hw = pix - n * HW;
-    if (lane < COUT2) {
-      float v = 0.f;
-#pragma unroll
-      for (int o = 0; o < COUT2; ++o)
-        if (lane == o) v = part[o];
-      out[(n * COUT2 + lane) * HW + hw] = v + b2[lane];
+      for (int i = 0; i < 32; ++i) {
+        const int idx = grp * 32 + i;
+        v[i] = idx < CO * 4 ? part[idx >> 2 < CO ? idx >> 2 : 0][idx & 3] : 0.f;
+      }
+      const float tot = warp_transpose_reduce<32>(v, lane);
+      const int idx = grp * 32 + lane;
+      const int o = idx >> 2, q = idx & 3;
+      const long pix = base + q;
+      if (o < CO && pix < H.npix) {
+        const long n = pix / H.HW, hw = pix - n * H.HW;
+        H.out[(n * CO + o) * H.HW + hw] = tot + H.b2[o];
+      }
     }
   }
 }
-void launch_head_tail(const float* acc, const float* bias, const float* prelu, const float* w2, const float* b2,
-                      float* out_chw, int N, int H, int W, int Cmid, int Cout2, cudaStream_t st) {
-  FRCNN_REQUIRE(Cout2 == 18, FRCNN_E_INVALID, "anchor head must have 18 outputs (model_utilities.lua:33)");
-  FRCNN_REQUIRE(Cmid % 128 == 0, FRCNN_E_INVALID, "anchor head width must be a multiple of 128");
-  long npix = (long)N * H * W;
-  int smem = 19 * Cmid * sizeof(float);
-  int blocks = min(cdiv(npix, 8), 148 * 4);
-  head_tail_kernel<18><<<blocks, 256, smem, st>>>(acc, bias, prelu, w2, b2, out_chw, npix, H * W, Cmid);
+void launch_head_tail_group(const HeadTailGroup& g_in, int num_sms, cudaStream_t st) {
+  HeadTailGroup g = g_in;
+  FRCNN_REQUIRE(g.n >= 1 && g.n <= 4, FRCNN_E_INVALID, "anchor head group: 1..4 heads");
+  // blocks per head proportional to its pixels (8 warps x 4 pixels per block iteration), at most ~4 blocks per SM
+  long total_px = 0;
+  for (int i = 0; i < g.n; ++i) total_px += g.h[i].npix;
+  const long budget = (long)num_sms * 4;
+  int end = 0;
+  for (int i = 0; i < g.n; ++i) {
+    long want = (g.h[i].npix + 31) / 32;
+    long share = (budget * g.h[i].npix + total_px - 1) / total_px;
+    long blocks = want < share ? want : share;
+    if (blocks < 1) blocks = 1;
+    end += (int)blocks;
+    g.h[i].block_end = end;
+  }
+  const int smem = 19 * 256 * sizeof(float);
+  head_tail_group_kernel<<<end, 256, smem, st>>>(g);
 }
 
 // ------------------------------------------------------------------------------------------ layout converters
