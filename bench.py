@@ -235,18 +235,10 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return F.reduce_timing(x, 0, world, dist if world > 1 else None, "cuda")[0]
 
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return F.reduce_timing(0, x, world, dist if world > 1 else None, "cuda")[1]
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -269,9 +261,11 @@ def run_b200(args):
         # shard the 21 class segments over the ranks: no collective
         perm, seg = OB.class_segments(n, 21, seed=0)
         boxes = OB.sweep_boxes(n, seed=0)[perm]
-        mine = [s for s in range(21) if s % world == rank]
+        mine = F.shard_segments(21, world, rank)
         parts = [boxes[seg[s]:seg[s + 1]] for s in mine]
         local_boxes = np.ascontiguousarray(np.concatenate(parts)) if parts else np.zeros((0, 4), np.float32)
+        pinned_boxes = torch.from_numpy(local_boxes).pin_memory()
+        local_boxes = pinned_boxes.numpy()
         local_seg = np.concatenate([[0], np.cumsum([len(p) for p in parts])]).astype(np.int64)
         m = F.vgg_small(F.duplo_cfg, device=local)
         bd = torch.from_numpy(local_boxes).cuda()
@@ -318,7 +312,8 @@ def run_b200(args):
     B = args.batch
     frames = torch.stack([OM.synthetic_frame(h, w, seed=100 * rank + s) for s in range(B)])
     frames_dev = frames.cuda()
-    frames_host = frames.numpy()
+    frames_pinned = frames.pin_memory()  # e2e leg: inputs start in page-locked host memory
+    frames_host = frames_pinned.numpy()
     n_det = ffi.new("int*")
     out = det._out
 

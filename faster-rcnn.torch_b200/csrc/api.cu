@@ -118,6 +118,7 @@ struct frcnn_ctx {
   int* pick1 = nullptr;
   int* count1 = nullptr;
   int* roi_base = nullptr;
+  int4* roi_rect = nullptr;
   bf16* roi_out = nullptr;
   int* roi_img = nullptr;
   int* roi_cand = nullptr;
@@ -643,6 +644,7 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
   const int bins = c->roi_kh * c->roi_kw;
   c->roi_out = (bf16*)dev_alloc(A, (size_t)R * bins * c->feat_c * sizeof(bf16));
   c->roi_img = (int*)dev_alloc(A, (size_t)R * sizeof(int));
+  c->roi_rect = (int4*)dev_alloc(A, (size_t)R * sizeof(int4));
   c->roi_cand = (int*)dev_alloc(A, (size_t)R * sizeof(int));
   const int ncls = c->class_count + 1;
   c->reg_out = (float*)dev_alloc(A, (size_t)R * 4 * sizeof(float));
@@ -761,13 +763,13 @@ static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, f
   FRCNN_CUDA_TRY(cudaMemcpyAsync(c->count1, c->nms.st.counts, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
   if (prof) cudaEventRecord(c->ev[2], st);
   // --- Detector.lua:91-98: ROI pooling of every candidate
-  launch_roi_base(c->count1, N, c->roi_base, c->flags + 2, c->roi_cap, st);
   RoiParams rp;
   rp.fmap = c->pool_out.back(); rp.FH = c->feat_h; rp.FW = c->feat_w; rp.C = c->feat_c; rp.kh = c->roi_kh; rp.kw = c->roi_kw;
   rp.loc = c->roi_loc;
   rp.cand_r = c->cand_r; rp.pick = c->pick1; rp.pick_count = c->count1; rp.roi_base = c->roi_base; rp.cap = c->cand_cap;
   rp.out = c->roi_out; rp.roi_img = c->roi_img; rp.roi_cand = c->roi_cand; rp.status = c->flags + 1;
-  launch_roi_pool_nhwc(rp, N, st);
+  rp.roi_base_out = c->roi_base; rp.roi_total = c->flags + 2; rp.total_cap = c->roi_cap; rp.roi_rect = c->roi_rect;
+  launch_roi_pool_nhwc(rp, N, c->sm_count, st);
   c->launches += 2;
   if (prof) cudaEventRecord(c->ev[3], st);
   // --- Detector.lua:101: cnet
@@ -1267,9 +1269,17 @@ int frcnn_detect(frcnn_ctx* c, const float* img_host, int n, int h, int w, frcnn
     FRCNN_CUDA_TRY(cudaMallocHost(&c->h_img, bytes));
     c->d_img_bytes = bytes;
   }
-  // Input:cuda() (Detector.lua:32): stage through pinned memory so the copy is a true async DMA
-  memcpy(c->h_img, img_host, bytes);
-  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_img, c->h_img, bytes, cudaMemcpyHostToDevice, c->stream));
+  // Input:cuda() (Detector.lua:32).  A page-locked caller buffer is DMA'd directly; pageable memory is staged
+  // through the ctx's pinned buffer so that the copy is a true asynchronous DMA either way.
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, img_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (pinned) {
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_img, img_host, bytes, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    memcpy(c->h_img, img_host, bytes);
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_img, c->h_img, bytes, cudaMemcpyHostToDevice, c->stream));
+  }
   frcnn::do_detect(c, c->d_img, n, h, w, det_host, cap, n_det);
   API_END(c)
 }

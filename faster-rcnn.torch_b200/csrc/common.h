@@ -64,6 +64,7 @@ struct ConvParams {
   const float* bias;        // [Cout] or null
   const float* prelu;       // device pointer to the shared slope, or null (identity)
   float scale;              // post-activation scale (SpatialDropout eval factor), 1 if none
+  void* out;                // EPI_STORE: bf16 NHWC [N][Hout][Wout][Cout]; EPI_POOL: its pooled map; fp32 modes: workspace
   const int* m_limit;       // optional device int: tiles whose first row >= *m_limit are skipped (GEMM rows)
   int dyn_ctas;             // with m_limit: > 0 = choose the split-K factor on the device so that the tiles of the
                             // *m_limit live rows fill dyn_ctas CTAs (host `splits` is then the upper bound)

@@ -38,10 +38,9 @@ static constexpr int BLOCK_M = 128;
 static constexpr int BLOCK_K = 64;                           // bf16 elements = 128 bytes = one swizzle row
 static constexpr int A_SUB_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB per 128-row sub-tile
 static constexpr int STAGE_TILE_BYTES = 128 * 128;           // epilogue staging: 128 px x 64 ch bf16
-static constexpr int STAGE_POOL_BYTES = 32 * 128;            // pooled 32 px x 64 ch
 static constexpr int MAX_BIAS = 512;
 static constexpr int SMEM_LIMIT = 227 * 1024;
-static constexpr int SMEM_FIXED = STAGE_TILE_BYTES + STAGE_POOL_BYTES + MAX_BIAS * 4 + 256 + 1024;
+static constexpr int SMEM_FIXED = STAGE_TILE_BYTES + MAX_BIAS * 4 + 256 + 1024;
 
 __host__ __device__ constexpr int stage_bytes(int BN, int MT) { return MT * A_SUB_BYTES + BN * BLOCK_K * 2; }
 __host__ __device__ constexpr int conv_stages(int BN, int MT) {
@@ -113,31 +112,44 @@ __device__ __forceinline__ bool next_unit(const ConvGroup& grp, const GroupSched
 }
 
 // ------------------------------------------------------------------------------------------------- epilogue
-// Runs on the four epilogue warps (warp & 3 = TMEM lane quarter).  tile_buf / pool_buf: 1024-byte aligned staging.
+// Runs on EIGHT epilogue warps (256 threads): warp e handles TMEM lane quarter (e & 3) -- thread = pixel row of the
+// 128-row sub-tile -- and the column half (e >> 2) of every 64-channel group.  With one epilogue warp per scheduler
+// the fixed-latency dependency stalls of the bias / PReLU / convert math paced every layer; two warps per
+// scheduler interleave.  tile_buf: 1024-byte aligned 16 KB staging tile of 128 rows x 128 bytes (64 bf16 or 32 fp32
+// channels of 128 pixels), 16-byte chunks XOR-swizzled by (row & 7) so that both the row-wise writes (thread =
+// pixel) and the chunk-wise reads (8 lanes = one 128-byte pixel segment) are bank-conflict free.  Output leaves
+// the SM as fully coalesced 128-byte segments written with plain 16-byte st.global by all 256 threads.
+static constexpr int EPI_THREADS = 256;
 template <int BN, int MT>
 __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtensorMap* tmOuts, uint8_t* tile_buf,
-                                              uint8_t* pool_buf, const float* sbias, uint32_t tmem_base, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty, const GroupSched& sc, int warp, int lane) {
-  const int q = warp & 3;
-  const int row = q * 32 + lane;  // TMEM lane == pixel row of the sub-tile
-  const bool store_thread = (row == 0);
+                                              const float* sbias, uint32_t tmem_base, uint64_t* tmem_full,
+                                              uint64_t* tmem_empty, const GroupSched& sc, int ewarp, int lane) {
+  const int q = ewarp & 3;
+  const int half = ewarp >> 2;
+  const int row = q * 32 + lane;    // TMEM lane == pixel row of the sub-tile
+  const int tid = ewarp * 32 + lane;
+  const bool store_thread = (tid == 0);
   const uint32_t tile_addr = ptx::smem_u32(tile_buf);
-  const uint32_t pool_addr = ptx::smem_u32(pool_buf);
+  const uint32_t bias_addr = ptx::smem_u32(sbias);
   const uint32_t my_row_addr = tile_addr + row * 128;
   const int sw = row & 7;
   const int total_units = grp.unit_end[grp.n - 1];
-  int acc = 0;
-  uint32_t acc_phase = 0;
+  int seq = 0;  // index of the unit in this CTA's sequence of live units: accumulator stage = seq & 1
   for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
     int gi;
     TileCoord t;
     if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+    const int acc = seq & 1;
+    const uint32_t acc_phase = (uint32_t)(seq >> 1) & 1u;
+    ++seq;
     const ConvParams& p = grp.p[gi];
     const CUtensorMap* tmOut = tmOuts + gi;
     const int dy = row >> p.bw_shift;
     const int dx = row & (p.BW - 1);
+    // PReLU(x) * scale = scale * x + scale * (slope - 1) * min(x, 0); no PReLU: slope = 1
     const float slope = p.prelu ? __ldg(p.prelu) : 1.0f;
-    const bool has_prelu = p.prelu != nullptr;
+    const float k_neg = (slope - 1.0f) * p.scale;
+    const float k_pos = p.scale;
     ptx::mbar_wait(&tmem_full[acc], acc_phase);
     ptx::tc_fence_after();
 #pragma unroll 1
@@ -147,92 +159,116 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
       const bool valid = (h < p.Hout) && (w < p.Wout);
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN * MT + mt * BN) + ((uint32_t)(q * 32) << 16);
       if (p.mode == EPI_F32_SLICES || p.mode == EPI_F32_REDUCE) {
-        // raw fp32 partial sums: 32 columns = one 128-byte staging row.  SLICES: plain store into slice
-        // split * N + image (deterministic); REDUCE: TMA tensor reduction (add) into the image's map
+        // raw fp32 partial sums: 32 columns = one 128-byte staging row (16 per column half).  SLICES: plain stores
+        // into slice split * N + image (deterministic); REDUCE: TMA tensor reduction (add) into the image's map
         const int slice = p.mode == EPI_F32_SLICES ? (t.k_begin / sc.kps[gi]) * p.N + t.n_img : t.n_img;
+        float* out_img = reinterpret_cast<float*>(p.out) + (size_t)slice * p.Hout * p.Wout * p.Cout;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(taddr + c0, v);
+          uint32_t v[16];
+          ptx::tmem_ld_32x32b_x16(taddr + c0 + half * 16, v);
           ptx::tmem_ld_wait();
-          if (store_thread) ptx::tma_store_wait_read();
-          ptx::named_bar_sync(1, 128);
+          if (p.mode == EPI_F32_REDUCE && store_thread) ptx::tma_store_wait_read();
+          ptx::named_bar_sync(1, EPI_THREADS);
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            ptx::st_shared_v4(my_row_addr + ((c ^ sw) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
-          ptx::fence_proxy_async();
-          ptx::named_bar_sync(1, 128);
-          if (store_thread) {
-            if (p.mode == EPI_F32_SLICES) ptx::tma_store_4d(tmOut, tile_buf, t.n0 + c0, t.w0, hbase, slice);
-            else ptx::tma_reduce_add_4d(tmOut, tile_buf, t.n0 + c0, t.w0, hbase, slice);
-            ptx::tma_store_commit();
+          for (int c = 0; c < 4; ++c)
+            ptx::st_shared_v4(my_row_addr + (((half * 4 + c) ^ sw) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+          if (p.mode == EPI_F32_REDUCE) {
+            ptx::fence_proxy_async();
+            ptx::named_bar_sync(1, EPI_THREADS);
+            if (store_thread) {
+              ptx::tma_reduce_add_4d(tmOut, tile_buf, t.n0 + c0, t.w0, hbase, slice);
+              ptx::tma_store_commit();
+            }
+          } else {
+            ptx::named_bar_sync(1, EPI_THREADS);
+            if (t.n0 + c0 < p.Cout) {
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int idx = it * EPI_THREADS + tid;
+                const int r = idx >> 3, c = idx & 7;
+                const int hh = hbase + (r >> p.bw_shift), ww = t.w0 + (r & (p.BW - 1));
+                if (hh < p.Hout && ww < p.Wout) {
+                  const uint4 val = ptx::ld_shared_v4(tile_addr + r * 128 + ((c ^ (r & 7)) << 4));
+                  *reinterpret_cast<uint4*>(out_img + ((size_t)hh * p.Wout + ww) * p.Cout + t.n0 + c0 + c * 4) = val;
+                }
+              }
+            }
           }
         }
       } else {
+        const int Hp = (p.Hout + 1) >> 1, Wp = (p.Wout + 1) >> 1;
+        bf16* out_img = reinterpret_cast<bf16*>(p.out) +
+                        (size_t)t.n_img * (p.mode == EPI_POOL ? (size_t)Hp * Wp : (size_t)p.Hout * p.Wout) * p.Cout;
 #pragma unroll 1
         for (int g = 0; g < BN / 64; ++g) {
           const int cbase = t.n0 + g * 64;
-          uint32_t o[32];
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
+          uint32_t o[16];
+          {
             uint32_t v[32];
             ptx::tmem_ld_32x32b_x32(taddr + g * 64 + half * 32, v);
+            const uint32_t baddr = bias_addr + (uint32_t)(cbase + half * 32) * 4u;
+            uint4 bq[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bq[j] = ptx::ld_shared_v4(baddr + j * 16);
             ptx::tmem_ld_wait();
-            const float4* b4 = reinterpret_cast<const float4*>(sbias + cbase + half * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 b = b4[j];
-              float x0 = __uint_as_float(v[4 * j]) + b.x, x1 = __uint_as_float(v[4 * j + 1]) + b.y;
-              float x2 = __uint_as_float(v[4 * j + 2]) + b.z, x3 = __uint_as_float(v[4 * j + 3]) + b.w;
-              if (has_prelu) {
-                x0 = x0 > 0.f ? x0 : x0 * slope;
-                x1 = x1 > 0.f ? x1 : x1 * slope;
-                x2 = x2 > 0.f ? x2 : x2 * slope;
-                x3 = x3 > 0.f ? x3 : x3 * slope;
-              }
-              o[half * 16 + 2 * j] = ptx::pack_bf16x2(x0 * p.scale, x1 * p.scale);
-              o[half * 16 + 2 * j + 1] = ptx::pack_bf16x2(x2 * p.scale, x3 * p.scale);
+              const float x0 = __uint_as_float(v[4 * j]) + __uint_as_float(bq[j].x);
+              const float x1 = __uint_as_float(v[4 * j + 1]) + __uint_as_float(bq[j].y);
+              const float x2 = __uint_as_float(v[4 * j + 2]) + __uint_as_float(bq[j].z);
+              const float x3 = __uint_as_float(v[4 * j + 3]) + __uint_as_float(bq[j].w);
+              const float y0 = fmaf(fminf(x0, 0.f), k_neg, x0 * k_pos);
+              const float y1 = fmaf(fminf(x1, 0.f), k_neg, x1 * k_pos);
+              const float y2 = fmaf(fminf(x2, 0.f), k_neg, x2 * k_pos);
+              const float y3 = fmaf(fminf(x3, 0.f), k_neg, x3 * k_pos);
+              o[2 * j] = ptx::pack_bf16x2(y0, y1);
+              o[2 * j + 1] = ptx::pack_bf16x2(y2, y3);
             }
           }
           if (p.mode == EPI_POOL && !valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = 0xFF80FF80u;  // -inf: outside the map, never wins a ceil-mode window
+            for (int j = 0; j < 16; ++j) o[j] = 0xFF80FF80u;  // -inf: outside the map, never wins a ceil-mode window
           }
-          // the previous TMA store must have finished reading the staging buffers before they are overwritten
-          if (store_thread) ptx::tma_store_wait_read();
-          ptx::named_bar_sync(1, 128);
+          ptx::named_bar_sync(1, EPI_THREADS);  // every thread has finished reading the previous staging pass
 #pragma unroll
-          for (int c = 0; c < 8; ++c)
-            ptx::st_shared_v4(my_row_addr + ((c ^ sw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-          if (p.mode == EPI_POOL) {
-            ptx::named_bar_sync(1, 128);
-            const int pw_shift = p.bw_shift - 1;  // pooled tile width BW / 2
-#pragma unroll
-            for (int it = 0; it < 2; ++it) {
-              const int item = row + it * 128;
-              const int pp = item >> 3, c = item & 7;
+          for (int c = 0; c < 4; ++c)
+            ptx::st_shared_v4(my_row_addr + (((half * 4 + c) ^ sw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+          ptx::named_bar_sync(1, EPI_THREADS);
+          if (cbase < p.Cout) {
+            if (p.mode == EPI_POOL) {
+              // 2x2 stride-2 ceil-mode max pool: 32 pooled pixels x 8 chunks, one per thread, straight to HBM
+              const int pw_shift = p.bw_shift - 1;  // pooled tile width BW / 2
+              const int pp = tid >> 3, c = tid & 7;
               const int ppy = pp >> pw_shift, ppx = pp & ((p.BW >> 1) - 1);
-              const int r00 = (2 * ppy) * p.BW + 2 * ppx;
-              const int r01 = r00 + 1, r10 = r00 + p.BW, r11 = r10 + 1;
-              uint4 a = ptx::ld_shared_v4(tile_addr + r00 * 128 + ((c ^ (r00 & 7)) << 4));
-              const uint4 b = ptx::ld_shared_v4(tile_addr + r01 * 128 + ((c ^ (r01 & 7)) << 4));
-              const uint4 cc = ptx::ld_shared_v4(tile_addr + r10 * 128 + ((c ^ (r10 & 7)) << 4));
-              const uint4 d = ptx::ld_shared_v4(tile_addr + r11 * 128 + ((c ^ (r11 & 7)) << 4));
-              __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
-              const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
-              const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&cc);
-              const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&d);
+              const int ph = (hbase >> 1) + ppy, pw = (t.w0 >> 1) + ppx;
+              if (ph < Hp && pw < Wp) {
+                const int r00 = (2 * ppy) * p.BW + 2 * ppx;
+                const int r01 = r00 + 1, r10 = r00 + p.BW, r11 = r10 + 1;
+                uint4 a = ptx::ld_shared_v4(tile_addr + r00 * 128 + ((c ^ (r00 & 7)) << 4));
+                const uint4 b = ptx::ld_shared_v4(tile_addr + r01 * 128 + ((c ^ (r01 & 7)) << 4));
+                const uint4 cc = ptx::ld_shared_v4(tile_addr + r10 * 128 + ((c ^ (r10 & 7)) << 4));
+                const uint4 d = ptx::ld_shared_v4(tile_addr + r11 * 128 + ((c ^ (r11 & 7)) << 4));
+                __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
+                const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+                const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&cc);
+                const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&d);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) pa[j] = __hmax2(__hmax2(pa[j], pb[j]), __hmax2(pc[j], pd[j]));
-              ptx::st_shared_v4(pool_addr + pp * 128 + ((c ^ (pp & 7)) << 4), a.x, a.y, a.z, a.w);
+                for (int j = 0; j < 4; ++j) pa[j] = __hmax2(__hmax2(pa[j], pb[j]), __hmax2(pc[j], pd[j]));
+                *reinterpret_cast<uint4*>(out_img + ((size_t)ph * Wp + pw) * p.Cout + cbase + c * 8) = a;
+              }
+            } else {
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int idx = it * EPI_THREADS + tid;
+                const int r = idx >> 3, c = idx & 7;
+                const int hh = hbase + (r >> p.bw_shift), ww = t.w0 + (r & (p.BW - 1));
+                if (hh < p.Hout && ww < p.Wout) {
+                  const uint4 val = ptx::ld_shared_v4(tile_addr + r * 128 + ((c ^ (r & 7)) << 4));
+                  *reinterpret_cast<uint4*>(out_img + ((size_t)hh * p.Wout + ww) * p.Cout + cbase + c * 8) = val;
+                }
+              }
             }
-          }
-          ptx::fence_proxy_async();
-          ptx::named_bar_sync(1, 128);
-          if (store_thread) {
-            if (p.mode == EPI_POOL) ptx::tma_store_4d(tmOut, pool_buf, cbase, t.w0 >> 1, hbase >> 1, t.n_img);
-            else ptx::tma_store_4d(tmOut, tile_buf, cbase, t.w0, hbase, t.n_img);
-            ptx::tma_store_commit();
           }
         }
       }
@@ -240,17 +276,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
     ptx::tc_fence_before();
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-    if (++acc == 2) {
-      acc = 0;
-      acc_phase ^= 1;
-    }
   }
   if (store_thread) ptx::tma_store_wait_all();
 }
 
 // ------------------------------------------------------------------------------------------------- main kernel
+static constexpr int CONV_THREADS = 128 + EPI_THREADS;
 template <int BN, int MT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(CONV_THREADS, 1)
     conv_igemm_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGroup grp) {
   constexpr int STAGES = conv_stages(BN, MT);
   constexpr int A_STAGE_BYTES = MT * A_SUB_BYTES;
@@ -264,8 +297,7 @@ __global__ void __launch_bounds__(256, 1)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   uint8_t* tile_buf = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
-  uint8_t* pool_buf = tile_buf + STAGE_TILE_BYTES;
-  float* sbias = reinterpret_cast<float*>(pool_buf + STAGE_POOL_BYTES);
+  float* sbias = reinterpret_cast<float*>(tile_buf + STAGE_TILE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
@@ -283,7 +315,7 @@ __global__ void __launch_bounds__(256, 1)
     for (int g = 0; g < grp.n; ++g) {
       ptx::tma_prefetch_desc(&maps.a[g]);
       ptx::tma_prefetch_desc(&maps.b[g]);
-      ptx::tma_prefetch_desc(&maps.o[g]);
+      if (grp.p[g].mode == EPI_F32_REDUCE) ptx::tma_prefetch_desc(&maps.o[g]);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -293,7 +325,7 @@ __global__ void __launch_bounds__(256, 1)
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 4);
+      ptx::mbar_init(&tmem_empty[a], EPI_THREADS / 32);
     }
     ptx::fence_barrier_init();
   }
@@ -383,7 +415,7 @@ __global__ void __launch_bounds__(256, 1)
       }
     }
   } else if (warp >= 4) {
-    epilogue_loop<BN, MT>(grp, maps.o, tile_buf, pool_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp, lane);
+    epilogue_loop<BN, MT>(grp, maps.o, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 4, lane);
   }
 
   ptx::tc_fence_before();
@@ -396,13 +428,43 @@ __global__ void __launch_bounds__(256, 1)
 
 // ------------------------------------------------------------------------------------------------- first layer
 // 3 x (3x3) first convolution on the fp32 NCHW frame (Detector.lua:32-33 uploads exactly this tensor).
-// 384 threads: warps 0-3 build the im2col rows (K = 27 -> 32, 64 bytes of each 128-byte swizzled row), warp 4 issues
-// two tcgen05.mma (M128 x N64 x K16) per tile, warp 5 owns TMEM, warps 8-11 run the shared epilogue.
+// 512 threads: warps 0-3 build the im2col rows (K = 27 -> 32, 64 bytes of each 128-byte swizzled row), each thread
+// prefetching its next tile's 27 taps into registers before it publishes the current one; warp 4 issues two
+// tcgen05.mma (M128 x N64 x K16) per tile, warp 5 owns TMEM; warps 8-15 run the shared epilogue (which paces this
+// layer: K is tiny).
 static constexpr int FIRST_STAGES = 6;
 static constexpr int FIRST_BN = 64;
+static constexpr int FIRST_THREADS = 512;
 static constexpr int FIRST_SMEM = FIRST_STAGES * A_SUB_BYTES + FIRST_BN * 128 + SMEM_FIXED;
 
-__global__ void __launch_bounds__(384, 1)
+__device__ __forceinline__ void first_load_taps(const ConvParams& p, int tile, int dy, int dx, float (&v)[27]) {
+  const TileCoord t = decode_tile(p, tile, FIRST_BN, 1, 1);
+  const int h = t.h0 + dy - p.padH, w = t.w0 + dx - p.padW;  // top-left tap in input coordinates
+  const size_t plane = (size_t)p.Hin * p.Win;
+  const float* base = p.img + (size_t)t.n_img * 3 * plane;
+  if (h >= 0 && h + 2 < p.Hin && w >= 0 && w + 2 < p.Win) {  // interior: no predicates
+    const float* q = base + (size_t)h * p.Win + w;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) v[c * 9 + kh * 3 + kw] = __ldg(q + c * plane + kh * p.Win + kw);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int yy = h + kh, xx = w + kw;
+          const bool in = yy >= 0 && yy < p.Hin && xx >= 0 && xx < p.Win;
+          v[c * 9 + kh * 3 + kw] = in ? __ldg(base + c * plane + (size_t)yy * p.Win + xx) : 0.f;
+        }
+  }
+}
+
+__global__ void __launch_bounds__(FIRST_THREADS, 1)
     conv_first_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvGroup grp,
                       const bf16* __restrict__ w32) {
   constexpr int BN = FIRST_BN;
@@ -414,8 +476,7 @@ __global__ void __launch_bounds__(384, 1)
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + FIRST_STAGES * A_SUB_BYTES;
   uint8_t* tile_buf = smem_b + BN * 128;
-  uint8_t* pool_buf = tile_buf + STAGE_TILE_BYTES;
-  float* sbias = reinterpret_cast<float*>(pool_buf + STAGE_POOL_BYTES);
+  float* sbias = reinterpret_cast<float*>(tile_buf + STAGE_TILE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
   uint64_t* empty_bar = full_bar + FIRST_STAGES;
   uint64_t* tmem_full = empty_bar + FIRST_STAGES;
@@ -427,14 +488,13 @@ __global__ void __launch_bounds__(384, 1)
   const int total_tiles = p.n_tiles_m;
 
   if (warp == 4 && lane == 0) {
-    ptx::tma_prefetch_desc(&tmOut);
     for (int s = 0; s < FIRST_STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 128);
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], 4);
+      ptx::mbar_init(&tmem_empty[a], EPI_THREADS / 32);
     }
     ptx::fence_barrier_init();
   }
@@ -460,40 +520,27 @@ __global__ void __launch_bounds__(384, 1)
     const int row = threadIdx.x;
     const int dy = row >> p.bw_shift, dx = row & (p.BW - 1);
     const int sw = row & 7;
-    const size_t plane = (size_t)p.Hin * p.Win;
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      TileCoord t = decode_tile(p, tile, BN, 1, 1);
-      const int h = t.h0 + dy - p.padH, w = t.w0 + dx - p.padW;  // top-left tap in input coordinates
-      const float* base = p.img + (size_t)t.n_img * 3 * plane;
-      float v[27];
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const int yy = h + kh, xx = w + kw;
-            const bool in = yy >= 0 && yy < p.Hin && xx >= 0 && xx < p.Win;
-            v[c * 9 + kh * 3 + kw] = in ? __ldg(base + c * plane + (size_t)yy * p.Win + xx) : 0.f;
-          }
+    const int stride = gridDim.x;
+    int tile = blockIdx.x;
+    int local = 0;                        // position of `tile` in this CTA's tile sequence
+    float v[27];
+    if (tile < total_tiles) first_load_taps(p, tile, dy, dx, v);
+    for (; tile < total_tiles; tile += stride, ++local) {
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 13; ++j) o[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
       o[13] = ptx::pack_bf16x2(v[26], 0.f);
       o[14] = 0u;
       o[15] = 0u;
+      if (tile + stride < total_tiles) first_load_taps(p, tile + stride, dy, dx, v);  // in flight across the wait
+      const int stage = local % FIRST_STAGES;
+      const uint32_t phase = (uint32_t)(local / FIRST_STAGES) & 1u;
       ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
       const uint32_t dst = ptx::smem_u32(smem_a + stage * A_SUB_BYTES) + row * 128;
 #pragma unroll
       for (int c = 0; c < 4; ++c) ptx::st_shared_v4(dst + ((c ^ sw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&full_bar[stage]);
-      if (++stage == FIRST_STAGES) {
-        stage = 0;
-        phase ^= 1;
-      }
     }
   } else if (warp == 4) {
     if (lane == 0) {
@@ -524,7 +571,7 @@ __global__ void __launch_bounds__(384, 1)
   } else if (warp >= 8) {
     GroupSched sc;
     make_sched(grp, BN, sc);
-    epilogue_loop<BN, 1>(grp, &tmOut, tile_buf, pool_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp, lane);
+    epilogue_loop<BN, 1>(grp, &tmOut, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 8, lane);
   }
 
   ptx::tc_fence_before();
@@ -625,18 +672,17 @@ static void fill_geometry(ConvParams& p, int N, int Hin, int Win, int Cin, int C
 }
 
 static void make_out_map(ConvLaunch* L, bf16* out) {
-  const ConvParams& p = L->p;
-  if (p.mode == EPI_STORE) make_tmap_act(&L->tmOut, out, p.N, p.Hout, p.Wout, p.Cout, p.BW, p.BH);
-  else if (p.mode == EPI_POOL)
-    make_tmap_act(&L->tmOut, out, p.N, (p.Hout + 1) / 2, (p.Wout + 1) / 2, p.Cout, p.BW / 2, p.BH / 2);
-  else L->tmOut = L->tmB;  // unused (EPI_F32_REDUCE) or set later by conv_set_slices_output (EPI_F32_SLICES)
+  L->p.out = out;          // bf16 NHWC map (EPI_STORE) or its 2x2-pooled map (EPI_POOL); fp32 modes: conv_set_f32_output
+  L->tmOut = L->tmB;       // only EPI_F32_REDUCE uses an output tensor map
 }
 
 void conv_set_f32_output(ConvLaunch* L, float* ws) {
   const ConvParams& p = L->p;
   FRCNN_REQUIRE((p.mode == EPI_F32_SLICES || p.mode == EPI_F32_REDUCE) && ws != nullptr, FRCNN_E_INVALID,
                 "conv: not an fp32 split-K launch");
-  const int S = p.mode == EPI_F32_SLICES ? p.splits * p.N : p.N;
+  L->p.out = ws;
+  if (p.mode == EPI_F32_SLICES) return;  // plain stores, no tensor map
+  const int S = p.N;
   cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wout, (cuuint64_t)p.Hout, (cuuint64_t)S};
   cuuint64_t strides[3] = {(cuuint64_t)p.Cout * 4, (cuuint64_t)p.Wout * p.Cout * 4, (cuuint64_t)p.Hout * p.Wout * p.Cout * 4};
   cuuint32_t box[4] = {32, (cuuint32_t)p.BW, (cuuint32_t)p.BH, 1};
@@ -725,7 +771,7 @@ static void launch_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cud
     FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  conv_igemm_kernel<BN, MT><<<grid, 256, smem, st>>>(maps, grp);
+  conv_igemm_kernel<BN, MT><<<grid, CONV_THREADS, smem, st>>>(maps, grp);
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
@@ -757,7 +803,7 @@ void conv_launch(const ConvLaunch& L, cudaStream_t st) {
       configured = true;
     }
     FRCNN_REQUIRE(L.p.img != nullptr, FRCNN_E_STATE, "first-layer kernel: image pointer not set");
-    conv_first_kernel<<<L.grid, 384, FIRST_SMEM, st>>>(L.tmOut, grp, L.w_first);
+    conv_first_kernel<<<L.grid, FIRST_THREADS, FIRST_SMEM, st>>>(L.tmOut, grp, L.w_first);
     FRCNN_CUDA_TRY(cudaGetLastError());
     return;
   }

@@ -51,9 +51,14 @@ struct RoiParams {
   int* roi_img;            // [R_total]
   int* roi_cand;           // [R_total]
   int* status;             // [1] number of degenerate ROIs
+  int* roi_base_out;       // [N] written by the prepare kernel (exclusive prefix of pick_count)
+  int* roi_total;          // [1] written by the prepare kernel (clamped to total_cap)
+  int total_cap;
+  int4* roi_rect;          // [R_total] crop {y0, y1, x0, x1} in feature cells, y0 < 0 = degenerate
 };
-void launch_roi_base(const int* pick_count, int N, int* roi_base, int* roi_total, int total_cap, cudaStream_t st);
-void launch_roi_pool_nhwc(const RoiParams& p, int N, cudaStream_t st);
+// prepare: ROI row table (image, candidate, crop rect) for every NMS survivor, one thread per survivor;
+// pool: persistent CTAs over the rows
+void launch_roi_pool_nhwc(const RoiParams& p, int N, int num_sms, cudaStream_t st);
 void launch_roi_pool_chw(const float* fmap, int C, int H, int W, const LocalizerDev& loc, const double* rects_dev, int R,
                          int kh, int kw, float* out, int32_t* argmax, int* status, cudaStream_t st);
 

@@ -114,23 +114,30 @@ void launch_rpn_decode(const DecodeParams& p, int N, cudaStream_t st) {
 // Localizer:inputToFeatureRect (Localizer.lua:41-67) including its dW/dH mix-ups, then the clip and the 1-based
 // crop of extract_roi_pooling_input (objective.lua:5-13).  Returns false where the reference would raise.
 __device__ __forceinline__ double lua_mod(double a, double b) { return a - floor(a / b) * b; }
+// x / d for a small positive integer d: a multiplication by the exactly representable reciprocal when d is a power of
+// two (bit-identical to the division), the division otherwise
+__device__ __forceinline__ double div_int(double x, int d) {
+  return (d & (d - 1)) == 0 ? x * (1.0 / (double)d) : x / (double)d;
+}
+__device__ __forceinline__ double lua_mod_int(double a, int b) { return a - floor(div_int(a, b)) * (double)b; }
 
 __device__ bool roi_crop(const LocalizerDev& loc, double minX, double minY, double maxX, double maxY, int FH, int FW, int* y0,
                          int* y1, int* x0, int* x1) {
   for (int i = 0; i < loc.n; ++i) {
-    const double kW = loc.l[i][0], kH = loc.l[i][1], dW = loc.l[i][2], dH = loc.l[i][3], pW = loc.l[i][4], pH = loc.l[i][5];
+    const int ikW = loc.l[i][0], ikH = loc.l[i][1], idW = loc.l[i][2], idH = loc.l[i][3];
+    const double kW = ikW, kH = ikH, dW = idW, dH = idH, pW = loc.l[i][4], pH = loc.l[i][5];
     if (dW < kW) {
       minX -= (kW - dW); maxX += (kW - dW);
       minY -= (kH - dH); maxY += (kH - dH);
     }
     minX += pW; maxX += pW;
     minY += pH; maxY += pH;
-    minX = minX / dH;  // sic (Localizer.lua:52)
-    minY = minY / dH;
-    if (lua_mod(maxX - kW, dW) == 0.0) maxX = fmax((maxX - kW) / dW + 1.0, minX + 1.0);
-    else maxX = fmax(ceil((maxX - kW) / dW) + 1.0, minX + 1.0);
-    if (lua_mod(maxY - kH, dH) == 0.0) maxY = fmax((maxY - kH) / dW + 1.0, minY + 1.0);  // sic: / dW (Localizer.lua:60)
-    else maxY = fmax(ceil((maxY - kH) / dH) + 1.0, minY + 1.0);
+    minX = div_int(minX, idH);  // sic (Localizer.lua:52)
+    minY = div_int(minY, idH);
+    if (lua_mod_int(maxX - kW, idW) == 0.0) maxX = fmax(div_int(maxX - kW, idW) + 1.0, minX + 1.0);
+    else maxX = fmax(ceil(div_int(maxX - kW, idW)) + 1.0, minX + 1.0);
+    if (lua_mod_int(maxY - kH, idH) == 0.0) maxY = fmax(div_int(maxY - kH, idW) + 1.0, minY + 1.0);  // sic: / dW (Localizer.lua:60)
+    else maxY = fmax(ceil(div_int(maxY - kH, idH)) + 1.0, minY + 1.0);
   }
   minX = floor(minX); minY = floor(minY); maxX = ceil(maxX); maxY = ceil(maxY);  // snapToInt (Rect.lua:147-149)
   // r:clip(Rect.new(0, 0, W, H)) (Rect.lua:73-80)
@@ -143,73 +150,77 @@ __device__ bool roi_crop(const LocalizerDev& loc, double minX, double minY, doub
   return true;
 }
 
-__global__ void roi_base_kernel(const int* __restrict__ pick_count, int N, int* __restrict__ roi_base, int* __restrict__ roi_total,
-                                int total_cap) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    int run = 0;
-    for (int n = 0; n < N; ++n) {
-      roi_base[n] = run;
-      run += pick_count[n];
-    }
-    *roi_total = min(run, total_cap);
+// One thread per NMS survivor: row index = (survivors of earlier images) + position in pick order; the crop rect is
+// Localizer:inputToFeatureRect in double on the device.
+__global__ void __launch_bounds__(256) roi_prepare_kernel(RoiParams p, int N) {
+  const int img = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int base = 0, total = 0;
+  for (int n = 0; n < N; ++n) {
+    const int c = p.pick_count[n];
+    if (n < img) base += c;
+    total += c;
   }
-}
-void launch_roi_base(const int* pick_count, int N, int* roi_base, int* roi_total, int total_cap, cudaStream_t st) {
-  roi_base_kernel<<<1, 32, 0, st>>>(pick_count, N, roi_base, roi_total, total_cap);
+  if (i == 0) {
+    p.roi_base_out[img] = base;
+    if (img == 0) *p.roi_total = min(total, p.total_cap);
+  }
+  if (i >= p.pick_count[img]) return;
+  const int row = base + i;
+  if (row >= p.total_cap) return;
+  const int cand = p.pick[(long)img * p.cap + i];
+  const double* r = p.cand_r + ((long)img * p.cap + cand) * 4;
+  int y0, y1, x0, x1;
+  const bool ok = roi_crop(p.loc, r[0], r[1], r[2], r[3], p.FH, p.FW, &y0, &y1, &x0, &x1);
+  if (!ok) atomicAdd(p.status, 1);
+  p.roi_rect[row] = ok ? make_int4(y0, y1, x0, x1) : make_int4(-1, -1, -1, -1);
+  p.roi_img[row] = img;
+  p.roi_cand[row] = cand;
 }
 
 // nn.SpatialAdaptiveMaxPooling(kw, kh) on the crop (Detector.lua:96-97), NHWC bf16 feature map, output
 // [row][bin][C] bf16 (channel-contiguous; the first cnet weight matrix is permuted to match at pack time).
-// One CTA per ROI; a thread handles 8 channels (16 bytes) of one bin; max is exact in any format.
+// Persistent CTAs over the ROI rows; a thread handles 8 channels (16 bytes) of one bin; max is exact in any format.
 __global__ void __launch_bounds__(256) roi_pool_nhwc_kernel(RoiParams p) {
-  __shared__ int s_rect[5];
-  const int img = blockIdx.y, i = blockIdx.x;
-  if (i >= p.pick_count[img]) return;
-  const int row = p.roi_base[img] + i;
-  const int cand = p.pick[(long)img * p.cap + i];
-  if (threadIdx.x == 0) {
-    const double* r = p.cand_r + ((long)img * p.cap + cand) * 4;
-    int y0, y1, x0, x1;
-    bool ok = roi_crop(p.loc, r[0], r[1], r[2], r[3], p.FH, p.FW, &y0, &y1, &x0, &x1);
-    s_rect[0] = y0; s_rect[1] = y1; s_rect[2] = x0; s_rect[3] = x1; s_rect[4] = ok;
-    if (!ok) atomicAdd(p.status, 1);
-    p.roi_img[row] = img;
-    p.roi_cand[row] = cand;
-  }
-  __syncthreads();
-  const int y0 = s_rect[0], x0 = s_rect[2];
-  const int ch = s_rect[1] - y0, cw = s_rect[3] - x0;
-  const bool ok = s_rect[4] != 0;
+  const int total = *p.roi_total;
   const int cv = p.C >> 3;
-  const int bins = p.kh * p.kw;
-  const uint4* fm = reinterpret_cast<const uint4*>(p.fmap) + (long)img * p.FH * p.FW * cv;
-  uint4* out = reinterpret_cast<uint4*>(p.out) + (long)row * bins * cv;
-  for (int item = threadIdx.x; item < bins * cv; item += blockDim.x) {
+  const int per_row = p.kh * p.kw * cv;
+  const long n_items = (long)total * per_row;
+  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+  // flat (row, bin, 8-channel group) index space over the whole grid: few large ROIs still fill the machine
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n_items; idx += (long)gridDim.x * blockDim.x) {
+    const int row = (int)(idx / per_row);
+    const int item = (int)(idx - (long)row * per_row);
+    const int4 rc = p.roi_rect[row];
+    const int img = p.roi_img[row];
     const int c8 = item % cv, bin = item / cv;
     uint4 m = make_uint4(0, 0, 0, 0);
-    if (ok) {
+    if (rc.x >= 0) {
+      const int y0 = rc.x, x0 = rc.z, ch = rc.y - rc.x, cw = rc.w - rc.z;
+      const uint4* fm = reinterpret_cast<const uint4*>(p.fmap) + (long)img * p.FH * p.FW * cv + c8;
       const int by = bin / p.kw, bx = bin - by * p.kw;
       // adaptive pooling window: [floor(b*S/k), ceil((b+1)*S/k))
       const int ys = (by * ch) / p.kh, ye = ((by + 1) * ch + p.kh - 1) / p.kh;
       const int xs = (bx * cw) / p.kw, xe = ((bx + 1) * cw + p.kw - 1) / p.kw;
-      bool first = true;
-      for (int yy = ys; yy < ye; ++yy)
+      m = ninf;
+      for (int yy = ys; yy < ye; ++yy) {
+        const uint4* rowp = fm + ((long)(y0 + yy) * p.FW + x0) * cv;
+#pragma unroll 4
         for (int xx = xs; xx < xe; ++xx) {
-          uint4 v = fm[((long)(y0 + yy) * p.FW + (x0 + xx)) * cv + c8];
-          if (first) { m = v; first = false; }
-          else {
-            __nv_bfloat162* pm = reinterpret_cast<__nv_bfloat162*>(&m);
-            __nv_bfloat162* pv = reinterpret_cast<__nv_bfloat162*>(&v);
+          const uint4 v = __ldg(rowp + (long)xx * cv);
+          __nv_bfloat162* pm = reinterpret_cast<__nv_bfloat162*>(&m);
+          const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) pm[j] = __hmax2(pm[j], pv[j]);
-          }
+          for (int j = 0; j < 4; ++j) pm[j] = __hmax2(pm[j], pv[j]);
         }
+      }
     }
-    out[item] = m;
+    reinterpret_cast<uint4*>(p.out)[(long)row * per_row + item] = m;
   }
 }
-void launch_roi_pool_nhwc(const RoiParams& p, int N, cudaStream_t st) {
-  roi_pool_nhwc_kernel<<<dim3(p.cap, N), 256, 0, st>>>(p);
+void launch_roi_pool_nhwc(const RoiParams& p, int N, int num_sms, cudaStream_t st) {
+  roi_prepare_kernel<<<dim3((p.cap + 255) / 256, N), 256, 0, st>>>(p, N);
+  roi_pool_nhwc_kernel<<<num_sms * 4, 256, 0, st>>>(p);
 }
 
 // Same operation on a Torch-layout fp32 feature map [C][H][W] with the reference's output ordering

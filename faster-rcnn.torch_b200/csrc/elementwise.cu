@@ -150,20 +150,29 @@ __global__ void __launch_bounds__(256) head_tail_group_kernel(HeadTailGroup g) {
       const float4 b = *reinterpret_cast<const float4*>(sbias + c);
       float4 hv[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (base + q < H.npix) {
-          const float* src = H.ws + (base + q) * CM + c;
-          for (int s = 0; s < H.splits; ++s) {  // fixed order: deterministic
-            const float4 t = *reinterpret_cast<const float4*>(src + (size_t)s * H.slice_stride);
-            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-          }
-          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-          a.x = a.x > 0.f ? a.x : a.x * slope;
-          a.y = a.y > 0.f ? a.y : a.y * slope;
-          a.z = a.z > 0.f ? a.z : a.z * slope;
-          a.w = a.w > 0.f ? a.w : a.w * slope;
+      for (int q = 0; q < 4; ++q) hv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      // split-K slices summed in slice order (deterministic); the 4 pixels' loads of a slice are independent
+#pragma unroll 2
+      for (int s = 0; s < H.splits; ++s) {
+        float4 t[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const long pix = base + q < H.npix ? base + q : H.npix - 1;
+          t[q] = __ldg(reinterpret_cast<const float4*>(H.ws + (size_t)s * H.slice_stride + pix * CM + c));
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          hv[q].x += t[q].x; hv[q].y += t[q].y; hv[q].z += t[q].z; hv[q].w += t[q].w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float4 a = hv[q];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        a.x = a.x > 0.f ? a.x : a.x * slope;
+        a.y = a.y > 0.f ? a.y : a.y * slope;
+        a.z = a.z > 0.f ? a.z : a.z * slope;
+        a.w = a.w > 0.f ? a.w : a.w * slope;
         hv[q] = a;
       }
 #pragma unroll
