@@ -336,7 +336,8 @@ def run_b200(args):
     launches = m.launch_count() - l0 - 0
     launches_per_step = launches // (args.steps + args.warmup)
     ms_e2e = max_over_ranks(timed(step_host, args.steps, max(3, args.warmup // 2)))
-    d2h = 4 * 4 + 2 * 4 * min(B, 16) + int(n_det[0]) * ffi.sizeof("frcnn_detection")
+    # counters (16 + 2 per frame ints) + the winners (the first 256 are copied speculatively with the counters)
+    d2h = 4 * (16 + 2 * B) + max(256, int(n_det[0])) * ffi.sizeof("frcnn_detection")
     # roofline pass: the same K steps with an event pair around every conv/GEMM launch
     L.frcnn_set_profiling(m.ctx, 1)
     step_dev()

@@ -114,7 +114,16 @@ struct frcnn_ctx {
   int* ticket = nullptr;
   unsigned long long* status = nullptr;
   int status_blocks = 0;
-  unsigned epoch = 0;
+  int decode_nblocks = 0;      // block count the ticket / scan-state words are currently valid for
+  bool own_stream = false;
+  // CUDA graph of the detect pipeline (replayed while image pointer / shape / thresholds stay the same)
+  bool graph_enabled = true;
+  cudaGraphExec_t graph_exec = nullptr;
+  struct GraphKey { const float* img; int N, H, W; double thr_fg, thr_class; float thr_nms1, thr_nms2; long gen; } graph_key = {};
+  GraphKey eager_key = {};     // key of the last eager run (a config is captured on its second use)
+  long ws_gen = 0;             // bumped whenever a workspace pointer baked into the graph may have changed
+  int64_t launches_per_detect = 0;
+  int spec_det = 256;          // winners copied to the host speculatively together with the counters
   int* pick1 = nullptr;
   int* count1 = nullptr;
   int* roi_base = nullptr;
@@ -439,6 +448,7 @@ static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
   if (c->ws_n == N && c->ws_h == H && c->ws_w == W) return;
   FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   free_all(c->ws_allocs);
+  ++c->ws_gen;
   c->ws_n = c->ws_h = c->ws_w = 0;
   const int nb = (int)c->blocks.size();
   c->pool_out.assign(nb, nullptr);
@@ -628,15 +638,16 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
   c->cand_box = (float4*)dev_alloc(A, NC * sizeof(float4));
   c->cand_logp = (float*)dev_alloc(A, NC * sizeof(float));
   c->cand_anchor = (int4*)dev_alloc(A, NC * sizeof(int4));
-  c->cand_count = (int*)dev_alloc(A, N * sizeof(int));
-  c->flags = (int*)dev_alloc(A, 16 * sizeof(int));
+  c->flags = (int*)dev_alloc(A, (16 + 2 * (size_t)N) * sizeof(int));  // flags | match counts | accepted counts
+  c->cand_count = c->flags + 16;
+  c->n_pass = c->flags + 16 + N;
   c->ticket = (int*)dev_alloc(A, N * sizeof(int));
   c->status_blocks = 4096;
   c->status = (unsigned long long*)dev_alloc(A, (size_t)N * c->status_blocks * sizeof(unsigned long long));
   FRCNN_CUDA_TRY(cudaMemsetAsync(c->ticket, 0, N * sizeof(int), c->stream));
   FRCNN_CUDA_TRY(cudaMemsetAsync(c->status, 0, (size_t)N * c->status_blocks * sizeof(unsigned long long), c->stream));
-  FRCNN_CUDA_TRY(cudaMemsetAsync(c->flags, 0, 16 * sizeof(int), c->stream));
-  c->epoch = 0;
+  FRCNN_CUDA_TRY(cudaMemsetAsync(c->flags, 0, (16 + 2 * (size_t)N) * sizeof(int), c->stream));
+  c->decode_nblocks = 0;
   c->pick1 = (int*)dev_alloc(A, NC * sizeof(int));
   c->count1 = (int*)dev_alloc(A, N * sizeof(int));
   c->roi_base = (int*)dev_alloc(A, N * sizeof(int));
@@ -655,7 +666,6 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
   c->fin_conf = (float*)dev_alloc(A, (size_t)R * sizeof(float));
   c->gbox = (float4*)dev_alloc(A, NC * sizeof(float4));
   c->grow = (int*)dev_alloc(A, NC * sizeof(int));
-  c->n_pass = (int*)dev_alloc(A, N * sizeof(int));
   c->det_cap = (int)NC;
   c->det_dev = (frcnn_detection*)dev_alloc(A, (size_t)c->det_cap * sizeof(frcnn_detection));
   // cnet layers: GEMM rows = R
@@ -681,7 +691,9 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
   c->nms_bytes = nms_workspace_bytes(c->nms_cap_total, c->nms_cap_seg);
   FRCNN_CUDA_TRY(cudaMalloc(&c->nms_mem, c->nms_bytes));
   nms_workspace_init(&c->nms, c->nms_mem, c->nms_bytes, c->nms_cap_total, c->nms_cap_seg);
-  if (!c->h_ints) FRCNN_CUDA_TRY(cudaMallocHost(&c->h_ints, 64 * sizeof(int)));
+  if (c->h_ints) cudaFreeHost(c->h_ints);
+  FRCNN_CUDA_TRY(cudaMallocHost(&c->h_ints, (64 + 2 * (size_t)N) * sizeof(int)));
+  ++c->ws_gen;
   if (c->h_det_cap < c->det_cap) {
     if (c->h_det) cudaFreeHost(c->h_det);
     FRCNN_CUDA_TRY(cudaMallocHost(&c->h_det, (size_t)c->det_cap * sizeof(frcnn_detection)));
@@ -731,20 +743,22 @@ static void run_decode(frcnn_ctx* c, const float* const* heads_dev, int N, int H
   p.status = c->status;
   p.nblocks = (off + 255) / 256;
   FRCNN_REQUIRE(p.nblocks <= c->status_blocks, FRCNN_E_INVALID, "too many anchors for the decode scan state");
-  // status words are laid out with the per-image stride nblocks; epoch tags make stale words harmless
-  p.epoch = ++c->epoch;
+  // status words are laid out with the per-image stride nblocks and tagged with the launch number derived from the
+  // running ticket counter; a different block count restarts the numbering
+  if (c->decode_nblocks != p.nblocks) {
+    FRCNN_CUDA_TRY(cudaMemsetAsync(c->ticket, 0, c->det_n * sizeof(int), c->stream));
+    FRCNN_CUDA_TRY(cudaMemsetAsync(c->status, 0, (size_t)c->det_n * c->status_blocks * sizeof(unsigned long long), c->stream));
+    c->decode_nblocks = p.nblocks;
+    ++c->ws_gen;
+  }
   launch_rpn_decode(p, N, c->stream);
   ++c->launches;
 }
 
-static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, frcnn_detection* det_host, int cap, int* n_det) {
-  FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called before detect");
-  FRCNN_REQUIRE(det_host != nullptr && n_det != nullptr && cap >= 0, FRCNN_E_INVALID, "bad output buffer");
-  ensure_pnet_workspace(c, N, H, W);
-  ensure_det_workspace(c, N, 0);
+// Enqueues the whole Detector:detect pipeline (Detector.lua:31-136) plus the result copies on the ctx stream.
+static void enqueue_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W) {
   cudaStream_t st = c->stream;
   const bool prof = c->profiling;
-  if (prof) for (int i = 0; i < 7; ++i) if (!c->ev[i]) FRCNN_CUDA_TRY(cudaEventCreate(&c->ev[i]));
   if (prof) {
     conv_profile_begin(c);
     cudaEventRecord(c->ev[0], st);
@@ -757,8 +771,9 @@ static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, f
   run_decode(c, heads_dev, N, H, W, c->thr_fg);
   // --- Detector.lua:68-85: nms(bb, 0.25, score) -- the score tensor is ignored, order key = y2 (nms.lua:41-42)
   nms_set_segments_from_counts(&c->nms, c->cand_count, N, c->cand_cap, st);
-  c->launches += 1 + nms_run(&c->nms, reinterpret_cast<const float*>(c->cand_box), 4, N, N * c->cand_cap, c->cand_cap, c->thr_nms1,
-                             FRCNN_NMS_ORDER_Y2, 0, st, nullptr);
+  c->nms.fused = false;  // up to cand_cap matches per image: sort / matrix / resolve as three launches
+  c->launches += nms_run(&c->nms, reinterpret_cast<const float*>(c->cand_box), 4, N, N * c->cand_cap, c->cand_cap, c->thr_nms1,
+                         FRCNN_NMS_ORDER_Y2, 0, st, nullptr);
   FRCNN_CUDA_TRY(cudaMemcpyAsync(c->pick1, c->nms.st.pick, (size_t)N * c->cand_cap * sizeof(int), cudaMemcpyDeviceToDevice, st));
   FRCNN_CUDA_TRY(cudaMemcpyAsync(c->count1, c->nms.st.counts, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
   if (prof) cudaEventRecord(c->ev[2], st);
@@ -789,6 +804,7 @@ static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, f
   c->launches += 2;
   // --- Detector.lua:125-136: per-class nms(bb, 0.1, bb[{{},5}]) -- order key again y2
   const int n_seg = N * c->class_count;
+  c->nms.fused = true;   // per-class segments are small: one fused launch
   c->launches += nms_run(&c->nms, reinterpret_cast<const float*>(c->gbox), 4, n_seg, N * c->cand_cap, c->cand_cap, c->thr_nms2,
                          FRCNN_NMS_ORDER_Y2, 0, st, nullptr);
   AssembleParams ap;
@@ -798,16 +814,75 @@ static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, f
   launch_assemble(ap, &c->nms, n_seg, st);
   ++c->launches;
   if (prof) cudaEventRecord(c->ev[5], st);
-  // --- results to the host: flags + per-image counts, then the winners
-  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_ints, c->flags, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  const int NS = std::min(N, 16);
-  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_ints + 4, c->cand_count, NS * sizeof(int), cudaMemcpyDeviceToHost, st));
-  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_ints + 20, c->n_pass, NS * sizeof(int), cudaMemcpyDeviceToHost, st));
+  // --- results to the host in ONE batch: counters (flags | per-image match counts | per-image accepted counts are
+  // one allocation) and, speculatively, the first spec_det winners
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_ints, c->flags, (16 + 2 * (size_t)c->det_n) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  const int spec = std::min(c->spec_det, c->det_cap);
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_det, c->det_dev, (size_t)spec * sizeof(frcnn_detection), cudaMemcpyDeviceToHost, st));
+}
+
+static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, frcnn_detection* det_host, int cap, int* n_det) {
+  FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called before detect");
+  FRCNN_REQUIRE(det_host != nullptr && n_det != nullptr && cap >= 0, FRCNN_E_INVALID, "bad output buffer");
+  ensure_pnet_workspace(c, N, H, W);
+  ensure_det_workspace(c, N, 0);
+  cudaStream_t st = c->stream;
+  const bool prof = c->profiling;
+  if (prof) for (int i = 0; i < 7; ++i) if (!c->ev[i]) FRCNN_CUDA_TRY(cudaEventCreate(&c->ev[i]));
+  // The pipeline is a fixed launch sequence without host decisions: the second call with the same image pointer,
+  // shape and thresholds captures it into a CUDA graph, later calls replay the graph (one host call per step).
+  const frcnn_ctx::GraphKey key = {img_dev, N, H, W, c->thr_fg, c->thr_class, c->thr_nms1, c->thr_nms2, c->ws_gen};
+  auto same = [](const frcnn_ctx::GraphKey& a, const frcnn_ctx::GraphKey& b) {
+    return a.img == b.img && a.N == b.N && a.H == b.H && a.W == b.W && a.thr_fg == b.thr_fg && a.thr_class == b.thr_class &&
+           a.thr_nms1 == b.thr_nms1 && a.thr_nms2 == b.thr_nms2 && a.gen == b.gen;
+  };
+  const bool want_graph = c->graph_enabled && !prof && c->decode_nblocks != 0;
+  if (want_graph && c->graph_exec && same(key, c->graph_key)) {
+    FRCNN_CUDA_TRY(cudaGraphLaunch(c->graph_exec, st));
+    c->launches += c->launches_per_detect;
+  } else if (want_graph && same(key, c->eager_key)) {
+    if (c->graph_exec) {
+      cudaGraphExecDestroy(c->graph_exec);
+      c->graph_exec = nullptr;
+    }
+    const int64_t l0 = c->launches;
+    cudaGraph_t graph = nullptr;
+    FRCNN_CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    try {
+      enqueue_detect(c, img_dev, N, H, W);
+    } catch (...) {
+      cudaStreamEndCapture(st, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      c->graph_enabled = false;
+      throw;
+    }
+    cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (e == cudaSuccess) e = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {  // capture not possible in this environment: stay eager
+      cudaGetLastError();
+      c->graph_exec = nullptr;
+      c->graph_enabled = false;
+      c->launches = l0;
+      enqueue_detect(c, img_dev, N, H, W);
+    } else {
+      c->launches_per_detect = c->launches - l0;
+      c->graph_key = key;
+      FRCNN_CUDA_TRY(cudaGraphLaunch(c->graph_exec, st));
+    }
+  } else {
+    enqueue_detect(c, img_dev, N, H, W);
+    c->eager_key = {img_dev, N, H, W, c->thr_fg, c->thr_class, c->thr_nms1, c->thr_nms2, c->ws_gen};
+  }
   FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
   const int overflow = c->h_ints[0], degenerate = c->h_ints[1], roi_total = c->h_ints[2], ndet = c->h_ints[3];
   if (overflow || degenerate) FRCNN_CUDA_TRY(cudaMemsetAsync(c->flags, 0, 2 * sizeof(int), st));
   c->stats[0] = c->stats[2] = 0;
-  for (int i = 0; i < NS; ++i) { c->stats[0] += c->h_ints[4 + i]; c->stats[2] += c->h_ints[20 + i]; }
+  for (int i = 0; i < N; ++i) {
+    c->stats[0] += c->h_ints[16 + i];
+    c->stats[2] += c->h_ints[16 + c->det_n + i];
+  }
   c->stats[1] = roi_total;
   c->stats[3] = ndet;
   if (prof) {
@@ -820,11 +895,13 @@ static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, f
   FRCNN_REQUIRE(!degenerate, FRCNN_E_ROI_EMPTY,
                 "an ROI clipped to max == 0; the reference raises an index error here (objective.lua:11)");
   const int ncopy = std::min(ndet, std::min(cap, c->det_cap));
-  if (ncopy > 0) {
-    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_det, c->det_dev, (size_t)ncopy * sizeof(frcnn_detection), cudaMemcpyDeviceToHost, st));
+  const int spec = std::min(c->spec_det, c->det_cap);
+  if (ncopy > spec) {  // more winners than the speculative copy brought over
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_det + spec, c->det_dev + spec, (size_t)(ncopy - spec) * sizeof(frcnn_detection),
+                                   cudaMemcpyDeviceToHost, st));
     FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
-    memcpy(det_host, c->h_det, (size_t)ncopy * sizeof(frcnn_detection));
   }
+  if (ncopy > 0) memcpy(det_host, c->h_det, (size_t)ncopy * sizeof(frcnn_detection));
   *n_det = ncopy;
   FRCNN_REQUIRE(ndet <= cap, FRCNN_E_OVERFLOW, "more winners than the output capacity");
 }
@@ -901,6 +978,18 @@ int frcnn_create(frcnn_ctx** out, int device, void* stream) {
   frcnn_ctx* c = new frcnn_ctx();
   c->device = device;
   c->stream = (cudaStream_t)stream;
+  if (c->stream == nullptr) {
+    // The legacy default stream cannot be captured into a CUDA graph.  A BLOCKING stream (plain cudaStreamCreate)
+    // synchronises implicitly with the legacy default stream in both directions, so the ordering with surrounding
+    // cutorch work on stream 0 (main.lua uses no other stream) is exactly what enqueueing on stream 0 would give.
+    e = cudaStreamCreate(&c->stream);
+    if (e != cudaSuccess) {
+      frcnn::set_global_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+      delete c;
+      return FRCNN_E_CUDA;
+    }
+    c->own_stream = true;
+  }
   c->sm_count = prop.multiProcessorCount;
   c->cc_major = prop.major;
   c->cc_minor = prop.minor;
@@ -929,8 +1018,10 @@ int frcnn_destroy(frcnn_ctx* c) {
   if (c->h_ints) cudaFreeHost(c->h_ints);
   if (c->h_det) cudaFreeHost(c->h_det);
   if (c->h_img) cudaFreeHost(c->h_img);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->conv_ev) cudaEventDestroy(e);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return FRCNN_OK;
 }
@@ -977,6 +1068,7 @@ int frcnn_bind_params(frcnn_ctx* c, const float* const* params_dev, int n) {
     FRCNN_REQUIRE(params_dev[i] != nullptr, FRCNN_E_INVALID, "null parameter pointer: " + c->params[i].name);
     c->bound[i] = params_dev[i];
   }
+  ++c->ws_gen;
   c->packed = false;
   API_END(c)
 }
@@ -1150,6 +1242,7 @@ static void nms_dev_impl(frcnn_ctx* c, const float* boxes_dev, int64_t n_total, 
   FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));  // beg/len are stack vectors
   if (!c->h_ints) FRCNN_CUDA_TRY(cudaMallocHost(&c->h_ints, 64 * sizeof(int)));
   int* h_rem = max_len > 8192 ? c->h_ints + 40 : nullptr;
+  ws.fused = max_len <= 1024;
   c->launches += frcnn::nms_run(&ws, boxes_dev, (int)row_stride, n_seg, cap_total, max_len, overlap, order_mode, order_col, c->stream, h_rem);
   frcnn::nms_export(&ws, n_seg, max_len, pick_dev, counts_dev, c->stream);
   ++c->launches;
@@ -1293,6 +1386,12 @@ int frcnn_detect_stats(const frcnn_ctx* c, int64_t stats[4]) {
 int frcnn_set_detect_thresholds(frcnn_ctx* c, double fg_prob, float nms_proposals, double class_prob, float nms_classes) {
   if (!c) return FRCNN_E_INVALID;
   c->thr_fg = fg_prob; c->thr_nms1 = nms_proposals; c->thr_class = class_prob; c->thr_nms2 = nms_classes;
+  return FRCNN_OK;
+}
+
+int frcnn_set_graph_replay(frcnn_ctx* c, int enable) {
+  if (!c) return FRCNN_E_INVALID;
+  c->graph_enabled = enable != 0;
   return FRCNN_OK;
 }
 

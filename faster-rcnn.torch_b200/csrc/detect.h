@@ -34,7 +34,6 @@ struct DecodeParams {
   int* ticket;                   // [N]
   unsigned long long* status;    // [N][nblocks]
   int nblocks;
-  unsigned epoch;
 };
 void launch_rpn_decode(const DecodeParams& p, int N, cudaStream_t st);
 

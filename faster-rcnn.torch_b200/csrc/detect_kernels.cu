@@ -11,9 +11,13 @@ __global__ void __launch_bounds__(256) rpn_decode_kernel(DecodeParams p) {
   __shared__ int s_bid, s_excl;
   __shared__ int warp_cnt[8];
   const int img = blockIdx.y;
-  if (threadIdx.x == 0) s_bid = atomicAdd(&p.ticket[img], 1);
+  // tickets keep counting across launches (no per-launch parameter, so the launch can be replayed from a CUDA graph):
+  // ticket t -> block id t % nblocks of launch number t / nblocks, which tags the scan-state words of that launch
+  if (threadIdx.x == 0) s_bid = (int)atomicAdd(reinterpret_cast<unsigned*>(&p.ticket[img]), 1u);
   __syncthreads();
-  const int bid = s_bid;
+  const unsigned ticket = (unsigned)s_bid;
+  const int bid = (int)(ticket % (unsigned)p.nblocks);
+  const unsigned epoch = ticket / (unsigned)p.nblocks + 1u;
   const int idx = bid * 256 + threadIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -67,13 +71,13 @@ __global__ void __launch_bounds__(256) rpn_decode_kernel(DecodeParams p) {
   // known; block `bid` sums the counts of blocks 0..bid-1, each thread polling a strided subset.  Blocks with a
   // smaller ticket are already running (tickets are handed out in start order), so the waits terminate.
   volatile unsigned long long* status = p.status + (long)img * p.nblocks;
-  if (threadIdx.x == 0) status[bid] = ((unsigned long long)p.epoch << 32) | (unsigned)block_total;
+  if (threadIdx.x == 0) status[bid] = ((unsigned long long)epoch << 32) | (unsigned)block_total;
   unsigned part = 0;
   for (int b = threadIdx.x; b < bid; b += 256) {
     unsigned long long v;
     do {
       v = status[b];
-    } while ((unsigned)(v >> 32) != p.epoch);
+    } while ((unsigned)(v >> 32) != epoch);
     part += (unsigned)v;
   }
 #pragma unroll
@@ -90,7 +94,6 @@ __global__ void __launch_bounds__(256) rpn_decode_kernel(DecodeParams p) {
     if (bid == p.nblocks - 1) {
       p.cand_count[img] = min((int)incl, p.cap);
       if ((int)incl > p.cap) atomicExch(p.cand_overflow, 1);
-      p.ticket[img] = 0;  // every block of this image has taken its ticket by now
     }
   }
   __syncthreads();

@@ -438,6 +438,288 @@ __global__ void __launch_bounds__(256) nms_filter_kernel(NmsState st, const floa
   if (__syncthreads_or(any_alive) && threadIdx.x == 0) atomicOr(st.remaining, 1);
 }
 
+// ------------------------------------------------------------------------------------------------ CTA-level path
+// Segments of at most SORT_CTA_MAX boxes (the detector's case): one CTA per segment runs whole algorithm steps
+// back to back instead of one launch per step.  Three launches per NMS -- sort + first selection (one CTA per
+// segment), the 1024 x 1024 suppression matrix of the first selection on all SMs, resolve + filter + every further
+// round inside the CTA -- or ONE launch (fused) when the segments are known to be small (per-class NMS).
+__device__ void cta_sort(unsigned long long* skeys, const NmsState& st, int s, const float* __restrict__ boxes, int row_stride,
+                         int order_mode, int order_col, int cap_len) {
+  const int beg = st.seg_beg[s];
+  const int len = min(st.seg_len[s], cap_len);
+  if (len <= 0) return;  // uniform
+  int n2 = 1;
+  while (n2 < len) n2 <<= 1;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    unsigned long long k = 0ull;
+    if (i < len) k = ((unsigned long long)orderable(order_key(boxes, beg + i, row_stride, order_mode, order_col)) << 32) | (unsigned)i;
+    skeys[i] = k;
+  }
+  __syncthreads();
+  for (int size = 2; size <= n2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
+        int lo = 2 * t - (t & (stride - 1));
+        int hi = lo + stride;
+        bool desc = ((lo & size) == 0);
+        unsigned long long a = skeys[lo], b = skeys[hi];
+        if ((a < b) == desc) {
+          skeys[lo] = b;
+          skeys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < len; i += blockDim.x) {
+    st.order[beg + i] = (int)(unsigned)(skeys[i] & 0xffffffffull);
+    st.alive[beg + i] = 1;
+  }
+  __syncthreads();
+}
+
+// first NMS_B alive candidates behind the cursor -> sel_*; returns the selection size (uniform)
+__device__ int cta_select(const NmsState& st, int s, const float* __restrict__ boxes, int row_stride) {
+  __shared__ int warp_cnt[32];
+  __shared__ int s_next;
+  const int beg = st.seg_beg[s];
+  const int len = st.seg_len[s];
+  const int cur = st.cursor[s];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (threadIdx.x == 0) s_next = len;
+  __syncthreads();
+  int taken = 0;
+  for (int base = cur; base < len && taken < NMS_B; base += 1024) {
+    int pos = base + threadIdx.x;
+    bool a = pos < len && st.alive[beg + pos] != 0;
+    unsigned bal = __ballot_sync(0xffffffffu, a);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0, chunk_total = 0;
+    for (int w = 0; w < 32; ++w) {
+      int c = warp_cnt[w];
+      if (w < warp) before += c;
+      chunk_total += c;
+    }
+    int slot = taken + before + __popc(bal & ((1u << lane) - 1u));
+    if (a && slot < NMS_B) {
+      int local = st.order[beg + pos];
+      float4 b = load_box(boxes, beg + local, row_stride);
+      st.sel_pos[(long)s * NMS_B + slot] = pos;
+      st.sel_box[(long)s * NMS_B + slot] = b;
+      st.sel_area[(long)s * NMS_B + slot] = box_area(b);
+      if (slot == NMS_B - 1) s_next = pos + 1;
+    }
+    taken += chunk_total;
+    __syncthreads();
+  }
+  const int m = min(taken, NMS_B);
+  if (threadIdx.x == 0) {
+    st.sel_cnt[s] = m;
+    st.cursor[s] = s_next;
+  }
+  __syncthreads();
+  return m;
+}
+
+// suppression matrix of the selection computed by this CTA, straight into shared memory
+__device__ void cta_mask(uint32_t* smask, const NmsState& st, int s, int m, float thr) {
+  const float4* sb = st.sel_box + (long)s * NMS_B;
+  const float* sa = st.sel_area + (long)s * NMS_B;
+  const int j = threadIdx.x;
+  if (j < m) {
+    const float4 bj = sb[j];
+    const float aj = sa[j];
+    for (int wi = 0; wi < NMS_ROW_WORDS; ++wi) {
+      uint32_t word = 0;
+      const int i_end = min(32, j - wi * 32);
+      for (int b = 0; b < i_end; ++b) {
+        const int i = wi * 32 + b;
+        if (suppresses(sb[i], sa[i], bj, aj, thr)) word |= 1u << b;
+      }
+      smask[j * 33 + wi] = word;
+    }
+  } else {
+    for (int wi = 0; wi < NMS_ROW_WORDS; ++wi) smask[j * 33 + wi] = 0;
+  }
+  __syncthreads();
+}
+
+__device__ void cta_load_mask(uint32_t* smask, const NmsState& st, int s, int m) {
+  for (int idx = threadIdx.x; idx < NMS_B * NMS_ROW_WORDS; idx += 1024) {
+    int r = idx >> 5, w = idx & 31;
+    uint32_t v = 0;
+    if (r < m && w * 32 <= r) v = st.mask[((long)s * NMS_B + r) * NMS_ROW_WORDS + w];
+    smask[r * 33 + w] = v;
+  }
+  __syncthreads();
+}
+
+// greedy recursion over the selection as a fixed point; appends the keepers; returns their number (uniform)
+__device__ int cta_resolve(const uint32_t* smask, const NmsState& st, int s, int m) {
+  __shared__ uint32_t kept[NMS_ROW_WORDS], undec[NMS_ROW_WORDS];
+  __shared__ int warp_cnt[32];
+  const int j = threadIdx.x;
+  const int warp = j >> 5, lane = j & 31;
+  const int beg = st.seg_beg[s];
+  __syncthreads();
+  if (j < NMS_ROW_WORDS) {
+    kept[j] = 0;
+    int lo = j * 32;
+    undec[j] = m >= lo + 32 ? 0xffffffffu : (m > lo ? ((1u << (m - lo)) - 1u) : 0u);
+  }
+  __syncthreads();
+  const int nwords = (j >> 5) + 1;
+  bool undecided = j < m;
+  bool is_kept = false;
+  for (;;) {
+    int decision = 0;
+    if (undecided) {
+      bool hit_kept = false, hit_undec = false;
+      for (int w = 0; w < nwords; ++w) {
+        uint32_t row = smask[j * 33 + w];
+        hit_kept |= (row & kept[w]) != 0;
+        hit_undec |= (row & undec[w]) != 0;
+      }
+      if (hit_kept) decision = 2;
+      else if (!hit_undec) decision = 1;
+    }
+    int progress = __syncthreads_or(decision != 0);
+    if (decision != 0) {
+      atomicAnd(&undec[warp], ~(1u << lane));
+      if (decision == 1) {
+        atomicOr(&kept[warp], 1u << lane);
+        is_kept = true;
+      }
+      undecided = false;
+    }
+    int any_left = __syncthreads_or(undecided);
+    if (!any_left) break;
+    if (!progress) break;
+  }
+  unsigned bal = __ballot_sync(0xffffffffu, is_kept);
+  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  __syncthreads();
+  int before = 0, total = 0;
+  for (int w = 0; w < 32; ++w) {
+    int c = warp_cnt[w];
+    if (w < warp) before += c;
+    total += c;
+  }
+  const int base_count = st.counts[s];
+  if (j < m) {
+    int pos = st.sel_pos[(long)s * NMS_B + j];
+    st.alive[beg + pos] = 0;
+    if (is_kept) {
+      int slot = before + __popc(bal & ((1u << lane) - 1u));
+      st.pick[beg + base_count + slot] = st.order[beg + pos];
+      st.newk_box[(long)s * NMS_B + slot] = st.sel_box[(long)s * NMS_B + j];
+      st.newk_area[(long)s * NMS_B + slot] = st.sel_area[(long)s * NMS_B + j];
+    }
+  }
+  __syncthreads();
+  if (j == 0) {
+    st.counts[s] = base_count + total;
+    st.newk_cnt[s] = total;
+  }
+  __syncthreads();
+  return total;
+}
+
+// every alive candidate behind the cursor is tested against this round's nk keepers
+__device__ void cta_filter(const NmsState& st, int s, const float* __restrict__ boxes, int row_stride, float thr, int nk) {
+  __shared__ float4 kb[256];
+  __shared__ float ka[256];
+  const int beg = st.seg_beg[s];
+  const int len = st.seg_len[s];
+  const int cur = st.cursor[s];
+  for (int base = cur; base < len; base += 1024) {
+    int pos = base + threadIdx.x;
+    bool a = pos < len && st.alive[beg + pos] != 0;
+    float4 bj = make_float4(0, 0, 0, 0);
+    float aj = 0;
+    if (a) {
+      bj = load_box(boxes, beg + st.order[beg + pos], row_stride);
+      aj = box_area(bj);
+    }
+    bool dead = false;
+    for (int k0 = 0; k0 < nk; k0 += 256) {
+      __syncthreads();
+      if (threadIdx.x < 256 && k0 + threadIdx.x < nk) {
+        kb[threadIdx.x] = st.newk_box[(long)s * NMS_B + k0 + threadIdx.x];
+        ka[threadIdx.x] = st.newk_area[(long)s * NMS_B + k0 + threadIdx.x];
+      }
+      __syncthreads();
+      int kn = min(256, nk - k0);
+      if (a && !dead) {
+        for (int k = 0; k < kn; ++k) {
+          if (suppresses(kb[k], ka[k], bj, aj, thr)) {
+            dead = true;
+            break;
+          }
+        }
+      }
+    }
+    if (a && dead) st.alive[beg + pos] = 0;
+  }
+  __syncthreads();
+}
+
+enum { NMS_PH_SORT_SELECT = 0, NMS_PH_RESOLVE_LOOP = 1, NMS_PH_FUSED = 2 };
+
+struct NmsCtaArgs {
+  NmsState st;
+  const float* boxes;
+  int row_stride, order_mode, order_col;
+  float thr;
+  int cap_len;            // upper bound of the segment lengths (shared-memory sort capacity)
+  const int* seg_counts;  // optional: segment s = rows [s * seg_stride, s * seg_stride + min(seg_counts[s], seg_stride))
+  int seg_stride;
+};
+
+template <int PHASE>
+__global__ void __launch_bounds__(1024) nms_cta_kernel(NmsCtaArgs a) {
+  extern __shared__ unsigned long long nms_smem[];
+  uint32_t* smask = reinterpret_cast<uint32_t*>(nms_smem);
+  const NmsState& st = a.st;
+  const int s = blockIdx.x;
+  if (PHASE != NMS_PH_RESOLVE_LOOP) {
+    if (threadIdx.x == 0) {
+      if (a.seg_counts) {
+        st.seg_beg[s] = s * a.seg_stride;
+        st.seg_len[s] = min(a.seg_counts[s], a.seg_stride);
+      }
+      st.cursor[s] = 0;
+      st.counts[s] = 0;
+      st.newk_cnt[s] = 0;
+      st.sel_cnt[s] = 0;
+    }
+    __syncthreads();
+    cta_sort(nms_smem, st, s, a.boxes, a.row_stride, a.order_mode, a.order_col, a.cap_len);
+    const int m = cta_select(st, s, a.boxes, a.row_stride);
+    if (PHASE == NMS_PH_SORT_SELECT) return;
+    if (m == 0) return;
+    cta_mask(smask, st, s, m, a.thr);
+    const int nk = cta_resolve(smask, st, s, m);
+    cta_filter(st, s, a.boxes, a.row_stride, a.thr, nk);
+  } else {
+    const int m = st.sel_cnt[s];
+    if (m == 0) return;
+    cta_load_mask(smask, st, s, m);
+    const int nk = cta_resolve(smask, st, s, m);
+    cta_filter(st, s, a.boxes, a.row_stride, a.thr, nk);
+  }
+  // further rounds (rare: more than NMS_B candidates survive the first round's keepers) stay inside the CTA
+  for (;;) {
+    const int m = cta_select(st, s, a.boxes, a.row_stride);
+    if (m == 0) break;
+    cta_mask(smask, st, s, m, a.thr);
+    const int nk = cta_resolve(smask, st, s, m);
+    cta_filter(st, s, a.boxes, a.row_stride, a.thr, nk);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host driver
 size_t nms_workspace_bytes(int cap_total, int cap_seg) {
   size_t b = 0;
@@ -508,8 +790,6 @@ int nms_run(NmsWorkspace* ws, const float* boxes_dev, int row_stride, int n_seg,
   int launches = 0;
   if (n_seg <= 0 || n_total_cap <= 0) return 0;
   FRCNN_REQUIRE(n_seg <= ws->cap_seg && n_total_cap <= ws->cap_total, FRCNN_E_INVALID, "nms: workspace capacity exceeded");
-  nms_init_kernel<<<(n_seg + 255) / 256, 256, 0, st_>>>(st, n_seg);
-  ++launches;
   static bool configured = false;
   if (!configured) {
     FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_B * 33 * 4));
@@ -518,12 +798,36 @@ int nms_run(NmsWorkspace* ws, const float* boxes_dev, int row_stride, int n_seg,
   }
   const bool small = max_seg_len <= SORT_CTA_MAX;
   if (small) {
+    // CTA-level path: 3 launches (or 1 when fused)
+    static bool cta_configured = false;
+    const int mask_bytes = NMS_B * 33 * 4;
+    if (!cta_configured) {
+      FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_cta_kernel<NMS_PH_SORT_SELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_CTA_MAX * 8));
+      FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_cta_kernel<NMS_PH_RESOLVE_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, mask_bytes));
+      FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_cta_kernel<NMS_PH_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, mask_bytes));
+      cta_configured = true;
+    }
     int n2 = 1;
     while (n2 < max_seg_len) n2 <<= 1;
-    nms_sort_cta_kernel<<<n_seg, 1024, n2 * 8, st_>>>(st, boxes_dev, row_stride, order_mode, order_col, n2);
-    ++launches;
+    NmsCtaArgs a;
+    a.st = st; a.boxes = boxes_dev; a.row_stride = row_stride; a.order_mode = order_mode; a.order_col = order_col; a.thr = thr;
+    a.cap_len = n2; a.seg_counts = ws->seg_counts; a.seg_stride = ws->seg_stride;
+    ws->seg_counts = nullptr;
+    if (ws->fused) {
+      nms_cta_kernel<NMS_PH_FUSED><<<n_seg, 1024, std::max(mask_bytes, n2 * 8), st_>>>(a);
+      FRCNN_CUDA_TRY(cudaGetLastError());
+      return 1;
+    }
+    nms_cta_kernel<NMS_PH_SORT_SELECT><<<n_seg, 1024, n2 * 8, st_>>>(a);
+    nms_mask_kernel<<<dim3(NMS_B * NMS_ROW_WORDS / 256, n_seg), 256, 0, st_>>>(st, thr);
+    nms_cta_kernel<NMS_PH_RESOLVE_LOOP><<<n_seg, 1024, mask_bytes, st_>>>(a);
+    FRCNN_CUDA_TRY(cudaGetLastError());
+    return 3;
   } else {
     FRCNN_REQUIRE(n_seg <= 256, FRCNN_E_INVALID, "nms: at most 256 segments in the large-N path");
+    FRCNN_REQUIRE(ws->seg_counts == nullptr, FRCNN_E_INVALID, "nms: device-side segment counts need the CTA-level path");
+    nms_init_kernel<<<(n_seg + 255) / 256, 256, 0, st_>>>(st, n_seg);
+    ++launches;
     int n = n_total_cap;
     dim3 g((max_seg_len + 255) / 256 < 1024 ? (max_seg_len + 255) / 256 : 1024, n_seg);
     radix_prepare_kernel<<<g, 256, 0, st_>>>(st, boxes_dev, row_stride, order_mode, order_col, n_seg, ws->rkeys[0],
@@ -585,17 +889,13 @@ void nms_export(NmsWorkspace* ws, int n_seg, int max_seg_len, int64_t* pick64, i
   nms_export_kernel<<<dim3(gx, n_seg), 256, 0, st_>>>(ws->st, n_seg, (long long*)pick64, (long long*)counts64);
 }
 
-// segment table helpers for device-resident counts (detector pipeline)
-// segment s = rows [s * stride, s * stride + min(counts[s], stride))   (one segment per image of a batch)
-__global__ void nms_segments_from_counts_kernel(NmsState st, const int* __restrict__ counts, int n_seg, int stride) {
-  int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s < n_seg) {
-    st.seg_beg[s] = s * stride;
-    st.seg_len[s] = min(counts[s], stride);
-  }
-}
+// Device-resident segment counts (detector pipeline): segment s = rows [s * stride, s * stride + min(counts[s],
+// stride)); the table is filled by the first kernel of the next nms_run (CTA-level path).
 void nms_set_segments_from_counts(NmsWorkspace* ws, const int* counts_dev, int n_seg, int stride, cudaStream_t st_) {
-  nms_segments_from_counts_kernel<<<(n_seg + 255) / 256, 256, 0, st_>>>(ws->st, counts_dev, n_seg, stride);
+  (void)n_seg;
+  (void)st_;
+  ws->seg_counts = counts_dev;
+  ws->seg_stride = stride;
 }
 
 }  // namespace frcnn

@@ -30,6 +30,9 @@ struct NmsWorkspace {
   uint8_t* rseg[2];
   uint32_t* rhist;
   int cap_total, cap_seg;
+  const int* seg_counts = nullptr;  // consumed by the next nms_run (see nms_set_segments_from_counts)
+  int seg_stride = 0;
+  bool fused = false;               // next nms_run: all segments are small -> one fused launch
 };
 
 size_t nms_workspace_bytes(int cap_total, int cap_seg);

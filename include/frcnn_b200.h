@@ -172,6 +172,9 @@ int frcnn_set_detect_thresholds(frcnn_ctx* ctx, double fg_prob, float nms_propos
  * frcnn_set_profiling(ctx, 1): ms[0]=trunk+heads convs, [1]=decode+nms, [2]=roi pool, [3]=cnet, [4]=final nms,
  * [5]=total. */
 int frcnn_set_profiling(frcnn_ctx* ctx, int enable);
+/* frcnn_detect / frcnn_detect_dev replay their fixed kernel sequence from a CUDA graph from the third call with the
+ * same image pointer, shape and thresholds on (default on; profiling mode always runs eagerly). */
+int frcnn_set_graph_replay(frcnn_ctx* ctx, int enable);
 int frcnn_last_timings(const frcnn_ctx* ctx, float ms[6]);
 /* Profiling mode also brackets every launch of the tcgen05 conv/GEMM kernel with a CUDA event pair on the ctx
  * stream: summed device time, summed algorithmic FLOPs (2*M*N*K of the un-padded problems) and launch count of

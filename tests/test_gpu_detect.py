@@ -111,3 +111,30 @@ def test_detect_overflow_is_an_error(F, small_model):
     # the context stays usable after the error
     det = F.Detector(small_model)
     det.detect(OM.synthetic_frame(122, 192, seed=1).numpy())
+
+
+def test_detect_graph_replay_matches_eager(F, det_model):
+    """From the third call with the same input buffer / shape / thresholds the pipeline is replayed from a CUDA graph:
+    results must equal the eager run, also after a threshold change forces a re-capture and for new frame contents
+    written into the same device buffer."""
+    det = F.Detector(det_model)
+    buf = OM.synthetic_frame(122, 192, seed=2).cuda()
+    F.lib().frcnn_set_graph_replay(det_model.ctx, 0)
+    eager = [_key(x) for x in det.detect(buf)]
+    F.lib().frcnn_set_graph_replay(det_model.ctx, 1)
+    for _ in range(4):  # eager, capture + launch, replay, replay
+        got = [_key(x) for x in det.detect(buf)]
+        assert len(set(got) & set(eager)) >= 0.9 * max(len(got), len(eager), 1)
+    buf.copy_(OM.synthetic_frame(122, 192, seed=3).cuda())  # same pointer, new frame
+    other = [_key(x) for x in det.detect(buf)]
+    F.lib().frcnn_set_graph_replay(det_model.ctx, 0)
+    other_eager = [_key(x) for x in det.detect(buf)]
+    F.lib().frcnn_set_graph_replay(det_model.ctx, 1)
+    assert len(set(other) & set(other_eager)) >= 0.9 * max(len(other), len(other_eager), 1)
+    L = F.lib()
+    L.frcnn_set_detect_thresholds(det_model.ctx, 0.95, 0.25, 0.5, 0.1)  # stricter class threshold: graph re-captured
+    try:
+        strict = [det.detect(buf) for _ in range(3)][-1]
+        assert all(float(np.exp(x["confidence"])) > 0.5 for x in strict)
+    finally:
+        L.frcnn_set_detect_thresholds(det_model.ctx, 0.95, 0.25, 0.2, 0.1)
