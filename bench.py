@@ -21,6 +21,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -299,8 +300,11 @@ def run_b200(args):
         if rank == 0:
             if not args.no_cpu_baseline:
                 line["cpu_baseline"] = cpu_baseline_nms(n)
-            print(json.dumps(line))
+            print(json.dumps(line), flush=True)
         m.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
         return
 
     # ---- detect workload
@@ -356,6 +360,16 @@ def run_b200(args):
         stage_ms += np.array([st[i] for i in range(6)])
     L.frcnn_set_profiling(m.ctx, 0)
     achieved = conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    # DRAM traffic of the same launches from the committed `ncu --set full` capture (profiles/), if it covers this batch
+    traffic, traffic_src = None, None
+    try:
+        summ = json.load(open(os.path.join(ROOT, "profiles", "r1_summary.json")))
+        rows = summ.get("full_b%d" % B)
+        if rows and args.model == "vgg_small" and (h, w) == (450, 800):
+            traffic = sum(r["dram_mb"] for r in rows) * 1e6
+            traffic_src = "profiles/r1_ncu_conv_b%d.md (dram__bytes_read.sum + dram__bytes_write.sum over %d conv launches)" % (B, len(rows))
+    except Exception:
+        pass
     total_frames = sum_over_ranks(float(B)) * args.steps
     value = total_frames / (ms * 1e-3)
     peak = pk["bf16_sustained"]
@@ -370,7 +384,7 @@ def run_b200(args):
                          d2h_bytes_per_step=int(d2h)),
                 gpu_launches=int(launches_per_step * args.steps),
                 roofline=dict(bound="tensor", kernel="conv_igemm_kernel (all launches of a step)", achieved=achieved, peak=peak,
-                              unit="TFLOP/s", frac=achieved / peak if peak else None, traffic=None,
+                              unit="TFLOP/s", frac=achieved / peak if peak else None, traffic=traffic, traffic_source=traffic_src,
                               launches_per_step=conv_n // max(args.steps, 1), ms_per_step=conv_ms / max(args.steps, 1),
                               flops_per_step=conv_fl / max(args.steps, 1),
                               pnet_conv_flops_per_image=conv_flops_per_image(desc, h, w),
@@ -380,9 +394,10 @@ def run_b200(args):
     if rank == 0:
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline_detect(args, desc, cfg, params, h, w)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     m.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

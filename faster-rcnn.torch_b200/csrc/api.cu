@@ -1,6 +1,7 @@
 // C ABI of the library (include/frcnn_b200.h): context, model plan, weight packing, pnet / cnet forward and the
 // fused Detector:detect pipeline.  Host orchestration only -- every arithmetic step is a kernel of this library.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -990,6 +991,7 @@ int frcnn_create(frcnn_ctx** out, int device, void* stream) {
     }
     c->own_stream = true;
   }
+  if (const char* ng = getenv("FRCNN_NO_GRAPH")) c->graph_enabled = !(ng[0] == '1');  // profiling under ncu
   c->sm_count = prop.multiProcessorCount;
   c->cc_major = prop.major;
   c->cc_minor = prop.minor;

@@ -428,13 +428,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 
 // ------------------------------------------------------------------------------------------------- first layer
 // 3 x (3x3) first convolution on the fp32 NCHW frame (Detector.lua:32-33 uploads exactly this tensor).
-// 512 threads: warps 0-3 build the im2col rows (K = 27 -> 32, 64 bytes of each 128-byte swizzled row), each thread
-// prefetching its next tile's 27 taps into registers before it publishes the current one; warp 4 issues two
-// tcgen05.mma (M128 x N64 x K16) per tile, warp 5 owns TMEM; warps 8-15 run the shared epilogue (which paces this
-// layer: K is tiny).
+// 640 threads: warps 0-7 build the im2col rows (K = 27 -> 32, 64 bytes of each 128-byte swizzled row) in two groups
+// that alternate tiles, each thread prefetching its next tile's 27 taps into registers before it publishes the
+// current one; warp 8 issues two tcgen05.mma (M128 x N64 x K16) per tile, warp 9 owns TMEM; warps 12-19 run the
+// shared epilogue.  K is tiny, so this layer is paced by instruction latency of producers and epilogue: two warps
+// of each role per scheduler.
 static constexpr int FIRST_STAGES = 6;
 static constexpr int FIRST_BN = 64;
-static constexpr int FIRST_THREADS = 512;
+static constexpr int FIRST_THREADS = 640;
 static constexpr int FIRST_SMEM = FIRST_STAGES * A_SUB_BYTES + FIRST_BN * 128 + SMEM_FIXED;
 
 __device__ __forceinline__ void first_load_taps(const ConvParams& p, int tile, int dy, int dx, float (&v)[27]) {
@@ -487,7 +488,7 @@ __global__ void __launch_bounds__(FIRST_THREADS, 1)
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.n_tiles_m;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     for (int s = 0; s < FIRST_STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 128);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -498,7 +499,7 @@ __global__ void __launch_bounds__(FIRST_THREADS, 1)
     }
     ptx::fence_barrier_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     ptx::tmem_alloc(tmem_base_slot, TMEM_COLS);
     ptx::tmem_relinquish();
   }
@@ -515,17 +516,18 @@ __global__ void __launch_bounds__(FIRST_THREADS, 1)
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ------------------------------------------------------------ im2col producers: thread <-> pixel row
-    const int row = threadIdx.x;
+    const int group = warp >> 2;          // tiles with an even / odd local index
+    const int row = threadIdx.x & 127;
     const int dy = row >> p.bw_shift, dx = row & (p.BW - 1);
     const int sw = row & 7;
-    const int stride = gridDim.x;
-    int tile = blockIdx.x;
-    int local = 0;                        // position of `tile` in this CTA's tile sequence
+    const int stride = 2 * gridDim.x;
+    int tile = blockIdx.x + group * gridDim.x;
+    int local = group;                    // position of `tile` in this CTA's tile sequence
     float v[27];
     if (tile < total_tiles) first_load_taps(p, tile, dy, dx, v);
-    for (; tile < total_tiles; tile += stride, ++local) {
+    for (; tile < total_tiles; tile += stride, local += 2) {
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 13; ++j) o[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
@@ -542,7 +544,7 @@ __global__ void __launch_bounds__(FIRST_THREADS, 1)
       ptx::fence_proxy_async();
       ptx::mbar_arrive(&full_bar[stage]);
     }
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
@@ -568,15 +570,15 @@ __global__ void __launch_bounds__(FIRST_THREADS, 1)
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     GroupSched sc;
     make_sched(grp, BN, sc);
-    epilogue_loop<BN, 1>(grp, &tmOut, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 8, lane);
+    epilogue_loop<BN, 1>(grp, &tmOut, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 12, lane);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
