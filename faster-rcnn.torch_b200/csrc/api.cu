@@ -1417,6 +1417,48 @@ int frcnn_last_conv_profile(const frcnn_ctx* c, float* ms, double* flops, int* l
   return FRCNN_OK;
 }
 
+// ---- backward primitives of nn.SpatialConvolution (pnet:backward, objective.lua:189)
+int frcnn_conv_dgrad_bf16(frcnn_ctx* c, const uint16_t* dy_dev, const float* w_dev, int n, int h, int w, int cin, int cout, int k,
+                          int pad, uint16_t* dx_dev) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(dy_dev && w_dev && dx_dev, FRCNN_E_INVALID, "null argument");
+  const int ho = h + 2 * pad - k + 1, wo = w + 2 * pad - k + 1;
+  FRCNN_REQUIRE(ho > 0 && wo > 0 && k - 1 - pad >= 0, FRCNN_E_INVALID, "bad convolution geometry");
+  const size_t wbytes = ((size_t)cout * cin * k * k * sizeof(frcnn::bf16) + 255) & ~size_t(255);
+  frcnn::bf16* wp = (frcnn::bf16*)frcnn::ensure_scratch(c, wbytes + 256);
+  frcnn::launch_pack_conv_weight_dgrad(w_dev, wp, cout, cin, k, k, c->stream);
+  // transposed convolution = stride-1 convolution of dY with the flipped, channel-transposed filters, padding k-1-pad
+  frcnn::ConvLaunch L;
+  frcnn::conv_prepare(&L, (const frcnn::bf16*)dy_dev, wp, n, ho, wo, cout, cin, k, k, k - 1 - pad, k - 1 - pad, frcnn::EPI_STORE,
+                      (frcnn::bf16*)dx_dev, c->sm_count, 0, 0, 0);
+  frcnn::conv_launch(L, c->stream);
+  c->launches += 2;
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  API_END(c)
+}
+
+int frcnn_conv_wgrad_bf16(frcnn_ctx* c, const uint16_t* x_dev, const uint16_t* dy_dev, int n, int h, int w, int cin, int cout, int k,
+                          int pad, float* dw_dev) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(x_dev && dy_dev && dw_dev, FRCNN_E_INVALID, "null argument");
+  const int ho = h + 2 * pad - k + 1, wo = w + 2 * pad - k + 1;
+  FRCNN_REQUIRE(ho > 0 && wo > 0, FRCNN_E_INVALID, "bad convolution geometry");
+  float* dw_taps = (float*)frcnn::ensure_scratch(c, (size_t)cout * k * k * cin * 4 + 256);
+  FRCNN_CUDA_TRY(cudaMemsetAsync(dw_taps, 0, (size_t)cout * k * k * cin * 4, c->stream));
+  frcnn::ConvLaunch L;
+  frcnn::conv_wgrad_prepare(&L, (const frcnn::bf16*)dy_dev, (const frcnn::bf16*)x_dev, dw_taps, n, h, w, cin, cout, k, k, pad, pad,
+                            c->sm_count);
+  frcnn::conv_launch(L, c->stream);
+  frcnn::launch_wgrad_finish(dw_taps, dw_dev, cout, cin, k, k, c->stream);
+  c->launches += 2;
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  API_END(c)
+}
+
 int frcnn_conv_first(frcnn_ctx* c, const float* img_dev, const float* w_dev, const float* bias_dev, const float* prelu_dev,
                      float scale, int n, int h, int w, int cout, int pad, int pool, uint16_t* out_dev, int iters, float* elapsed_ms) {
   API_BEGIN(c)

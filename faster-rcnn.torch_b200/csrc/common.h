@@ -68,6 +68,11 @@ struct ConvParams {
   const int* m_limit;       // optional device int: tiles whose first row >= *m_limit are skipped (GEMM rows)
   int dyn_ctas;             // with m_limit: > 0 = choose the split-K factor on the device so that the tiles of the
                             // *m_limit live rows fill dyn_ctas CTAs (host `splits` is then the upper bound)
+  // weight-gradient GEMM (conv_wgrad_prepare): M = Cout rows, N = Cin columns of ONE filter tap, K = output pixels
+  // in BW x BH = 64-pixel patches.  Both operands are read from the NHWC tensors as MN-major tiles ([64 pixels][64
+  // channels] TMA boxes); the tap shift and the zero padding are TMA coordinates / OOB fill.  Reuses the fields:
+  // n_tiles_m = taps * co_tiles, n_tiles_n = ci tiles, wchunks / tiles_h = patch columns / rows, k_iters = N * patches.
+  int wgrad, co_tiles, wchunks;
   const float* img;         // first-layer kernel only: [N][Cimg][Hin][Win] fp32 input frames (Torch layout)
   int Cimg;                 // first-layer kernel only: image channels (3); K = Cimg * KH * KW <= 32
 };
@@ -108,6 +113,10 @@ void conv_first_prepare(ConvLaunch* L, const bf16* w_packed32, int N, int Hin, i
 void conv_launch(const ConvLaunch& L, cudaStream_t st);
 // all members: same BN, MT == 1, not the first-layer kernel; pass them heaviest (longest K per unit) first
 void conv_launch_group(const ConvLaunch* const* Ls, int n, int num_sms, cudaStream_t st);
+// dW[co][tap][ci] (fp32, zeroed by the caller) += sum over pixels dY[p][co] * X[p + tap][ci]; dy / x: NHWC bf16;
+// always EPI_F32_REDUCE
+void conv_wgrad_prepare(ConvLaunch* L, const bf16* dy, const bf16* x, float* dw_taps, int N, int Hin, int Win, int Cin,
+                        int Cout, int KH, int KW, int padH, int padW, int num_sms);
 // fp32 output map: EPI_F32_SLICES: ws is [splits * N][Hout][Wout][Cout]; EPI_F32_REDUCE: [N][Hout][Wout][Cout]
 void conv_set_f32_output(ConvLaunch* L, float* ws);
 int conv_smem_bytes(int BN);
@@ -115,6 +124,13 @@ int conv_smem_bytes(int BN);
 // ------------------------------------------------------------------ element kernels (elementwise.cu)
 void launch_pack_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st);
 void launch_pack_first_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st);
+// dgrad weights: out[ci][kh'][kw'][co] = w[co][ci][KH-1-kh'][KW-1-kw'] (bf16), the K-major B operand of the
+// transposed convolution
+void launch_pack_conv_weight_dgrad(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st);
+// NHWC bf16 -> planar [N][C][H][pitch] bf16 (pitch >= W, padding columns zeroed)
+void launch_nhwc_to_planar_bf16(const bf16* in, bf16* out, int N, int H, int W, int C, int pitch, cudaStream_t st);
+// grad[co][ci][kh][kw] (Torch layout, fp32) += dw_taps[co][kh*KW+kw][ci]
+void launch_wgrad_finish(const float* dw_taps, float* grad, int Cout, int Cin, int KH, int KW, cudaStream_t st);
 void launch_pack_fc_weight(const float* w, bf16* out, int nout, int C, int bins, int permute, cudaStream_t st);
 void launch_maxpool2x2(const bf16* in, bf16* out, int N, int H, int W, int C, cudaStream_t st);
 // AnchorNetwork tails of all heads in one launch (mid width 256, 18 outputs: model_utilities.lua:29-35)

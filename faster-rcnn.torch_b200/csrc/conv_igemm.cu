@@ -72,6 +72,13 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
   t.k_begin = ks * k_per_split;
   t.k_end = min(p.k_iters, t.k_begin + k_per_split);
   t.m0 = t.w0;  // first GEMM row of the tile; only used with m_limit (GEMM use: BH == 1, N == 1, tiles_h == 1)
+  if (p.wgrad) {
+    // M index = (tap, 128-row Cout tile): the epilogue's reduce-add coordinates are (ci, tap, co, 0)
+    t.w0 = mt / p.co_tiles;               // filter tap
+    t.h0 = (mt % p.co_tiles) * BLOCK_M;   // first output channel
+    t.n_img = 0;
+    t.m0 = 0;
+  }
   return t;
 }
 
@@ -290,6 +297,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
   constexpr int B_STAGE_BYTES = BN * BLOCK_K * 2;
   constexpr uint32_t TX_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BN);
+  constexpr uint32_t IDESC_MN = ptx::make_idesc_bf16(BLOCK_M, BN, 1, 1);  // both operands MN-major (wgrad)
   constexpr int TMEM_COLS = tmem_cols(BN, MT);
 
   extern __shared__ uint8_t smem_raw[];
@@ -356,15 +364,34 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         const CUtensorMap& tmA = maps.a[gi];
         const CUtensorMap& tmB = maps.b[gi];
         for (int k = t.k_begin; k < t.k_end; ++k) {
-          int tap = k / p.cchunks;
-          int cc = k - tap * p.cchunks;
-          int kh = tap / p.KW;
-          int kw = tap - kh * p.KW;
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full_bar[stage], TX_BYTES);
-          ptx::tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], cc * BLOCK_K, t.w0 + kw - p.padW,
-                           t.h0 + kh - p.padH, t.n_img);
-          ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], k * BLOCK_K, t.n0);
+          if (p.wgrad) {
+            // K = output pixels in patches of BW x BH = 64: k -> (image, patch row, patch column).  A = dY patch
+            // [64 px][128 co], B = X patch shifted by the tap [64 px][BN ci]: MN-major operands, one 8 KB TMA box per
+            // 64 channels; the tap shift / zero padding are coordinates of the (unconstrained) W, H dimensions
+            const int per_img = p.tiles_h * p.wchunks;
+            const int n = k / per_img;
+            const int r = k - n * per_img;
+            const int ph = r / p.wchunks;
+            const int pw = r - ph * p.wchunks;
+            const int kh = t.w0 / p.KW, kw = t.w0 - kh * p.KW;
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i)
+              ptx::tma_load_4d(smem_a + stage * A_STAGE_BYTES + i * 8192, &tmA, &full_bar[stage], t.h0 + 64 * i, pw * p.BW, ph * p.BH, n);
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              ptx::tma_load_4d(smem_b + stage * B_STAGE_BYTES + j * 8192, &tmB, &full_bar[stage], t.n0 + 64 * j, pw * p.BW + kw - p.padW,
+                               ph * p.BH + kh - p.padH, n);
+          } else {
+            int tap = k / p.cchunks;
+            int cc = k - tap * p.cchunks;
+            int kh = tap / p.KW;
+            int kw = tap - kh * p.KW;
+            ptx::tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], cc * BLOCK_K, t.w0 + kw - p.padW,
+                             t.h0 + kh - p.padH, t.n_img);
+            ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], k * BLOCK_K, t.n0);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -389,16 +416,26 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         for (int k = t.k_begin; k < t.k_end; ++k) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
+          if (grp.p[gi].wgrad) {
+            // MN-major operands: [64 K rows (pixels)][64 channels = 128 B] atoms, 8-row groups 1024 B apart (SBO), the
+            // next 64 channels 8 KB further (LBO); one K = 16 step = 16 rows = 2048 B
+            const uint64_t da = ptx::make_desc_mn_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES), 8192);
+            const uint64_t db = ptx::make_desc_mn_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES), 8192);
 #pragma unroll
-          for (int j = 0; j < BLOCK_K / 16; ++j) {
+            for (int j = 0; j < BLOCK_K / 16; ++j)
+              ptx::mma_bf16_ss(d_tmem, da + (uint64_t)(j * 2048 >> 4), db + (uint64_t)(j * 2048 >> 4), IDESC_MN, (k > t.k_begin || j > 0) ? 1u : 0u);
+          } else {
+            const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES));
+            const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field; the second
-              // 128-row sub-tile starts 16 KB further
-              ptx::mma_bf16_ss(d_tmem + mt * BN, da + 2 * j + mt * (A_SUB_BYTES >> 4), db + 2 * j, IDESC,
-                               (k > t.k_begin || j > 0) ? 1u : 0u);
+            for (int j = 0; j < BLOCK_K / 16; ++j) {
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field; the second
+                // 128-row sub-tile starts 16 KB further
+                ptx::mma_bf16_ss(d_tmem + mt * BN, da + 2 * j + mt * (A_SUB_BYTES >> 4), db + 2 * j, IDESC,
+                                 (k > t.k_begin || j > 0) ? 1u : 0u);
+              }
             }
           }
           ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
@@ -740,6 +777,66 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
   make_tmap_weight(&L->tmB, w_packed, Cout, KH * KW * Cin, BN);
   make_out_map(L, out);
   int total = p.n_tiles_m * p.n_tiles_n * p.splits;
+  L->grid = total < num_sms ? total : num_sms;
+}
+
+void conv_wgrad_prepare(ConvLaunch* L, const bf16* dy, const bf16* x, float* dw_taps, int N, int Hin, int Win, int Cin, int Cout,
+                        int KH, int KW, int padH, int padW, int num_sms) {
+  FRCNN_REQUIRE(Cin % 64 == 0 && Cout % 64 == 0, FRCNN_E_INVALID, "wgrad: channel counts must be multiples of 64");
+  ConvParams& p = L->p;
+  p = ConvParams();
+  L->first = false;
+  L->w_first = nullptr;
+  p.N = N; p.Hin = Hin; p.Win = Win; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.padH = padH; p.padW = padW;
+  p.Hout = Hin + 2 * padH - KH + 1;
+  p.Wout = Win + 2 * padW - KW + 1;
+  FRCNN_REQUIRE(p.Hout > 0 && p.Wout > 0, FRCNN_E_INVALID, "wgrad: input smaller than the kernel");
+  const int BN = Cin % 256 == 0 ? 256 : (Cin % 192 == 0 ? 192 : (Cin % 128 == 0 ? 128 : 64));
+  L->BN = BN;
+  p.MT = 1;
+  p.wgrad = 1;
+  // K chunks = BW x BH = 64 output pixels: the rectangle that wastes the fewest padded pixels
+  long best = -1;
+  for (int bw = 64; bw >= 1; bw >>= 1) {
+    const int bh = 64 / bw;
+    const long padded = (long)((p.Wout + bw - 1) / bw) * bw * (long)((p.Hout + bh - 1) / bh) * bh;
+    if (best < 0 || padded < best) {
+      best = padded;
+      p.BW = bw;
+      p.BH = bh;
+    }
+  }
+  p.bw_shift = 0;
+  while ((1 << p.bw_shift) < p.BW) ++p.bw_shift;
+  p.co_tiles = (Cout + BLOCK_M - 1) / BLOCK_M;
+  p.wchunks = (p.Wout + p.BW - 1) / p.BW;           // patch columns
+  p.tiles_h = (p.Hout + p.BH - 1) / p.BH;           // patch rows
+  p.tiles_w = KH * KW * p.co_tiles;
+  p.n_tiles_m = KH * KW * p.co_tiles;
+  p.n_tiles_n = (Cin + BN - 1) / BN;
+  p.cchunks = 1;
+  p.k_iters = N * p.tiles_h * p.wchunks;
+  p.mode = EPI_F32_REDUCE;
+  p.scale = 1.f;
+  // split the pixel dimension so that the units fill the machine about twice, at least 8 K iterations each
+  const int base = p.n_tiles_m * p.n_tiles_n;
+  int splits = (2 * num_sms + base - 1) / base;
+  splits = std::max(1, std::min(splits, std::max(1, p.k_iters / 8)));
+  p.k_per_split = (p.k_iters + splits - 1) / splits;
+  p.splits = (p.k_iters + p.k_per_split - 1) / p.k_per_split;
+  make_tmap_act(&L->tmA, dy, N, p.Hout, p.Wout, Cout, p.BW, p.BH);
+  make_tmap_act(&L->tmB, x, N, Hin, Win, Cin, p.BW, p.BH);
+  // output dW[co][tap][ci] fp32: dims {Cin, taps, Cout, 1}, box {32 ci, 1 tap, 128 co, 1} = the staging tile
+  p.out = dw_taps;
+  cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)(KH * KW), (cuuint64_t)Cout, 1};
+  cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)KH * KW * Cin * 4, (cuuint64_t)Cout * KH * KW * Cin * 4};
+  cuuint32_t box[4] = {32, 1, BLOCK_M, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = get_encode()(&L->tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dw_taps, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FRCNN_REQUIRE(r == CUDA_SUCCESS, FRCNN_E_CUDA, "cuTensorMapEncodeTiled(wgrad out) failed, CUresult " + std::to_string((int)r));
+  const int total = p.n_tiles_m * p.n_tiles_n * p.splits;
   L->grid = total < num_sms ? total : num_sms;
 }
 

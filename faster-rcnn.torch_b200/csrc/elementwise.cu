@@ -39,6 +39,60 @@ void launch_pack_first_conv_weight(const float* w, bf16* out, int Cout, int Cin,
   pack_first_conv_weight_kernel<<<cdiv(Cout * 32, 256), 256, 0, st>>>(w, out, Cout, Cin * KH * KW);
 }
 
+__global__ void pack_conv_weight_dgrad_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int KH,
+                                              int KW) {
+  long total = (long)Cout * Cin * KH * KW;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int co = i % Cout;
+    long r = i / Cout;
+    int kw = r % KW;
+    r /= KW;
+    int kh = r % KH;
+    int ci = r / KH;
+    out[i] = __float2bfloat16_rn(w[(((long)co * Cin + ci) * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)]);
+  }
+}
+void launch_pack_conv_weight_dgrad(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st) {
+  long total = (long)Cout * Cin * KH * KW;
+  pack_conv_weight_dgrad_kernel<<<min(cdiv(total, 256), 148 * 8), 256, 0, st>>>(w, out, Cout, Cin, KH, KW);
+}
+
+__global__ void wgrad_finish_kernel(const float* __restrict__ dw, float* __restrict__ grad, int Cout, int Cin, int taps) {
+  long total = (long)Cout * Cin * taps;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int t = i % taps;
+    long r = i / taps;
+    int ci = r % Cin;
+    int co = r / Cin;
+    grad[i] += dw[((long)co * taps + t) * Cin + ci];
+  }
+}
+void launch_wgrad_finish(const float* dw_taps, float* grad, int Cout, int Cin, int KH, int KW, cudaStream_t st) {
+  long total = (long)Cout * Cin * KH * KW;
+  wgrad_finish_kernel<<<min(cdiv(total, 256), 148 * 8), 256, 0, st>>>(dw_taps, grad, Cout, Cin, KH * KW);
+}
+
+// NHWC bf16 -> planar [N][C][H][pitch] bf16 through a 32 x 32 shared-memory transpose of (pixel-in-row, channel)
+__global__ void nhwc_to_planar_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int H, int W, int C, int pitch) {
+  __shared__ bf16 tile[32][34];
+  const int n = blockIdx.z / H, h = blockIdx.z % H;
+  const int w0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const bf16 zero = __float2bfloat16_rn(0.f);
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int w = w0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (w < W && c < C) ? in[(((long)n * H + h) * W + w) * C + c] : zero;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    int c = c0 + j, w = w0 + threadIdx.x;
+    if (w < pitch && c < C) out[(((long)n * C + c) * H + h) * pitch + w] = tile[threadIdx.x][j];
+  }
+}
+void launch_nhwc_to_planar_bf16(const bf16* in, bf16* out, int N, int H, int W, int C, int pitch, cudaStream_t st) {
+  dim3 grid(cdiv(pitch, 32), cdiv(C, 32), N * H), block(32, 8);
+  nhwc_to_planar_kernel<<<grid, block, 0, st>>>(in, out, H, W, C, pitch);
+}
+
 // Linear weight [nout][K] fp32 -> bf16.  With permute: K index c*bins + b (reference ROI-pool flatten order,
 // Detector.lua:97) -> b*C + c (the channel-contiguous order the ROI-pool kernel writes).
 __global__ void pack_fc_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int nout, int C, int bins,

@@ -191,6 +191,14 @@ int frcnn_last_conv_profile(const frcnn_ctx* ctx, float* ms, double* flops, int*
 int frcnn_conv_bf16(frcnn_ctx* ctx, const uint16_t* x_dev, const float* w_dev, const float* bias_dev,
                     const float* prelu_dev, float scale, int n, int h, int w, int cin, int cout, int k, int pad,
                     int splits, int bn, int mt, int pool, uint16_t* out_dev, int iters, float* elapsed_ms);
+/* Backward primitives of nn.SpatialConvolution (pnet:backward, objective.lua:189), stride 1, NHWC bf16 tensors:
+ * dgrad: dx[n][h][w][cin] = conv_transpose(dy[n][ho][wo][cout], w); wgrad: dw (fp32, Torch layout [cout][cin][k][k])
+ * += sum over pixels of dy (x) x.  Both run on the tcgen05 conv kernel (dgrad: flipped filters, padding k-1-pad;
+ * wgrad: K = output pixels over planar copies of x and dy, one filter tap per work unit, TMA reduce-add). */
+int frcnn_conv_dgrad_bf16(frcnn_ctx* ctx, const uint16_t* dy_dev, const float* w_dev, int n, int h, int w, int cin,
+                          int cout, int k, int pad, uint16_t* dx_dev);
+int frcnn_conv_wgrad_bf16(frcnn_ctx* ctx, const uint16_t* x_dev, const uint16_t* dy_dev, int n, int h, int w, int cin,
+                          int cout, int k, int pad, float* dw_dev);
 /* The fused first layer: img_dev [n][3][h][w] fp32 (Torch layout), w_dev [cout = 64][3][3][3] fp32; output as above. */
 int frcnn_conv_first(frcnn_ctx* ctx, const float* img_dev, const float* w_dev, const float* bias_dev,
                      const float* prelu_dev, float scale, int n, int h, int w, int cout, int pad, int pool,
