@@ -11,6 +11,7 @@
 #include "common.h"
 #include "detect.h"
 #include "nms.h"
+#include "train.h"
 
 namespace frcnn {
 
@@ -35,6 +36,12 @@ struct ConvLayer {
   bf16* in = nullptr;
   bf16* out = nullptr;
   ConvLaunch launch;
+  // training
+  float dropout = 0.f;          // SpatialDropout p applied to this conv's output (first conv of a block), else 0
+  float* mask = nullptr;        // [N][cout] Bernoulli(1 - p) mask of the last training forward
+  bf16* w_dgrad = nullptr;      // [cin][k][k][cout] flipped filters (transposed convolution)
+  float* dw_taps = nullptr;     // [cout][k*k][cin] fp32 wgrad accumulator
+  ConvLaunch dgrad, wgrad;
 };
 
 struct Head {
@@ -44,6 +51,7 @@ struct Head {
   float* acc = nullptr;      // [splits * N][hh][hw][n] fp32 split-K slices
   float* out = nullptr;      // [N][18][hh][hw] fp32
   int hh = 0, hw = 0;
+  bf16* dpre = nullptr;      // training: [N][hh][hw][n] gradient wrt the k x k conv's pre-activation output
 };
 
 struct FcLayer {
@@ -90,6 +98,15 @@ struct frcnn_ctx {
   float* d_h_lut = nullptr;
   LocalizerDev roi_loc;
 
+  // training (pnet:backward): gradient views, per-block winners / gradient accumulators, two scratch gradient maps
+  std::vector<float*> grads;
+  bool train_ready = false;      // the last pnet forward ran in training mode on the current workspace
+  int tws_n = 0, tws_h = 0, tws_w = 0;
+  std::vector<void*> tws_allocs;
+  std::vector<uint8_t*> pool_arg;  // per block [N][Hp][Wp][C]
+  std::vector<float*> dblock;      // per block fp32 [N][Hp][Wp][C]: gradient wrt the block's (pooled) output
+  bf16* gscratch[2] = {nullptr, nullptr};
+  const float* train_img = nullptr;
   // thresholds (Detector.lua:54,81,115,133)
   double thr_fg = 0.95, thr_class = 0.2;
   float thr_nms1 = 0.25f, thr_nms2 = 0.1f;
@@ -318,7 +335,10 @@ static void do_plan(frcnn_ctx* c, const frcnn_block_desc* blocks, int n_blocks, 
       cv.first = (cin == 3);
       cv.block = b;
       cv.scale = 1.0f;
-      if (s == 0 && l.dropout > 0.f) cv.scale = dropout_eval_scale < 0.f ? 1.0f - l.dropout : dropout_eval_scale;  // Q5
+      if (s == 0 && l.dropout > 0.f) {
+        cv.scale = dropout_eval_scale < 0.f ? 1.0f - l.dropout : dropout_eval_scale;  // Q5
+        cv.dropout = l.dropout;
+      }
       std::string n = "b" + std::to_string(b + 1) + "_c" + std::to_string(s + 1);
       cv.p_w = add_param(c, n + ".weight", (int64_t)l.filters * cin * l.kH * l.kW);
       cv.p_b = add_param(c, n + ".bias", l.filters);
@@ -392,6 +412,7 @@ static void do_plan(frcnn_ctx* c, const frcnn_block_desc* blocks, int n_blocks, 
     for (int e = 0; e < 6; ++e) c->roi_loc.l[i][e] = c->loc.back()[i][e];
   build_luts(c);
   c->bound.assign(c->params.size(), nullptr);
+  c->grads.assign(c->params.size(), nullptr);
   c->planned = true;
 }
 
@@ -449,6 +470,9 @@ static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
   if (c->ws_n == N && c->ws_h == H && c->ws_w == W) return;
   FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   free_all(c->ws_allocs);
+  free_all(c->tws_allocs);
+  c->tws_n = c->tws_h = c->tws_w = 0;
+  c->train_ready = false;
   ++c->ws_gen;
   c->ws_n = c->ws_h = c->ws_w = 0;
   const int nb = (int)c->blocks.size();
@@ -577,18 +601,31 @@ static void conv_profile_end(frcnn_ctx* c) {
 static void run_conv(frcnn_ctx* c, ConvLayer& cv) {
   cv.launch.p.bias = P(c, cv.p_b);
   cv.launch.p.prelu = P(c, cv.p_prelu);
+  const float keep = cv.launch.p.scale;  // set by the caller (evaluate / training)
   conv_launch_timed(c, cv.launch);
+  (void)keep;
 }
 
-static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, int W) {
+static void ensure_train_workspace(frcnn_ctx* c, int N, int H, int W);
+
+static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, int W, bool train = false) {
   FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called before the forward pass");
   FRCNN_REQUIRE(N >= 1 && H >= 16 && W >= 16, FRCNN_E_INVALID, "bad input size");
   ensure_pnet_workspace(c, N, H, W);
+  if (train) ensure_train_workspace(c, N, H, W);
+  c->train_ready = train;
+  c->train_img = train ? img_dev : nullptr;
   size_t li = 0;
   for (size_t b = 0; b < c->blocks.size(); ++b) {
     for (int s = 0; s < c->blocks[b].conv_steps; ++s, ++li) {
       ConvLayer& cv = c->trunk[li];
       if (cv.first) cv.launch.p.img = img_dev;
+      // evaluate: SpatialDropout multiplies by (1 - p) (Q5); training: per-(image, channel) Bernoulli mask, no rescale,
+      // and the pooled convs remember the winner of every window for the backward pass
+      const bool masked = train && cv.dropout > 0.f;
+      cv.launch.p.scale = masked ? 1.0f : (train ? 1.0f : cv.scale);
+      cv.launch.p.chan_scale = masked ? cv.mask : nullptr;
+      cv.launch.p.pool_arg = (train && cv.pooled) ? c->pool_arg[b] : nullptr;
       run_conv(c, cv);
     }
   }
@@ -620,6 +657,154 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
     }
     launch_head_tail_group(tg, c->sm_count, c->stream);
     ++c->launches;
+  }
+  FRCNN_CUDA_TRY(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------- training workspace
+static float* G(frcnn_ctx* c, int idx) { return idx >= 0 ? c->grads[idx] : nullptr; }
+
+// buffers and prepared dgrad / wgrad launches of pnet:backward for the (N, H, W) activation workspace
+static void ensure_train_workspace(frcnn_ctx* c, int N, int H, int W) {
+  if (c->tws_n == N && c->tws_h == H && c->tws_w == W) return;
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  free_all(c->tws_allocs);
+  c->tws_n = c->tws_h = c->tws_w = 0;
+  auto& A = c->tws_allocs;
+  const int nb = (int)c->blocks.size();
+  c->pool_arg.assign(nb, nullptr);
+  c->dblock.assign(nb, nullptr);
+  size_t max_map = 0;
+  size_t li = 0;
+  for (int b = 0; b < nb; ++b) {
+    const int C = c->blocks[b].filters;
+    c->pool_arg[b] = (uint8_t*)dev_alloc(A, (size_t)N * c->pool_h[b] * c->pool_w[b] * C);
+    c->dblock[b] = (float*)dev_alloc(A, (size_t)N * c->pool_h[b] * c->pool_w[b] * C * sizeof(float));
+    for (int s = 0; s < c->blocks[b].conv_steps; ++s, ++li) {
+      ConvLayer& cv = c->trunk[li];
+      max_map = std::max(max_map, (size_t)N * cv.hout * cv.wout * cv.cout);
+      max_map = std::max(max_map, (size_t)N * cv.hin * cv.win * (size_t)std::max(cv.cin, 64));
+      if (cv.dropout > 0.f) cv.mask = (float*)dev_alloc(A, (size_t)N * cv.cout * sizeof(float));
+      if (!cv.first) {
+        cv.w_dgrad = (bf16*)dev_alloc(A, (size_t)cv.cout * cv.cin * cv.k * cv.k * sizeof(bf16));
+        cv.dw_taps = (float*)dev_alloc(A, (size_t)cv.cout * cv.cin * cv.k * cv.k * sizeof(float));
+      }
+    }
+  }
+  c->gscratch[0] = (bf16*)dev_alloc(A, max_map * sizeof(bf16));
+  c->gscratch[1] = (bf16*)dev_alloc(A, max_map * sizeof(bf16));
+  // trunk launches: dy always lives in gscratch[0] ("cur"), the bf16 dgrad output in gscratch[1]
+  li = 0;
+  for (int b = 0; b < nb; ++b) {
+    for (int s = 0; s < c->blocks[b].conv_steps; ++s, ++li) {
+      ConvLayer& cv = c->trunk[li];
+      if (cv.first) continue;
+      conv_wgrad_prepare(&cv.wgrad, c->gscratch[0], cv.in, cv.dw_taps, N, cv.hin, cv.win, cv.cin, cv.cout, cv.k, cv.k, cv.pad, cv.pad,
+                         c->sm_count);
+      const int padT = cv.k - 1 - cv.pad;
+      if (s > 0) {  // the producer of this conv's input is a plain conv of the same block: bf16 gradient map
+        conv_prepare(&cv.dgrad, c->gscratch[0], cv.w_dgrad, N, cv.hout, cv.wout, cv.cout, cv.cin, cv.k, cv.k, padT, padT, EPI_STORE,
+                     c->gscratch[1], c->sm_count, 0, 0, 0);
+      } else {      // the input is the pooled output of the previous block: accumulate into its fp32 gradient
+        conv_prepare(&cv.dgrad, c->gscratch[0], cv.w_dgrad, N, cv.hout, cv.wout, cv.cout, cv.cin, cv.k, cv.k, padT, padT,
+                     EPI_F32_REDUCE, nullptr, c->sm_count, 1, 0, 0);
+        conv_set_f32_output(&cv.dgrad, c->dblock[b - 1]);
+      }
+    }
+  }
+  for (auto& hd : c->heads) {
+    ConvLayer& cv = hd.conv;
+    hd.dpre = (bf16*)dev_alloc(A, (size_t)N * hd.hh * hd.hw * hd.n * sizeof(bf16));
+    cv.w_dgrad = (bf16*)dev_alloc(A, (size_t)cv.cout * cv.cin * cv.k * cv.k * sizeof(bf16));
+    cv.dw_taps = (float*)dev_alloc(A, (size_t)cv.cout * cv.cin * cv.k * cv.k * sizeof(float));
+    conv_wgrad_prepare(&cv.wgrad, hd.dpre, c->pool_out[hd.input - 1], cv.dw_taps, N, cv.hin, cv.win, cv.cin, cv.cout, cv.k, cv.k, 0, 0,
+                       c->sm_count);
+    conv_prepare(&cv.dgrad, hd.dpre, cv.w_dgrad, N, hd.hh, hd.hw, cv.cout, cv.cin, cv.k, cv.k, cv.k - 1, cv.k - 1, EPI_F32_REDUCE,
+                 nullptr, c->sm_count, 1, 0, 0);
+    conv_set_f32_output(&cv.dgrad, c->dblock[hd.input - 1]);
+  }
+  c->tws_n = N; c->tws_h = H; c->tws_w = W;
+}
+
+// weight gradient of one conv: taps buffer zeroed, tensor-core wgrad, accumulated into the bound Torch-layout gradient
+static void run_wgrad(frcnn_ctx* c, ConvLayer& cv) {
+  FRCNN_CUDA_TRY(cudaMemsetAsync(cv.dw_taps, 0, (size_t)cv.cout * cv.cin * cv.k * cv.k * sizeof(float), c->stream));
+  conv_launch(cv.wgrad, c->stream);
+  launch_wgrad_finish(cv.dw_taps, G(c, cv.p_w), cv.cout, cv.cin, cv.k, cv.k, c->stream);
+  c->launches += 2;
+}
+static void run_dgrad(frcnn_ctx* c, ConvLayer& cv) {
+  launch_pack_conv_weight_dgrad(P(c, cv.p_w), cv.w_dgrad, cv.cout, cv.cin, cv.k, cv.k, c->stream);
+  cv.dgrad.p.bias = nullptr;
+  cv.dgrad.p.prelu = nullptr;
+  cv.dgrad.p.scale = 1.f;
+  conv_launch(cv.dgrad, c->stream);
+  c->launches += 2;
+}
+
+// pnet:backward(img, delta_outputs) (objective.lua:189): parameter gradients are ACCUMULATED into the bound gradient
+// views (the reference zeroes them once per batch, objective.lua:49); the input gradient is not computed (unused).
+static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out) {
+  FRCNN_REQUIRE(c->train_ready, FRCNN_E_STATE, "pnet:backward needs a preceding training-mode forward on this context");
+  for (auto g : c->grads) FRCNN_REQUIRE(g != nullptr, FRCNN_E_STATE, "frcnn_bind_grads must be called before the backward pass");
+  const int N = c->ws_n, nb = (int)c->blocks.size();
+  cudaStream_t st = c->stream;
+  for (int b = 0; b < nb; ++b)
+    FRCNN_CUDA_TRY(cudaMemsetAsync(c->dblock[b], 0, (size_t)N * c->pool_h[b] * c->pool_w[b] * c->blocks[b].filters * sizeof(float), st));
+  // delta_outputs[5]: ROI-pool gradients on the last conv block (objective.lua:184)
+  const int nh = (int)c->heads.size();
+  if (d_out[nh]) {
+    launch_add_chw_to_nhwc(d_out[nh], c->dblock[nb - 1], N, c->feat_h, c->feat_w, c->feat_c, st);
+    ++c->launches;
+  }
+  // anchor heads
+  for (int i = 0; i < nh; ++i) {
+    if (!d_out[i]) continue;
+    Head& hd = c->heads[i];
+    HeadTailBwd hb;
+    hb.d_out = d_out[i];
+    hb.ws = hd.acc;
+    hb.splits = hd.conv.launch.p.splits;
+    hb.npix = (long)N * hd.hh * hd.hw;
+    hb.slice_stride = hb.npix * hd.n;
+    hb.HW = hd.hh * hd.hw;
+    hb.bias = P(c, hd.conv.p_b); hb.prelu = P(c, hd.conv.p_prelu); hb.w2 = P(c, hd.p_w2);
+    hb.dpre = hd.dpre;
+    hb.dw2 = G(c, hd.p_w2); hb.db2 = G(c, hd.p_b2); hb.db1 = G(c, hd.conv.p_b); hb.dslope = G(c, hd.conv.p_prelu);
+    launch_head_tail_bwd(hb, c->sm_count, st);
+    ++c->launches;
+    run_wgrad(c, hd.conv);
+    run_dgrad(c, hd.conv);
+  }
+  // trunk, last block first
+  size_t li_end = c->trunk.size();
+  for (int b = nb - 1; b >= 0; --b) {
+    const size_t li_first = li_end - c->blocks[b].conv_steps;
+    ConvLayer& last = c->trunk[li_end - 1];
+    launch_unpool_prelu_bwd(c->dblock[b], c->pool_arg[b], c->pool_out[b], P(c, last.p_prelu), last.dropout > 0.f ? last.mask : nullptr,
+                            c->gscratch[0], G(c, last.p_b), G(c, last.p_prelu), N, last.hout, last.wout, last.cout, c->sm_count, st);
+    ++c->launches;
+    for (size_t li = li_end; li-- > li_first;) {
+      ConvLayer& cv = c->trunk[li];
+      if (cv.first) {
+        launch_first_wgrad(c->gscratch[0], c->train_img, G(c, cv.p_w), N, cv.hin, cv.win, cv.pad, c->sm_count, st);
+        ++c->launches;
+        break;
+      }
+      run_wgrad(c, cv);
+      run_dgrad(c, cv);
+      if (li > li_first) {
+        // gradient wrt the previous conv's output (bf16, gscratch[1]) -> its pre-activation gradient, which becomes
+        // the next iteration's dy in gscratch[0]
+        ConvLayer& prev = c->trunk[li - 1];
+        launch_prelu_bwd(c->gscratch[1], prev.out, P(c, prev.p_prelu), prev.dropout > 0.f ? prev.mask : nullptr, G(c, prev.p_b),
+                         G(c, prev.p_prelu), N, prev.hout, prev.wout, prev.cout, c->sm_count, st);
+        FRCNN_CUDA_TRY(cudaMemcpyAsync(c->gscratch[0], c->gscratch[1], (size_t)N * prev.hout * prev.wout * prev.cout * sizeof(bf16),
+                                       cudaMemcpyDeviceToDevice, st));
+        ++c->launches;
+      }
+    }
+    li_end = li_first;
   }
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
@@ -1009,6 +1194,7 @@ int frcnn_destroy(frcnn_ctx* c) {
   cudaStreamSynchronize(c->stream);
   frcnn::free_all(c->ws_allocs);
   frcnn::free_all(c->det_allocs);
+  frcnn::free_all(c->tws_allocs);
   if (c->nms_mem) cudaFree(c->nms_mem);
   for (auto& cv : c->trunk) if (cv.w_packed) cudaFree(cv.w_packed);
   for (auto& h : c->heads) if (h.conv.w_packed) cudaFree(h.conv.w_packed);
@@ -1164,6 +1350,71 @@ int frcnn_pnet_forward(frcnn_ctx* c, const float* img_dev, int n, int h, int w, 
     }
   }
   FRCNN_CUDA_TRY(cudaGetLastError());
+  API_END(c)
+}
+
+int frcnn_bind_grads(frcnn_ctx* c, float* const* grads_dev, int n) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(c->planned, FRCNN_E_STATE, "frcnn_model_plan must be called first");
+  FRCNN_REQUIRE(grads_dev && n == (int)c->params.size(), FRCNN_E_INVALID,
+                "expected " + std::to_string(c->params.size()) + " gradient pointers");
+  for (int i = 0; i < n; ++i) {
+    FRCNN_REQUIRE(grads_dev[i] != nullptr, FRCNN_E_INVALID, "null gradient pointer: " + c->params[i].name);
+    c->grads[i] = grads_dev[i];
+  }
+  API_END(c)
+}
+
+int frcnn_dropout_layers(const frcnn_ctx* c, int* channels, int cap, int* n_layers) {
+  if (!c || !c->planned || !n_layers) return FRCNN_E_INVALID;
+  int n = 0;
+  for (const auto& cv : c->trunk)
+    if (cv.dropout > 0.f) {
+      if (channels && n < cap) channels[n] = cv.cout;
+      ++n;
+    }
+  *n_layers = n;
+  return FRCNN_OK;
+}
+
+int frcnn_pnet_forward_train(frcnn_ctx* c, const float* img_dev, int n, int h, int w, float* const* out_dev,
+                             const float* const* masks_dev, uint64_t seed) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(img_dev != nullptr, FRCNN_E_INVALID, "null image");
+  frcnn::ensure_pnet_workspace(c, n, h, w);
+  frcnn::ensure_train_workspace(c, n, h, w);
+  // SpatialDropout masks: injected by the caller (parity tests) or drawn from the seed
+  int mi = 0;
+  for (auto& cv : c->trunk) {
+    if (cv.dropout <= 0.f) continue;
+    if (masks_dev && masks_dev[mi]) {
+      FRCNN_CUDA_TRY(cudaMemcpyAsync(cv.mask, masks_dev[mi], (size_t)n * cv.cout * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+      frcnn::launch_dropout_mask(cv.mask, n * cv.cout, cv.dropout, seed, (uint32_t)mi, c->stream);
+      ++c->launches;
+    }
+    ++mi;
+  }
+  frcnn::conv_profile_begin(c);
+  frcnn::do_pnet_forward(c, img_dev, n, h, w, true);
+  if (out_dev) {
+    for (size_t i = 0; i < c->heads.size(); ++i)
+      if (out_dev[i])
+        FRCNN_CUDA_TRY(cudaMemcpyAsync(out_dev[i], c->heads[i].out, (size_t)n * 18 * c->heads[i].hh * c->heads[i].hw * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, c->stream));
+    if (out_dev[c->heads.size()]) {
+      frcnn::launch_nhwc_bf16_to_chw_f32(c->pool_out.back(), out_dev[c->heads.size()], n, c->feat_h, c->feat_w, c->feat_c, c->stream);
+      ++c->launches;
+    }
+  }
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  API_END(c)
+}
+
+int frcnn_pnet_backward(frcnn_ctx* c, const float* const* d_out_dev) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(d_out_dev != nullptr, FRCNN_E_INVALID, "null delta_outputs");
+  frcnn::do_pnet_backward(c, d_out_dev);
   API_END(c)
 }
 

@@ -64,6 +64,8 @@ struct ConvParams {
   const float* bias;        // [Cout] or null
   const float* prelu;       // device pointer to the shared slope, or null (identity)
   float scale;              // post-activation scale (SpatialDropout eval factor), 1 if none
+  const float* chan_scale;  // training: per-(image, channel) SpatialDropout mask [N][Cout] (0 / 1, no rescale), or null
+  uint8_t* pool_arg;        // training, EPI_POOL: winner of every 2x2 window (0..3 = dy*2+dx) [N][Hp][Wp][Cout], or null
   void* out;                // EPI_STORE: bf16 NHWC [N][Hout][Wout][Cout]; EPI_POOL: its pooled map; fp32 modes: workspace
   const int* m_limit;       // optional device int: tiles whose first row >= *m_limit are skipped (GEMM rows)
   int dyn_ctas;             // with m_limit: > 0 = choose the split-K factor on the device so that the tiles of the

@@ -225,10 +225,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
               const float x1 = __uint_as_float(v[4 * j + 1]) + __uint_as_float(bq[j].y);
               const float x2 = __uint_as_float(v[4 * j + 2]) + __uint_as_float(bq[j].z);
               const float x3 = __uint_as_float(v[4 * j + 3]) + __uint_as_float(bq[j].w);
-              const float y0 = fmaf(fminf(x0, 0.f), k_neg, x0 * k_pos);
-              const float y1 = fmaf(fminf(x1, 0.f), k_neg, x1 * k_pos);
-              const float y2 = fmaf(fminf(x2, 0.f), k_neg, x2 * k_pos);
-              const float y3 = fmaf(fminf(x3, 0.f), k_neg, x3 * k_pos);
+              float y0 = fmaf(fminf(x0, 0.f), k_neg, x0 * k_pos);
+              float y1 = fmaf(fminf(x1, 0.f), k_neg, x1 * k_pos);
+              float y2 = fmaf(fminf(x2, 0.f), k_neg, x2 * k_pos);
+              float y3 = fmaf(fminf(x3, 0.f), k_neg, x3 * k_pos);
+              if (p.chan_scale) {  // training: SpatialDropout mask of this image's channels
+                const float4 m = __ldg(reinterpret_cast<const float4*>(p.chan_scale + (size_t)t.n_img * p.Cout + cbase + half * 32) + j);
+                y0 *= m.x; y1 *= m.y; y2 *= m.z; y3 *= m.w;
+              }
               o[2 * j] = ptx::pack_bf16x2(y0, y1);
               o[2 * j + 1] = ptx::pack_bf16x2(y2, y3);
             }
@@ -260,6 +264,25 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
                 const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
                 const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&cc);
                 const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&d);
+                if (p.pool_arg) {
+                  // training: remember the winner (first maximum in window scan order, as nn.SpatialMaxPooling)
+                  const bf16* ea = reinterpret_cast<const bf16*>(&a);
+                  const bf16* eb = reinterpret_cast<const bf16*>(&b);
+                  const bf16* ec = reinterpret_cast<const bf16*>(&cc);
+                  const bf16* ed = reinterpret_cast<const bf16*>(&d);
+                  uint32_t lo = 0, hi = 0;
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) {
+                    float best = __bfloat162float(ea[e]);
+                    uint32_t arg = 0;
+                    const float vb = __bfloat162float(eb[e]), vc = __bfloat162float(ec[e]), vd = __bfloat162float(ed[e]);
+                    if (vb > best) { best = vb; arg = 1; }
+                    if (vc > best) { best = vc; arg = 2; }
+                    if (vd > best) { best = vd; arg = 3; }
+                    if (e < 4) lo |= arg << (8 * e); else hi |= arg << (8 * (e - 4));
+                  }
+                  *reinterpret_cast<uint2*>(p.pool_arg + (((size_t)t.n_img * Hp + ph) * Wp + pw) * p.Cout + cbase + c * 8) = make_uint2(lo, hi);
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) pa[j] = __hmax2(__hmax2(pa[j], pb[j]), __hmax2(pc[j], pd[j]));
                 *reinterpret_cast<uint4*>(out_img + ((size_t)ph * Wp + pw) * p.Cout + cbase + c * 8) = a;

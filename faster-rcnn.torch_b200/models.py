@@ -22,8 +22,9 @@ imgnet_cfg = dict(class_count=200, target_smaller_side=480, scales=[48, 96, 192,
 class _Net:
     """Stands in for an nn.gModule: forward()/evaluate()/training() with the reference's call shapes."""
 
-    def __init__(self, fwd):
+    def __init__(self, fwd, bwd=None):
         self._fwd = fwd
+        self._bwd = bwd
         self.train = False
 
     def forward(self, *a, **k):
@@ -35,7 +36,12 @@ class _Net:
         self.train = False
 
     def training(self):
-        raise NotImplementedError("training-mode forward/backward is not built yet (SURVEY 8a rows P2, O1)")
+        self.train = True
+
+    def backward(self, *a, **k):
+        if self._bwd is None:
+            raise NotImplementedError("backward of this net is not built yet (SURVEY 8a row P3)")
+        return self._bwd(*a, **k)
 
 
 class Model:
@@ -72,7 +78,7 @@ class Model:
             check(self.ctx, L.frcnn_param_info(self.ctx, i, name, 64, numel))
             self.param_names.append(ffi.string(name).decode())
             self.param_numel.append(int(numel[0]))
-        self.pnet = _Net(self._pnet_forward)
+        self.pnet = _Net(self._pnet_forward, self._pnet_backward)
         self.cnet = _Net(self._cnet_forward)
         self.n_heads = len(anchor_nets)
         if self.host_only:
@@ -85,6 +91,19 @@ class Model:
             off += k
         ptrs = ffi.new("const float*[]", [ffi.cast("const float*", self.params[n].data_ptr()) for n in self.param_names])
         check(self.ctx, L.frcnn_bind_params(self.ctx, ptrs, len(self.param_names)))
+        # the flat gradient buffer of combine_and_flatten_parameters (utilities.lua:136-147), same layout as `weights`
+        self.gradient = torch.zeros_like(self.weights)
+        self.grads, off = {}, 0
+        for n, k in zip(self.param_names, self.param_numel):
+            self.grads[n] = self.gradient[off:off + k]
+            off += k
+        gptrs = ffi.new("float*[]", [ffi.cast("float*", self.grads[n].data_ptr()) for n in self.param_names])
+        check(self.ctx, L.frcnn_bind_grads(self.ctx, gptrs, len(self.param_names)))
+        nl = ffi.new("int*")
+        check(self.ctx, L.frcnn_dropout_layers(self.ctx, ffi.NULL, 0, nl))
+        ch = ffi.new("int[]", max(nl[0], 1))
+        check(self.ctx, L.frcnn_dropout_layers(self.ctx, ch, nl[0], nl))
+        self.dropout_channels = [ch[i] for i in range(nl[0])]
 
     def close(self):
         if getattr(self, "ctx", None) is not None:
@@ -117,16 +136,40 @@ class Model:
         check(self.ctx, lib().frcnn_pnet_output_dims(self.ctx, h, w, dims))
         return [tuple(dims[3 * i + j] for j in range(3)) for i in range(self.n_heads + 1)]
 
-    def _pnet_forward(self, img):
-        """pnet:forward(img) (Detector.lua:33): img [3][H][W] (or [N][3][H][W]) fp32 CUDA tensor -> list of the
-        4 anchor-head maps [18][h][w] and the last conv-block map [C][h][w] (leading N if batched)."""
+    def _pnet_forward(self, img, dropout_masks=None, seed=0):
+        """pnet:forward(img) (Detector.lua:33, objective.lua:71): img [3][H][W] (or [N][3][H][W]) fp32 CUDA tensor ->
+        list of the 4 anchor-head maps [18][h][w] and the last conv-block map [C][h][w] (leading N if batched).
+        After pnet.training() the forward runs in training mode (SpatialDropout masks: `dropout_masks` = list of
+        [N][C] 0/1 tensors per dropout layer, or drawn from `seed`) and keeps the state pnet.backward needs."""
         batched = img.dim() == 4
         x = (img if batched else img.unsqueeze(0)).to(self.device, torch.float32).contiguous()
         n, _, h, w = x.shape
         outs = [torch.empty((n,) + d, dtype=torch.float32, device=self.device) for d in self.output_dims(h, w)]
         ptrs = ffi.new("float*[]", [ffi.cast("float*", o.data_ptr()) for o in outs])
-        check(self.ctx, lib().frcnn_pnet_forward(self.ctx, ffi.cast("const float*", x.data_ptr()), n, h, w, ptrs))
+        if self.pnet.train:
+            self._train_img = x  # pnet:backward re-reads the frame (first-layer weight gradient)
+            keep, mp = [], ffi.NULL
+            if dropout_masks is not None:
+                keep = [m.to(self.device, torch.float32).reshape(n, -1).contiguous() for m in dropout_masks]
+                mp = ffi.new("const float*[]", [ffi.cast("const float*", m.data_ptr()) for m in keep])
+            check(self.ctx, lib().frcnn_pnet_forward_train(self.ctx, ffi.cast("const float*", x.data_ptr()), n, h, w, ptrs, mp, seed))
+            torch.cuda.synchronize(self.device)  # `keep` may be released afterwards
+        else:
+            check(self.ctx, lib().frcnn_pnet_forward(self.ctx, ffi.cast("const float*", x.data_ptr()), n, h, w, ptrs))
         return outs if batched else [o[0] for o in outs]
+
+    def _pnet_backward(self, img, delta_outputs):
+        """pnet:backward(img, delta_outputs) (objective.lua:189): accumulates the parameter gradients into
+        `self.gradient`; entries of delta_outputs may be None (= zero)."""
+        keep = [None if d is None else (d if d.dim() == 4 else d.unsqueeze(0)).to(self.device, torch.float32).contiguous()
+                for d in delta_outputs]
+        ptrs = ffi.new("const float*[]", [ffi.NULL if d is None else ffi.cast("const float*", d.data_ptr()) for d in keep])
+        check(self.ctx, lib().frcnn_pnet_backward(self.ctx, ptrs))
+        torch.cuda.synchronize(self.device)
+        return None  # the reference ignores the returned input gradient (objective.lua:189)
+
+    def zero_grad(self):
+        self.gradient.zero_()
 
     def _cnet_forward(self, x):
         """cnet:forward(cinput) (Detector.lua:101): x [R][kh*kw*C] fp32 -> (bbox [R][4], log-softmax [R][classes+1])."""

@@ -120,6 +120,23 @@ int frcnn_pnet_forward(frcnn_ctx* ctx, const float* img_dev, int n, int h, int w
 /* Shapes of the outputs above for an h x w input: dims[i] = {channels, height, width}, i = 0..n_heads */
 int frcnn_pnet_output_dims(const frcnn_ctx* ctx, int h, int w, int* dims3);
 
+/* ---- training: replaces pnet:training() / pnet:forward / pnet:backward (objective.lua:47,71,189) ------------- */
+/* Gradient views in frcnn_param_info order (the flat gradient CudaTensor of utilities.lua:136-147).  Gradients are
+ * ACCUMULATED (the reference zeroes the flat buffer once per batch, objective.lua:49).  Entries of non-learnable
+ * parameters (BatchNorm running statistics) are never written. */
+int frcnn_bind_grads(frcnn_ctx* ctx, float* const* grads_dev, int n);
+/* Channels of every nn.SpatialDropout layer in trunk order (model_utilities.lua:10-12). */
+int frcnn_dropout_layers(const frcnn_ctx* ctx, int* channels, int cap, int* n_layers);
+/* Training-mode forward: SpatialDropout draws one Bernoulli(1 - p) mask per (image, channel) without rescale
+ * (SURVEY Q5); masks_dev[i] ([n][channels_i] fp32 of 0 / 1) injects the masks of dropout layer i (NULL = draw from
+ * seed).  Keeps what frcnn_pnet_backward needs (activations, pooling winners, split-K slices of the heads). */
+int frcnn_pnet_forward_train(frcnn_ctx* ctx, const float* img_dev, int n, int h, int w, float* const* out_dev,
+                             const float* const* masks_dev, uint64_t seed);
+/* pnet:backward(img, delta_outputs): d_out_dev[0..n_heads-1]: [n][18][hi][wi] fp32; d_out_dev[n_heads]: [n][C][hf][wf]
+ * fp32 (ROI-pool gradients, objective.lua:184); NULL entries are treated as zero.  dgrad / wgrad run on the
+ * tcgen05 conv kernel with bf16 gradient maps and fp32 accumulation.  PReLU slopes must be > 0. */
+int frcnn_pnet_backward(frcnn_ctx* ctx, const float* const* d_out_dev);
+
 /* ---- RPN decode: replaces the per-anchor Lua loop Detector.lua:36-66 ------------------------------------- */
 /* heads_dev[i]: [18][hi][wi] fp32 of ONE image.  Writes the ordered match list (layer, y, x, aspect order) to
  * cand_host and its length to n_cand.  threshold = 0.95 in the reference (Detector.lua:54). */

@@ -110,12 +110,18 @@ def prelu(x, slope):
     return torch.where(x > 0, x, x * slope)
 
 
-def pnet_forward(desc, p, img, train=False, dropout_masks=None, dropout_eval_scale=None, quant=None):
+def pnet_forward(desc, p, img, train=False, dropout_masks=None, dropout_eval_scale=None, quant=None, act_quant=None,
+                 tail_quant="same"):
     """create_proposal_net forward (model_utilities.lua:3-58). img: [3][H][W] fp32 (single image, no batch
     dim, as Detector.lua:33).  Returns [o1..o4 (18xhxw), o5 (CxH/16xW/16)].
     `quant`, if given, is applied to every conv input and weight (e.g. bf16 round trip) -- used by the
-    kernel-level tests to separate operand quantisation from accumulation-order effects."""
+    kernel-level tests to separate operand quantisation from accumulation-order effects.  `act_quant` is applied
+    to every trunk activation where the CUDA path stores it (after PReLU / dropout, BEFORE the pool), so that
+    pooling winners and PReLU signs are decided on the same values; `tail_quant` overrides `quant` for the 1x1
+    convs of the anchor heads (the CUDA path keeps them in fp32: pass None)."""
     q = quant or (lambda t: t)
+    aq = act_quant or (lambda t: t)
+    tq = q if tail_quant == "same" else (tail_quant or (lambda t: t))
     x = img.unsqueeze(0)
     block_out = []
     for bi, l in enumerate(desc["layers"]):
@@ -129,6 +135,7 @@ def pnet_forward(desc, p, img, train=False, dropout_masks=None, dropout_eval_sca
                 else:
                     s = (1 - l["dropout"]) if dropout_eval_scale is None else dropout_eval_scale
                     x = x * s
+            x = aq(x)
         x = F.max_pool2d(x, 2, 2, ceil_mode=True)  # model_utilities.lua:23
         block_out.append(x)
     outs = []
@@ -136,7 +143,7 @@ def pnet_forward(desc, p, img, train=False, dropout_masks=None, dropout_eval_sca
         n = "h%d" % (hi + 1)
         y = F.conv2d(q(block_out[a["input"] - 1]), q(p[n + "_conv.weight"]), p[n + "_conv.bias"])
         y = prelu(y, p[n + "_conv.prelu"])
-        y = F.conv2d(q(y), q(p[n + "_out.weight"]), p[n + "_out.bias"])
+        y = F.conv2d(tq(y), tq(p[n + "_out.weight"]), p[n + "_out.bias"])
         outs.append(y[0])
     outs.append(block_out[-1][0])
     return outs
