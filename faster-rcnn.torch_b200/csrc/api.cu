@@ -63,6 +63,11 @@ struct FcLayer {
   bf16* out_bf16 = nullptr;  // [R_cap][nout]
   float* out_f32 = nullptr;  // last layer only
   ConvLaunch launch;
+  float dropout = 0.f;
+  // training buffers for up to cw_rows example rows
+  float *t_acc = nullptr, *t_pre = nullptr, *t_xhat = nullptr, *t_rstd = nullptr, *t_mask = nullptr, *t_din = nullptr, *t_out32 = nullptr;
+  bf16 *t_out = nullptr, *t_dy = nullptr, *w_dgrad = nullptr;
+  float* dw_taps = nullptr;
 };
 
 }  // namespace frcnn
@@ -107,6 +112,15 @@ struct frcnn_ctx {
   std::vector<float*> dblock;      // per block fp32 [N][Hp][Wp][C]: gradient wrt the block's (pooled) output
   bf16* gscratch[2] = {nullptr, nullptr};
   const float* train_img = nullptr;
+  // objective.lua stage buffers (frcnn_train_image), sized for cw_rows examples
+  int cw_rows = 0;
+  std::vector<void*> cw_allocs;
+  ExampleDev* ex_dev = nullptr;
+  double* ex_rects = nullptr;
+  float *crtarget = nullptr, *losses_dev = nullptr, *t_dhidden = nullptr, *t_dz = nullptr, *t_dx = nullptr;
+  int *cctarget = nullptr, *t_status = nullptr, *t_argmax = nullptr;
+  bf16* t_rows = nullptr;
+  std::vector<float*> head_dout;   // per head [18][hh][hw] fp32 (delta_outputs of one frame)
   // thresholds (Detector.lua:54,81,115,133)
   double thr_fg = 0.95, thr_class = 0.2;
   float thr_nms1 = 0.25f, thr_nms2 = 0.1f;
@@ -369,6 +383,7 @@ static void do_plan(frcnn_ctx* c, const frcnn_block_desc* blocks, int n_blocks, 
     FRCNN_REQUIRE(fcs[i].n % 64 == 0, FRCNN_E_INVALID, "class layer width must be a multiple of 64");
     FcLayer f;
     f.nin = fin; f.nout = fcs[i].n; f.bn = fcs[i].batch_norm != 0;
+    f.dropout = fcs[i].dropout;
     std::string n = "fc" + std::to_string(i + 1);
     f.p_w = add_param(c, n + ".weight", (int64_t)f.nout * fin);
     f.p_b = add_param(c, n + ".bias", f.nout);
@@ -744,13 +759,20 @@ static void run_dgrad(frcnn_ctx* c, ConvLayer& cv) {
 
 // pnet:backward(img, delta_outputs) (objective.lua:189): parameter gradients are ACCUMULATED into the bound gradient
 // views (the reference zeroes them once per batch, objective.lua:49); the input gradient is not computed (unused).
-static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out) {
+static void zero_block_grads(frcnn_ctx* c) {
+  const int N = c->ws_n, nb = (int)c->blocks.size();
+  for (int b = 0; b < nb; ++b)
+    FRCNN_CUDA_TRY(cudaMemsetAsync(c->dblock[b], 0, (size_t)N * c->pool_h[b] * c->pool_w[b] * c->blocks[b].filters * sizeof(float),
+                                   c->stream));
+}
+
+// keep_block_grads: the caller has already zeroed the per-block gradient maps and added the ROI-pool gradients
+static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out, bool keep_block_grads = false) {
   FRCNN_REQUIRE(c->train_ready, FRCNN_E_STATE, "pnet:backward needs a preceding training-mode forward on this context");
   for (auto g : c->grads) FRCNN_REQUIRE(g != nullptr, FRCNN_E_STATE, "frcnn_bind_grads must be called before the backward pass");
   const int N = c->ws_n, nb = (int)c->blocks.size();
   cudaStream_t st = c->stream;
-  for (int b = 0; b < nb; ++b)
-    FRCNN_CUDA_TRY(cudaMemsetAsync(c->dblock[b], 0, (size_t)N * c->pool_h[b] * c->pool_w[b] * c->blocks[b].filters * sizeof(float), st));
+  if (!keep_block_grads) zero_block_grads(c);
   // delta_outputs[5]: ROI-pool gradients on the last conv block (objective.lua:184)
   const int nh = (int)c->heads.size();
   if (d_out[nh]) {
@@ -807,6 +829,180 @@ static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out) {
     li_end = li_first;
   }
   FRCNN_CUDA_TRY(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------- objective.lua stage
+static void ensure_objective_workspace(frcnn_ctx* c, int rows) {
+  if (rows <= c->cw_rows && !c->head_dout.empty()) return;
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  free_all(c->cw_allocs);
+  c->cw_rows = 0;
+  auto& A = c->cw_allocs;
+  const int R = std::max(64, (rows + 63) / 64 * 64);
+  const int feat = c->roi_kh * c->roi_kw * c->feat_c;
+  c->ex_dev = (ExampleDev*)dev_alloc(A, (size_t)R * sizeof(ExampleDev));
+  c->ex_rects = (double*)dev_alloc(A, (size_t)R * 4 * sizeof(double));
+  c->crtarget = (float*)dev_alloc(A, (size_t)R * 4 * sizeof(float));
+  c->cctarget = (int*)dev_alloc(A, (size_t)R * sizeof(int));
+  c->losses_dev = (float*)dev_alloc(A, 8 * sizeof(float));
+  c->t_status = (int*)dev_alloc(A, 4 * sizeof(int));
+  c->t_rows = (bf16*)dev_alloc(A, (size_t)R * feat * sizeof(bf16));
+  c->t_argmax = (int*)dev_alloc(A, (size_t)R * feat * sizeof(int));
+  c->t_dx = (float*)dev_alloc(A, (size_t)R * feat * sizeof(float));
+  const int last_n = c->fcs.back().nout;
+  c->t_dhidden = (float*)dev_alloc(A, (size_t)R * last_n * sizeof(float));
+  c->t_dz = (float*)dev_alloc(A, (size_t)R * (c->class_count + 5) * sizeof(float));
+  for (auto& f : c->fcs) {
+    const size_t rn = (size_t)R * f.nout;
+    f.t_acc = (float*)dev_alloc(A, rn * sizeof(float));
+    f.t_pre = (float*)dev_alloc(A, rn * sizeof(float));
+    f.t_xhat = f.bn ? (float*)dev_alloc(A, rn * sizeof(float)) : nullptr;
+    f.t_rstd = (float*)dev_alloc(A, f.nout * sizeof(float));
+    f.t_mask = (float*)dev_alloc(A, rn * sizeof(float));
+    f.t_din = (float*)dev_alloc(A, rn * sizeof(float));
+    f.t_out32 = (float*)dev_alloc(A, rn * sizeof(float));
+    f.t_out = (bf16*)dev_alloc(A, rn * sizeof(bf16));
+    f.t_dy = (bf16*)dev_alloc(A, rn * sizeof(bf16));
+    f.w_dgrad = (bf16*)dev_alloc(A, (size_t)f.nin * f.nout * sizeof(bf16));
+    f.dw_taps = (float*)dev_alloc(A, (size_t)f.nin * f.nout * sizeof(float));
+  }
+  c->head_dout.clear();
+  for (auto& hd : c->heads) c->head_dout.push_back((float*)dev_alloc(A, (size_t)18 * hd.hh * hd.hw * sizeof(float)));
+  c->cw_rows = R;
+}
+
+// [R][nin] bf16 rows x [nout][nin] bf16 weights -> fp32 [R][nout] (plain stores, deterministic)
+static void gemm_rows(frcnn_ctx* c, const bf16* a, const bf16* w, int R, int nin, int nout, float* out) {
+  ConvLaunch L;
+  conv_prepare(&L, a, w, 1, 1, R, nin, nout, 1, 1, 0, 0, EPI_F32_SLICES, nullptr, c->sm_count, 1, 0, 1);
+  conv_set_f32_output(&L, out);
+  conv_launch(L, c->stream);
+  ++c->launches;
+}
+// dW[nout][nin] (fp32 taps buffer, zeroed here) = dy[R][nout]^T x[R][nin]
+static void wgrad_rows(frcnn_ctx* c, const bf16* dy, const bf16* x, int R, int nin, int nout, float* dw) {
+  FRCNN_CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)nin * nout * sizeof(float), c->stream));
+  ConvLaunch L;
+  conv_wgrad_prepare(&L, dy, x, dw, 1, 1, R, nin, nout, 1, 1, 0, 0, c->sm_count);
+  conv_launch(L, c->stream);
+  ++c->launches;
+}
+
+// cnet:forward (training) -> detection-stage criteria -> cnet:backward (objective.lua:164-179) on the R example rows in
+// c->t_rows ([R][bins][C] bf16) with targets c->crtarget / c->cctarget; leaves d(loss)/d(rows) in c->t_dx (fp32, same
+// layout) and adds the losses to c->losses_dev[2..3].
+static void run_cnet_train(frcnn_ctx* c, int R, int n_pos, const float* const* cnet_masks, uint64_t seed) {
+  cudaStream_t st = c->stream;
+  const int bins = c->roi_kh * c->roi_kw;
+  // ---- cnet forward, training mode (objective.lua:164)
+  const bf16* in = c->t_rows;
+  for (size_t i = 0; i < c->fcs.size(); ++i) {
+    FcLayer& f = c->fcs[i];
+    gemm_rows(c, in, f.w_packed, R, f.nin, f.nout, f.t_acc);
+    if (cnet_masks && cnet_masks[i]) FRCNN_CUDA_TRY(cudaMemcpyAsync(f.t_mask, cnet_masks[i], (size_t)R * f.nout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else launch_dropout_mask(f.t_mask, R * f.nout, f.dropout, seed, 100u + (uint32_t)i, st);
+    FcTrainFwd ff;
+    ff.acc = f.t_acc; ff.bias = P(c, f.p_b); ff.bn_w = P(c, f.p_bn_w); ff.bn_b = P(c, f.p_bn_b); ff.prelu = P(c, f.p_prelu);
+    ff.bn_mean = const_cast<float*>(P(c, f.p_bn_mean)); ff.bn_var = const_cast<float*>(P(c, f.p_bn_var));
+    ff.mask = f.t_mask; ff.keep_scale = f.dropout > 0.f ? 1.f / (1.f - f.dropout) : 1.f;
+    ff.pre = f.t_pre; ff.xhat = f.t_xhat; ff.rstd = f.t_rstd; ff.out_bf16 = f.t_out; ff.out_f32 = f.t_out32; ff.R = R; ff.n = f.nout;
+    launch_fc_train_fwd(ff, st);
+    c->launches += 2;
+    in = f.t_out;
+  }
+  // ---- detection-stage criteria + backward through the two output branches (objective.lua:166-179)
+  FcLayer& last = c->fcs.back();
+  CnetLossParams cl;
+  cl.hidden = last.t_out32; cl.w_reg = P(c, c->p_reg_w); cl.b_reg = P(c, c->p_reg_b); cl.w_cls = P(c, c->p_cls_w); cl.b_cls = P(c, c->p_cls_b);
+  cl.crtarget = c->crtarget; cl.cctarget = c->cctarget; cl.R = R; cl.n_pos = n_pos; cl.nin = last.nout; cl.ncls = c->class_count + 1;
+  cl.d_hidden = c->t_dhidden; cl.dz = c->t_dz;
+  cl.g_w_reg = G(c, c->p_reg_w); cl.g_b_reg = G(c, c->p_reg_b); cl.g_w_cls = G(c, c->p_cls_w); cl.g_b_cls = G(c, c->p_cls_b);
+  cl.losses = c->losses_dev;
+  launch_cnet_loss_bwd(cl, st);
+  c->launches += 2;
+  // ---- cnet backward (objective.lua:179)
+  const float* d_in = c->t_dhidden;
+  for (int i = (int)c->fcs.size() - 1; i >= 0; --i) {
+    FcLayer& f = c->fcs[i];
+    FcTrainBwd fb;
+    fb.d_in = d_in; fb.pre = f.t_pre; fb.xhat = f.t_xhat; fb.rstd = f.t_rstd; fb.bn_w = P(c, f.p_bn_w); fb.prelu = P(c, f.p_prelu);
+    fb.mask = f.t_mask; fb.keep_scale = f.dropout > 0.f ? 1.f / (1.f - f.dropout) : 1.f;
+    fb.d_out_bf16 = f.t_dy;
+    fb.g_bias = G(c, f.p_b); fb.g_bn_w = G(c, f.p_bn_w); fb.g_bn_b = G(c, f.p_bn_b); fb.g_prelu = G(c, f.p_prelu);
+    fb.R = R; fb.n = f.nout;
+    launch_fc_train_bwd(fb, st);
+    const bf16* x_in = i == 0 ? c->t_rows : c->fcs[i - 1].t_out;
+    wgrad_rows(c, f.t_dy, x_in, R, f.nin, f.nout, f.dw_taps);
+    const bool perm = i == 0;
+    launch_wgrad_finish_fc(f.dw_taps, G(c, f.p_w), f.nout, perm ? c->feat_c : f.nin, perm ? bins : 1, perm ? 1 : 0, st);
+    launch_pack_fc_weight_dgrad(P(c, f.p_w), f.w_dgrad, f.nout, perm ? c->feat_c : f.nin, perm ? bins : 1, perm ? 1 : 0, st);
+    float* d_prev = i == 0 ? c->t_dx : c->fcs[i - 1].t_din;
+    gemm_rows(c, f.t_dy, f.w_dgrad, R, f.nout, f.nin, d_prev);
+    c->launches += 3;
+    d_in = d_prev;
+  }
+}
+
+static void do_train_image(frcnn_ctx* c, const float* img_dev, int H, int W, const frcnn_example* pos, int n_pos,
+                           const frcnn_example* neg, int n_neg, const float* const* pnet_masks, const float* const* cnet_masks,
+                           uint64_t seed, float losses_host[4]) {
+  static_assert(sizeof(frcnn_example) == sizeof(ExampleDev), "example layouts must match");
+  FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called first");
+  for (auto g : c->grads) FRCNN_REQUIRE(g != nullptr, FRCNN_E_STATE, "frcnn_bind_grads must be called first");
+  const int R = n_pos + n_neg;
+  cudaStream_t st = c->stream;
+  ensure_pnet_workspace(c, 1, H, W);
+  ensure_train_workspace(c, 1, H, W);
+  ensure_objective_workspace(c, R);
+  // ---- pnet forward, training mode (objective.lua:60,71)
+  int mi = 0;
+  for (auto& cv : c->trunk) {
+    if (cv.dropout <= 0.f) continue;
+    if (pnet_masks && pnet_masks[mi]) FRCNN_CUDA_TRY(cudaMemcpyAsync(cv.mask, pnet_masks[mi], cv.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else launch_dropout_mask(cv.mask, cv.cout, cv.dropout, seed, (uint32_t)mi, st);
+    ++mi;
+  }
+  do_pnet_forward(c, img_dev, 1, H, W, true);
+  FRCNN_CUDA_TRY(cudaMemsetAsync(c->losses_dev, 0, 8 * sizeof(float), st));
+  FRCNN_CUDA_TRY(cudaMemsetAsync(c->t_status, 0, 4 * sizeof(int), st));
+  for (size_t i = 0; i < c->heads.size(); ++i)
+    FRCNN_CUDA_TRY(cudaMemsetAsync(c->head_dout[i], 0, (size_t)18 * c->heads[i].hh * c->heads[i].hw * sizeof(float), st));
+  zero_block_grads(c);
+  if (R > 0) {
+    // ---- RPN criteria on the listed anchors (objective.lua:91-140)
+    if (n_pos) FRCNN_CUDA_TRY(cudaMemcpyAsync(c->ex_dev, pos, (size_t)n_pos * sizeof(ExampleDev), cudaMemcpyHostToDevice, st));
+    if (n_neg) FRCNN_CUDA_TRY(cudaMemcpyAsync(c->ex_dev + n_pos, neg, (size_t)n_neg * sizeof(ExampleDev), cudaMemcpyHostToDevice, st));
+    RpnLossParams lp;
+    lp.ex = c->ex_dev; lp.n_pos = n_pos; lp.n_neg = n_neg;
+    for (int i = 0; i < MAX_HEADS; ++i) {
+      lp.out[i] = c->heads[i].out; lp.d_out[i] = c->head_dout[i]; lp.hh[i] = c->heads[i].hh; lp.hw[i] = c->heads[i].hw;
+    }
+    lp.crtarget = c->crtarget; lp.cctarget = c->cctarget; lp.bg_class = c->class_count; lp.rects = c->ex_rects;
+    lp.losses = c->losses_dev; lp.status = c->t_status;
+    launch_rpn_loss(lp, st);
+    // ---- ROI pooling of ground-truth rects / negative anchors (objective.lua:117-119,137-139)
+    const int bins = c->roi_kh * c->roi_kw, feat = bins * c->feat_c;
+    launch_roi_pool_train(c->pool_out.back(), c->feat_h, c->feat_w, c->feat_c, c->roi_kh, c->roi_kw, c->roi_loc, c->ex_rects, R,
+                          c->t_rows, c->t_argmax, c->t_status + 1, st);
+    c->launches += 2;
+    run_cnet_train(c, R, n_pos, cnet_masks, seed);
+    // ---- ROI-pool backward into delta_outputs[5] (objective.lua:182-185), kept as the fp32 NHWC block gradient
+    launch_roi_pool_bwd(c->t_dx, c->t_argmax, R, bins, c->feat_c, c->dblock.back(), st);
+    ++c->launches;
+    (void)feat;
+  }
+  // ---- pnet backward (objective.lua:189)
+  std::vector<const float*> d_out(c->heads.size() + 1, nullptr);
+  for (size_t i = 0; i < c->heads.size(); ++i) d_out[i] = c->head_dout[i];
+  do_pnet_backward(c, d_out.data(), true);
+  float lh[8];
+  int sh[4];
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(lh, c->losses_dev, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(sh, c->t_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
+  for (int i = 0; i < 4; ++i) losses_host[i] = lh[i];
+  FRCNN_REQUIRE(sh[0] == 0, FRCNN_E_INVALID, "an example indexes outside its anchor map: apply cleanAnchors first (objective.lua:32-43)");
+  FRCNN_REQUIRE(sh[1] == 0, FRCNN_E_ROI_EMPTY, "an ROI clipped to max == 0; the reference raises an index error here (objective.lua:11)");
 }
 
 // detector / cnet workspace for a batch of N images
@@ -1195,6 +1391,7 @@ int frcnn_destroy(frcnn_ctx* c) {
   frcnn::free_all(c->ws_allocs);
   frcnn::free_all(c->det_allocs);
   frcnn::free_all(c->tws_allocs);
+  frcnn::free_all(c->cw_allocs);
   if (c->nms_mem) cudaFree(c->nms_mem);
   for (auto& cv : c->trunk) if (cv.w_packed) cudaFree(cv.w_packed);
   for (auto& h : c->heads) if (h.conv.w_packed) cudaFree(h.conv.w_packed);
@@ -1415,6 +1612,52 @@ int frcnn_pnet_backward(frcnn_ctx* c, const float* const* d_out_dev) {
   API_BEGIN(c)
   FRCNN_REQUIRE(d_out_dev != nullptr, FRCNN_E_INVALID, "null delta_outputs");
   frcnn::do_pnet_backward(c, d_out_dev);
+  API_END(c)
+}
+
+int frcnn_train_image(frcnn_ctx* c, const float* img_dev, int h, int w, const frcnn_example* pos_host, int n_pos,
+                      const frcnn_example* neg_host, int n_neg, const float* const* pnet_masks_dev, const float* const* cnet_masks_dev,
+                      uint64_t seed, float losses_host[4]) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(img_dev && losses_host && n_pos >= 0 && n_neg >= 0 && (n_pos == 0 || pos_host) && (n_neg == 0 || neg_host),
+                FRCNN_E_INVALID, "bad argument");
+  frcnn::do_train_image(c, img_dev, h, w, pos_host, n_pos, neg_host, n_neg, pnet_masks_dev, cnet_masks_dev, seed, losses_host);
+  API_END(c)
+}
+
+// reference order (c*bins + b) fp32 <-> [row][bin][C]
+__global__ void unpack_roi_rows_kernel(const float* __restrict__ x, float* __restrict__ out, long R, int C, int bins) {
+  long total = R * C * bins;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    long r = i / ((long)C * bins);
+    int k = i - r * (long)C * bins;
+    int b = k / C, cc = k - b * C;
+    out[r * (long)C * bins + (long)cc * bins + b] = x[i];
+  }
+}
+
+int frcnn_cnet_train_step(frcnn_ctx* c, const float* x_dev, int R, int n_pos, const float* crtarget_dev, const int32_t* cctarget_dev,
+                          const float* const* masks_dev, uint64_t seed, float* dx_dev, float losses_host[2]) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called first");
+  for (auto g : c->grads) FRCNN_REQUIRE(g != nullptr, FRCNN_E_STATE, "frcnn_bind_grads must be called first");
+  FRCNN_REQUIRE(x_dev && crtarget_dev && cctarget_dev && losses_host && R >= 1 && n_pos >= 0 && n_pos <= R, FRCNN_E_INVALID, "bad argument");
+  frcnn::ensure_objective_workspace(c, R);
+  const int bins = c->roi_kh * c->roi_kw;
+  const long total = (long)R * bins * c->feat_c;
+  const int blocks = (int)std::min<long>((total + 255) / 256, 148 * 16);
+  frcnn::pack_roi_rows_kernel<<<blocks, 256, 0, c->stream>>>(x_dev, c->t_rows, R, c->feat_c, bins);
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->crtarget, crtarget_dev, (size_t)R * 4 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->cctarget, cctarget_dev, (size_t)R * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+  FRCNN_CUDA_TRY(cudaMemsetAsync(c->losses_dev, 0, 8 * sizeof(float), c->stream));
+  frcnn::run_cnet_train(c, R, n_pos, masks_dev, seed);
+  if (dx_dev) unpack_roi_rows_kernel<<<blocks, 256, 0, c->stream>>>(c->t_dx, dx_dev, R, c->feat_c, bins);
+  c->launches += 2;
+  float lh[8];
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(lh, c->losses_dev, 8 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  losses_host[0] = lh[2];
+  losses_host[1] = lh[3];
   API_END(c)
 }
 

@@ -1,0 +1,364 @@
+// Kernels of the training objective (objective.lua:91-186) around the tensor-core GEMMs: RPN criteria on the listed
+// anchors, training ROI pooling with winners and its scatter backward, the cnet training chains (Linear bias +
+// BatchNorm batch statistics + PReLU + Dropout v2) forward / backward and the detection-stage criteria.
+// Un-vendored torch7 `nn` criteria restated from their published definitions (oracle/objective.py header).
+#include "train.h"
+#include "roi_geom.cuh"
+
+namespace frcnn {
+
+static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ float smooth_l1(float d) { float a = fabsf(d); return a < 1.f ? 0.5f * d * d : a - 0.5f; }
+__device__ __forceinline__ float smooth_l1_grad(float d) { return fminf(fmaxf(d, -1.f), 1.f); }
+
+// ------------------------------------------------------------------------------------------ RPN criteria
+// objective.lua:91-140, one thread per listed anchor: CrossEntropy on the (fg, bg) pair (target 1 = positive,
+// 2 = negative), 10 * SmoothL1(sum) on the 4 regression outputs of the positives, deltas ADDED into delta_outputs
+// (an anchor may be listed twice), detection-stage targets: class index / background and
+// Anchors.inputToAnchor(Anchors.anchorToInput(anchor, reg_out), roi.rect) in double (Anchors.lua:237-252).
+__global__ void rpn_loss_kernel(RpnLossParams p) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int R = p.n_pos + p.n_neg;
+  float l_cls = 0.f, l_reg = 0.f;
+  if (e < R) {
+    const ExampleDev& x = p.ex[e];
+    const bool pos = e < p.n_pos;
+    const int l = x.layer - 1, a = x.aspect - 1, yy = x.y - 1, xx = x.x - 1;
+    bool ok = l >= 0 && l < MAX_HEADS && a >= 0 && a < 3;
+    if (ok) ok = yy >= 0 && yy < p.hh[l] && xx >= 0 && xx < p.hw[l];
+    const double* pool_rect = pos ? x.roi : x.anchor;
+    for (int i = 0; i < 4; ++i) p.rects[e * 4 + i] = pool_rect[i];
+    p.cctarget[e] = pos ? x.class_index - 1 : p.bg_class;
+    for (int i = 0; i < 4; ++i) p.crtarget[e * 4 + i] = 0.f;
+    if (!ok) {
+      atomicExch(p.status, 1);
+    } else {
+      const long plane = (long)p.hh[l] * p.hw[l];
+      const long base = (long)(a * 6) * plane + (long)yy * p.hw[l] + xx;
+      const float* v = p.out[l] + base;
+      float* d = p.d_out[l] + base;
+      const float v1 = v[0], v2 = v[plane];
+      const float m = fmaxf(v1, v2);
+      const float lse = m + logf(expf(v1 - m) + expf(v2 - m));
+      const float p1 = expf(v1 - lse), p2 = expf(v2 - lse);
+      l_cls = pos ? lse - v1 : lse - v2;                       // -log softmax[target]
+      atomicAdd(d, p1 - (pos ? 1.f : 0.f));                    // softmax - onehot
+      atomicAdd(d + plane, p2 - (pos ? 0.f : 1.f));
+      if (pos) {
+        float t[4];
+        for (int i = 0; i < 4; ++i) {
+          t[i] = v[(2 + i) * plane];
+          const float df = t[i] - x.reg_target[i];
+          l_reg += 10.f * smooth_l1(df);
+          atomicAdd(d + (2 + i) * plane, 10.f * smooth_l1_grad(df));
+        }
+        // reg_proposal = Anchors.anchorToInput(anchor, reg_out); crtarget = Anchors.inputToAnchor(reg_proposal, roi)
+        const double aw = __dsub_rn(x.anchor[2], x.anchor[0]), ah = __dsub_rn(x.anchor[3], x.anchor[1]);
+        const double px = __dadd_rn(__dmul_rn((double)t[0], aw), x.anchor[0]);
+        const double py = __dadd_rn(__dmul_rn((double)t[1], ah), x.anchor[1]);
+        const double pw = __dmul_rn(exp((double)t[2]), aw), ph = __dmul_rn(exp((double)t[3]), ah);
+        // Rect.fromXYWidthHeight(x, y, w, h) = (x, y, x + w, y + h); width() = maxX - minX
+        const double pmaxx = __dadd_rn(px, pw), pmaxy = __dadd_rn(py, ph);
+        const double w2 = __dsub_rn(pmaxx, px), h2 = __dsub_rn(pmaxy, py);
+        p.crtarget[e * 4 + 0] = (float)((x.roi[0] - px) / w2);
+        p.crtarget[e * 4 + 1] = (float)((x.roi[1] - py) / h2);
+        p.crtarget[e * 4 + 2] = (float)log((x.roi[2] - x.roi[0]) / w2);
+        p.crtarget[e * 4 + 3] = (float)log((x.roi[3] - x.roi[1]) / h2);
+      }
+    }
+  }
+  l_cls = wsum(l_cls);
+  l_reg = wsum(l_reg);
+  if ((threadIdx.x & 31) == 0) {
+    if (l_cls != 0.f) atomicAdd(p.losses + 0, l_cls);
+    if (l_reg != 0.f) atomicAdd(p.losses + 1, l_reg);
+  }
+}
+void launch_rpn_loss(const RpnLossParams& p, cudaStream_t st) {
+  const int R = p.n_pos + p.n_neg;
+  if (R > 0) rpn_loss_kernel<<<cdiv(R, 128), 128, 0, st>>>(p);
+}
+
+// ------------------------------------------------------------------------------------------ training ROI pooling
+__global__ void __launch_bounds__(256) roi_pool_train_kernel(const bf16* __restrict__ fmap, int FH, int FW, int C, int kh, int kw,
+                                                             LocalizerDev loc, const double* __restrict__ rects, bf16* __restrict__ out,
+                                                             int* __restrict__ argmax, int* status) {
+  __shared__ int s_rect[5];
+  const int r = blockIdx.x;
+  if (threadIdx.x == 0) {
+    const double* q = rects + (long)r * 4;
+    int y0, y1, x0, x1;
+    const bool ok = roi_crop(loc, q[0], q[1], q[2], q[3], FH, FW, &y0, &y1, &x0, &x1);
+    s_rect[0] = y0; s_rect[1] = y1; s_rect[2] = x0; s_rect[3] = x1; s_rect[4] = ok;
+    if (!ok) atomicAdd(status, 1);
+  }
+  __syncthreads();
+  const int y0 = s_rect[0], x0 = s_rect[2], ch = s_rect[1] - y0, cw = s_rect[3] - x0;
+  const bool ok = s_rect[4] != 0;
+  const int bins = kh * kw;
+  // output [row][bin][C]; thread <-> (bin, channel), channel fastest (coalesced feature reads)
+  for (int item = threadIdx.x; item < bins * C; item += blockDim.x) {
+    const int c = item % C, bin = item / C;
+    float m = 0.f;
+    int am = 0;
+    if (ok) {
+      const int by = bin / kw, bx = bin - by * kw;
+      const int ys = (by * ch) / kh, ye = ((by + 1) * ch + kh - 1) / kh;
+      const int xs = (bx * cw) / kw, xe = ((bx + 1) * cw + kw - 1) / kw;
+      m = -INFINITY;
+      am = (y0 + ys) * FW + x0 + xs;
+      for (int yy = ys; yy < ye; ++yy)
+        for (int xx = xs; xx < xe; ++xx) {
+          const int pos = (y0 + yy) * FW + x0 + xx;
+          const float v = __bfloat162float(fmap[(long)pos * C + c]);
+          if (v > m) { m = v; am = pos; }   // first maximum in scan order, as nn.SpatialAdaptiveMaxPooling
+        }
+    }
+    out[(long)r * bins * C + item] = __float2bfloat16_rn(m);
+    argmax[(long)r * bins * C + item] = am;
+  }
+}
+void launch_roi_pool_train(const bf16* fmap, int FH, int FW, int C, int kh, int kw, const LocalizerDev& loc, const double* rects_dev,
+                           int R, bf16* out, int* argmax, int* status, cudaStream_t st) {
+  if (R > 0) roi_pool_train_kernel<<<R, 256, 0, st>>>(fmap, FH, FW, C, kh, kw, loc, rects_dev, out, argmax, status);
+}
+
+__global__ void roi_pool_bwd_kernel(const float* __restrict__ d_rows, const int* __restrict__ argmax, long total, int C,
+                                    float* __restrict__ dfeat) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const float d = d_rows[i];
+    if (d != 0.f) atomicAdd(dfeat + (long)argmax[i] * C + (int)(i % C), d);  // ROIs overlap: atomics
+  }
+}
+void launch_roi_pool_bwd(const float* d_rows, const int* argmax, int R, int bins, int C, float* dfeat, cudaStream_t st) {
+  const long total = (long)R * bins * C;
+  if (total > 0) roi_pool_bwd_kernel<<<(int)std::min<long>(cdiv(total, 256), 148 * 16), 256, 0, st>>>(d_rows, argmax, total, C, dfeat);
+}
+
+// ------------------------------------------------------------------------------------------ cnet chains
+// One CTA = 32 feature columns x all R rows (32 x 8 threads: threadIdx.x = column, threadIdx.y strides the rows).
+__global__ void __launch_bounds__(256) fc_train_fwd_kernel(FcTrainFwd p) {
+  __shared__ float s_a[8][33], s_b[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const bool live = col < p.n;
+  const float bias = live ? p.bias[col] : 0.f;
+  float mean = 0.f, rstd = 1.f;
+  if (p.bn_w) {
+    // nn.BatchNormalization in training mode: batch mean, biased variance for the normalisation, running statistics
+    // updated with momentum 0.1 (unbiased variance)
+    float s = 0.f, ss = 0.f;
+    if (live)
+      for (int r = threadIdx.y; r < p.R; r += 8) {
+        const float x = p.acc[(long)r * p.n + col] + bias;
+        s += x;
+        ss += x * x;
+      }
+    s_a[threadIdx.y][threadIdx.x] = s;
+    s_b[threadIdx.y][threadIdx.x] = ss;
+    __syncthreads();
+    s = 0.f; ss = 0.f;
+    for (int k = 0; k < 8; ++k) { s += s_a[k][threadIdx.x]; ss += s_b[k][threadIdx.x]; }
+    mean = s / p.R;
+    float var = ss / p.R - mean * mean;
+    var = fmaxf(var, 0.f);
+    rstd = rsqrtf(var + 1e-5f);
+    if (live && threadIdx.y == 0) {
+      p.rstd[col] = rstd;
+      if (p.bn_mean) {
+        const float unbiased = p.R > 1 ? var * p.R / (p.R - 1) : var;
+        p.bn_mean[col] = 0.9f * p.bn_mean[col] + 0.1f * mean;
+        p.bn_var[col] = 0.9f * p.bn_var[col] + 0.1f * unbiased;
+      }
+    }
+  }
+  if (!live) return;
+  const float slope = p.prelu[0];
+  const float g = p.bn_w ? p.bn_w[col] : 1.f, b = p.bn_w ? p.bn_b[col] : 0.f;
+  for (int r = threadIdx.y; r < p.R; r += 8) {
+    const long i = (long)r * p.n + col;
+    float x = p.acc[i] + bias;
+    if (p.bn_w) {
+      const float xh = (x - mean) * rstd;
+      p.xhat[i] = xh;
+      x = xh * g + b;
+    }
+    p.pre[i] = x;
+    float a = x > 0.f ? x : x * slope;
+    a *= p.mask[i] * p.keep_scale;   // nn.Dropout v2: scale by 1 / (1 - p) at training time
+    if (p.out_bf16) p.out_bf16[i] = __float2bfloat16_rn(a);
+    if (p.out_f32) p.out_f32[i] = a;
+  }
+}
+void launch_fc_train_fwd(const FcTrainFwd& p, cudaStream_t st) {
+  fc_train_fwd_kernel<<<cdiv(p.n, 32), dim3(32, 8), 0, st>>>(p);
+}
+
+__global__ void __launch_bounds__(256) fc_train_bwd_kernel(FcTrainBwd p) {
+  __shared__ float s_a[8][33], s_b[8][33], s_c[8][33];
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  const bool live = col < p.n;
+  const float slope = p.prelu[0];
+  // pass 1: d wrt the PReLU input (= BN output), column sums for bias / BN parameter gradients, slope gradient
+  float sum_d = 0.f, sum_dx = 0.f, ds = 0.f;
+  if (live)
+    for (int r = threadIdx.y; r < p.R; r += 8) {
+      const long i = (long)r * p.n + col;
+      const float x = p.pre[i];
+      const float da = p.d_in[i] * p.mask[i] * p.keep_scale;
+      const float d = x > 0.f ? da : da * slope;
+      if (!(x > 0.f)) ds += da * x;
+      sum_d += d;
+      if (p.xhat) sum_dx += d * p.xhat[i];
+    }
+  s_a[threadIdx.y][threadIdx.x] = sum_d;
+  s_b[threadIdx.y][threadIdx.x] = sum_dx;
+  s_c[threadIdx.y][threadIdx.x] = ds;
+  __syncthreads();
+  sum_d = 0.f; sum_dx = 0.f; ds = 0.f;
+  for (int k = 0; k < 8; ++k) { sum_d += s_a[k][threadIdx.x]; sum_dx += s_b[k][threadIdx.x]; ds += s_c[k][threadIdx.x]; }
+  if (threadIdx.y == 0) {
+    const float t = wsum(live ? ds : 0.f);
+    if (threadIdx.x == 0 && t != 0.f) atomicAdd(p.g_prelu, t);
+  }
+  if (!live) return;
+  const float g = p.xhat ? p.bn_w[col] : 1.f;
+  const float rstd = p.xhat ? p.rstd[col] : 1.f;
+  // Linear bias gradient = column sum of the gradient wrt the Linear output; with BatchNorm that sum is exactly zero
+  // analytically (dx below sums to 0), as in the reference
+  if (threadIdx.y == 0) {
+    if (p.xhat) {
+      atomicAdd(p.g_bn_w + col, sum_dx);
+      atomicAdd(p.g_bn_b + col, sum_d);
+    } else {
+      atomicAdd(p.g_bias + col, sum_d);
+    }
+  }
+  float col_dx = 0.f;
+  for (int r = threadIdx.y; r < p.R; r += 8) {
+    const long i = (long)r * p.n + col;
+    const float x = p.pre[i];
+    const float da = p.d_in[i] * p.mask[i] * p.keep_scale;
+    float d = x > 0.f ? da : da * slope;
+    if (p.xhat) d = g * rstd * (d - sum_d / p.R - p.xhat[i] * sum_dx / p.R);   // BatchNorm backward, batch statistics
+    col_dx += d;
+    p.d_out_bf16[i] = __float2bfloat16_rn(d);
+  }
+  if (p.xhat) {
+    s_a[threadIdx.y][threadIdx.x] = col_dx;
+    // (no barrier needed for correctness of g_bias: tiny residual of the analytic zero, added for completeness)
+    atomicAdd(p.g_bias + col, col_dx);
+  }
+}
+void launch_fc_train_bwd(const FcTrainBwd& p, cudaStream_t st) {
+  fc_train_bwd_kernel<<<cdiv(p.n, 32), dim3(32, 8), 0, st>>>(p);
+}
+
+// objective.lua:166-177 + backward through Linear(nin -> 4) and Linear(nin -> ncls) + LogSoftMax.
+// kernel 1: one CTA per row: outputs, losses, dz, d_hidden.  kernel 2: one CTA per output neuron: weight gradients.
+__global__ void __launch_bounds__(256) cnet_loss_row_kernel(CnetLossParams p) {
+  extern __shared__ float sh[];  // [nin] hidden, [ncls + 4] outputs -> dz
+  const int r = blockIdx.x;
+  float* h = sh;
+  float* z = sh + p.nin;
+  for (int i = threadIdx.x; i < p.nin; i += blockDim.x) h[i] = p.hidden[(long)r * p.nin + i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int no = p.ncls + 4;
+  for (int o = warp; o < no; o += nw) {
+    const float* wr = o < 4 ? p.w_reg + (long)o * p.nin : p.w_cls + (long)(o - 4) * p.nin;
+    float s = 0.f;
+    for (int k = lane; k < p.nin; k += 32) s += h[k] * wr[k];
+    s = wsum(s);
+    if (lane == 0) z[o] = s + (o < 4 ? p.b_reg[o] : p.b_cls[o - 4]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const bool pos = r < p.n_pos;
+    float l_reg = 0.f;
+    for (int i = 0; i < 4; ++i) {
+      const float out = pos ? z[i] : 0.f;                       // crout of the negatives is zeroed (objective.lua:170)
+      const float d = out - p.crtarget[r * 4 + i];
+      l_reg += 10.f * smooth_l1(d);
+      z[i] = pos ? 10.f * smooth_l1_grad(d) : 0.f;
+    }
+    float m = -INFINITY;
+    for (int c = 0; c < p.ncls; ++c) m = fmaxf(m, z[4 + c]);
+    float s = 0.f;
+    for (int c = 0; c < p.ncls; ++c) s += expf(z[4 + c] - m);
+    const float lse = m + logf(s);
+    const int t = p.cctarget[r];
+    const float l_cls = (lse - z[4 + t]) / p.R;                  // ClassNLLCriterion, sizeAverage
+    for (int c = 0; c < p.ncls; ++c) z[4 + c] = (expf(z[4 + c] - lse) - (c == t ? 1.f : 0.f)) / p.R;
+    if (l_reg != 0.f) atomicAdd(p.losses + 2, l_reg);
+    atomicAdd(p.losses + 3, l_cls);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < no; o += blockDim.x) p.dz[(long)r * no + o] = z[o];
+  for (int k = threadIdx.x; k < p.nin; k += blockDim.x) {
+    float d = 0.f;
+    for (int o = 0; o < 4; ++o) d += z[o] * p.w_reg[(long)o * p.nin + k];
+    for (int c = 0; c < p.ncls; ++c) d += z[4 + c] * p.w_cls[(long)c * p.nin + k];
+    p.d_hidden[(long)r * p.nin + k] = d;
+  }
+}
+__global__ void __launch_bounds__(256) cnet_loss_wgrad_kernel(CnetLossParams p) {
+  const int o = blockIdx.x, no = p.ncls + 4;
+  float* gw = o < 4 ? p.g_w_reg + (long)o * p.nin : p.g_w_cls + (long)(o - 4) * p.nin;
+  float bsum = 0.f;
+  for (int k = threadIdx.x; k < p.nin; k += blockDim.x) {
+    float s = 0.f;
+    for (int r = 0; r < p.R; ++r) s += p.dz[(long)r * no + o] * p.hidden[(long)r * p.nin + k];
+    gw[k] += s;
+  }
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < p.R; ++r) bsum += p.dz[(long)r * no + o];
+    if (o < 4) p.g_b_reg[o] += bsum; else p.g_b_cls[o - 4] += bsum;
+  }
+}
+void launch_cnet_loss_bwd(const CnetLossParams& p, cudaStream_t st) {
+  if (p.R <= 0) return;
+  cnet_loss_row_kernel<<<p.R, 256, (p.nin + p.ncls + 4) * sizeof(float), st>>>(p);
+  cnet_loss_wgrad_kernel<<<p.ncls + 4, 256, 0, st>>>(p);
+}
+
+// ------------------------------------------------------------------------------------------ fc weight layouts
+__global__ void pack_fc_weight_dgrad_kernel(const float* __restrict__ w, bf16* __restrict__ out, int nout, int C, int bins, int permute) {
+  const long K = (long)C * bins, total = K * nout;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int o = (int)(i % nout);
+    const long k = i / nout;
+    long src = k;
+    if (permute) {
+      const int b = (int)(k / C), c = (int)(k - (long)b * C);
+      src = (long)c * bins + b;
+    }
+    out[i] = __float2bfloat16_rn(w[(long)o * K + src]);
+  }
+}
+void launch_pack_fc_weight_dgrad(const float* w, bf16* out, int nout, int C, int bins, int permute, cudaStream_t st) {
+  const long total = (long)nout * C * bins;
+  pack_fc_weight_dgrad_kernel<<<(int)std::min<long>(cdiv(total, 256), 148 * 8), 256, 0, st>>>(w, out, nout, C, bins, permute);
+}
+__global__ void wgrad_finish_fc_kernel(const float* __restrict__ dw, float* __restrict__ grad, int nout, int C, int bins, int permute) {
+  const long K = (long)C * bins, total = K * nout;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long o = i / K, k = i - o * K;
+    long dst = k;
+    if (permute) {
+      const int b = (int)(k / C), c = (int)(k - (long)b * C);
+      dst = (long)c * bins + b;
+    }
+    grad[o * K + dst] += dw[i];
+  }
+}
+void launch_wgrad_finish_fc(const float* dw, float* grad, int nout, int C, int bins, int permute, cudaStream_t st) {
+  const long total = (long)nout * C * bins;
+  wgrad_finish_fc_kernel<<<(int)std::min<long>(cdiv(total, 256), 148 * 8), 256, 0, st>>>(dw, grad, nout, C, bins, permute);
+}
+
+}  // namespace frcnn

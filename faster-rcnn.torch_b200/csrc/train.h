@@ -28,3 +28,79 @@ void launch_add_chw_to_nhwc(const float* src, float* dst, int N, int H, int W, i
 void launch_check_slopes(const float* const* slopes_dev, int n, int* flag, cudaStream_t st);
 
 }  // namespace frcnn
+
+// ---- objective.lua:91-186: RPN losses, training ROI pooling, cnet training forward / backward ------------------
+#include "detect.h"
+namespace frcnn {
+
+struct ExampleDev {          // device copy of frcnn_example
+  double anchor[4], roi[4];
+  float reg_target[4];
+  int layer, aspect, y, x, class_index, pad_;
+};
+
+struct RpnLossParams {
+  const ExampleDev* ex;      // positives first, then negatives
+  int n_pos, n_neg;
+  const float* out[MAX_HEADS];   // [18][hh][hw] fp32 of the image
+  float* d_out[MAX_HEADS];       // zeroed delta_outputs, same shape
+  int hh[MAX_HEADS], hw[MAX_HEADS];
+  float* crtarget;           // [R][4] regression targets of the detection stage (zeros for negatives)
+  int* cctarget;             // [R] 0-based class targets (background = class_count)
+  int bg_class;              // 0-based background index
+  double* rects;             // [R][4] rect that is ROI-pooled: ground truth (positives) / anchor (negatives)
+  float* losses;             // [0] += sum CE, [1] += 10 * sum SmoothL1
+  int* status;               // set when an example indexes outside its map (cleanAnchors was not applied)
+};
+void launch_rpn_loss(const RpnLossParams& p, cudaStream_t st);
+
+// ROI pooling of explicit rects with winners (flat feature-plane positions) for the backward scatter
+void launch_roi_pool_train(const bf16* fmap, int FH, int FW, int C, int kh, int kw, const LocalizerDev& loc, const double* rects_dev,
+                           int R, bf16* out, int* argmax, int* status, cudaStream_t st);
+// dfeat (fp32 NHWC [FH][FW][C]) += scatter of d_rows ([R][bins][C] fp32) to the winners
+void launch_roi_pool_bwd(const float* d_rows, const int* argmax, int R, int bins, int C, float* dfeat, cudaStream_t st);
+
+struct FcTrainFwd {          // Linear bias (+ BatchNorm, training statistics) + PReLU + Dropout v2 on the GEMM output
+  const float* acc;          // [R][n] fp32 GEMM result
+  const float *bias, *bn_w, *bn_b, *prelu;
+  float *bn_mean, *bn_var;   // running statistics, updated with momentum 0.1 (null: no BatchNorm)
+  const float* mask;         // [R][n] 0/1 dropout mask
+  float keep_scale;          // 1 / (1 - p)
+  float* pre;                // [R][n] value entering the PReLU (after BN)
+  float* xhat;               // [R][n] normalised BN input (BatchNorm only)
+  float* rstd;               // [n]
+  bf16* out_bf16;            // [R][n] next GEMM operand (after dropout), or null
+  float* out_f32;            // [R][n] same in fp32, or null
+  int R, n;
+};
+void launch_fc_train_fwd(const FcTrainFwd& p, cudaStream_t st);
+
+struct FcTrainBwd {          // backward of the same chain: d (wrt the dropout output) -> d wrt the Linear output
+  const float* d_in;         // [R][n]
+  const float *pre, *xhat, *rstd, *bn_w, *prelu, *mask;
+  float keep_scale;
+  bf16* d_out_bf16;          // [R][n] gradient wrt the Linear output (GEMM operand)
+  float *g_bias, *g_bn_w, *g_bn_b, *g_prelu;
+  int R, n;
+};
+void launch_fc_train_bwd(const FcTrainBwd& p, cudaStream_t st);
+
+struct CnetLossParams {      // objective.lua:166-177 on the two cnet outputs + backward through the output Linear layers
+  const float* hidden;       // [R][nin] fp32 input of both branches
+  const float *w_reg, *b_reg, *w_cls, *b_cls;
+  const float* crtarget;     // [R][4]
+  const int* cctarget;       // [R]
+  int R, n_pos, nin, ncls;
+  float* d_hidden;           // [R][nin]
+  float* dz;                 // [R][ncls + 4] scratch: gradient wrt the branch outputs (4 reg, then ncls logits)
+  float *g_w_reg, *g_b_reg, *g_w_cls, *g_b_cls;
+  float* losses;             // [2] += 10 * SmoothL1 sum, [3] += mean NLL
+};
+void launch_cnet_loss_bwd(const CnetLossParams& p, cudaStream_t st);
+
+// fc weight for the dgrad GEMM: out[k'][o] = w[o][src(k')] bf16, k' = b*C + c <- c*bins + b when permute
+void launch_pack_fc_weight_dgrad(const float* w, bf16* out, int nout, int C, int bins, int permute, cudaStream_t st);
+// grad[o][src(k')] += dw[o][k'] (inverse of the ROI column permutation)
+void launch_wgrad_finish_fc(const float* dw, float* grad, int nout, int C, int bins, int permute, cudaStream_t st);
+
+}  // namespace frcnn

@@ -171,6 +171,50 @@ class Model:
     def zero_grad(self):
         self.gradient.zero_()
 
+    def train_image(self, img, positives, negatives, pnet_masks=None, cnet_masks=None, seed=0):
+        """The body of the per-image loop of lossAndGradient (objective.lua:65-198) for one frame: forward, criteria,
+        backward; gradients accumulate into `self.gradient`.  positives: [(anchor, roi)], negatives: [(anchor,)] as
+        BatchIterator:nextTraining yields them (anchor = Anchors:get result, roi = {rect, class_index}); the lists
+        must be cleaned with cleanAnchors first.  Returns {cls, reg, creg, ccls} loss sums of the frame."""
+        from .geometry import Anchors
+        x = img.to(self.device, torch.float32).contiguous()
+        _, h, w = x.shape
+
+        def fill(arr, i, anchor, roi):
+            e = arr[i]
+            for k, v in enumerate(anchor.unpack()):
+                e.anchor[k] = v
+            e.layer, e.aspect, e.y, e.x = anchor.layer, anchor.aspect, anchor.index[1], anchor.index[2]
+            if roi is not None:
+                for k, v in enumerate(roi["rect"].unpack()):
+                    e.roi[k] = v
+                t = Anchors.inputToAnchor(anchor, roi["rect"])
+                for k in range(4):
+                    e.reg_target[k] = float(t[k])
+                e.class_index = int(roi["class_index"])
+
+        pos = ffi.new("frcnn_example[]", max(len(positives), 1))
+        neg = ffi.new("frcnn_example[]", max(len(negatives), 1))
+        for i, (a, roi) in enumerate(positives):
+            fill(pos, i, a, roi)
+        for i, ex in enumerate(negatives):
+            fill(neg, i, ex[0], None)
+        keep = []
+
+        def ptrs(masks):
+            if masks is None:
+                return ffi.NULL
+            ts = [m.to(self.device, torch.float32).contiguous() for m in masks]
+            keep.extend(ts)
+            return ffi.new("const float*[]", [ffi.cast("const float*", t.data_ptr()) for t in ts])
+
+        pm, cm = ptrs(pnet_masks), ptrs(cnet_masks)
+        losses = ffi.new("float[4]")
+        torch.cuda.synchronize(self.device)
+        check(self.ctx, lib().frcnn_train_image(self.ctx, ffi.cast("const float*", x.data_ptr()), h, w, pos, len(positives), neg,
+                                                len(negatives), pm, cm, seed, losses))
+        return dict(cls=losses[0], reg=losses[1], creg=losses[2], ccls=losses[3])
+
     def _cnet_forward(self, x):
         """cnet:forward(cinput) (Detector.lua:101): x [R][kh*kw*C] fp32 -> (bbox [R][4], log-softmax [R][classes+1])."""
         x = x.to(self.device, torch.float32).contiguous()
@@ -180,6 +224,23 @@ class Model:
         check(self.ctx, lib().frcnn_cnet_forward(self.ctx, ffi.cast("const float*", x.data_ptr()), R,
                                                  ffi.cast("float*", reg.data_ptr()), ffi.cast("float*", cls.data_ptr())))
         return reg, cls
+
+    def cnet_train_step(self, x, n_pos, crtarget, cctarget, masks=None, seed=0):
+        """cnet:forward (training) + detection-stage criteria + cnet:backward (objective.lua:164-179) on example rows
+        x [R][kh*kw*C]; returns (post_roi_delta [R][kh*kw*C], {creg, ccls}); gradients accumulate in self.gradient."""
+        x = x.to(self.device, torch.float32).contiguous()
+        R = x.shape[0]
+        crt = crtarget.to(self.device, torch.float32).contiguous()
+        cct = cctarget.to(self.device, torch.int32).contiguous()
+        dx = torch.empty_like(x)
+        keep = [m.to(self.device, torch.float32).contiguous() for m in masks] if masks is not None else []
+        mp = ffi.new("const float*[]", [ffi.cast("const float*", m.data_ptr()) for m in keep]) if keep else ffi.NULL
+        losses = ffi.new("float[2]")
+        torch.cuda.synchronize(self.device)
+        check(self.ctx, lib().frcnn_cnet_train_step(self.ctx, ffi.cast("const float*", x.data_ptr()), R, n_pos,
+                                                    ffi.cast("const float*", crt.data_ptr()), ffi.cast("const int32_t*", cct.data_ptr()),
+                                                    mp, seed, ffi.cast("float*", dx.data_ptr()), losses))
+        return dx, dict(creg=losses[0], ccls=losses[1])
 
     def launch_count(self):
         return int(lib().frcnn_launch_count(self.ctx))

@@ -78,6 +78,17 @@ typedef struct frcnn_detection {
   int image;      /* 0-based index of the frame inside the batch */
 } frcnn_detection;
 
+/* One training example of objective.lua:91-140: a positive {anchor, roi} or a negative {anchor} as produced by
+ * BatchIterator:nextTraining (Anchors:findPositive / sampleNegative stay host-side Lua). */
+typedef struct frcnn_example {
+  double anchor[4];     /* anchor rect {minX, minY, maxX, maxY} (Anchors:get) */
+  double roi[4];        /* ground-truth rect roi.rect (positives only) */
+  float reg_target[4];  /* Anchors.inputToAnchor(anchor, roi.rect), the fp32 FloatTensor of objective.lua:110 */
+  int layer, aspect, y, x; /* 1-based anchor index {layer, aspect, index[2], index[3]} */
+  int class_index;      /* roi.class_index, 1-based (positives only) */
+  int pad_;
+} frcnn_example;
+
 /* ---- lifetime -------------------------------------------------------------------------------------------- */
 int frcnn_version(void);
 /* replaces cutorch.setDevice + :cuda() setup (main.lua:52, Detector.lua:13-14).  stream: cudaStream_t or NULL. */
@@ -136,6 +147,29 @@ int frcnn_pnet_forward_train(frcnn_ctx* ctx, const float* img_dev, int n, int h,
  * fp32 (ROI-pool gradients, objective.lua:184); NULL entries are treated as zero.  dgrad / wgrad run on the
  * tcgen05 conv kernel with bf16 gradient maps and fp32 accumulation.  PReLU slopes must be > 0. */
 int frcnn_pnet_backward(frcnn_ctx* ctx, const float* const* d_out_dev);
+
+/* One iteration of the per-image loop of lossAndGradient (objective.lua:65-198) for ONE frame img_dev [3][h][w]:
+ * pnet forward (training) -> RPN criteria on the listed anchors (CrossEntropy on the fg/bg pair, 10 * SmoothL1) ->
+ * ROI pooling of the ground-truth rects (positives) / anchor rects (negatives) -> cnet forward (training: BatchNorm
+ * batch statistics, Dropout v2) -> 10 * SmoothL1 on the positives' bbox outputs + mean ClassNLL -> cnet backward ->
+ * ROI-pool backward -> pnet backward.  Parameter gradients are ACCUMULATED into the views given to
+ * frcnn_bind_grads; the caller zeroes them per batch and divides by cls_count (objective.lua:49,200).
+ * Examples must already be cleaned (cleanAnchors, objective.lua:32-43).  losses_host: {sum CE, 10 * sum SmoothL1,
+ * 10 * SmoothL1 sum of the detection stage, mean NLL} of this frame.
+ * pnet_masks_dev: per SpatialDropout layer [1][C] or NULL; cnet_masks_dev: per class layer [n_pos + n_neg][n] of
+ * 0 / 1 or NULL (= drawn from seed). */
+int frcnn_train_image(frcnn_ctx* ctx, const float* img_dev, int h, int w, const frcnn_example* pos_host, int n_pos,
+                      const frcnn_example* neg_host, int n_neg, const float* const* pnet_masks_dev,
+                      const float* const* cnet_masks_dev, uint64_t seed, float losses_host[4]);
+
+/* cnet:forward(cinput) in training mode + the detection-stage criteria + cnet:backward (objective.lua:164-179).
+ * x_dev: [R][kh*kw*C] fp32 (reference ordering), the first n_pos rows are positives; crtarget_dev [R][4];
+ * cctarget_dev [R] 0-based class targets (background = class_count).  dx_dev (optional) receives post_roi_delta
+ * [R][kh*kw*C] fp32; parameter gradients are accumulated; the BatchNorm running statistics are updated (momentum
+ * 0.1).  losses_host: {10 * SmoothL1 sum over the positives' bbox outputs, mean ClassNLL}. */
+int frcnn_cnet_train_step(frcnn_ctx* ctx, const float* x_dev, int R, int n_pos, const float* crtarget_dev,
+                          const int32_t* cctarget_dev, const float* const* masks_dev, uint64_t seed, float* dx_dev,
+                          float losses_host[2]);
 
 /* ---- RPN decode: replaces the per-anchor Lua loop Detector.lua:36-66 ------------------------------------- */
 /* heads_dev[i]: [18][hi][wi] fp32 of ONE image.  Writes the ordered match list (layer, y, x, aspect order) to
