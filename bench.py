@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="detect", choices=["detect", "nms"])
+    ap.add_argument("--workload", default="detect", choices=["detect", "nms", "train"])
     ap.add_argument("--batch", type=int, default=1, help="frames per step per GPU (configs[1]: batch=1)")
     ap.add_argument("--model", default="vgg_small", choices=["vgg_small", "vgg_large"])
     ap.add_argument("--height", type=int, default=0)
@@ -300,6 +300,56 @@ def run_b200(args):
         if rank == 0:
             if not args.no_cpu_baseline:
                 line["cpu_baseline"] = cpu_baseline_nms(n)
+            print(json.dumps(line), flush=True)
+        m.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    if args.workload == "train":
+        # BASELINE configs[2]: vgg_small training fwd/bwd (objective.lua) 800x450, batch frames per GPU, 128 positive +
+        # 128 negative anchors and 8 ground-truth boxes per frame; frames sharded over the ranks,
+        # ONE all-reduce of the flat gradient (+ counters) per step
+        from oracle import anchors as OA, objective as OO
+        desc, cfg, params, h, w = model_setup(args)
+        m = (F.vgg_small if args.model == "vgg_small" else F.vgg_large)(F.duplo_cfg if args.model == "vgg_small" else F.imgnet_cfg, device=local)
+        m.load_params(params)
+        oa = OA.Anchors(desc["layers"], desc["anchor_nets"], cfg["scales"])
+        dims = m.output_dims(h, w)
+        B = max(args.batch, 1)
+        batch = []
+        for s in range(B):
+            pos, neg, _ = OO.synthetic_examples(oa, dims, w, h, 128, 128, 8, cfg["class_count"], seed=1000 * rank + s)
+            batch.append(dict(img=OM.synthetic_frame(h, w, seed=100 * rank + s).cuda(), positive=pos, negative=neg))
+        objective = F.create_objective(m, dist if world > 1 else None)
+        l0 = m.launch_count()
+        state = dict(step=0)
+
+        def step():
+            state["step"] += 1
+            objective(batch, seed=state["step"])
+
+        sampler.start()
+        ms = max_over_ranks(timed(step, args.steps, args.warmup))
+        clocks = sampler.stop()
+        launches = (m.launch_count() - l0) // (args.steps + args.warmup)
+        total = sum_over_ranks(float(B)) * args.steps
+        fwd = conv_flops_per_image(desc, h, w)
+        line = dict(metric="train_images_per_sec", value=total / (ms * 1e-3), unit="images/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="bf16", data="synthetic",
+                    config=dict(workload="%s lossAndGradient (objective.lua) %dx%d, %d frames per GPU, 128+128 anchors, 8 boxes per frame "
+                                         "(BASELINE configs[2])" % (args.model, w, h, B), l2="flushed between steps",
+                                sharding="frames over ranks; one all-reduce of the flat gradient per step", launches_per_step=int(launches)),
+                    clocks=clocks, gpu_launches=int(launches * args.steps),
+                    e2e=dict(value=total / (ms * 1e-3), unit="images/s", h2d_bytes_per_step=int(B * 256 * 96), d2h_bytes_per_step=int(B * 48),
+                             note="frames resident; per frame the example lists go up and the four loss sums come back"),
+                    roofline=dict(bound="tensor", kernel="conv_igemm_kernel (fwd + dgrad + wgrad launches of a step)",
+                                  achieved=3 * fwd * B / (ms / args.steps * 1e-3) / 1e12, peak=pk["bf16_sustained"], unit="TFLOP/s",
+                                  frac=3 * fwd * B / (ms / args.steps * 1e-3) / 1e12 / pk["bf16_sustained"], traffic=None,
+                                  note="whole-step time as denominator (not the conv launches alone): lower bound of the kernel fraction"))
+        if rank == 0:
             print(json.dumps(line), flush=True)
         m.close()
         if world > 1:

@@ -41,6 +41,7 @@ struct ConvLayer {
   float* mask = nullptr;        // [N][cout] Bernoulli(1 - p) mask of the last training forward
   bf16* w_dgrad = nullptr;      // [cin][k][k][cout] flipped filters (transposed convolution)
   float* dw_taps = nullptr;     // [cout][k*k][cin] fp32 wgrad accumulator
+  long dgrad_gen = -1;          // weights generation w_dgrad was packed from
   ConvLaunch dgrad, wgrad;
 };
 
@@ -68,6 +69,7 @@ struct FcLayer {
   float *t_acc = nullptr, *t_pre = nullptr, *t_xhat = nullptr, *t_rstd = nullptr, *t_mask = nullptr, *t_din = nullptr, *t_out32 = nullptr;
   bf16 *t_out = nullptr, *t_dy = nullptr, *w_dgrad = nullptr;
   float* dw_taps = nullptr;
+  long dgrad_gen = -1;
 };
 
 }  // namespace frcnn
@@ -153,6 +155,7 @@ struct frcnn_ctx {
   cudaGraphExec_t graph_exec = nullptr;
   struct GraphKey { const float* img; int N, H, W; double thr_fg, thr_class; float thr_nms1, thr_nms2; long gen; } graph_key = {};
   GraphKey eager_key = {};     // key of the last eager run (a config is captured on its second use)
+  long weights_gen = 0;        // bumped by frcnn_pack_weights: invalidates the cached dgrad weight layouts
   long ws_gen = 0;             // bumped whenever a workspace pointer baked into the graph may have changed
   int64_t launches_per_detect = 0;
   int spec_det = 256;          // winners copied to the host speculatively together with the counters
@@ -477,6 +480,7 @@ static void do_pack(frcnn_ctx* c) {
   }
   FRCNN_CUDA_TRY(cudaGetLastError());
   FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));  // the LUT host vectors / caller buffers may change afterwards
+  ++c->weights_gen;
   c->packed = true;
 }
 
@@ -706,6 +710,8 @@ static void ensure_train_workspace(frcnn_ctx* c, int N, int H, int W) {
       }
     }
   }
+  for (auto& cv : c->trunk) cv.dgrad_gen = -1;
+  for (auto& hd : c->heads) hd.conv.dgrad_gen = -1;
   c->gscratch[0] = (bf16*)dev_alloc(A, max_map * sizeof(bf16));
   c->gscratch[1] = (bf16*)dev_alloc(A, max_map * sizeof(bf16));
   // trunk launches: dy always lives in gscratch[0] ("cur"), the bf16 dgrad output in gscratch[1]
@@ -749,12 +755,17 @@ static void run_wgrad(frcnn_ctx* c, ConvLayer& cv) {
   c->launches += 2;
 }
 static void run_dgrad(frcnn_ctx* c, ConvLayer& cv) {
-  launch_pack_conv_weight_dgrad(P(c, cv.p_w), cv.w_dgrad, cv.cout, cv.cin, cv.k, cv.k, c->stream);
+  // the flipped filters are re-packed once per frcnn_pack_weights (= once per optimiser step), not per frame
+  if (cv.dgrad_gen != c->weights_gen) {
+    launch_pack_conv_weight_dgrad(P(c, cv.p_w), cv.w_dgrad, cv.cout, cv.cin, cv.k, cv.k, c->stream);
+    cv.dgrad_gen = c->weights_gen;
+    ++c->launches;
+  }
   cv.dgrad.p.bias = nullptr;
   cv.dgrad.p.prelu = nullptr;
   cv.dgrad.p.scale = 1.f;
   conv_launch(cv.dgrad, c->stream);
-  c->launches += 2;
+  ++c->launches;
 }
 
 // pnet:backward(img, delta_outputs) (objective.lua:189): parameter gradients are ACCUMULATED into the bound gradient
@@ -864,6 +875,7 @@ static void ensure_objective_workspace(frcnn_ctx* c, int rows) {
     f.t_out = (bf16*)dev_alloc(A, rn * sizeof(bf16));
     f.t_dy = (bf16*)dev_alloc(A, rn * sizeof(bf16));
     f.w_dgrad = (bf16*)dev_alloc(A, (size_t)f.nin * f.nout * sizeof(bf16));
+    f.dgrad_gen = -1;
     f.dw_taps = (float*)dev_alloc(A, (size_t)f.nin * f.nout * sizeof(float));
   }
   c->head_dout.clear();
@@ -871,10 +883,19 @@ static void ensure_objective_workspace(frcnn_ctx* c, int rows) {
   c->cw_rows = R;
 }
 
-// [R][nin] bf16 rows x [nout][nin] bf16 weights -> fp32 [R][nout] (plain stores, deterministic)
+// [R][nin] bf16 rows x [nout][nin] bf16 weights -> fp32 [R][nout].  Few output tiles with a long K (fc1: 8 tiles,
+// K = 13824) are split along K and summed by TMA reduce-add into the zeroed output; otherwise plain stores.
 static void gemm_rows(frcnn_ctx* c, const bf16* a, const bf16* w, int R, int nin, int nout, float* out) {
   ConvLaunch L;
-  conv_prepare(&L, a, w, 1, 1, R, nin, nout, 1, 1, 0, 0, EPI_F32_SLICES, nullptr, c->sm_count, 1, 0, 1);
+  const int tiles = ((R + 127) / 128) * ((nout + 255) / 256);
+  const int k_iters = nin / 64;
+  int splits = std::min(std::max(1, c->sm_count / std::max(tiles, 1)), std::max(1, k_iters / 8));
+  if (splits > 1) {
+    FRCNN_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)R * nout * sizeof(float), c->stream));
+    conv_prepare(&L, a, w, 1, 1, R, nin, nout, 1, 1, 0, 0, EPI_F32_REDUCE, nullptr, c->sm_count, splits, 0, 1);
+  } else {
+    conv_prepare(&L, a, w, 1, 1, R, nin, nout, 1, 1, 0, 0, EPI_F32_SLICES, nullptr, c->sm_count, 1, 0, 1);
+  }
   conv_set_f32_output(&L, out);
   conv_launch(L, c->stream);
   ++c->launches;

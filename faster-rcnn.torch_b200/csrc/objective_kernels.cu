@@ -85,7 +85,7 @@ void launch_rpn_loss(const RpnLossParams& p, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------ training ROI pooling
-__global__ void __launch_bounds__(256) roi_pool_train_kernel(const bf16* __restrict__ fmap, int FH, int FW, int C, int kh, int kw,
+__global__ void __launch_bounds__(128) roi_pool_train_kernel(const bf16* __restrict__ fmap, int FH, int FW, int C, int kh, int kw,
                                                              LocalizerDev loc, const double* __restrict__ rects, bf16* __restrict__ out,
                                                              int* __restrict__ argmax, int* status) {
   __shared__ int s_rect[5];
@@ -95,15 +95,15 @@ __global__ void __launch_bounds__(256) roi_pool_train_kernel(const bf16* __restr
     int y0, y1, x0, x1;
     const bool ok = roi_crop(loc, q[0], q[1], q[2], q[3], FH, FW, &y0, &y1, &x0, &x1);
     s_rect[0] = y0; s_rect[1] = y1; s_rect[2] = x0; s_rect[3] = x1; s_rect[4] = ok;
-    if (!ok) atomicAdd(status, 1);
+    if (!ok && blockIdx.y == 0) atomicAdd(status, 1);
   }
   __syncthreads();
   const int y0 = s_rect[0], x0 = s_rect[2], ch = s_rect[1] - y0, cw = s_rect[3] - x0;
   const bool ok = s_rect[4] != 0;
   const int bins = kh * kw;
-  // output [row][bin][C]; thread <-> (bin, channel), channel fastest (coalesced feature reads)
-  for (int item = threadIdx.x; item < bins * C; item += blockDim.x) {
-    const int c = item % C, bin = item / C;
+  // output [row][bin][C]; CTA <-> (row, bin), thread <-> channel (coalesced feature reads)
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int bin = blockIdx.y, item = bin * C + c;
     float m = 0.f;
     int am = 0;
     if (ok) {
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) roi_pool_train_kernel(const bf16* __restr
 }
 void launch_roi_pool_train(const bf16* fmap, int FH, int FW, int C, int kh, int kw, const LocalizerDev& loc, const double* rects_dev,
                            int R, bf16* out, int* argmax, int* status, cudaStream_t st) {
-  if (R > 0) roi_pool_train_kernel<<<R, 256, 0, st>>>(fmap, FH, FW, C, kh, kw, loc, rects_dev, out, argmax, status);
+  if (R > 0) roi_pool_train_kernel<<<dim3(R, kh * kw), 128, 0, st>>>(fmap, FH, FW, C, kh, kw, loc, rects_dev, out, argmax, status);
 }
 
 __global__ void roi_pool_bwd_kernel(const float* __restrict__ d_rows, const int* __restrict__ argmax, long total, int C,
@@ -344,21 +344,35 @@ void launch_pack_fc_weight_dgrad(const float* w, bf16* out, int nout, int C, int
   const long total = (long)nout * C * bins;
   pack_fc_weight_dgrad_kernel<<<(int)std::min<long>(cdiv(total, 256), 148 * 8), 256, 0, st>>>(w, out, nout, C, bins, permute);
 }
-__global__ void wgrad_finish_fc_kernel(const float* __restrict__ dw, float* __restrict__ grad, int nout, int C, int bins, int permute) {
-  const long K = (long)C * bins, total = K * nout;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long o = i / K, k = i - o * K;
-    long dst = k;
-    if (permute) {
-      const int b = (int)(k / C), c = (int)(k - (long)b * C);
-      dst = (long)c * bins + b;
+// One CTA per output neuron: the row [bins][C] (ROI order) is staged in shared memory and added to the Torch-order
+// row [C][bins] with coalesced accesses on both sides.
+__global__ void __launch_bounds__(256) wgrad_finish_fc_kernel(const float* __restrict__ dw, float* __restrict__ grad, int nout, int C,
+                                                              int bins, int permute) {
+  extern __shared__ float srow[];
+  const long K = (long)C * bins;
+  for (int o = blockIdx.x; o < nout; o += gridDim.x) {
+    if (!permute) {
+      for (long k = threadIdx.x; k < K; k += blockDim.x) grad[o * K + k] += dw[o * K + k];
+      continue;
     }
-    grad[o * K + dst] += dw[i];
+    __syncthreads();
+    for (long k = threadIdx.x; k < K; k += blockDim.x) srow[k] = dw[o * K + k];
+    __syncthreads();
+    for (long d = threadIdx.x; d < K; d += blockDim.x) {
+      const int c = (int)(d / bins), b = (int)(d - (long)c * bins);
+      grad[o * K + d] += srow[(long)b * C + c];
+    }
   }
 }
 void launch_wgrad_finish_fc(const float* dw, float* grad, int nout, int C, int bins, int permute, cudaStream_t st) {
-  const long total = (long)nout * C * bins;
-  wgrad_finish_fc_kernel<<<(int)std::min<long>(cdiv(total, 256), 148 * 8), 256, 0, st>>>(dw, grad, nout, C, bins, permute);
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(wgrad_finish_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    configured = true;
+  }
+  const size_t smem = permute ? (size_t)C * bins * sizeof(float) : 0;
+  FRCNN_REQUIRE(smem <= 96 * 1024, FRCNN_E_INVALID, "fc row too long for the transposing gradient accumulation");
+  wgrad_finish_fc_kernel<<<std::min(nout, 148 * 4), 256, smem, st>>>(dw, grad, nout, C, bins, permute);
 }
 
 }  // namespace frcnn

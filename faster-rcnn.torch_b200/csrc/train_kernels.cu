@@ -232,32 +232,55 @@ void launch_head_tail_bwd(const HeadTailBwd& H, int num_sms, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------ first-layer wgrad
 // dW[co][c][kh][kw] += sum over pixels of dpre[n][h][w][co] * img[n][c][h + kh - pad][w + kw - pad] for the 3-channel
-// first convolution (K = 27 is too narrow for the tensor-core wgrad).  CTA = strip of pixels; thread <-> (co, tap group).
+// first convolution (K = 27 is too narrow for the tensor-core wgrad).  Persistent CTAs over 8 x 32 pixel tiles: the
+// gradient tile [256 px][64 co] and the (8+2) x (32+2) x 3 image patch are staged in shared memory, thread <-> (co,
+// tap group) accumulates its 7 taps in registers across all its tiles, one atomic per accumulator at the end.
 __global__ void __launch_bounds__(256) first_wgrad_kernel(const bf16* __restrict__ dpre, const float* __restrict__ img,
-                                                          float* __restrict__ dw, int N, int H, int W, int pad, long strip) {
-  constexpr int CO = 64, TAPS = 27, TG = 4, PER = 7;  // 4 tap groups x 7 taps >= 27
+                                                          float* __restrict__ dw, int N, int H, int W, int pad) {
+  constexpr int CO = 64, TAPS = 27, TG = 4, PER = 7, TH = 8, TW = 32;
+  __shared__ __align__(16) bf16 s_d[TH * TW][CO];        // 32 KB
+  __shared__ float s_img[3][TH + 2][TW + 2];
   const int co = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  int t_c[PER], t_kh[PER], t_kw[PER];
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int tap = min(tg + j * TG, TAPS - 1);
+    t_c[j] = tap / 9;
+    t_kh[j] = (tap % 9) / 3;
+    t_kw[j] = tap % 3;
+  }
   float acc[PER];
 #pragma unroll
   for (int j = 0; j < PER; ++j) acc[j] = 0.f;
-  const long total = (long)N * H * W;
-  const long p0 = blockIdx.x * strip, p1 = min(total, p0 + strip);
+  const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
+  const long total_tiles = (long)N * tiles_h * tiles_w;
   const long plane = (long)H * W;
-  for (long pix = p0; pix < p1; ++pix) {
-    const float d = __bfloat162float(dpre[pix * CO + co]);
-    if (__ballot_sync(0xffffffffu, d != 0.f) == 0) continue;  // three quarters of the gradient are zeros (pool backward)
-    const int n = (int)(pix / plane);
-    const long r = pix - (long)n * plane;
-    const int h = (int)(r / W), w = (int)(r - (long)h * W);
+  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tw = (int)(tile % tiles_w);
+    const long r = tile / tiles_w;
+    const int th = (int)(r % tiles_h), n = (int)(r / tiles_h);
+    const int h0 = th * TH, w0 = tw * TW;
+    __syncthreads();
+    // gradient tile: 256 px x 128 B, 16-byte vectors
+    for (int i = threadIdx.x; i < TH * TW * 8; i += 256) {
+      const int px = i >> 3, c8 = i & 7;
+      const int h = h0 + px / TW, w = w0 + px % TW;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (h < H && w < W) v = *reinterpret_cast<const uint4*>(dpre + (((long)n * H + h) * W + w) * CO + c8 * 8);
+      *reinterpret_cast<uint4*>(&s_d[px][c8 * 8]) = v;
+    }
+    for (int i = threadIdx.x; i < 3 * (TH + 2) * (TW + 2); i += 256) {
+      const int c = i / ((TH + 2) * (TW + 2)), rr = i % ((TH + 2) * (TW + 2));
+      const int yy = h0 + rr / (TW + 2) - pad, xx = w0 + rr % (TW + 2) - pad;
+      s_img[c][rr / (TW + 2)][rr % (TW + 2)] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + ((long)n * 3 + c) * plane + (long)yy * W + xx) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int px = 0; px < TH * TW; ++px) {
+      const float d = __bfloat162float(s_d[px][co]);
+      const int y = px / TW, x = px % TW;
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const int tap = tg + j * TG;
-      if (tap < TAPS) {
-        const int c = tap / 9, t9 = tap - c * 9, kh = t9 / 3, kw = t9 - kh * 3;
-        const int yy = h + kh - pad, xx = w + kw - pad;
-        const float v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + ((long)n * 3 + c) * plane + (long)yy * W + xx) : 0.f;
-        acc[j] += d * v;
-      }
+      for (int j = 0; j < PER; ++j) acc[j] += d * s_img[t_c[j]][y + t_kh[j]][x + t_kw[j]];
     }
   }
 #pragma unroll
@@ -267,9 +290,9 @@ __global__ void __launch_bounds__(256) first_wgrad_kernel(const bf16* __restrict
   }
 }
 void launch_first_wgrad(const bf16* dpre, const float* img, float* dw, int N, int H, int W, int pad, int num_sms, cudaStream_t st) {
-  const long total = (long)N * H * W;
-  const long strip = std::max<long>(256, (total + (long)num_sms * 8 - 1) / ((long)num_sms * 8));
-  first_wgrad_kernel<<<cdiv(total, strip), 256, 0, st>>>(dpre, img, dw, N, H, W, pad, strip);
+  const long tiles = (long)N * ((H + 7) / 8) * ((W + 31) / 32);
+  const int grid = (int)std::min<long>(tiles, (long)num_sms * 4);
+  first_wgrad_kernel<<<grid, 256, 0, st>>>(dpre, img, dw, N, H, W, pad);
 }
 
 // ------------------------------------------------------------------------------------------ misc

@@ -80,6 +80,7 @@ class Model:
             self.param_numel.append(int(numel[0]))
         self.pnet = _Net(self._pnet_forward, self._pnet_backward)
         self.cnet = _Net(self._cnet_forward)
+        self.cnet._bwd = None
         self.n_heads = len(anchor_nets)
         if self.host_only:
             return

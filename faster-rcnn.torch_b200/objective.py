@@ -1,0 +1,57 @@
+"""Host mirror of objective.lua: create_objective(model, ...) -> lossAndGradient.
+
+The per-anchor Lua loops, the per-ROI pooling calls and every criterion of objective.lua:65-198 run inside
+frcnn_train_image (one call per frame); what stays here is what objective.lua does around them: zero the flat
+gradient (objective.lua:49), loop over the frames of the batch (:65), sum the statistics, and divide by the number of
+anchor examples (:200).  With torch.distributed initialised the frames of a batch are sharded over the ranks and the
+flat gradient plus the example / loss counters are summed with ONE all-reduce (NCCL over NVLink on the GPU box)
+before the division -- the only collective of the path."""
+import torch
+
+
+def clean_anchors(examples, dims):
+    """cleanAnchors (objective.lua:32-43): drop examples whose index lies outside the actual feature map."""
+    return [e for e in examples if e[0].index[1] <= dims[e[0].layer - 1][1] and e[0].index[2] <= dims[e[0].layer - 1][2]]
+
+
+def allreduce_gradient(gradient, counters, dist=None):
+    """Sums the flat gradient and the counters [cls_loss, reg_loss, creg_loss, ccls_loss, cls_count, reg_count,
+    ccls_count] over the ranks with one collective: the counters ride in the tail of the same buffer."""
+    c = torch.as_tensor(counters, dtype=gradient.dtype, device=gradient.device)
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return gradient, c
+    buf = torch.cat([gradient, c])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    gradient.copy_(buf[:gradient.numel()])
+    return gradient, buf[gradient.numel():].clone()
+
+
+def create_objective(model, dist=None):
+    """Returns lossAndGradient(batch, seed) -> (loss, gradient, stats); batch = list of dicts {img [3][H][W] tensor,
+    positive [(anchor, roi)], negative [(anchor,)]} as BatchIterator:nextTraining yields them (this rank's share)."""
+
+    def lossAndGradient(batch, seed=0):
+        model.zero_grad()                                   # gradient:zero()
+        model.pnet.training()
+        model.cnet.training()
+        sums = dict(cls=0.0, reg=0.0, creg=0.0, ccls=0.0)
+        cls_count = reg_count = ccls_count = 0
+        for i, x in enumerate(batch):
+            img = x["img"]
+            dims = model.output_dims(img.shape[1], img.shape[2])
+            p, n = clean_anchors(x["positive"], dims), clean_anchors(x["negative"], dims)
+            losses = model.train_image(img, p, n, seed=seed * 1000003 + i)
+            for k in sums:
+                sums[k] += losses[k]
+            reg_count += len(p)
+            cls_count += len(p) + len(n)
+            ccls_count += 1
+        gradient, c = allreduce_gradient(model.gradient, [sums["cls"], sums["reg"], sums["creg"], sums["ccls"], cls_count,
+                                                           reg_count, ccls_count], dist)
+        c = c.tolist()
+        gradient.div_(max(c[4], 1.0))                        # gradient:div(cls_count)
+        stats = dict(pcls=c[0] / max(c[4], 1.0), preg=c[1] / max(c[5], 1.0), dcls=c[3] / max(c[6], 1.0), dreg=c[2] / max(c[5], 1.0),
+                     cls_count=int(c[4]), reg_count=int(c[5]))
+        return stats["pcls"] + stats["preg"], gradient, stats
+
+    return lossAndGradient

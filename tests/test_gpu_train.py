@@ -231,3 +231,40 @@ def test_cnet_train_step_vs_autograd(F, small_model, R, n_pos):
         m.weights.copy_(saved)
         m.pack_weights()
         m.zero_grad()
+
+
+def test_create_objective_matches_manual_loop(F, small_model):
+    """lossAndGradient (objective.lua:45-218): zero, per-frame loop, gradient / cls_count, statistics."""
+    from oracle import anchors as OA, objective as OO
+    m = small_model
+    cfg = OM.CFG_DUPLO
+    h, w = 122, 192
+    dims = m.output_dims(h, w)
+    oa = OA.Anchors(OM.VGG_SMALL["layers"], OM.VGG_SMALL["anchor_nets"], cfg["scales"])
+    batch = []
+    for s in range(2):
+        pos, neg, _ = OO.synthetic_examples(oa, dims, w, h, 10, 14, 3, cfg["class_count"], seed=20 + s)
+        batch.append(dict(img=OM.synthetic_frame(h, w, seed=30 + s).cuda(), positive=pos, negative=neg))
+    saved = m.weights.clone()
+    try:
+        objective = F.create_objective(m)
+        loss, grad, stats = objective(batch, seed=5)
+        got = grad.clone()
+        assert stats["cls_count"] == 48 and stats["reg_count"] == 20 and np.isfinite(loss)
+        m.weights.copy_(saved)
+        m.pack_weights()
+        m.zero_grad()
+        tot = dict(cls=0.0, reg=0.0)
+        for i, x in enumerate(batch):
+            l = m.train_image(x["img"], x["positive"], x["negative"], seed=5 * 1000003 + i)
+            tot["cls"] += l["cls"]
+            tot["reg"] += l["reg"]
+        want = m.gradient / 48.0
+        assert ((got - want).norm() / want.norm()).item() < 2e-2   # same kernels; atomics / TMA reductions reorder sums
+        assert loss == pytest.approx(tot["cls"] / 48 + tot["reg"] / 20, rel=1e-3)
+    finally:
+        m.weights.copy_(saved)
+        m.pack_weights()
+        m.zero_grad()
+        m.pnet.evaluate()
+        m.cnet.evaluate()

@@ -57,3 +57,29 @@ def test_two_rank_gloo_job(tmp_path):
     assert sorted(res["merged"]) == list(range(21))
     for s in range(21):
         assert res["merged"][s] == ON.nms(boxes[seg[s]:seg[s + 1]], 0.25).tolist()
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import frcnn_b200 as F
+    g = torch.arange(10, dtype=torch.float32) * (rank + 1)
+    grad, c = F.allreduce_gradient(g, [1.0 + rank, 2.0, 3.0, 4.0, 100 + rank, 50, 1], dist)
+    if rank == 0:
+        torch.save(dict(grad=grad, c=c), out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_two_ranks(tmp_path):
+    """The one collective of the path: flat gradient + loss / example counters summed in one all-reduce."""
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_grad_worker, args=(2, 31500 + os.getpid() % 2000, out), nprocs=2, join=True)
+    res = torch.load(out)
+    assert torch.equal(res["grad"], torch.arange(10, dtype=torch.float32) * 3)
+    assert res["c"].tolist() == [3.0, 4.0, 6.0, 8.0, 201.0, 100.0, 2.0]
+    import frcnn_b200 as F
+    g = torch.ones(4)
+    grad, c = F.allreduce_gradient(g, [1, 2, 3, 4, 5, 6, 7], None)   # single process: identity
+    assert torch.equal(grad, torch.ones(4)) and c.tolist() == [1, 2, 3, 4, 5, 6, 7]
