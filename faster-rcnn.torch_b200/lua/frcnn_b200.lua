@@ -141,4 +141,39 @@ function M.pnet_forward(model, img)
   return outs
 end
 
+-- ---------------------------------------------------------------------------------------------- training
+-- Binds the flat gradient views (same walk as accelerate, but over gradWeight / gradBias).  Call once after
+-- combine_and_flatten_parameters (main.lua:92).
+function M.bind_grads(model, grad_ptrs)
+  local ctx = model.b200.ctx
+  local arr = ffi.new('float*[?]', #grad_ptrs, grad_ptrs)
+  check(ctx, C.frcnn_bind_grads(ctx, arr, #grad_ptrs))
+end
+
+-- The body of the per-image loop of lossAndGradient (objective.lua:65-198) as ONE call: positives = { {anchor, roi}, ... },
+-- negatives = { {anchor}, ... } exactly as BatchIterator:nextTraining yields them (after cleanAnchors).
+-- Returns cls_loss, reg_loss, creg_loss, ccls_loss of the frame; gradients accumulate in the flat gradient tensor.
+function M.train_image(model, img, positives, negatives, seed)
+  local ctx = model.b200.ctx
+  local function fill(e, anchor, roi)
+    e.anchor[0], e.anchor[1], e.anchor[2], e.anchor[3] = anchor.minX, anchor.minY, anchor.maxX, anchor.maxY
+    e.layer, e.aspect, e.y, e.x = anchor.layer, anchor.aspect, anchor.index[2], anchor.index[3]
+    if roi then
+      local r = roi.rect
+      e.roi[0], e.roi[1], e.roi[2], e.roi[3] = r.minX, r.minY, r.maxX, r.maxY
+      local t = Anchors.inputToAnchor(anchor, r)          -- FloatTensor(4), objective.lua:110
+      for k = 0, 3 do e.reg_target[k] = t[k + 1] end
+      e.class_index = roi.class_index
+    end
+  end
+  local pos = ffi.new('frcnn_example[?]', math.max(#positives, 1))
+  local neg = ffi.new('frcnn_example[?]', math.max(#negatives, 1))
+  for i, x in ipairs(positives) do fill(pos[i - 1], x[1], x[2]) end
+  for i, x in ipairs(negatives) do fill(neg[i - 1], x[1], nil) end
+  local losses = ffi.new('float[4]')
+  check(ctx, C.frcnn_train_image(ctx, img:data(), img:size(2), img:size(3), pos, #positives, neg, #negatives, nil, nil,
+                                 seed or 0, losses))
+  return losses[0], losses[1], losses[2], losses[3]
+end
+
 return M
