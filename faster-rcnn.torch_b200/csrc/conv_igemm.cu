@@ -486,6 +486,133 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
   }
 }
 
+// Warp-local epilogue of the first layer (64 output channels, tile width BW <= 16 so that every 2x2 pooling window lies
+// inside one warp's 32 pixel rows).  Warp e drains TMEM lane quarter (e & 3) of accumulator stage (e >> 2) -- the two
+// stages are drained concurrently -- through its own 4 KB staging tile with __syncwarp only: the per-tile latency
+// chain of the CTA-wide epilogue (two 256-thread barriers per tile) paced this K = 27 layer.
+__device__ __forceinline__ void epilogue_first_warp(const ConvParams& p, uint8_t* stage_base, const float* sbias, uint32_t tmem_base,
+                                                    uint64_t* tmem_full, uint64_t* tmem_empty, int total_tiles, int ewarp, int lane) {
+  constexpr int BN = 64;
+  const int q = ewarp & 3, stg = ewarp >> 2;
+  const int row = q * 32 + lane;
+  const uint32_t st_addr = ptx::smem_u32(stage_base + ewarp * 4096);
+  const uint32_t bias_addr = ptx::smem_u32(sbias);
+  const int sw = lane & 7;
+  const int dy = row >> p.bw_shift, dx = row & (p.BW - 1);
+  const float slope = p.prelu ? __ldg(p.prelu) : 1.0f;
+  const float k_neg = (slope - 1.0f) * p.scale, k_pos = p.scale;
+  const int Hp = (p.Hout + 1) >> 1, Wp = (p.Wout + 1) >> 1;
+  const int rows_per_warp = 32 >> p.bw_shift;  // tile rows covered by this warp (>= 2, even)
+  int seq = 0;
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++seq) {
+    if ((seq & 1) != stg) continue;
+    const uint32_t acc_phase = (uint32_t)(seq >> 1) & 1u;
+    const TileCoord t = decode_tile(p, tile, BN, 1, 1);
+    ptx::mbar_wait(&tmem_full[stg], acc_phase);
+    ptx::tc_fence_after();
+    const int h = t.h0 + dy, w = t.w0 + dx;
+    const bool valid = (h < p.Hout) && (w < p.Wout);
+    const uint32_t taddr = tmem_base + (uint32_t)(stg * BN) + ((uint32_t)(q * 32) << 16);
+    __syncwarp();  // the previous tile's staging reads are done
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(taddr + half * 32, v);
+      uint4 bq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bq[j] = ptx::ld_shared_v4(bias_addr + (uint32_t)(half * 32) * 4u + j * 16);
+      ptx::tmem_ld_wait();
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x0 = __uint_as_float(v[4 * j]) + __uint_as_float(bq[j].x);
+        const float x1 = __uint_as_float(v[4 * j + 1]) + __uint_as_float(bq[j].y);
+        const float x2 = __uint_as_float(v[4 * j + 2]) + __uint_as_float(bq[j].z);
+        const float x3 = __uint_as_float(v[4 * j + 3]) + __uint_as_float(bq[j].w);
+        float y0 = fmaf(fminf(x0, 0.f), k_neg, x0 * k_pos);
+        float y1 = fmaf(fminf(x1, 0.f), k_neg, x1 * k_pos);
+        float y2 = fmaf(fminf(x2, 0.f), k_neg, x2 * k_pos);
+        float y3 = fmaf(fminf(x3, 0.f), k_neg, x3 * k_pos);
+        if (p.chan_scale) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(p.chan_scale + (size_t)t.n_img * p.Cout + half * 32) + j);
+          y0 *= m.x; y1 *= m.y; y2 *= m.z; y3 *= m.w;
+        }
+        o[2 * j] = ptx::pack_bf16x2(y0, y1);
+        o[2 * j + 1] = ptx::pack_bf16x2(y2, y3);
+      }
+      if (p.mode == EPI_POOL && !valid) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = 0xFF80FF80u;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        ptx::st_shared_v4(st_addr + lane * 128 + (((half * 4 + c) ^ sw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+    }
+    // all TMEM reads of this warp's quarter are done: release the accumulator stage early
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&tmem_empty[stg]);
+    if (p.mode == EPI_POOL) {
+      bf16* out_img = reinterpret_cast<bf16*>(p.out) + (size_t)t.n_img * Hp * Wp * p.Cout;
+      const int pw_shift = p.bw_shift - 1;
+      const int pooled = 8;  // 32 pixels = 8 windows per warp
+#pragma unroll
+      for (int it = 0; it < 2; ++it) {
+        const int item = it * 32 + lane;           // (window, chunk)
+        const int pp = item >> 3, c = item & 7;
+        const int lppy = pp >> pw_shift, ppx = pp & ((p.BW >> 1) - 1);
+        const int ph = ((t.h0 + q * rows_per_warp) >> 1) + lppy, pw = (t.w0 >> 1) + ppx;
+        if (pp < pooled && ph < Hp && pw < Wp) {
+          const int r00 = (2 * lppy) * p.BW + 2 * ppx;   // local row inside the warp's 32 rows
+          const int r01 = r00 + 1, r10 = r00 + p.BW, r11 = r10 + 1;
+          uint4 a = ptx::ld_shared_v4(st_addr + r00 * 128 + ((c ^ (r00 & 7)) << 4));
+          const uint4 b = ptx::ld_shared_v4(st_addr + r01 * 128 + ((c ^ (r01 & 7)) << 4));
+          const uint4 cc = ptx::ld_shared_v4(st_addr + r10 * 128 + ((c ^ (r10 & 7)) << 4));
+          const uint4 d = ptx::ld_shared_v4(st_addr + r11 * 128 + ((c ^ (r11 & 7)) << 4));
+          if (p.pool_arg) {
+            const bf16* ea = reinterpret_cast<const bf16*>(&a);
+            const bf16* eb = reinterpret_cast<const bf16*>(&b);
+            const bf16* ec = reinterpret_cast<const bf16*>(&cc);
+            const bf16* ed = reinterpret_cast<const bf16*>(&d);
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float best = __bfloat162float(ea[e]);
+              uint32_t arg = 0;
+              const float vb = __bfloat162float(eb[e]), vc = __bfloat162float(ec[e]), vd = __bfloat162float(ed[e]);
+              if (vb > best) { best = vb; arg = 1; }
+              if (vc > best) { best = vc; arg = 2; }
+              if (vd > best) { best = vd; arg = 3; }
+              if (e < 4) lo |= arg << (8 * e); else hi |= arg << (8 * (e - 4));
+            }
+            *reinterpret_cast<uint2*>(p.pool_arg + (((size_t)t.n_img * Hp + ph) * Wp + pw) * p.Cout + c * 8) = make_uint2(lo, hi);
+          }
+          __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
+          const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+          const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&cc);
+          const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&d);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) pa[j] = __hmax2(__hmax2(pa[j], pb[j]), __hmax2(pc[j], pd[j]));
+          *reinterpret_cast<uint4*>(out_img + ((size_t)ph * Wp + pw) * p.Cout + c * 8) = a;
+        }
+      }
+    } else {
+      bf16* out_img = reinterpret_cast<bf16*>(p.out) + (size_t)t.n_img * p.Hout * p.Wout * p.Cout;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int idx = it * 32 + lane;
+        const int lr = idx >> 3, c = idx & 7;
+        const int r = q * 32 + lr;
+        const int hh = t.h0 + (r >> p.bw_shift), ww = t.w0 + (r & (p.BW - 1));
+        if (hh < p.Hout && ww < p.Wout) {
+          const uint4 val = ptx::ld_shared_v4(st_addr + lr * 128 + ((c ^ (lr & 7)) << 4));
+          *reinterpret_cast<uint4*>(out_img + ((size_t)hh * p.Wout + ww) * p.Cout + c * 8) = val;
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- first layer
 // 3 x (3x3) first convolution on the fp32 NCHW frame (Detector.lua:32-33 uploads exactly this tensor).
 // 640 threads: warps 0-7 build the im2col rows (K = 27 -> 32, 64 bytes of each 128-byte swizzled row) in two groups
@@ -496,7 +623,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 static constexpr int FIRST_STAGES = 6;
 static constexpr int FIRST_BN = 64;
 static constexpr int FIRST_THREADS = 640;
-static constexpr int FIRST_SMEM = FIRST_STAGES * A_SUB_BYTES + FIRST_BN * 128 + SMEM_FIXED;
+static constexpr int FIRST_SMEM = FIRST_STAGES * A_SUB_BYTES + FIRST_BN * 128 + SMEM_FIXED + STAGE_TILE_BYTES;  // 8 x 4 KB warp staging
 
 __device__ __forceinline__ void first_load_taps(const ConvParams& p, int tile, int dy, int dx, float (&v)[27]) {
   const TileCoord t = decode_tile(p, tile, FIRST_BN, 1, 1);
@@ -536,8 +663,8 @@ __global__ void __launch_bounds__(FIRST_THREADS, 1)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + FIRST_STAGES * A_SUB_BYTES;
-  uint8_t* tile_buf = smem_b + BN * 128;
-  float* sbias = reinterpret_cast<float*>(tile_buf + STAGE_TILE_BYTES);
+  uint8_t* tile_buf = smem_b + BN * 128;                      // 8 warps x 4 KB
+  float* sbias = reinterpret_cast<float*>(tile_buf + 2 * STAGE_TILE_BYTES);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
   uint64_t* empty_bar = full_bar + FIRST_STAGES;
   uint64_t* tmem_full = empty_bar + FIRST_STAGES;
@@ -555,7 +682,7 @@ __global__ void __launch_bounds__(FIRST_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], EPI_THREADS / 32);
+      ptx::mbar_init(&tmem_empty[a], 4);  // four warps (one per TMEM lane quarter) drain each accumulator stage
     }
     ptx::fence_barrier_init();
   }
@@ -631,9 +758,7 @@ __global__ void __launch_bounds__(FIRST_THREADS, 1)
       }
     }
   } else if (warp >= 12) {
-    GroupSched sc;
-    make_sched(grp, BN, sc);
-    epilogue_loop<BN, 1>(grp, &tmOut, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 12, lane);
+    epilogue_first_warp(p, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, total_tiles, warp - 12, lane);
   }
 
   ptx::tc_fence_before();
@@ -691,9 +816,9 @@ void make_tmap_weight(CUtensorMap* m, const bf16* base, int Cout, int K, int BN)
 
 // Pick the BW x BH (= 128) rectangle that wastes the fewest padded pixels.  mt: sub-tiles stacked along H;
 // even: both sides even (needed by the fused 2x2 pool).
-static void choose_tile(int Hout, int Wout, int mt, bool even, int* BW, int* BH) {
+static void choose_tile(int Hout, int Wout, int mt, bool even, int* BW, int* BH, int max_bw = 128) {
   long best = -1;
-  for (int bw = even ? 64 : 128; bw >= (even ? 2 : 1); bw >>= 1) {
+  for (int bw = std::min(even ? 64 : 128, max_bw); bw >= (even ? 2 : 1); bw >>= 1) {
     int bh = 128 / bw;
     long th = (long)bh * mt;
     long padded = (long)((Wout + bw - 1) / bw) * bw * (long)((Hout + th - 1) / th) * th;
@@ -713,9 +838,8 @@ static int choose_bn(int Cout) {
   if (Cout <= 64) return 64;
   return 128;
 }
-
 static void fill_geometry(ConvParams& p, int N, int Hin, int Win, int Cin, int Cout, int KH, int KW, int padH, int padW,
-                          int mode, int MT) {
+                          int mode, int MT, int max_bw = 128) {
   p = ConvParams();
   p.N = N; p.Hin = Hin; p.Win = Win; p.Cin = Cin;
   p.Hout = Hin + 2 * padH - KH + 1;
@@ -723,7 +847,7 @@ static void fill_geometry(ConvParams& p, int N, int Hin, int Win, int Cin, int C
   FRCNN_REQUIRE(p.Hout > 0 && p.Wout > 0, FRCNN_E_INVALID, "conv: input smaller than the kernel");
   p.Cout = Cout; p.KH = KH; p.KW = KW; p.padH = padH; p.padW = padW;
   p.MT = MT;
-  choose_tile(p.Hout, p.Wout, MT, mode == EPI_POOL, &p.BW, &p.BH);
+  choose_tile(p.Hout, p.Wout, MT, mode == EPI_POOL || max_bw < 128, &p.BW, &p.BH, max_bw);
   p.bw_shift = 0;
   while ((1 << p.bw_shift) < p.BW) ++p.bw_shift;
   p.tiles_w = (p.Wout + p.BW - 1) / p.BW;
@@ -762,7 +886,9 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
   FRCNN_REQUIRE(f32 ? Cout % 32 == 0 : (Cout % 64 == 0 && Cout <= MAX_BIAS), FRCNN_E_INVALID,
                 "conv: Cout must be a multiple of 64 (<= 512) for the bf16 epilogues, of 32 for split-K");
   FRCNN_REQUIRE(f32 || out != nullptr, FRCNN_E_INVALID, "conv: null output");
-  int BN = force_bn > 0 ? force_bn : choose_bn(Cout);
+  // the widest tile dividing Cout wins even when it leaves SMs idle (measured at batch 1, conv4_x: 100 CTAs of BN=192
+  // take 20/26 us, 135 CTAs of BN=128 take 34/46 us -- operand traffic per MAC, not occupancy, bounds these layers)
+  const int BN = force_bn > 0 ? force_bn : choose_bn(Cout);
   L->BN = BN;
   L->first = false;
   L->w_first = nullptr;
@@ -871,7 +997,7 @@ void conv_first_prepare(ConvLaunch* L, const bf16* w_packed32, int N, int Hin, i
   L->BN = FIRST_BN;
   L->first = true;
   L->w_first = w_packed32;
-  fill_geometry(L->p, N, Hin, Win, 64, Cout, KH, KW, padH, padW, mode, 1);
+  fill_geometry(L->p, N, Hin, Win, 64, Cout, KH, KW, padH, padW, mode, 1, 16);  // BW <= 16: warp-local pooling windows
   ConvParams& p = L->p;
   p.Cimg = Cimg;
   p.n_tiles_n = 1;

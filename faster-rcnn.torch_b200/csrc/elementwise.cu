@@ -184,9 +184,15 @@ __global__ void __launch_bounds__(256) head_tail_group_kernel(HeadTailGroup g) {
   while (hi + 1 < g.n && (int)blockIdx.x >= g.h[hi].block_end) ++hi;
   const HeadTail& H = g.h[hi];
   const int block0 = hi ? g.h[hi - 1].block_end : 0;
-  // parameter pointers are views into Torch's flat buffer at arbitrary 4-byte offsets: scalar loads
-  for (int i = threadIdx.x; i < CO * CM; i += blockDim.x) sw[i] = H.w2[i];
-  for (int i = threadIdx.x; i < CM; i += blockDim.x) sbias[i] = H.bias[i];
+  // parameter pointers are views into Torch's flat buffer at arbitrary 4-byte offsets: vector loads only when the
+  // view happens to be 16-byte aligned
+  if ((reinterpret_cast<uintptr_t>(H.w2) & 15) == 0) {
+    for (int i = threadIdx.x; i < CO * CM / 4; i += blockDim.x)
+      reinterpret_cast<float4*>(sw)[i] = __ldg(reinterpret_cast<const float4*>(H.w2) + i);
+  } else {
+    for (int i = threadIdx.x; i < CO * CM; i += blockDim.x) sw[i] = __ldg(H.w2 + i);
+  }
+  for (int i = threadIdx.x; i < CM; i += blockDim.x) sbias[i] = __ldg(H.bias + i);
   __syncthreads();
   const float slope = H.prelu[0];
   const int lane = threadIdx.x & 31;
@@ -258,10 +264,11 @@ __global__ void __launch_bounds__(256) head_tail_group_kernel(HeadTailGroup g) {
 void launch_head_tail_group(const HeadTailGroup& g_in, int num_sms, cudaStream_t st) {
   HeadTailGroup g = g_in;
   FRCNN_REQUIRE(g.n >= 1 && g.n <= 4, FRCNN_E_INVALID, "anchor head group: 1..4 heads");
-  // blocks per head proportional to its pixels (8 warps x 4 pixels per block iteration), at most ~4 blocks per SM
+  // blocks per head proportional to its pixels (8 warps x 4 pixels per block iteration), about two blocks per SM:
+  // every block stages the 18 x 256 weights once, so fewer, longer-running blocks amortise that better
   long total_px = 0;
   for (int i = 0; i < g.n; ++i) total_px += g.h[i].npix;
-  const long budget = (long)num_sms * 4;
+  const long budget = (long)num_sms * 2;
   int end = 0;
   for (int i = 0; i < g.n; ++i) {
     long want = (g.h[i].npix + 31) / 32;
