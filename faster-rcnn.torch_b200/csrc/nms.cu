@@ -39,14 +39,20 @@ __device__ __forceinline__ float box_area(float4 b) {
 }
 
 // true iff the reference would drop box j after picking box i: NOT (IoU <= overlap)   (nms.lua:72-96)
+// A zero intersection (the common case) never reaches the divider: +0 / d is NaN for d == 0 or NaN and +-0 otherwise,
+// so the IEEE result of the comparison is known; those lanes divide 1 / 1 instead, which keeps the whole warp off the
+// slow path the division takes for zero / denormal numerators.  Bit-identical to dividing.
 __device__ __forceinline__ bool suppresses(float4 bi, float ai, float4 bj, float aj, float thr) {
   float xx1 = fmaxf(bj.x, bi.x), yy1 = fmaxf(bj.y, bi.y);
   float xx2 = fminf(bj.z, bi.z), yy2 = fminf(bj.w, bi.w);
   float w = fmaxf(__fadd_rn(__fsub_rn(xx2, xx1), 1.0f), 0.0f);
   float h = fmaxf(__fadd_rn(__fsub_rn(yy2, yy1), 1.0f), 0.0f);
   float inter = __fmul_rn(w, h);
-  float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aj, ai), inter));
-  return !(iou <= thr);
+  float denom = __fsub_rn(__fadd_rn(aj, ai), inter);
+  const bool zero = inter == 0.0f;
+  const float iou = __fdiv_rn(zero ? 1.0f : inter, zero ? 1.0f : denom);
+  const bool sup_zero = (denom != denom) || (denom == 0.0f) || !(0.0f <= thr);
+  return zero ? sup_zero : !(iou <= thr);
 }
 
 __device__ __forceinline__ float4 load_box(const float* boxes, long row, int row_stride) {
@@ -285,109 +291,47 @@ __global__ void __launch_bounds__(1024) nms_select_kernel(NmsState st, const flo
 // mask[s][j][wi] bit b  <=>  selected candidate i = 32*wi + b (i < j) would suppress selected candidate j.
 // Thread <-> (j, wi) with consecutive threads on consecutive j: box i is a warp-wide broadcast.
 __global__ void __launch_bounds__(256) nms_mask_kernel(NmsState st, float thr) {
+  __shared__ float4 ib[32];
+  __shared__ float ia[32];
   const int s = blockIdx.y;
   const int m = st.sel_cnt[s];
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int j = idx % NMS_B;
+  const int j = idx % NMS_B;           // a block covers 256 consecutive j of one word index
   const int wi = idx / NMS_B;
-  const int j_warp_max = (j | 31);
-  if (wi * 32 > j_warp_max || (j & ~31) >= m) return;  // warp-uniform: upper triangle or beyond the selection
+  const int j_block_max = (j - (int)threadIdx.x) + 255;
+  if (wi * 32 > j_block_max || (j - (int)threadIdx.x) >= m) return;  // block-uniform: upper triangle or beyond the selection
   const float4* sb = st.sel_box + (long)s * NMS_B;
   const float* sa = st.sel_area + (long)s * NMS_B;
-  uint32_t word = 0;
-  if (j < m) {
-    float4 bj = sb[j];
-    float aj = sa[j];
-    int i_end = min(32, j - wi * 32);  // only i < j
-    for (int b = 0; b < i_end; ++b) {
-      int i = wi * 32 + b;
-      if (suppresses(sb[i], sa[i], bj, aj, thr)) word |= 1u << b;
-    }
+  if (threadIdx.x < 32) {
+    const int i = wi * 32 + threadIdx.x;
+    ib[threadIdx.x] = i < m ? sb[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    ia[threadIdx.x] = i < m ? sa[i] : 0.f;
   }
-  if (j < m) st.mask[((long)s * NMS_B + j) * NMS_ROW_WORDS + wi] = word;
+  __syncthreads();
+  if (j >= m || wi * 32 > j) return;
+  const float4 bj = sb[j];
+  const float aj = sa[j];
+  uint32_t word = 0;
+#pragma unroll 8
+  for (int b = 0; b < 32; ++b) word |= suppresses(ib[b], ia[b], bj, aj, thr) ? (1u << b) : 0u;
+  word &= (wi == (j >> 5)) ? ((1u << (j & 31)) - 1u) : 0xffffffffu;
+  st.mask[((long)s * NMS_B + j) * NMS_ROW_WORDS + wi] = word;
 }
 
 // ------------------------------------------------------------------------------------------------ resolve
+__device__ void cta_load_mask(uint32_t* smask, const NmsState& st, int s, int m);
+__device__ int cta_resolve(const uint32_t* smask, const NmsState& st, int s, int m);
+
 __global__ void __launch_bounds__(1024) nms_resolve_kernel(NmsState st) {
   extern __shared__ uint32_t smask[];  // [NMS_B][33] padded rows (bank-conflict-free column walks)
-  __shared__ uint32_t kept[NMS_ROW_WORDS], undec[NMS_ROW_WORDS];
-  __shared__ int warp_cnt[32];
   const int s = blockIdx.x;
   const int m = st.sel_cnt[s];
-  const int j = threadIdx.x;
-  const int warp = j >> 5, lane = j & 31;
   if (m == 0) {
-    if (j == 0) st.newk_cnt[s] = 0;
+    if (threadIdx.x == 0) st.newk_cnt[s] = 0;
     return;
   }
-  const int beg = st.seg_beg[s];
-  // rows < m, words <= row/32 are valid in global memory; everything else is treated as zero
-  for (int idx = j; idx < NMS_B * NMS_ROW_WORDS; idx += 1024) {
-    int r = idx >> 5, w = idx & 31;
-    uint32_t v = 0;
-    if (r < m && w * 32 <= r) v = st.mask[((long)s * NMS_B + r) * NMS_ROW_WORDS + w];
-    smask[r * 33 + w] = v;
-  }
-  if (j < NMS_ROW_WORDS) {
-    kept[j] = 0;
-    int lo = j * 32;
-    undec[j] = m >= lo + 32 ? 0xffffffffu : (m > lo ? ((1u << (m - lo)) - 1u) : 0u);
-  }
-  __syncthreads();
-  const int nwords = (j >> 5) + 1;  // predecessors of j live in words 0..j/32
-  bool undecided = j < m;
-  bool is_kept = false;
-  for (;;) {
-    int decision = 0;  // 1 keep, 2 drop
-    if (undecided) {
-      bool hit_kept = false, hit_undec = false;
-      for (int w = 0; w < nwords; ++w) {
-        uint32_t row = smask[j * 33 + w];
-        hit_kept |= (row & kept[w]) != 0;
-        hit_undec |= (row & undec[w]) != 0;
-      }
-      if (hit_kept) decision = 2;
-      else if (!hit_undec) decision = 1;
-    }
-    int progress = __syncthreads_or(decision != 0);  // also separates the read phase from the write phase
-    if (decision != 0) {
-      atomicAnd(&undec[warp], ~(1u << lane));
-      if (decision == 1) {
-        atomicOr(&kept[warp], 1u << lane);
-        is_kept = true;
-      }
-      undecided = false;
-    }
-    int any_left = __syncthreads_or(undecided);
-    if (!any_left) break;
-    if (!progress) break;  // cannot happen (the first undecided candidate is always decidable); guards against hangs
-  }
-  // append the keepers in priority order
-  unsigned bal = __ballot_sync(0xffffffffu, is_kept);
-  if (lane == 0) warp_cnt[warp] = __popc(bal);
-  __syncthreads();
-  int before = 0, total = 0;
-  for (int w = 0; w < 32; ++w) {
-    int c = warp_cnt[w];
-    if (w < warp) before += c;
-    total += c;
-  }
-  const int base_count = st.counts[s];
-  if (j < m) {
-    int pos = st.sel_pos[(long)s * NMS_B + j];
-    st.alive[beg + pos] = 0;  // every selected candidate is decided now
-    if (is_kept) {
-      int slot = before + __popc(bal & ((1u << lane) - 1u));
-      st.pick[beg + base_count + slot] = st.order[beg + pos];
-      st.newk_box[(long)s * NMS_B + slot] = st.sel_box[(long)s * NMS_B + j];
-      st.newk_area[(long)s * NMS_B + slot] = st.sel_area[(long)s * NMS_B + j];
-    }
-  }
-  __syncthreads();
-  if (j == 0) {
-    st.counts[s] = base_count + total;
-    st.newk_cnt[s] = total;
-  }
+  cta_load_mask(smask, st, s, m);
+  cta_resolve(smask, st, s, m);
 }
 
 // ------------------------------------------------------------------------------------------------ filter
@@ -443,43 +387,110 @@ __global__ void __launch_bounds__(256) nms_filter_kernel(NmsState st, const floa
 // back to back instead of one launch per step.  Three launches per NMS -- sort + first selection (one CTA per
 // segment), the 1024 x 1024 suppression matrix of the first selection on all SMs, resolve + filter + every further
 // round inside the CTA -- or ONE launch (fused) when the segments are known to be small (per-class NMS).
+// Bitonic sort (descending) of <= SORT_CTA_MAX 64-bit keys.  Thread t keeps the adjacent pairs (c * 2048 + 2t, + 1) in
+// registers: the compare-exchange distances 1..32 run on shuffles without a block barrier, only distances >= 64 go
+// through shared memory (15 block-level stages instead of 66 for 2048 keys).
+__device__ __forceinline__ void cx_reg(unsigned long long& mine, unsigned long long other, bool take_max) {
+  const bool other_bigger = other > mine;
+  if (other_bigger == take_max) mine = other;
+}
 __device__ void cta_sort(unsigned long long* skeys, const NmsState& st, int s, const float* __restrict__ boxes, int row_stride,
                          int order_mode, int order_col, int cap_len) {
+  constexpr int MAXC = SORT_CTA_MAX / 2048;
   const int beg = st.seg_beg[s];
   const int len = min(st.seg_len[s], cap_len);
   if (len <= 0) return;  // uniform
-  int n2 = 1;
+  int n2 = 2;
   while (n2 < len) n2 <<= 1;
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-    unsigned long long k = 0ull;
-    if (i < len) k = ((unsigned long long)orderable(order_key(boxes, beg + i, row_stride, order_mode, order_col)) << 32) | (unsigned)i;
-    skeys[i] = k;
-  }
-  __syncthreads();
-  for (int size = 2; size <= n2; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int t = threadIdx.x; t < (n2 >> 1); t += blockDim.x) {
-        int lo = 2 * t - (t & (stride - 1));
-        int hi = lo + stride;
-        bool desc = ((lo & size) == 0);
-        unsigned long long a = skeys[lo], b = skeys[hi];
-        if ((a < b) == desc) {
-          skeys[lo] = b;
-          skeys[hi] = a;
-        }
-      }
-      __syncthreads();
+  const int t = threadIdx.x, lane = t & 31;
+  const int nchunks = (n2 + 2047) >> 11;
+  unsigned long long k0[MAXC], k1[MAXC];
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int e = c * 2048 + 2 * t;
+    k0[c] = 0ull;
+    k1[c] = 0ull;
+    if (c < nchunks) {
+      if (e < len) k0[c] = ((unsigned long long)orderable(order_key(boxes, beg + e, row_stride, order_mode, order_col)) << 32) | (unsigned)e;
+      if (e + 1 < len) k1[c] = ((unsigned long long)orderable(order_key(boxes, beg + e + 1, row_stride, order_mode, order_col)) << 32) | (unsigned)(e + 1);
     }
   }
-  for (int i = threadIdx.x; i < len; i += blockDim.x) {
-    st.order[beg + i] = (int)(unsigned)(skeys[i] & 0xffffffffull);
-    st.alive[beg + i] = 1;
+  for (int size = 2; size <= n2; size <<= 1) {
+    int stride = size >> 1;
+    if (stride >= 64) {
+      // block-level distances through shared memory
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c)
+        if (c < nchunks && c * 2048 + 2 * t < n2) {
+          skeys[c * 2048 + 2 * t] = k0[c];
+          skeys[c * 2048 + 2 * t + 1] = k1[c];
+        }
+      __syncthreads();
+      for (; stride >= 64; stride >>= 1) {
+        for (int u = t; u < (n2 >> 1); u += 1024) {
+          const int lo = 2 * u - (u & (stride - 1));
+          const int hi = lo + stride;
+          const bool desc = ((lo & size) == 0);
+          const unsigned long long a = skeys[lo], b = skeys[hi];
+          if ((a < b) == desc) {
+            skeys[lo] = b;
+            skeys[hi] = a;
+          }
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int c = 0; c < MAXC; ++c)
+        if (c < nchunks && c * 2048 + 2 * t < n2) {
+          k0[c] = skeys[c * 2048 + 2 * t];
+          k1[c] = skeys[c * 2048 + 2 * t + 1];
+        }
+    }
+    // distances 32..2 between lanes, distance 1 inside the thread
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+      if (c >= nchunks) continue;  // uniform
+      const int e = c * 2048 + 2 * t;
+      const bool desc = ((e & size) == 0);
+      for (int sd = min(stride, 32); sd >= 2; sd >>= 1) {
+        const int x = sd >> 1;
+        const unsigned long long o0 = __shfl_xor_sync(0xffffffffu, k0[c], x);
+        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, k1[c], x);
+        const bool is_lo = (lane & x) == 0;
+        cx_reg(k0[c], o0, desc == is_lo);
+        cx_reg(k1[c], o1, desc == is_lo);
+      }
+      if ((k0[c] < k1[c]) == desc) {
+        const unsigned long long tmp = k0[c];
+        k0[c] = k1[c];
+        k1[c] = tmp;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < MAXC; ++c) {
+    const int e = c * 2048 + 2 * t;
+    if (c < nchunks) {
+      if (e < len) {
+        st.order[beg + e] = (int)(unsigned)(k0[c] & 0xffffffffull);
+        st.alive[beg + e] = 1;
+      }
+      if (e + 1 < len) {
+        st.order[beg + e + 1] = (int)(unsigned)(k1[c] & 0xffffffffull);
+        st.alive[beg + e + 1] = 1;
+      }
+    }
   }
   __syncthreads();
 }
 
 // first NMS_B alive candidates behind the cursor -> sel_*; returns the selection size (uniform)
-__device__ int cta_select(const NmsState& st, int s, const float* __restrict__ boxes, int row_stride) {
+struct CtaSel {  // this round's selection, kept on chip for the in-CTA suppression matrix
+  float4 box[NMS_B];
+  float area[NMS_B];
+};
+__device__ int cta_select(const NmsState& st, int s, const float* __restrict__ boxes, int row_stride, CtaSel* sel) {
   __shared__ int warp_cnt[32];
   __shared__ int s_next;
   const int beg = st.seg_beg[s];
@@ -492,7 +503,9 @@ __device__ int cta_select(const NmsState& st, int s, const float* __restrict__ b
   int taken = 0;
   for (int base = cur; base < len && taken < NMS_B; base += 1024) {
     int pos = base + threadIdx.x;
-    bool a = pos < len && st.alive[beg + pos] != 0;
+    const bool in = pos < len;
+    const int local = in ? st.order[beg + pos] : 0;  // independent of the alive flag: one memory round trip
+    bool a = in && st.alive[beg + pos] != 0;
     unsigned bal = __ballot_sync(0xffffffffu, a);
     if (lane == 0) warp_cnt[warp] = __popc(bal);
     __syncthreads();
@@ -504,11 +517,13 @@ __device__ int cta_select(const NmsState& st, int s, const float* __restrict__ b
     }
     int slot = taken + before + __popc(bal & ((1u << lane) - 1u));
     if (a && slot < NMS_B) {
-      int local = st.order[beg + pos];
       float4 b = load_box(boxes, beg + local, row_stride);
+      const float ar = box_area(b);
       st.sel_pos[(long)s * NMS_B + slot] = pos;
       st.sel_box[(long)s * NMS_B + slot] = b;
-      st.sel_area[(long)s * NMS_B + slot] = box_area(b);
+      st.sel_area[(long)s * NMS_B + slot] = ar;
+      sel->box[slot] = b;
+      sel->area[slot] = ar;
       if (slot == NMS_B - 1) s_next = pos + 1;
     }
     taken += chunk_total;
@@ -523,80 +538,96 @@ __device__ int cta_select(const NmsState& st, int s, const float* __restrict__ b
   return m;
 }
 
-// suppression matrix of the selection computed by this CTA, straight into shared memory
-__device__ void cta_mask(uint32_t* smask, const NmsState& st, int s, int m, float thr) {
-  const float4* sb = st.sel_box + (long)s * NMS_B;
-  const float* sa = st.sel_area + (long)s * NMS_B;
-  const int j = threadIdx.x;
-  if (j < m) {
-    const float4 bj = sb[j];
-    const float aj = sa[j];
-    for (int wi = 0; wi < NMS_ROW_WORDS; ++wi) {
-      uint32_t word = 0;
-      const int i_end = min(32, j - wi * 32);
-      for (int b = 0; b < i_end; ++b) {
-        const int i = wi * 32 + b;
-        if (suppresses(sb[i], sa[i], bj, aj, thr)) word |= 1u << b;
-      }
-      smask[j * 33 + wi] = word;
+// suppression matrix of the selection computed by this CTA from the on-chip selection, straight into shared memory
+// (rows < m, words <= row / 32: all the resolve reads).  Thread <-> (word, row) with consecutive threads on
+// consecutive rows: box i is a warp-wide shared-memory broadcast.
+__device__ void cta_mask(uint32_t* smask, const CtaSel* sel, int m, float thr) {
+  const int nw = (m + 31) >> 5;
+  for (int idx = threadIdx.x; idx < m * nw; idx += 1024) {
+    const int wi = idx / m, j = idx - wi * m;
+    if (wi > (j >> 5)) continue;
+    const float4 bj = sel->box[j];
+    const float aj = sel->area[j];
+    // all 32 tests of the word, independent of each other (entries i >= j are masked off afterwards; slots beyond m
+    // hold stale boxes, which is harmless for the same reason)
+    uint32_t word = 0;
+#pragma unroll 8
+    for (int b = 0; b < 32; ++b) {
+      const int i = wi * 32 + b;
+      const bool in = i < j;  // later slots may hold stale boxes: test the box against itself instead
+      word |= suppresses(in ? sel->box[i] : bj, in ? sel->area[i] : aj, bj, aj, thr) ? (1u << b) : 0u;
     }
-  } else {
-    for (int wi = 0; wi < NMS_ROW_WORDS; ++wi) smask[j * 33 + wi] = 0;
+    word &= (wi == (j >> 5)) ? ((1u << (j & 31)) - 1u) : 0xffffffffu;
+    smask[j * 33 + wi] = word;
   }
   __syncthreads();
 }
 
 __device__ void cta_load_mask(uint32_t* smask, const NmsState& st, int s, int m) {
-  for (int idx = threadIdx.x; idx < NMS_B * NMS_ROW_WORDS; idx += 1024) {
-    int r = idx >> 5, w = idx & 31;
-    uint32_t v = 0;
-    if (r < m && w * 32 <= r) v = st.mask[((long)s * NMS_B + r) * NMS_ROW_WORDS + w];
-    smask[r * 33 + w] = v;
+  const uint32_t* g = st.mask + (long)s * NMS_B * NMS_ROW_WORDS;
+  const int total = m * NMS_ROW_WORDS;
+  for (int base = threadIdx.x; base < total; base += 8 * 1024) {
+    uint32_t v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * 1024;
+      const int r = idx >> 5, w = idx & 31;
+      v[u] = (idx < total && w * 32 <= r) ? g[idx] : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * 1024;
+      const int r = idx >> 5, w = idx & 31;
+      if (idx < total && w * 32 <= r) smask[r * 33 + w] = v[u];
+    }
   }
   __syncthreads();
 }
 
-// greedy recursion over the selection as a fixed point; appends the keepers; returns their number (uniform)
+// Greedy recursion over the selection; appends the keepers; returns their number (uniform).  Warp w owns candidates
+// 32w..32w+31: it folds in the keeper words of the earlier warps as they are published (spin on a shared 64-bit
+// {flag, word} slot -- all 32 warps of the CTA are resident and warp w only ever waits for warps < w), then settles its
+// own 32 candidates with a warp-local fixed point on ballots (as many iterations as the longest suppression chain
+// inside the block, usually 1-3).  The critical path is 32 x (one word hand-over + that fixed point), not one
+// block-wide barrier pair per level of the whole dependency graph.
 __device__ int cta_resolve(const uint32_t* smask, const NmsState& st, int s, int m) {
-  __shared__ uint32_t kept[NMS_ROW_WORDS], undec[NMS_ROW_WORDS];
+  __shared__ volatile unsigned long long kept_slot[NMS_ROW_WORDS];  // bit 32 = published, low word = keepers
   __shared__ int warp_cnt[32];
   const int j = threadIdx.x;
   const int warp = j >> 5, lane = j & 31;
   const int beg = st.seg_beg[s];
+  const int base_count = st.counts[s];
+  const int my_pos = j < m ? st.sel_pos[(long)s * NMS_B + j] : 0;
   __syncthreads();
-  if (j < NMS_ROW_WORDS) {
-    kept[j] = 0;
-    int lo = j * 32;
-    undec[j] = m >= lo + 32 ? 0xffffffffu : (m > lo ? ((1u << (m - lo)) - 1u) : 0u);
-  }
+  if (j < NMS_ROW_WORDS) kept_slot[j] = 0ull;
   __syncthreads();
-  const int nwords = (j >> 5) + 1;
-  bool undecided = j < m;
+  const int nblocks = (m + 31) >> 5;
   bool is_kept = false;
-  for (;;) {
-    int decision = 0;
-    if (undecided) {
-      bool hit_kept = false, hit_undec = false;
-      for (int w = 0; w < nwords; ++w) {
-        uint32_t row = smask[j * 33 + w];
-        hit_kept |= (row & kept[w]) != 0;
-        hit_undec |= (row & undec[w]) != 0;
-      }
-      if (hit_kept) decision = 2;
-      else if (!hit_undec) decision = 1;
+  if (warp < nblocks) {
+    bool dead = j >= m;
+    const uint32_t* row = smask + j * 33;
+    const uint32_t d = dead ? 0u : (row[warp] & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) {
+      const uint32_t r = dead ? 0u : row[w];
+      unsigned long long slot;
+      do {
+        slot = kept_slot[w];
+      } while ((slot >> 32) == 0ull);
+      dead |= (r & (uint32_t)slot) != 0;
     }
-    int progress = __syncthreads_or(decision != 0);
-    if (decision != 0) {
-      atomicAnd(&undec[warp], ~(1u << lane));
-      if (decision == 1) {
-        atomicOr(&kept[warp], 1u << lane);
-        is_kept = true;
-      }
-      undecided = false;
+    uint32_t undec = ~__ballot_sync(0xffffffffu, dead);
+    uint32_t kw = 0;
+    while (undec != 0u) {  // uniform
+      const bool me = (undec >> lane) & 1u;
+      const bool hit_kept = (d & kw) != 0u;
+      const bool hit_undec = (d & undec) != 0u;
+      const uint32_t k = __ballot_sync(0xffffffffu, me && !hit_kept && !hit_undec);
+      const uint32_t dr = __ballot_sync(0xffffffffu, me && hit_kept);
+      kw |= k;
+      undec &= ~(k | dr);
     }
-    int any_left = __syncthreads_or(undecided);
-    if (!any_left) break;
-    if (!progress) break;
+    is_kept = (kw >> lane) & 1u;
+    if (lane == 0) kept_slot[warp] = (1ull << 32) | kw;
   }
   unsigned bal = __ballot_sync(0xffffffffu, is_kept);
   if (lane == 0) warp_cnt[warp] = __popc(bal);
@@ -607,9 +638,8 @@ __device__ int cta_resolve(const uint32_t* smask, const NmsState& st, int s, int
     if (w < warp) before += c;
     total += c;
   }
-  const int base_count = st.counts[s];
   if (j < m) {
-    int pos = st.sel_pos[(long)s * NMS_B + j];
+    const int pos = my_pos;
     st.alive[beg + pos] = 0;
     if (is_kept) {
       int slot = before + __popc(bal & ((1u << lane) - 1u));
@@ -668,6 +698,13 @@ __device__ void cta_filter(const NmsState& st, int s, const float* __restrict__ 
 
 enum { NMS_PH_SORT_SELECT = 0, NMS_PH_RESOLVE_LOOP = 1, NMS_PH_FUSED = 2 };
 
+// development aid (FRCNN_NMS_PROF=1): phase time stamps of CTA 0, printed by the host after the launch
+__device__ long long g_nms_prof[64];
+__device__ __forceinline__ void prof_mark(int enabled, int& slot) {
+  if (enabled && threadIdx.x == 0 && slot < 64) g_nms_prof[slot] = clock64();
+  ++slot;
+}
+
 struct NmsCtaArgs {
   NmsState st;
   const float* boxes;
@@ -676,14 +713,23 @@ struct NmsCtaArgs {
   int cap_len;            // upper bound of the segment lengths (shared-memory sort capacity)
   const int* seg_counts;  // optional: segment s = rows [s * seg_stride, s * seg_stride + min(seg_counts[s], seg_stride))
   int seg_stride;
+  int prof;
 };
 
 template <int PHASE>
 __global__ void __launch_bounds__(1024) nms_cta_kernel(NmsCtaArgs a) {
   extern __shared__ unsigned long long nms_smem[];
+  __shared__ CtaSel sel;
   uint32_t* smask = reinterpret_cast<uint32_t*>(nms_smem);
   const NmsState& st = a.st;
   const int s = blockIdx.x;
+  int ps = 0;
+  int prof_on = 0;
+  if (a.prof) {
+    const int len0 = a.seg_counts ? min(a.seg_counts[s], a.seg_stride) : st.seg_len[s];
+    prof_on = a.prof > 1000 ? (len0 > 4) : ((int)blockIdx.x == a.prof - 1);
+  }
+  prof_mark(prof_on, ps);
   if (PHASE != NMS_PH_RESOLVE_LOOP) {
     if (threadIdx.x == 0) {
       if (a.seg_counts) {
@@ -697,27 +743,50 @@ __global__ void __launch_bounds__(1024) nms_cta_kernel(NmsCtaArgs a) {
     }
     __syncthreads();
     cta_sort(nms_smem, st, s, a.boxes, a.row_stride, a.order_mode, a.order_col, a.cap_len);
-    const int m = cta_select(st, s, a.boxes, a.row_stride);
+    prof_mark(prof_on, ps);
+    const int m = cta_select(st, s, a.boxes, a.row_stride, &sel);
+    prof_mark(prof_on, ps);
     if (PHASE == NMS_PH_SORT_SELECT) return;
     if (m == 0) return;
-    cta_mask(smask, st, s, m, a.thr);
+    cta_mask(smask, &sel, m, a.thr);
+    prof_mark(prof_on, ps);
     const int nk = cta_resolve(smask, st, s, m);
+    prof_mark(prof_on, ps);
     cta_filter(st, s, a.boxes, a.row_stride, a.thr, nk);
+    prof_mark(prof_on, ps);
   } else {
     const int m = st.sel_cnt[s];
     if (m == 0) return;
     cta_load_mask(smask, st, s, m);
+    prof_mark(prof_on, ps);
     const int nk = cta_resolve(smask, st, s, m);
+    prof_mark(prof_on, ps);
     cta_filter(st, s, a.boxes, a.row_stride, a.thr, nk);
+    prof_mark(prof_on, ps);
   }
   // further rounds (rare: more than NMS_B candidates survive the first round's keepers) stay inside the CTA
   for (;;) {
-    const int m = cta_select(st, s, a.boxes, a.row_stride);
+    const int m = cta_select(st, s, a.boxes, a.row_stride, &sel);
+    prof_mark(prof_on, ps);
     if (m == 0) break;
-    cta_mask(smask, st, s, m, a.thr);
+    cta_mask(smask, &sel, m, a.thr);
+    prof_mark(prof_on, ps);
     const int nk = cta_resolve(smask, st, s, m);
+    prof_mark(prof_on, ps);
     cta_filter(st, s, a.boxes, a.row_stride, a.thr, nk);
+    prof_mark(prof_on, ps);
   }
+  if (prof_on && threadIdx.x == 0) g_nms_prof[63] = ps;
+}
+
+static void nms_prof_dump(const char* what, cudaStream_t st_) {
+  long long h[64];
+  cudaStreamSynchronize(st_);
+  cudaMemcpyFromSymbol(h, g_nms_prof, sizeof(h));
+  const int n = (int)std::min<long long>(h[63], 62);
+  fprintf(stderr, "[nms prof] %s:", what);
+  for (int i = 1; i < n; ++i) fprintf(stderr, " %.1f", (double)(h[i] - h[i - 1]) / 1965.0);
+  fprintf(stderr, " us\n");
 }
 
 // ------------------------------------------------------------------------------------------------ host driver
@@ -812,16 +881,21 @@ int nms_run(NmsWorkspace* ws, const float* boxes_dev, int row_stride, int n_seg,
     NmsCtaArgs a;
     a.st = st; a.boxes = boxes_dev; a.row_stride = row_stride; a.order_mode = order_mode; a.order_col = order_col; a.thr = thr;
     a.cap_len = n2; a.seg_counts = ws->seg_counts; a.seg_stride = ws->seg_stride;
+    static const int prof = getenv("FRCNN_NMS_PROF") ? atoi(getenv("FRCNN_NMS_PROF")) + 1 : 0;  // value = CTA to time
+    a.prof = prof;  // > 1000: every CTA that gets past the first selection (racy, last writer wins)
     ws->seg_counts = nullptr;
     if (ws->fused) {
       nms_cta_kernel<NMS_PH_FUSED><<<n_seg, 1024, std::max(mask_bytes, n2 * 8), st_>>>(a);
       FRCNN_CUDA_TRY(cudaGetLastError());
+      if (prof) nms_prof_dump("fused sort|select|mask|resolve|filter|select...", st_);
       return 1;
     }
     nms_cta_kernel<NMS_PH_SORT_SELECT><<<n_seg, 1024, n2 * 8, st_>>>(a);
+    if (prof) nms_prof_dump("phase0 sort|select", st_);
     nms_mask_kernel<<<dim3(NMS_B * NMS_ROW_WORDS / 256, n_seg), 256, 0, st_>>>(st, thr);
     nms_cta_kernel<NMS_PH_RESOLVE_LOOP><<<n_seg, 1024, mask_bytes, st_>>>(a);
     FRCNN_CUDA_TRY(cudaGetLastError());
+    if (prof) nms_prof_dump("phase1 load_mask|resolve|filter|select|mask|resolve|filter|select...", st_);
     return 3;
   } else {
     FRCNN_REQUIRE(n_seg <= 256, FRCNN_E_INVALID, "nms: at most 256 segments in the large-N path");

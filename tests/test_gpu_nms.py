@@ -85,6 +85,25 @@ def test_special_values(F):
     assert len(got) > 0 and len(want) > 0
 
 
+def test_zero_intersection_paths(F):
+    """Disjoint pairs never reach the divider in the kernels: the comparison result of +0 / d is derived instead.
+    Zero-area pairs (0 / 0 = NaN -> dropped), negative areas, and thresholds <= 0 must match the dividing oracle."""
+    rng = np.random.default_rng(21)
+    b = OB.sweep_boxes(1500, seed=21)
+    z = rng.choice(1500, 200, replace=False)
+    b[z[:100], 2] = b[z[:100], 0] - 1       # width 0: area 0, every intersection 0
+    b[z[100:150], 3] = b[z[100:150], 1] - 3  # negative height: negative area
+    b[z[150:], :] = b[z[150], :]             # exact duplicates of one box
+    for thr in (0.25, 0.0, -0.5, 1.5):
+        for arg, mode in ((None, 0), ("area", 1)):
+            assert np.array_equal(F.nms(b, thr, arg), nms_c.nms(b, thr, mode, 0)), (thr, mode)
+    zero = np.zeros((300, 4), np.float32)
+    zero[:, 2:] = -1                          # all areas 0, all sums of areas 0: every test is 0 / 0
+    zero[:, 3] -= np.arange(300)
+    zero[:, 1] = zero[:, 3] + 1
+    assert np.array_equal(F.nms(zero, 0.25), nms_c.nms(zero, 0.25))
+
+
 @pytest.mark.parametrize("n,n_seg", [(4000, 21), (50, 21), (64000, 21), (300000, 21)])
 def test_segmented(F, n, n_seg):
     b = OB.sweep_boxes(n, seed=7)
