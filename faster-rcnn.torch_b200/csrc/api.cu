@@ -155,6 +155,8 @@ struct frcnn_ctx {
   cudaGraphExec_t graph_exec = nullptr;
   struct GraphKey { const float* img; int N, H, W; double thr_fg, thr_class; float thr_nms1, thr_nms2; long gen; } graph_key = {};
   GraphKey eager_key = {};     // key of the last eager run (a config is captured on its second use)
+  bool det_pending = false;    // frcnn_detect_begin without its frcnn_detect_end yet
+  int det_pending_n = 0;
   long weights_gen = 0;        // bumped by frcnn_pack_weights: invalidates the cached dgrad weight layouts
   long ws_gen = 0;             // bumped whenever a workspace pointer baked into the graph may have changed
   int64_t launches_per_detect = 0;
@@ -1224,9 +1226,11 @@ static void enqueue_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int
   FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_det, c->det_dev, (size_t)spec * sizeof(frcnn_detection), cudaMemcpyDeviceToHost, st));
 }
 
-static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, frcnn_detection* det_host, int cap, int* n_det) {
+// First half of a detection: the whole launch sequence (graph replay from the third use of a configuration) goes onto
+// the context's stream; nothing waits.  do_detect_finish is the second half.
+static void do_detect_enqueue(frcnn_ctx* c, const float* img_dev, int N, int H, int W) {
   FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called before detect");
-  FRCNN_REQUIRE(det_host != nullptr && n_det != nullptr && cap >= 0, FRCNN_E_INVALID, "bad output buffer");
+  FRCNN_REQUIRE(!c->det_pending, FRCNN_E_STATE, "a detection is already in flight on this context (frcnn_detect_end it first)");
   ensure_pnet_workspace(c, N, H, W);
   ensure_det_workspace(c, N, 0);
   cudaStream_t st = c->stream;
@@ -1278,6 +1282,17 @@ static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, f
     enqueue_detect(c, img_dev, N, H, W);
     c->eager_key = {img_dev, N, H, W, c->thr_fg, c->thr_class, c->thr_nms1, c->thr_nms2, c->ws_gen};
   }
+  c->det_pending = true;
+  c->det_pending_n = N;
+}
+
+static void do_detect_finish(frcnn_ctx* c, frcnn_detection* det_host, int cap, int* n_det) {
+  FRCNN_REQUIRE(det_host != nullptr && n_det != nullptr && cap >= 0, FRCNN_E_INVALID, "bad output buffer");
+  FRCNN_REQUIRE(c->det_pending, FRCNN_E_STATE, "no detection in flight on this context");
+  cudaStream_t st = c->stream;
+  const bool prof = c->profiling;
+  const int N = c->det_pending_n;
+  c->det_pending = false;
   FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
   const int overflow = c->h_ints[0], degenerate = c->h_ints[1], roi_total = c->h_ints[2], ndet = c->h_ints[3];
   if (overflow || degenerate) FRCNN_CUDA_TRY(cudaMemsetAsync(c->flags, 0, 2 * sizeof(int), st));
@@ -1307,6 +1322,43 @@ static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, f
   if (ncopy > 0) memcpy(det_host, c->h_det, (size_t)ncopy * sizeof(frcnn_detection));
   *n_det = ncopy;
   FRCNN_REQUIRE(ndet <= cap, FRCNN_E_OVERFLOW, "more winners than the output capacity");
+}
+
+static void do_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W, frcnn_detection* det_host, int cap, int* n_det) {
+  FRCNN_REQUIRE(det_host != nullptr && n_det != nullptr && cap >= 0, FRCNN_E_INVALID, "bad output buffer");
+  do_detect_enqueue(c, img_dev, N, H, W);
+  do_detect_finish(c, det_host, cap, n_det);
+}
+
+// Input:cuda() (Detector.lua:32) into the context's staging frame buffer, asynchronously on the context's stream.
+// A page-locked caller buffer is DMA'd directly; pageable memory is staged through the context's pinned buffer so
+// that the copy is a true asynchronous DMA either way; a device buffer is copied device to device (the staging
+// buffer keeps the captured graph's input pointer constant whatever frame the caller passes).
+static const float* stage_frames(frcnn_ctx* c, const float* img, bool on_device, int n, int h, int w) {
+  const size_t bytes = (size_t)n * 3 * h * w * sizeof(float);
+  if (bytes > c->d_img_bytes) {
+    FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->d_img) cudaFree(c->d_img);
+    if (c->h_img) cudaFreeHost(c->h_img);
+    c->d_img = nullptr; c->h_img = nullptr; c->d_img_bytes = 0;
+    FRCNN_CUDA_TRY(cudaMalloc(&c->d_img, bytes));
+    FRCNN_CUDA_TRY(cudaMallocHost(&c->h_img, bytes));
+    c->d_img_bytes = bytes;
+  }
+  if (on_device) {
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_img, img, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return c->d_img;
+  }
+  cudaPointerAttributes attr;
+  const bool pinned = cudaPointerGetAttributes(&attr, img) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  if (pinned) {
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_img, img, bytes, cudaMemcpyHostToDevice, c->stream));
+  } else {
+    memcpy(c->h_img, img, bytes);
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_img, c->h_img, bytes, cudaMemcpyHostToDevice, c->stream));
+  }
+  return c->d_img;
 }
 
 }  // namespace frcnn
@@ -1869,28 +1921,23 @@ int frcnn_detect_dev(frcnn_ctx* c, const float* img_dev, int n, int h, int w, fr
 int frcnn_detect(frcnn_ctx* c, const float* img_host, int n, int h, int w, frcnn_detection* det_host, int cap, int* n_det) {
   API_BEGIN(c)
   FRCNN_REQUIRE(img_host != nullptr && n >= 1 && h >= 1 && w >= 1, FRCNN_E_INVALID, "null image");
-  const size_t bytes = (size_t)n * 3 * h * w * sizeof(float);
-  if (bytes > c->d_img_bytes) {
-    FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (c->d_img) cudaFree(c->d_img);
-    if (c->h_img) cudaFreeHost(c->h_img);
-    c->d_img = nullptr; c->h_img = nullptr; c->d_img_bytes = 0;
-    FRCNN_CUDA_TRY(cudaMalloc(&c->d_img, bytes));
-    FRCNN_CUDA_TRY(cudaMallocHost(&c->h_img, bytes));
-    c->d_img_bytes = bytes;
-  }
-  // Input:cuda() (Detector.lua:32).  A page-locked caller buffer is DMA'd directly; pageable memory is staged
-  // through the ctx's pinned buffer so that the copy is a true asynchronous DMA either way.
-  cudaPointerAttributes attr;
-  const bool pinned = cudaPointerGetAttributes(&attr, img_host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-  cudaGetLastError();
-  if (pinned) {
-    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_img, img_host, bytes, cudaMemcpyHostToDevice, c->stream));
-  } else {
-    memcpy(c->h_img, img_host, bytes);
-    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_img, c->h_img, bytes, cudaMemcpyHostToDevice, c->stream));
-  }
-  frcnn::do_detect(c, c->d_img, n, h, w, det_host, cap, n_det);
+  const float* img_dev = frcnn::stage_frames(c, img_host, false, n, h, w);
+  frcnn::do_detect(c, img_dev, n, h, w, det_host, cap, n_det);
+  API_END(c)
+}
+
+int frcnn_detect_begin(frcnn_ctx* c, const float* img, int img_on_device, int n, int h, int w) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(img != nullptr && n >= 1 && h >= 1 && w >= 1, FRCNN_E_INVALID, "null image");
+  FRCNN_REQUIRE(!c->det_pending, FRCNN_E_STATE, "a detection is already in flight on this context (frcnn_detect_end it first)");
+  const float* img_dev = frcnn::stage_frames(c, img, img_on_device != 0, n, h, w);
+  frcnn::do_detect_enqueue(c, img_dev, n, h, w);
+  API_END(c)
+}
+
+int frcnn_detect_end(frcnn_ctx* c, frcnn_detection* det_host, int cap, int* n_det) {
+  API_BEGIN(c)
+  frcnn::do_detect_finish(c, det_host, cap, n_det);
   API_END(c)
 }
 
@@ -2014,7 +2061,7 @@ int frcnn_conv_bf16(frcnn_ctx* c, const uint16_t* x_dev, const float* w_dev, con
   REQUIRE_DEVICE(c);
   FRCNN_REQUIRE(x_dev && w_dev && out_dev, FRCNN_E_INVALID, "null argument");
   FRCNN_REQUIRE(bn == 0 || bn == 64 || bn == 128 || bn == 192 || bn == 256, FRCNN_E_INVALID, "bn must be 0, 64, 128, 192 or 256");
-  FRCNN_REQUIRE(mt >= 0 && mt <= 2 && !(pool && splits > 1), FRCNN_E_INVALID, "bad mt / pool");
+  FRCNN_REQUIRE(((mt >= 0 && mt <= 2) || mt == 11 || mt == 12) && !(pool && splits > 1), FRCNN_E_INVALID, "bad mt / pool");
   const int ho = h + 2 * pad - k + 1, wo = w + 2 * pad - k + 1;
   FRCNN_REQUIRE(ho > 0 && wo > 0, FRCNN_E_INVALID, "input smaller than the kernel");
   const size_t wbytes = ((size_t)cout * cin * k * k * sizeof(frcnn::bf16) + 255) & ~size_t(255);

@@ -77,6 +77,12 @@ struct ConvParams {
   int wgrad, co_tiles, wchunks;
   const float* img;         // first-layer kernel only: [N][Cimg][Hin][Win] fp32 input frames (Torch layout)
   int Cimg;                 // first-layer kernel only: image channels (3); K = Cimg * KH * KW <= 32
+  // halo-tile kernel (conv_halo_kernel): the A operand of ALL filter taps of one 64-channel chunk is ONE TMA box
+  // {64 ch, BW + KW - 1, BH * MT + KH - 1} = the CTA tile plus its halo; tap (kh, kw) is a row offset of the UMMA
+  // descriptor into that box.  BW = 8 (one 8-row descriptor group per tile row), BH = 16.
+  int halo;                 // 1: launched with conv_halo_kernel
+  int halo_desc;            // descriptor base-offset mode for the row-shifted start address (0: field left 0)
+  int dbg;                  // FRCNN_CONV_DBG (measurement only): 1 skip the global stores, 2 skip the epilogue body, 4 skip the MMAs
 };
 
 struct TensorMapCache;

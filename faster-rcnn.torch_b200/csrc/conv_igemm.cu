@@ -28,6 +28,9 @@
 // conv_first_kernel: the 3-channel first layer.  Same MMA / epilogue, but the A operand (K = 27 padded to 32) is
 // built in shared memory by four producer warps straight from the fp32 NCHW frame -- no im2col buffer in HBM.
 #include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -127,7 +130,7 @@ __device__ __forceinline__ bool next_unit(const ConvGroup& grp, const GroupSched
 // pixel) and the chunk-wise reads (8 lanes = one 128-byte pixel segment) are bank-conflict free.  Output leaves
 // the SM as fully coalesced 128-byte segments written with plain 16-byte st.global by all 256 threads.
 static constexpr int EPI_THREADS = 256;
-template <int BN, int MT>
+template <int BN, int MT, int ACC = 2>
 __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtensorMap* tmOuts, uint8_t* tile_buf,
                                               const float* sbias, uint32_t tmem_base, uint64_t* tmem_full,
                                               uint64_t* tmem_empty, const GroupSched& sc, int ewarp, int lane) {
@@ -141,13 +144,13 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
   const uint32_t my_row_addr = tile_addr + row * 128;
   const int sw = row & 7;
   const int total_units = grp.unit_end[grp.n - 1];
-  int seq = 0;  // index of the unit in this CTA's sequence of live units: accumulator stage = seq & 1
+  int seq = 0;  // index of the unit in this CTA's sequence of live units: accumulator stage = seq & 1 (ACC = 2)
   for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
     int gi;
     TileCoord t;
     if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
-    const int acc = seq & 1;
-    const uint32_t acc_phase = (uint32_t)(seq >> 1) & 1u;
+    const int acc = ACC == 2 ? (seq & 1) : 0;
+    const uint32_t acc_phase = (uint32_t)(ACC == 2 ? (seq >> 1) : seq) & 1u;
     ++seq;
     const ConvParams& p = grp.p[gi];
     const CUtensorMap* tmOut = tmOuts + gi;
@@ -160,7 +163,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
     ptx::mbar_wait(&tmem_full[acc], acc_phase);
     ptx::tc_fence_after();
 #pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
+    for (int mt = 0; mt < ((p.dbg & 2) ? 0 : MT); ++mt) {
       const int hbase = t.h0 + mt * p.BH;
       const int h = hbase + dy, w = t.w0 + dx;
       const bool valid = (h < p.Hout) && (w < p.Wout);
@@ -246,7 +249,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
           for (int c = 0; c < 4; ++c)
             ptx::st_shared_v4(my_row_addr + (((half * 4 + c) ^ sw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
           ptx::named_bar_sync(1, EPI_THREADS);
-          if (cbase < p.Cout) {
+          if (cbase < p.Cout && !(p.dbg & 1)) {
             if (p.mode == EPI_POOL) {
               // 2x2 stride-2 ceil-mode max pool: 32 pooled pixels x 8 chunks, one per thread, straight to HBM
               const int pw_shift = p.bw_shift - 1;  // pooled tile width BW / 2
@@ -456,8 +459,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
               for (int mt = 0; mt < MT; ++mt) {
                 // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field; the second
                 // 128-row sub-tile starts 16 KB further
-                ptx::mma_bf16_ss(d_tmem + mt * BN, da + 2 * j + mt * (A_SUB_BYTES >> 4), db + 2 * j, IDESC,
-                                 (k > t.k_begin || j > 0) ? 1u : 0u);
+                if (!(grp.p[gi].dbg & 4))
+                  ptx::mma_bf16_ss(d_tmem + mt * BN, da + 2 * j + mt * (A_SUB_BYTES >> 4), db + 2 * j, IDESC,
+                                   (k > t.k_begin || j > 0) ? 1u : 0u);
               }
             }
           }
@@ -476,6 +480,203 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     }
   } else if (warp >= 4) {
     epilogue_loop<BN, MT>(grp, maps.o, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 4, lane);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- halo kernel
+// The k x k convolutions of the trunk re-read every activation k*k times when each filter tap is its own TMA box
+// (conv_igemm_kernel): at 800x450 the block-2 layers then move 9 x 23 MB = 207 MB of A operand L2 -> SM per launch
+// and run at the L2 bandwidth, not at the tensor pipe.  Here the CTA tile (8 wide x 16*MT tall) is loaded ONCE per
+// 64-channel chunk together with its halo -- one TMA box {64 ch, 8 + KW - 1, 16*MT + KH - 1}, 1.33x the tile instead
+// of 9x -- and filter tap (kh, kw) of sub-tile mt is just a UMMA descriptor whose start address is moved by
+// ((mt*16 + kh) * pitch + kw) rows of 128 bytes into that box: with a tile width of 8 pixels every 8-row group of
+// the M = 128 operand is one tile row, so the group stride (SBO) is the halo pitch and the canonical K-major
+// 128-byte-swizzle layout holds for every tap (the swizzle is a function of the absolute shared-memory address, the
+// box starts on a 1024-byte boundary).  Weights stream through their own ring, one {64 x BN} box per (chunk, tap).
+// Same warp roles and the same epilogue as conv_igemm_kernel; BN x MT = 512 columns run with ONE accumulator stage.
+static constexpr int HALO_BW = 8, HALO_BH = 16, HALO_MAXK = 3;
+__host__ __device__ constexpr int halo_a_slot(int MT) {
+  return (((HALO_BH * MT + HALO_MAXK - 1) * (HALO_BW + HALO_MAXK - 1) * 128) + 1023) & ~1023;
+}
+__host__ __device__ constexpr int halo_a_slots(int MT) { return MT == 2 ? 2 : 3; }
+__host__ __device__ constexpr int halo_b_slots(int BN, int MT) {
+  return (SMEM_LIMIT - SMEM_FIXED - halo_a_slots(MT) * halo_a_slot(MT)) / (BN * 128) > 8
+             ? 8
+             : (SMEM_LIMIT - SMEM_FIXED - halo_a_slots(MT) * halo_a_slot(MT)) / (BN * 128);
+}
+__host__ __device__ constexpr int halo_acc_stages(int BN, int MT) { return 2 * BN * MT <= 512 ? 2 : 1; }
+__host__ __device__ constexpr int halo_tmem_cols(int BN, int MT) {
+  return halo_acc_stages(BN, MT) * BN * MT <= 128 ? 128 : (halo_acc_stages(BN, MT) * BN * MT <= 256 ? 256 : 512);
+}
+static int halo_smem_bytes(int BN, int MT) {
+  return halo_a_slots(MT) * halo_a_slot(MT) + halo_b_slots(BN, MT) * BN * 128 + SMEM_FIXED;
+}
+
+template <int BN, int MT>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+    conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGroup grp) {
+  constexpr int A_SLOT = halo_a_slot(MT), A_SLOTS = halo_a_slots(MT);
+  constexpr int B_SLOT = BN * 128, B_SLOTS = halo_b_slots(BN, MT);
+  constexpr int ACC = halo_acc_stages(BN, MT);
+  constexpr int TMEM_COLS = halo_tmem_cols(BN, MT);
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BN);
+  static_assert(B_SLOTS >= 2, "weight ring too small");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + A_SLOTS * A_SLOT;
+  uint8_t* tile_buf = smem_b + B_SLOTS * B_SLOT;
+  float* sbias = reinterpret_cast<float*>(tile_buf + STAGE_TILE_BYTES);
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
+  uint64_t* empty_a = full_a + A_SLOTS;
+  uint64_t* full_b = empty_a + A_SLOTS;
+  uint64_t* empty_b = full_b + B_SLOTS;
+  uint64_t* tmem_full = empty_b + B_SLOTS;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_units = grp.unit_end[0];
+  GroupSched sc;
+  make_sched(grp, BN, sc);
+  const ConvParams& p = grp.p[0];
+  const int PW = HALO_BW + p.KW - 1;                                            // halo pitch, pixels
+  const uint32_t a_tx = (uint32_t)(PW * (HALO_BH * MT + p.KH - 1)) * 128u;      // bytes of one A box
+
+  if (warp == 0 && lane == 0) {
+    ptx::tma_prefetch_desc(&maps.a[0]);
+    ptx::tma_prefetch_desc(&maps.b[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < A_SLOTS; ++s) {
+      ptx::mbar_init(&full_a[s], 1);
+      ptx::mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < B_SLOTS; ++s) {
+      ptx::mbar_init(&full_b[s], 1);
+      ptx::mbar_init(&empty_b[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], EPI_THREADS / 32);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_base_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    // Items are issued in consumption order, except that the A box of the NEXT chunk goes out after the first
+    // `kpre` weight boxes of the current one: its slot frees when the previous chunk retires, i.e. about when the
+    // MMA warp starts on the weight boxes already in flight, so neither ring starves the other (and the order
+    // cannot deadlock: everything the MMA warp needs to retire the previous chunk was issued before).
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      const int taps = p.KH * p.KW;
+      const int kpre = min(B_SLOTS - 1, taps - 1);
+      int ua = blockIdx.x, ca = 0;  // cursor of the A ring: one chunk ahead of the weight ring
+      auto issue_a = [&]() {
+        if (ua >= total_units) return;
+        const TileCoord ta = decode_tile(p, ua, BN, 1, p.k_iters);
+        ptx::mbar_wait(&empty_a[as], aph ^ 1);
+        ptx::mbar_arrive_expect_tx(&full_a[as], a_tx);
+        ptx::tma_load_4d(smem_a + as * A_SLOT, &maps.a[0], &full_a[as], ca * BLOCK_K, ta.w0 - p.padW, ta.h0 - p.padH, ta.n_img);
+        if (++as == A_SLOTS) {
+          as = 0;
+          aph ^= 1;
+        }
+        if (++ca == p.cchunks) {
+          ca = 0;
+          ua += gridDim.x;
+        }
+      };
+      issue_a();
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        const TileCoord t = decode_tile(p, unit, BN, 1, p.k_iters);
+        for (int c = 0; c < p.cchunks; ++c) {
+          for (int tap = 0; tap < taps; ++tap) {
+            if (tap == kpre) issue_a();
+            ptx::mbar_wait(&empty_b[bs], bph ^ 1);
+            ptx::mbar_arrive_expect_tx(&full_b[bs], B_SLOT);
+            ptx::tma_load_2d(smem_b + bs * B_SLOT, &maps.b[0], &full_b[bs], (tap * p.cchunks + c) * BLOCK_K, t.n0);
+            if (++bs == B_SLOTS) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int seq = 0;
+      const uint32_t sbo = (uint32_t)PW * 128u;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        int gi;
+        TileCoord t;
+        if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+        const int acc = ACC == 2 ? (seq & 1) : 0;
+        const uint32_t acc_phase = (uint32_t)(ACC == 2 ? (seq >> 1) : seq) & 1u;
+        ++seq;
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN * MT;
+        for (int c = 0; c < p.cchunks; ++c) {
+          ptx::mbar_wait(&full_a[as], aph);
+          const uint32_t a_addr = ptx::smem_u32(smem_a + as * A_SLOT);
+          for (int kh = 0; kh < p.KH; ++kh) {
+            for (int kw = 0; kw < p.KW; ++kw) {
+              ptx::mbar_wait(&full_b[bs], bph);
+              ptx::tc_fence_after();
+              const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + bs * B_SLOT));
+              const uint32_t first = (c == 0 && kh == 0 && kw == 0) ? 0u : 1u;
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const int row0 = (mt * HALO_BH + kh) * PW + kw;  // first 128-byte row of this tap's operand
+                const uint64_t da = ptx::make_desc_k_sw128_sbo(a_addr + row0 * 128, sbo, p.halo_desc ? (uint32_t)row0 : 0u);
+#pragma unroll
+                for (int j = 0; j < BLOCK_K / 16; ++j)
+                  if (!(p.dbg & 4)) ptx::mma_bf16_ss(d_tmem + mt * BN, da + 2 * j, db + 2 * j, IDESC, j > 0 ? 1u : first);
+              }
+              ptx::mma_commit(&empty_b[bs]);
+              if (++bs == B_SLOTS) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+          }
+          ptx::mma_commit(&empty_a[as]);
+          if (++as == A_SLOTS) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+        ptx::mma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    epilogue_loop<BN, MT, ACC>(grp, maps.o, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 4, lane);
   }
 
   ptx::tc_fence_before();
@@ -878,6 +1079,52 @@ void conv_set_f32_output(ConvLaunch* L, float* ws) {
   FRCNN_REQUIRE(r == CUDA_SUCCESS, FRCNN_E_CUDA, "cuTensorMapEncodeTiled(fp32 slices) failed, CUresult " + std::to_string((int)r));
 }
 
+// Environment switches for A/B measurements: FRCNN_CONV_HALO=0 keeps every layer on the tap-per-box kernel;
+// FRCNN_HALO_DESC=1 fills the descriptor's base-offset field with the row phase of the shifted start address.
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && v[0] ? atoi(v) : dflt;
+}
+
+static bool halo_cfg_ok(int Cout, int BN, int MT) {
+  return Cout % BN == 0 && BN * MT <= 512 && (BN == 64 || BN == 128 || BN == 192 || BN == 256) && (MT == 1 || MT == 2);
+}
+
+static void conv_prepare_halo(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
+                              int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int BN, int MT) {
+  FRCNN_REQUIRE(halo_cfg_ok(Cout, BN, MT), FRCNN_E_INVALID, "conv (halo kernel): unsupported (BN, MT) for this Cout");
+  L->BN = BN;
+  L->first = false;
+  L->w_first = nullptr;
+  ConvParams& p = L->p;
+  p = ConvParams();
+  p.N = N; p.Hin = Hin; p.Win = Win; p.Cin = Cin;
+  p.Hout = Hin + 2 * padH - KH + 1;
+  p.Wout = Win + 2 * padW - KW + 1;
+  FRCNN_REQUIRE(p.Hout > 0 && p.Wout > 0, FRCNN_E_INVALID, "conv: input smaller than the kernel");
+  p.Cout = Cout; p.KH = KH; p.KW = KW; p.padH = padH; p.padW = padW;
+  p.MT = MT;
+  p.BW = HALO_BW; p.BH = HALO_BH; p.bw_shift = 3;
+  p.tiles_w = (p.Wout + p.BW - 1) / p.BW;
+  p.tiles_h = (p.Hout + p.BH * MT - 1) / (p.BH * MT);
+  p.n_tiles_m = N * p.tiles_h * p.tiles_w;
+  p.n_tiles_n = Cout / BN;
+  p.cchunks = Cin / 64;
+  p.k_iters = KH * KW * p.cchunks;
+  p.splits = 1;
+  p.k_per_split = p.k_iters;
+  p.mode = mode;
+  p.scale = 1.0f;
+  p.halo = 1;
+  p.halo_desc = env_int("FRCNN_HALO_DESC", 0);
+  p.dbg = env_int("FRCNN_CONV_DBG", 0);
+  make_tmap_act(&L->tmA, in, N, Hin, Win, Cin, HALO_BW + KW - 1, HALO_BH * MT + KH - 1);
+  make_tmap_weight(&L->tmB, w_packed, Cout, KH * KW * Cin, BN);
+  make_out_map(L, out);
+  const int total = p.n_tiles_m * p.n_tiles_n;
+  L->grid = total < num_sms ? total : num_sms;
+}
+
 void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
                   int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int force_splits, int force_bn,
                   int force_mt) {
@@ -886,6 +1133,43 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
   FRCNN_REQUIRE(f32 ? Cout % 32 == 0 : (Cout % 64 == 0 && Cout <= MAX_BIAS), FRCNN_E_INVALID,
                 "conv: Cout must be a multiple of 64 (<= 512) for the bf16 epilogues, of 32 for split-K");
   FRCNN_REQUIRE(f32 || out != nullptr, FRCNN_E_INVALID, "conv: null output");
+  // halo-tile kernel: k x k (k = 2, 3) filters with a bf16 epilogue.  force_mt: 0 = automatic, 1 / 2 = tap-per-box
+  // kernel with that MT, 11 / 12 = halo kernel with MT 1 / 2
+  {
+    const bool eligible = !f32 && KH <= HALO_MAXK && KW <= HALO_MAXK && KH * KW > 1 && Cout % 64 == 0;
+    const bool forced = force_mt >= 10;
+    FRCNN_REQUIRE(!forced || eligible, FRCNN_E_INVALID, "conv: the halo kernel needs 2x2..3x3 filters and a bf16 epilogue");
+    if (eligible && (forced || (force_mt == 0 && env_int("FRCNN_CONV_HALO", 1)))) {
+      // Measured on B200 (tools/bench_conv_layers.py sweep, profiles/r1_conv_sweep.md): the halo kernel wins where the
+      // N tile is wide (BN >= 192: the M128 x N128 MMA is bound by shared-memory operand bandwidth whichever way its A
+      // operand arrives, and the tap-per-box kernel is as fast there); with BN = 256 two accumulator stages (MT = 1)
+      // beat the larger tile as soon as there are two waves of units, with BN = 192 the 256-pixel tile (one stage of
+      // 384 columns) wins from two waves on.
+      int bn = 0, mt = 0;
+      const int Ho = Hin + 2 * padH - KH + 1, Wo = Win + 2 * padW - KW + 1;
+      auto units = [&](int cbn, int cmt) {
+        return (long)N * ((Ho + HALO_BH * cmt - 1) / (HALO_BH * cmt)) * ((Wo + HALO_BW - 1) / HALO_BW) * (Cout / cbn);
+      };
+      if (forced) {
+        mt = force_mt - 10;
+        bn = force_bn > 0 ? force_bn : (Cout % 256 == 0 ? 256 : (Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : 64)));
+        if (!halo_cfg_ok(Cout, bn, mt)) bn = 0;
+      } else if (force_bn == 0 || force_bn >= 192) {
+        if ((force_bn == 0 || force_bn == 256) && Cout % 256 == 0) {
+          bn = 256;
+          mt = units(256, 1) >= 2L * num_sms ? 1 : 2;
+        } else if ((force_bn == 0 || force_bn == 192) && Cout % 192 == 0) {
+          bn = 192;
+          mt = units(192, 2) >= 2L * num_sms ? 2 : 1;
+        }
+      }
+      if (bn) {
+        conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, bn, mt);
+        return;
+      }
+      FRCNN_REQUIRE(!forced, FRCNN_E_INVALID, "conv: no halo-kernel tile for this (Cout, bn, mt)");
+    }
+  }
   // the widest tile dividing Cout wins even when it leaves SMs idle (measured at batch 1, conv4_x: 100 CTAs of BN=192
   // take 20/26 us, 135 CTAs of BN=128 take 34/46 us -- operand traffic per MAC, not occupancy, bounds these layers)
   const int BN = force_bn > 0 ? force_bn : choose_bn(Cout);
@@ -922,6 +1206,7 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
   if (splits > p.k_iters) splits = p.k_iters;
   p.k_per_split = (p.k_iters + splits - 1) / splits;
   p.splits = (p.k_iters + p.k_per_split - 1) / p.k_per_split;
+  p.dbg = env_int("FRCNN_CONV_DBG", 0);
   make_tmap_act(&L->tmA, in, N, Hin, Win, Cin, p.BW, p.BH * MT);
   make_tmap_weight(&L->tmB, w_packed, Cout, KH * KW * Cin, BN);
   make_out_map(L, out);
@@ -1023,6 +1308,32 @@ static void launch_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cud
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
+template <int BN, int MT>
+static void launch_halo_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+  static bool configured = false;
+  const int smem = halo_smem_bytes(BN, MT);
+  if (!configured) {
+    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  conv_halo_kernel<BN, MT><<<grid, CONV_THREADS, smem, st>>>(maps, grp);
+  FRCNN_CUDA_TRY(cudaGetLastError());
+}
+
+static void launch_halo_key(int BN, int MT, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+  switch (BN * 10 + MT) {
+    case 641: launch_halo_cfg<64, 1>(maps, grp, grid, st); break;
+    case 642: launch_halo_cfg<64, 2>(maps, grp, grid, st); break;
+    case 1281: launch_halo_cfg<128, 1>(maps, grp, grid, st); break;
+    case 1282: launch_halo_cfg<128, 2>(maps, grp, grid, st); break;
+    case 1921: launch_halo_cfg<192, 1>(maps, grp, grid, st); break;
+    case 1922: launch_halo_cfg<192, 2>(maps, grp, grid, st); break;
+    case 2561: launch_halo_cfg<256, 1>(maps, grp, grid, st); break;
+    case 2562: launch_halo_cfg<256, 2>(maps, grp, grid, st); break;
+    default: throw Error{FRCNN_E_INVALID, "conv (halo kernel): unsupported (BN, MT)"};
+  }
+}
+
 static void launch_key(int BN, int MT, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
   switch (BN * 10 + MT) {
     case 641: launch_cfg<64, 1>(maps, grp, grid, st); break;
@@ -1061,7 +1372,8 @@ void conv_launch(const ConvLaunch& L, cudaStream_t st) {
     maps.b[g] = L.tmB;
     maps.o[g] = L.tmOut;
   }
-  launch_key(L.BN, L.p.MT, maps, grp, L.grid, st);
+  if (L.p.halo) launch_halo_key(L.BN, L.p.MT, maps, grp, L.grid, st);
+  else launch_key(L.BN, L.p.MT, maps, grp, L.grid, st);
 }
 
 void conv_launch_group(const ConvLaunch* const* Ls, int n, int num_sms, cudaStream_t st) {
@@ -1072,7 +1384,7 @@ void conv_launch_group(const ConvLaunch* const* Ls, int n, int num_sms, cudaStre
   int total = 0;
   for (int g = 0; g < MAX_GROUP; ++g) {
     const ConvLaunch& L = *Ls[g < n ? g : n - 1];
-    FRCNN_REQUIRE(!L.first && L.p.MT == 1 && L.BN == Ls[0]->BN, FRCNN_E_INVALID, "conv group: members must share BN, MT = 1");
+    FRCNN_REQUIRE(!L.first && !L.p.halo && L.p.MT == 1 && L.BN == Ls[0]->BN, FRCNN_E_INVALID, "conv group: members must share BN, MT = 1");
     FRCNN_REQUIRE(L.p.mode == EPI_F32_SLICES || L.p.mode == EPI_F32_REDUCE, FRCNN_E_INVALID, "conv group: fp32 epilogues only");
     grp.p[g] = L.p;
     maps.a[g] = L.tmA;

@@ -170,6 +170,20 @@ __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;             // SWIZZLE_128B
   return d;
 }
+// As make_desc_k_sw128 with an arbitrary 8-row group stride and a start address that is only 128-byte aligned (a row
+// offset into a swizzled tile whose pattern starts on a 1024-byte boundary): the halo-tile A operand of the conv
+// kernel -- rows of one 8-pixel tile row are contiguous, tile rows are `sbo_bytes` (the halo pitch) apart.
+// base_offset: bits [49,52), 0 when the swizzle pattern itself starts on a 1024-byte boundary.
+__device__ __forceinline__ uint64_t make_desc_k_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes, uint32_t base_offset) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)(base_offset & 7) << 49;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // Shared-memory matrix descriptor for an MN-major operand: the tile is [K rows][64 MN elements = 128 B]
 // (again exactly a TMA SWIZZLE_128B box); 8-row K groups 1024 B apart (SBO); consecutive 64-element MN atoms
 // `lbo_bytes` apart (LBO).

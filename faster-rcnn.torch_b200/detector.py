@@ -76,7 +76,78 @@ class Detector:
             check(ctx, lib().frcnn_detect(ctx, ffi.cast("const float*", x4.ctypes.data), n, h, w, self._out, self._cap, n_det))
         return self._winners(n_det[0])
 
+    # -- the same call in two halves (frcnn_detect_begin / frcnn_detect_end): several frames in flight ----------
+    def detect_begin(self, input):
+        """Enqueues Detector:detect for `input` (host array / CPU tensor / CUDA tensor) and returns immediately.  The
+        frame is copied into the context's staging buffer asynchronously: the detector keeps a reference to `input` until
+        detect_end."""
+        ctx = self.model.ctx
+        if torch.is_tensor(input) and input.is_cuda:
+            x = input.to(torch.float32).contiguous()
+            x4 = x if x.dim() == 4 else x.unsqueeze(0)
+            n, _, h, w = x4.shape
+            self._keep = x4
+            check(ctx, lib().frcnn_detect_begin(ctx, ffi.cast("const float*", x4.data_ptr()), 1, n, h, w))
+        else:
+            x = np.ascontiguousarray(input.numpy() if torch.is_tensor(input) else input, dtype=np.float32)
+            x4 = x if x.ndim == 4 else x[None]
+            n, _, h, w = x4.shape
+            self._keep = x4
+            check(ctx, lib().frcnn_detect_begin(ctx, ffi.cast("const float*", x4.ctypes.data), 0, n, h, w))
+
+    def detect_end(self):
+        ctx = self.model.ctx
+        n_det = ffi.new("int*")
+        check(ctx, lib().frcnn_detect_end(ctx, self._out, self._cap, n_det))
+        self._keep = None
+        return self._winners(n_det[0])
+
     def stats(self):
         s = ffi.new("int64_t[4]")
         check(self.model.ctx, lib().frcnn_detect_stats(self.model.ctx, s))
         return dict(matches=int(s[0]), candidates=int(s[1]), classified=int(s[2]), winners=int(s[3]))
+
+
+class DetectorPipeline:
+    """`in_flight` Detector replicas (one context = stream + workspaces + CUDA graph each, same parameters) behind a
+    submit / drain interface: the host loop of main.lua:198-206 over a stream of frames with several frames in
+    flight.  Winners come back in submission order and are identical to Detector:detect frame by frame."""
+
+    def __init__(self, model, in_flight=2):
+        assert in_flight >= 1
+        self.models = [model] + [model.replicate() for _ in range(in_flight - 1)]
+        self.detectors = [Detector(m) for m in self.models]
+        self._busy = [False] * in_flight
+        self._next = 0
+
+    def submit(self, frame):
+        """Enqueues `frame`; returns the winners of the frame that previously occupied the slot (submitted `in_flight`
+        calls ago), or None while the pipeline is filling."""
+        i = self._next
+        self._next = (i + 1) % len(self.detectors)
+        done = self.detectors[i].detect_end() if self._busy[i] else None
+        self.detectors[i].detect_begin(frame)
+        self._busy[i] = True
+        return done
+
+    def drain(self):
+        """Winners of every frame still in flight, oldest first."""
+        out = []
+        for k in range(len(self.detectors)):
+            i = (self._next + k) % len(self.detectors)
+            if self._busy[i]:
+                out.append(self.detectors[i].detect_end())
+                self._busy[i] = False
+        return out
+
+    def detect_many(self, frames):
+        out = []
+        for f in frames:
+            r = self.submit(f)
+            if r is not None:
+                out.append(r)
+        return out + self.drain()
+
+    def close(self):
+        for m in self.models[1:]:
+            m.close()

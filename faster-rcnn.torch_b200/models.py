@@ -47,6 +47,7 @@ class _Net:
 class Model:
     def __init__(self, cfg, layers, anchor_nets, class_layers, device=0, dropout_eval_scale=-1.0, stream=None):
         self.cfg, self.layers, self.anchor_nets, self.class_layers = cfg, layers, anchor_nets, class_layers
+        self._ctor = dict(device=device, dropout_eval_scale=dropout_eval_scale)
         self.host_only = device == -1  # plan + Localizer / Anchors geometry only; no compute entry point works
         if not self.host_only and not torch.cuda.is_available():
             # fail loudly: the product has no CPU path
@@ -125,6 +126,14 @@ class Model:
             v = torch.as_tensor(np.asarray(v) if not torch.is_tensor(v) else v, dtype=torch.float32)
             self.params[n].copy_(v.reshape(-1).to(self.device))
         self.pack_weights()
+
+    def replicate(self):
+        """A second context of the same architecture on the same device holding a copy of the current weights (own
+        stream, workspaces and CUDA graph): one more frame in flight for DetectorPipeline."""
+        r = Model(self.cfg, self.layers, self.anchor_nets, self.class_layers, **self._ctor)
+        r.weights.copy_(self.weights)
+        r.pack_weights()
+        return r
 
     def pack_weights(self):
         """Re-packs the flat fp32 weights into the tensor-core layouts; call after every change of `weights`."""

@@ -215,6 +215,15 @@ int frcnn_detect_dev(frcnn_ctx* ctx, const float* img_dev, int n, int h, int w, 
                      int* n_det);
 /* Stage statistics of the last detect call: {matches, candidates after NMS, classified (non-bg, conf>0.2),
  * winners} summed over the batch. */
+/* The same call in two halves, for a host loop that keeps several frames in flight (the loop of main.lua:198-206
+ * over a stream of frames).  frcnn_detect_begin copies the frames (img: host memory, or device memory with
+ * img_on_device != 0) into the context's staging buffer and enqueues the whole launch sequence on the context's
+ * stream without waiting; frcnn_detect_end waits for it and returns the winners exactly as frcnn_detect does.
+ * One detection may be in flight per context (FRCNN_E_STATE otherwise); contexts are independent (own stream,
+ * workspaces, CUDA graph), so K contexts holding the same parameters keep K frames in flight: the few-CTA stages of
+ * one frame (NMS, finalize) then overlap the convolutions of the next.  Results are identical to frcnn_detect. */
+int frcnn_detect_begin(frcnn_ctx* ctx, const float* img, int img_on_device, int n, int h, int w);
+int frcnn_detect_end(frcnn_ctx* ctx, frcnn_detection* det_host, int cap, int* n_det);
 int frcnn_detect_stats(const frcnn_ctx* ctx, int64_t stats[4]);
 /* Thresholds of Detector.lua:54,81,115,133; defaults 0.95, 0.25, 0.2, 0.1. */
 int frcnn_set_detect_thresholds(frcnn_ctx* ctx, double fg_prob, float nms_proposals, double class_prob,
@@ -237,7 +246,7 @@ int frcnn_last_conv_profile(const frcnn_ctx* ctx, float* ms, double* flops, int*
  * x_dev: [n][h][w][cin]; w_dev: fp32 Torch layout [cout][cin][k][k]; out_dev: [n][ho][wo][cout] bf16, or with
  * pool != 0 the 2x2 stride-2 ceil-mode max-pooled map [n][ceil(ho/2)][ceil(wo/2)][cout] (model_utilities.lua:23).
  * splits > 1 exercises the split-K fp32-atomic path; bn in {0 (auto), 64, 128, 192, 256}; mt in {0 (auto), 1, 2} =
- * 128-row sub-tiles per CTA.  elapsed_ms (optional) receives the device time of `iters` back-to-back launches of
+ * 128-row sub-tiles per CTA of the tap-per-box kernel, 11 / 12 = the halo-tile kernel with 1 / 2 sub-tiles.  elapsed_ms (optional) receives the device time of `iters` back-to-back launches of
  * the conv kernel alone. */
 int frcnn_conv_bf16(frcnn_ctx* ctx, const uint16_t* x_dev, const float* w_dev, const float* bias_dev,
                     const float* prelu_dev, float scale, int n, int h, int w, int cin, int cout, int k, int pad,

@@ -89,6 +89,28 @@ def test_conv_two_subtiles_per_cta(F, small_model, case, pool):
 
 
 @pytest.mark.parametrize("pool", [False, True])
+@pytest.mark.parametrize("mt", [11, 12])
+@pytest.mark.parametrize("case,bn", [
+    ((1, 16, 16, 64, 64, 3, 1), 0), ((1, 29, 51, 128, 128, 3, 1), 128), ((2, 57, 100, 128, 256, 3, 1), 256),
+    ((1, 57, 99, 256, 384, 3, 1), 192), ((1, 57, 99, 256, 384, 3, 1), 128), ((1, 45, 77, 64, 128, 3, 1), 64),
+    ((1, 33, 20, 128, 256, 3, 0), 0), ((1, 40, 41, 64, 64, 2, 0), 0), ((4, 113, 200, 128, 256, 3, 1), 0),
+])
+def test_conv_halo_kernel(F, small_model, case, bn, mt, pool):
+    """conv_halo_kernel (mt = 11 / 12 forces it with 1 / 2 sub-tiles): the CTA tile + halo is ONE TMA box per 64-channel
+    chunk and every filter tap is a row-shifted UMMA descriptor into it.  Covers every tile width, the single-accumulator
+    configuration (bn 256 x 2 sub-tiles), several units per persistent CTA (ring phase wrap), odd map sizes, pad 0."""
+    _conv_case(F, small_model, *case, seed=sum(case) + mt, bn=bn, mt=mt, pool=pool)
+
+
+def test_conv_halo_equals_tap_kernel(F, small_model):
+    """Both kernels accumulate the same products in fp32 in the same (chunk-major vs tap-major) grouping only up to
+    fp32 rounding: outputs agree to one bf16 ulp, and exactly on small-integer data."""
+    a, _ = _conv_case(F, small_model, 1, 57, 100, 128, 256, 3, 1, seed=5, mt=1)
+    b, _ = _conv_case(F, small_model, 1, 57, 100, 128, 256, 3, 1, seed=5, mt=12)
+    assert (a - b).abs().max().item() <= 2.0 ** -7 * a.abs().max().item()
+
+
+@pytest.mark.parametrize("pool", [False, True])
 @pytest.mark.parametrize("n,h,w", [(1, 16, 16), (1, 450, 800), (2, 123, 77), (1, 61, 96)])
 def test_conv_first_layer(F, small_model, n, h, w, pool):
     """The fused first layer (in-kernel im2col of the fp32 NCHW frame, K = 27) against conv2d on bf16-rounded
@@ -117,7 +139,8 @@ def test_conv_first_layer(F, small_model, n, h, w, pool):
     assert bool((err <= tol).all()), "max err %g at ref max %g" % (err.max(), ref.abs().max())
 
 
-def test_conv_exact_integers(F, small_model):
+@pytest.mark.parametrize("mt", [1, 11, 12])
+def test_conv_exact_integers(F, small_model, mt):
     """Small-integer operands are exact in bf16 and in fp32 accumulation: the result must be bit-identical to the
     reference convolution -- catches any tap / channel / swizzle mis-addressing that tolerances could hide."""
     g = torch.Generator().manual_seed(1)
@@ -132,7 +155,7 @@ def test_conv_exact_integers(F, small_model):
     wd, bd = wt.cuda(), bias.cuda()
     ffi, L = F.ffi, F.lib()
     rc = L.frcnn_conv_bf16(small_model.ctx, ffi.cast("const uint16_t*", x_nhwc.data_ptr()), ffi.cast("const float*", wd.data_ptr()),
-                           ffi.cast("const float*", bd.data_ptr()), ffi.NULL, 1.0, n, h, w, cin, cout, k, pad, 0, 0, 0, 0,
+                           ffi.cast("const float*", bd.data_ptr()), ffi.NULL, 1.0, n, h, w, cin, cout, k, pad, 0, 0, mt, 0,
                            ffi.cast("uint16_t*", out.data_ptr()), 1, ffi.NULL)
     assert rc == 0
     got = out.float().cpu().permute(0, 3, 1, 2)

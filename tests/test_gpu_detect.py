@@ -138,3 +138,42 @@ def test_detect_graph_replay_matches_eager(F, det_model):
         assert all(float(np.exp(x["confidence"])) > 0.5 for x in strict)
     finally:
         L.frcnn_set_detect_thresholds(det_model.ctx, 0.95, 0.25, 0.2, 0.1)
+
+
+@pytest.mark.parametrize("in_flight,host", [(2, True), (3, False)])
+def test_detect_pipeline_matches_sequential(F, det_model, in_flight, host):
+    """frcnn_detect_begin / frcnn_detect_end with several frames in flight (one context per frame, the few-CTA stages of
+    one frame overlapping the convolutions of the next) returns, in submission order, what Detector:detect returns
+    frame by frame.  The stage counters (matches, NMS survivors) are bit-exact; winners to the stated 90 % bar (cnet
+    split-K summation order is not reproducible)."""
+    det = F.Detector(det_model)
+    frames = [OM.synthetic_frame(122, 192, seed=s) for s in range(2, 11)]
+    seq, seq_stats = [], []
+    for f in frames:
+        seq.append([_key(x) for x in det.detect(f.cuda())])
+        seq_stats.append(det.stats())
+    pipe = F.DetectorPipeline(det_model, in_flight=in_flight)
+    try:
+        got = pipe.detect_many([f.numpy() if host else f.cuda() for f in frames])
+        assert len(got) == len(frames)
+        for g, s in zip(got, seq):
+            g = [_key(x) for x in g]
+            assert len(set(g) & set(s)) >= 0.9 * max(len(g), len(s), 1)
+        # a second pass replays every context's captured graph
+        again = pipe.detect_many([f.cuda() for f in frames])
+        for g, s in zip(again, seq):
+            g = [_key(x) for x in g]
+            assert len(set(g) & set(s)) >= 0.9 * max(len(g), len(s), 1)
+        # one detection in flight per context
+        pipe.detectors[0].detect_begin(frames[0].cuda())
+        with pytest.raises(F.FrcnnError) as e:
+            pipe.detectors[0].detect_begin(frames[1].cuda())
+        assert e.value.code == 4
+        first = [_key(x) for x in pipe.detectors[0].detect_end()]
+        assert len(set(first) & set(seq[0])) >= 0.9 * max(len(first), len(seq[0]), 1)
+        assert pipe.detectors[0].stats()["matches"] == seq_stats[0]["matches"]
+        assert pipe.detectors[0].stats()["candidates"] == seq_stats[0]["candidates"]
+        with pytest.raises(F.FrcnnError):
+            pipe.detectors[0].detect_end()
+    finally:
+        pipe.close()
