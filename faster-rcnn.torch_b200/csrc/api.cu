@@ -51,6 +51,7 @@ struct Head {
   int p_w2, p_b2;
   float* acc = nullptr;      // [splits * N][hh][hw][n] fp32 split-K slices
   float* out = nullptr;      // [N][18][hh][hw] fp32
+  ConvLaunch fused;          // throughput schedule: k x k conv + tail in one unsplit halo-kernel unit (EPI_HEAD)
   int hh = 0, hw = 0;
   bf16* dpre = nullptr;      // training: [N][hh][hw][n] gradient wrt the k x k conv's pre-activation output
 };
@@ -152,6 +153,7 @@ struct frcnn_ctx {
   bool own_stream = false;
   // CUDA graph of the detect pipeline (replayed while image pointer / shape / thresholds stay the same)
   bool graph_enabled = true;
+  int schedule = FRCNN_SCHED_LATENCY;  // frcnn_set_schedule
   cudaGraphExec_t graph_exec = nullptr;
   struct GraphKey { const float* img; int N, H, W; double thr_fg, thr_class; float thr_nms1, thr_nms2; long gen; } graph_key = {};
   GraphKey eager_key = {};     // key of the last eager run (a config is captured on its second use)
@@ -555,6 +557,7 @@ static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
     hd.acc = (float*)dev_alloc(c->ws_allocs, slices * hd.hh * hd.hw * hd.n * sizeof(float));
     hd.out = (float*)dev_alloc(c->ws_allocs, (size_t)N * 18 * hd.hh * hd.hw * sizeof(float));
     conv_set_f32_output(&hd.conv.launch, hd.acc);
+    conv_prepare_head(&hd.fused, c->pool_out[hd.input - 1], hd.conv.w_packed, N, ih, iw, hd.conv.cin, hd.kW, c->sm_count);
   }
   c->ws_n = N; c->ws_h = H; c->ws_w = W;
 }
@@ -650,9 +653,38 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
       run_conv(c, cv);
     }
   }
-  // anchor heads (model_utilities.lua:29-35,51-54): one grouped split-K conv launch, heaviest units first, then one
-  // grouped tail launch
-  {
+  // anchor heads (model_utilities.lua:29-35,51-54).  Throughput schedule (several frames in flight, evaluate mode):
+  // ONE launch of unsplit units, k x k conv and tail fused -- the least SM time per frame, the machine is filled by
+  // the other frames.  Latency schedule: one grouped split-K conv launch (every SM busy on this frame), heaviest
+  // units first, then one grouped tail launch.
+  if (c->schedule == FRCNN_SCHED_THROUGHPUT && !train) {
+    std::vector<const ConvLaunch*> order;
+    for (auto& hd : c->heads) {
+      ConvParams& p = hd.fused.p;
+      p.bias = P(c, hd.conv.p_b); p.prelu = P(c, hd.conv.p_prelu); p.w2 = P(c, hd.p_w2); p.b2 = P(c, hd.p_b2);
+      p.out = hd.out;
+      order.push_back(&hd.fused);
+    }
+    std::stable_sort(order.begin(), order.end(), [](const ConvLaunch* a, const ConvLaunch* b) { return a->p.k_iters > b->p.k_iters; });
+    const bool prof = c->profiling;
+    if (prof) {
+      if ((int)c->conv_ev.size() < c->conv_ev_used + 2) {
+        cudaEvent_t a, b;
+        FRCNN_CUDA_TRY(cudaEventCreate(&a));
+        FRCNN_CUDA_TRY(cudaEventCreate(&b));
+        c->conv_ev.push_back(a);
+        c->conv_ev.push_back(b);
+      }
+      cudaEventRecord(c->conv_ev[c->conv_ev_used], c->stream);
+    }
+    conv_launch_head_group(order.data(), (int)order.size(), c->sm_count, c->stream);
+    ++c->launches;
+    if (prof) {
+      cudaEventRecord(c->conv_ev[c->conv_ev_used + 1], c->stream);
+      c->conv_ev_used += 2;
+      for (auto* L : order) c->conv_flops += 2.0 * (double)L->p.N * L->p.Hout * L->p.Wout * L->p.Cout * (double)L->p.KH * L->p.KW * L->p.Cin;
+    }
+  } else {
     std::vector<const ConvLaunch*> order;
     for (auto& hd : c->heads) {
       hd.conv.launch.p.bias = nullptr;
@@ -1087,7 +1119,8 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
     conv_prepare(&f.launch, in, f.w_packed, 1, 1, R, f.nin, f.nout, 1, 1, 0, 0, EPI_F32_REDUCE, nullptr, c->sm_count, splits, 0, 0);
     conv_set_f32_output(&f.launch, f.acc);
     f.launch.p.m_limit = c->flags + 2;  // roi_total
-    f.launch.p.dyn_ctas = c->sm_count;  // split-K factor chosen on the device from the live row count
+    // split-K factor chosen on the device from the live row count so that the units fill about dyn_ctas CTAs
+    f.launch.p.dyn_ctas = getenv("FRCNN_CNET_CTAS") ? atoi(getenv("FRCNN_CNET_CTAS")) : c->sm_count;
     in = f.out_bf16;
   }
   // NMS workspace: segments = max(N images, N * classes)
@@ -1950,6 +1983,15 @@ int frcnn_detect_stats(const frcnn_ctx* c, int64_t stats[4]) {
 int frcnn_set_detect_thresholds(frcnn_ctx* c, double fg_prob, float nms_proposals, double class_prob, float nms_classes) {
   if (!c) return FRCNN_E_INVALID;
   c->thr_fg = fg_prob; c->thr_nms1 = nms_proposals; c->thr_class = class_prob; c->thr_nms2 = nms_classes;
+  return FRCNN_OK;
+}
+
+int frcnn_set_schedule(frcnn_ctx* c, int schedule) {
+  if (!c || (schedule != FRCNN_SCHED_LATENCY && schedule != FRCNN_SCHED_THROUGHPUT)) return FRCNN_E_INVALID;
+  if (c->schedule != schedule) {
+    c->schedule = schedule;
+    ++c->ws_gen;  // a captured detect graph holds the other schedule's launches: re-capture
+  }
   return FRCNN_OK;
 }
 

@@ -47,6 +47,8 @@ enum ConvEpilogue {
                        // only the pooled map is written
   EPI_F32_SLICES = 3,  // deterministic split-K: raw fp32 partial sums, split s of image n -> slice [s * N + n] of an
                        // fp32 NHWC workspace [splits * N][Hout][Wout][Cout] (TMA store); summed by the consumer
+  EPI_HEAD = 4,        // fused AnchorNetwork (model_utilities.lua:29-35): bias + PReLU + 1x1 conv to 18 channels in the
+                       // epilogue, fp32; out = [N][18][Hout][Wout] fp32 (halo kernel, Cout = 256, no split-K)
 };
 
 struct ConvParams {
@@ -82,6 +84,8 @@ struct ConvParams {
   // descriptor into that box.  BW = 8 (one 8-row descriptor group per tile row), BH = 16.
   int halo;                 // 1: launched with conv_halo_kernel
   int halo_desc;            // descriptor base-offset mode for the row-shifted start address (0: field left 0)
+  const float* w2;          // EPI_HEAD: [18][256] weights of the 1x1 convolution (Torch layout)
+  const float* b2;          // EPI_HEAD: [18] bias of the 1x1 convolution
   int dbg;                  // FRCNN_CONV_DBG (measurement only): 1 skip the global stores, 2 skip the epilogue body, 4 skip the MMAs
 };
 
@@ -121,6 +125,11 @@ void conv_first_prepare(ConvLaunch* L, const bf16* w_packed32, int N, int Hin, i
 void conv_launch(const ConvLaunch& L, cudaStream_t st);
 // all members: same BN, MT == 1, not the first-layer kernel; pass them heaviest (longest K per unit) first
 void conv_launch_group(const ConvLaunch* const* Ls, int n, int num_sms, cudaStream_t st);
+// Fused anchor head (EPI_HEAD): k x k valid conv (k <= 7) to 256 hidden channels + the 1x1 tail in the epilogue; set
+// p.bias / p.prelu / p.w2 / p.b2 / p.out before launching.  conv_launch_head_group: up to 4 heads in ONE launch of the
+// halo kernel, pass them heaviest first.
+void conv_prepare_head(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int K, int num_sms);
+void conv_launch_head_group(const ConvLaunch* const* Ls, int n, int num_sms, cudaStream_t st);
 // dW[co][tap][ci] (fp32, zeroed by the caller) += sum over pixels dY[p][co] * X[p + tap][ci]; dy / x: NHWC bf16;
 // always EPI_F32_REDUCE
 void conv_wgrad_prepare(ConvLaunch* L, const bf16* dy, const bf16* x, float* dw_taps, int N, int Hin, int Win, int Cin,

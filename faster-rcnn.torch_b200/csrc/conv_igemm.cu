@@ -501,40 +501,134 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 // 128-byte-swizzle layout holds for every tap (the swizzle is a function of the absolute shared-memory address, the
 // box starts on a 1024-byte boundary).  Weights stream through their own ring, one {64 x BN} box per (chunk, tap).
 // Same warp roles and the same epilogue as conv_igemm_kernel; BN x MT = 512 columns run with ONE accumulator stage.
-static constexpr int HALO_BW = 8, HALO_BH = 16, HALO_MAXK = 3;
-__host__ __device__ constexpr int halo_a_slot(int MT) {
-  return (((HALO_BH * MT + HALO_MAXK - 1) * (HALO_BW + HALO_MAXK - 1) * 128) + 1023) & ~1023;
+static constexpr int HALO_BW = 8, HALO_BH = 16, HALO_MAXK = 3, HEAD_MAXK = 7;
+// extra shared memory of the fused anchor-head epilogue (EPI_HEAD): 1x1 weights [256][20] fp32 + the second column
+// half's partial sums [128][19] fp32 (the 16 KB staging tile of the bf16 epilogues is not used in that mode)
+static constexpr int HEAD_CO = 18, HEAD_CM = 256, HEAD_W2_PITCH = 20, HEAD_PART_PITCH = 19;
+static constexpr int HEAD_SMEM = HEAD_CM * HEAD_W2_PITCH * 4 + 128 * HEAD_PART_PITCH * 4 + 128;
+__host__ __device__ constexpr int halo_a_slot(int MT, int KMAX) {
+  return (((HALO_BH * MT + KMAX - 1) * (HALO_BW + KMAX - 1) * 128) + 1023) & ~1023;
 }
-__host__ __device__ constexpr int halo_a_slots(int MT) { return MT == 2 ? 2 : 3; }
-__host__ __device__ constexpr int halo_b_slots(int BN, int MT) {
-  return (SMEM_LIMIT - SMEM_FIXED - halo_a_slots(MT) * halo_a_slot(MT)) / (BN * 128) > 8
+__host__ __device__ constexpr int halo_a_slots(int MT, int KMAX) { return (MT == 2 || KMAX > HALO_MAXK) ? 2 : 3; }
+__host__ __device__ constexpr int halo_extra(int KMAX) { return KMAX > HALO_MAXK ? HEAD_SMEM - STAGE_TILE_BYTES : 0; }
+__host__ __device__ constexpr int halo_b_slots(int BN, int MT, int KMAX) {
+  return (SMEM_LIMIT - SMEM_FIXED - halo_extra(KMAX) - halo_a_slots(MT, KMAX) * halo_a_slot(MT, KMAX)) / (BN * 128) > 8
              ? 8
-             : (SMEM_LIMIT - SMEM_FIXED - halo_a_slots(MT) * halo_a_slot(MT)) / (BN * 128);
+             : (SMEM_LIMIT - SMEM_FIXED - halo_extra(KMAX) - halo_a_slots(MT, KMAX) * halo_a_slot(MT, KMAX)) / (BN * 128);
 }
 __host__ __device__ constexpr int halo_acc_stages(int BN, int MT) { return 2 * BN * MT <= 512 ? 2 : 1; }
 __host__ __device__ constexpr int halo_tmem_cols(int BN, int MT) {
   return halo_acc_stages(BN, MT) * BN * MT <= 128 ? 128 : (halo_acc_stages(BN, MT) * BN * MT <= 256 ? 256 : 512);
 }
-static int halo_smem_bytes(int BN, int MT) {
-  return halo_a_slots(MT) * halo_a_slot(MT) + halo_b_slots(BN, MT) * BN * 128 + SMEM_FIXED;
+static int halo_smem_bytes(int BN, int MT, int KMAX) {
+  return halo_a_slots(MT, KMAX) * halo_a_slot(MT, KMAX) + halo_b_slots(BN, MT, KMAX) * BN * 128 + SMEM_FIXED + halo_extra(KMAX);
 }
 
-template <int BN, int MT>
+// Fused AnchorNetwork epilogue (model_utilities.lua:29-35): the k x k conv's 256 fp32 sums per pixel never leave the
+// SM -- bias + PReLU and the 1x1 convolution to 18 channels run on the CUDA cores straight out of TMEM, in fp32 with
+// a fixed summation order (channels ascending inside a column half, then half 0 + half 1), and only the 18-channel
+// map [N][18][H][W] (Torch layout, what Detector.lua:47-49 indexes) is written.  No split-K, no slice workspace.
+// Thread = pixel row of the tile (TMEM lane); warp e covers lane quarter (e & 3) and column half (e >> 2).
+template <int ACC>
+__device__ __forceinline__ void epilogue_head(const ConvGroup& grp, float* w2s, float* parts, float* sb, uint32_t tmem_base,
+                                              uint64_t* tmem_full, uint64_t* tmem_empty, const GroupSched& sc, int ewarp, int lane) {
+  constexpr int BN = HEAD_CM;
+  const int q = ewarp & 3, half = ewarp >> 2;
+  const int row = q * 32 + lane;
+  const int tid = ewarp * 32 + lane;
+  const int total_units = grp.unit_end[grp.n - 1];
+  int seq = 0, cur = -1;
+  for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    int gi;
+    TileCoord t;
+    if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+    const ConvParams& p = grp.p[gi];
+    const int acc = ACC == 2 ? (seq & 1) : 0;
+    const uint32_t acc_phase = (uint32_t)(ACC == 2 ? (seq >> 1) : seq) & 1u;
+    ++seq;
+    if (gi != cur) {  // another head: its 1x1 weights [18][256] -> [256][20], hidden bias [256], output bias [18]
+      ptx::named_bar_sync(1, EPI_THREADS);
+      for (int i = tid; i < HEAD_CO * HEAD_CM; i += EPI_THREADS) {
+        const int o = i / HEAD_CM, c = i - o * HEAD_CM;
+        w2s[c * HEAD_W2_PITCH + o] = __ldg(p.w2 + i);
+      }
+      for (int i = tid; i < HEAD_CM; i += EPI_THREADS) sb[i] = __ldg(p.bias + i);
+      if (tid < HEAD_CO) sb[HEAD_CM + tid] = __ldg(p.b2 + tid);
+      ptx::named_bar_sync(1, EPI_THREADS);
+      cur = gi;
+    }
+    const float slope = p.prelu ? __ldg(p.prelu) : 1.0f;
+    float o18[HEAD_CO];
+#pragma unroll
+    for (int o = 0; o < HEAD_CO; ++o) o18[o] = 0.f;
+    ptx::mbar_wait(&tmem_full[acc], acc_phase);
+    ptx::tc_fence_after();
+    const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + half * 128) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < 128; c0 += 16) {
+      uint32_t v[16];
+      ptx::tmem_ld_32x32b_x16(taddr + c0, v);
+      ptx::tmem_ld_wait();
+      const float* wrow = w2s + (half * 128 + c0) * HEAD_W2_PITCH;
+      const float* brow = sb + half * 128 + c0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float h = __uint_as_float(v[j]) + brow[j];
+        h = h > 0.f ? h : h * slope;
+        const float4* w4 = reinterpret_cast<const float4*>(wrow + j * HEAD_W2_PITCH);
+#pragma unroll
+        for (int g = 0; g < 5; ++g) {
+          const float4 w = w4[g];
+          o18[4 * g] = fmaf(h, w.x, o18[4 * g]);
+          o18[4 * g + 1] = fmaf(h, w.y, o18[4 * g + 1]);
+          if (g < 4) {
+            o18[4 * g + 2] = fmaf(h, w.z, o18[4 * g + 2]);
+            o18[4 * g + 3] = fmaf(h, w.w, o18[4 * g + 3]);
+          }
+        }
+      }
+    }
+    // all TMEM reads of this thread are done: the accumulator stage can be refilled while the halves are combined
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+    if (half == 1) {
+#pragma unroll
+      for (int o = 0; o < HEAD_CO; ++o) parts[row * HEAD_PART_PITCH + o] = o18[o];
+    }
+    ptx::named_bar_sync(1, EPI_THREADS);
+    if (half == 0) {
+      const int h = t.h0 + (row >> p.bw_shift), w = t.w0 + (row & (p.BW - 1));
+      if (h < p.Hout && w < p.Wout) {
+        const size_t HW = (size_t)p.Hout * p.Wout;
+        float* o_px = reinterpret_cast<float*>(p.out) + (size_t)t.n_img * HEAD_CO * HW + (size_t)h * p.Wout + w;
+#pragma unroll
+        for (int o = 0; o < HEAD_CO; ++o) o_px[o * HW] = (o18[o] + parts[row * HEAD_PART_PITCH + o]) + sb[HEAD_CM + o];
+      }
+    }
+    ptx::named_bar_sync(1, EPI_THREADS);  // `parts` may be overwritten by the next unit
+  }
+}
+
+template <int BN, int MT, int KMAX>
 __global__ void __launch_bounds__(CONV_THREADS, 1)
     conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGroup grp) {
-  constexpr int A_SLOT = halo_a_slot(MT), A_SLOTS = halo_a_slots(MT);
-  constexpr int B_SLOT = BN * 128, B_SLOTS = halo_b_slots(BN, MT);
+  constexpr int A_SLOT = halo_a_slot(MT, KMAX), A_SLOTS = halo_a_slots(MT, KMAX);
+  constexpr int B_SLOT = BN * 128, B_SLOTS = halo_b_slots(BN, MT, KMAX);
   constexpr int ACC = halo_acc_stages(BN, MT);
   constexpr int TMEM_COLS = halo_tmem_cols(BN, MT);
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BN);
+  constexpr bool HEAD = KMAX > HALO_MAXK;  // the fused anchor-head configuration: EPI_HEAD units of up to 4 convs
   static_assert(B_SLOTS >= 2, "weight ring too small");
+  static_assert(!HEAD || (BN == HEAD_CM && MT == 1), "anchor heads: 256 hidden channels, one sub-tile");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + A_SLOTS * A_SLOT;
-  uint8_t* tile_buf = smem_b + B_SLOTS * B_SLOT;
-  float* sbias = reinterpret_cast<float*>(tile_buf + STAGE_TILE_BYTES);
+  uint8_t* tile_buf = smem_b + B_SLOTS * B_SLOT;   // bf16 epilogues: 16 KB staging tile; EPI_HEAD: w2 | partial sums
+  uint8_t* after_tile = tile_buf + (HEAD ? HEAD_SMEM : STAGE_TILE_BYTES);
+  float* sbias = reinterpret_cast<float*>(after_tile);
   uint64_t* full_a = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
   uint64_t* empty_a = full_a + A_SLOTS;
   uint64_t* full_b = empty_a + A_SLOTS;
@@ -545,16 +639,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_units = grp.unit_end[0];
+  const int total_units = grp.unit_end[grp.n - 1];
   GroupSched sc;
   make_sched(grp, BN, sc);
-  const ConvParams& p = grp.p[0];
-  const int PW = HALO_BW + p.KW - 1;                                            // halo pitch, pixels
-  const uint32_t a_tx = (uint32_t)(PW * (HALO_BH * MT + p.KH - 1)) * 128u;      // bytes of one A box
 
   if (warp == 0 && lane == 0) {
-    ptx::tma_prefetch_desc(&maps.a[0]);
-    ptx::tma_prefetch_desc(&maps.b[0]);
+    for (int g = 0; g < grp.n; ++g) {
+      ptx::tma_prefetch_desc(&maps.a[g]);
+      ptx::tma_prefetch_desc(&maps.b[g]);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < A_SLOTS; ++s) {
@@ -575,7 +668,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     ptx::tmem_alloc(tmem_base_slot, TMEM_COLS);
     ptx::tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+  if (!HEAD) {
+    const ConvParams& p0 = grp.p[0];
+    for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (p0.bias && i < p0.Cout) ? p0.bias[i] : 0.f;
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -590,33 +686,40 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     if (lane == 0) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
-      const int taps = p.KH * p.KW;
-      const int kpre = min(B_SLOTS - 1, taps - 1);
       int ua = blockIdx.x, ca = 0;  // cursor of the A ring: one chunk ahead of the weight ring
       auto issue_a = [&]() {
+        int ga;
+        TileCoord ta;
+        while (ua < total_units && !next_unit(grp, sc, ua, BN, ga, ta)) ua += gridDim.x;
         if (ua >= total_units) return;
-        const TileCoord ta = decode_tile(p, ua, BN, 1, p.k_iters);
+        const ConvParams& pa = grp.p[ga];
+        const uint32_t a_tx = (uint32_t)((HALO_BW + pa.KW - 1) * (HALO_BH * MT + pa.KH - 1)) * 128u;
         ptx::mbar_wait(&empty_a[as], aph ^ 1);
         ptx::mbar_arrive_expect_tx(&full_a[as], a_tx);
-        ptx::tma_load_4d(smem_a + as * A_SLOT, &maps.a[0], &full_a[as], ca * BLOCK_K, ta.w0 - p.padW, ta.h0 - p.padH, ta.n_img);
+        ptx::tma_load_4d(smem_a + as * A_SLOT, &maps.a[ga], &full_a[as], ca * BLOCK_K, ta.w0 - pa.padW, ta.h0 - pa.padH, ta.n_img);
         if (++as == A_SLOTS) {
           as = 0;
           aph ^= 1;
         }
-        if (++ca == p.cchunks) {
+        if (++ca == pa.cchunks) {
           ca = 0;
           ua += gridDim.x;
         }
       };
       issue_a();
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
-        const TileCoord t = decode_tile(p, unit, BN, 1, p.k_iters);
+        int gi;
+        TileCoord t;
+        if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+        const ConvParams& p = grp.p[gi];
+        const int taps = p.KH * p.KW;
+        const int kpre = min(B_SLOTS - 1, taps - 1);
         for (int c = 0; c < p.cchunks; ++c) {
           for (int tap = 0; tap < taps; ++tap) {
             if (tap == kpre) issue_a();
             ptx::mbar_wait(&empty_b[bs], bph ^ 1);
             ptx::mbar_arrive_expect_tx(&full_b[bs], B_SLOT);
-            ptx::tma_load_2d(smem_b + bs * B_SLOT, &maps.b[0], &full_b[bs], (tap * p.cchunks + c) * BLOCK_K, t.n0);
+            ptx::tma_load_2d(smem_b + bs * B_SLOT, &maps.b[gi], &full_b[bs], (tap * p.cchunks + c) * BLOCK_K, t.n0);
             if (++bs == B_SLOTS) {
               bs = 0;
               bph ^= 1;
@@ -631,11 +734,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int seq = 0;
-      const uint32_t sbo = (uint32_t)PW * 128u;
       for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
         int gi;
         TileCoord t;
         if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+        const ConvParams& p = grp.p[gi];
+        const int PW = HALO_BW + p.KW - 1;  // halo pitch, pixels
+        const uint32_t sbo = (uint32_t)PW * 128u;
         const int acc = ACC == 2 ? (seq & 1) : 0;
         const uint32_t acc_phase = (uint32_t)(ACC == 2 ? (seq >> 1) : seq) & 1u;
         ++seq;
@@ -676,7 +781,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
       }
     }
   } else if (warp >= 4) {
-    epilogue_loop<BN, MT, ACC>(grp, maps.o, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 4, lane);
+    if constexpr (HEAD) {
+      float* w2s = reinterpret_cast<float*>(tile_buf);
+      float* parts = w2s + HEAD_CM * HEAD_W2_PITCH;
+      epilogue_head<ACC>(grp, w2s, parts, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 4, lane);
+    } else {
+      epilogue_loop<BN, MT, ACC>(grp, maps.o, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 4, lane);
+    }
   }
 
   ptx::tc_fence_before();
@@ -1125,6 +1236,38 @@ static void conv_prepare_halo(ConvLaunch* L, const bf16* in, const bf16* w_packe
   L->grid = total < num_sms ? total : num_sms;
 }
 
+void conv_prepare_head(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int K, int num_sms) {
+  FRCNN_REQUIRE(Cin % 64 == 0 && K >= 1 && K <= HEAD_MAXK, FRCNN_E_INVALID, "fused anchor head: Cin % 64 == 0, kernel size <= 7");
+  FRCNN_REQUIRE(Hin >= K && Win >= K, FRCNN_E_INVALID, "fused anchor head: input smaller than the kernel");
+  L->BN = HEAD_CM;
+  L->first = false;
+  L->w_first = nullptr;
+  ConvParams& p = L->p;
+  p = ConvParams();
+  p.N = N; p.Hin = Hin; p.Win = Win; p.Cin = Cin;
+  p.Hout = Hin - K + 1;
+  p.Wout = Win - K + 1;
+  p.Cout = HEAD_CM; p.KH = K; p.KW = K; p.padH = 0; p.padW = 0;
+  p.MT = 1;
+  p.BW = HALO_BW; p.BH = HALO_BH; p.bw_shift = 3;
+  p.tiles_w = (p.Wout + p.BW - 1) / p.BW;
+  p.tiles_h = (p.Hout + p.BH - 1) / p.BH;
+  p.n_tiles_m = N * p.tiles_h * p.tiles_w;
+  p.n_tiles_n = 1;
+  p.cchunks = Cin / 64;
+  p.k_iters = K * K * p.cchunks;
+  p.splits = 1;
+  p.k_per_split = p.k_iters;
+  p.mode = EPI_HEAD;
+  p.scale = 1.0f;
+  p.halo = 1;
+  p.halo_desc = env_int("FRCNN_HALO_DESC", 0);
+  make_tmap_act(&L->tmA, in, N, Hin, Win, Cin, HALO_BW + K - 1, HALO_BH + K - 1);
+  make_tmap_weight(&L->tmB, w_packed, HEAD_CM, K * K * Cin, HEAD_CM);
+  L->tmOut = L->tmB;
+  L->grid = p.n_tiles_m < num_sms ? p.n_tiles_m : num_sms;
+}
+
 void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
                   int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int force_splits, int force_bn,
                   int force_mt) {
@@ -1308,28 +1451,28 @@ static void launch_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cud
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int KMAX>
 static void launch_halo_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
   static bool configured = false;
-  const int smem = halo_smem_bytes(BN, MT);
+  const int smem = halo_smem_bytes(BN, MT, KMAX);
   if (!configured) {
-    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  conv_halo_kernel<BN, MT><<<grid, CONV_THREADS, smem, st>>>(maps, grp);
+  conv_halo_kernel<BN, MT, KMAX><<<grid, CONV_THREADS, smem, st>>>(maps, grp);
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
 static void launch_halo_key(int BN, int MT, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
   switch (BN * 10 + MT) {
-    case 641: launch_halo_cfg<64, 1>(maps, grp, grid, st); break;
-    case 642: launch_halo_cfg<64, 2>(maps, grp, grid, st); break;
-    case 1281: launch_halo_cfg<128, 1>(maps, grp, grid, st); break;
-    case 1282: launch_halo_cfg<128, 2>(maps, grp, grid, st); break;
-    case 1921: launch_halo_cfg<192, 1>(maps, grp, grid, st); break;
-    case 1922: launch_halo_cfg<192, 2>(maps, grp, grid, st); break;
-    case 2561: launch_halo_cfg<256, 1>(maps, grp, grid, st); break;
-    case 2562: launch_halo_cfg<256, 2>(maps, grp, grid, st); break;
+    case 641: launch_halo_cfg<64, 1, HALO_MAXK>(maps, grp, grid, st); break;
+    case 642: launch_halo_cfg<64, 2, HALO_MAXK>(maps, grp, grid, st); break;
+    case 1281: launch_halo_cfg<128, 1, HALO_MAXK>(maps, grp, grid, st); break;
+    case 1282: launch_halo_cfg<128, 2, HALO_MAXK>(maps, grp, grid, st); break;
+    case 1921: launch_halo_cfg<192, 1, HALO_MAXK>(maps, grp, grid, st); break;
+    case 1922: launch_halo_cfg<192, 2, HALO_MAXK>(maps, grp, grid, st); break;
+    case 2561: launch_halo_cfg<256, 1, HALO_MAXK>(maps, grp, grid, st); break;
+    case 2562: launch_halo_cfg<256, 2, HALO_MAXK>(maps, grp, grid, st); break;
     default: throw Error{FRCNN_E_INVALID, "conv (halo kernel): unsupported (BN, MT)"};
   }
 }
@@ -1394,6 +1537,26 @@ void conv_launch_group(const ConvLaunch* const* Ls, int n, int num_sms, cudaStre
     grp.unit_end[g] = total;
   }
   launch_key(Ls[0]->BN, 1, maps, grp, total < num_sms ? total : num_sms, st);
+}
+
+void conv_launch_head_group(const ConvLaunch* const* Ls, int n, int num_sms, cudaStream_t st) {
+  FRCNN_REQUIRE(n >= 1 && n <= MAX_GROUP, FRCNN_E_INVALID, "anchor head group: 1..4 members");
+  ConvGroup grp;
+  ConvMaps maps;
+  grp.n = n;
+  int total = 0;
+  for (int g = 0; g < MAX_GROUP; ++g) {
+    const ConvLaunch& L = *Ls[g < n ? g : n - 1];
+    FRCNN_REQUIRE(L.p.mode == EPI_HEAD && L.p.halo && L.p.w2 && L.p.b2 && L.p.bias && L.p.out, FRCNN_E_INVALID,
+                  "anchor head group: members must be prepared by conv_prepare_head with their tail parameters set");
+    grp.p[g] = L.p;
+    maps.a[g] = L.tmA;
+    maps.b[g] = L.tmB;
+    maps.o[g] = L.tmOut;
+    if (g < n) total += L.p.n_tiles_m;
+    grp.unit_end[g] = total;
+  }
+  launch_halo_cfg<HEAD_CM, 1, HEAD_MAXK>(maps, grp, total < num_sms ? total : num_sms, st);
 }
 
 }  // namespace frcnn

@@ -113,9 +113,11 @@ class DetectorPipeline:
     submit / drain interface: the host loop of main.lua:198-206 over a stream of frames with several frames in
     flight.  Winners come back in submission order and are identical to Detector:detect frame by frame."""
 
-    def __init__(self, model, in_flight=2):
+    def __init__(self, model, in_flight=2, schedule="throughput"):
         assert in_flight >= 1
-        self.models = [model] + [model.replicate() for _ in range(in_flight - 1)]
+        self.models = [model.replicate() for _ in range(in_flight)]  # `model` itself keeps its own schedule / graph
+        for m in self.models:
+            m.set_schedule(schedule)
         self.detectors = [Detector(m) for m in self.models]
         self._busy = [False] * in_flight
         self._next = 0
@@ -149,5 +151,5 @@ class DetectorPipeline:
         return out + self.drain()
 
     def close(self):
-        for m in self.models[1:]:
+        for m in self.models:
             m.close()

@@ -127,6 +127,15 @@ class Model:
             self.params[n].copy_(v.reshape(-1).to(self.device))
         self.pack_weights()
 
+    def set_schedule(self, schedule):
+        """'latency' (default: every stage fills the machine with one frame batch) or 'throughput' (least SM time per
+        frame: unsplit anchor heads with the tail fused; for several frames in flight).  frcnn_set_schedule."""
+        L = lib()
+        mode = {"latency": L.FRCNN_SCHED_LATENCY, "throughput": L.FRCNN_SCHED_THROUGHPUT}[schedule]
+        rc = L.frcnn_set_schedule(self.ctx, mode)
+        if rc != 0:
+            raise RuntimeError("frcnn_set_schedule failed")
+
     def replicate(self):
         """A second context of the same architecture on the same device holding a copy of the current weights (own
         stream, workspaces and CUDA graph): one more frame in flight for DetectorPipeline."""

@@ -235,6 +235,15 @@ int frcnn_set_profiling(frcnn_ctx* ctx, int enable);
 /* frcnn_detect / frcnn_detect_dev replay their fixed kernel sequence from a CUDA graph from the third call with the
  * same image pointer, shape and thresholds on (default on; profiling mode always runs eagerly). */
 int frcnn_set_graph_replay(frcnn_ctx* ctx, int enable);
+/* Launch schedule of pnet:forward in evaluate mode (frcnn_pnet_forward, frcnn_detect*).  FRCNN_SCHED_LATENCY
+ * (default): every stage is cut so that ONE frame batch fills the machine -- the anchor-head convolutions run as
+ * split-K units on all SMs followed by a tail kernel (fastest single synchronous call).  FRCNN_SCHED_THROUGHPUT: the
+ * least SM time per frame -- the four AnchorNetworks (model_utilities.lua:29-35) run as unsplit units with bias +
+ * PReLU + the 1x1 convolution fused into the conv epilogue (no slice workspace, no tail launch); meant for several
+ * frames in flight (frcnn_detect_begin / _end on several contexts), where the other frames fill the machine.  Both
+ * compute the same fp32 sums in a different, fixed order (results agree to fp32 rounding). */
+enum { FRCNN_SCHED_LATENCY = 0, FRCNN_SCHED_THROUGHPUT = 1 };
+int frcnn_set_schedule(frcnn_ctx* ctx, int schedule);
 int frcnn_last_timings(const frcnn_ctx* ctx, float ms[6]);
 /* Profiling mode also brackets every launch of the tcgen05 conv/GEMM kernel with a CUDA event pair on the ctx
  * stream: summed device time, summed algorithmic FLOPs (2*M*N*K of the un-padded problems) and launch count of

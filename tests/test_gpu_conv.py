@@ -194,6 +194,48 @@ def test_pnet_batch_equals_single(F, small_model):
             assert (a[s] - b).abs().max().item() <= 1e-5 * b.abs().max().item()
 
 
+@pytest.mark.parametrize("n,h,w", [(1, 122, 192), (1, 450, 800), (3, 122, 192)])
+def test_pnet_forward_throughput_schedule(F, small_model, n, h, w):
+    """FRCNN_SCHED_THROUGHPUT: the four AnchorNetworks as unsplit halo-kernel units with bias + PReLU + the 1x1 conv fused
+    into the epilogue (fp32, fixed order).  Same sums as the split-K + tail-kernel schedule in another order: the 18-channel
+    maps agree to fp32 rounding (1e-4 of the map magnitude: up to 18 816 products per sum), the trunk is untouched (bit-identical), and the fused path
+    is itself bit-reproducible and batch-invariant (no split factor depends on the batch)."""
+    imgs = torch.stack([OM.synthetic_frame(h, w, seed=7 + s) for s in range(n)]).cuda()
+    base = [o.clone() for o in small_model.pnet.forward(imgs)]
+    small_model.set_schedule("throughput")
+    try:
+        fused = [o.clone() for o in small_model.pnet.forward(imgs)]
+        again = small_model.pnet.forward(imgs)
+        for a, b in zip(fused, again):
+            assert torch.equal(a, b)
+        assert torch.equal(fused[4], base[4])
+        for a, b in zip(fused[:4], base[:4]):
+            assert a.shape == b.shape
+            assert (a - b).abs().max().item() <= 1e-4 * b.abs().max().item()
+        if n > 1:
+            for s in range(n):
+                single = small_model.pnet.forward(imgs[s])
+                for a, b in zip(fused[:4], single[:4]):
+                    assert torch.equal(a[s], b)
+    finally:
+        small_model.set_schedule("latency")
+
+
+def test_vgg_large_throughput_schedule(F):
+    m = F.vgg_large(F.imgnet_cfg)
+    p = OM.init_params(OM.VGG_LARGE, OM.CFG_IMAGENET, seed=2, randomize_aux=True)
+    m.load_params(p)
+    m.set_schedule("throughput")
+    img = OM.synthetic_frame(150, 200, seed=4)
+    outs = m.pnet.forward(img.cuda())
+    with torch.no_grad():
+        want = OM.pnet_forward(OM.VGG_LARGE, p, img, quant=OM.bf16_round)
+    for o, q in zip(outs, want):
+        assert tuple(o.shape) == tuple(q.shape)
+        assert (o.cpu() - q).abs().max().item() <= 0.03 * q.abs().max().item()
+    m.close()
+
+
 def test_pnet_forward_is_deterministic(F, small_model):
     """Every kernel of pnet:forward has a fixed summation order (split-K slices, no atomics): two runs on the same
     frame are bit-identical, which is what makes the decode / NMS index parity reproducible end to end."""
