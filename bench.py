@@ -30,7 +30,7 @@ import torch  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=0, help="default: 200 (detect), 20 (nms, train)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="detect", choices=["detect", "nms", "train"])
@@ -44,7 +44,10 @@ def parse():
                     help="detect: frames (steps) in flight, one library context each (1 = every step synchronous)")
     ap.add_argument("--schedule", default="throughput", choices=["throughput", "latency"],
                     help="detect: launch schedule of the in-flight contexts (frcnn_set_schedule)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.steps <= 0:
+        a.steps = 200 if (a.workload == "detect" and a.impl == "b200") else 20
+    return a
 
 
 def dist_env():

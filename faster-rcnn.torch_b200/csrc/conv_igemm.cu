@@ -802,6 +802,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 // inside one warp's 32 pixel rows).  Warp e drains TMEM lane quarter (e & 3) of accumulator stage (e >> 2) -- the two
 // stages are drained concurrently -- through its own 4 KB staging tile with __syncwarp only: the per-tile latency
 // chain of the CTA-wide epilogue (two 256-thread barriers per tile) paced this K = 27 layer.
+template <bool FOLDED, int NACC = 2>
 __device__ __forceinline__ void epilogue_first_warp(const ConvParams& p, uint8_t* stage_base, const float* sbias, uint32_t tmem_base,
                                                     uint64_t* tmem_full, uint64_t* tmem_empty, int total_tiles, int ewarp, int lane) {
   constexpr int BN = 64;
@@ -817,8 +818,8 @@ __device__ __forceinline__ void epilogue_first_warp(const ConvParams& p, uint8_t
   const int rows_per_warp = 32 >> p.bw_shift;  // tile rows covered by this warp (>= 2, even)
   int seq = 0;
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++seq) {
-    if ((seq & 1) != stg) continue;
-    const uint32_t acc_phase = (uint32_t)(seq >> 1) & 1u;
+    if ((seq % NACC) != stg) continue;
+    const uint32_t acc_phase = (uint32_t)(seq / NACC) & 1u;
     const TileCoord t = decode_tile(p, tile, BN, 1, 1);
     ptx::mbar_wait(&tmem_full[stg], acc_phase);
     ptx::tc_fence_after();
@@ -831,20 +832,32 @@ __device__ __forceinline__ void epilogue_first_warp(const ConvParams& p, uint8_t
       uint32_t v[32];
       ptx::tmem_ld_32x32b_x32(taddr + half * 32, v);
       uint4 bq[8];
+      if (!FOLDED) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) bq[j] = ptx::ld_shared_v4(bias_addr + (uint32_t)(half * 32) * 4u + j * 16);
+        for (int j = 0; j < 8; ++j) bq[j] = ptx::ld_shared_v4(bias_addr + (uint32_t)(half * 32) * 4u + j * 16);
+      }
       ptx::tmem_ld_wait();
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float x0 = __uint_as_float(v[4 * j]) + __uint_as_float(bq[j].x);
-        const float x1 = __uint_as_float(v[4 * j + 1]) + __uint_as_float(bq[j].y);
-        const float x2 = __uint_as_float(v[4 * j + 2]) + __uint_as_float(bq[j].z);
-        const float x3 = __uint_as_float(v[4 * j + 3]) + __uint_as_float(bq[j].w);
-        float y0 = fmaf(fminf(x0, 0.f), k_neg, x0 * k_pos);
-        float y1 = fmaf(fminf(x1, 0.f), k_neg, x1 * k_pos);
-        float y2 = fmaf(fminf(x2, 0.f), k_neg, x2 * k_pos);
-        float y3 = fmaf(fminf(x3, 0.f), k_neg, x3 * k_pos);
+        float x0 = __uint_as_float(v[4 * j]), x1 = __uint_as_float(v[4 * j + 1]);
+        float x2 = __uint_as_float(v[4 * j + 2]), x3 = __uint_as_float(v[4 * j + 3]);
+        float y0, y1, y2, y3;
+        if (FOLDED) {  // bias arrived through the tensor core (two spare K slots); scale == 1: x + min(x, 0) * (slope - 1)
+          y0 = fmaf(fminf(x0, 0.f), k_neg, x0);
+          y1 = fmaf(fminf(x1, 0.f), k_neg, x1);
+          y2 = fmaf(fminf(x2, 0.f), k_neg, x2);
+          y3 = fmaf(fminf(x3, 0.f), k_neg, x3);
+        } else {
+          x0 += __uint_as_float(bq[j].x);
+          x1 += __uint_as_float(bq[j].y);
+          x2 += __uint_as_float(bq[j].z);
+          x3 += __uint_as_float(bq[j].w);
+          y0 = fmaf(fminf(x0, 0.f), k_neg, x0 * k_pos);
+          y1 = fmaf(fminf(x1, 0.f), k_neg, x1 * k_pos);
+          y2 = fmaf(fminf(x2, 0.f), k_neg, x2 * k_pos);
+          y3 = fmaf(fminf(x3, 0.f), k_neg, x3 * k_pos);
+        }
         if (p.chan_scale) {
           const float4 m = __ldg(reinterpret_cast<const float4*>(p.chan_scale + (size_t)t.n_img * p.Cout + half * 32) + j);
           y0 *= m.x; y1 *= m.y; y2 *= m.z; y3 *= m.w;
@@ -1070,7 +1083,182 @@ __global__ void __launch_bounds__(FIRST_THREADS, 1)
       }
     }
   } else if (warp >= 12) {
-    epilogue_first_warp(p, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, total_tiles, warp - 12, lane);
+    epilogue_first_warp<false>(p, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, total_tiles, warp - 12, lane);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- first layer, TMA patches
+// Same layer as conv_first_kernel, restructured after its ncu capture showed it instruction-bound (about 1000 warp
+// instructions per warp and tile: 27 predicated scalar global loads with 64-bit address arithmetic per pixel, tile
+// decoding by integer division, and an epilogue of four fp32 operations per output):
+//  * the 3 x 10 x 18 input patch of a 16 x 8 tile arrives by ONE TMA load from the fp32 NCHW frame (tensor map over
+//    the caller's frame, box {24, 10, 3}; zero padding and the borders are the TMA unit's out-of-bounds fill), so a
+//    producer thread only gathers its 27 taps from shared memory;
+//  * the bias rides through the tensor core: K slots 27 and 28 of every A row hold 1.0 and the matching weight columns
+//    the bf16 pair (hi, lo) of the fp32 bias (hi + lo reproduces it to 2^-17 relative), which removes the bias add;
+//  * with scale == 1 (block 1 has no dropout) PReLU is x + min(x, 0) * (slope - 1): two operations.
+// Requires a 16-byte aligned frame pointer and Win % 4 == 0 (TMA global strides); other frames take conv_first_kernel.
+// Measured on B200: cp.async.bulk.tensor raises "illegal instruction" when the byte offset of the box start along the
+// innermost dimension is not a multiple of 16 -- the box therefore starts 4 pixels (16 bytes) left of the tile, not 1.
+static constexpr int FT_PATCH_W = 24, FT_PATCH_H = 10, FT_PATCH_X0 = 4;
+static constexpr int FT_PATCH_BYTES = FT_PATCH_W * FT_PATCH_H * 3 * 4;   // 2880
+static constexpr int FT_PATCH_PITCH = 2944;  // 24 floats x 10 rows x 3 planes = 2880, 128-byte aligned
+// The layer is paced by the latency of one tile's trip through an epilogue warp (TMEM load, activation, staging,
+// pooling, store: ~3600 clocks), not by instruction issue: FOUR accumulator stages, each drained by its own four warps.
+static constexpr int FT_ACC = 4;
+static constexpr int FT_THREADS = 384 + FT_ACC * 128;   // 8 gather warps, MMA / TMEM / TMA / spare, 4 epilogue warps per stage
+static constexpr int FT_SMEM = FIRST_STAGES * A_SUB_BYTES + FIRST_STAGES * FT_PATCH_PITCH + FIRST_BN * 128 + FT_ACC * 4 * 4096 +
+                               MAX_BIAS * 4 + 512 + 1024;
+
+__global__ void __launch_bounds__(FT_THREADS, 1)
+    conv_first_tma_kernel(const __grid_constant__ CUtensorMap tmImg, const __grid_constant__ ConvGroup grp, const bf16* __restrict__ w32) {
+  constexpr int BN = FIRST_BN;
+  const ConvParams& p = grp.p[0];
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BN);
+  constexpr int TMEM_COLS = FT_ACC * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + FIRST_STAGES * A_SUB_BYTES;
+  uint8_t* patches = smem_b + BN * 128;
+  uint8_t* tile_buf = patches + FIRST_STAGES * FT_PATCH_PITCH;  // 16 warps x 4 KB
+  float* sbias = reinterpret_cast<float*>(tile_buf + FT_ACC * 4 * 4096);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
+  uint64_t* empty_bar = full_bar + FIRST_STAGES;
+  uint64_t* patch_full = empty_bar + FIRST_STAGES;
+  uint64_t* patch_empty = patch_full + FIRST_STAGES;
+  uint64_t* tmem_full = patch_empty + FIRST_STAGES;
+  uint64_t* tmem_empty = tmem_full + FT_ACC;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + FT_ACC);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.n_tiles_m;
+
+  if (warp == 8 && lane == 0) {
+    ptx::tma_prefetch_desc(&tmImg);
+    for (int s = 0; s < FIRST_STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 4);
+      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&patch_full[s], 1);
+      ptx::mbar_init(&patch_empty[s], 4);   // the four warps of the gathering group
+    }
+    for (int a = 0; a < FT_ACC; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 9) {
+    ptx::tmem_alloc(tmem_base_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  // weights [64][32] bf16 -> K-major 128-byte-swizzled rows (chunks 0..3 of every row); K slots 27 / 28 <- bias (hi, lo)
+  for (int i = threadIdx.x; i < BN * 4; i += blockDim.x) {
+    const int n = i >> 2, c = i & 3;
+    uint4 v = reinterpret_cast<const uint4*>(w32)[i];
+    if (c == 3) {  // elements 24..31: 27 = high half of v.y, 28 = low half of v.z
+      const float b = (p.bias && n < p.Cout) ? p.bias[n] : 0.f;
+      const bf16 hi = __float2bfloat16_rn(b);
+      const bf16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+      v.y = (v.y & 0x0000FFFFu) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+      v.z = (v.z & 0xFFFF0000u) | (uint32_t)__bfloat16_as_ushort(lo);
+    }
+    *reinterpret_cast<uint4*>(smem_b + n * 128 + ((c ^ (n & 7)) << 4)) = v;
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp < 8) {
+    // ------------------------------------------------------------ gatherers: thread <-> pixel row, taps from the patch
+    const int group = warp >> 2;          // tiles with an even / odd local index
+    const int row = threadIdx.x & 127;
+    const int dy = row >> p.bw_shift, dx = row & (p.BW - 1);
+    const int sw = row & 7;
+    int local = group;
+    for (int tile = blockIdx.x + group * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, local += 2) {
+      const int stage = local % FIRST_STAGES;
+      const uint32_t phase = (uint32_t)(local / FIRST_STAGES) & 1u;
+      ptx::mbar_wait(&patch_full[stage], phase);
+      constexpr int pw = FT_PATCH_W;
+      const float* pt = reinterpret_cast<const float*>(patches + stage * FT_PATCH_PITCH) + dy * pw + dx + (FT_PATCH_X0 - 1);
+      float v[27];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) v[c * 9 + kh * 3 + kw] = pt[(c * FT_PATCH_H + kh) * pw + kw];
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&patch_empty[stage]);
+      uint32_t o[16];
+#pragma unroll
+      for (int j = 0; j < 13; ++j) o[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+      o[13] = ptx::pack_bf16x2(v[26], 1.0f);   // K slot 27: 1.0 x bias_hi
+      o[14] = ptx::pack_bf16x2(1.0f, 0.f);     // K slot 28: 1.0 x bias_lo
+      o[15] = 0u;
+      ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+      const uint32_t dst = ptx::smem_u32(smem_a + stage * A_SUB_BYTES) + row * 128;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) ptx::st_shared_v4(dst + ((c ^ sw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+      ptx::fence_proxy_async();   // every writer orders its own stores before the async proxy (the MMA) reads them
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&full_bar[stage]);   // one arrival per warp instead of 32
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b));
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + stage * A_SUB_BYTES));
+        ptx::mma_bf16_ss(tmem_base + acc * BN, da, db, IDESC, 0u);
+        ptx::mma_bf16_ss(tmem_base + acc * BN, da + 2, db + 2, IDESC, 1u);
+        ptx::mma_commit(&empty_bar[stage]);
+        ptx::mma_commit(&tmem_full[acc]);
+        if (++stage == FIRST_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+        if (++acc == FT_ACC) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ------------------------------------------------------------ patch loader: one TMA box per tile
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BN, 1, 1);
+        ptx::mbar_wait(&patch_empty[stage], phase ^ 1);
+        ptx::mbar_arrive_expect_tx(&patch_full[stage], FT_PATCH_BYTES);
+        ptx::tma_load_4d(patches + stage * FT_PATCH_PITCH, &tmImg, &patch_full[stage], t.w0 - FT_PATCH_X0, t.h0 - p.padH, 0, t.n_img);
+        if (++stage == FIRST_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 12) {
+    epilogue_first_warp<true, FT_ACC>(p, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, total_tiles, warp - 12, lane);
   }
 
   ptx::tc_fence_before();
@@ -1427,6 +1615,15 @@ void conv_first_prepare(ConvLaunch* L, const bf16* w_packed32, int N, int Hin, i
   L->w_first = w_packed32;
   fill_geometry(L->p, N, Hin, Win, 64, Cout, KH, KW, padH, padW, mode, 1, 16);  // BW <= 16: warp-local pooling windows
   ConvParams& p = L->p;
+  if (Win % 4 == 0 && padH == 1 && padW == 1 && env_int("FRCNN_FIRST_TMA", 1)) {
+    // conv_first_tma_kernel: fixed 16 x 8 tiles (its patch box is {20, 10, 3}); chosen at launch when the frame
+    // pointer is 16-byte aligned and scale == 1
+    p.BW = 16; p.BH = 8; p.bw_shift = 4;
+    p.tiles_w = (p.Wout + p.BW - 1) / p.BW;
+    p.tiles_h = (p.Hout + p.BH - 1) / p.BH;
+    p.n_tiles_m = N * p.tiles_h * p.tiles_w;
+    p.halo = 2;  // marks the TMA-patch variant as eligible
+  }
   p.Cimg = Cimg;
   p.n_tiles_n = 1;
   p.cchunks = 1;
@@ -1505,6 +1702,27 @@ void conv_launch(const ConvLaunch& L, cudaStream_t st) {
       configured = true;
     }
     FRCNN_REQUIRE(L.p.img != nullptr, FRCNN_E_STATE, "first-layer kernel: image pointer not set");
+    if (L.p.halo == 2 && L.p.scale == 1.0f && (reinterpret_cast<uintptr_t>(L.p.img) & 15) == 0) {
+      static bool configured_tma = false;
+      if (!configured_tma) {
+        FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_first_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
+        configured_tma = true;
+      }
+      // tensor map over the caller's fp32 NCHW frames (a pure host-side encode, redone per launch: the pointer changes)
+      const ConvParams& p = L.p;
+      CUtensorMap tmImg;
+      cuuint64_t dims[4] = {(cuuint64_t)p.Win, (cuuint64_t)p.Hin, 3, (cuuint64_t)p.N};
+      cuuint64_t strides[3] = {(cuuint64_t)p.Win * 4, (cuuint64_t)p.Hin * p.Win * 4, (cuuint64_t)3 * p.Hin * p.Win * 4};
+      cuuint32_t box[4] = {FT_PATCH_W, FT_PATCH_H, 3, 1};
+      cuuint32_t estr[4] = {1, 1, 1, 1};
+      CUresult r = get_encode()(&tmImg, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(p.img), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      FRCNN_REQUIRE(r == CUDA_SUCCESS, FRCNN_E_CUDA, "cuTensorMapEncodeTiled(frame) failed, CUresult " + std::to_string((int)r));
+      conv_first_tma_kernel<<<L.grid, FT_THREADS, FT_SMEM, st>>>(tmImg, grp, L.w_first);
+      FRCNN_CUDA_TRY(cudaGetLastError());
+      return;
+    }
     conv_first_kernel<<<L.grid, FIRST_THREADS, FIRST_SMEM, st>>>(L.tmOut, grp, L.w_first);
     FRCNN_CUDA_TRY(cudaGetLastError());
     return;
