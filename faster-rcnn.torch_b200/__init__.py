@@ -12,3 +12,4 @@ from .models import Model, create_model, duplo_cfg, imgnet_cfg, vgg_large, vgg_s
 from .detector import Detector, DetectorPipeline, extract_roi_pooling_input  # noqa: F401
 from .shard import reduce_timing, shard_frames, shard_segments  # noqa: F401
 from .objective import allreduce_gradient, clean_anchors, create_objective  # noqa: F401
+from .optim import rmsprop, rmsprop_step  # noqa: F401

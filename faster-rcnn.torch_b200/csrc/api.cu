@@ -12,6 +12,7 @@
 #include "detect.h"
 #include "nms.h"
 #include "train.h"
+#include "label.h"
 
 namespace frcnn {
 
@@ -442,6 +443,17 @@ static const float* P(frcnn_ctx* c, int idx) { return idx >= 0 ? c->bound[idx] :
 
 #define REQUIRE_DEVICE(c) FRCNN_REQUIRE((c)->device >= 0, FRCNN_E_CUDA, "host-only context: no CUDA device (there is no CPU fallback)")
 
+// the anchor LUTs (Anchors.lua:18-19) in device memory; the host vectors are built at plan time
+static void ensure_luts_dev(frcnn_ctx* c) {
+  if (c->d_w_lut) return;
+  FRCNN_REQUIRE(!c->w_lut.empty(), FRCNN_E_STATE, "frcnn_model_plan must be called first");
+  FRCNN_CUDA_TRY(cudaMalloc(&c->d_w_lut, c->w_lut.size() * sizeof(float)));
+  FRCNN_CUDA_TRY(cudaMalloc(&c->d_h_lut, c->h_lut.size() * sizeof(float)));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_w_lut, c->w_lut.data(), c->w_lut.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_h_lut, c->h_lut.data(), c->h_lut.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+}
+
 static void do_pack(frcnn_ctx* c) {
   REQUIRE_DEVICE(c);
   FRCNN_REQUIRE(c->planned, FRCNN_E_STATE, "frcnn_model_plan must be called first");
@@ -476,12 +488,7 @@ static void do_pack(frcnn_ctx* c) {
     else launch_pack_fc_weight(P(c, f.p_w), f.w_packed, f.nout, f.nin, 1, 0, c->stream);
     ++c->launches;
   }
-  if (!c->d_w_lut) {
-    FRCNN_CUDA_TRY(cudaMalloc(&c->d_w_lut, c->w_lut.size() * sizeof(float)));
-    FRCNN_CUDA_TRY(cudaMalloc(&c->d_h_lut, c->h_lut.size() * sizeof(float)));
-    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_w_lut, c->w_lut.data(), c->w_lut.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_h_lut, c->h_lut.data(), c->h_lut.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  }
+  ensure_luts_dev(c);
   FRCNN_CUDA_TRY(cudaGetLastError());
   FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));  // the LUT host vectors / caller buffers may change afterwards
   ++c->weights_gen;
@@ -1984,6 +1991,110 @@ int frcnn_set_detect_thresholds(frcnn_ctx* c, double fg_prob, float nms_proposal
   if (!c) return FRCNN_E_INVALID;
   c->thr_fg = fg_prob; c->thr_nms1 = nms_proposals; c->thr_class = class_prob; c->thr_nms2 = nms_classes;
   return FRCNN_OK;
+}
+
+int frcnn_find_positive(frcnn_ctx* c, const double* rois_host, int n_rois, const double* clip_host, double pos_threshold,
+                        double neg_threshold, int include_best, frcnn_anchor_ref* out_host, int* out_roi_host, int cap, int* n_out) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(n_out != nullptr && cap >= 0 && n_rois >= 0 && (n_rois == 0 || rois_host), FRCNN_E_INVALID, "bad argument");
+  *n_out = 0;
+  if (n_rois > 0) {
+    frcnn::ensure_luts_dev(c);
+    const int n_scales = (int)c->w_lut.size() / (3 * frcnn::LUT_CELLS * 2);
+    FRCNN_REQUIRE(n_scales * 3 <= frcnn::MAX_LABEL_IJ, FRCNN_E_INVALID, "find_positive: at most 4 scales");
+    const int cap_roi = 16384;
+    const size_t b_rois = ((size_t)n_rois * 4 * sizeof(double) + 255) & ~size_t(255);
+    const size_t b_out = (size_t)n_rois * cap_roi * sizeof(frcnn_anchor_ref);
+    const size_t b_cnt = (((size_t)n_rois + 1) * sizeof(int) + 255) & ~size_t(255);
+    uint8_t* mem = (uint8_t*)frcnn::ensure_scratch(c, b_rois + 2 * b_out + b_cnt);
+    frcnn::FindPositiveParams p;
+    p.w_lut = c->d_w_lut; p.h_lut = c->d_h_lut; p.n_scales = n_scales;
+    p.rois = (const double*)mem;
+    p.out = (frcnn_anchor_ref*)(mem + b_rois);
+    p.best_scratch = (frcnn_anchor_ref*)(mem + b_rois + b_out);
+    p.n_out = (int*)(mem + b_rois + 2 * b_out);
+    p.status = p.n_out + n_rois;
+    p.cap_per_roi = cap_roi;
+    p.has_clip = clip_host != nullptr;
+    for (int k = 0; k < 4; ++k) p.clip[k] = clip_host ? clip_host[k] : 0.0;
+    p.pos_threshold = pos_threshold; p.neg_threshold = neg_threshold; p.include_best = include_best ? 1 : 0;
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(mem, rois_host, (size_t)n_rois * 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    FRCNN_CUDA_TRY(cudaMemsetAsync(p.status, 0, sizeof(int), c->stream));
+    frcnn::launch_find_positive(p, n_rois, c->stream);
+    ++c->launches;
+    std::vector<int> counts(n_rois + 1);
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(counts.data(), p.n_out, ((size_t)n_rois + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    FRCNN_REQUIRE(counts[n_rois] == 0, FRCNN_E_OVERFLOW, "find_positive: more than 16384 matches for one ROI");
+    long total = 0;
+    for (int r = 0; r < n_rois; ++r) total += counts[r];
+    FRCNN_REQUIRE(total <= cap, FRCNN_E_OVERFLOW, "find_positive: more matches than the output capacity");
+    FRCNN_REQUIRE(total == 0 || (out_host && out_roi_host), FRCNN_E_INVALID, "null output");
+    int at = 0;
+    for (int r = 0; r < n_rois; ++r) {
+      if (!counts[r]) continue;
+      FRCNN_CUDA_TRY(cudaMemcpyAsync(out_host + at, p.out + (size_t)r * cap_roi, (size_t)counts[r] * sizeof(frcnn_anchor_ref),
+                                     cudaMemcpyDeviceToHost, c->stream));
+      for (int i = 0; i < counts[r]; ++i) out_roi_host[at + i] = r;
+      at += counts[r];
+    }
+    FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *n_out = at;
+  }
+  API_END(c)
+}
+
+int frcnn_sample_negative(frcnn_ctx* c, const double image_rect[4], const double* rois_host, int n_rois, double neg_threshold, int count,
+                          const uint32_t* rnd_host, int n_trials, frcnn_anchor_ref* out_host, int cap, int* n_out, int* trials_consumed,
+                          int* finished) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(image_rect && n_out && trials_consumed && finished && cap >= 0 && n_rois >= 0 && n_trials >= 0 &&
+                    (n_rois == 0 || rois_host) && (n_trials == 0 || rnd_host),
+                FRCNN_E_INVALID, "bad argument");
+  frcnn::ensure_luts_dev(c);
+  const int n_scales = (int)c->w_lut.size() / (3 * frcnn::LUT_CELLS * 2);
+  FRCNN_REQUIRE(n_scales * 3 <= frcnn::MAX_LABEL_IJ, FRCNN_E_INVALID, "sample_negative: at most 4 scales");
+  const size_t b_rois = ((size_t)std::max(n_rois, 1) * 4 * sizeof(double) + 255) & ~size_t(255);
+  const size_t b_rnd = ((size_t)std::max(n_trials, 1) * 3 * sizeof(uint32_t) + 255) & ~size_t(255);
+  const size_t b_out = ((size_t)std::max(cap, 1) * sizeof(frcnn_anchor_ref) + 255) & ~size_t(255);
+  uint8_t* mem = (uint8_t*)frcnn::ensure_scratch(c, b_rois + b_rnd + b_out + 256);
+  frcnn::SampleNegativeParams p;
+  p.w_lut = c->d_w_lut; p.h_lut = c->d_h_lut; p.n_scales = n_scales;
+  for (int k = 0; k < 4; ++k) p.image_rect[k] = image_rect[k];
+  p.rois = (const double*)mem; p.n_rois = n_rois; p.neg_threshold = neg_threshold; p.count = count;
+  p.rnd = (const uint32_t*)(mem + b_rois); p.n_trials = n_trials;
+  p.out = (frcnn_anchor_ref*)(mem + b_rois + b_rnd); p.cap = cap;
+  p.result = (int*)(mem + b_rois + b_rnd + b_out);
+  if (n_rois) FRCNN_CUDA_TRY(cudaMemcpyAsync(mem, rois_host, (size_t)n_rois * 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (n_trials) FRCNN_CUDA_TRY(cudaMemcpyAsync(mem + b_rois, rnd_host, (size_t)n_trials * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+  frcnn::launch_sample_negative(p, c->stream);
+  ++c->launches;
+  int res[4];
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(res, p.result, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  FRCNN_REQUIRE(res[0] == 0 || out_host, FRCNN_E_INVALID, "null output");
+  if (res[0]) FRCNN_CUDA_TRY(cudaMemcpy(out_host, p.out, (size_t)res[0] * sizeof(frcnn_anchor_ref), cudaMemcpyDeviceToHost));
+  *n_out = res[0];
+  *trials_consumed = res[1];
+  *finished = res[2];
+  FRCNN_REQUIRE(count <= cap || res[0] < cap, FRCNN_E_OVERFLOW, "sample_negative: output capacity smaller than count");
+  API_END(c)
+}
+
+int frcnn_rmsprop_step(frcnn_ctx* c, float* weights_dev, float* gradient_dev, float* state_m_dev, int64_t n, double grad_div, double lr,
+                       double alpha, double epsilon, double weight_decay) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(weights_dev && gradient_dev && state_m_dev && n >= 0, FRCNN_E_INVALID, "null argument");
+  FRCNN_REQUIRE(grad_div != 0.0, FRCNN_E_INVALID, "grad_div must be non-zero (pass 1 for no division)");
+  if (n > 0) {
+    frcnn::launch_rmsprop_step(weights_dev, gradient_dev, state_m_dev, (long)n, grad_div, lr, alpha, epsilon, weight_decay, c->sm_count,
+                               c->stream);
+    ++c->launches;
+  }
+  API_END(c)
 }
 
 int frcnn_set_schedule(frcnn_ctx* c, int schedule) {

@@ -59,6 +59,41 @@ class Anchors:
         r.index = ((aspect * 6 - 5, aspect * 6), y, x)
         return r
 
+    def findPositive(self, roi_list, clip_rect, pos_threshold, neg_threshold, include_best):  # Anchors.lua:147-195
+        """roi_list: list of dicts with 'rect' (Rect).  Returns [(anchor_rect, roi), ...] in the reference's order; the
+        nested loops over anchors x ROIs run in one CUDA launch (frcnn_find_positive), one CTA per ROI."""
+        n = len(roi_list)
+        if n == 0:
+            return []
+        rois = np.ascontiguousarray([list(r["rect"].unpack()) for r in roi_list], dtype=np.float64).reshape(-1)
+        clip = ffi.new("double[4]", list(clip_rect.unpack())) if clip_rect is not None else ffi.NULL
+        cap = 1 << 16
+        while True:
+            out, out_roi, n_out = ffi.new("frcnn_anchor_ref[]", cap), ffi.new("int[]", cap), ffi.new("int*")
+            rc = lib().frcnn_find_positive(self.model.ctx, ffi.cast("const double*", rois.ctypes.data), n, clip, pos_threshold,
+                                           neg_threshold, 1 if include_best else 0, out, out_roi, cap, n_out)
+            if rc == 6 and cap < (1 << 22):  # FRCNN_E_OVERFLOW: more matches than the buffer
+                cap *= 4
+                continue
+            check(self.model.ctx, rc)
+            break
+        return [(self.get(out[i].layer, out[i].aspect, out[i].y, out[i].x), roi_list[out_roi[i]]) for i in range(n_out[0])]
+
+    def sampleNegative(self, image_rect, roi_list, neg_threshold, count, rnd):  # Anchors.lua:197-235
+        """`rnd`: numpy uint32 array of torch.random() values, three per trial (the RNG contract: the caller owns the
+        generator).  Returns ([(anchor_rect,), ...], trials consumed, finished)."""
+        rnd = np.ascontiguousarray(rnd, dtype=np.uint32)
+        n_trials = len(rnd) // 3
+        rois = np.ascontiguousarray([list(r["rect"].unpack()) for r in roi_list], dtype=np.float64).reshape(-1)
+        img = ffi.new("double[4]", list(image_rect.unpack()))
+        cap = max(count, 1)
+        out = ffi.new("frcnn_anchor_ref[]", cap)
+        n_out, used, fin = ffi.new("int*"), ffi.new("int*"), ffi.new("int*")
+        check(self.model.ctx, lib().frcnn_sample_negative(self.model.ctx, img, ffi.cast("const double*", rois.ctypes.data) if len(roi_list) else ffi.NULL,
+                                                          len(roi_list), neg_threshold, count, ffi.cast("const uint32_t*", rnd.ctypes.data),
+                                                          n_trials, out, cap, n_out, used, fin))
+        return [(self.get(out[i].layer, out[i].aspect, out[i].y, out[i].x),) for i in range(n_out[0])], used[0], bool(fin[0])
+
     @staticmethod
     def inputToAnchor(anchor, rect):  # Anchors.lua:237-243
         return np.array([(rect.minX - anchor.minX) / anchor.width(), (rect.minY - anchor.minY) / anchor.height(),

@@ -176,4 +176,75 @@ function M.train_image(model, img, positives, negatives, seed)
   return losses[0], losses[1], losses[2], losses[3]
 end
 
+-- Anchors:findPositive (Anchors.lua:147-195) as one launch.  `anchors` is the reference's own Anchors object (its :get
+-- builds the returned rects); returns { {anchor_rect, roi}, ... } in the reference's order.
+function M.find_positive(model, anchors, roi_list, clip_rect, pos_threshold, neg_threshold, include_best)
+  local ctx, n = model.b200.ctx, #roi_list
+  if n == 0 then return {} end
+  local rois = ffi.new('double[?]', 4 * n)
+  for i, roi in ipairs(roi_list) do
+    local r = roi.rect
+    rois[4 * i - 4], rois[4 * i - 3], rois[4 * i - 2], rois[4 * i - 1] = r.minX, r.minY, r.maxX, r.maxY
+  end
+  local clip = nil
+  if clip_rect then clip = ffi.new('double[4]', clip_rect.minX, clip_rect.minY, clip_rect.maxX, clip_rect.maxY) end
+  local cap = 65536
+  local out, out_roi, cnt = ffi.new('frcnn_anchor_ref[?]', cap), ffi.new('int[?]', cap), ffi.new('int[1]')
+  check(ctx, C.frcnn_find_positive(ctx, rois, n, clip, pos_threshold, neg_threshold, include_best and 1 or 0, out, out_roi, cap, cnt))
+  local matches = {}
+  for i = 0, cnt[0] - 1 do
+    matches[i + 1] = { anchors:get(out[i].layer, out[i].aspect, out[i].y, out[i].x), roi_list[out_roi[i] + 1] }
+  end
+  return matches
+end
+
+-- Anchors:sampleNegative (Anchors.lua:197-235).  The generator stays in Lua: three torch.random() values per trial are
+-- drawn here and handed over; the reference consumes exactly `used` trials, so over-drawn values are discarded only
+-- when the caller does not care about stream equality (pass `exact_stream = true` to draw trial by trial instead).
+function M.sample_negative(model, anchors, image_rect, roi_list, neg_threshold, count)
+  local ctx, n = model.b200.ctx, #roi_list
+  local rois = ffi.new('double[?]', math.max(4 * n, 1))
+  for i, roi in ipairs(roi_list) do
+    local r = roi.rect
+    rois[4 * i - 4], rois[4 * i - 3], rois[4 * i - 2], rois[4 * i - 1] = r.minX, r.minY, r.maxX, r.maxY
+  end
+  local img = ffi.new('double[4]', image_rect.minX, image_rect.minY, image_rect.maxX, image_rect.maxY)
+  local neg, out = {}, ffi.new('frcnn_anchor_ref[?]', math.max(count, 1))
+  local cnt, used, fin = ffi.new('int[1]'), ffi.new('int[1]'), ffi.new('int[1]')
+  local need = count
+  repeat
+    local trials = need + 500
+    local rnd = ffi.new('uint32_t[?]', 3 * trials)
+    for i = 0, 3 * trials - 1 do rnd[i] = torch.random() end
+    check(ctx, C.frcnn_sample_negative(ctx, img, rois, n, neg_threshold, need, rnd, trials, out, need, cnt, used, fin))
+    for i = 0, cnt[0] - 1 do neg[#neg + 1] = { anchors:get(out[i].layer, out[i].aspect, out[i].y, out[i].x) } end
+    need = need - cnt[0]
+  until fin[0] == 1 or need <= 0
+  return neg
+end
+
+-- gradient:div(cls_count) (objective.lua:200) + optim.rmsprop (main.lua:122,133) as one fused pass over the flat
+-- CudaTensors; state.m is created zeroed on first use like optim.rmsprop does.
+function M.rmsprop_step(model, weights, gradient, state, cls_count)
+  state.m = state.m or weights.new(weights:size()):zero()
+  check(model.b200.ctx, C.frcnn_rmsprop_step(model.b200.ctx, weights:data(), gradient:data(), state.m:data(), weights:nElement(),
+                                             cls_count or 1, state.learningRate or 1e-2, state.alpha or 0.99,
+                                             state.epsilon or 1e-8, state.weightDecay or 0))
+  M.pack(model)
+end
+
+-- Detector:detect in two halves (several frames in flight: one accelerated model / context per frame)
+function M.detect_begin(model, img)
+  local x = img:float():contiguous()
+  model.b200.pending = x                                   -- keep the host frame alive until detect_end
+  check(model.b200.ctx, C.frcnn_detect_begin(model.b200.ctx, x:data(), 0, 1, x:size(2), x:size(3)))
+end
+function M.detect_end(model, out, cap, cnt)
+  check(model.b200.ctx, C.frcnn_detect_end(model.b200.ctx, out, cap, cnt))
+  model.b200.pending = nil
+end
+function M.set_schedule(model, throughput)
+  check(model.b200.ctx, C.frcnn_set_schedule(model.b200.ctx, throughput and C.FRCNN_SCHED_THROUGHPUT or C.FRCNN_SCHED_LATENCY))
+end
+
 return M

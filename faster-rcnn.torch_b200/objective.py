@@ -26,9 +26,11 @@ def allreduce_gradient(gradient, counters, dist=None):
     return gradient, buf[gradient.numel():].clone()
 
 
-def create_objective(model, dist=None):
+def create_objective(model, dist=None, defer_div=False):
     """Returns lossAndGradient(batch, seed) -> (loss, gradient, stats); batch = list of dicts {img [3][H][W] tensor,
-    positive [(anchor, roi)], negative [(anchor,)]} as BatchIterator:nextTraining yields them (this rank's share)."""
+    positive [(anchor, roi)], negative [(anchor,)]} as BatchIterator:nextTraining yields them (this rank's share).
+    defer_div: leave gradient:div(cls_count) (objective.lua:200) to the fused optimiser pass (optim.rmsprop_step's
+    grad_div = stats['deferred_div'])."""
 
     def lossAndGradient(batch, seed=0):
         model.zero_grad()                                   # gradient:zero()
@@ -49,9 +51,10 @@ def create_objective(model, dist=None):
         gradient, c = allreduce_gradient(model.gradient, [sums["cls"], sums["reg"], sums["creg"], sums["ccls"], cls_count,
                                                            reg_count, ccls_count], dist)
         c = c.tolist()
-        gradient.div_(max(c[4], 1.0))                        # gradient:div(cls_count)
+        if not defer_div:
+            gradient.div_(max(c[4], 1.0))                    # gradient:div(cls_count)
         stats = dict(pcls=c[0] / max(c[4], 1.0), preg=c[1] / max(c[5], 1.0), dcls=c[3] / max(c[6], 1.0), dreg=c[2] / max(c[5], 1.0),
-                     cls_count=int(c[4]), reg_count=int(c[5]))
+                     cls_count=int(c[4]), reg_count=int(c[5]), deferred_div=max(c[4], 1.0) if defer_div else 1.0)
         return stats["pcls"] + stats["preg"], gradient, stats
 
     return lossAndGradient

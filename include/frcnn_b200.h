@@ -250,6 +250,40 @@ int frcnn_last_timings(const frcnn_ctx* ctx, float ms[6]);
  * the last detect call (bench.py's roofline figure). */
 int frcnn_last_conv_profile(const frcnn_ctx* ctx, float* ms, double* flops, int* launches);
 
+/* ---- anchor labelling: replaces Anchors:findPositive / Anchors:sampleNegative (Anchors.lua:147-235; called per
+ *      training image by BatchIterator.lua:200-225) -- SURVEY 8f row 1 ------------------------------------------ */
+typedef struct frcnn_anchor_ref {
+  int layer, aspect, y, x; /* the arguments of Anchors:get (Anchors.lua:60-67), 1-based */
+} frcnn_anchor_ref;
+/* rois_host: n_rois ground-truth rects {minX, minY, maxX, maxY} (doubles); clip_host: 4 doubles or NULL.  Writes the
+ * match list in the reference's order -- ROI by ROI; inside a ROI the anchors with IoU > pos_threshold in
+ * enumeration order (scale, aspect, y, x), or, when there is none and include_best, the best set of
+ * Anchors.lua:171-186 -- as (anchor, roi index 0-based) pairs.  Bit-exact vs the reference's loops: float32 LUT
+ * entries read as doubles, Rect.IoU in double. */
+int frcnn_find_positive(frcnn_ctx* ctx, const double* rois_host, int n_rois, const double* clip_host,
+                        double pos_threshold, double neg_threshold, int include_best, frcnn_anchor_ref* out_host,
+                        int* out_roi_host, int cap, int* n_out);
+/* Anchors:sampleNegative(image_rect, roi_list, neg_threshold, count).  The reference draws three torch.random()
+ * values per trial (range, x, y); the caller supplies that stream: rnd_host holds 3 * n_trials uint32 values.  Returns
+ * the accepted anchors in order, how many trials the loop consumed (so the caller can keep its generator in step) and
+ * whether the loop's own stopping rule fired (count reached, or 500 consecutive rejections) before the supplied
+ * stream ran out (*finished == 0: call again with more random numbers). */
+int frcnn_sample_negative(frcnn_ctx* ctx, const double image_rect[4], const double* rois_host, int n_rois,
+                          double neg_threshold, int count, const uint32_t* rnd_host, int n_trials,
+                          frcnn_anchor_ref* out_host, int cap, int* n_out, int* trials_consumed, int* finished);
+
+/* ---- optimiser step on the flat buffers: replaces gradient:div(cls_count) (objective.lua:200) + optim.rmsprop
+ *      (main.lua:122,133) -- SURVEY 8f row 3 ------------------------------------------------------------------ */
+/* One fused pass over the three flat device buffers of n floats (16-byte aligned): g /= grad_div (1 = no division);
+ * [g += weight_decay * w]; m = alpha * m + (1 - alpha) * g * g; w += -lr * g / (sqrt(m) + epsilon) -- the statement
+ * sequence of optim.rmsprop (an un-vendored dependency; restated, see oracle/optim.py), every operation rounded to
+ * fp32 on its own.  state_m_dev is rmsprop_state.m (zero before the first step).  Asynchronous on the ctx stream;
+ * call frcnn_pack_weights afterwards.
+ * The scalars are doubles as in Lua and are rounded to fp32 where TH does: -lr, alpha, (1.0 - alpha) [evaluated in
+ * double first], epsilon, weight_decay, grad_div. */
+int frcnn_rmsprop_step(frcnn_ctx* ctx, float* weights_dev, float* gradient_dev, float* state_m_dev, int64_t n,
+                       double grad_div, double lr, double alpha, double epsilon, double weight_decay);
+
 /* ---- low-level conv / GEMM entry (tests, roofline measurement) ---------------------------------------- */
 /* y = prelu(conv(x, w) + bias) * scale on NHWC bf16 activations (passed as uint16 bit patterns).
  * x_dev: [n][h][w][cin]; w_dev: fp32 Torch layout [cout][cin][k][k]; out_dev: [n][ho][wo][cout] bf16, or with

@@ -126,6 +126,31 @@ class Anchors:
                     matches.append((v, roi))
         return matches
 
+    def sampleNegative(self, image_rect, roi_list, neg_threshold, count, rnd):  # Anchors.lua:197-235
+        """`rnd`: iterator over the values torch.random() returns (uint32): three per trial (range, x, y).  Returns the
+        accepted anchors and the number of trials run."""
+        ranges = self.findRangesXY(image_rect, image_rect)
+        neg, retry, trials = [], 0, 0
+        rnd = iter(rnd)
+        while len(neg) < count and retry < 500:
+            try:
+                r1, r2, r3 = int(next(rnd)), int(next(rnd)), int(next(rnd))
+            except StopIteration:
+                break
+            trials += 1
+            r = ranges[r1 % len(ranges)]
+            x = r2 % r["xs"].shape[0] + 1
+            y = r3 % r["ys"].shape[0] + 1
+            a = Rect(r["xs"][x - 1, 0], r["ys"][y - 1, 0], r["xs"][x - 1, 1], r["ys"][y - 1, 1])
+            a.layer, a.aspect = r["layer"], r["aspect"]
+            a.index = ((a.aspect * 6 - 5, a.aspect * 6), r["ly"] + y - 1, r["lx"] + x - 1)
+            if any(Rect.IoU(roi["rect"], a) > neg_threshold for roi in roi_list):
+                retry += 1
+            else:
+                retry = 0
+                neg.append((a,))
+        return neg, trials
+
     @staticmethod
     def inputToAnchor(anchor, rect):  # Anchors.lua:237-243 -> FloatTensor(4)
         x = (rect.minX - anchor.minX) / anchor.width()
