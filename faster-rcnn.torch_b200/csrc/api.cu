@@ -118,6 +118,9 @@ struct frcnn_ctx {
   const float* train_img = nullptr;
   // objective.lua stage buffers (frcnn_train_image), sized for cw_rows examples
   int cw_rows = 0;
+  int cw_n = 0;                    // frames the per-frame objective buffers (head_dout, losses_dev) are sized for
+  long cw_gen = -1;                // pnet workspace generation they were sized against
+  float* losses_cur = nullptr;     // the 8-float loss slot of the frame being processed
   std::vector<void*> cw_allocs;
   ExampleDev* ex_dev = nullptr;
   double* ex_rects = nullptr;
@@ -885,7 +888,9 @@ static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out, bool keep_
 
 // ---------------------------------------------------------------------------------------------- objective.lua stage
 static void ensure_objective_workspace(frcnn_ctx* c, int rows) {
-  if (rows <= c->cw_rows && !c->head_dout.empty()) return;
+  const int NF = std::max(1, c->ws_n);
+  if (rows <= c->cw_rows && !c->head_dout.empty() && c->cw_n >= NF && c->cw_gen == c->ws_gen) return;
+  rows = std::max(rows, c->cw_rows);
   FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   free_all(c->cw_allocs);
   c->cw_rows = 0;
@@ -896,7 +901,8 @@ static void ensure_objective_workspace(frcnn_ctx* c, int rows) {
   c->ex_rects = (double*)dev_alloc(A, (size_t)R * 4 * sizeof(double));
   c->crtarget = (float*)dev_alloc(A, (size_t)R * 4 * sizeof(float));
   c->cctarget = (int*)dev_alloc(A, (size_t)R * sizeof(int));
-  c->losses_dev = (float*)dev_alloc(A, 8 * sizeof(float));
+  c->losses_dev = (float*)dev_alloc(A, (size_t)NF * 8 * sizeof(float));
+  c->losses_cur = c->losses_dev;
   c->t_status = (int*)dev_alloc(A, 4 * sizeof(int));
   c->t_rows = (bf16*)dev_alloc(A, (size_t)R * feat * sizeof(bf16));
   c->t_argmax = (int*)dev_alloc(A, (size_t)R * feat * sizeof(int));
@@ -920,8 +926,10 @@ static void ensure_objective_workspace(frcnn_ctx* c, int rows) {
     f.dw_taps = (float*)dev_alloc(A, (size_t)f.nin * f.nout * sizeof(float));
   }
   c->head_dout.clear();
-  for (auto& hd : c->heads) c->head_dout.push_back((float*)dev_alloc(A, (size_t)18 * hd.hh * hd.hw * sizeof(float)));
+  for (auto& hd : c->heads) c->head_dout.push_back((float*)dev_alloc(A, (size_t)NF * 18 * hd.hh * hd.hw * sizeof(float)));
   c->cw_rows = R;
+  c->cw_n = NF;
+  c->cw_gen = c->ws_gen;
 }
 
 // [R][nin] bf16 rows x [nout][nin] bf16 weights -> fp32 [R][nout].  Few output tiles with a long K (fc1: 8 tiles,
@@ -979,7 +987,7 @@ static void run_cnet_train(frcnn_ctx* c, int R, int n_pos, const float* const* c
   cl.crtarget = c->crtarget; cl.cctarget = c->cctarget; cl.R = R; cl.n_pos = n_pos; cl.nin = last.nout; cl.ncls = c->class_count + 1;
   cl.d_hidden = c->t_dhidden; cl.dz = c->t_dz;
   cl.g_w_reg = G(c, c->p_reg_w); cl.g_b_reg = G(c, c->p_reg_b); cl.g_w_cls = G(c, c->p_cls_w); cl.g_b_cls = G(c, c->p_cls_b);
-  cl.losses = c->losses_dev;
+  cl.losses = c->losses_cur;
   launch_cnet_loss_bwd(cl, st);
   c->launches += 2;
   // ---- cnet backward (objective.lua:179)
@@ -1005,66 +1013,89 @@ static void run_cnet_train(frcnn_ctx* c, int R, int n_pos, const float* const* c
   }
 }
 
-static void do_train_image(frcnn_ctx* c, const float* img_dev, int H, int W, const frcnn_example* pos, int n_pos,
-                           const frcnn_example* neg, int n_neg, const float* const* pnet_masks, const float* const* cnet_masks,
-                           uint64_t seed, float losses_host[4]) {
+// The per-image loop of lossAndGradient (objective.lua:65-198) for N frames of one size: pnet forward (training) and
+// pnet:backward run ONCE over the whole batch (the conv kernels then work at batch efficiency and every elementwise
+// backward kernel is launched once instead of N times); the criteria, the ROI pooling and the cnet stage -- whose
+// BatchNormalization sees the ROI batch of ONE image (objective.lua:164 sits inside the per-image loop) -- run frame
+// by frame in between, each writing its own slice of delta_outputs.  One host synchronisation per batch.
+static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int W, const frcnn_example* const* pos, const int* n_pos,
+                           const frcnn_example* const* neg, const int* n_neg, const float* const* pnet_masks,
+                           const float* const* cnet_masks, const uint64_t* seeds, float* losses_host /* [N][4] */) {
   static_assert(sizeof(frcnn_example) == sizeof(ExampleDev), "example layouts must match");
   FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called first");
   for (auto g : c->grads) FRCNN_REQUIRE(g != nullptr, FRCNN_E_STATE, "frcnn_bind_grads must be called first");
-  const int R = n_pos + n_neg;
+  FRCNN_REQUIRE(N >= 1 && N <= 64, FRCNN_E_INVALID, "train: 1..64 frames per call");
+  FRCNN_REQUIRE(cnet_masks == nullptr || N == 1, FRCNN_E_INVALID, "explicit cnet masks are a single-frame (test) facility");
+  int Rmax = 0;
+  for (int n = 0; n < N; ++n) Rmax = std::max(Rmax, n_pos[n] + n_neg[n]);
   cudaStream_t st = c->stream;
-  ensure_pnet_workspace(c, 1, H, W);
-  ensure_train_workspace(c, 1, H, W);
-  ensure_objective_workspace(c, R);
+  ensure_pnet_workspace(c, N, H, W);
+  ensure_train_workspace(c, N, H, W);
+  ensure_objective_workspace(c, Rmax);
   // ---- pnet forward, training mode (objective.lua:60,71)
   int mi = 0;
   for (auto& cv : c->trunk) {
     if (cv.dropout <= 0.f) continue;
-    if (pnet_masks && pnet_masks[mi]) FRCNN_CUDA_TRY(cudaMemcpyAsync(cv.mask, pnet_masks[mi], cv.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    else launch_dropout_mask(cv.mask, cv.cout, cv.dropout, seed, (uint32_t)mi, st);
+    if (pnet_masks && pnet_masks[mi]) {
+      FRCNN_CUDA_TRY(cudaMemcpyAsync(cv.mask, pnet_masks[mi], (size_t)N * cv.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+      for (int n = 0; n < N; ++n) launch_dropout_mask(cv.mask + (size_t)n * cv.cout, cv.cout, cv.dropout, seeds[n], (uint32_t)mi, st);
+    }
     ++mi;
   }
-  do_pnet_forward(c, img_dev, 1, H, W, true);
-  FRCNN_CUDA_TRY(cudaMemsetAsync(c->losses_dev, 0, 8 * sizeof(float), st));
+  do_pnet_forward(c, img_dev, N, H, W, true);
+  FRCNN_CUDA_TRY(cudaMemsetAsync(c->losses_dev, 0, (size_t)N * 8 * sizeof(float), st));
   FRCNN_CUDA_TRY(cudaMemsetAsync(c->t_status, 0, 4 * sizeof(int), st));
   for (size_t i = 0; i < c->heads.size(); ++i)
-    FRCNN_CUDA_TRY(cudaMemsetAsync(c->head_dout[i], 0, (size_t)18 * c->heads[i].hh * c->heads[i].hw * sizeof(float), st));
+    FRCNN_CUDA_TRY(cudaMemsetAsync(c->head_dout[i], 0, (size_t)N * 18 * c->heads[i].hh * c->heads[i].hw * sizeof(float), st));
   zero_block_grads(c);
-  if (R > 0) {
+  const int bins = c->roi_kh * c->roi_kw;
+  const size_t fmap_elems = (size_t)c->feat_h * c->feat_w * c->feat_c;
+  for (int n = 0; n < N; ++n) {
+    const int np = n_pos[n], nn = n_neg[n], R = np + nn;
+    if (R <= 0) continue;
+    c->losses_cur = c->losses_dev + 8 * n;
     // ---- RPN criteria on the listed anchors (objective.lua:91-140)
-    if (n_pos) FRCNN_CUDA_TRY(cudaMemcpyAsync(c->ex_dev, pos, (size_t)n_pos * sizeof(ExampleDev), cudaMemcpyHostToDevice, st));
-    if (n_neg) FRCNN_CUDA_TRY(cudaMemcpyAsync(c->ex_dev + n_pos, neg, (size_t)n_neg * sizeof(ExampleDev), cudaMemcpyHostToDevice, st));
+    if (np) FRCNN_CUDA_TRY(cudaMemcpyAsync(c->ex_dev, pos[n], (size_t)np * sizeof(ExampleDev), cudaMemcpyHostToDevice, st));
+    if (nn) FRCNN_CUDA_TRY(cudaMemcpyAsync(c->ex_dev + np, neg[n], (size_t)nn * sizeof(ExampleDev), cudaMemcpyHostToDevice, st));
     RpnLossParams lp;
-    lp.ex = c->ex_dev; lp.n_pos = n_pos; lp.n_neg = n_neg;
+    lp.ex = c->ex_dev; lp.n_pos = np; lp.n_neg = nn;
     for (int i = 0; i < MAX_HEADS; ++i) {
-      lp.out[i] = c->heads[i].out; lp.d_out[i] = c->head_dout[i]; lp.hh[i] = c->heads[i].hh; lp.hw[i] = c->heads[i].hw;
+      const size_t per = (size_t)18 * c->heads[i].hh * c->heads[i].hw;
+      lp.out[i] = c->heads[i].out + n * per; lp.d_out[i] = c->head_dout[i] + n * per; lp.hh[i] = c->heads[i].hh; lp.hw[i] = c->heads[i].hw;
     }
     lp.crtarget = c->crtarget; lp.cctarget = c->cctarget; lp.bg_class = c->class_count; lp.rects = c->ex_rects;
-    lp.losses = c->losses_dev; lp.status = c->t_status;
+    lp.losses = c->losses_cur; lp.status = c->t_status;
     launch_rpn_loss(lp, st);
     // ---- ROI pooling of ground-truth rects / negative anchors (objective.lua:117-119,137-139)
-    const int bins = c->roi_kh * c->roi_kw, feat = bins * c->feat_c;
-    launch_roi_pool_train(c->pool_out.back(), c->feat_h, c->feat_w, c->feat_c, c->roi_kh, c->roi_kw, c->roi_loc, c->ex_rects, R,
-                          c->t_rows, c->t_argmax, c->t_status + 1, st);
+    launch_roi_pool_train(c->pool_out.back() + n * fmap_elems, c->feat_h, c->feat_w, c->feat_c, c->roi_kh, c->roi_kw, c->roi_loc,
+                          c->ex_rects, R, c->t_rows, c->t_argmax, c->t_status + 1, st);
     c->launches += 2;
-    run_cnet_train(c, R, n_pos, cnet_masks, seed);
+    run_cnet_train(c, R, np, cnet_masks, seeds[n]);
     // ---- ROI-pool backward into delta_outputs[5] (objective.lua:182-185), kept as the fp32 NHWC block gradient
-    launch_roi_pool_bwd(c->t_dx, c->t_argmax, R, bins, c->feat_c, c->dblock.back(), st);
+    launch_roi_pool_bwd(c->t_dx, c->t_argmax, R, bins, c->feat_c, c->dblock.back() + n * fmap_elems, st);
     ++c->launches;
-    (void)feat;
   }
-  // ---- pnet backward (objective.lua:189)
+  c->losses_cur = c->losses_dev;
+  // ---- pnet backward (objective.lua:189), all frames at once
   std::vector<const float*> d_out(c->heads.size() + 1, nullptr);
   for (size_t i = 0; i < c->heads.size(); ++i) d_out[i] = c->head_dout[i];
   do_pnet_backward(c, d_out.data(), true);
-  float lh[8];
+  std::vector<float> lh((size_t)N * 8);
   int sh[4];
-  FRCNN_CUDA_TRY(cudaMemcpyAsync(lh, c->losses_dev, 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(lh.data(), c->losses_dev, (size_t)N * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
   FRCNN_CUDA_TRY(cudaMemcpyAsync(sh, c->t_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
   FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
-  for (int i = 0; i < 4; ++i) losses_host[i] = lh[i];
+  for (int n = 0; n < N; ++n)
+    for (int i = 0; i < 4; ++i) losses_host[4 * n + i] = lh[8 * n + i];
   FRCNN_REQUIRE(sh[0] == 0, FRCNN_E_INVALID, "an example indexes outside its anchor map: apply cleanAnchors first (objective.lua:32-43)");
   FRCNN_REQUIRE(sh[1] == 0, FRCNN_E_ROI_EMPTY, "an ROI clipped to max == 0; the reference raises an index error here (objective.lua:11)");
+}
+
+static void do_train_image(frcnn_ctx* c, const float* img_dev, int H, int W, const frcnn_example* pos, int n_pos,
+                           const frcnn_example* neg, int n_neg, const float* const* pnet_masks, const float* const* cnet_masks,
+                           uint64_t seed, float losses_host[4]) {
+  do_train_batch(c, img_dev, 1, H, W, &pos, &n_pos, &neg, &n_neg, pnet_masks, cnet_masks, &seed, losses_host);
 }
 
 // detector / cnet workspace for a batch of N images
@@ -1749,6 +1780,18 @@ __global__ void unpack_roi_rows_kernel(const float* __restrict__ x, float* __res
   }
 }
 
+int frcnn_train_batch(frcnn_ctx* c, const float* img_dev, int n, int h, int w, const frcnn_example* const* pos_host, const int* n_pos,
+                      const frcnn_example* const* neg_host, const int* n_neg, const float* const* pnet_masks_dev, const uint64_t* seeds,
+                      float* losses_host) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(img_dev && losses_host && pos_host && neg_host && n_pos && n_neg && seeds && n >= 1, FRCNN_E_INVALID, "bad argument");
+  for (int i = 0; i < n; ++i)
+    FRCNN_REQUIRE(n_pos[i] >= 0 && n_neg[i] >= 0 && (n_pos[i] == 0 || pos_host[i]) && (n_neg[i] == 0 || neg_host[i]), FRCNN_E_INVALID,
+                  "bad example list");
+  frcnn::do_train_batch(c, img_dev, n, h, w, pos_host, n_pos, neg_host, n_neg, pnet_masks_dev, nullptr, seeds, losses_host);
+  API_END(c)
+}
+
 int frcnn_cnet_train_step(frcnn_ctx* c, const float* x_dev, int R, int n_pos, const float* crtarget_dev, const int32_t* cctarget_dev,
                           const float* const* masks_dev, uint64_t seed, float* dx_dev, float losses_host[2]) {
   API_BEGIN(c)
@@ -1763,6 +1806,7 @@ int frcnn_cnet_train_step(frcnn_ctx* c, const float* x_dev, int R, int n_pos, co
   FRCNN_CUDA_TRY(cudaMemcpyAsync(c->crtarget, crtarget_dev, (size_t)R * 4 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
   FRCNN_CUDA_TRY(cudaMemcpyAsync(c->cctarget, cctarget_dev, (size_t)R * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
   FRCNN_CUDA_TRY(cudaMemsetAsync(c->losses_dev, 0, 8 * sizeof(float), c->stream));
+  c->losses_cur = c->losses_dev;
   frcnn::run_cnet_train(c, R, n_pos, masks_dev, seed);
   if (dx_dev) unpack_roi_rows_kernel<<<blocks, 256, 0, c->stream>>>(c->t_dx, dx_dev, R, c->feat_c, bins);
   c->launches += 2;

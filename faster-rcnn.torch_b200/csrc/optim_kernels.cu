@@ -1,7 +1,8 @@
 // Fused optimiser step on the flat parameter buffer: replaces `gradient:div(cls_count)` (objective.lua:200) followed by
 // optim.rmsprop(eval_objective_grad, weights, rmsprop_state) (main.lua:122,133) -- in the reference four full passes
 // of TH vector ops over the 26.8 M-float `weights` / `gradient` / state buffers, here ONE pass: 12 bytes read and
-// 8 bytes written per parameter (HBM-bound; 536 MB per step for vgg_small).
+// 8 bytes written per parameter, + 4 for the divided gradient the caller still sees (HBM-bound; 643 MB per step for
+// vgg_small's 26.8 M parameters).
 //
 // optim.rmsprop is an un-vendored dependency; restated from its published algorithm (optim/rmsprop.lua,
 // 2015): [dfdx += wd * x]; m = alpha * m + (1 - alpha) * dfdx^2; tmp = sqrt(m) + epsilon; x += -lr * dfdx / tmp, every
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(256) rmsprop_step_kernel(float* __restrict__ w
       }
       *reinterpret_cast<float4*>(w + i) = wv;
       *reinterpret_cast<float4*>(m + i) = mv;
-      *reinterpret_cast<float4*>(g + i) = gv;   // the caller sees the divided gradient, as after gradient:div
+      if (grad_div != 1.0f || wd != 0.0f) *reinterpret_cast<float4*>(g + i) = gv;   // the caller sees gradient:div / dfdx:add, as in Lua
     } else {
       for (long j = i; j < n; ++j) {
         float d = grad_div != 1.0f ? __fdiv_rn(g[j], grad_div) : g[j];
@@ -44,7 +45,7 @@ __global__ void __launch_bounds__(256) rmsprop_step_kernel(float* __restrict__ w
         const float t = __fadd_rn(__fsqrt_rn(mm), eps);
         w[j] = __fadd_rn(w[j], __fdiv_rn(__fmul_rn(neg_lr, d), t));
         m[j] = mm;
-        g[j] = d;
+        if (grad_div != 1.0f || wd != 0.0f) g[j] = d;
       }
     }
   }

@@ -234,6 +234,51 @@ class Model:
                                                 len(negatives), pm, cm, seed, losses))
         return dict(cls=losses[0], reg=losses[1], creg=losses[2], ccls=losses[3])
 
+    # frcnn_example as a numpy record: the example lists are marshalled with array operations, not per-field cffi writes
+    _EXAMPLE_DTYPE = np.dtype([("anchor", np.float64, 4), ("roi", np.float64, 4), ("reg_target", np.float32, 4), ("layer", np.int32),
+                               ("aspect", np.int32), ("y", np.int32), ("x", np.int32), ("class_index", np.int32), ("pad_", np.int32)])
+
+    @classmethod
+    def pack_examples(cls, examples):
+        """[(anchor, roi)] or [(anchor,)] -> numpy record array laid out as frcnn_example[]."""
+        from .geometry import Anchors
+        arr = np.zeros(max(len(examples), 1), dtype=cls._EXAMPLE_DTYPE)
+        assert arr.dtype.itemsize == ffi.sizeof("frcnn_example")
+        for i, ex in enumerate(examples):
+            a = ex[0]
+            e = arr[i]
+            e["anchor"] = a.unpack()
+            e["layer"], e["aspect"], e["y"], e["x"] = a.layer, a.aspect, a.index[1], a.index[2]
+            if len(ex) > 1 and ex[1] is not None:
+                roi = ex[1]
+                e["roi"] = roi["rect"].unpack()
+                e["reg_target"] = Anchors.inputToAnchor(a, roi["rect"])
+                e["class_index"] = int(roi["class_index"])
+        return arr
+
+    def train_batch(self, imgs, positives, negatives, pnet_masks=None, seeds=None, packed=None):
+        """lossAndGradient's per-image loop (objective.lua:65-198) for a list / stack of frames of ONE size in one call
+        (frcnn_train_batch): pnet forward and backward once over all frames, the per-image stages in between.
+        positives / negatives: one example list per frame (cleaned).  packed: optional pre-marshalled
+        (pos_records, neg_records) per frame from pack_examples.  Returns a list of {cls, reg, creg, ccls} per frame."""
+        x = (imgs if torch.is_tensor(imgs) else torch.stack(list(imgs))).to(self.device, torch.float32).contiguous()
+        n, _, h, w = x.shape
+        if packed is None:
+            packed = [(self.pack_examples(p), self.pack_examples(q)) for p, q in zip(positives, negatives)]
+        n_pos = ffi.new("int[]", [len(p) for p in positives])
+        n_neg = ffi.new("int[]", [len(q) for q in negatives])
+        pp = ffi.new("const frcnn_example*[]", [ffi.cast("const frcnn_example*", a.ctypes.data) for a, _ in packed])
+        qq = ffi.new("const frcnn_example*[]", [ffi.cast("const frcnn_example*", b.ctypes.data) for _, b in packed])
+        sd = ffi.new("uint64_t[]", [int(v) for v in (seeds if seeds is not None else range(n))])
+        keep, pm = [], ffi.NULL
+        if pnet_masks is not None:
+            keep = [m.to(self.device, torch.float32).reshape(n, -1).contiguous() for m in pnet_masks]
+            pm = ffi.new("const float*[]", [ffi.cast("const float*", t.data_ptr()) for t in keep])
+        losses = ffi.new("float[]", 4 * n)
+        torch.cuda.synchronize(self.device)
+        check(self.ctx, lib().frcnn_train_batch(self.ctx, ffi.cast("const float*", x.data_ptr()), n, h, w, pp, n_pos, qq, n_neg, pm, sd, losses))
+        return [dict(cls=losses[4 * i], reg=losses[4 * i + 1], creg=losses[4 * i + 2], ccls=losses[4 * i + 3]) for i in range(n)]
+
     def _cnet_forward(self, x):
         """cnet:forward(cinput) (Detector.lua:101): x [R][kh*kw*C] fp32 -> (bbox [R][4], log-softmax [R][classes+1])."""
         x = x.to(self.device, torch.float32).contiguous()

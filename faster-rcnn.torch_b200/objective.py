@@ -26,9 +26,10 @@ def allreduce_gradient(gradient, counters, dist=None):
     return gradient, buf[gradient.numel():].clone()
 
 
-def create_objective(model, dist=None, defer_div=False):
+def create_objective(model, dist=None, defer_div=False, batched=True):
     """Returns lossAndGradient(batch, seed) -> (loss, gradient, stats); batch = list of dicts {img [3][H][W] tensor,
     positive [(anchor, roi)], negative [(anchor,)]} as BatchIterator:nextTraining yields them (this rank's share).
+    batched: frames of equal size are processed by one frcnn_train_batch call (False: frame by frame, frcnn_train_image).
     defer_div: leave gradient:div(cls_count) (objective.lua:200) to the fused optimiser pass (optim.rmsprop_step's
     grad_div = stats['deferred_div'])."""
 
@@ -38,16 +39,29 @@ def create_objective(model, dist=None, defer_div=False):
         model.cnet.training()
         sums = dict(cls=0.0, reg=0.0, creg=0.0, ccls=0.0)
         cls_count = reg_count = ccls_count = 0
+        # frames of one size go through frcnn_train_batch together (pnet forward / backward once over all of them);
+        # frames of different sizes one by one, as the reference's loop does
+        groups = {}
         for i, x in enumerate(batch):
-            img = x["img"]
-            dims = model.output_dims(img.shape[1], img.shape[2])
-            p, n = clean_anchors(x["positive"], dims), clean_anchors(x["negative"], dims)
-            losses = model.train_image(img, p, n, seed=seed * 1000003 + i)
-            for k in sums:
-                sums[k] += losses[k]
-            reg_count += len(p)
-            cls_count += len(p) + len(n)
-            ccls_count += 1
+            groups.setdefault(tuple(x["img"].shape), []).append(i)
+        for shape, idx in groups.items():
+            dims = model.output_dims(shape[1], shape[2])
+            ps = [clean_anchors(batch[i]["positive"], dims) for i in idx]
+            ns = [clean_anchors(batch[i]["negative"], dims) for i in idx]
+            packed = None
+            if all("packed" in batch[i] for i in idx):   # example records marshalled once by the caller (BatchIterator)
+                packed = [batch[i]["packed"] for i in idx]
+            if len(idx) == 1 and not batched:
+                all_losses = [model.train_image(batch[idx[0]]["img"], ps[0], ns[0], seed=seed * 1000003 + idx[0])]
+            else:
+                all_losses = model.train_batch([batch[i]["img"] for i in idx], ps, ns, seeds=[seed * 1000003 + i for i in idx],
+                                               packed=packed)
+            for losses, p, n in zip(all_losses, ps, ns):
+                for k in sums:
+                    sums[k] += losses[k]
+                reg_count += len(p)
+                cls_count += len(p) + len(n)
+                ccls_count += 1
         gradient, c = allreduce_gradient(model.gradient, [sums["cls"], sums["reg"], sums["creg"], sums["ccls"], cls_count,
                                                            reg_count, ccls_count], dist)
         c = c.tolist()

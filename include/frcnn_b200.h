@@ -161,6 +161,14 @@ int frcnn_pnet_backward(frcnn_ctx* ctx, const float* const* d_out_dev);
 int frcnn_train_image(frcnn_ctx* ctx, const float* img_dev, int h, int w, const frcnn_example* pos_host, int n_pos,
                       const frcnn_example* neg_host, int n_neg, const float* const* pnet_masks_dev,
                       const float* const* cnet_masks_dev, uint64_t seed, float losses_host[4]);
+/* The same for n frames of ONE size in one call (img_dev [n][3][h][w]): pnet forward (training) and pnet:backward run
+ * once over the whole batch, the per-image stages (criteria, ROI pooling, cnet with its per-image BatchNorm statistics,
+ * objective.lua:91-185) frame by frame in between; one host synchronisation.  pos_host / neg_host: n pointers to the
+ * frames' example lists, n_pos / n_neg their lengths, seeds one per frame, losses_host [n][4].  Gradients accumulate
+ * exactly as n calls of frcnn_train_image would (same sums; the tensor-core reductions differ in order). */
+int frcnn_train_batch(frcnn_ctx* ctx, const float* img_dev, int n, int h, int w, const frcnn_example* const* pos_host,
+                      const int* n_pos, const frcnn_example* const* neg_host, const int* n_neg,
+                      const float* const* pnet_masks_dev, const uint64_t* seeds, float* losses_host);
 
 /* cnet:forward(cinput) in training mode + the detection-stage criteria + cnet:backward (objective.lua:164-179).
  * x_dev: [R][kh*kw*C] fp32 (reference ordering), the first n_pos rows are positives; crtarget_dev [R][4];

@@ -26,3 +26,4 @@ for b in 1 8; do
   ls -la /tmp/r1b_full_b$b.ncu-rep gpurun_out/r1b_full_b$b.csv
 done
 du -sh gpurun_out
+timeout 300 python tools/bench_next_rows.py > gpurun_out/r1b_next_rows.jsonl 2>&1; cat gpurun_out/r1b_next_rows.jsonl | cut -c1-400
