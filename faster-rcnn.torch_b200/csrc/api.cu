@@ -121,6 +121,7 @@ struct frcnn_ctx {
   int cw_n = 0;                    // frames the per-frame objective buffers (head_dout, losses_dev) are sized for
   long cw_gen = -1;                // pnet workspace generation they were sized against
   float* losses_cur = nullptr;     // the 8-float loss slot of the frame being processed
+  bool cnet_wgrad_deferred = false; // frcnn_train_batch: cnet weight gradients accumulate in dw_taps over the frames
   std::vector<void*> cw_allocs;
   ExampleDev* ex_dev = nullptr;
   double* ex_rects = nullptr;
@@ -950,8 +951,8 @@ static void gemm_rows(frcnn_ctx* c, const bf16* a, const bf16* w, int R, int nin
   ++c->launches;
 }
 // dW[nout][nin] (fp32 taps buffer, zeroed here) = dy[R][nout]^T x[R][nin]
-static void wgrad_rows(frcnn_ctx* c, const bf16* dy, const bf16* x, int R, int nin, int nout, float* dw) {
-  FRCNN_CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)nin * nout * sizeof(float), c->stream));
+static void wgrad_rows(frcnn_ctx* c, const bf16* dy, const bf16* x, int R, int nin, int nout, float* dw, bool zero = true) {
+  if (zero) FRCNN_CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)nin * nout * sizeof(float), c->stream));
   ConvLaunch L;
   conv_wgrad_prepare(&L, dy, x, dw, 1, 1, R, nin, nout, 1, 1, 0, 0, c->sm_count);
   conv_launch(L, c->stream);
@@ -1002,13 +1003,22 @@ static void run_cnet_train(frcnn_ctx* c, int R, int n_pos, const float* const* c
     fb.R = R; fb.n = f.nout;
     launch_fc_train_bwd(fb, st);
     const bf16* x_in = i == 0 ? c->t_rows : c->fcs[i - 1].t_out;
-    wgrad_rows(c, f.t_dy, x_in, R, f.nin, f.nout, f.dw_taps);
+    // weight gradient: fp32 TMA reduce-add into dw_taps; inside frcnn_train_batch the frames of the batch accumulate
+    // there and the transposition into Torch's layout happens once per batch (cnet_wgrad_finish)
+    wgrad_rows(c, f.t_dy, x_in, R, f.nin, f.nout, f.dw_taps, !c->cnet_wgrad_deferred);
     const bool perm = i == 0;
-    launch_wgrad_finish_fc(f.dw_taps, G(c, f.p_w), f.nout, perm ? c->feat_c : f.nin, perm ? bins : 1, perm ? 1 : 0, st);
-    launch_pack_fc_weight_dgrad(P(c, f.p_w), f.w_dgrad, f.nout, perm ? c->feat_c : f.nin, perm ? bins : 1, perm ? 1 : 0, st);
+    if (!c->cnet_wgrad_deferred) {
+      launch_wgrad_finish_fc(f.dw_taps, G(c, f.p_w), f.nout, perm ? c->feat_c : f.nin, perm ? bins : 1, perm ? 1 : 0, st);
+      ++c->launches;
+    }
+    if (f.dgrad_gen != c->weights_gen) {  // the transposed bf16 weights of the data gradient: once per weight update
+      launch_pack_fc_weight_dgrad(P(c, f.p_w), f.w_dgrad, f.nout, perm ? c->feat_c : f.nin, perm ? bins : 1, perm ? 1 : 0, st);
+      f.dgrad_gen = c->weights_gen;
+      ++c->launches;
+    }
     float* d_prev = i == 0 ? c->t_dx : c->fcs[i - 1].t_din;
     gemm_rows(c, f.t_dy, f.w_dgrad, R, f.nout, f.nin, d_prev);
-    c->launches += 3;
+    ++c->launches;
     d_in = d_prev;
   }
 }
@@ -1051,6 +1061,9 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
   zero_block_grads(c);
   const int bins = c->roi_kh * c->roi_kw;
   const size_t fmap_elems = (size_t)c->feat_h * c->feat_w * c->feat_c;
+  for (auto& f : c->fcs) FRCNN_CUDA_TRY(cudaMemsetAsync(f.dw_taps, 0, (size_t)f.nin * f.nout * sizeof(float), st));
+  c->cnet_wgrad_deferred = true;
+  bool any_rows = false;
   for (int n = 0; n < N; ++n) {
     const int np = n_pos[n], nn = n_neg[n], R = np + nn;
     if (R <= 0) continue;
@@ -1075,6 +1088,16 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
     // ---- ROI-pool backward into delta_outputs[5] (objective.lua:182-185), kept as the fp32 NHWC block gradient
     launch_roi_pool_bwd(c->t_dx, c->t_argmax, R, bins, c->feat_c, c->dblock.back() + n * fmap_elems, st);
     ++c->launches;
+    any_rows = true;
+  }
+  c->cnet_wgrad_deferred = false;
+  if (any_rows) {
+    for (size_t i = 0; i < c->fcs.size(); ++i) {
+      FcLayer& f = c->fcs[i];
+      const bool perm = i == 0;
+      launch_wgrad_finish_fc(f.dw_taps, G(c, f.p_w), f.nout, perm ? c->feat_c : f.nin, perm ? bins : 1, perm ? 1 : 0, st);
+      ++c->launches;
+    }
   }
   c->losses_cur = c->losses_dev;
   // ---- pnet backward (objective.lua:189), all frames at once

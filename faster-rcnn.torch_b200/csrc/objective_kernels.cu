@@ -85,9 +85,11 @@ void launch_rpn_loss(const RpnLossParams& p, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------ training ROI pooling
-__global__ void __launch_bounds__(128) roi_pool_train_kernel(const bf16* __restrict__ fmap, int FH, int FW, int C, int kh, int kw,
+__global__ void __launch_bounds__(256) roi_pool_train_kernel(const bf16* __restrict__ fmap, int FH, int FW, int C, int kh, int kw,
                                                              LocalizerDev loc, const double* __restrict__ rects, bf16* __restrict__ out,
                                                              int* __restrict__ argmax, int* status) {
+  // CTA <-> ROI (the double-precision crop of extract_roi_pooling_input is evaluated once per ROI); thread <-> (bin, 8
+  // channels): 16-byte feature reads, 16-byte row writes.  output [row][bin][C]
   __shared__ int s_rect[5];
   const int r = blockIdx.x;
   if (threadIdx.x == 0) {
@@ -95,37 +97,51 @@ __global__ void __launch_bounds__(128) roi_pool_train_kernel(const bf16* __restr
     int y0, y1, x0, x1;
     const bool ok = roi_crop(loc, q[0], q[1], q[2], q[3], FH, FW, &y0, &y1, &x0, &x1);
     s_rect[0] = y0; s_rect[1] = y1; s_rect[2] = x0; s_rect[3] = x1; s_rect[4] = ok;
-    if (!ok && blockIdx.y == 0) atomicAdd(status, 1);
+    if (!ok) atomicAdd(status, 1);
   }
   __syncthreads();
   const int y0 = s_rect[0], x0 = s_rect[2], ch = s_rect[1] - y0, cw = s_rect[3] - x0;
   const bool ok = s_rect[4] != 0;
-  const int bins = kh * kw;
-  // output [row][bin][C]; CTA <-> (row, bin), thread <-> channel (coalesced feature reads)
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int bin = blockIdx.y, item = bin * C + c;
-    float m = 0.f;
-    int am = 0;
+  const int bins = kh * kw, cv = C >> 3;
+  for (int item = threadIdx.x; item < bins * cv; item += blockDim.x) {
+    const int bin = item / cv, c0 = (item - bin * cv) << 3;
+    float m[8];
+    int am[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { m[e] = 0.f; am[e] = 0; }
     if (ok) {
       const int by = bin / kw, bx = bin - by * kw;
       const int ys = (by * ch) / kh, ye = ((by + 1) * ch + kh - 1) / kh;
       const int xs = (bx * cw) / kw, xe = ((bx + 1) * cw + kw - 1) / kw;
-      m = -INFINITY;
-      am = (y0 + ys) * FW + x0 + xs;
+      const int first = (y0 + ys) * FW + x0 + xs;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { m[e] = -INFINITY; am[e] = first; }
       for (int yy = ys; yy < ye; ++yy)
         for (int xx = xs; xx < xe; ++xx) {
           const int pos = (y0 + yy) * FW + x0 + xx;
-          const float v = __bfloat162float(fmap[(long)pos * C + c]);
-          if (v > m) { m = v; am = pos; }   // first maximum in scan order, as nn.SpatialAdaptiveMaxPooling
+          const uint4 raw = *reinterpret_cast<const uint4*>(fmap + (long)pos * C + c0);
+          const bf16* v8 = reinterpret_cast<const bf16*>(&raw);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float v = __bfloat162float(v8[e]);
+            if (v > m[e]) { m[e] = v; am[e] = pos; }   // first maximum in scan order, as nn.SpatialAdaptiveMaxPooling
+          }
         }
     }
-    out[(long)r * bins * C + item] = __float2bfloat16_rn(m);
-    argmax[(long)r * bins * C + item] = am;
+    uint4 o;
+    bf16* o8 = reinterpret_cast<bf16*>(&o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o8[e] = __float2bfloat16_rn(m[e]);
+    const long base = (long)r * bins * C + (long)bin * C + c0;
+    *reinterpret_cast<uint4*>(out + base) = o;
+    *reinterpret_cast<int4*>(argmax + base) = make_int4(am[0], am[1], am[2], am[3]);
+    *reinterpret_cast<int4*>(argmax + base + 4) = make_int4(am[4], am[5], am[6], am[7]);
   }
 }
 void launch_roi_pool_train(const bf16* fmap, int FH, int FW, int C, int kh, int kw, const LocalizerDev& loc, const double* rects_dev,
                            int R, bf16* out, int* argmax, int* status, cudaStream_t st) {
-  if (R > 0) roi_pool_train_kernel<<<dim3(R, kh * kw), 128, 0, st>>>(fmap, FH, FW, C, kh, kw, loc, rects_dev, out, argmax, status);
+  FRCNN_REQUIRE(C % 8 == 0, FRCNN_E_INVALID, "training ROI pooling: channel count must be a multiple of 8");
+  if (R > 0) roi_pool_train_kernel<<<R, 256, 0, st>>>(fmap, FH, FW, C, kh, kw, loc, rects_dev, out, argmax, status);
 }
 
 __global__ void roi_pool_bwd_kernel(const float* __restrict__ d_rows, const int* __restrict__ argmax, long total, int C,
@@ -307,23 +323,39 @@ __global__ void __launch_bounds__(256) cnet_loss_row_kernel(CnetLossParams p) {
   }
 }
 __global__ void __launch_bounds__(256) cnet_loss_wgrad_kernel(CnetLossParams p) {
-  const int o = blockIdx.x, no = p.ncls + 4;
+  // CTA <-> (output o, 64 weights of its row); thread <-> (weight, one of 4 interleaved row groups): the R-long sums
+  // are four independent chains per weight instead of one (the serial chain paced this kernel), combined in fixed order
+  const int o = blockIdx.x, kc = blockIdx.y, no = p.ncls + 4;
+  const int kl = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const int k = kc * 64 + kl;
+  __shared__ float part[4][64];
+  __shared__ float bpart[256];
   float* gw = o < 4 ? p.g_w_reg + (long)o * p.nin : p.g_w_cls + (long)(o - 4) * p.nin;
-  float bsum = 0.f;
-  for (int k = threadIdx.x; k < p.nin; k += blockDim.x) {
-    float s = 0.f;
-    for (int r = 0; r < p.R; ++r) s += p.dz[(long)r * no + o] * p.hidden[(long)r * p.nin + k];
-    gw[k] += s;
+  float s = 0.f;
+  if (k < p.nin)
+    for (int r = rg; r < p.R; r += 4) s += p.dz[(long)r * no + o] * p.hidden[(long)r * p.nin + k];
+  part[rg][kl] = s;
+  if (kc == 0) {
+    float b = 0.f;
+    for (int r = threadIdx.x; r < p.R; r += 256) b += p.dz[(long)r * no + o];
+    bpart[threadIdx.x] = b;
   }
-  if (threadIdx.x == 0) {
-    for (int r = 0; r < p.R; ++r) bsum += p.dz[(long)r * no + o];
-    if (o < 4) p.g_b_reg[o] += bsum; else p.g_b_cls[o - 4] += bsum;
+  __syncthreads();
+  if (rg == 0 && k < p.nin) gw[k] += (part[0][kl] + part[1][kl]) + (part[2][kl] + part[3][kl]);
+  if (kc == 0) {
+    for (int off = 128; off > 0; off >>= 1) {
+      if ((int)threadIdx.x < off) bpart[threadIdx.x] += bpart[threadIdx.x + off];
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      if (o < 4) p.g_b_reg[o] += bpart[0]; else p.g_b_cls[o - 4] += bpart[0];
+    }
   }
 }
 void launch_cnet_loss_bwd(const CnetLossParams& p, cudaStream_t st) {
   if (p.R <= 0) return;
   cnet_loss_row_kernel<<<p.R, 256, (p.nin + p.ncls + 4) * sizeof(float), st>>>(p);
-  cnet_loss_wgrad_kernel<<<p.ncls + 4, 256, 0, st>>>(p);
+  cnet_loss_wgrad_kernel<<<dim3(p.ncls + 4, (p.nin + 63) / 64), 256, 0, st>>>(p);
 }
 
 // ------------------------------------------------------------------------------------------ fc weight layouts
