@@ -469,11 +469,11 @@ def run_b200(args):
     # DRAM traffic of the same launches from the committed `ncu --set full` capture (profiles/), if it covers this batch
     traffic, traffic_src = None, None
     try:
-        summ = json.load(open(os.path.join(ROOT, "profiles", "r1_summary.json")))
+        summ = json.load(open(os.path.join(ROOT, "profiles", "r1b_summary.json")))
         rows = summ.get("full_b%d" % B)
         if rows and args.model == "vgg_small" and (h, w) == (450, 800):
             traffic = sum(r["dram_mb"] for r in rows) * 1e6
-            traffic_src = "profiles/r1_ncu_conv_b%d.md (dram__bytes_read.sum + dram__bytes_write.sum over %d conv launches)" % (B, len(rows))
+            traffic_src = "profiles/r1b_ncu_full_b%d.md (dram__bytes_read.sum + dram__bytes_write.sum over %d conv launches)" % (B, len(rows))
     except Exception:
         pass
     total_frames = sum_over_ranks(float(B)) * args.steps

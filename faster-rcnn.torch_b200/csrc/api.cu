@@ -1121,6 +1121,11 @@ static void do_train_image(frcnn_ctx* c, const float* img_dev, int H, int W, con
   do_train_batch(c, img_dev, 1, H, W, &pos, &n_pos, &neg, &n_neg, pnet_masks, cnet_masks, &seed, losses_host);
 }
 
+static int cnet_ctas(const frcnn_ctx* c) {
+  if (const char* e = getenv("FRCNN_CNET_CTAS")) return atoi(e);
+  return c->schedule == FRCNN_SCHED_THROUGHPUT ? std::max(1, c->sm_count / 4) : c->sm_count;
+}
+
 // detector / cnet workspace for a batch of N images
 static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
   int want_rows = std::max(N * c->cand_cap, min_rows);
@@ -1180,8 +1185,10 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
     conv_prepare(&f.launch, in, f.w_packed, 1, 1, R, f.nin, f.nout, 1, 1, 0, 0, EPI_F32_REDUCE, nullptr, c->sm_count, splits, 0, 0);
     conv_set_f32_output(&f.launch, f.acc);
     f.launch.p.m_limit = c->flags + 2;  // roi_total
-    // split-K factor chosen on the device from the live row count so that the units fill about dyn_ctas CTAs
-    f.launch.p.dyn_ctas = getenv("FRCNN_CNET_CTAS") ? atoi(getenv("FRCNN_CNET_CTAS")) : c->sm_count;
+    // split-K factor chosen on the device from the live row count so that the units fill about dyn_ctas CTAs: the whole
+    // machine on the latency schedule, a quarter of it on the throughput schedule (measured: 37 CTAs cost a single
+    // frame nothing and leave the other SMs to the frames in flight; the 148-way TMA reduce-add contention goes away)
+    f.launch.p.dyn_ctas = cnet_ctas(c);
     in = f.out_bf16;
   }
   // NMS workspace: segments = max(N images, N * classes)
@@ -2168,6 +2175,8 @@ int frcnn_set_schedule(frcnn_ctx* c, int schedule) {
   if (!c || (schedule != FRCNN_SCHED_LATENCY && schedule != FRCNN_SCHED_THROUGHPUT)) return FRCNN_E_INVALID;
   if (c->schedule != schedule) {
     c->schedule = schedule;
+    for (auto& f : c->fcs)
+      if (f.launch.p.m_limit) f.launch.p.dyn_ctas = frcnn::cnet_ctas(c);
     ++c->ws_gen;  // a captured detect graph holds the other schedule's launches: re-capture
   }
   return FRCNN_OK;

@@ -53,8 +53,13 @@ __global__ void __launch_bounds__(256) unpool_prelu_bwd_kernel(const float* __re
   const float inv_slope = 1.0f / slope;
   const long total = (long)N * Hp * Wp * cv;
   float ds = 0.f;
+  // the launcher makes the grid stride a multiple of C / 8, so a thread keeps its 8 channels over all iterations and
+  // the bias-gradient partials live in registers (one shared-memory atomic per channel and thread at the end, not
+  // one per element: the shared atomics paced this kernel)
+  float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int c8_fixed = (int)((blockIdx.x * (long)blockDim.x + threadIdx.x) % cv);
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cv);
+    const int c8 = c8_fixed;
     long r = i / cv;
     const int pw = (int)(r % Wp);
     r /= Wp;
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(256) unpool_prelu_bwd_kernel(const float* __re
       val[e] = neg ? gy * slope : gy;
       if (neg) ds += gy * (y * inv_slope);  // d y / d slope = x * mask, x = y / (slope * mask)
       win[e] = ((e < 4 ? a8.x : a8.y) >> (8 * (e & 3))) & 3u;
-      atomicAdd(&sb[c8 * 8 + e], val[e]);
+      bacc[e] += val[e];
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -94,6 +99,9 @@ __global__ void __launch_bounds__(256) unpool_prelu_bwd_kernel(const float* __re
       }
     }
   }
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (bacc[e] != 0.f) atomicAdd(&sb[c8_fixed * 8 + e], bacc[e]);
   ds = warp_sum(ds);
   if ((threadIdx.x & 31) == 0) s_ds[threadIdx.x >> 5] = ds;
   __syncthreads();
@@ -105,10 +113,19 @@ __global__ void __launch_bounds__(256) unpool_prelu_bwd_kernel(const float* __re
     if (t != 0.f) atomicAdd(dslope, t);
   }
 }
+// grid such that (grid * 256) % (C / 8) == 0: every thread then owns one 8-channel group for the whole launch
+static int channel_stable_grid(long total, int cv, int num_sms) {
+  int g = 1, a = cv, b = 256;
+  while (b) { const int t = a % b; a = b; b = t; }   // a = gcd(cv, 256)
+  g = cv / a;
+  long blocks = std::min<long>(cdiv(total, 256), (long)num_sms * 8);
+  blocks = std::max<long>(g, blocks / g * g);
+  return (int)blocks;
+}
 void launch_unpool_prelu_bwd(const float* g, const uint8_t* arg, const bf16* yp, const float* slope, const float* mask, bf16* dpre,
                              float* dbias, float* dslope, int N, int H, int W, int C, int num_sms, cudaStream_t st) {
   const long total = (long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
-  const int blocks = (int)std::min<long>(cdiv(total, 256), (long)num_sms * 8);
+  const int blocks = channel_stable_grid(total, C / 8, num_sms);
   unpool_prelu_bwd_kernel<<<blocks, 256, C * sizeof(float), st>>>(g, arg, yp, slope, mask, dpre, dbias, dslope, N, H, W, C);
 }
 
@@ -127,8 +144,10 @@ __global__ void __launch_bounds__(256) prelu_bwd_kernel(bf16* __restrict__ d, co
   const float inv_slope = 1.0f / slope;
   const long total = (long)N * npix_per_img * cv;
   float ds = 0.f;
+  float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // see unpool_prelu_bwd_kernel
+  const int c8_fixed = (int)((blockIdx.x * (long)blockDim.x + threadIdx.x) % cv);
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cv);
+    const int c8 = c8_fixed;
     const long pix = i / cv;
     const int n = (int)(pix / npix_per_img);
     uint4 d8 = reinterpret_cast<uint4*>(d)[i];
@@ -143,11 +162,14 @@ __global__ void __launch_bounds__(256) prelu_bwd_kernel(bf16* __restrict__ d, co
       const bool neg = yv < 0.f;
       const float v = neg ? gy * slope : gy;
       if (neg) ds += gy * (yv * inv_slope);
-      atomicAdd(&sb[c8 * 8 + e], v);
+      bacc[e] += v;
       de[e] = __float2bfloat16_rn(v);
     }
     reinterpret_cast<uint4*>(d)[i] = d8;
   }
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (bacc[e] != 0.f) atomicAdd(&sb[c8_fixed * 8 + e], bacc[e]);
   ds = warp_sum(ds);
   if ((threadIdx.x & 31) == 0) s_ds[threadIdx.x >> 5] = ds;
   __syncthreads();
@@ -162,7 +184,7 @@ __global__ void __launch_bounds__(256) prelu_bwd_kernel(bf16* __restrict__ d, co
 void launch_prelu_bwd(bf16* d, const bf16* y, const float* slope, const float* mask, float* dbias, float* dslope, int N, int H, int W,
                       int C, int num_sms, cudaStream_t st) {
   const long total = (long)N * H * W * (C / 8);
-  const int blocks = (int)std::min<long>(cdiv(total, 256), (long)num_sms * 8);
+  const int blocks = channel_stable_grid(total, C / 8, num_sms);
   prelu_bwd_kernel<<<blocks, 256, C * sizeof(float), st>>>(d, y, slope, mask, dbias, dslope, (long)H * W, N, C);
 }
 
@@ -237,21 +259,25 @@ void launch_head_tail_bwd(const HeadTailBwd& H, int num_sms, cudaStream_t st) {
 // tap group) accumulates its 7 taps in registers across all its tiles, one atomic per accumulator at the end.
 __global__ void __launch_bounds__(256) first_wgrad_kernel(const bf16* __restrict__ dpre, const float* __restrict__ img,
                                                           float* __restrict__ dw, int N, int H, int W, int pad) {
-  constexpr int CO = 64, TAPS = 27, TG = 4, PER = 7, TH = 8, TW = 32;
+  // thread <-> (8 output channels, 7 of the 27 taps, one of 8 interleaved pixel subsets): per pixel ONE 16-byte
+  // gradient read + 7 image reads feed 56 FMAs into a register tile (the one-channel-per-thread version issued
+  // 8 shared-memory loads per 7 FMAs and ran at the LDS rate)
+  constexpr int CO = 64, TAPS = 27, TG = 4, PER = 7, TH = 8, TW = 32, PS = 8;
   __shared__ __align__(16) bf16 s_d[TH * TW][CO];        // 32 KB
   __shared__ float s_img[3][TH + 2][TW + 2];
-  const int co = threadIdx.x & 63, tg = threadIdx.x >> 6;
-  int t_c[PER], t_kh[PER], t_kw[PER];
+  const int cg = threadIdx.x & 7, tg = (threadIdx.x >> 3) & 3, ps = threadIdx.x >> 5;
+  int t_off[PER];
 #pragma unroll
   for (int j = 0; j < PER; ++j) {
     const int tap = min(tg + j * TG, TAPS - 1);
-    t_c[j] = tap / 9;
-    t_kh[j] = (tap % 9) / 3;
-    t_kw[j] = tap % 3;
+    t_off[j] = ((tap / 9) * (TH + 2) + (tap % 9) / 3) * (TW + 2) + tap % 3;
   }
-  float acc[PER];
+  float acc[8][PER];
 #pragma unroll
-  for (int j = 0; j < PER; ++j) acc[j] = 0.f;
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int j = 0; j < PER; ++j) acc[e][j] = 0.f;
+  const float* simg = &s_img[0][0][0];
   const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
   const long total_tiles = (long)N * tiles_h * tiles_w;
   const long plane = (long)H * W;
@@ -275,19 +301,29 @@ __global__ void __launch_bounds__(256) first_wgrad_kernel(const bf16* __restrict
       s_img[c][rr / (TW + 2)][rr % (TW + 2)] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + ((long)n * 3 + c) * plane + (long)yy * W + xx) : 0.f;
     }
     __syncthreads();
-#pragma unroll 4
-    for (int px = 0; px < TH * TW; ++px) {
-      const float d = __bfloat162float(s_d[px][co]);
-      const int y = px / TW, x = px % TW;
+#pragma unroll 2
+    for (int px = ps; px < TH * TW; px += PS) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(&s_d[px][cg * 8]);
+      const bf16* d8 = reinterpret_cast<const bf16*>(&raw);
+      const int base = (px / TW) * (TW + 2) + (px % TW);
+      float iv[PER];
 #pragma unroll
-      for (int j = 0; j < PER; ++j) acc[j] += d * s_img[t_c[j]][y + t_kh[j]][x + t_kw[j]];
+      for (int j = 0; j < PER; ++j) iv[j] = simg[base + t_off[j]];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = __bfloat162float(d8[e]);
+#pragma unroll
+        for (int j = 0; j < PER; ++j) acc[e][j] = fmaf(d, iv[j], acc[e][j]);
+      }
     }
   }
 #pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    const int tap = tg + j * TG;
-    if (tap < TAPS && acc[j] != 0.f) atomicAdd(dw + co * TAPS + tap, acc[j]);  // Torch layout [co][c][kh][kw]: tap = c*9+kh*3+kw
-  }
+  for (int e = 0; e < 8; ++e)
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+      const int tap = tg + j * TG;
+      if (tap < TAPS && acc[e][j] != 0.f) atomicAdd(dw + (cg * 8 + e) * TAPS + tap, acc[e][j]);  // Torch layout [co][c][kh][kw]
+    }
 }
 void launch_first_wgrad(const bf16* dpre, const float* img, float* dw, int N, int H, int W, int pad, int num_sms, cudaStream_t st) {
   const long tiles = (long)N * ((H + 7) / 8) * ((W + 31) / 32);
