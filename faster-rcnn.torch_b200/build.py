@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfrcnn_b200.so")
-SOURCES = ["conv_igemm.cu", "elementwise.cu", "nms.cu", "detect_kernels.cu", "train_kernels.cu", "objective_kernels.cu", "optim_kernels.cu", "label_kernels.cu", "api.cu"]
+SOURCES = ["conv_igemm.cu", "elementwise.cu", "nms.cu", "detect_kernels.cu", "train_kernels.cu", "objective_kernels.cu", "optim_kernels.cu", "label_kernels.cu", "preprocess_kernels.cu", "api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-diag-suppress", "550"]
 

@@ -2067,6 +2067,37 @@ int frcnn_set_detect_thresholds(frcnn_ctx* c, double fg_prob, float nms_proposal
   return FRCNN_OK;
 }
 
+int frcnn_normalize_frame(frcnn_ctx* c, float* img_dev, int h, int w, int rgb2yuv, int centering, int scaling, int contrastive_width) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(img_dev && h >= 1 && w >= 1 && contrastive_width >= 0, FRCNN_E_INVALID, "bad argument");
+  FRCNN_REQUIRE(contrastive_width == 0 || (contrastive_width % 2 == 1 && contrastive_width <= 17), FRCNN_E_INVALID,
+                "contrastive normalisation: odd kernel width <= 17");
+  const size_t b_stat = 4096, b_k = 256;
+  uint8_t* mem = (uint8_t*)frcnn::ensure_scratch(c, b_stat + b_k + (size_t)h * w * sizeof(float) + 256);
+  float kh[32];
+  if (contrastive_width > 0) {
+    // image.gaussian1D(size): sigma 0.25, amplitude 1, mean 0.5, not normalised: exp(-((i - center) / (sigma * size))^2 / 2)
+    // with center = mean * size + 0.5 (1-based i); nn.SpatialSubtractiveNormalization then divides by kernel:sum()
+    const int n = contrastive_width;
+    double sum = 0.0;
+    float g[32];
+    for (int i = 1; i <= n; ++i) {
+      const double center = 0.5 * n + 0.5;
+      const double t = ((double)i - center) / (0.25 * n);
+      g[i - 1] = (float)exp(-(t * t) / 2.0);
+      sum += (double)g[i - 1];
+    }
+    for (int i = 0; i < n; ++i) kh[i] = g[i] / (float)sum;   // kernel:div(kernel:sum() * sqrt(nInputPlane)), nInputPlane = 1
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(mem + b_stat, kh, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  }
+  frcnn::launch_normalize_frame(img_dev, h, w, rgb2yuv, centering, scaling, (const float*)(mem + b_stat), contrastive_width, 1e-4f,
+                                (double*)mem, (float*)(mem + b_stat + b_k), c->stream);
+  c->launches += (rgb2yuv ? 1 : 0) + (centering ? 3 : 0) + (scaling ? 5 : 0) + (contrastive_width ? 2 : 0);
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));   // kh lives on this stack frame
+  API_END(c)
+}
+
 int frcnn_find_positive(frcnn_ctx* c, const double* rois_host, int n_rois, const double* clip_host, double pos_threshold,
                         double neg_threshold, int include_best, frcnn_anchor_ref* out_host, int* out_roi_host, int cap, int* n_out) {
   API_BEGIN(c)

@@ -175,6 +175,10 @@ void launch_cnet_out(const float* hidden, const float* w_reg, const float* b_reg
                      const float* b_cls, float* reg_out, float* cls_out, int rows_max, const int* rows_dev, int nin,
                      int ncls, cudaStream_t st);
 
+// ------------------------------------------------------------------ frame normalisation (preprocess_kernels.cu)
+void launch_normalize_frame(float* img, int H, int W, int rgb2yuv, int centering, int scaling, const float* k1d_dev, int ksize,
+                            float threshold, double* scratch, float* plane_tmp, cudaStream_t st);
+
 // ------------------------------------------------------------------ optimiser (optim_kernels.cu)
 void launch_rmsprop_step(float* w, float* g, float* m, long n, double grad_div, double lr, double alpha, double eps, double wd,
                          int num_sms, cudaStream_t st);

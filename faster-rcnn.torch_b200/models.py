@@ -127,6 +127,14 @@ class Model:
             self.params[n].copy_(v.reshape(-1).to(self.device))
         self.pack_weights()
 
+    def normalize_frame(self, img, rgb2yuv=False, centering=True, scaling=True, contrastive_width=7):
+        """The frame normalisation of BatchIterator:processImage / load_image (BatchIterator.lua:146-161,
+        utilities.lua:211-212) on the GPU, in place on a [3][H][W] fp32 CUDA tensor (frcnn_normalize_frame)."""
+        assert img.is_cuda and img.dtype == torch.float32 and img.dim() == 3 and img.is_contiguous()
+        check(self.ctx, lib().frcnn_normalize_frame(self.ctx, ffi.cast("float*", img.data_ptr()), img.shape[1], img.shape[2],
+                                                    1 if rgb2yuv else 0, 1 if centering else 0, 1 if scaling else 0, int(contrastive_width)))
+        return img
+
     def set_schedule(self, schedule):
         """'latency' (default: every stage fills the machine with one frame batch) or 'throughput' (least SM time per
         frame: unsplit anchor heads with the tail fused; for several frames in flight).  frcnn_set_schedule."""

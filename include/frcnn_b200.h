@@ -79,7 +79,7 @@ typedef struct frcnn_detection {
 } frcnn_detection;
 
 /* One training example of objective.lua:91-140: a positive {anchor, roi} or a negative {anchor} as produced by
- * BatchIterator:nextTraining (Anchors:findPositive / sampleNegative stay host-side Lua). */
+ * BatchIterator:nextTraining (from Anchors:findPositive / sampleNegative: frcnn_find_positive / frcnn_sample_negative). */
 typedef struct frcnn_example {
   double anchor[4];     /* anchor rect {minX, minY, maxX, maxY} (Anchors:get) */
   double roi[4];        /* ground-truth rect roi.rect (positives only) */
@@ -257,6 +257,15 @@ int frcnn_last_timings(const frcnn_ctx* ctx, float ms[6]);
  * stream: summed device time, summed algorithmic FLOPs (2*M*N*K of the un-padded problems) and launch count of
  * the last detect call (bench.py's roofline figure). */
 int frcnn_last_conv_profile(const frcnn_ctx* ctx, float* ms, double* flops, int* launches);
+
+/* ---- frame normalisation: replaces the tail of load_image / BatchIterator:processImage (utilities.lua:211-212,
+ *      BatchIterator.lua:86,146-161) -- the step before pnet:forward, SURVEY 8f row 2 ------------------------------ */
+/* In place on img_dev [3][h][w] fp32 (already resized): optional image.rgb2yuv; per-channel centering (x - mean);
+ * per-channel scaling (x / std, unbiased, skipped when std <= 1e-8); nn.SpatialContrastiveNormalization(1,
+ * image.gaussian1D(contrastive_width)) on channel 1 (contrastive_width = 0: none; config/duplo.lua:6 uses 7).
+ * `image` / `nn` are un-vendored: algorithms restated in oracle/preprocess.py (tolerance 1e-5, parity unpinned). */
+int frcnn_normalize_frame(frcnn_ctx* ctx, float* img_dev, int h, int w, int rgb2yuv, int centering, int scaling,
+                          int contrastive_width);
 
 /* ---- anchor labelling: replaces Anchors:findPositive / Anchors:sampleNegative (Anchors.lua:147-235; called per
  *      training image by BatchIterator.lua:200-225) -- SURVEY 8f row 1 ------------------------------------------ */

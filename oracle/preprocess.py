@@ -1,0 +1,72 @@
+"""TEST INFRASTRUCTURE (oracle): CPU restatement of the frame normalisation that precedes pnet:forward.
+
+Reference call sites: load_image (utilities.lua:206-218: image.load + image.rgb2yuv for color_space = 'yuv'),
+BatchIterator:processImage (BatchIterator.lua:146-161: per-channel centering, per-channel scaling by the unbiased
+std when > 1e-8, then `img[1] = self.normalization:forward(img[{{1}}])` with
+self.normalization = nn.SpatialContrastiveNormalization(1, image.gaussian1D(cfg.normalization.width)), :86).
+
+`image` and `nn` are un-vendored Torch7 packages without a pinned version; their published algorithms
+(2015) are restated here.  PARITY UNPINNED: there is no reference run or golden vector for this step.
+
+  image.gaussian1D(size): sigma = 0.25, amplitude = 1, mean = 0.5, normalize = false:
+      g[i] = exp(-(((i - center) / (sigma * size))^2) / 2), center = mean * size + 0.5, i = 1..size
+  nn.SpatialSubtractiveNormalization(1, k1d): k = k1d / (sum(k1d) * sqrt(nInputPlane)); meanestimator = zero padding
+      (size/2 each side) -> horizontal k -> vertical k; coef = meanestimator(ones); out = x - meanestimator(x) / coef
+  nn.SpatialDivisiveNormalization(1, k1d, 1e-4, 1e-4): localstds = sqrt(meanestimator(x^2)); adjusted = localstds / coef;
+      thresholded = adjusted > 1e-4 ? adjusted : 1e-4; out = x / thresholded
+  nn.SpatialContrastiveNormalization = Subtractive then Divisive, same kernel."""
+import numpy as np
+import torch
+import torch.nn.functional as TF
+
+
+def gaussian1D(size, sigma=0.25, amplitude=1.0, mean=0.5):
+    center = mean * size + 0.5
+    i = np.arange(1, size + 1, dtype=np.float64)
+    return (amplitude * np.exp(-(((i - center) / (sigma * size)) ** 2) / 2.0)).astype(np.float32)
+
+
+def rgb2yuv(img):
+    """image.rgb2yuv on a [3][H][W] float tensor."""
+    r, g, b = img[0], img[1], img[2]
+    y = 0.299 * r + 0.587 * g + 0.114 * b
+    u = -0.14713 * r - 0.28886 * g + 0.436 * b
+    v = 0.615 * r - 0.51499 * g - 0.10001 * b
+    return torch.stack([y, u, v]).to(torch.float32)
+
+
+def _mean_estimator(x, k):
+    """zero padding -> horizontal k -> vertical k on a [H][W] plane."""
+    r = len(k) // 2
+    kt = torch.from_numpy(k)
+    t = TF.conv2d(x[None, None], kt.view(1, 1, 1, -1), padding=(0, r))
+    t = TF.conv2d(t, kt.view(1, 1, -1, 1), padding=(r, 0))
+    return t[0, 0]
+
+
+def contrastive_normalization(plane, width=7, threshold=1e-4):
+    k = gaussian1D(width)
+    k = (k / np.float32(k.sum())).astype(np.float32)
+    coef = _mean_estimator(torch.ones_like(plane), k)
+    s = plane - _mean_estimator(plane, k) / coef
+    sd = torch.sqrt(_mean_estimator(s * s, k)) / coef
+    sd = torch.where(sd > threshold, sd, torch.full_like(sd, threshold))
+    return s / sd
+
+
+def normalize_frame(img, rgb_to_yuv=False, centering=True, scaling=True, contrastive_width=7):
+    """img: [3][H][W] float32 tensor -> normalised copy (BatchIterator.lua:146-161 order)."""
+    x = img.clone().to(torch.float32)
+    if rgb_to_yuv:
+        x = rgb2yuv(x)
+    if centering:
+        for i in range(3):
+            x[i] = x[i] - np.float32(x[i].double().mean().item())       # TH meanall accumulates in double
+    if scaling:
+        for i in range(3):
+            s = x[i].double().std(unbiased=True).item()                  # TH stdall, double accumulation
+            if s > 1e-8:
+                x[i] = x[i] / np.float32(s)
+    if contrastive_width:
+        x[0] = contrastive_normalization(x[0], contrastive_width)
+    return x

@@ -49,6 +49,33 @@ print(json.dumps({"row": "rmsprop_step (gradient:div + optim.rmsprop, fused)", "
                   "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": round(gbs / peaks["hbm_gbs"], 3)},
                   "cpu_baseline": {"ms": round(cpu_s * 1e3, 2), "kind": "port", "cores": 1, "sample": "numpy fp32 restatement, same buffer"}}))
 
+# ---- frame normalisation
+from oracle import preprocess as OP  # noqa: E402
+frame = torch.rand(3, 450, 800)
+fd = frame.clone().cuda()
+evs = []
+for it in range(13):
+    fd.copy_(frame)
+    flush.fill_(1)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    m.normalize_frame(fd, rgb2yuv=True)
+    b.record()
+    torch.cuda.synchronize()
+    if it >= 3:
+        evs.append(a.elapsed_time(b))
+ms = float(np.median(evs))
+torch.set_num_threads(os.cpu_count() or 1)
+t0 = time.perf_counter()
+OP.normalize_frame(frame, rgb_to_yuv=True)
+cpu_s = time.perf_counter() - t0
+fb = frame.numel() * 4
+print(json.dumps({"row": "normalize_frame (rgb2yuv + centering + scaling + contrastive 7), 800x450", "ms": round(ms, 4), "launches": 11,
+                  "algorithmic_bytes": int(fb * 2 + fb * 2 * 2 / 3), "note": "call incl. its final stream synchronisation; latency-bound at this size (11 small launches)",
+                  "roofline": {"bound": "hbm", "achieved": round((fb * 2 + fb * 4 / 3) / (ms * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                               "frac": round((fb * 2 + fb * 4 / 3) / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)},
+                  "cpu_baseline": {"ms": round(cpu_s * 1e3, 2), "kind": "port", "cores": os.cpu_count(), "sample": "PyTorch-CPU restatement, same frame"}}))
+
 # ---- labelling
 rng = np.random.default_rng(0)
 rois = []
