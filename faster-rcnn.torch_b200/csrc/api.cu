@@ -162,6 +162,8 @@ struct frcnn_ctx {
   cudaGraphExec_t graph_exec = nullptr;
   struct GraphKey { const float* img; int N, H, W; double thr_fg, thr_class; float thr_nms1, thr_nms2; long gen; } graph_key = {};
   GraphKey eager_key = {};     // key of the last eager run (a config is captured on its second use)
+  void* nms_stage = nullptr;   // device staging of the host-side nms entry points (boxes | picks | counts)
+  size_t nms_stage_bytes = 0;
   bool det_pending = false;    // frcnn_detect_begin without its frcnn_detect_end yet
   int det_pending_n = 0;
   long weights_gen = 0;        // bumped by frcnn_pack_weights: invalidates the cached dgrad weight layouts
@@ -1573,6 +1575,7 @@ int frcnn_destroy(frcnn_ctx* c) {
   if (c->d_w_lut) cudaFree(c->d_w_lut);
   if (c->d_h_lut) cudaFree(c->d_h_lut);
   if (c->scratch) cudaFree(c->scratch);
+  if (c->nms_stage) cudaFree(c->nms_stage);
   if (c->d_img) cudaFree(c->d_img);
   if (c->h_ints) cudaFreeHost(c->h_ints);
   if (c->h_det) cudaFreeHost(c->h_det);
@@ -1959,12 +1962,22 @@ int frcnn_nms_segmented(frcnn_ctx* c, const float* boxes_host, int64_t row_strid
     for (int s = 0; s < n_seg; ++s) counts_host[s] = 0;
     return FRCNN_OK;
   }
-  // staging buffers: boxes | picks | counts
-  std::vector<void*> tmp;
-  struct Guard { std::vector<void*>& v; ~Guard() { for (void* p : v) cudaFree(p); } } guard{tmp};
-  float* d_boxes = (float*)frcnn::dev_alloc(tmp, (size_t)n * row_stride * sizeof(float));
-  int64_t* d_pick = (int64_t*)frcnn::dev_alloc(tmp, (size_t)n * sizeof(int64_t));
-  int64_t* d_counts = (int64_t*)frcnn::dev_alloc(tmp, (size_t)n_seg * sizeof(int64_t));
+  // staging buffers: boxes | picks | counts -- one allocation kept by the context and grown on demand (a cudaMalloc /
+  // cudaFree pair per call costs more than the whole NMS of a few thousand boxes)
+  const size_t b_boxes = ((size_t)n * row_stride * sizeof(float) + 255) & ~size_t(255);
+  const size_t b_pick = ((size_t)n * sizeof(int64_t) + 255) & ~size_t(255);
+  const size_t b_counts = ((size_t)n_seg * sizeof(int64_t) + 255) & ~size_t(255);
+  if (b_boxes + b_pick + b_counts > c->nms_stage_bytes) {
+    FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (c->nms_stage) cudaFree(c->nms_stage);
+    c->nms_stage = nullptr;
+    c->nms_stage_bytes = 0;
+    FRCNN_CUDA_TRY(cudaMalloc(&c->nms_stage, b_boxes + b_pick + b_counts));
+    c->nms_stage_bytes = b_boxes + b_pick + b_counts;
+  }
+  float* d_boxes = (float*)c->nms_stage;
+  int64_t* d_pick = (int64_t*)((uint8_t*)c->nms_stage + b_boxes);
+  int64_t* d_counts = (int64_t*)((uint8_t*)c->nms_stage + b_boxes + b_pick);
   FRCNN_CUDA_TRY(cudaMemcpyAsync(d_boxes, boxes_host, (size_t)n * row_stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   nms_dev_impl(c, d_boxes, n, row_stride, seg_offsets_host, n_seg, overlap, order_mode, order_col, d_pick, d_counts);
   FRCNN_CUDA_TRY(cudaMemcpyAsync(counts_host, d_counts, n_seg * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));

@@ -76,9 +76,9 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
   t.k_end = min(p.k_iters, t.k_begin + k_per_split);
   t.m0 = t.w0;  // first GEMM row of the tile; only used with m_limit (GEMM use: BH == 1, N == 1, tiles_h == 1)
   if (p.wgrad) {
-    // M index = (tap, 128-row Cout tile): the epilogue's reduce-add coordinates are (ci, tap, co, 0)
-    t.w0 = mt / p.co_tiles;               // filter tap
-    t.h0 = (mt % p.co_tiles) * BLOCK_M;   // first output channel
+    // M index = (tap [group], 128-row Cout tile): the epilogue's reduce-add coordinates are (ci, tap, co, 0)
+    t.w0 = (mt / p.co_tiles) * (p.halo ? p.MT : 1);   // (first) filter tap
+    t.h0 = (mt % p.co_tiles) * BLOCK_M;               // first output channel
     t.n_img = 0;
     t.m0 = 0;
   }
@@ -162,9 +162,12 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
     const float k_pos = p.scale;
     ptx::mbar_wait(&tmem_full[acc], acc_phase);
     ptx::tc_fence_after();
+    // weight-gradient tap groups (conv_wgrad_halo_kernel): sub-tile mt is filter tap t.w0 + mt of the same Cout rows
+    const int mt_count = (p.wgrad && p.halo) ? min(MT, p.KH * p.KW - t.w0) : MT;
 #pragma unroll 1
-    for (int mt = 0; mt < ((p.dbg & 2) ? 0 : MT); ++mt) {
-      const int hbase = t.h0 + mt * p.BH;
+    for (int mt = 0; mt < ((p.dbg & 2) ? 0 : mt_count); ++mt) {
+      const int hbase = (p.wgrad && p.halo) ? t.h0 : t.h0 + mt * p.BH;
+      const int wcoord = (p.wgrad && p.halo) ? t.w0 + mt : t.w0;
       const int h = hbase + dy, w = t.w0 + dx;
       const bool valid = (h < p.Hout) && (w < p.Wout);
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN * MT + mt * BN) + ((uint32_t)(q * 32) << 16);
@@ -187,7 +190,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
             ptx::fence_proxy_async();
             ptx::named_bar_sync(1, EPI_THREADS);
             if (store_thread) {
-              ptx::tma_reduce_add_4d(tmOut, tile_buf, t.n0 + c0, t.w0, hbase, slice);
+              ptx::tma_reduce_add_4d(tmOut, tile_buf, t.n0 + c0, wcoord, hbase, slice);
               ptx::tma_store_commit();
             }
           } else {
@@ -795,6 +798,158 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- weight gradient, tap groups
+// conv_igemm_kernel's weight-gradient mode makes one unit per filter tap: dY and X are re-read nine times and every
+// K step moves 16 KB + BN/64 x 8 KB through the SM's L2 port for 4 MMAs -- 94 to 188 B/clk against the ~50 B/clk the port
+// sustains (profiles/r1b_conv_sweep.md).  Here a unit covers a GROUP of T taps of one (Cout tile, Cin tile): per K step
+// (an 8 x 8 pixel patch) ONE dY box and ONE X box with the patch's halo are loaded, and tap (kh, kw) is an MN-major UMMA
+// descriptor whose start is moved (kh * pitch + kw) pixel rows into the X box (8-pixel patch rows = 8-row descriptor
+// groups, SBO = halo pitch: the scheme of conv_halo_kernel applied to the K dimension).  T accumulators of BN columns
+// live in TMEM (T x BN <= 512, one stage); the epilogue reduce-adds them into dW[co][tap][ci] tap by tap.
+__host__ __device__ constexpr int wgh_b_atom(int KMAX) { return (((8 + KMAX - 1) * (8 + KMAX - 1) * 128) + 1023) & ~1023; }
+__host__ __device__ constexpr int wgh_stage_bytes(int BN) { return A_SUB_BYTES + (BN / 64) * wgh_b_atom(HALO_MAXK); }
+__host__ __device__ constexpr int wgh_stages(int BN) {
+  return (SMEM_LIMIT - SMEM_FIXED) / wgh_stage_bytes(BN) > 6 ? 6 : (SMEM_LIMIT - SMEM_FIXED) / wgh_stage_bytes(BN);
+}
+static int wgh_smem_bytes(int BN) { return wgh_stages(BN) * wgh_stage_bytes(BN) + SMEM_FIXED; }
+
+template <int BN, int T>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+    conv_wgrad_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGroup grp) {
+  constexpr int STAGES = wgh_stages(BN);
+  constexpr int B_ATOM = wgh_b_atom(HALO_MAXK);
+  constexpr int STAGE_BYTES = wgh_stage_bytes(BN);
+  constexpr uint32_t IDESC_MN = ptx::make_idesc_bf16(BLOCK_M, BN, 1, 1);
+  static_assert(T * BN <= 512 && STAGES >= 2, "accumulators must fit TMEM; at least two stages");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tile_buf = smem + STAGES * STAGE_BYTES;
+  float* sbias = reinterpret_cast<float*>(tile_buf + STAGE_TILE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_units = grp.unit_end[0];
+  GroupSched sc;
+  make_sched(grp, BN, sc);
+  const ConvParams& p = grp.p[0];
+  const int PW = 8 + p.KW - 1, PH = 8 + p.KH - 1;
+  const uint32_t tx_bytes = (uint32_t)(A_SUB_BYTES + (BN / 64) * PW * PH * 128);
+
+  if (warp == 0 && lane == 0) {
+    ptx::tma_prefetch_desc(&maps.a[0]);
+    ptx::tma_prefetch_desc(&maps.b[0]);
+    ptx::tma_prefetch_desc(&maps.o[0]);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], EPI_THREADS / 32);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_base_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        int gi;
+        TileCoord t;
+        if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+        for (int k = t.k_begin; k < t.k_end; ++k) {
+          // k -> (image, patch row, patch column) of the 8 x 8 output-pixel patch
+          const int per_img = p.tiles_h * p.wchunks;
+          const int n = k / per_img;
+          const int r = k - n * per_img;
+          const int ph = r / p.wchunks;
+          const int pw = r - ph * p.wchunks;
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], tx_bytes);
+#pragma unroll
+          for (int i = 0; i < BLOCK_M / 64; ++i)
+            ptx::tma_load_4d(st + i * 8192, &maps.a[0], &full_bar[stage], t.h0 + 64 * i, pw * 8, ph * 8, n);
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j)
+            ptx::tma_load_4d(st + A_SUB_BYTES + j * B_ATOM, &maps.b[0], &full_bar[stage], t.n0 + 64 * j, pw * 8 - p.padW, ph * 8 - p.padH, n);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int seq = 0;
+      const int taps = p.KH * p.KW;
+      const uint32_t sbo = (uint32_t)PW * 128u;
+      for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+        int gi;
+        TileCoord t;
+        if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+        const uint32_t acc_phase = (uint32_t)seq & 1u;
+        ++seq;
+        ptx::mbar_wait(&tmem_empty[0], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const int ntap = min(T, taps - t.w0);
+        for (int k = t.k_begin; k < t.k_end; ++k) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_SUB_BYTES;
+          const uint64_t da = ptx::make_desc_mn_sw128(a_addr, 8192);
+          for (int ti = 0; ti < ntap; ++ti) {
+            const int tap = t.w0 + ti;
+            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+#pragma unroll
+            for (int j = 0; j < BLOCK_K / 16; ++j) {
+              // K step j = patch rows 2j, 2j + 1: A rows [16j, 16j + 16) contiguous; X rows (kh + 2j) * PW + kw of the halo box
+              const uint64_t db = ptx::make_desc_mn_sw128_sbo(b_addr + (uint32_t)(((kh + 2 * j) * PW + kw) * 128), B_ATOM, sbo);
+              ptx::mma_bf16_ss(tmem_base + ti * BN, da + (uint64_t)(j * 2048 >> 4), db, IDESC_MN, (k > t.k_begin || j > 0) ? 1u : 0u);
+            }
+          }
+          ptx::mma_commit(&empty_bar[stage]);
+          if (k == t.k_end - 1) ptx::mma_commit(&tmem_full[0]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    epilogue_loop<BN, T, 1>(grp, maps.o, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 4, lane);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -1560,6 +1715,43 @@ void conv_wgrad_prepare(ConvLaunch* L, const bf16* dy, const bf16* x, float* dw_
   L->BN = BN;
   p.MT = 1;
   p.wgrad = 1;
+  if (KH <= HALO_MAXK && KW <= HALO_MAXK && KH * KW > 1 && env_int("FRCNN_WGRAD_HALO", 1)) {
+    // conv_wgrad_halo_kernel: units of T filter taps sharing one dY box and one X halo box per 8 x 8 pixel patch
+    const int T = BN == 64 ? 5 : (BN == 128 ? 3 : 2);
+    const int groups = (KH * KW + T - 1) / T;
+    p.halo = 1;
+    p.MT = T;
+    p.BW = 8; p.BH = 8; p.bw_shift = 3;
+    p.co_tiles = (Cout + BLOCK_M - 1) / BLOCK_M;
+    p.wchunks = (p.Wout + 7) / 8;
+    p.tiles_h = (p.Hout + 7) / 8;
+    p.tiles_w = groups * p.co_tiles;
+    p.n_tiles_m = groups * p.co_tiles;
+    p.n_tiles_n = (Cin + BN - 1) / BN;
+    p.cchunks = 1;
+    p.k_iters = N * p.tiles_h * p.wchunks;
+    p.mode = EPI_F32_REDUCE;
+    p.scale = 1.f;
+    const int base = p.n_tiles_m * p.n_tiles_n;
+    int splits = (2 * num_sms + base - 1) / base;
+    splits = std::max(1, std::min(splits, std::max(1, p.k_iters / 8)));
+    p.k_per_split = (p.k_iters + splits - 1) / splits;
+    p.splits = (p.k_iters + p.k_per_split - 1) / p.k_per_split;
+    make_tmap_act(&L->tmA, dy, N, p.Hout, p.Wout, Cout, 8, 8);
+    make_tmap_act(&L->tmB, x, N, Hin, Win, Cin, 8 + KW - 1, 8 + KH - 1);
+    p.out = dw_taps;
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)(KH * KW), (cuuint64_t)Cout, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)KH * KW * Cin * 4, (cuuint64_t)Cout * KH * KW * Cin * 4};
+    cuuint32_t box[4] = {32, 1, BLOCK_M, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = get_encode()(&L->tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, dw_taps, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FRCNN_REQUIRE(r == CUDA_SUCCESS, FRCNN_E_CUDA, "cuTensorMapEncodeTiled(wgrad out) failed, CUresult " + std::to_string((int)r));
+    const int total = p.n_tiles_m * p.n_tiles_n * p.splits;
+    L->grid = total < num_sms ? total : num_sms;
+    return;
+  }
   // K chunks = BW x BH = 64 output pixels: the rectangle that wastes the fewest padded pixels
   long best = -1;
   for (int bw = 64; bw >= 1; bw >>= 1) {
@@ -1674,6 +1866,27 @@ static void launch_halo_key(int BN, int MT, const ConvMaps& maps, const ConvGrou
   }
 }
 
+template <int BN, int T>
+static void launch_wgrad_halo_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+  static bool configured = false;
+  const int smem = wgh_smem_bytes(BN);
+  if (!configured) {
+    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_halo_kernel<BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  conv_wgrad_halo_kernel<BN, T><<<grid, CONV_THREADS, smem, st>>>(maps, grp);
+  FRCNN_CUDA_TRY(cudaGetLastError());
+}
+static void launch_wgrad_halo_key(int BN, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+  switch (BN) {
+    case 64: launch_wgrad_halo_cfg<64, 5>(maps, grp, grid, st); break;
+    case 128: launch_wgrad_halo_cfg<128, 3>(maps, grp, grid, st); break;
+    case 192: launch_wgrad_halo_cfg<192, 2>(maps, grp, grid, st); break;
+    case 256: launch_wgrad_halo_cfg<256, 2>(maps, grp, grid, st); break;
+    default: throw Error{FRCNN_E_INVALID, "wgrad (tap-group kernel): unsupported Cin tile"};
+  }
+}
+
 static void launch_key(int BN, int MT, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
   switch (BN * 10 + MT) {
     case 641: launch_cfg<64, 1>(maps, grp, grid, st); break;
@@ -1733,7 +1946,8 @@ void conv_launch(const ConvLaunch& L, cudaStream_t st) {
     maps.b[g] = L.tmB;
     maps.o[g] = L.tmOut;
   }
-  if (L.p.halo) launch_halo_key(L.BN, L.p.MT, maps, grp, L.grid, st);
+  if (L.p.wgrad && L.p.halo) launch_wgrad_halo_key(L.BN, maps, grp, L.grid, st);
+  else if (L.p.halo) launch_halo_key(L.BN, L.p.MT, maps, grp, L.grid, st);
   else launch_key(L.BN, L.p.MT, maps, grp, L.grid, st);
 }
 

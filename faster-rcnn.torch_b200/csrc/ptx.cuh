@@ -196,6 +196,17 @@ __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint3
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major operand whose 8-row K groups are `sbo_bytes` apart and whose start is only 128-byte aligned: a tap-shifted
+// view into a halo box of [pixels][64 channels] rows (the weight-gradient kernel's X operand)
+__device__ __forceinline__ uint64_t make_desc_mn_sw128_sbo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // Instruction descriptor, kind::f16: D fp32, A/B bf16.  a_mn / b_mn: 0 = K-major, 1 = MN-major.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn = 0, uint32_t b_mn = 0) {
   return (1u << 4)            // c_format = F32

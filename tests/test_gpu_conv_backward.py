@@ -13,7 +13,7 @@ CASES = [
     # n, h, w, cin, cout, k, pad
     (1, 16, 16, 64, 64, 3, 1), (2, 29, 50, 128, 256, 3, 1), (1, 57, 100, 256, 256, 3, 1), (1, 29, 50, 384, 256, 5, 0),
     (1, 29, 50, 384, 256, 7, 0), (1, 57, 100, 256, 256, 3, 0), (3, 9, 7, 64, 192, 3, 1), (1, 113, 200, 64, 128, 3, 1),
-    (1, 30, 41, 128, 64, 1, 0),
+    (1, 30, 41, 128, 64, 1, 0), (1, 29, 50, 384, 384, 3, 1), (4, 57, 100, 128, 128, 3, 1), (1, 40, 40, 64, 64, 2, 0),
 ]
 
 
