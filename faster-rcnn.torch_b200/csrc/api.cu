@@ -121,7 +121,7 @@ struct frcnn_ctx {
   int cw_n = 0;                    // frames the per-frame objective buffers (head_dout, losses_dev) are sized for
   long cw_gen = -1;                // pnet workspace generation they were sized against
   float* losses_cur = nullptr;     // the 8-float loss slot of the frame being processed
-  bool cnet_wgrad_deferred = false; // frcnn_train_batch: cnet weight gradients accumulate in dw_taps over the frames
+  std::vector<ExampleDev> ex_host; // host staging of a batch's example records
   std::vector<void*> cw_allocs;
   ExampleDev* ex_dev = nullptr;
   double* ex_rects = nullptr;
@@ -918,7 +918,7 @@ static void ensure_objective_workspace(frcnn_ctx* c, int rows) {
     f.t_acc = (float*)dev_alloc(A, rn * sizeof(float));
     f.t_pre = (float*)dev_alloc(A, rn * sizeof(float));
     f.t_xhat = f.bn ? (float*)dev_alloc(A, rn * sizeof(float)) : nullptr;
-    f.t_rstd = (float*)dev_alloc(A, f.nout * sizeof(float));
+    f.t_rstd = (float*)dev_alloc(A, (size_t)NF * f.nout * sizeof(float));   // BatchNorm 1/std of every frame's ROI batch
     f.t_mask = (float*)dev_alloc(A, rn * sizeof(float));
     f.t_din = (float*)dev_alloc(A, rn * sizeof(float));
     f.t_out32 = (float*)dev_alloc(A, rn * sizeof(float));
@@ -961,68 +961,96 @@ static void wgrad_rows(frcnn_ctx* c, const bf16* dy, const bf16* x, int R, int n
   ++c->launches;
 }
 
-// cnet:forward (training) -> detection-stage criteria -> cnet:backward (objective.lua:164-179) on the R example rows in
-// c->t_rows ([R][bins][C] bf16) with targets c->crtarget / c->cctarget; leaves d(loss)/d(rows) in c->t_dx (fp32, same
-// layout) and adds the losses to c->losses_dev[2..3].
-static void run_cnet_train(frcnn_ctx* c, int R, int n_pos, const float* const* cnet_masks, uint64_t seed) {
+// cnet:forward (training) -> detection-stage criteria -> cnet:backward (objective.lua:164-179) for the example rows of
+// nf frames stored back to back in c->t_rows ([rows][bins][C] bf16; frame f = rows [off[f], off[f] + R[f])) with targets
+// c->crtarget / c->cctarget; leaves d(loss)/d(rows) in c->t_dx and adds frame f's losses to c->losses_dev[8 f + 2..3].
+// Stage-wise over the frames: every Linear layer is ONE tensor-core GEMM over all rows (forward, data gradient, weight
+// gradient), while BatchNormalization / PReLU / Dropout and the criteria run per frame on its row slice -- in the
+// reference cnet sees the ROI batch of one image at a time (objective.lua:164 inside the per-image loop), so the batch
+// statistics, the running-statistics updates (in frame order) and the mean over the frame's rows stay per frame.
+static void run_cnet_train_frames(frcnn_ctx* c, int nf, const int* off, const int* R, const int* n_pos, const float* const* cnet_masks,
+                                  const uint64_t* seeds) {
   cudaStream_t st = c->stream;
   const int bins = c->roi_kh * c->roi_kw;
+  const int rows = off[nf - 1] + R[nf - 1];
+  if (rows <= 0) return;
   // ---- cnet forward, training mode (objective.lua:164)
   const bf16* in = c->t_rows;
   for (size_t i = 0; i < c->fcs.size(); ++i) {
     FcLayer& f = c->fcs[i];
-    gemm_rows(c, in, f.w_packed, R, f.nin, f.nout, f.t_acc);
-    if (cnet_masks && cnet_masks[i]) FRCNN_CUDA_TRY(cudaMemcpyAsync(f.t_mask, cnet_masks[i], (size_t)R * f.nout * sizeof(float), cudaMemcpyDeviceToDevice, st));
-    else launch_dropout_mask(f.t_mask, R * f.nout, f.dropout, seed, 100u + (uint32_t)i, st);
-    FcTrainFwd ff;
-    ff.acc = f.t_acc; ff.bias = P(c, f.p_b); ff.bn_w = P(c, f.p_bn_w); ff.bn_b = P(c, f.p_bn_b); ff.prelu = P(c, f.p_prelu);
-    ff.bn_mean = const_cast<float*>(P(c, f.p_bn_mean)); ff.bn_var = const_cast<float*>(P(c, f.p_bn_var));
-    ff.mask = f.t_mask; ff.keep_scale = f.dropout > 0.f ? 1.f / (1.f - f.dropout) : 1.f;
-    ff.pre = f.t_pre; ff.xhat = f.t_xhat; ff.rstd = f.t_rstd; ff.out_bf16 = f.t_out; ff.out_f32 = f.t_out32; ff.R = R; ff.n = f.nout;
-    launch_fc_train_fwd(ff, st);
-    c->launches += 2;
+    gemm_rows(c, in, f.w_packed, rows, f.nin, f.nout, f.t_acc);
+    for (int fr = 0; fr < nf; ++fr) {
+      if (R[fr] <= 0) continue;
+      const size_t o = (size_t)off[fr] * f.nout;
+      if (cnet_masks && cnet_masks[i]) {
+        FRCNN_CUDA_TRY(cudaMemcpyAsync(f.t_mask + o, cnet_masks[i], (size_t)R[fr] * f.nout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      } else {
+        launch_dropout_mask(f.t_mask + o, R[fr] * f.nout, f.dropout, seeds[fr], 100u + (uint32_t)i, st);
+      }
+      FcTrainFwd ff;
+      ff.acc = f.t_acc + o; ff.bias = P(c, f.p_b); ff.bn_w = P(c, f.p_bn_w); ff.bn_b = P(c, f.p_bn_b); ff.prelu = P(c, f.p_prelu);
+      ff.bn_mean = const_cast<float*>(P(c, f.p_bn_mean)); ff.bn_var = const_cast<float*>(P(c, f.p_bn_var));
+      ff.mask = f.t_mask + o; ff.keep_scale = f.dropout > 0.f ? 1.f / (1.f - f.dropout) : 1.f;
+      ff.pre = f.t_pre + o; ff.xhat = f.t_xhat ? f.t_xhat + o : nullptr; ff.rstd = f.t_rstd + (size_t)fr * f.nout;
+      ff.out_bf16 = f.t_out + o; ff.out_f32 = f.t_out32 + o; ff.R = R[fr]; ff.n = f.nout;
+      launch_fc_train_fwd(ff, st);
+      c->launches += 2;
+    }
     in = f.t_out;
   }
-  // ---- detection-stage criteria + backward through the two output branches (objective.lua:166-179)
+  // ---- detection-stage criteria + backward through the two output branches (objective.lua:166-179), per frame
   FcLayer& last = c->fcs.back();
-  CnetLossParams cl;
-  cl.hidden = last.t_out32; cl.w_reg = P(c, c->p_reg_w); cl.b_reg = P(c, c->p_reg_b); cl.w_cls = P(c, c->p_cls_w); cl.b_cls = P(c, c->p_cls_b);
-  cl.crtarget = c->crtarget; cl.cctarget = c->cctarget; cl.R = R; cl.n_pos = n_pos; cl.nin = last.nout; cl.ncls = c->class_count + 1;
-  cl.d_hidden = c->t_dhidden; cl.dz = c->t_dz;
-  cl.g_w_reg = G(c, c->p_reg_w); cl.g_b_reg = G(c, c->p_reg_b); cl.g_w_cls = G(c, c->p_cls_w); cl.g_b_cls = G(c, c->p_cls_b);
-  cl.losses = c->losses_cur;
-  launch_cnet_loss_bwd(cl, st);
-  c->launches += 2;
+  const int no = c->class_count + 5;
+  for (int fr = 0; fr < nf; ++fr) {
+    if (R[fr] <= 0) continue;
+    CnetLossParams cl;
+    cl.hidden = last.t_out32 + (size_t)off[fr] * last.nout;
+    cl.w_reg = P(c, c->p_reg_w); cl.b_reg = P(c, c->p_reg_b); cl.w_cls = P(c, c->p_cls_w); cl.b_cls = P(c, c->p_cls_b);
+    cl.crtarget = c->crtarget + (size_t)off[fr] * 4; cl.cctarget = c->cctarget + off[fr];
+    cl.R = R[fr]; cl.n_pos = n_pos[fr]; cl.nin = last.nout; cl.ncls = c->class_count + 1;
+    cl.d_hidden = c->t_dhidden + (size_t)off[fr] * last.nout; cl.dz = c->t_dz + (size_t)off[fr] * no;
+    cl.g_w_reg = G(c, c->p_reg_w); cl.g_b_reg = G(c, c->p_reg_b); cl.g_w_cls = G(c, c->p_cls_w); cl.g_b_cls = G(c, c->p_cls_b);
+    cl.losses = nf == 1 ? c->losses_cur : c->losses_dev + 8 * fr;
+    launch_cnet_loss_bwd(cl, st);
+    c->launches += 2;
+  }
   // ---- cnet backward (objective.lua:179)
   const float* d_in = c->t_dhidden;
   for (int i = (int)c->fcs.size() - 1; i >= 0; --i) {
     FcLayer& f = c->fcs[i];
-    FcTrainBwd fb;
-    fb.d_in = d_in; fb.pre = f.t_pre; fb.xhat = f.t_xhat; fb.rstd = f.t_rstd; fb.bn_w = P(c, f.p_bn_w); fb.prelu = P(c, f.p_prelu);
-    fb.mask = f.t_mask; fb.keep_scale = f.dropout > 0.f ? 1.f / (1.f - f.dropout) : 1.f;
-    fb.d_out_bf16 = f.t_dy;
-    fb.g_bias = G(c, f.p_b); fb.g_bn_w = G(c, f.p_bn_w); fb.g_bn_b = G(c, f.p_bn_b); fb.g_prelu = G(c, f.p_prelu);
-    fb.R = R; fb.n = f.nout;
-    launch_fc_train_bwd(fb, st);
-    const bf16* x_in = i == 0 ? c->t_rows : c->fcs[i - 1].t_out;
-    // weight gradient: fp32 TMA reduce-add into dw_taps; inside frcnn_train_batch the frames of the batch accumulate
-    // there and the transposition into Torch's layout happens once per batch (cnet_wgrad_finish)
-    wgrad_rows(c, f.t_dy, x_in, R, f.nin, f.nout, f.dw_taps, !c->cnet_wgrad_deferred);
-    const bool perm = i == 0;
-    if (!c->cnet_wgrad_deferred) {
-      launch_wgrad_finish_fc(f.dw_taps, G(c, f.p_w), f.nout, perm ? c->feat_c : f.nin, perm ? bins : 1, perm ? 1 : 0, st);
+    for (int fr = 0; fr < nf; ++fr) {
+      if (R[fr] <= 0) continue;
+      const size_t o = (size_t)off[fr] * f.nout;
+      FcTrainBwd fb;
+      fb.d_in = d_in + o; fb.pre = f.t_pre + o; fb.xhat = f.t_xhat ? f.t_xhat + o : nullptr; fb.rstd = f.t_rstd + (size_t)fr * f.nout;
+      fb.bn_w = P(c, f.p_bn_w); fb.prelu = P(c, f.p_prelu);
+      fb.mask = f.t_mask + o; fb.keep_scale = f.dropout > 0.f ? 1.f / (1.f - f.dropout) : 1.f;
+      fb.d_out_bf16 = f.t_dy + o;
+      fb.g_bias = G(c, f.p_b); fb.g_bn_w = G(c, f.p_bn_w); fb.g_bn_b = G(c, f.p_bn_b); fb.g_prelu = G(c, f.p_prelu);
+      fb.R = R[fr]; fb.n = f.nout;
+      launch_fc_train_bwd(fb, st);
       ++c->launches;
     }
+    const bf16* x_in = i == 0 ? c->t_rows : c->fcs[i - 1].t_out;
+    // weight gradient over ALL rows: one fp32 TMA reduce-add GEMM into dw_taps, transposed into Torch's layout
+    wgrad_rows(c, f.t_dy, x_in, rows, f.nin, f.nout, f.dw_taps, true);
+    const bool perm = i == 0;
+    launch_wgrad_finish_fc(f.dw_taps, G(c, f.p_w), f.nout, perm ? c->feat_c : f.nin, perm ? bins : 1, perm ? 1 : 0, st);
+    ++c->launches;
     if (f.dgrad_gen != c->weights_gen) {  // the transposed bf16 weights of the data gradient: once per weight update
       launch_pack_fc_weight_dgrad(P(c, f.p_w), f.w_dgrad, f.nout, perm ? c->feat_c : f.nin, perm ? bins : 1, perm ? 1 : 0, st);
       f.dgrad_gen = c->weights_gen;
       ++c->launches;
     }
     float* d_prev = i == 0 ? c->t_dx : c->fcs[i - 1].t_din;
-    gemm_rows(c, f.t_dy, f.w_dgrad, R, f.nout, f.nin, d_prev);
-    ++c->launches;
+    gemm_rows(c, f.t_dy, f.w_dgrad, rows, f.nout, f.nin, d_prev);
     d_in = d_prev;
   }
+}
+
+static void run_cnet_train(frcnn_ctx* c, int R, int n_pos, const float* const* cnet_masks, uint64_t seed) {
+  const int off = 0;
+  run_cnet_train_frames(c, 1, &off, &R, &n_pos, cnet_masks, &seed);
 }
 
 // The per-image loop of lossAndGradient (objective.lua:65-198) for N frames of one size: pnet forward (training) and
@@ -1038,12 +1066,17 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
   for (auto g : c->grads) FRCNN_REQUIRE(g != nullptr, FRCNN_E_STATE, "frcnn_bind_grads must be called first");
   FRCNN_REQUIRE(N >= 1 && N <= 64, FRCNN_E_INVALID, "train: 1..64 frames per call");
   FRCNN_REQUIRE(cnet_masks == nullptr || N == 1, FRCNN_E_INVALID, "explicit cnet masks are a single-frame (test) facility");
-  int Rmax = 0;
-  for (int n = 0; n < N; ++n) Rmax = std::max(Rmax, n_pos[n] + n_neg[n]);
+  std::vector<int> off(N), Rn(N);
+  int rows = 0;
+  for (int n = 0; n < N; ++n) {
+    off[n] = rows;
+    Rn[n] = n_pos[n] + n_neg[n];
+    rows += Rn[n];
+  }
   cudaStream_t st = c->stream;
   ensure_pnet_workspace(c, N, H, W);
   ensure_train_workspace(c, N, H, W);
-  ensure_objective_workspace(c, Rmax);
+  ensure_objective_workspace(c, rows);
   // ---- pnet forward, training mode (objective.lua:60,71)
   int mi = 0;
   for (auto& cv : c->trunk) {
@@ -1061,43 +1094,43 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
   for (size_t i = 0; i < c->heads.size(); ++i)
     FRCNN_CUDA_TRY(cudaMemsetAsync(c->head_dout[i], 0, (size_t)N * 18 * c->heads[i].hh * c->heads[i].hw * sizeof(float), st));
   zero_block_grads(c);
-  const int bins = c->roi_kh * c->roi_kw;
+  const int bins = c->roi_kh * c->roi_kw, feat = bins * c->feat_c;
   const size_t fmap_elems = (size_t)c->feat_h * c->feat_w * c->feat_c;
-  for (auto& f : c->fcs) FRCNN_CUDA_TRY(cudaMemsetAsync(f.dw_taps, 0, (size_t)f.nin * f.nout * sizeof(float), st));
-  c->cnet_wgrad_deferred = true;
-  bool any_rows = false;
-  for (int n = 0; n < N; ++n) {
-    const int np = n_pos[n], nn = n_neg[n], R = np + nn;
-    if (R <= 0) continue;
-    c->losses_cur = c->losses_dev + 8 * n;
-    // ---- RPN criteria on the listed anchors (objective.lua:91-140)
-    if (np) FRCNN_CUDA_TRY(cudaMemcpyAsync(c->ex_dev, pos[n], (size_t)np * sizeof(ExampleDev), cudaMemcpyHostToDevice, st));
-    if (nn) FRCNN_CUDA_TRY(cudaMemcpyAsync(c->ex_dev + np, neg[n], (size_t)nn * sizeof(ExampleDev), cudaMemcpyHostToDevice, st));
-    RpnLossParams lp;
-    lp.ex = c->ex_dev; lp.n_pos = np; lp.n_neg = nn;
-    for (int i = 0; i < MAX_HEADS; ++i) {
-      const size_t per = (size_t)18 * c->heads[i].hh * c->heads[i].hw;
-      lp.out[i] = c->heads[i].out + n * per; lp.d_out[i] = c->head_dout[i] + n * per; lp.hh[i] = c->heads[i].hh; lp.hw[i] = c->heads[i].hw;
+  if (rows > 0) {
+    // all example records of the batch in one upload (frame f = rows [off[f], off[f] + R[f]): positives, then negatives)
+    std::vector<ExampleDev>& ex = c->ex_host;   // staging owned by the context: alive until the next call
+    ex.resize((size_t)rows);
+    for (int n = 0; n < N; ++n) {
+      if (n_pos[n]) memcpy(&ex[off[n]], pos[n], (size_t)n_pos[n] * sizeof(ExampleDev));
+      if (n_neg[n]) memcpy(&ex[off[n] + n_pos[n]], neg[n], (size_t)n_neg[n] * sizeof(ExampleDev));
     }
-    lp.crtarget = c->crtarget; lp.cctarget = c->cctarget; lp.bg_class = c->class_count; lp.rects = c->ex_rects;
-    lp.losses = c->losses_cur; lp.status = c->t_status;
-    launch_rpn_loss(lp, st);
-    // ---- ROI pooling of ground-truth rects / negative anchors (objective.lua:117-119,137-139)
-    launch_roi_pool_train(c->pool_out.back() + n * fmap_elems, c->feat_h, c->feat_w, c->feat_c, c->roi_kh, c->roi_kw, c->roi_loc,
-                          c->ex_rects, R, c->t_rows, c->t_argmax, c->t_status + 1, st);
-    c->launches += 2;
-    run_cnet_train(c, R, np, cnet_masks, seeds[n]);
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->ex_dev, ex.data(), (size_t)rows * sizeof(ExampleDev), cudaMemcpyHostToDevice, st));
+    for (int n = 0; n < N; ++n) {
+      if (Rn[n] <= 0) continue;
+      // ---- RPN criteria on the listed anchors (objective.lua:91-140)
+      RpnLossParams lp;
+      lp.ex = c->ex_dev + off[n]; lp.n_pos = n_pos[n]; lp.n_neg = n_neg[n];
+      for (int i = 0; i < MAX_HEADS; ++i) {
+        const size_t per = (size_t)18 * c->heads[i].hh * c->heads[i].hw;
+        lp.out[i] = c->heads[i].out + n * per; lp.d_out[i] = c->head_dout[i] + n * per; lp.hh[i] = c->heads[i].hh; lp.hw[i] = c->heads[i].hw;
+      }
+      lp.crtarget = c->crtarget + (size_t)off[n] * 4; lp.cctarget = c->cctarget + off[n]; lp.bg_class = c->class_count;
+      lp.rects = c->ex_rects + (size_t)off[n] * 4;
+      lp.losses = c->losses_dev + 8 * n; lp.status = c->t_status;
+      launch_rpn_loss(lp, st);
+      // ---- ROI pooling of ground-truth rects / negative anchors (objective.lua:117-119,137-139)
+      launch_roi_pool_train(c->pool_out.back() + n * fmap_elems, c->feat_h, c->feat_w, c->feat_c, c->roi_kh, c->roi_kw, c->roi_loc,
+                            c->ex_rects + (size_t)off[n] * 4, Rn[n], c->t_rows + (size_t)off[n] * feat, c->t_argmax + (size_t)off[n] * feat,
+                            c->t_status + 1, st);
+      c->launches += 2;
+    }
+    c->losses_cur = c->losses_dev;
+    run_cnet_train_frames(c, N, off.data(), Rn.data(), n_pos, cnet_masks, seeds);
     // ---- ROI-pool backward into delta_outputs[5] (objective.lua:182-185), kept as the fp32 NHWC block gradient
-    launch_roi_pool_bwd(c->t_dx, c->t_argmax, R, bins, c->feat_c, c->dblock.back() + n * fmap_elems, st);
-    ++c->launches;
-    any_rows = true;
-  }
-  c->cnet_wgrad_deferred = false;
-  if (any_rows) {
-    for (size_t i = 0; i < c->fcs.size(); ++i) {
-      FcLayer& f = c->fcs[i];
-      const bool perm = i == 0;
-      launch_wgrad_finish_fc(f.dw_taps, G(c, f.p_w), f.nout, perm ? c->feat_c : f.nin, perm ? bins : 1, perm ? 1 : 0, st);
+    for (int n = 0; n < N; ++n) {
+      if (Rn[n] <= 0) continue;
+      launch_roi_pool_bwd(c->t_dx + (size_t)off[n] * feat, c->t_argmax + (size_t)off[n] * feat, Rn[n], bins, c->feat_c,
+                          c->dblock.back() + n * fmap_elems, st);
       ++c->launches;
     }
   }

@@ -38,6 +38,20 @@ void set_global_error(const std::string& msg);
     if (!(cond)) throw ::frcnn::Error{(code), (text)};    \
   } while (0)
 
+// cudaFuncSetAttribute is per device: a `static bool configured` would skip the second device of a multi-device
+// process.  first_use_on_device(flags) is true once per (call site, device).
+struct DeviceOnce {
+  bool done[64] = {};
+};
+inline bool first_use_on_device(DeviceOnce& o) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  dev &= 63;
+  if (o.done[dev]) return false;
+  o.done[dev] = true;
+  return true;
+}
+
 // ------------------------------------------------------------------ conv / GEMM kernel interface
 enum ConvEpilogue {
   EPI_STORE = 0,       // y = prelu(acc + bias) * scale -> bf16 NHWC, staged in shared memory, written by TMA store
@@ -82,7 +96,8 @@ struct ConvParams {
   // halo-tile kernel (conv_halo_kernel): the A operand of ALL filter taps of one 64-channel chunk is ONE TMA box
   // {64 ch, BW + KW - 1, BH * MT + KH - 1} = the CTA tile plus its halo; tap (kh, kw) is a row offset of the UMMA
   // descriptor into that box.  BW = 8 (one 8-row descriptor group per tile row), BH = 16.
-  int halo;                 // 1: launched with conv_halo_kernel
+  int halo;                 // 1: launched with conv_halo_kernel (with wgrad: conv_wgrad_halo_kernel, MT = taps per unit)
+  int first_tma;            // first-layer kernel: eligible for conv_first_tma_kernel (16 x 8 tiles, Win % 4 == 0)
   int halo_desc;            // descriptor base-offset mode for the row-shifted start address (0: field left 0)
   const float* w2;          // EPI_HEAD: [18][256] weights of the 1x1 convolution (Torch layout)
   const float* b2;          // EPI_HEAD: [18] bias of the 1x1 convolution

@@ -1814,7 +1814,7 @@ void conv_first_prepare(ConvLaunch* L, const bf16* w_packed32, int N, int Hin, i
     p.tiles_w = (p.Wout + p.BW - 1) / p.BW;
     p.tiles_h = (p.Hout + p.BH - 1) / p.BH;
     p.n_tiles_m = N * p.tiles_h * p.tiles_w;
-    p.halo = 2;  // marks the TMA-patch variant as eligible
+    p.first_tma = 1;
   }
   p.Cimg = Cimg;
   p.n_tiles_n = 1;
@@ -1830,11 +1830,10 @@ void conv_first_prepare(ConvLaunch* L, const bf16* w_packed32, int N, int Hin, i
 
 template <int BN, int MT>
 static void launch_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
-  static bool configured = false;
+  static DeviceOnce configured;
   int smem = conv_smem_bytes_mt(BN, MT);
-  if (!configured) {
+  if (first_use_on_device(configured)) {
     FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_igemm_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   conv_igemm_kernel<BN, MT><<<grid, CONV_THREADS, smem, st>>>(maps, grp);
   FRCNN_CUDA_TRY(cudaGetLastError());
@@ -1842,11 +1841,10 @@ static void launch_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cud
 
 template <int BN, int MT, int KMAX>
 static void launch_halo_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
-  static bool configured = false;
+  static DeviceOnce configured;
   const int smem = halo_smem_bytes(BN, MT, KMAX);
-  if (!configured) {
+  if (first_use_on_device(configured)) {
     FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   conv_halo_kernel<BN, MT, KMAX><<<grid, CONV_THREADS, smem, st>>>(maps, grp);
   FRCNN_CUDA_TRY(cudaGetLastError());
@@ -1868,11 +1866,10 @@ static void launch_halo_key(int BN, int MT, const ConvMaps& maps, const ConvGrou
 
 template <int BN, int T>
 static void launch_wgrad_halo_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
-  static bool configured = false;
+  static DeviceOnce configured;
   const int smem = wgh_smem_bytes(BN);
-  if (!configured) {
+  if (first_use_on_device(configured)) {
     FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_wgrad_halo_kernel<BN, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   conv_wgrad_halo_kernel<BN, T><<<grid, CONV_THREADS, smem, st>>>(maps, grp);
   FRCNN_CUDA_TRY(cudaGetLastError());
@@ -1909,17 +1906,15 @@ void conv_launch(const ConvLaunch& L, cudaStream_t st) {
     grp.unit_end[g] = grp.unit_end[0];
   }
   if (L.first) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (first_use_on_device(configured)) {
       FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_SMEM));
-      configured = true;
     }
     FRCNN_REQUIRE(L.p.img != nullptr, FRCNN_E_STATE, "first-layer kernel: image pointer not set");
-    if (L.p.halo == 2 && L.p.scale == 1.0f && (reinterpret_cast<uintptr_t>(L.p.img) & 15) == 0) {
-      static bool configured_tma = false;
-      if (!configured_tma) {
+    if (L.p.first_tma && L.p.scale == 1.0f && (reinterpret_cast<uintptr_t>(L.p.img) & 15) == 0) {
+      static DeviceOnce configured_tma;
+      if (first_use_on_device(configured_tma)) {
         FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_first_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM));
-        configured_tma = true;
       }
       // tensor map over the caller's fp32 NCHW frames (a pure host-side encode, redone per launch: the pointer changes)
       const ConvParams& p = L.p;

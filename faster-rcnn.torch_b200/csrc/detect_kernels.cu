@@ -329,10 +329,9 @@ __global__ void __launch_bounds__(1024) group_by_class_kernel(GroupParams p, Nms
   }
 }
 void launch_group_by_class(const GroupParams& p, NmsWorkspace* ws, int N, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (first_use_on_device(configured)) {
     FRCNN_CUDA_TRY(cudaFuncSetAttribute(group_by_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
-    configured = true;
   }
   FRCNN_REQUIRE(p.cap <= 8192, FRCNN_E_INVALID, "candidate capacity per image must be <= 8192");
   int n2 = 1;

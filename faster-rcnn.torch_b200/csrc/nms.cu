@@ -859,22 +859,20 @@ int nms_run(NmsWorkspace* ws, const float* boxes_dev, int row_stride, int n_seg,
   int launches = 0;
   if (n_seg <= 0 || n_total_cap <= 0) return 0;
   FRCNN_REQUIRE(n_seg <= ws->cap_seg && n_total_cap <= ws->cap_total, FRCNN_E_INVALID, "nms: workspace capacity exceeded");
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (first_use_on_device(configured)) {
     FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_B * 33 * 4));
     FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_sort_cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_CTA_MAX * 8));
-    configured = true;
   }
   const bool small = max_seg_len <= SORT_CTA_MAX;
   if (small) {
     // CTA-level path: 3 launches (or 1 when fused)
-    static bool cta_configured = false;
+    static DeviceOnce cta_configured;
     const int mask_bytes = NMS_B * 33 * 4;
-    if (!cta_configured) {
+    if (first_use_on_device(cta_configured)) {
       FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_cta_kernel<NMS_PH_SORT_SELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_CTA_MAX * 8));
       FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_cta_kernel<NMS_PH_RESOLVE_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, mask_bytes));
       FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_cta_kernel<NMS_PH_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, mask_bytes));
-      cta_configured = true;
     }
     int n2 = 1;
     while (n2 < max_seg_len) n2 <<= 1;

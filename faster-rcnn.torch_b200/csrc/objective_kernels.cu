@@ -397,10 +397,9 @@ __global__ void __launch_bounds__(256) wgrad_finish_fc_kernel(const float* __res
   }
 }
 void launch_wgrad_finish_fc(const float* dw, float* grad, int nout, int C, int bins, int permute, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (first_use_on_device(configured)) {
     cudaFuncSetAttribute(wgrad_finish_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    configured = true;
   }
   const size_t smem = permute ? (size_t)C * bins * sizeof(float) : 0;
   FRCNN_REQUIRE(smem <= 96 * 1024, FRCNN_E_INVALID, "fc row too long for the transposing gradient accumulation");
