@@ -6,11 +6,15 @@
   python bench.py --impl reference --gpus N ...            the reference's CPU path (oracle restatement: the
                                                            reference is pure Lua/Torch7 and cannot run here)
 
-A step = one Detector:detect pass over one batch of synthetic frames.  `value` = frames of all ranks / device time
-of the K steps (CUDA events around every step on the library's stream, L2 flushed between steps, max over ranks)
-with the frames already resident in HBM; `e2e` = the same through frcnn_detect with HOST frames (pinned staging,
-H2D copy and D2H of the winners inside the timed region).  The roofline entry times the dominant kernel (the tcgen05
-implicit-GEMM conv) with an event pair around every launch.  One JSON line on stdout (rank 0)."""
+A step = one Detector:detect pass over one batch of synthetic frames (batch 1 = BASELINE configs[1]).  The measured
+configuration keeps `--in-flight` steps in flight (frcnn_detect_begin / frcnn_detect_end on that many library contexts,
+throughput schedule): `value` = frames of all ranks / device time of the K steps (one CUDA-event pair around the whole
+region, every step a different resident frame batch out of a set larger than L2, max over ranks); `e2e` = the same loop
+fed from page-locked HOST frames (the H2D copy of every step's frames and the D2H read of its winners inside the timed
+region).  `config.sync` is one step at a time through frcnn_detect_dev with the L2 flushed in between (latency).  The
+roofline entry is the algorithmic conv/GEMM FLOPs of the K steps over the same timed region (a lower bound of the tcgen05
+kernels' own rate); `roofline.sync_pass` keeps the per-launch event-pair numbers of synchronous steps.
+One JSON line on stdout (rank 0)."""
 import argparse
 import json
 import os

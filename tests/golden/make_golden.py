@@ -48,3 +48,34 @@ np.savez_compressed(
     logp=np.array([x["p"] for x in m], dtype=np.float32), r=np.array([x["r"].unpack() for x in m], dtype=np.float64),
     box=np.stack([x["r"].totensor() for x in m]))
 print("golden fixtures written:", len(m), "decode matches")
+
+# ---- anchor labelling, optimiser step, frame normalisation (next_rows.npz)
+from oracle import optim as OO, preprocess as OP  # noqa: E402
+rng = np.random.default_rng(3)
+rois = []
+for _ in range(6):
+    bw, bh = rng.uniform(20, 300), rng.uniform(20, 250)
+    x, y = rng.uniform(0, 800 - bw), rng.uniform(0, 450 - bh)
+    rois.append([x, y, x + bw, y + bh])
+rois[0] = [100, 100, 112, 109]          # too small for any positive anchor: the best-set branch
+rois = np.array(rois, dtype=np.float64)
+roi_list = [{"rect": Rect(*r)} for r in rois]
+img = Rect(0, 0, 800, 450)
+pos = small.findPositive(roi_list, img, 0.6, 0.3, True)
+idx = {id(r): i for i, r in enumerate(roi_list)}
+rnd = rng.integers(0, 2 ** 32, 3 * 600, dtype=np.uint64).astype(np.uint32)
+neg, trials = small.sampleNegative(img, roi_list, 0.3, 96, rnd)
+w = rng.standard_normal(4099).astype(np.float32)
+gsteps = [(rng.standard_normal(4099) * 10.0 ** rng.integers(-5, 2, 4099)).astype(np.float32) for _ in range(3)]
+w_ref, st = w.copy(), {}
+for gstep in gsteps:
+    OO.rmsprop_step(w_ref, OO.gradient_div(gstep, 37.0), st, learningRate=1e-3, alpha=0.99, epsilon=1e-8, weightDecay=0.0005)
+frame = rng.uniform(0, 1, (3, 45, 80)).astype(np.float32)
+frame[:, 10:25, 20:50] += 0.7
+np.savez_compressed(
+    os.path.join(out, "next_rows.npz"), rois=rois,
+    pos=np.array([[a.layer, a.aspect, a.index[1], a.index[2], idx[id(r)]] for a, r in pos], dtype=np.int32),
+    rnd=rnd, neg=np.array([[a.layer, a.aspect, a.index[1], a.index[2]] for (a,) in neg], dtype=np.int32), neg_trials=np.int32(trials),
+    opt_w0=w, opt_g=np.stack(gsteps), opt_w3=w_ref, opt_m3=st["m"],
+    frame=frame, frame_norm=OP.normalize_frame(torch.from_numpy(frame), rgb_to_yuv=True).numpy())
+print("next_rows fixture:", len(pos), "positives,", len(neg), "negatives in", trials, "trials")
