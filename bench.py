@@ -286,8 +286,11 @@ def run_b200(args):
         def step_dev():
             F.nms_segmented_dev(bd, local_seg, 0.25, model=m)
 
+        picked = dict(n=0)
+
         def step_host():
-            F.nms_segmented(local_boxes, local_seg, 0.25, model=m)
+            _, cnts = F.nms_segmented(local_boxes, local_seg, 0.25, model=m)
+            picked["n"] = int(cnts.sum())
 
         sampler.start()
         ms = max_over_ranks(timed(step_dev, args.steps, args.warmup))
@@ -302,7 +305,8 @@ def run_b200(args):
                                 l2="flushed between steps", sharding="class segments round-robin over ranks, no collective"),
                     clocks=clocks,
                     e2e=dict(value=total * args.steps / (ms_e2e * 1e-3), unit="boxes/s", h2d_bytes_per_step=int(local_boxes.nbytes),
-                             d2h_bytes_per_step=int(8 * len(local_boxes) + 8 * len(mine))),
+                             d2h_bytes_per_step=int(8 * picked["n"] + 8 * len(mine)),
+                             note="boxes from page-locked host memory; the counts and the picked indices of every class come back"),
                     gpu_launches=int(launches),
                     roofline=dict(bound="hbm", achieved=20.0 * total * args.steps / (ms * 1e-3) / 1e9 / world, peak=pk["hbm"], unit="GB/s",
                                   frac=20.0 * total * args.steps / (ms * 1e-3) / 1e9 / world / pk["hbm"], traffic=None,

@@ -2013,8 +2013,19 @@ int frcnn_nms_segmented(frcnn_ctx* c, const float* boxes_host, int64_t row_strid
   int64_t* d_counts = (int64_t*)((uint8_t*)c->nms_stage + b_boxes + b_pick);
   FRCNN_CUDA_TRY(cudaMemcpyAsync(d_boxes, boxes_host, (size_t)n * row_stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   nms_dev_impl(c, d_boxes, n, row_stride, seg_offsets_host, n_seg, overlap, order_mode, order_col, d_pick, d_counts);
+  // results: the counts first, then only the picked prefix of every segment (the picks are a small fraction of the
+  // boxes: copying all n int64 slots back cost more than the NMS itself)
   FRCNN_CUDA_TRY(cudaMemcpyAsync(counts_host, d_counts, n_seg * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-  FRCNN_CUDA_TRY(cudaMemcpyAsync(pick_host, d_pick, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  if ((size_t)n * sizeof(int64_t) <= (256u << 10)) {   // small problem: one copy and one synchronisation beat per-segment copies
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(pick_host, d_pick, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return FRCNN_OK;
+  }
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  for (int sgm = 0; sgm < n_seg; ++sgm) {
+    const int64_t a = seg_offsets_host[sgm], cnt = counts_host[sgm];
+    if (cnt > 0) FRCNN_CUDA_TRY(cudaMemcpyAsync(pick_host + a, d_pick + a, (size_t)cnt * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+  }
   FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   API_END(c)
 }
