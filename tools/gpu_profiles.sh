@@ -27,3 +27,6 @@ for b in 1 8; do
 done
 du -sh gpurun_out
 timeout 300 python tools/bench_next_rows.py > gpurun_out/r1b_next_rows.jsonl 2>&1; cat gpurun_out/r1b_next_rows.jsonl | cut -c1-400
+bash tools/gpu_nms_sweep.sh > /dev/null 2>&1; wc -l gpurun_out/r1b_nms_sweep.jsonl
+bash tools/gpu_trainll.sh 2>&1 | tail -32 > gpurun_out/r1b_train_launches.txt; head -3 gpurun_out/r1b_train_launches.txt
+timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2
