@@ -1622,7 +1622,10 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
   // halo-tile kernel: k x k (k = 2, 3) filters with a bf16 epilogue.  force_mt: 0 = automatic, 1 / 2 = tap-per-box
   // kernel with that MT, 11 / 12 = halo kernel with MT 1 / 2
   {
-    const bool eligible = !f32 && KH <= HALO_MAXK && KW <= HALO_MAXK && KH * KW > 1 && Cout % 64 == 0;
+    // (also the unsplit fp32 reduce-add mode: the data gradients that accumulate into a block gradient, where the
+    // tap-per-box kernel's narrow N tiles are the most ingress-bound)
+    const bool f32_single = mode == EPI_F32_REDUCE && force_splits == 1;
+    const bool eligible = (!f32 || f32_single) && KH <= HALO_MAXK && KW <= HALO_MAXK && KH * KW > 1 && Cout % 64 == 0;
     const bool forced = force_mt >= 10;
     FRCNN_REQUIRE(!forced || eligible, FRCNN_E_INVALID, "conv: the halo kernel needs 2x2..3x3 filters and a bf16 epilogue");
     if (eligible && (forced || (force_mt == 0 && env_int("FRCNN_CONV_HALO", 1)))) {
@@ -1640,6 +1643,9 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
         mt = force_mt - 10;
         bn = force_bn > 0 ? force_bn : (Cout % 256 == 0 ? 256 : (Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : 64)));
         if (!halo_cfg_ok(Cout, bn, mt)) bn = 0;
+      } else if (f32_single && force_bn == 0 && Cout % 192 != 0 && Cout % 256 != 0) {
+        bn = Cout % 128 == 0 ? 128 : 64;
+        mt = 2;
       } else if (force_bn == 0 || force_bn >= 192) {
         if ((force_bn == 0 || force_bn == 256) && Cout % 256 == 0) {
           bn = 256;
