@@ -116,3 +116,16 @@ def test_nms_order_dispatch(F):
     assert _order(5) == (ORDER_COLUMN, 4)
     assert _order("area") == (ORDER_AREA, 0)
     assert _order(np.zeros(3)) == (ORDER_Y2, 0) and _order(None) == (ORDER_Y2, 0) and _order("score") == (ORDER_Y2, 0)
+
+
+def test_example_record_layout_matches_header():
+    """Model.pack_examples marshals frcnn_example[] as a numpy record array: field offsets and the record size must equal the
+    C struct's (include/frcnn_b200.h), or frcnn_train_image / frcnn_train_batch would read garbage."""
+    import importlib
+    F = importlib.import_module("frcnn_b200")
+    from frcnn_b200 import ffi
+    dt = F.Model._EXAMPLE_DTYPE
+    assert dt.itemsize == ffi.sizeof("frcnn_example")
+    for name in ("anchor", "roi", "reg_target", "layer", "aspect", "y", "x", "class_index"):
+        assert dt.fields[name][1] == ffi.offsetof("frcnn_example", name), name
+    assert ffi.sizeof("frcnn_anchor_ref") == 16

@@ -19,7 +19,16 @@ LAYERS = [  # name, h, w, cin, cout, pool
 ]
 
 
+LARGE = [  # vgg_large at 1000x600: the layers vgg_small does not have (FRCNN_BENCH_MODEL=large)
+    ("conv1_2+pool", 600, 1000, 64, 64, 1), ("conv2_2+pool", 300, 500, 128, 128, 1), ("conv3_3+pool", 150, 250, 256, 256, 1),
+    ("conv4_1", 75, 125, 256, 512, 0), ("conv4_3+pool", 75, 125, 512, 512, 1),
+]
+
+
 def main():
+    global LAYERS
+    if os.environ.get("FRCNN_BENCH_MODEL") == "large":
+        LAYERS = LARGE
     batches = [int(a) for a in sys.argv[1:]] or [1, 8]
     m = F.vgg_small(F.duplo_cfg)
     ffi, L = F.ffi, F.lib()
