@@ -2208,8 +2208,8 @@ int frcnn_find_positive(frcnn_ctx* c, const double* rois_host, int n_rois, const
 }
 
 int frcnn_sample_negative(frcnn_ctx* c, const double image_rect[4], const double* rois_host, int n_rois, double neg_threshold, int count,
-                          const uint32_t* rnd_host, int n_trials, frcnn_anchor_ref* out_host, int cap, int* n_out, int* trials_consumed,
-                          int* finished) {
+                          const uint32_t* rnd_host, int n_trials, int retry_in, frcnn_anchor_ref* out_host, int cap, int* n_out,
+                          int* trials_consumed, int* finished, int* retry_out) {
   API_BEGIN(c)
   REQUIRE_DEVICE(c);
   FRCNN_REQUIRE(image_rect && n_out && trials_consumed && finished && cap >= 0 && n_rois >= 0 && n_trials >= 0 &&
@@ -2226,14 +2226,14 @@ int frcnn_sample_negative(frcnn_ctx* c, const double image_rect[4], const double
   p.w_lut = c->d_w_lut; p.h_lut = c->d_h_lut; p.n_scales = n_scales;
   for (int k = 0; k < 4; ++k) p.image_rect[k] = image_rect[k];
   p.rois = (const double*)mem; p.n_rois = n_rois; p.neg_threshold = neg_threshold; p.count = count;
-  p.rnd = (const uint32_t*)(mem + b_rois); p.n_trials = n_trials;
+  p.rnd = (const uint32_t*)(mem + b_rois); p.n_trials = n_trials; p.retry_in = retry_in < 0 ? 0 : retry_in;
   p.out = (frcnn_anchor_ref*)(mem + b_rois + b_rnd); p.cap = cap;
   p.result = (int*)(mem + b_rois + b_rnd + b_out);
   if (n_rois) FRCNN_CUDA_TRY(cudaMemcpyAsync(mem, rois_host, (size_t)n_rois * 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   if (n_trials) FRCNN_CUDA_TRY(cudaMemcpyAsync(mem + b_rois, rnd_host, (size_t)n_trials * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
   frcnn::launch_sample_negative(p, c->stream);
   ++c->launches;
-  int res[4];
+  int res[5];
   FRCNN_CUDA_TRY(cudaMemcpyAsync(res, p.result, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
   FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   FRCNN_REQUIRE(res[0] == 0 || out_host, FRCNN_E_INVALID, "null output");
@@ -2241,6 +2241,7 @@ int frcnn_sample_negative(frcnn_ctx* c, const double image_rect[4], const double
   *n_out = res[0];
   *trials_consumed = res[1];
   *finished = res[2];
+  if (retry_out) *retry_out = res[4];
   FRCNN_REQUIRE(count <= cap || res[0] < cap, FRCNN_E_OVERFLOW, "sample_negative: output capacity smaller than count");
   API_END(c)
 }

@@ -35,7 +35,8 @@ struct SampleNegativeParams {
   int n_trials;
   frcnn_anchor_ref* out;
   int cap;
-  int* result;                  // {n_out, trials consumed, stopping rule fired, #ranges}
+  int retry_in;                 // consecutive rejections carried over from a previous call of the same loop
+  int* result;                  // {n_out, trials consumed, stopping rule fired, #ranges, retry at the end}
 };
 void launch_sample_negative(const SampleNegativeParams& p, cudaStream_t st);
 

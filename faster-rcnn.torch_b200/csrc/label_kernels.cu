@@ -258,8 +258,8 @@ __global__ void __launch_bounds__(LB_THREADS) sample_negative_kernel(SampleNegat
     n_ranges = n;
   }
   __syncthreads();
-  int n_neg = 0, retry = 0, consumed = 0;   // identical in every thread
-  bool done = n_ranges == 0 || p.count <= 0;
+  int n_neg = 0, retry = p.retry_in, consumed = 0;   // identical in every thread
+  bool done = n_ranges == 0 || p.count <= 0 || retry >= 500;
   for (int base = 0; base < p.n_trials && !done; base += LB_THREADS) {
     const int t = base + threadIdx.x;
     bool live = t < p.n_trials, reject = false;
@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(LB_THREADS) sample_negative_kernel(SampleNegat
     p.result[1] = consumed;
     p.result[2] = done ? 1 : 0;     // 0: the random stream ran out before the loop's stopping rule fired
     p.result[3] = n_ranges;
+    p.result[4] = retry;            // consecutive rejections at the end (continue a run with retry_in = this)
   }
 }
 

@@ -79,20 +79,22 @@ class Anchors:
             break
         return [(self.get(out[i].layer, out[i].aspect, out[i].y, out[i].x), roi_list[out_roi[i]]) for i in range(n_out[0])]
 
-    def sampleNegative(self, image_rect, roi_list, neg_threshold, count, rnd):  # Anchors.lua:197-235
+    def sampleNegative(self, image_rect, roi_list, neg_threshold, count, rnd, retry=0, return_retry=False):  # Anchors.lua:197-235
         """`rnd`: numpy uint32 array of torch.random() values, three per trial (the RNG contract: the caller owns the
-        generator).  Returns ([(anchor_rect,), ...], trials consumed, finished)."""
+        generator).  Returns ([(anchor_rect,), ...], trials consumed, finished[, retry]); `retry` continues a loop whose
+        random stream ran out (pass the returned retry and the remaining count)."""
         rnd = np.ascontiguousarray(rnd, dtype=np.uint32)
         n_trials = len(rnd) // 3
         rois = np.ascontiguousarray([list(r["rect"].unpack()) for r in roi_list], dtype=np.float64).reshape(-1)
         img = ffi.new("double[4]", list(image_rect.unpack()))
         cap = max(count, 1)
         out = ffi.new("frcnn_anchor_ref[]", cap)
-        n_out, used, fin = ffi.new("int*"), ffi.new("int*"), ffi.new("int*")
+        n_out, used, fin, rt = ffi.new("int*"), ffi.new("int*"), ffi.new("int*"), ffi.new("int*")
         check(self.model.ctx, lib().frcnn_sample_negative(self.model.ctx, img, ffi.cast("const double*", rois.ctypes.data) if len(roi_list) else ffi.NULL,
                                                           len(roi_list), neg_threshold, count, ffi.cast("const uint32_t*", rnd.ctypes.data),
-                                                          n_trials, out, cap, n_out, used, fin))
-        return [(self.get(out[i].layer, out[i].aspect, out[i].y, out[i].x),) for i in range(n_out[0])], used[0], bool(fin[0])
+                                                          n_trials, int(retry), out, cap, n_out, used, fin, rt))
+        res = [(self.get(out[i].layer, out[i].aspect, out[i].y, out[i].x),) for i in range(n_out[0])]
+        return (res, used[0], bool(fin[0]), rt[0]) if return_retry else (res, used[0], bool(fin[0]))
 
     @staticmethod
     def inputToAnchor(anchor, rect):  # Anchors.lua:237-243

@@ -199,8 +199,10 @@ function M.find_positive(model, anchors, roi_list, clip_rect, pos_threshold, neg
 end
 
 -- Anchors:sampleNegative (Anchors.lua:197-235).  The generator stays in Lua: three torch.random() values per trial are
--- drawn here and handed over; the reference consumes exactly `used` trials, so over-drawn values are discarded only
--- when the caller does not care about stream equality (pass `exact_stream = true` to draw trial by trial instead).
+-- drawn here and handed over.  The reference consumes exactly three values per trial it runs, so the generator is put
+-- back and advanced by 3 * used afterwards: the Lua random stream stays identical to the reference's.  If the drawn
+-- stream runs out before the loop's stopping rule fires (more than 500 rejections spread between the accepts) the loop
+-- is continued with the remaining count and the carried run of rejections.
 function M.sample_negative(model, anchors, image_rect, roi_list, neg_threshold, count)
   local ctx, n = model.b200.ctx, #roi_list
   local rois = ffi.new('double[?]', math.max(4 * n, 1))
@@ -210,15 +212,18 @@ function M.sample_negative(model, anchors, image_rect, roi_list, neg_threshold, 
   end
   local img = ffi.new('double[4]', image_rect.minX, image_rect.minY, image_rect.maxX, image_rect.maxY)
   local neg, out = {}, ffi.new('frcnn_anchor_ref[?]', math.max(count, 1))
-  local cnt, used, fin = ffi.new('int[1]'), ffi.new('int[1]'), ffi.new('int[1]')
-  local need = count
+  local cnt, used, fin, retry = ffi.new('int[1]'), ffi.new('int[1]'), ffi.new('int[1]'), ffi.new('int[1]')
+  local need, carried = count, 0
   repeat
     local trials = need + 500
     local rnd = ffi.new('uint32_t[?]', 3 * trials)
+    local rng_state = torch.getRNGState()
     for i = 0, 3 * trials - 1 do rnd[i] = torch.random() end
-    check(ctx, C.frcnn_sample_negative(ctx, img, rois, n, neg_threshold, need, rnd, trials, out, need, cnt, used, fin))
+    check(ctx, C.frcnn_sample_negative(ctx, img, rois, n, neg_threshold, need, rnd, trials, carried, out, need, cnt, used, fin, retry))
+    torch.setRNGState(rng_state)
+    for i = 1, 3 * used[0] do torch.random() end
     for i = 0, cnt[0] - 1 do neg[#neg + 1] = { anchors:get(out[i].layer, out[i].aspect, out[i].y, out[i].x) } end
-    need = need - cnt[0]
+    need, carried = need - cnt[0], retry[0]
   until fin[0] == 1 or need <= 0
   return neg
 end

@@ -284,10 +284,12 @@ int frcnn_find_positive(frcnn_ctx* ctx, const double* rois_host, int n_rois, con
  * values per trial (range, x, y); the caller supplies that stream: rnd_host holds 3 * n_trials uint32 values.  Returns
  * the accepted anchors in order, how many trials the loop consumed (so the caller can keep its generator in step) and
  * whether the loop's own stopping rule fired (count reached, or 500 consecutive rejections) before the supplied
- * stream ran out (*finished == 0: call again with more random numbers). */
+ * stream ran out (*finished == 0: call again with more random numbers, count reduced by *n_out and retry_in set to
+ * *retry_out, the run of rejections the loop was in; retry_in = 0 for a fresh loop; retry_out may be NULL). */
 int frcnn_sample_negative(frcnn_ctx* ctx, const double image_rect[4], const double* rois_host, int n_rois,
-                          double neg_threshold, int count, const uint32_t* rnd_host, int n_trials,
-                          frcnn_anchor_ref* out_host, int cap, int* n_out, int* trials_consumed, int* finished);
+                          double neg_threshold, int count, const uint32_t* rnd_host, int n_trials, int retry_in,
+                          frcnn_anchor_ref* out_host, int cap, int* n_out, int* trials_consumed, int* finished,
+                          int* retry_out);
 
 /* ---- optimiser step on the flat buffers: replaces gradient:div(cls_count) (objective.lua:200) + optim.rmsprop
  *      (main.lua:122,133) -- SURVEY 8f row 3 ------------------------------------------------------------------ */

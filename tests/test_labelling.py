@@ -109,3 +109,31 @@ def test_gpu_sample_negative_stopping_rules(F, small_model):
     want, trials = oa.sampleNegative(img, rois, 0.02, 40, rnd)
     got, used, finished = ga.sampleNegative(img, rois, 0.02, 40, rnd)
     assert [_ref(a) for (a,) in got] == [_ref(a) for (a,) in want] and used == trials
+
+
+@pytest.mark.gpu
+def test_gpu_sample_negative_continued_stream(F, small_model):
+    """A loop whose random stream is handed over in pieces (remaining count + carried run of rejections) returns what
+    the uninterrupted loop returns: the accepted anchors, the number of trials, and the stopping rule."""
+    ga = F.Anchors(small_model)
+    oa = _oracle_anchors()
+    rng = np.random.default_rng(9)
+    rnd = rng.integers(0, 2 ** 32, 3 * 1500, dtype=np.uint64).astype(np.uint32)
+    img = Rect(0, 0, 800, 450)
+    rois = [{"rect": Rect(0, 0, 800, 450)}]          # threshold 0.02: most trials are rejected
+    want, trials = oa.sampleNegative(img, rois, 0.02, 40, rnd)
+    got, pos, need, retry, finished = [], 0, 40, 0, False
+    for piece in (70, 130, 300, 1000):
+        part, used, finished, retry = ga.sampleNegative(img, rois, 0.02, need, rnd[3 * pos:3 * (pos + piece)], retry=retry, return_retry=True)
+        got += part
+        pos += used
+        need -= len(part)
+        if finished:
+            break
+    assert finished and pos == trials
+    assert [_ref(a) for (a,) in got] == [_ref(a) for (a,) in want]
+    # the give-up rule across pieces: 500 consecutive rejections in total
+    part, used, finished, retry = ga.sampleNegative(img, rois, -1.0, 5, rnd[:3 * 300], return_retry=True)
+    assert part == [] and used == 300 and not finished and retry == 300
+    part, used, finished, retry = ga.sampleNegative(img, rois, -1.0, 5, rnd[3 * 300:3 * 900], retry=retry, return_retry=True)
+    assert part == [] and used == 200 and finished
