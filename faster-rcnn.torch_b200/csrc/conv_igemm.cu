@@ -17,16 +17,23 @@
 // layout -- and is consumed by four tcgen05.mma (M=128, N=BN, K=16) per 64-channel chunk and 128-row sub-tile.
 // MT = 2 halves the weight traffic per MAC for the narrow (Cout <= 128) layers, which are L2->SM bandwidth bound.
 //
-// Kernel structure (persistent, warp-specialised, 256 threads, 1 CTA / SM):
-//   warp 0   TMA producer   (one elected lane)        smem ring: full[s] / empty[s] mbarriers
-//   warp 1   MMA issuer     (one elected lane)        TMEM accumulators double-buffered: tmem_full / tmem_empty
-//   warp 2   TMEM allocator
-//   warps 4-7 epilogue: tcgen05.ld 32x32b -> bias (smem) + PReLU + scale -> bf16 -> swizzled smem tile
-//             [-> 2x2 max pool in smem] -> one TMA tensor store per 64-channel group (coalesced, clips borders);
-//             or fp32 red.add for split-K (cnet, anchor heads).
+// Kernel structure (persistent, warp-specialised, 384 threads, 1 CTA / SM):
+//   warp 0    TMA producer   (one elected lane)        smem ring: full[s] / empty[s] mbarriers
+//   warp 1    MMA issuer     (one elected lane)        TMEM accumulators double-buffered: tmem_full / tmem_empty
+//   warp 2    TMEM allocator
+//   warps 4-11 epilogue: tcgen05.ld 32x32b -> bias (smem) + PReLU + scale -> bf16 -> swizzled smem tile
+//             [-> 2x2 max pool in smem] -> coalesced 16-byte global stores (borders clipped);
+//             or fp32 slices / TMA reduce-add for split-K (cnet, anchor heads, weight and data gradients).
 //
-// conv_first_kernel: the 3-channel first layer.  Same MMA / epilogue, but the A operand (K = 27 padded to 32) is
-// built in shared memory by four producer warps straight from the fp32 NCHW frame -- no im2col buffer in HBM.
+// Kernels of this file (all share the warp roles and, except the first-layer ones, epilogue_loop):
+//   conv_igemm_kernel<BN, MT>        one TMA box per filter tap (any k x k, GEMMs, split-K, weight-gradient mode)
+//   conv_halo_kernel<BN, MT, KMAX>   tile + halo in ONE box per 64-channel chunk, taps = row-shifted UMMA descriptors
+//                                    (the wide 3x3 layers; KMAX = 7: the fused anchor heads with epilogue_head)
+//   conv_wgrad_halo_kernel<BN, T>    weight gradient, T filter taps per unit sharing one dY box and one X halo box
+//   conv_first_kernel                the 3-channel first layer: the A operand (K = 27 padded to 32) is built in shared
+//                                    memory by producer warps straight from the fp32 NCHW frame (any frame)
+//   conv_first_tma_kernel            the same with the input patch brought in by TMA, the bias through the tensor core
+//                                    and four accumulator stages (16-byte aligned frames with W % 4 == 0)
 #include <stdio.h>
 #include <stdlib.h>
 
