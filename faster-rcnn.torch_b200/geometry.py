@@ -50,6 +50,51 @@ class Anchors:
         check(model.ctx, lib().frcnn_anchors_build(model.ctx, w, h))
         self.w = np.frombuffer(ffi.buffer(w), dtype=np.float32).reshape(len(scales), 3, 200, 2).copy()
         self.h = np.frombuffer(ffi.buffer(h), dtype=np.float32).reshape(len(scales), 3, 200, 2).copy()
+        # centre-point bins for findNearby (Anchors.lua:22-30,46,54): key = floor(centre / BIN_SIZE) -> {scale, aspect, cell}
+        self.cx, self.cy = {}, {}
+        for i, loc in enumerate(self.localizers):
+            for j in range(3):
+                for v in range(1, 201):
+                    cy = loc.featureToInputRect(0, v - 1, 0, v).center()[1]
+                    cx = loc.featureToInputRect(v - 1, 0, v, 0).center()[0]
+                    self.cy.setdefault(math.floor(cy / self.BIN_SIZE), []).append((i + 1, j + 1, v))
+                    self.cx.setdefault(math.floor(cx / self.BIN_SIZE), []).append((i + 1, j + 1, v))
+
+    BIN_SIZE = 16  # Anchors.lua:5
+
+    def findNearby(self, centerX, centerY):  # Anchors.lua:69-84 (host-side, like the reference)
+        found = []
+        xl = self.cx.get(math.floor(centerX / self.BIN_SIZE))
+        yl = self.cy.get(math.floor(centerY / self.BIN_SIZE))
+        if xl and yl:
+            for y in yl:
+                for x in xl:
+                    if y[0] == x[0] and y[1] == x[1]:
+                        found.append(self.get(y[0], y[1], y[2], x[2]))
+        return found
+
+    def findRangesXY(self, rect, clip_rect=None):  # Anchors.lua:86-145 (host-side; the device twin lives in label_kernels.cu)
+        """Per (scale, aspect) the 1-based LUT cell ranges [lx, ux) x [ly, uy) of the anchors that touch `rect` (and lie
+        inside `clip_rect`): list of dicts {layer, aspect, lx, ly, ux, uy, xs, ys} like the Lua tables."""
+        def lower_bound(t, value):   # first 1-based index with t[i] >= value
+            return int(np.searchsorted(t, value, side="left")) + 1
+
+        def upper_bound(t, value):   # first 1-based index with t[i] > value
+            return int(np.searchsorted(t, value, side="right")) + 1
+
+        ranges = []
+        w, h = self.w.astype(np.float64), self.h.astype(np.float64)
+        for i in range(w.shape[0]):
+            for j in range(3):
+                lx, ly = upper_bound(w[i, j, :, 1], rect.minX), upper_bound(h[i, j, :, 1], rect.minY)
+                ux, uy = lower_bound(w[i, j, :, 0], rect.maxX), lower_bound(h[i, j, :, 0], rect.maxY)
+                if clip_rect is not None:
+                    lx, ly = max(lx, lower_bound(w[i, j, :, 0], clip_rect.minX)), max(ly, lower_bound(h[i, j, :, 0], clip_rect.minY))
+                    ux, uy = min(ux, upper_bound(w[i, j, :, 1], clip_rect.maxX)), min(uy, upper_bound(h[i, j, :, 1], clip_rect.maxY))
+                if ux > lx and uy > ly:
+                    ranges.append(dict(layer=i + 1, aspect=j + 1, lx=lx, ly=ly, ux=ux, uy=uy,
+                                       xs=self.w[i, j, lx - 1:ux - 1, :], ys=self.h[i, j, ly - 1:uy - 1, :]))
+        return ranges
 
     def get(self, layer, aspect, y, x):  # Anchors.lua:60-67, 1-based indices
         w, h = self.w, self.h

@@ -164,3 +164,28 @@ def test_golden_fixtures():
     assert np.array_equal(ON.nms(b, 0.25), g["nms_pick_025"])
     assert np.array_equal(ON.nms(b, 0.1), g["nms_pick_010"])
     assert np.array_equal(ON.nms(b, 0.25, "area"), g["nms_pick_area"])
+
+
+def test_host_mirror_anchor_lookups_match_oracle():
+    """Anchors:findRangesXY / Anchors:findNearby of the host mirror (host-side logic, like the reference's) against the
+    oracle on a host-only context (no GPU needed): same ranges, same anchors, same order."""
+    import frcnn_b200 as F
+    m = F.vgg_small(F.duplo_cfg, device=-1)
+    ga = F.Anchors(m)
+    oa = OA.Anchors(OM.VGG_SMALL["layers"], OM.VGG_SMALL["anchor_nets"], OM.CFG_DUPLO["scales"])
+    assert np.array_equal(ga.w, oa.w) and np.array_equal(ga.h, oa.h)
+    rng = np.random.default_rng(4)
+    img = Rect(0, 0, 800, 450)
+    for _ in range(20):
+        bw, bh = rng.uniform(5, 400), rng.uniform(5, 300)
+        x, y = rng.uniform(-40, 800 - bw), rng.uniform(-40, 450 - bh)
+        r = Rect(x, y, x + bw, y + bh)
+        for clip in (None, img):
+            a, b = ga.findRangesXY(r, clip), oa.findRangesXY(r, clip)
+            assert [(q["layer"], q["aspect"], q["lx"], q["ly"], q["ux"], q["uy"]) for q in a] == \
+                   [(q["layer"], q["aspect"], q["lx"], q["ly"], q["ux"], q["uy"]) for q in b]
+        cx, cy = rng.uniform(0, 800), rng.uniform(0, 450)
+        fa, fb = ga.findNearby(cx, cy), oa.findNearby(cx, cy)
+        assert [(q.layer, q.aspect, q.index[1], q.index[2]) for q in fa] == [(q.layer, q.aspect, q.index[1], q.index[2]) for q in fb]
+    assert len(ga.findNearby(400.0, 225.0)) > 0
+    m.close()
