@@ -151,7 +151,7 @@ struct frcnn_ctx {
   int4* cand_anchor = nullptr;
   int* cand_count = nullptr;
   int* flags = nullptr;      // [0] candidate overflow, [1] degenerate ROIs, [2] roi_total, [3] n_det
-  int* ticket = nullptr;
+  unsigned long long* ticket = nullptr;
   unsigned long long* status = nullptr;
   int status_blocks = 0;
   int decode_nblocks = 0;      // block count the ticket / scan-state words are currently valid for
@@ -159,13 +159,16 @@ struct frcnn_ctx {
   // CUDA graph of the detect pipeline (replayed while image pointer / shape / thresholds stay the same)
   bool graph_enabled = true;
   int schedule = FRCNN_SCHED_LATENCY;  // frcnn_set_schedule
+  int eval_f16 = 1;            // frcnn_set_eval_precision: evaluate-mode operands fp16 (default) or bf16
+  int act_f16 = 0;             // 16-bit format of the activations the last pnet forward left in the workspace
   cudaGraphExec_t graph_exec = nullptr;
   struct GraphKey { const float* img; int N, H, W; double thr_fg, thr_class; float thr_nms1, thr_nms2; long gen; } graph_key = {};
   GraphKey eager_key = {};     // key of the last eager run (a config is captured on its second use)
   void* nms_stage = nullptr;   // device staging of the host-side nms entry points (boxes | picks | counts)
   size_t nms_stage_bytes = 0;
   bool det_pending = false;    // frcnn_detect_begin without its frcnn_detect_end yet
-  int det_pending_n = 0;
+  int det_pending_n = 0, det_pending_h = 0, det_pending_w = 0;
+  const float* det_pending_img = nullptr;  // device frames of the detection in flight (re-run if the match list outgrew cand_cap)
   long weights_gen = 0;        // bumped by frcnn_pack_weights: invalidates the cached dgrad weight layouts
   long ws_gen = 0;             // bumped whenever a workspace pointer baked into the graph may have changed
   int64_t launches_per_detect = 0;
@@ -248,13 +251,15 @@ static void* ensure_scratch(frcnn_ctx* c, size_t bytes) {
 // small utility kernels --------------------------------------------------------------------------------------
 __global__ void set_int_kernel(int* p, int v) { *p = v; }
 // fp32 [R][C*bins] in the reference's flatten order (c*bins + b) -> bf16 [R][bins][C]
-__global__ void pack_roi_rows_kernel(const float* __restrict__ x, bf16* __restrict__ out, long R, int C, int bins) {
+__global__ void pack_roi_rows_kernel(const float* __restrict__ x, bf16* __restrict__ out, long R, int C, int bins, int f16) {
   long total = R * C * bins;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long r = i / ((long)C * bins);
     int k = i - r * (long)C * bins;
     int b = k / C, c = k - b * C;
-    out[i] = __float2bfloat16_rn(x[r * (long)C * bins + (long)c * bins + b]);
+    const float v = x[r * (long)C * bins + (long)c * bins + b];
+    if (f16) reinterpret_cast<__half*>(out)[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    else out[i] = __float2bfloat16_rn(v);
   }
 }
 // split-K sums -> prelu(acc + bias) * scale -> bf16 (test entry frcnn_conv_bf16 with splits > 1)
@@ -473,25 +478,26 @@ static void do_pack(frcnn_ctx* c) {
   for (auto& cv : c->trunk) {
     if (cv.first) {
       FRCNN_REQUIRE(cv.cin * cv.k * cv.k <= 32, FRCNN_E_INVALID, "first-layer im2col K exceeds 32");
-      if (!cv.w_packed) cv.w_packed = alloc_w((size_t)cv.cout * 32);
+      // every forward weight is packed twice: [bf16 copy | fp16 copy] (training / evaluate operands, ConvParams::f16)
+      if (!cv.w_packed) cv.w_packed = alloc_w(2 * (size_t)cv.cout * 32);
       launch_pack_first_conv_weight(P(c, cv.p_w), cv.w_packed, cv.cout, cv.cin, cv.k, cv.k, c->stream);
     } else {
-      if (!cv.w_packed) cv.w_packed = alloc_w((size_t)cv.cout * cv.cin * cv.k * cv.k);
-      launch_pack_conv_weight(P(c, cv.p_w), cv.w_packed, cv.cout, cv.cin, cv.k, cv.k, c->stream);
+      if (!cv.w_packed) cv.w_packed = alloc_w(2 * (size_t)cv.cout * cv.cin * cv.k * cv.k);
+      launch_pack_conv_weight(P(c, cv.p_w), cv.w_packed, cv.cout, cv.cin, cv.k, cv.k, c->stream, 2);
     }
     ++c->launches;
   }
   for (auto& h : c->heads) {
     auto& cv = h.conv;
-    if (!cv.w_packed) cv.w_packed = alloc_w((size_t)cv.cout * cv.cin * cv.k * cv.k);
-    launch_pack_conv_weight(P(c, cv.p_w), cv.w_packed, cv.cout, cv.cin, cv.k, cv.k, c->stream);
+    if (!cv.w_packed) cv.w_packed = alloc_w(2 * (size_t)cv.cout * cv.cin * cv.k * cv.k);
+    launch_pack_conv_weight(P(c, cv.p_w), cv.w_packed, cv.cout, cv.cin, cv.k, cv.k, c->stream, 2);
     ++c->launches;
   }
   for (size_t i = 0; i < c->fcs.size(); ++i) {
     auto& f = c->fcs[i];
-    if (!f.w_packed) f.w_packed = alloc_w((size_t)f.nout * f.nin);
-    if (i == 0) launch_pack_fc_weight(P(c, f.p_w), f.w_packed, f.nout, c->feat_c, c->roi_kh * c->roi_kw, 1, c->stream);
-    else launch_pack_fc_weight(P(c, f.p_w), f.w_packed, f.nout, f.nin, 1, 0, c->stream);
+    if (!f.w_packed) f.w_packed = alloc_w(2 * (size_t)f.nout * f.nin);
+    if (i == 0) launch_pack_fc_weight(P(c, f.p_w), f.w_packed, f.nout, c->feat_c, c->roi_kh * c->roi_kw, 1, c->stream, 2);
+    else launch_pack_fc_weight(P(c, f.p_w), f.w_packed, f.nout, f.nin, 1, 0, c->stream, 2);
     ++c->launches;
   }
   ensure_luts_dev(c);
@@ -534,7 +540,7 @@ static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
       } else {
         cv.in = cur;
         conv_prepare(&cv.launch, cur, cv.w_packed, N, h, w, cv.cin, cv.cout, cv.k, cv.k, cv.pad, cv.pad, mode, cv.out,
-                     c->sm_count, 0, 0, 0);
+                     c->sm_count, 0, 0, 0, 2);
       }
       cv.launch.p.scale = cv.scale;
       cur = cv.out;
@@ -565,7 +571,7 @@ static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
     splits = std::max(1, std::min(splits, std::max(1, k_iters / 8)));
     hd.conv.hin = ih; hd.conv.win = iw; hd.conv.hout = hd.hh; hd.conv.wout = hd.hw;
     conv_prepare(&hd.conv.launch, c->pool_out[hd.input - 1], hd.conv.w_packed, N, ih, iw, hd.conv.cin, hd.conv.cout, hd.kW,
-                 hd.kW, 0, 0, EPI_F32_SLICES, nullptr, c->sm_count, splits, 256, 1);
+                 hd.kW, 0, 0, EPI_F32_SLICES, nullptr, c->sm_count, splits, 256, 1, 2);
     const size_t slices = (size_t)hd.conv.launch.p.splits * N;
     hd.acc = (float*)dev_alloc(c->ws_allocs, slices * hd.hh * hd.hw * hd.n * sizeof(float));
     hd.out = (float*)dev_alloc(c->ws_allocs, (size_t)N * 18 * hd.hh * hd.hw * sizeof(float));
@@ -652,6 +658,10 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
   if (train) ensure_train_workspace(c, N, H, W);
   c->train_ready = train;
   c->train_img = train ? img_dev : nullptr;
+  // operand format: training stays bf16 (gradient maps need the exponent range); evaluate mode uses fp16 by default --
+  // three more significand bits at the same tensor-core rate (precision contract)
+  const int f16 = (!train && c->eval_f16) ? 1 : 0;
+  c->act_f16 = f16;
   size_t li = 0;
   for (size_t b = 0; b < c->blocks.size(); ++b) {
     for (int s = 0; s < c->blocks[b].conv_steps; ++s, ++li) {
@@ -663,6 +673,7 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
       cv.launch.p.scale = masked ? 1.0f : (train ? 1.0f : cv.scale);
       cv.launch.p.chan_scale = masked ? cv.mask : nullptr;
       cv.launch.p.pool_arg = (train && cv.pooled) ? c->pool_arg[b] : nullptr;
+      cv.launch.p.f16 = f16;
       run_conv(c, cv);
     }
   }
@@ -676,6 +687,7 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
       ConvParams& p = hd.fused.p;
       p.bias = P(c, hd.conv.p_b); p.prelu = P(c, hd.conv.p_prelu); p.w2 = P(c, hd.p_w2); p.b2 = P(c, hd.p_b2);
       p.out = hd.out;
+      p.f16 = f16;
       order.push_back(&hd.fused);
     }
     std::stable_sort(order.begin(), order.end(), [](const ConvLaunch* a, const ConvLaunch* b) { return a->p.k_iters > b->p.k_iters; });
@@ -702,6 +714,7 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
     for (auto& hd : c->heads) {
       hd.conv.launch.p.bias = nullptr;
       hd.conv.launch.p.prelu = nullptr;
+      hd.conv.launch.p.f16 = f16;
       order.push_back(&hd.conv.launch);
     }
     std::stable_sort(order.begin(), order.end(),
@@ -1179,10 +1192,10 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
   c->flags = (int*)dev_alloc(A, (16 + 2 * (size_t)N) * sizeof(int));  // flags | match counts | accepted counts
   c->cand_count = c->flags + 16;
   c->n_pass = c->flags + 16 + N;
-  c->ticket = (int*)dev_alloc(A, N * sizeof(int));
+  c->ticket = (unsigned long long*)dev_alloc(A, N * sizeof(unsigned long long));
   c->status_blocks = 4096;
   c->status = (unsigned long long*)dev_alloc(A, (size_t)N * c->status_blocks * sizeof(unsigned long long));
-  FRCNN_CUDA_TRY(cudaMemsetAsync(c->ticket, 0, N * sizeof(int), c->stream));
+  FRCNN_CUDA_TRY(cudaMemsetAsync(c->ticket, 0, N * sizeof(unsigned long long), c->stream));
   FRCNN_CUDA_TRY(cudaMemsetAsync(c->status, 0, (size_t)N * c->status_blocks * sizeof(unsigned long long), c->stream));
   FRCNN_CUDA_TRY(cudaMemsetAsync(c->flags, 0, (16 + 2 * (size_t)N) * sizeof(int), c->stream));
   c->decode_nblocks = 0;
@@ -1210,15 +1223,20 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
   const bf16* in = c->roi_out;
   for (size_t i = 0; i < c->fcs.size(); ++i) {
     FcLayer& f = c->fcs[i];
-    f.acc = (float*)dev_alloc(A, (size_t)R * f.nout * sizeof(float));
     const bool last = i + 1 == c->fcs.size();
     f.out_bf16 = last ? nullptr : (bf16*)dev_alloc(A, (size_t)R * f.nout * sizeof(bf16));
     f.out_f32 = last ? (float*)dev_alloc(A, (size_t)R * f.nout * sizeof(float)) : nullptr;
     // split-K sized for the detector's typical few hundred ROIs: 8 K-iterations per split
     int k_iters = f.nin / 64;
     int splits = std::max(1, k_iters / 8);
-    conv_prepare(&f.launch, in, f.w_packed, 1, 1, R, f.nin, f.nout, 1, 1, 0, 0, EPI_F32_REDUCE, nullptr, c->sm_count, splits, 0, 0);
+    // deterministic split-K: every split writes its own fp32 slice (no reduce-add, no memset); fc_tail sums the slices in
+    // ascending order.  Tile-major slices bound the workspace by max(M tiles, dyn_ctas / N tiles) tiles of 128 rows.
+    conv_prepare(&f.launch, in, f.w_packed, 1, 1, R, f.nin, f.nout, 1, 1, 0, 0, EPI_F32_SLICES, nullptr, c->sm_count, splits, 0, 0, 2);
+    const ConvParams& fp = f.launch.p;
+    const size_t ws_tiles = (size_t)std::max(fp.n_tiles_m, c->sm_count / std::max(1, fp.n_tiles_n) + 1) + 1;
+    f.acc = (float*)dev_alloc(A, ws_tiles * 128 * f.nout * sizeof(float));
     conv_set_f32_output(&f.launch, f.acc);
+    f.launch.p.slice_tile_major = 1;
     f.launch.p.m_limit = c->flags + 2;  // roi_total
     // split-K factor chosen on the device from the live row count so that the units fill about dyn_ctas CTAs: the whole
     // machine on the latency schedule, a quarter of it on the throughput schedule (measured: 37 CTAs cost a single
@@ -1233,7 +1251,7 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
   FRCNN_CUDA_TRY(cudaMalloc(&c->nms_mem, c->nms_bytes));
   nms_workspace_init(&c->nms, c->nms_mem, c->nms_bytes, c->nms_cap_total, c->nms_cap_seg);
   if (c->h_ints) cudaFreeHost(c->h_ints);
-  FRCNN_CUDA_TRY(cudaMallocHost(&c->h_ints, (64 + 2 * (size_t)N) * sizeof(int)));
+  FRCNN_CUDA_TRY(cudaMallocHost(&c->h_ints, (96 + 2 * (size_t)N) * sizeof(int)));
   ++c->ws_gen;
   if (c->h_det_cap < c->det_cap) {
     if (c->h_det) cudaFreeHost(c->h_det);
@@ -1248,10 +1266,12 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
 static void run_cnet(frcnn_ctx* c, int rows_max) {
   for (size_t i = 0; i < c->fcs.size(); ++i) {
     FcLayer& f = c->fcs[i];
-    FRCNN_CUDA_TRY(cudaMemsetAsync(f.acc, 0, (size_t)rows_max * f.nout * sizeof(float), c->stream));
+    f.launch.p.f16 = c->eval_f16;   // cnet:forward here is evaluate mode (Detector.lua:101): the rows are in that format
     conv_launch_timed(c, f.launch, c->profiling ? c->prof_rows : -1);
+    const ConvParams& fp = f.launch.p;
+    const FcSlices sl = {fp.k_iters, fp.splits, fp.n_tiles_n, fp.dyn_ctas};
     launch_fc_tail(f.acc, P(c, f.p_b), P(c, f.p_bn_w), P(c, f.p_bn_b), P(c, f.p_bn_mean), P(c, f.p_bn_var), P(c, f.p_prelu),
-                   f.out_bf16, f.out_f32, rows_max, c->flags + 2, f.nout, c->stream);
+                   f.out_bf16, f.out_f32, rows_max, c->flags + 2, f.nout, c->stream, &sl, 512, c->eval_f16);
     ++c->launches;
   }
   const FcLayer& last = c->fcs.back();
@@ -1287,7 +1307,7 @@ static void run_decode(frcnn_ctx* c, const float* const* heads_dev, int N, int H
   // status words are laid out with the per-image stride nblocks and tagged with the launch number derived from the
   // running ticket counter; a different block count restarts the numbering
   if (c->decode_nblocks != p.nblocks) {
-    FRCNN_CUDA_TRY(cudaMemsetAsync(c->ticket, 0, c->det_n * sizeof(int), c->stream));
+    FRCNN_CUDA_TRY(cudaMemsetAsync(c->ticket, 0, c->det_n * sizeof(unsigned long long), c->stream));
     FRCNN_CUDA_TRY(cudaMemsetAsync(c->status, 0, (size_t)c->det_n * c->status_blocks * sizeof(unsigned long long), c->stream));
     c->decode_nblocks = p.nblocks;
     ++c->ws_gen;
@@ -1311,15 +1331,45 @@ static void enqueue_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int
   for (int i = 0; i < MAX_HEADS; ++i) heads_dev[i] = c->heads[i].out;
   run_decode(c, heads_dev, N, H, W, c->thr_fg);
   // --- Detector.lua:68-85: nms(bb, 0.25, score) -- the score tensor is ignored, order key = y2 (nms.lua:41-42)
-  nms_set_segments_from_counts(&c->nms, c->cand_count, N, c->cand_cap, st);
-  c->nms.fused = false;  // up to cand_cap matches per image: sort / matrix / resolve as three launches
-  c->launches += nms_run(&c->nms, reinterpret_cast<const float*>(c->cand_box), 4, N, N * c->cand_cap, c->cand_cap, c->thr_nms1,
-                         FRCNN_NMS_ORDER_Y2, 0, st, nullptr);
-  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->pick1, c->nms.st.pick, (size_t)N * c->cand_cap * sizeof(int), cudaMemcpyDeviceToDevice, st));
-  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->count1, c->nms.st.counts, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  if (c->cand_cap <= NMS_CTA_MAX_SEG) {
+    nms_set_segments_from_counts(&c->nms, c->cand_count, N, c->cand_cap, st);
+    c->nms.fused = false;  // up to cand_cap matches per image: sort / matrix / resolve as three launches
+    c->launches += nms_run(&c->nms, reinterpret_cast<const float*>(c->cand_box), 4, N, N * c->cand_cap, c->cand_cap, c->thr_nms1,
+                           FRCNN_NMS_ORDER_Y2, 0, st, nullptr);
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->pick1, c->nms.st.pick, (size_t)N * c->cand_cap * sizeof(int), cudaMemcpyDeviceToDevice, st));
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->count1, c->nms.st.counts, N * sizeof(int), cudaMemcpyDeviceToDevice, st));
+  } else {
+    // The candidate capacity has grown past the CTA-level NMS (a frame with more than 8192 matches above the
+    // foreground threshold: rare, the match list is unbounded in the reference, Detector.lua:59).  The radix-sort path
+    // takes its segment table from the host: read the match counts back and run it image by image (eager only).
+    int* hs = c->h_ints + 16 + 2 * c->det_n;  // pinned scratch behind the counters: [0..1] segment table, [8..24) counts
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(hs + 8, c->cand_count, std::min(N, 16) * sizeof(int), cudaMemcpyDeviceToHost, st));
+    FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
+    FRCNN_REQUIRE(N <= 16, FRCNN_E_OVERFLOW, "more than 8192 matches per image is supported for batches of at most 16 frames");
+    int counts[16];
+    for (int i = 0; i < N; ++i) counts[i] = hs[8 + i];
+    for (int i = 0; i < N; ++i) {
+      const int n = counts[i];
+      if (n == 0) {
+        FRCNN_CUDA_TRY(cudaMemsetAsync(c->count1 + i, 0, sizeof(int), st));
+        continue;
+      }
+      hs[0] = 0; hs[1] = n;
+      FRCNN_CUDA_TRY(cudaMemcpyAsync(c->nms.st.seg_beg, hs, sizeof(int), cudaMemcpyHostToDevice, st));
+      FRCNN_CUDA_TRY(cudaMemcpyAsync(c->nms.st.seg_len, hs + 1, sizeof(int), cudaMemcpyHostToDevice, st));
+      FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
+      c->nms.fused = false;
+      c->nms.seg_counts = nullptr;
+      c->launches += nms_run(&c->nms, reinterpret_cast<const float*>(c->cand_box + (size_t)i * c->cand_cap), 4, 1, n, n, c->thr_nms1,
+                             FRCNN_NMS_ORDER_Y2, 0, st, nullptr);
+      FRCNN_CUDA_TRY(cudaMemcpyAsync(c->pick1 + (size_t)i * c->cand_cap, c->nms.st.pick, (size_t)n * sizeof(int), cudaMemcpyDeviceToDevice, st));
+      FRCNN_CUDA_TRY(cudaMemcpyAsync(c->count1 + i, c->nms.st.counts, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    }
+  }
   if (prof) cudaEventRecord(c->ev[2], st);
   // --- Detector.lua:91-98: ROI pooling of every candidate
   RoiParams rp;
+  rp.f16 = c->act_f16;
   rp.fmap = c->pool_out.back(); rp.FH = c->feat_h; rp.FW = c->feat_w; rp.C = c->feat_c; rp.kh = c->roi_kh; rp.kw = c->roi_kw;
   rp.loc = c->roi_loc;
   rp.cand_r = c->cand_r; rp.pick = c->pick1; rp.pick_count = c->count1; rp.roi_base = c->roi_base; rp.cap = c->cand_cap;
@@ -1341,13 +1391,14 @@ static void enqueue_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int
   GroupParams gp;
   gp.roi_base = c->roi_base; gp.pick_count = c->count1; gp.fin_cls = c->fin_cls; gp.fin_box = c->fin_box;
   gp.cap = c->cand_cap; gp.n_classes = c->class_count; gp.gbox = c->gbox; gp.grow = c->grow; gp.n_pass = c->n_pass;
+  gp.overflow = c->flags + 4;
   launch_group_by_class(gp, &c->nms, N, st);
   c->launches += 2;
   // --- Detector.lua:125-136: per-class nms(bb, 0.1, bb[{{},5}]) -- order key again y2
   const int n_seg = N * c->class_count;
   c->nms.fused = true;   // per-class segments are small: one fused launch
-  c->launches += nms_run(&c->nms, reinterpret_cast<const float*>(c->gbox), 4, n_seg, N * c->cand_cap, c->cand_cap, c->thr_nms2,
-                         FRCNN_NMS_ORDER_Y2, 0, st, nullptr);
+  c->launches += nms_run(&c->nms, reinterpret_cast<const float*>(c->gbox), 4, n_seg, N * c->cand_cap,
+                         std::min(c->cand_cap, NMS_CTA_MAX_SEG), c->thr_nms2, FRCNN_NMS_ORDER_Y2, 0, st, nullptr);
   AssembleParams ap;
   ap.grow = c->grow; ap.cand_r = c->cand_r; ap.cand_logp = c->cand_logp; ap.cand_anchor = c->cand_anchor;
   ap.roi_img = c->roi_img; ap.roi_cand = c->roi_cand; ap.fin_r2 = c->fin_r2; ap.fin_cls = c->fin_cls; ap.fin_conf = c->fin_conf;
@@ -1379,7 +1430,7 @@ static void do_detect_enqueue(frcnn_ctx* c, const float* img_dev, int N, int H, 
     return a.img == b.img && a.N == b.N && a.H == b.H && a.W == b.W && a.thr_fg == b.thr_fg && a.thr_class == b.thr_class &&
            a.thr_nms1 == b.thr_nms1 && a.thr_nms2 == b.thr_nms2 && a.gen == b.gen;
   };
-  const bool want_graph = c->graph_enabled && !prof && c->decode_nblocks != 0;
+  const bool want_graph = c->graph_enabled && !prof && c->decode_nblocks != 0 && c->cand_cap <= NMS_CTA_MAX_SEG;
   if (want_graph && c->graph_exec && same(key, c->graph_key)) {
     FRCNN_CUDA_TRY(cudaGraphLaunch(c->graph_exec, st));
     c->launches += c->launches_per_detect;
@@ -1419,7 +1470,8 @@ static void do_detect_enqueue(frcnn_ctx* c, const float* img_dev, int N, int H, 
     c->eager_key = {img_dev, N, H, W, c->thr_fg, c->thr_class, c->thr_nms1, c->thr_nms2, c->ws_gen};
   }
   c->det_pending = true;
-  c->det_pending_n = N;
+  c->det_pending_n = N; c->det_pending_h = H; c->det_pending_w = W;
+  c->det_pending_img = img_dev;
 }
 
 static void do_detect_finish(frcnn_ctx* c, frcnn_detection* det_host, int cap, int* n_det) {
@@ -1430,6 +1482,24 @@ static void do_detect_finish(frcnn_ctx* c, frcnn_detection* det_host, int cap, i
   const int N = c->det_pending_n;
   c->det_pending = false;
   FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
+  // The reference's match list has no bound (Detector.lua:59): when a frame produced more matches than the candidate
+  // buffers hold, grow them (doubling, up to the number of anchors) and run the frames again.
+  while (c->h_ints[0]) {
+    long total_anchors = 0;
+    for (auto& hd : c->heads) total_anchors += 3L * hd.hh * hd.hw;
+    FRCNN_REQUIRE(c->cand_cap < total_anchors, FRCNN_E_OVERFLOW, "candidate overflow with a capacity of every anchor");
+    c->cand_cap = (int)std::min<long>(2L * c->cand_cap, (total_anchors + 255) / 256 * 256);
+    FRCNN_CUDA_TRY(cudaMemsetAsync(c->flags, 0, 2 * sizeof(int), st));
+    if (c->graph_exec) {
+      cudaGraphExecDestroy(c->graph_exec);
+      c->graph_exec = nullptr;
+    }
+    c->eager_key = {};
+    c->det_n = 0;  // forces ensure_det_workspace to rebuild for the new capacity
+    do_detect_enqueue(c, c->det_pending_img, N, c->det_pending_h, c->det_pending_w);
+    c->det_pending = false;
+    FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
+  }
   const int overflow = c->h_ints[0], degenerate = c->h_ints[1], roi_total = c->h_ints[2], ndet = c->h_ints[3];
   if (overflow || degenerate) FRCNN_CUDA_TRY(cudaMemsetAsync(c->flags, 0, 2 * sizeof(int), st));
   c->stats[0] = c->stats[2] = 0;
@@ -1446,6 +1516,10 @@ static void do_detect_finish(frcnn_ctx* c, frcnn_detection* det_host, int cap, i
     c->prof_rows = roi_total;
   }
   FRCNN_REQUIRE(!overflow, FRCNN_E_OVERFLOW, "more RPN matches than the candidate capacity (" + std::to_string(c->cand_cap) + " per image)");
+  if (c->h_ints[4]) {
+    FRCNN_CUDA_TRY(cudaMemsetAsync(c->flags + 4, 0, sizeof(int), st));
+    FRCNN_REQUIRE(false, FRCNN_E_OVERFLOW, "more than 8192 candidates of one image survived nms(bb, 0.25) (Detector.lua:82)");
+  }
   FRCNN_REQUIRE(!degenerate, FRCNN_E_ROI_EMPTY,
                 "an ROI clipped to max == 0; the reference raises an index error here (objective.lua:11)");
   const int ncopy = std::min(ndet, std::min(cap, c->det_cap));
@@ -1752,7 +1826,8 @@ int frcnn_pnet_forward(frcnn_ctx* c, const float* img_dev, int n, int h, int w, 
         FRCNN_CUDA_TRY(cudaMemcpyAsync(out_dev[i], c->heads[i].out, (size_t)n * 18 * c->heads[i].hh * c->heads[i].hw * sizeof(float),
                                        cudaMemcpyDeviceToDevice, c->stream));
     if (out_dev[c->heads.size()]) {
-      frcnn::launch_nhwc_bf16_to_chw_f32(c->pool_out.back(), out_dev[c->heads.size()], n, c->feat_h, c->feat_w, c->feat_c, c->stream);
+      frcnn::launch_nhwc_bf16_to_chw_f32(c->pool_out.back(), out_dev[c->heads.size()], n, c->feat_h, c->feat_w, c->feat_c, c->stream,
+                                         c->act_f16);
       ++c->launches;
     }
   }
@@ -1810,7 +1885,8 @@ int frcnn_pnet_forward_train(frcnn_ctx* c, const float* img_dev, int n, int h, i
         FRCNN_CUDA_TRY(cudaMemcpyAsync(out_dev[i], c->heads[i].out, (size_t)n * 18 * c->heads[i].hh * c->heads[i].hw * sizeof(float),
                                        cudaMemcpyDeviceToDevice, c->stream));
     if (out_dev[c->heads.size()]) {
-      frcnn::launch_nhwc_bf16_to_chw_f32(c->pool_out.back(), out_dev[c->heads.size()], n, c->feat_h, c->feat_w, c->feat_c, c->stream);
+      frcnn::launch_nhwc_bf16_to_chw_f32(c->pool_out.back(), out_dev[c->heads.size()], n, c->feat_h, c->feat_w, c->feat_c, c->stream,
+                                         c->act_f16);
       ++c->launches;
     }
   }
@@ -1868,7 +1944,7 @@ int frcnn_cnet_train_step(frcnn_ctx* c, const float* x_dev, int R, int n_pos, co
   const int bins = c->roi_kh * c->roi_kw;
   const long total = (long)R * bins * c->feat_c;
   const int blocks = (int)std::min<long>((total + 255) / 256, 148 * 16);
-  frcnn::pack_roi_rows_kernel<<<blocks, 256, 0, c->stream>>>(x_dev, c->t_rows, R, c->feat_c, bins);
+  frcnn::pack_roi_rows_kernel<<<blocks, 256, 0, c->stream>>>(x_dev, c->t_rows, R, c->feat_c, bins, 0);
   FRCNN_CUDA_TRY(cudaMemcpyAsync(c->crtarget, crtarget_dev, (size_t)R * 4 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
   FRCNN_CUDA_TRY(cudaMemcpyAsync(c->cctarget, cctarget_dev, (size_t)R * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
   FRCNN_CUDA_TRY(cudaMemsetAsync(c->losses_dev, 0, 8 * sizeof(float), c->stream));
@@ -2072,7 +2148,7 @@ int frcnn_cnet_forward(frcnn_ctx* c, const float* x_dev, int R, float* reg_dev, 
   const int bins = c->roi_kh * c->roi_kw;
   long total = (long)R * bins * c->feat_c;
   int blocks = (int)std::min<long>((total + 255) / 256, 148 * 16);
-  frcnn::pack_roi_rows_kernel<<<blocks, 256, 0, c->stream>>>(x_dev, c->roi_out, R, c->feat_c, bins);
+  frcnn::pack_roi_rows_kernel<<<blocks, 256, 0, c->stream>>>(x_dev, c->roi_out, R, c->feat_c, bins, c->eval_f16);
   frcnn::set_int_kernel<<<1, 1, 0, c->stream>>>(c->flags + 2, R);
   c->launches += 2;
   frcnn::run_cnet(c, R);
@@ -2271,6 +2347,16 @@ int frcnn_set_schedule(frcnn_ctx* c, int schedule) {
   return FRCNN_OK;
 }
 
+int frcnn_set_eval_precision(frcnn_ctx* c, int precision) {
+  if (!c || (precision != FRCNN_PREC_BF16 && precision != FRCNN_PREC_FP16)) return FRCNN_E_INVALID;
+  const int f16 = precision == FRCNN_PREC_FP16 ? 1 : 0;
+  if (c->eval_f16 != f16) {
+    c->eval_f16 = f16;
+    ++c->ws_gen;  // a captured detect graph holds the other format's launches: re-capture
+  }
+  return FRCNN_OK;
+}
+
 int frcnn_set_graph_replay(frcnn_ctx* c, int enable) {
   if (!c) return FRCNN_E_INVALID;
   c->graph_enabled = enable != 0;
@@ -2344,7 +2430,7 @@ int frcnn_conv_first(frcnn_ctx* c, const float* img_dev, const float* w_dev, con
   API_BEGIN(c)
   REQUIRE_DEVICE(c);
   FRCNN_REQUIRE(img_dev && w_dev && out_dev, FRCNN_E_INVALID, "null argument");
-  uint8_t* mem = (uint8_t*)frcnn::ensure_scratch(c, (size_t)cout * 32 * sizeof(frcnn::bf16) + 256);
+  uint8_t* mem = (uint8_t*)frcnn::ensure_scratch(c, 2 * (size_t)cout * 32 * sizeof(frcnn::bf16) + 256);
   frcnn::bf16* wp = (frcnn::bf16*)mem;
   frcnn::launch_pack_first_conv_weight(w_dev, wp, cout, 3, 3, 3, c->stream);
   frcnn::ConvLaunch L;

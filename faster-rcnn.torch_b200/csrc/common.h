@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -101,6 +102,13 @@ struct ConvParams {
   int halo_desc;            // descriptor base-offset mode for the row-shifted start address (0: field left 0)
   const float* w2;          // EPI_HEAD: [18][256] weights of the 1x1 convolution (Torch layout)
   const float* b2;          // EPI_HEAD: [18] bias of the 1x1 convolution
+  int f16;                  // 16-bit operand format of this launch: 0 = bf16 (training: gradients need the exponent range),
+                            // 1 = fp16 (evaluate / detect: 11 significand bits instead of 8 at the same tensor-core rate; the
+                            // precision contract of DESIGN.md).  Selects the weight copy (third coordinate of the weight
+                            // tensor map), the MMA instruction descriptor's operand formats and the epilogue's conversion
+  int slice_tile_major;     // EPI_F32_SLICES of a GEMM (BH == 1, N == 1) whose split count is chosen on the device: slice s of
+                            // 128-row tile m is rows [(m * splits + s) * 128, +128) of the workspace, so that the workspace
+                            // is bounded by max(M tiles, dyn_ctas / N tiles) tiles whatever the live row count
   int dbg;                  // FRCNN_CONV_DBG (measurement only): 1 skip the global stores, 2 skip the epilogue body, 4 skip the MMAs
 };
 
@@ -111,7 +119,8 @@ struct ConvLaunch {
   int BN;
   bool first;               // fused first-layer kernel (in-kernel im2col of the fp32 image)
   CUtensorMap tmA, tmB, tmOut;
-  const bf16* w_first;      // first-layer kernel: packed [Cout][32] bf16 weights
+  const bf16* w_first;      // first-layer kernel: packed [2][Cout][32] weights (bf16 copy, fp16 copy)
+  int w_copies;             // operand-format copies behind tmB: 1 = bf16 only, 2 = [bf16 | fp16] (ConvParams::f16 selects)
   int grid;
 };
 
@@ -130,10 +139,10 @@ struct ConvMaps {
 // Host helpers (conv_igemm.cu)
 void conv_choose_tile(int Hout, int Wout, int* BW, int* BH);
 void make_tmap_act(CUtensorMap* m, const bf16* base, int N, int H, int W, int C, int BW, int BH);
-void make_tmap_weight(CUtensorMap* m, const bf16* base, int Cout, int K, int BN);
+void make_tmap_weight(CUtensorMap* m, const bf16* base, int Cout, int K, int BN, int copies);
 void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
                   int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int force_splits, int force_bn,
-                  int force_mt);
+                  int force_mt, int w_copies = 1);
 // First layer (Cin = 3): reads the fp32 NCHW frames directly; w_packed32: [Cout][32] bf16 (K = Cin*KH*KW padded).
 void conv_first_prepare(ConvLaunch* L, const bf16* w_packed32, int N, int Hin, int Win, int Cimg, int Cout, int KH,
                         int KW, int padH, int padW, int mode, bf16* out, int num_sms);
@@ -154,7 +163,8 @@ void conv_set_f32_output(ConvLaunch* L, float* ws);
 int conv_smem_bytes(int BN);
 
 // ------------------------------------------------------------------ element kernels (elementwise.cu)
-void launch_pack_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st);
+// copies = 2: out is [2][...]: the bf16 copy followed by the fp16 copy (ConvParams::f16)
+void launch_pack_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st, int copies = 1);
 void launch_pack_first_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st);
 // dgrad weights: out[ci][kh'][kw'][co] = w[co][ci][KH-1-kh'][KW-1-kw'] (bf16), the K-major B operand of the
 // transposed convolution
@@ -163,7 +173,7 @@ void launch_pack_conv_weight_dgrad(const float* w, bf16* out, int Cout, int Cin,
 void launch_nhwc_to_planar_bf16(const bf16* in, bf16* out, int N, int H, int W, int C, int pitch, cudaStream_t st);
 // grad[co][ci][kh][kw] (Torch layout, fp32) += dw_taps[co][kh*KW+kw][ci]
 void launch_wgrad_finish(const float* dw_taps, float* grad, int Cout, int Cin, int KH, int KW, cudaStream_t st);
-void launch_pack_fc_weight(const float* w, bf16* out, int nout, int C, int bins, int permute, cudaStream_t st);
+void launch_pack_fc_weight(const float* w, bf16* out, int nout, int C, int bins, int permute, cudaStream_t st, int copies = 1);
 void launch_maxpool2x2(const bf16* in, bf16* out, int N, int H, int W, int C, cudaStream_t st);
 // AnchorNetwork tails of all heads in one launch (mid width 256, 18 outputs: model_utilities.lua:29-35)
 struct HeadTail {
@@ -181,11 +191,15 @@ struct HeadTailGroup {
   int n;
 };
 void launch_head_tail_group(const HeadTailGroup& g, int num_sms, cudaStream_t st);
-void launch_nhwc_bf16_to_chw_f32(const bf16* in, float* out, int N, int H, int W, int C, cudaStream_t st);
+void launch_nhwc_bf16_to_chw_f32(const bf16* in, float* out, int N, int H, int W, int C, cudaStream_t st, int f16 = 0);
 void launch_chw_f32_to_nhwc_bf16(const float* in, bf16* out, int N, int H, int W, int C, cudaStream_t st);
+// split-K slices of a GEMM launched with ConvParams::slice_tile_major (k_iters == 0: acc is the finished sum)
+struct FcSlices {
+  int k_iters, host_splits, n_tiles_n, dyn_ctas;
+};
 void launch_fc_tail(const float* acc, const float* bias, const float* bn_w, const float* bn_b, const float* bn_mean,
                     const float* bn_var, const float* prelu, bf16* out_bf16, float* out_f32, int rows_max,
-                    const int* rows_dev, int n, cudaStream_t st);
+                    const int* rows_dev, int n, cudaStream_t st, const FcSlices* sl = nullptr, int grid_rows = 0, int f16 = 0);
 void launch_cnet_out(const float* hidden, const float* w_reg, const float* b_reg, const float* w_cls,
                      const float* b_cls, float* reg_out, float* cls_out, int rows_max, const int* rows_dev, int nin,
                      int ncls, cudaStream_t st);

@@ -183,6 +183,9 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
         // into slice split * N + image (deterministic); REDUCE: TMA tensor reduction (add) into the image's map
         const int slice = p.mode == EPI_F32_SLICES ? (t.k_begin / sc.kps[gi]) * p.N + t.n_img : t.n_img;
         float* out_img = reinterpret_cast<float*>(p.out) + (size_t)slice * p.Hout * p.Wout * p.Cout;
+        if (p.slice_tile_major)  // GEMM rows: tile-major slices, addressed below with the tile-local row (ww - t.w0)
+          out_img = reinterpret_cast<float*>(p.out) +
+                    (((long long)(t.w0 / BLOCK_M) * sc.splits[gi] + slice) * BLOCK_M - (long long)t.w0) * p.Cout;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           uint32_t v[16];
@@ -246,13 +249,14 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
                 const float4 m = __ldg(reinterpret_cast<const float4*>(p.chan_scale + (size_t)t.n_img * p.Cout + cbase + half * 32) + j);
                 y0 *= m.x; y1 *= m.y; y2 *= m.z; y3 *= m.w;
               }
-              o[2 * j] = ptx::pack_bf16x2(y0, y1);
-              o[2 * j + 1] = ptx::pack_bf16x2(y2, y3);
+              o[2 * j] = ptx::pack_op16x2(y0, y1, p.f16);
+              o[2 * j + 1] = ptx::pack_op16x2(y2, y3, p.f16);
             }
           }
           if (p.mode == EPI_POOL && !valid) {
+            const uint32_t ninf = p.f16 ? 0xFC00FC00u : 0xFF80FF80u;  // -inf: outside the map, never wins a ceil-mode window
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = 0xFF80FF80u;  // -inf: outside the map, never wins a ceil-mode window
+            for (int j = 0; j < 16; ++j) o[j] = ninf;
           }
           ptx::named_bar_sync(1, EPI_THREADS);  // every thread has finished reading the previous staging pass
 #pragma unroll
@@ -273,12 +277,8 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
                 const uint4 b = ptx::ld_shared_v4(tile_addr + r01 * 128 + ((c ^ (r01 & 7)) << 4));
                 const uint4 cc = ptx::ld_shared_v4(tile_addr + r10 * 128 + ((c ^ (r10 & 7)) << 4));
                 const uint4 d = ptx::ld_shared_v4(tile_addr + r11 * 128 + ((c ^ (r11 & 7)) << 4));
-                __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
-                const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
-                const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&cc);
-                const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&d);
                 if (p.pool_arg) {
-                  // training: remember the winner (first maximum in window scan order, as nn.SpatialMaxPooling)
+                  // training (bf16): remember the winner (first maximum in window scan order, as nn.SpatialMaxPooling)
                   const bf16* ea = reinterpret_cast<const bf16*>(&a);
                   const bf16* eb = reinterpret_cast<const bf16*>(&b);
                   const bf16* ec = reinterpret_cast<const bf16*>(&cc);
@@ -296,8 +296,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
                   }
                   *reinterpret_cast<uint2*>(p.pool_arg + (((size_t)t.n_img * Hp + ph) * Wp + pw) * p.Cout + cbase + c * 8) = make_uint2(lo, hi);
                 }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) pa[j] = __hmax2(__hmax2(pa[j], pb[j]), __hmax2(pc[j], pd[j]));
+                a.x = ptx::max4_op16x2(a.x, b.x, cc.x, d.x, p.f16);
+                a.y = ptx::max4_op16x2(a.y, b.y, cc.y, d.y, p.f16);
+                a.z = ptx::max4_op16x2(a.z, b.z, cc.z, d.z, p.f16);
+                a.w = ptx::max4_op16x2(a.w, b.w, cc.w, d.w, p.f16);
                 *reinterpret_cast<uint4*>(out_img + ((size_t)ph * Wp + pw) * p.Cout + cbase + c * 8) = a;
               }
             } else {
@@ -426,7 +428,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
             int kw = tap - kh * p.KW;
             ptx::tma_load_4d(smem_a + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], cc * BLOCK_K, t.w0 + kw - p.padW,
                              t.h0 + kh - p.padH, t.n_img);
-            ptx::tma_load_2d(smem_b + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], k * BLOCK_K, t.n0);
+            ptx::tma_load_3d(smem_b + stage * B_STAGE_BYTES, &tmB, &full_bar[stage], k * BLOCK_K, t.n0, p.f16);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -463,6 +465,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
           } else {
             const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES));
             const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
+            const uint32_t idesc = grp.p[gi].f16 ? ptx::idesc_to_f16(IDESC) : IDESC;
 #pragma unroll
             for (int j = 0; j < BLOCK_K / 16; ++j) {
 #pragma unroll
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                 // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field; the second
                 // 128-row sub-tile starts 16 KB further
                 if (!(grp.p[gi].dbg & 4))
-                  ptx::mma_bf16_ss(d_tmem + mt * BN, da + 2 * j + mt * (A_SUB_BYTES >> 4), db + 2 * j, IDESC,
+                  ptx::mma_bf16_ss(d_tmem + mt * BN, da + 2 * j + mt * (A_SUB_BYTES >> 4), db + 2 * j, idesc,
                                    (k > t.k_begin || j > 0) ? 1u : 0u);
               }
             }
@@ -729,7 +732,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
             if (tap == kpre) issue_a();
             ptx::mbar_wait(&empty_b[bs], bph ^ 1);
             ptx::mbar_arrive_expect_tx(&full_b[bs], B_SLOT);
-            ptx::tma_load_2d(smem_b + bs * B_SLOT, &maps.b[gi], &full_b[bs], (tap * p.cchunks + c) * BLOCK_K, t.n0);
+            ptx::tma_load_3d(smem_b + bs * B_SLOT, &maps.b[gi], &full_b[bs], (tap * p.cchunks + c) * BLOCK_K, t.n0, p.f16);
             if (++bs == B_SLOTS) {
               bs = 0;
               bph ^= 1;
@@ -751,6 +754,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         const ConvParams& p = grp.p[gi];
         const int PW = HALO_BW + p.KW - 1;  // halo pitch, pixels
         const uint32_t sbo = (uint32_t)PW * 128u;
+        const uint32_t idesc = p.f16 ? ptx::idesc_to_f16(IDESC) : IDESC;
         const int acc = ACC == 2 ? (seq & 1) : 0;
         const uint32_t acc_phase = (uint32_t)(ACC == 2 ? (seq >> 1) : seq) & 1u;
         ++seq;
@@ -772,7 +776,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                 const uint64_t da = ptx::make_desc_k_sw128_sbo(a_addr + row0 * 128, sbo, p.halo_desc ? (uint32_t)row0 : 0u);
 #pragma unroll
                 for (int j = 0; j < BLOCK_K / 16; ++j)
-                  if (!(p.dbg & 4)) ptx::mma_bf16_ss(d_tmem + mt * BN, da + 2 * j, db + 2 * j, IDESC, j > 0 ? 1u : first);
+                  if (!(p.dbg & 4)) ptx::mma_bf16_ss(d_tmem + mt * BN, da + 2 * j, db + 2 * j, idesc, j > 0 ? 1u : first);
               }
               ptx::mma_commit(&empty_b[bs]);
               if (++bs == B_SLOTS) {
@@ -1024,12 +1028,13 @@ __device__ __forceinline__ void epilogue_first_warp(const ConvParams& p, uint8_t
           const float4 m = __ldg(reinterpret_cast<const float4*>(p.chan_scale + (size_t)t.n_img * p.Cout + half * 32) + j);
           y0 *= m.x; y1 *= m.y; y2 *= m.z; y3 *= m.w;
         }
-        o[2 * j] = ptx::pack_bf16x2(y0, y1);
-        o[2 * j + 1] = ptx::pack_bf16x2(y2, y3);
+        o[2 * j] = ptx::pack_op16x2(y0, y1, p.f16);
+        o[2 * j + 1] = ptx::pack_op16x2(y2, y3, p.f16);
       }
       if (p.mode == EPI_POOL && !valid) {
+        const uint32_t ninf = p.f16 ? 0xFC00FC00u : 0xFF80FF80u;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = 0xFF80FF80u;
+        for (int j = 0; j < 16; ++j) o[j] = ninf;
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c)
@@ -1074,12 +1079,10 @@ __device__ __forceinline__ void epilogue_first_warp(const ConvParams& p, uint8_t
             }
             *reinterpret_cast<uint2*>(p.pool_arg + (((size_t)t.n_img * Hp + ph) * Wp + pw) * p.Cout + c * 8) = make_uint2(lo, hi);
           }
-          __nv_bfloat162* pa = reinterpret_cast<__nv_bfloat162*>(&a);
-          const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
-          const __nv_bfloat162* pc = reinterpret_cast<const __nv_bfloat162*>(&cc);
-          const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(&d);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) pa[j] = __hmax2(__hmax2(pa[j], pb[j]), __hmax2(pc[j], pd[j]));
+          a.x = ptx::max4_op16x2(a.x, b.x, cc.x, d.x, p.f16);
+          a.y = ptx::max4_op16x2(a.y, b.y, cc.y, d.y, p.f16);
+          a.z = ptx::max4_op16x2(a.z, b.z, cc.z, d.z, p.f16);
+          a.w = ptx::max4_op16x2(a.w, b.w, cc.w, d.w, p.f16);
           *reinterpret_cast<uint4*>(out_img + ((size_t)ph * Wp + pw) * p.Cout + c * 8) = a;
         }
       }
@@ -1181,7 +1184,7 @@ __global__ void __launch_bounds__(FIRST_THREADS, 1)
   // weights [64][32] bf16 -> K-major 128-byte-swizzled rows (chunks 0..3 of every row)
   for (int i = threadIdx.x; i < BN * 4; i += blockDim.x) {
     const int n = i >> 2, c = i & 3;
-    const uint4 v = reinterpret_cast<const uint4*>(w32)[i];
+    const uint4 v = reinterpret_cast<const uint4*>(w32 + (p.f16 ? BN * 32 : 0))[i];   // [bf16 copy | fp16 copy]
     *reinterpret_cast<uint4*>(smem_b + n * 128 + ((c ^ (n & 7)) << 4)) = v;
   }
   ptx::fence_proxy_async();
@@ -1204,8 +1207,8 @@ __global__ void __launch_bounds__(FIRST_THREADS, 1)
     for (; tile < total_tiles; tile += stride, local += 2) {
       uint32_t o[16];
 #pragma unroll
-      for (int j = 0; j < 13; ++j) o[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
-      o[13] = ptx::pack_bf16x2(v[26], 0.f);
+      for (int j = 0; j < 13; ++j) o[j] = ptx::pack_op16x2(v[2 * j], v[2 * j + 1], p.f16);
+      o[13] = ptx::pack_op16x2(v[26], 0.f, p.f16);
       o[14] = 0u;
       o[15] = 0u;
       if (tile + stride < total_tiles) first_load_taps(p, tile + stride, dy, dx, v);  // in flight across the wait
@@ -1225,13 +1228,14 @@ __global__ void __launch_bounds__(FIRST_THREADS, 1)
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b));
+      const uint32_t idesc = p.f16 ? ptx::idesc_to_f16(IDESC) : IDESC;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + stage * A_SUB_BYTES));
-        ptx::mma_bf16_ss(tmem_base + acc * BN, da, db, IDESC, 0u);
-        ptx::mma_bf16_ss(tmem_base + acc * BN, da + 2, db + 2, IDESC, 1u);
+        ptx::mma_bf16_ss(tmem_base + acc * BN, da, db, idesc, 0u);
+        ptx::mma_bf16_ss(tmem_base + acc * BN, da + 2, db + 2, idesc, 1u);
         ptx::mma_commit(&empty_bar[stage]);
         ptx::mma_commit(&tmem_full[acc]);
         if (++stage == FIRST_STAGES) {
@@ -1325,13 +1329,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
   // weights [64][32] bf16 -> K-major 128-byte-swizzled rows (chunks 0..3 of every row); K slots 27 / 28 <- bias (hi, lo)
   for (int i = threadIdx.x; i < BN * 4; i += blockDim.x) {
     const int n = i >> 2, c = i & 3;
-    uint4 v = reinterpret_cast<const uint4*>(w32)[i];
+    uint4 v = reinterpret_cast<const uint4*>(w32 + (p.f16 ? BN * 32 : 0))[i];   // [bf16 copy | fp16 copy]
     if (c == 3) {  // elements 24..31: 27 = high half of v.y, 28 = low half of v.z
       const float b = (p.bias && n < p.Cout) ? p.bias[n] : 0.f;
-      const bf16 hi = __float2bfloat16_rn(b);
-      const bf16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
-      v.y = (v.y & 0x0000FFFFu) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
-      v.z = (v.z & 0xFFFF0000u) | (uint32_t)__bfloat16_as_ushort(lo);
+      const uint16_t hi = ptx::float_to_op16(b, p.f16);
+      const uint16_t lo = ptx::float_to_op16(b - ptx::op16_to_float(hi, p.f16), p.f16);
+      v.y = (v.y & 0x0000FFFFu) | ((uint32_t)hi << 16);
+      v.z = (v.z & 0xFFFF0000u) | (uint32_t)lo;
     }
     *reinterpret_cast<uint4*>(smem_b + n * 128 + ((c ^ (n & 7)) << 4)) = v;
   }
@@ -1365,9 +1369,9 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
       if (lane == 0) ptx::mbar_arrive(&patch_empty[stage]);
       uint32_t o[16];
 #pragma unroll
-      for (int j = 0; j < 13; ++j) o[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
-      o[13] = ptx::pack_bf16x2(v[26], 1.0f);   // K slot 27: 1.0 x bias_hi
-      o[14] = ptx::pack_bf16x2(1.0f, 0.f);     // K slot 28: 1.0 x bias_lo
+      for (int j = 0; j < 13; ++j) o[j] = ptx::pack_op16x2(v[2 * j], v[2 * j + 1], p.f16);
+      o[13] = ptx::pack_op16x2(v[26], 1.0f, p.f16);   // K slot 27: 1.0 x bias_hi
+      o[14] = ptx::pack_op16x2(1.0f, 0.f, p.f16);     // K slot 28: 1.0 x bias_lo
       o[15] = 0u;
       ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
       const uint32_t dst = ptx::smem_u32(smem_a + stage * A_SUB_BYTES) + row * 128;
@@ -1384,13 +1388,14 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b));
+      const uint32_t idesc = p.f16 ? ptx::idesc_to_f16(IDESC) : IDESC;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + stage * A_SUB_BYTES));
-        ptx::mma_bf16_ss(tmem_base + acc * BN, da, db, IDESC, 0u);
-        ptx::mma_bf16_ss(tmem_base + acc * BN, da + 2, db + 2, IDESC, 1u);
+        ptx::mma_bf16_ss(tmem_base + acc * BN, da, db, idesc, 0u);
+        ptx::mma_bf16_ss(tmem_base + acc * BN, da + 2, db + 2, idesc, 1u);
         ptx::mma_commit(&empty_bar[stage]);
         ptx::mma_commit(&tmem_full[acc]);
         if (++stage == FIRST_STAGES) {
@@ -1464,12 +1469,14 @@ void make_tmap_act(CUtensorMap* m, const bf16* base, int N, int H, int W, int C,
                     std::to_string(BW) + "x" + std::to_string(BH));
 }
 
-void make_tmap_weight(CUtensorMap* m, const bf16* base, int Cout, int K, int BN) {
-  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Cout};
-  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)BN};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(base), dims, strides, box, estr,
+// K-major weight rows [copies][Cout][K] of 16-bit operands: box {64, BN, 1}; the third coordinate selects the copy
+// (0 = bf16, 1 = fp16 where the packer wrote both; ConvParams::f16).  The element type only sets the element size.
+void make_tmap_weight(CUtensorMap* m, const bf16* base, int Cout, int K, int BN, int copies) {
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)Cout, (cuuint64_t)copies};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)Cout * K * 2};
+  cuuint32_t box[3] = {BLOCK_K, (cuuint32_t)BN, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<bf16*>(base), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   FRCNN_REQUIRE(r == CUDA_SUCCESS, FRCNN_E_CUDA,
@@ -1552,7 +1559,8 @@ static bool halo_cfg_ok(int Cout, int BN, int MT) {
 }
 
 static void conv_prepare_halo(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
-                              int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int BN, int MT) {
+                              int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int BN, int MT, int w_copies) {
+  L->w_copies = w_copies;
   FRCNN_REQUIRE(halo_cfg_ok(Cout, BN, MT), FRCNN_E_INVALID, "conv (halo kernel): unsupported (BN, MT) for this Cout");
   L->BN = BN;
   L->first = false;
@@ -1580,7 +1588,7 @@ static void conv_prepare_halo(ConvLaunch* L, const bf16* in, const bf16* w_packe
   p.halo_desc = env_int("FRCNN_HALO_DESC", 0);
   p.dbg = env_int("FRCNN_CONV_DBG", 0);
   make_tmap_act(&L->tmA, in, N, Hin, Win, Cin, HALO_BW + KW - 1, HALO_BH * MT + KH - 1);
-  make_tmap_weight(&L->tmB, w_packed, Cout, KH * KW * Cin, BN);
+  make_tmap_weight(&L->tmB, w_packed, Cout, KH * KW * Cin, BN, w_copies);
   make_out_map(L, out);
   const int total = p.n_tiles_m * p.n_tiles_n;
   L->grid = total < num_sms ? total : num_sms;
@@ -1613,14 +1621,16 @@ void conv_prepare_head(ConvLaunch* L, const bf16* in, const bf16* w_packed, int 
   p.halo = 1;
   p.halo_desc = env_int("FRCNN_HALO_DESC", 0);
   make_tmap_act(&L->tmA, in, N, Hin, Win, Cin, HALO_BW + K - 1, HALO_BH + K - 1);
-  make_tmap_weight(&L->tmB, w_packed, HEAD_CM, K * K * Cin, HEAD_CM);
+  make_tmap_weight(&L->tmB, w_packed, HEAD_CM, K * K * Cin, HEAD_CM, 2);   // forward weights: [bf16 | fp16] copies
+  L->w_copies = 2;
   L->tmOut = L->tmB;
   L->grid = p.n_tiles_m < num_sms ? p.n_tiles_m : num_sms;
 }
 
 void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
                   int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int force_splits, int force_bn,
-                  int force_mt) {
+                  int force_mt, int w_copies) {
+  L->w_copies = w_copies;
   FRCNN_REQUIRE(Cin % 64 == 0, FRCNN_E_INVALID, "conv: Cin must be a multiple of 64");
   const bool f32 = mode == EPI_F32_REDUCE || mode == EPI_F32_SLICES;
   FRCNN_REQUIRE(f32 ? Cout % 32 == 0 : (Cout % 64 == 0 && Cout <= MAX_BIAS), FRCNN_E_INVALID,
@@ -1663,7 +1673,7 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
         }
       }
       if (bn) {
-        conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, bn, mt);
+        conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, bn, mt, w_copies);
         return;
       }
       FRCNN_REQUIRE(!forced, FRCNN_E_INVALID, "conv: no halo-kernel tile for this (Cout, bn, mt)");
@@ -1707,7 +1717,7 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
   p.splits = (p.k_iters + p.k_per_split - 1) / p.k_per_split;
   p.dbg = env_int("FRCNN_CONV_DBG", 0);
   make_tmap_act(&L->tmA, in, N, Hin, Win, Cin, p.BW, p.BH * MT);
-  make_tmap_weight(&L->tmB, w_packed, Cout, KH * KW * Cin, BN);
+  make_tmap_weight(&L->tmB, w_packed, Cout, KH * KW * Cin, BN, w_copies);
   make_out_map(L, out);
   int total = p.n_tiles_m * p.n_tiles_n * p.splits;
   L->grid = total < num_sms ? total : num_sms;
@@ -1720,6 +1730,7 @@ void conv_wgrad_prepare(ConvLaunch* L, const bf16* dy, const bf16* x, float* dw_
   p = ConvParams();
   L->first = false;
   L->w_first = nullptr;
+  L->w_copies = 1;
   p.N = N; p.Hin = Hin; p.Win = Win; p.Cin = Cin; p.Cout = Cout; p.KH = KH; p.KW = KW; p.padH = padH; p.padW = padW;
   p.Hout = Hin + 2 * padH - KH + 1;
   p.Wout = Win + 2 * padW - KW + 1;
@@ -1817,7 +1828,8 @@ void conv_first_prepare(ConvLaunch* L, const bf16* w_packed32, int N, int Hin, i
   FRCNN_REQUIRE(mode == EPI_STORE || mode == EPI_POOL, FRCNN_E_INVALID, "first-layer kernel: bf16 epilogues only");
   L->BN = FIRST_BN;
   L->first = true;
-  L->w_first = w_packed32;
+  L->w_first = w_packed32;   // [2][Cout][32]: bf16 copy, fp16 copy
+  L->w_copies = 2;
   fill_geometry(L->p, N, Hin, Win, 64, Cout, KH, KW, padH, padW, mode, 1, 16);  // BW <= 16: warp-local pooling windows
   ConvParams& p = L->p;
   if (Win % 4 == 0 && padH == 1 && padW == 1 && env_int("FRCNN_FIRST_TMA", 1)) {
@@ -1910,6 +1922,7 @@ static void launch_key(int BN, int MT, const ConvMaps& maps, const ConvGroup& gr
 }
 
 void conv_launch(const ConvLaunch& L, cudaStream_t st) {
+  FRCNN_REQUIRE(!L.p.f16 || (L.w_copies == 2 && !L.p.wgrad), FRCNN_E_STATE, "conv: fp16 operands need the two-copy weight pack");
   ConvGroup grp;
   grp.n = 1;
   grp.p[0] = L.p;

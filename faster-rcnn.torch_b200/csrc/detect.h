@@ -31,14 +31,15 @@ struct DecodeParams {
   int* cand_count;               // [N]   (clamped to cap)
   int* cand_overflow;            // [1]   set when an image produced more than cap matches
   // chained-scan state
-  int* ticket;                   // [N]
+  unsigned long long* ticket;    // [N] 64-bit running block tickets
   unsigned long long* status;    // [N][nblocks]
   int nblocks;
 };
 void launch_rpn_decode(const DecodeParams& p, int N, cudaStream_t st);
 
 struct RoiParams {
-  const bf16* fmap;  // [N][FH][FW][C] bf16
+  const bf16* fmap;  // [N][FH][FW][C] 16-bit (bf16, or fp16 with f16 != 0)
+  int f16;
   int FH, FW, C, kh, kw;
   LocalizerDev loc;
   const double* cand_r;    // [N][cap][4]
@@ -89,6 +90,7 @@ struct GroupParams {
   float4* gbox;           // [N][cap]
   int* grow;              // [N][cap] roi row
   int* n_pass;            // [N]
+  int* overflow;          // set when an image has more NMS survivors than the in-CTA sort holds (8192)
 };
 void launch_group_by_class(const GroupParams& p, NmsWorkspace* ws, int N, cudaStream_t st);
 

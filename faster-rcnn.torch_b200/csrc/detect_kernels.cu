@@ -9,16 +9,20 @@ namespace frcnn {
 // anchors are written in that order (ordered stream compaction: ballot + a chained block prefix; block ids are
 // handed out by an atomic ticket so that a block only ever waits for blocks that are already running).
 __global__ void __launch_bounds__(256) rpn_decode_kernel(DecodeParams p) {
-  __shared__ int s_bid, s_excl;
+  __shared__ unsigned long long s_ticket;
+  __shared__ int s_excl;
   __shared__ int warp_cnt[8];
   const int img = blockIdx.y;
   // tickets keep counting across launches (no per-launch parameter, so the launch can be replayed from a CUDA graph):
-  // ticket t -> block id t % nblocks of launch number t / nblocks, which tags the scan-state words of that launch
-  if (threadIdx.x == 0) s_bid = (int)atomicAdd(reinterpret_cast<unsigned*>(&p.ticket[img]), 1u);
+  // ticket t -> block id t % nblocks of launch number t / nblocks, which tags the scan-state words of that launch.
+  // The counter is 64 bits wide: a 32-bit one wraps after 2^32 / nblocks launches and, unless nblocks divides 2^32,
+  // the launch straddling the wrap would hand out duplicate block ids.  The tag is the low 32 bits of the launch
+  // number + 1; launches 2^32 apart never overlap in time.
+  if (threadIdx.x == 0) s_ticket = atomicAdd(&p.ticket[img], 1ull);
   __syncthreads();
-  const unsigned ticket = (unsigned)s_bid;
-  const int bid = (int)(ticket % (unsigned)p.nblocks);
-  const unsigned epoch = ticket / (unsigned)p.nblocks + 1u;
+  const unsigned long long ticket = s_ticket;
+  const int bid = (int)(ticket % (unsigned long long)p.nblocks);
+  const unsigned epoch = (unsigned)(ticket / (unsigned long long)p.nblocks + 1ull);
   const int idx = bid * 256 + threadIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -150,7 +154,8 @@ __global__ void __launch_bounds__(256) roi_pool_nhwc_kernel(RoiParams p) {
   const int cv = p.C >> 3;
   const int per_row = p.kh * p.kw * cv;
   const long n_items = (long)total * per_row;
-  const uint4 ninf = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+  const uint32_t ni = p.f16 ? 0xFC00FC00u : 0xFF80FF80u;   // -inf pairs in the feature map's 16-bit format
+  const uint4 ninf = make_uint4(ni, ni, ni, ni);
   // flat (row, bin, 8-channel group) index space over the whole grid: few large ROIs still fill the machine
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < n_items; idx += (long)gridDim.x * blockDim.x) {
     const int row = (int)(idx / per_row);
@@ -172,10 +177,17 @@ __global__ void __launch_bounds__(256) roi_pool_nhwc_kernel(RoiParams p) {
 #pragma unroll 4
         for (int xx = xs; xx < xe; ++xx) {
           const uint4 v = __ldg(rowp + (long)xx * cv);
-          __nv_bfloat162* pm = reinterpret_cast<__nv_bfloat162*>(&m);
-          const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+          if (p.f16) {
+            __half2* pm = reinterpret_cast<__half2*>(&m);
+            const __half2* pv = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) pm[j] = __hmax2(pm[j], pv[j]);
+            for (int j = 0; j < 4; ++j) pm[j] = __hmax2(pm[j], pv[j]);
+          } else {
+            __nv_bfloat162* pm = reinterpret_cast<__nv_bfloat162*>(&m);
+            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pm[j] = __hmax2(pm[j], pv[j]);
+          }
         }
       }
     }
@@ -272,7 +284,11 @@ void launch_finalize(const FinalizeParams& p, int R_cap, cudaStream_t st) {
 __global__ void __launch_bounds__(1024) group_by_class_kernel(GroupParams p, NmsState st) {
   extern __shared__ unsigned long long gkeys[];
   const int img = blockIdx.x;
-  const int n = min(p.pick_count[img], p.cap);
+  int n = min(p.pick_count[img], p.cap);
+  if (n > NMS_CTA_MAX_SEG) {  // only reachable once the candidate capacity has grown past 8192 (api.cu)
+    if (threadIdx.x == 0) atomicExch(p.overflow, 1);
+    n = NMS_CTA_MAX_SEG;
+  }
   const int base = p.roi_base[img];
   int n2 = 1;
   while (n2 < n) n2 <<= 1;
@@ -333,9 +349,8 @@ void launch_group_by_class(const GroupParams& p, NmsWorkspace* ws, int N, cudaSt
   if (first_use_on_device(configured)) {
     FRCNN_CUDA_TRY(cudaFuncSetAttribute(group_by_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * 8));
   }
-  FRCNN_REQUIRE(p.cap <= 8192, FRCNN_E_INVALID, "candidate capacity per image must be <= 8192");
   int n2 = 1;
-  while (n2 < p.cap) n2 <<= 1;
+  while (n2 < std::min(p.cap, NMS_CTA_MAX_SEG)) n2 <<= 1;
   group_by_class_kernel<<<N, 1024, n2 * 8, st>>>(p, ws->st);
 }
 

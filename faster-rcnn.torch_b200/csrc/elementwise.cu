@@ -2,17 +2,34 @@
 // variant; the trunk uses the pool fused into the conv epilogue), anchor-head tail (bias + PReLU + 1x1 conv), cnet tails and layout converters.
 // All are coalesced / 16-byte vectorised streaming kernels; none has data reuse worth staging in shared memory
 // except the small weight matrices of the tails.
+#include <algorithm>
+
 #include "common.h"
 
 namespace frcnn {
 
 static inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }
 
+// Forward weights are packed TWICE: copy 0 = bf16 (training forward), copy 1 = fp16 (evaluate / detect,
+// ConvParams::f16); `copy_stride` elements apart (0 = bf16 copy only).  fp16 conversion saturates to +-65504.
+__device__ __forceinline__ void store_op16_copies(bf16* out, long i, long copy_stride, float v) {
+  out[i] = __float2bfloat16_rn(v);
+  if (copy_stride) reinterpret_cast<__half*>(out)[copy_stride + i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+}
+__device__ __forceinline__ float load_op16(const bf16* p, int f16) {
+  return f16 ? __half2float(*reinterpret_cast<const __half*>(p)) : __bfloat162float(*p);
+}
+__device__ __forceinline__ void store_op16(bf16* p, float v, int f16) {
+  if (f16) *reinterpret_cast<__half*>(p) = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+  else *p = __float2bfloat16_rn(v);
+}
+
 // ------------------------------------------------------------------------------------------ weight packing
 // Torch conv weight [Cout][Cin][KH][KW] fp32 -> [Cout][KH][KW][Cin] bf16 (K-major GEMM B operand).
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int KH,
-                                        int KW) {
+                                        int KW, int copies) {
   long total = (long)Cout * Cin * KH * KW;
+  const long cs = copies > 1 ? total : 0;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     int c = i % Cin;
     long r = i / Cin;
@@ -20,12 +37,12 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, bf16* __res
     r /= KW;
     int kh = r % KH;
     int o = r / KH;
-    out[i] = __float2bfloat16_rn(w[(((long)o * Cin + c) * KH + kh) * KW + kw]);
+    store_op16_copies(out, i, cs, w[(((long)o * Cin + c) * KH + kh) * KW + kw]);
   }
 }
-void launch_pack_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st) {
+void launch_pack_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st, int copies) {
   long total = (long)Cout * Cin * KH * KW;
-  pack_conv_weight_kernel<<<min(cdiv(total, 256), 148 * 8), 256, 0, st>>>(w, out, Cout, Cin, KH, KW);
+  pack_conv_weight_kernel<<<min(cdiv(total, 256), 148 * 8), 256, 0, st>>>(w, out, Cout, Cin, KH, KW, copies);
 }
 
 // First layer (Cin = 3): the flat Torch weight row [Cin*KH*KW] is already the im2col K order; pad K to 32.
@@ -33,7 +50,7 @@ __global__ void pack_first_conv_weight_kernel(const float* __restrict__ w, bf16*
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Cout * 32) return;
   int k = i & 31, o = i >> 5;
-  out[i] = __float2bfloat16_rn(k < K ? w[o * K + k] : 0.f);
+  store_op16_copies(out, i, (long)Cout * 32, k < K ? w[o * K + k] : 0.f);   // always both copies: [2][Cout][32]
 }
 void launch_pack_first_conv_weight(const float* w, bf16* out, int Cout, int Cin, int KH, int KW, cudaStream_t st) {
   pack_first_conv_weight_kernel<<<cdiv(Cout * 32, 256), 256, 0, st>>>(w, out, Cout, Cin * KH * KW);
@@ -96,9 +113,10 @@ void launch_nhwc_to_planar_bf16(const bf16* in, bf16* out, int N, int H, int W, 
 // Linear weight [nout][K] fp32 -> bf16.  With permute: K index c*bins + b (reference ROI-pool flatten order,
 // Detector.lua:97) -> b*C + c (the channel-contiguous order the ROI-pool kernel writes).
 __global__ void pack_fc_weight_kernel(const float* __restrict__ w, bf16* __restrict__ out, int nout, int C, int bins,
-                                      int permute) {
+                                      int permute, int copies) {
   long K = (long)C * bins;
   long total = (long)nout * K;
+  const long cs = copies > 1 ? total : 0;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     long o = i / K;
     long k = i - o * K;
@@ -107,12 +125,12 @@ __global__ void pack_fc_weight_kernel(const float* __restrict__ w, bf16* __restr
       int b = k / C, c = k - (long)b * C;
       src = (long)c * bins + b;
     }
-    out[i] = __float2bfloat16_rn(w[o * K + src]);
+    store_op16_copies(out, i, cs, w[o * K + src]);
   }
 }
-void launch_pack_fc_weight(const float* w, bf16* out, int nout, int C, int bins, int permute, cudaStream_t st) {
+void launch_pack_fc_weight(const float* w, bf16* out, int nout, int C, int bins, int permute, cudaStream_t st, int copies) {
   long total = (long)nout * C * bins;
-  pack_fc_weight_kernel<<<min(cdiv(total, 256), 148 * 8), 256, 0, st>>>(w, out, nout, C, bins, permute);
+  pack_fc_weight_kernel<<<min(cdiv(total, 256), 148 * 8), 256, 0, st>>>(w, out, nout, C, bins, permute, copies);
 }
 
 // ------------------------------------------------------------------------------------------ 2x2 ceil max pool
@@ -284,13 +302,13 @@ void launch_head_tail_group(const HeadTailGroup& g_in, int num_sms, cudaStream_t
 
 // ------------------------------------------------------------------------------------------ layout converters
 // NHWC bf16 -> [N][C][H][W] fp32 (Torch layout) through a 32x32 shared-memory transpose of (pixel, channel).
-__global__ void nhwc_to_chw_kernel(const bf16* __restrict__ in, float* __restrict__ out, int HW, int C) {
+__global__ void nhwc_to_chw_kernel(const bf16* __restrict__ in, float* __restrict__ out, int HW, int C, int f16) {
   __shared__ float tile[32][33];
   int n = blockIdx.z;
   int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     int p = p0 + j, c = c0 + threadIdx.x;
-    if (p < HW && c < C) tile[j][threadIdx.x] = __bfloat162float(in[((long)n * HW + p) * C + c]);
+    if (p < HW && c < C) tile[j][threadIdx.x] = load_op16(in + ((long)n * HW + p) * C + c, f16);
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -298,9 +316,9 @@ __global__ void nhwc_to_chw_kernel(const bf16* __restrict__ in, float* __restric
     if (p < HW && c < C) out[((long)n * C + c) * HW + p] = tile[threadIdx.x][j];
   }
 }
-void launch_nhwc_bf16_to_chw_f32(const bf16* in, float* out, int N, int H, int W, int C, cudaStream_t st) {
+void launch_nhwc_bf16_to_chw_f32(const bf16* in, float* out, int N, int H, int W, int C, cudaStream_t st, int f16) {
   dim3 grid(cdiv((long)H * W, 32), cdiv(C, 32), N), block(32, 8);
-  nhwc_to_chw_kernel<<<grid, block, 0, st>>>(in, out, H * W, C);
+  nhwc_to_chw_kernel<<<grid, block, 0, st>>>(in, out, H * W, C, f16);
 }
 __global__ void chw_to_nhwc_kernel(const float* __restrict__ in, bf16* __restrict__ out, int HW, int C) {
   __shared__ float tile[32][33];
@@ -324,31 +342,55 @@ void launch_chw_f32_to_nhwc_bf16(const float* in, bf16* out, int N, int H, int W
 // ------------------------------------------------------------------------------------------ cnet tails
 // nn.Linear bias + nn.BatchNormalization (evaluate mode, eps 1e-5) + nn.PReLU (model_utilities.lua:82-86) on the
 // fp32 split-K sums of a Linear layer.  Writes bf16 (operand of the next tensor-core GEMM) and/or fp32.
+// acc: either the summed fp32 GEMM output [rows][n] (sl.k_iters == 0) or the tile-major split-K slices the conv kernel
+// wrote with a device-chosen split count (ConvParams::slice_tile_major): the count is re-derived here from the live
+// row count with the kernel's own formula (make_sched) and the slices are summed in ascending order -- a fixed
+// summation order, so cnet:forward is reproducible run to run.
 __global__ void fc_tail_kernel(const float* __restrict__ acc, const float* __restrict__ bias, const float* __restrict__ bn_w,
                                const float* __restrict__ bn_b, const float* __restrict__ bn_mean,
                                const float* __restrict__ bn_var, const float* __restrict__ prelu, bf16* __restrict__ out_bf16,
-                               float* __restrict__ out_f32, int rows_max, const int* __restrict__ rows_dev, int n) {
+                               float* __restrict__ out_f32, int rows_max, const int* __restrict__ rows_dev, int n, FcSlices sl,
+                               int f16) {
   int rows = rows_dev ? min(*rows_dev, rows_max) : rows_max;
   long total = (long)rows * n;
   const float slope = prelu[0];
+  int splits = 0;
+  if (sl.k_iters > 0) {
+    const int m_tiles = max(1, (rows + 127) / 128);
+    int want = sl.dyn_ctas / (m_tiles * sl.n_tiles_n);
+    want = max(1, min(want, sl.host_splits));
+    const int kps = (sl.k_iters + want - 1) / want;
+    splits = (sl.k_iters + kps - 1) / kps;
+  }
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     int c = i % n;
-    float x = acc[i] + bias[c];
+    float x;
+    if (splits > 0) {
+      const long r = i / n;
+      const float* src = acc + (((r >> 7) * splits) * 128 + (r & 127)) * n + c;
+      x = src[0];
+      for (int s = 1; s < splits; ++s) x += src[(long)s * 128 * n];
+      x += bias[c];
+    } else {
+      x = acc[i] + bias[c];
+    }
     if (bn_w) {
       float inv = 1.0f / sqrtf(bn_var[c] + 1e-5f);
       x = (x - bn_mean[c]) * inv * bn_w[c] + bn_b[c];
     }
     x = x > 0.f ? x : x * slope;
-    if (out_bf16) out_bf16[i] = __float2bfloat16_rn(x);
+    if (out_bf16) store_op16(out_bf16 + i, x, f16);
     if (out_f32) out_f32[i] = x;
   }
 }
 void launch_fc_tail(const float* acc, const float* bias, const float* bn_w, const float* bn_b, const float* bn_mean,
                     const float* bn_var, const float* prelu, bf16* out_bf16, float* out_f32, int rows_max,
-                    const int* rows_dev, int n, cudaStream_t st) {
-  long total = (long)rows_max * n;
+                    const int* rows_dev, int n, cudaStream_t st, const FcSlices* sl, int grid_rows, int f16) {
+  FcSlices none = {0, 0, 0, 0};
+  // grid_rows: rows the grid is sized for (the typical live count, not the capacity): the grid-stride loop covers more
+  long total = (long)(grid_rows > 0 ? std::min(grid_rows, rows_max) : rows_max) * n;
   fc_tail_kernel<<<min(cdiv(total, 256), 148 * 8), 256, 0, st>>>(acc, bias, bn_w, bn_b, bn_mean, bn_var, prelu, out_bf16,
-                                                                  out_f32, rows_max, rows_dev, n);
+                                                                  out_f32, rows_max, rows_dev, n, sl ? *sl : none, f16);
 }
 
 // The two output branches of cnet (model_utilities.lua:96-105): Linear(nin -> 4) and Linear(nin -> ncls) +
@@ -359,10 +401,10 @@ __global__ void cnet_out_kernel(const float* __restrict__ hidden, const float* _
                                 float* __restrict__ cls_out, int rows_max, const int* __restrict__ rows_dev, int nin, int ncls) {
   extern __shared__ float sh[];  // [nin] hidden, [ncls + 4] logits
   int rows = rows_dev ? min(*rows_dev, rows_max) : rows_max;
-  int r = blockIdx.x;
-  if (r >= rows) return;
   float* h = sh;
   float* logit = sh + nin;
+  for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+  __syncthreads();  // the previous row's logits / hidden vector have been consumed
   for (int i = threadIdx.x; i < nin; i += blockDim.x) h[i] = hidden[(long)r * nin + i];
   __syncthreads();
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -388,12 +430,14 @@ __global__ void cnet_out_kernel(const float* __restrict__ hidden, const float* _
     float lse = m + logf(s);
     for (int c = lane; c < ncls; c += 32) cls_out[(long)r * ncls + c] = logit[4 + c] - lse;
   }
+  }
 }
 void launch_cnet_out(const float* hidden, const float* w_reg, const float* b_reg, const float* w_cls, const float* b_cls,
                      float* reg_out, float* cls_out, int rows_max, const int* rows_dev, int nin, int ncls, cudaStream_t st) {
   if (rows_max <= 0) return;
   int smem = (nin + ncls + 4) * sizeof(float);
-  cnet_out_kernel<<<rows_max, 256, smem, st>>>(hidden, w_reg, b_reg, w_cls, b_cls, reg_out, cls_out, rows_max, rows_dev, nin,
+  // the live row count is a device value: a grid of a few rows per SM strides over whatever it turns out to be
+  cnet_out_kernel<<<std::min(rows_max, 148 * 4), 256, smem, st>>>(hidden, w_reg, b_reg, w_cls, b_cls, reg_out, cls_out, rows_max, rows_dev, nin,
                                                 ncls);
 }
 

@@ -26,7 +26,7 @@ namespace frcnn {
 
 static constexpr int NMS_B = 1024;          // selection size per round
 static constexpr int NMS_ROW_WORDS = NMS_B / 32;
-static constexpr int SORT_CTA_MAX = 8192;   // largest segment sorted inside one CTA
+static constexpr int SORT_CTA_MAX = NMS_CTA_MAX_SEG;   // largest segment sorted inside one CTA
 
 __device__ __forceinline__ uint32_t orderable(float f) {
   uint32_t b = __float_as_uint(f);

@@ -4,6 +4,8 @@
 
 namespace frcnn {
 
+static constexpr int NMS_CTA_MAX_SEG = 8192;  // largest segment of the CTA-level path (the only one that takes device-side counts)
+
 struct NmsState {
   int* seg_beg;    // [n_seg] first row of segment s
   int* seg_len;    // [n_seg] number of rows of segment s

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -60,6 +61,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
           smem_u32(smem_dst)),
       "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"((uint64_t)m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
@@ -214,10 +222,38 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
          | (1u << 10)         // b_format = BF16
          | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// the same with fp16 operands (a_format = b_format = 0 = F16): clears the two format bits
+__host__ __device__ constexpr uint32_t idesc_to_f16(uint32_t idesc_bf16) { return idesc_bf16 & ~((1u << 7) | (1u << 10)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);
+}
+// fp16 pair, round to nearest even, saturating to +-65504 instead of overflowing to infinity
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// 16-bit operand pair in the format of the launch: f16 != 0 -> fp16, else bf16
+__device__ __forceinline__ uint32_t pack_op16x2(float lo, float hi, int f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+// element-wise maximum of four packed 16-bit pairs
+__device__ __forceinline__ uint32_t max4_op16x2(uint32_t a, uint32_t b, uint32_t c, uint32_t d, int f16) {
+  if (f16) {
+    const __half2 r = __hmax2(__hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b)),
+                              __hmax2(*reinterpret_cast<__half2*>(&c), *reinterpret_cast<__half2*>(&d)));
+    return *reinterpret_cast<const uint32_t*>(&r);
+  }
+  const __nv_bfloat162 r = __hmax2(__hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b)),
+                                   __hmax2(*reinterpret_cast<__nv_bfloat162*>(&c), *reinterpret_cast<__nv_bfloat162*>(&d)));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+// one 16-bit operand element -> float
+__device__ __forceinline__ float op16_to_float(uint16_t v, int f16) {
+  return f16 ? __half2float(__ushort_as_half(v)) : __bfloat162float(__ushort_as_bfloat16(v));
+}
+__device__ __forceinline__ uint16_t float_to_op16(float x, int f16) {
+  return f16 ? (uint16_t)(pack_f16x2(x, 0.f) & 0xFFFFu) : __bfloat16_as_ushort(__float2bfloat16_rn(x));
 }
 
 }  // namespace ptx

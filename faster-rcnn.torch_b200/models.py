@@ -127,6 +127,52 @@ class Model:
             self.params[n].copy_(v.reshape(-1).to(self.device))
         self.pack_weights()
 
+    # -- snapshots: utilities.lua:126-134 / main.lua:94-98 (Torch7 .t7 object streams, see t7.py) ---------------------
+    def learnable_names(self):
+        """Parameter tensors in `nn.Module.flatten` order as combine_and_flatten_parameters builds it (utilities.lua:136-147):
+        pnet's then cnet's learnable parameters.  BatchNormalization running statistics are not parameters in Torch.
+        (Inside pnet the order follows nngraph's topological sort of {block1..4, AnchorNetwork1..4} -- blocks, then heads,
+        is one valid order; the un-vendored nngraph's tie-breaking is unpinned.)"""
+        return [n for n in self.param_names if not n.endswith((".bn_mean", ".bn_var"))]
+
+    def get_flat_parameters(self):
+        """The reference's flat `weights` vector (learnable parameters only) as a float32 numpy array."""
+        return torch.cat([self.params[n].reshape(-1) for n in self.learnable_names()]).cpu().numpy()
+
+    def set_flat_parameters(self, w):
+        """weights:copy(stored.weights) (main.lua:97) + re-pack."""
+        w = torch.as_tensor(np.asarray(w, dtype=np.float32).reshape(-1))
+        names = self.learnable_names()
+        total = sum(self.params[n].numel() for n in names)
+        if w.numel() != total:
+            raise ValueError("snapshot holds %d parameters, the model has %d" % (w.numel(), total))
+        off = 0
+        for n in names:
+            k = self.params[n].numel()
+            self.params[n].copy_(w[off:off + k].to(self.device))
+            off += k
+        self.pack_weights()
+
+    def save_snapshot(self, file_name, options=None, stats=None, with_bn_running_stats=True, ascii=True):
+        """save_model(file_name, weights, opt, training_stats) (utilities.lua:126-134, main.lua:147)."""
+        from . import t7
+        bn = None
+        if with_bn_running_stats:
+            bn = {n: self.params[n].cpu().numpy() for n in self.param_names if n.endswith((".bn_mean", ".bn_var"))}
+        t7.save_model(file_name, t7.Tensor(self.get_flat_parameters(), "torch.CudaTensor"), options or {},
+                      stats or {"pcls": {}, "preg": {}, "dcls": {}, "dreg": {}}, bn, ascii=ascii)
+
+    def load_snapshot(self, file_name):
+        """load_model's restore branch (main.lua:94-98): returns the stored training_stats."""
+        from . import t7
+        w, _, stats, bn = t7.load_model(file_name)
+        self.set_flat_parameters(w)
+        if bn:
+            for n, v in bn.items():
+                self.params[n].copy_(torch.as_tensor(np.asarray(v, dtype=np.float32)).reshape(-1).to(self.device))
+            self.pack_weights()
+        return stats
+
     def normalize_frame(self, img, rgb2yuv=False, centering=True, scaling=True, contrastive_width=7):
         """The frame normalisation of BatchIterator:processImage / load_image (BatchIterator.lua:146-161,
         utilities.lua:211-212) on the GPU, in place on a [3][H][W] fp32 CUDA tensor (frcnn_normalize_frame)."""
@@ -144,12 +190,22 @@ class Model:
         if rc != 0:
             raise RuntimeError("frcnn_set_schedule failed")
 
+    def set_eval_precision(self, precision):
+        """'fp16' (default) or 'bf16': 16-bit operand format of the evaluate-mode tensor-core convolutions / Linear layers
+        (frcnn_set_eval_precision).  Training always uses bf16 operands."""
+        L = lib()
+        rc = L.frcnn_set_eval_precision(self.ctx, {"bf16": L.FRCNN_PREC_BF16, "fp16": L.FRCNN_PREC_FP16}[precision])
+        if rc != 0:
+            raise RuntimeError("frcnn_set_eval_precision failed")
+        self._precision = precision
+
     def replicate(self):
         """A second context of the same architecture on the same device holding a copy of the current weights (own
         stream, workspaces and CUDA graph): one more frame in flight for DetectorPipeline."""
         r = Model(self.cfg, self.layers, self.anchor_nets, self.class_layers, **self._ctor)
         r.weights.copy_(self.weights)
         r.pack_weights()
+        r.set_eval_precision(getattr(self, "_precision", "fp16"))
         return r
 
     def pack_weights(self):

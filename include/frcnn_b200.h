@@ -252,6 +252,14 @@ int frcnn_set_graph_replay(frcnn_ctx* ctx, int enable);
  * compute the same fp32 sums in a different, fixed order (results agree to fp32 rounding). */
 enum { FRCNN_SCHED_LATENCY = 0, FRCNN_SCHED_THROUGHPUT = 1 };
 int frcnn_set_schedule(frcnn_ctx* ctx, int schedule);
+/* 16-bit operand format of the tensor-core convolutions / Linear layers in EVALUATE mode (frcnn_pnet_forward,
+ * frcnn_cnet_forward, frcnn_detect*).  The reference computes in fp32 (cunn); FRCNN_PREC_FP16 (default) rounds operands
+ * to 11 significand bits -- the precision of tf32 at the bf16 tensor-core rate; outputs saturate at +-65504 -- and
+ * reproduces the fp32 path's discrete decisions (matches / candidates / winners) almost everywhere; FRCNN_PREC_BF16
+ * (8 bits) is kept for comparison.  Accumulation is fp32 either way.  Training entry points always use bf16 operands:
+ * gradient maps need its exponent range.  Measured agreement with the fp32 path: DESIGN.md 4, profiles/r2_precision*. */
+enum { FRCNN_PREC_BF16 = 0, FRCNN_PREC_FP16 = 1 };
+int frcnn_set_eval_precision(frcnn_ctx* ctx, int precision);
 int frcnn_last_timings(const frcnn_ctx* ctx, float ms[6]);
 /* Profiling mode also brackets every launch of the tcgen05 conv/GEMM kernel with a CUDA event pair on the ctx
  * stream: summed device time, summed algorithmic FLOPs (2*M*N*K of the un-padded problems) and launch count of

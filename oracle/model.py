@@ -176,6 +176,11 @@ def bf16_round(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def fp16_round(t):
+    """Operand rounding of the CUDA path's evaluate mode (FRCNN_PREC_FP16): 11 significand bits, saturating."""
+    return t.clamp(-65504.0, 65504.0).to(torch.float16).to(torch.float32)
+
+
 def synthetic_frame(h=450, w=800, seed=0):
     """One synthetic input frame: seeded N(0,1), then per-channel centring/scaling as
     BatchIterator.lua:146-159 applies to real images."""

@@ -163,22 +163,33 @@ def test_conv_exact_integers(F, small_model, mt):
     assert torch.equal(got[mask], ref[mask])
 
 
+# per-element tolerance of pnet:forward against the PURE fp32 oracle: |cuda - fp32| <= atol + rtol * |fp32|
+PNET_TOL = {"fp16": dict(atol=6e-3, rtol=4e-3), "bf16": dict(atol=4e-2, rtol=2e-2)}
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
 @pytest.mark.parametrize("h,w", [(122, 192), (450, 800)])
-def test_pnet_forward_vs_oracle(F, small_model, h, w):
-    """pnet:forward (model_utilities.lua:3-58) against the oracle.  Stated tolerance: against the oracle run with
-    bf16-rounded conv operands, 3 % of the per-map max magnitude (bf16 storage of the intermediate activations adds
-    one extra rounding per layer); against the pure fp32 oracle, 6 %."""
+def test_pnet_forward_vs_oracle(F, small_model, h, w, precision):
+    """pnet:forward (model_utilities.lua:3-58), evaluate mode, against the oracle at the headline size too.  Stated
+    tolerance per element against the pure fp32 oracle (the reference's arithmetic): PNET_TOL; against the oracle run
+    with the same 16-bit operand rounding, half of that (the stored intermediate activations add one rounding per
+    layer).  fp16 operands (the default) are 8x closer to the reference than bf16."""
     img = OM.synthetic_frame(h, w, seed=1)
-    outs = small_model.pnet.forward(img.cuda())
+    small_model.set_eval_precision(precision)
+    try:
+        outs = small_model.pnet.forward(img.cuda())
+    finally:
+        small_model.set_eval_precision("fp16")
+    q = OM.fp16_round if precision == "fp16" else OM.bf16_round
     with torch.no_grad():
-        want_q = OM.pnet_forward(OM.VGG_SMALL, small_model.oracle_params, img, quant=OM.bf16_round)
-        want_f = OM.pnet_forward(OM.VGG_SMALL, small_model.oracle_params, img) if h < 200 else None
-    for i, (o, q) in enumerate(zip(outs, want_q)):
-        assert tuple(o.shape) == tuple(q.shape)
-        scale = q.abs().max().item()
-        assert (o.cpu() - q).abs().max().item() <= 0.03 * scale, "output %d" % i
-        if want_f is not None:
-            assert (o.cpu() - want_f[i]).abs().max().item() <= 0.06 * want_f[i].abs().max().item()
+        want_q = OM.pnet_forward(OM.VGG_SMALL, small_model.oracle_params, img, quant=q)
+        want_f = OM.pnet_forward(OM.VGG_SMALL, small_model.oracle_params, img)
+    tol = PNET_TOL[precision]
+    for i, (o, wq, wf) in enumerate(zip(outs, want_q, want_f)):
+        assert tuple(o.shape) == tuple(wq.shape)
+        o = o.cpu()
+        assert bool(((o - wf).abs() <= tol["atol"] + tol["rtol"] * wf.abs()).all()), ("fp32 oracle, output %d" % i, float((o - wf).abs().max()))
+        assert bool(((o - wq).abs() <= 0.5 * (tol["atol"] + tol["rtol"] * wq.abs())).all()), ("rounded oracle, output %d" % i, float((o - wq).abs().max()))
 
 
 def test_pnet_batch_equals_single(F, small_model):
@@ -229,10 +240,10 @@ def test_vgg_large_throughput_schedule(F):
     img = OM.synthetic_frame(150, 200, seed=4)
     outs = m.pnet.forward(img.cuda())
     with torch.no_grad():
-        want = OM.pnet_forward(OM.VGG_LARGE, p, img, quant=OM.bf16_round)
+        want = OM.pnet_forward(OM.VGG_LARGE, p, img)   # pure fp32
     for o, q in zip(outs, want):
         assert tuple(o.shape) == tuple(q.shape)
-        assert (o.cpu() - q).abs().max().item() <= 0.03 * q.abs().max().item()
+        assert bool(((o.cpu() - q).abs() <= PNET_TOL["fp16"]["atol"] + PNET_TOL["fp16"]["rtol"] * q.abs()).all()), float((o.cpu() - q).abs().max())
     m.close()
 
 
@@ -253,8 +264,8 @@ def test_vgg_large_forward(F):
     img = OM.synthetic_frame(150, 200, seed=4)
     outs = m.pnet.forward(img.cuda())
     with torch.no_grad():
-        want = OM.pnet_forward(OM.VGG_LARGE, p, img, quant=OM.bf16_round)
+        want = OM.pnet_forward(OM.VGG_LARGE, p, img)   # pure fp32
     for o, q in zip(outs, want):
         assert tuple(o.shape) == tuple(q.shape)
-        assert (o.cpu() - q).abs().max().item() <= 0.03 * q.abs().max().item()
+        assert bool(((o.cpu() - q).abs() <= PNET_TOL["fp16"]["atol"] + PNET_TOL["fp16"]["rtol"] * q.abs()).all()), float((o.cpu() - q).abs().max())
     m.close()

