@@ -77,6 +77,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
   int th = r2 % p.tiles_h;
   t.n_img = r2 / p.tiles_h;
   t.h0 = th * p.BH * p.MT;
+  if (p.pair) t.h0 = (2 * th + (int)ptx::cluster_ctarank()) * p.BH * p.MT;  // CTA pair: this CTA's half of the pair tile
   t.w0 = tw * p.BW;
   t.n0 = nt * BN;
   t.k_begin = ks * k_per_split;
@@ -91,6 +92,11 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int tile, 
   }
   return t;
 }
+
+// Work units are dealt round-robin to the persistent CTAs -- or, on the CTA-pair kernel, to the pairs (both CTAs of a
+// pair walk the same unit sequence).
+__device__ __forceinline__ int unit_first(const ConvGroup& grp) { return grp.p[0].pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x; }
+__device__ __forceinline__ int unit_stride(const ConvGroup& grp) { return grp.p[0].pair ? (int)(gridDim.x >> 1) : (int)gridDim.x; }
 
 // Per-conv schedule values every warp role derives identically at kernel start.
 struct GroupSched {
@@ -140,7 +146,10 @@ static constexpr int EPI_THREADS = 256;
 template <int BN, int MT, int ACC = 2>
 __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtensorMap* tmOuts, uint8_t* tile_buf,
                                               const float* sbias, uint32_t tmem_base, uint64_t* tmem_full,
-                                              uint64_t* tmem_empty, const GroupSched& sc, int ewarp, int lane) {
+                                              uint64_t* tmem_empty, const GroupSched& sc, int ewarp, int lane,
+                                              uint32_t empty_leader_addr = 0) {
+  // empty_leader_addr (CTA-pair kernel): shared::cluster address of the LEADER's tmem_empty[0] -- the MMA issuer lives in the
+  // leader CTA and must see both CTAs' accumulator stages drained
   const int q = ewarp & 3;
   const int half = ewarp >> 2;
   const int row = q * 32 + lane;    // TMEM lane == pixel row of the sub-tile
@@ -152,7 +161,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
   const int sw = row & 7;
   const int total_units = grp.unit_end[grp.n - 1];
   int seq = 0;  // index of the unit in this CTA's sequence of live units: accumulator stage = seq & 1 (ACC = 2)
-  for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+  for (int unit = unit_first(grp); unit < total_units; unit += unit_stride(grp)) {
     int gi;
     TileCoord t;
     if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
@@ -320,7 +329,10 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
     }
     ptx::tc_fence_before();
     __syncwarp();
-    if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+    if (lane == 0) {
+      if (empty_leader_addr) ptx::mbar_arrive_cluster(empty_leader_addr + (uint32_t)acc * 8u);
+      else ptx::mbar_arrive(&tmem_empty[acc]);
+    }
   }
   if (store_thread) ptx::tma_store_wait_all();
 }
@@ -809,6 +821,214 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
   if (warp == 2) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- halo kernel on CTA pairs
+// conv_halo_kernel with cta_group::2.  What bounds the halo kernel (profiles/r1b_conv_sweep.md, r1b_ncu_full_*): every
+// CTA streams the WHOLE weight tensor of its N tile through its SM's L2 port (one CTA tile per unit at batch 1: 576 KB of
+// weights against 87 KB of activations for conv3_2) and reads A + B operands from shared memory at the 128 B/clk limit.
+// A CTA pair (two SMs of a TPC) computes a 2 x (128 * MT)-pixel tile with M = 256 MMAs: each CTA loads its own pixel
+// tile (with halo) but only HALF of every weight box, the tensor core reads the other half from the peer's shared
+// memory -- weight ingress and B operand reads per SM are halved.
+//   * cluster {2,1,1}; both CTAs run producer + epilogue warps, only the leader (rank 0) runs the MMA issuer;
+//   * full_a / full_b live in the leader: its producer arms them with the byte count of BOTH CTAs, the peer's TMA loads
+//     complete on them (cp.async.bulk.tensor .cta_group::2 with the leader's barrier address);
+//   * tcgen05.commit multicasts to empty_a / empty_b / tmem_full of both CTAs (same shared-memory offsets);
+//   * the peer's epilogue warps release the accumulator stage with a remote arrive on the leader's tmem_empty;
+//   * TMEM is allocated with cta_group::2 by the same warp of both CTAs; cluster barriers bracket the kernel.
+__host__ __device__ constexpr int pair_b_slots(int BN, int MT, int KMAX) {
+  return (SMEM_LIMIT - SMEM_FIXED - halo_extra(KMAX) - halo_a_slots(MT, KMAX) * halo_a_slot(MT, KMAX)) / (BN * 64) > 12
+             ? 12
+             : (SMEM_LIMIT - SMEM_FIXED - halo_extra(KMAX) - halo_a_slots(MT, KMAX) * halo_a_slot(MT, KMAX)) / (BN * 64);
+}
+static int pair_smem_bytes(int BN, int MT, int KMAX) {
+  return halo_a_slots(MT, KMAX) * halo_a_slot(MT, KMAX) + pair_b_slots(BN, MT, KMAX) * BN * 64 + SMEM_FIXED + halo_extra(KMAX);
+}
+
+template <int BN, int MT, int KMAX>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+    conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGroup grp) {
+  constexpr int A_SLOT = halo_a_slot(MT, KMAX), A_SLOTS = halo_a_slots(MT, KMAX);
+  constexpr int B_SLOT = BN * 64, B_SLOTS = pair_b_slots(BN, MT, KMAX);   // half a weight box: BN / 2 rows of 128 bytes
+  constexpr int ACC = halo_acc_stages(BN, MT);
+  constexpr int TMEM_COLS = halo_tmem_cols(BN, MT);
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(2 * BLOCK_M, BN);       // M = 256 over the pair
+  static_assert(B_SLOTS >= 2 && BN % 16 == 0, "weight ring too small / N must be a multiple of 16 for cta_group::2");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + A_SLOTS * A_SLOT;
+  uint8_t* tile_buf = smem_b + B_SLOTS * B_SLOT;
+  float* sbias = reinterpret_cast<float*>(tile_buf + STAGE_TILE_BYTES);
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
+  uint64_t* empty_a = full_a + A_SLOTS;
+  uint64_t* full_b = empty_a + A_SLOTS;
+  uint64_t* empty_b = full_b + B_SLOTS;
+  uint64_t* tmem_full = empty_b + B_SLOTS;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_units = grp.unit_end[grp.n - 1];
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  GroupSched sc;
+  make_sched(grp, BN, sc);
+
+  if (warp == 0 && lane == 0) {
+    for (int g = 0; g < grp.n; ++g) {
+      ptx::tma_prefetch_desc(&maps.a[g]);
+      ptx::tma_prefetch_desc(&maps.b[g]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < A_SLOTS; ++s) {
+      ptx::mbar_init(&full_a[s], 1);
+      ptx::mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < B_SLOTS; ++s) {
+      ptx::mbar_init(&full_b[s], 1);
+      ptx::mbar_init(&empty_b[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 2 * (EPI_THREADS / 32));   // the epilogue warps of BOTH CTAs (used in the leader only)
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2cta(tmem_base_slot, TMEM_COLS);
+    ptx::tmem_relinquish_2cta();
+  }
+  {
+    const ConvParams& p0 = grp.p[0];
+    for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (p0.bias && i < p0.Cout) ? p0.bias[i] : 0.f;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them remotely
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  const int u0 = unit_first(grp), ustride = unit_stride(grp);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs): own A box, half of every B box
+    if (lane == 0) {
+      const uint32_t full_a_leader = ptx::mapa_shared(ptx::smem_u32(full_a), 0);
+      const uint32_t full_b_leader = ptx::mapa_shared(ptx::smem_u32(full_b), 0);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int ua = u0, ca = 0;  // cursor of the A ring: one chunk ahead of the weight ring
+      auto issue_a = [&]() {
+        int ga;
+        TileCoord ta;
+        while (ua < total_units && !next_unit(grp, sc, ua, BN, ga, ta)) ua += ustride;
+        if (ua >= total_units) return;
+        const ConvParams& pa = grp.p[ga];
+        const uint32_t a_tx = (uint32_t)((HALO_BW + pa.KW - 1) * (HALO_BH * MT + pa.KH - 1)) * 128u;
+        ptx::mbar_wait(&empty_a[as], aph ^ 1);
+        if (leader) ptx::mbar_arrive_expect_tx(&full_a[as], 2 * a_tx);
+        ptx::tma_load_4d_2sm(smem_a + as * A_SLOT, &maps.a[ga], full_a_leader + (uint32_t)as * 8u, ca * BLOCK_K, ta.w0 - pa.padW,
+                             ta.h0 - pa.padH, ta.n_img);
+        if (++as == A_SLOTS) {
+          as = 0;
+          aph ^= 1;
+        }
+        if (++ca == pa.cchunks) {
+          ca = 0;
+          ua += ustride;
+        }
+      };
+      issue_a();
+      for (int unit = u0; unit < total_units; unit += ustride) {
+        int gi;
+        TileCoord t;
+        if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+        const ConvParams& p = grp.p[gi];
+        const int taps = p.KH * p.KW;
+        const int kpre = min(B_SLOTS - 1, taps - 1);
+        for (int c = 0; c < p.cchunks; ++c) {
+          for (int tap = 0; tap < taps; ++tap) {
+            if (tap == kpre) issue_a();
+            ptx::mbar_wait(&empty_b[bs], bph ^ 1);
+            if (leader) ptx::mbar_arrive_expect_tx(&full_b[bs], 2 * B_SLOT);
+            ptx::tma_load_3d_2sm(smem_b + bs * B_SLOT, &maps.b[gi], full_b_leader + (uint32_t)bs * 8u, (tap * p.cchunks + c) * BLOCK_K,
+                                 t.n0 + (int)rank * (BN / 2), p.f16);
+            if (++bs == B_SLOTS) {
+              bs = 0;
+              bph ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int seq = 0;
+      for (int unit = u0; unit < total_units; unit += ustride) {
+        int gi;
+        TileCoord t;
+        if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+        const ConvParams& p = grp.p[gi];
+        const int PW = HALO_BW + p.KW - 1;  // halo pitch, pixels
+        const uint32_t sbo = (uint32_t)PW * 128u;
+        const uint32_t idesc = p.f16 ? ptx::idesc_to_f16(IDESC) : IDESC;
+        const int acc = ACC == 2 ? (seq & 1) : 0;
+        const uint32_t acc_phase = (uint32_t)(ACC == 2 ? (seq >> 1) : seq) & 1u;
+        ++seq;
+        ptx::mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN * MT;
+        for (int c = 0; c < p.cchunks; ++c) {
+          ptx::mbar_wait(&full_a[as], aph);
+          const uint32_t a_addr = ptx::smem_u32(smem_a + as * A_SLOT);
+          for (int kh = 0; kh < p.KH; ++kh) {
+            for (int kw = 0; kw < p.KW; ++kw) {
+              ptx::mbar_wait(&full_b[bs], bph);
+              ptx::tc_fence_after();
+              const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + bs * B_SLOT));
+              const uint32_t first = (c == 0 && kh == 0 && kw == 0) ? 0u : 1u;
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const int row0 = (mt * HALO_BH + kh) * PW + kw;  // first 128-byte row of this tap's operand
+                const uint64_t da = ptx::make_desc_k_sw128_sbo(a_addr + row0 * 128, sbo, 0u);
+#pragma unroll
+                for (int j = 0; j < BLOCK_K / 16; ++j)
+                  if (!(p.dbg & 4)) ptx::mma_bf16_ss_2cta(d_tmem + mt * BN, da + 2 * j, db + 2 * j, idesc, j > 0 ? 1u : first);
+              }
+              ptx::mma_commit_2cta(&empty_b[bs], 3);
+              if (++bs == B_SLOTS) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+          }
+          ptx::mma_commit_2cta(&empty_a[as], 3);
+          if (++as == A_SLOTS) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+        ptx::mma_commit_2cta(&tmem_full[acc], 3);
+      }
+    }
+  } else if (warp >= 4) {
+    const uint32_t empty_leader = ptx::mapa_shared(ptx::smem_u32(tmem_empty), 0);
+    epilogue_loop<BN, MT, ACC>(grp, maps.o, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 4, lane, empty_leader);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the peer may still read its shared memory / barriers
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2cta(tmem_base, TMEM_COLS);
   }
 }
 
@@ -1594,6 +1814,23 @@ static void conv_prepare_halo(ConvLaunch* L, const bf16* in, const bf16* w_packe
   L->grid = total < num_sms ? total : num_sms;
 }
 
+// conv_pair_kernel (cta_group::2): same tiling as the halo kernel, a unit = two CTA tiles stacked along H, the weight
+// box is half an N tile (each CTA of the pair loads BN / 2 rows)
+static void conv_prepare_pair(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
+                              int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int BN, int MT, int w_copies) {
+  FRCNN_REQUIRE(halo_cfg_ok(Cout, BN, MT) && BN % 16 == 0, FRCNN_E_INVALID, "conv (pair kernel): unsupported (BN, MT) for this Cout");
+  conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, BN, MT, w_copies);
+  ConvParams& p = L->p;
+  p.pair = 1;
+  p.tiles_h = (p.Hout + 2 * p.BH * MT - 1) / (2 * p.BH * MT);
+  p.n_tiles_m = N * p.tiles_h * p.tiles_w;
+  make_tmap_weight(&L->tmB, w_packed, Cout, KH * KW * Cin, BN / 2, w_copies);
+  L->tmOut = L->tmB;
+  const int total = p.n_tiles_m * p.n_tiles_n;
+  const int pairs = std::max(1, num_sms / 2);
+  L->grid = 2 * (total < pairs ? total : pairs);
+}
+
 void conv_prepare_head(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int K, int num_sms) {
   FRCNN_REQUIRE(Cin % 64 == 0 && K >= 1 && K <= HEAD_MAXK, FRCNN_E_INVALID, "fused anchor head: Cin % 64 == 0, kernel size <= 7");
   FRCNN_REQUIRE(Hin >= K && Win >= K, FRCNN_E_INVALID, "fused anchor head: input smaller than the kernel");
@@ -1645,6 +1882,24 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
     const bool eligible = (!f32 || f32_single) && KH <= HALO_MAXK && KW <= HALO_MAXK && KH * KW > 1 && Cout % 64 == 0;
     const bool forced = force_mt >= 10;
     FRCNN_REQUIRE(!forced || eligible, FRCNN_E_INVALID, "conv: the halo kernel needs 2x2..3x3 filters and a bf16 epilogue");
+    // CTA-pair kernel (cta_group::2): force_mt 21 / 22, or automatically (FRCNN_CONV_PAIR, see the selection rule below)
+    const bool pair_ok = eligible && !f32 && Cout % 64 == 0;
+    if (pair_ok && (force_mt == 21 || force_mt == 22)) {
+      const int mt = force_mt - 20;
+      int bn = force_bn > 0 ? force_bn : (Cout % 256 == 0 ? 256 : (Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : 64)));
+      FRCNN_REQUIRE(halo_cfg_ok(Cout, bn, mt), FRCNN_E_INVALID, "conv: no pair-kernel tile for this (Cout, bn, mt)");
+      conv_prepare_pair(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, bn, mt, w_copies);
+      return;
+    }
+    FRCNN_REQUIRE(force_mt < 20, FRCNN_E_INVALID, "conv: the pair kernel needs 2x2..3x3 filters and a bf16 epilogue");
+    if (pair_ok && force_mt == 0 && force_bn == 0 && env_int("FRCNN_CONV_PAIR", 0)) {
+      const int bn = Cout % 256 == 0 ? 256 : (Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : 64));
+      const int mt = env_int("FRCNN_CONV_PAIR_MT", bn <= 128 ? 2 : 1);
+      if (halo_cfg_ok(Cout, bn, mt)) {
+        conv_prepare_pair(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, bn, mt, w_copies);
+        return;
+      }
+    }
     if (eligible && (forced || (force_mt == 0 && env_int("FRCNN_CONV_HALO", 1)))) {
       // Measured on B200 (tools/bench_conv_layers.py sweep, profiles/r1_conv_sweep.md): the halo kernel wins where the
       // N tile is wide (BN >= 192: the M128 x N128 MMA is bound by shared-memory operand bandwidth whichever way its A
@@ -1875,6 +2130,41 @@ static void launch_halo_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
+template <int BN, int MT, int KMAX>
+static void launch_pair_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+  static DeviceOnce configured;
+  const int smem = pair_smem_bytes(BN, MT, KMAX);
+  if (first_use_on_device(configured)) {
+    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<BN, MT, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(CONV_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FRCNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_pair_kernel<BN, MT, KMAX>, maps, grp));
+}
+static void launch_pair_key(int BN, int MT, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+  switch (BN * 10 + MT) {
+    case 641: launch_pair_cfg<64, 1, HALO_MAXK>(maps, grp, grid, st); break;
+    case 642: launch_pair_cfg<64, 2, HALO_MAXK>(maps, grp, grid, st); break;
+    case 1281: launch_pair_cfg<128, 1, HALO_MAXK>(maps, grp, grid, st); break;
+    case 1282: launch_pair_cfg<128, 2, HALO_MAXK>(maps, grp, grid, st); break;
+    case 1921: launch_pair_cfg<192, 1, HALO_MAXK>(maps, grp, grid, st); break;
+    case 1922: launch_pair_cfg<192, 2, HALO_MAXK>(maps, grp, grid, st); break;
+    case 2561: launch_pair_cfg<256, 1, HALO_MAXK>(maps, grp, grid, st); break;
+    case 2562: launch_pair_cfg<256, 2, HALO_MAXK>(maps, grp, grid, st); break;
+    default: throw Error{FRCNN_E_INVALID, "conv (pair kernel): unsupported (BN, MT)"};
+  }
+}
+
 static void launch_halo_key(int BN, int MT, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
   switch (BN * 10 + MT) {
     case 641: launch_halo_cfg<64, 1, HALO_MAXK>(maps, grp, grid, st); break;
@@ -1968,6 +2258,7 @@ void conv_launch(const ConvLaunch& L, cudaStream_t st) {
     maps.o[g] = L.tmOut;
   }
   if (L.p.wgrad && L.p.halo) launch_wgrad_halo_key(L.BN, maps, grp, L.grid, st);
+  else if (L.p.pair) launch_pair_key(L.BN, L.p.MT, maps, grp, L.grid, st);
   else if (L.p.halo) launch_halo_key(L.BN, L.p.MT, maps, grp, L.grid, st);
   else launch_key(L.BN, L.p.MT, maps, grp, L.grid, st);
 }

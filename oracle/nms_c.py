@@ -23,6 +23,8 @@ def lib():
         _LIB.oracle_nms.restype = ctypes.c_int64
         _LIB.oracle_nms.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_float, ctypes.c_int,
                                     ctypes.c_int, ctypes.c_void_p]
+        _LIB.oracle_nms_pairs.restype = ctypes.c_int64
+        _LIB.oracle_nms_pairs.argtypes = [ctypes.c_int]
         _LIB.oracle_nms_segmented.restype = None
         _LIB.oracle_nms_segmented.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int,
                                               ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
@@ -48,3 +50,8 @@ def nms_segmented(boxes, seg_offsets, overlap, order_mode=0, order_col=0, thread
     lib().oracle_nms_segmented(boxes.ctypes.data, boxes.shape[1], seg.ctypes.data, n_seg, overlap, order_mode,
                                order_col, pick.ctypes.data, counts.ctypes.data, threads)
     return pick, counts
+
+
+def pair_iou_count(reset=True):
+    """Pair-IoU evaluations the reference algorithm performed since the last reset (nms.lua:72-96)."""
+    return int(lib().oracle_nms_pairs(1 if reset else 0))

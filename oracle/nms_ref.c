@@ -13,6 +13,15 @@
 
 typedef struct { float key; int64_t idx; } kv_t;
 
+/* number of pair-IoU evaluations the reference algorithm performed (every pick tests all remaining boxes, nms.lua:72-96)
+ * since the last reset: the unit of SURVEY 8d's "pair-IoU/s" */
+static int64_t g_pairs = 0;
+int64_t oracle_nms_pairs(int reset) {
+  int64_t v = __atomic_load_n(&g_pairs, __ATOMIC_RELAXED);
+  if (reset) __atomic_store_n(&g_pairs, 0, __ATOMIC_RELAXED);
+  return v;
+}
+
 static int cmp_kv(const void *a, const void *b) {
   const kv_t *x = (const kv_t *)a, *y = (const kv_t *)b;
   if (x->key < y->key) return -1;
@@ -36,7 +45,7 @@ int64_t oracle_nms(const float *boxes, int64_t n, int64_t row_stride, float over
   }
   qsort(kv, (size_t)n, sizeof(kv_t), cmp_kv); /* nms.lua:45 */
   for (int64_t j = 0; j < n; ++j) I[j] = kv[j].idx;
-  int64_t m = n, count = 0;
+  int64_t m = n, count = 0, pairs = 0;
   while (m > 0) { /* nms.lua:58-97 */
     int64_t i = I[m - 1];
     pick[count++] = i;
@@ -45,6 +54,7 @@ int64_t oracle_nms(const float *boxes, int64_t n, int64_t row_stride, float over
     const float *bi = boxes + i * row_stride;
     const float x1i = bi[0], y1i = bi[1], x2i = bi[2], y2i = bi[3], ai = area[i];
     int64_t out = 0;
+    pairs += m;
     for (int64_t t = 0; t < m; ++t) {
       int64_t j = I[t];
       const float *b = boxes + j * row_stride;
@@ -60,6 +70,7 @@ int64_t oracle_nms(const float *boxes, int64_t n, int64_t row_stride, float over
     m = out;
   }
   free(area); free(kv); free(I);
+  __atomic_fetch_add(&g_pairs, pairs, __ATOMIC_RELAXED);
   return count;
 }
 
