@@ -11,6 +11,6 @@ from .nms import nms, nms_segmented, nms_segmented_dev  # noqa: F401
 from .models import Model, create_model, duplo_cfg, imgnet_cfg, vgg_large, vgg_small  # noqa: F401
 from .detector import Detector, DetectorPipeline, extract_roi_pooling_input  # noqa: F401
 from .shard import reduce_timing, shard_frames, shard_segments  # noqa: F401
-from .objective import allreduce_gradient, clean_anchors, create_objective  # noqa: F401
+from .objective import allreduce_gradient, clean_anchors, create_objective, dp_allreduce, dp_init  # noqa: F401
 from .optim import rmsprop, rmsprop_step  # noqa: F401
 from . import t7  # noqa: F401,E402  (Torch7 .t7 snapshots: utilities.lua:113-134)

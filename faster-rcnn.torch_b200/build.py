@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc compilation failed")
     if force or procs or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-                                                     "-Xlinker", "--exclude-libs=ALL", "-Xlinker", "-Bsymbolic"]
+                                                     "-Xlinker", "--exclude-libs=ALL", "-Xlinker", "-Bsymbolic", "-ldl"]
         subprocess.check_call(cmd)
     return LIB
 

@@ -1,5 +1,6 @@
 // C ABI of the library (include/frcnn_b200.h): context, model plan, weight packing, pnet / cnet forward and the
 // fused Detector:detect pipeline.  Host orchestration only -- every arithmetic step is a kernel of this library.
+#include <dlfcn.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -117,6 +118,7 @@ struct frcnn_ctx {
   bf16* gscratch[2] = {nullptr, nullptr};
   const float* train_img = nullptr;
   // objective.lua stage buffers (frcnn_train_image), sized for cw_rows examples
+  int cnet_train_rows = 0;         // rows of the last frcnn_cnet_forward_train (0: none pending for frcnn_cnet_backward)
   int cw_rows = 0;
   int cw_n = 0;                    // frames the per-frame objective buffers (head_dout, losses_dev) are sized for
   long cw_gen = -1;                // pnet workspace generation they were sized against
@@ -217,6 +219,15 @@ struct frcnn_ctx {
   // scratch for API-level calls
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
+  // data-parallel training: one NCCL communicator rank per context, gradient buckets all-reduced on a
+  // side stream as pnet:backward finishes them
+  void* dp_comm = nullptr;           // ncclComm_t
+  int dp_rank = 0, dp_nranks = 1;
+  cudaStream_t dp_stream = nullptr;
+  cudaEvent_t dp_ready = nullptr, dp_done = nullptr;
+  bool dp_overlap = false;           // frcnn_dp_set_overlap: buckets go out from inside frcnn_train_batch / frcnn_pnet_backward
+  std::vector<char> dp_bucket_sent;  // per bucket: already all-reduced in this step
+  int64_t dp_bytes = 0;              // bytes all-reduced so far (bench accounting)
 };
 
 namespace frcnn {
@@ -650,6 +661,7 @@ static void run_conv(frcnn_ctx* c, ConvLayer& cv) {
 }
 
 static void ensure_train_workspace(frcnn_ctx* c, int N, int H, int W);
+static int detect_stop_after();
 
 static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, int W, bool train = false) {
   FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called before the forward pass");
@@ -681,6 +693,7 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
   // ONE launch of unsplit units, k x k conv and tail fused -- the least SM time per frame, the machine is filled by
   // the other frames.  Latency schedule: one grouped split-K conv launch (every SM busy on this frame), heaviest
   // units first, then one grouped tail launch.
+  if (detect_stop_after() == 1 && !train) return;
   if (c->schedule == FRCNN_SCHED_THROUGHPUT && !train) {
     std::vector<const ConvLaunch*> order;
     for (auto& hd : c->heads) {
@@ -807,6 +820,8 @@ static void ensure_train_workspace(frcnn_ctx* c, int N, int H, int W) {
   c->tws_n = N; c->tws_h = H; c->tws_w = W;
 }
 
+static void dp_bucket_ready(frcnn_ctx* c, int bucket);
+
 // weight gradient of one conv: taps buffer zeroed, tensor-core wgrad, accumulated into the bound Torch-layout gradient
 static void run_wgrad(frcnn_ctx* c, ConvLayer& cv) {
   FRCNN_CUDA_TRY(cudaMemsetAsync(cv.dw_taps, 0, (size_t)cv.cout * cv.cin * cv.k * cv.k * sizeof(float), c->stream));
@@ -869,6 +884,7 @@ static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out, bool keep_
     run_wgrad(c, hd.conv);
     run_dgrad(c, hd.conv);
   }
+  dp_bucket_ready(c, 1);   // the anchor networks' gradients are final
   // trunk, last block first
   size_t li_end = c->trunk.size();
   for (int b = nb - 1; b >= 0; --b) {
@@ -898,6 +914,7 @@ static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out, bool keep_
       }
     }
     li_end = li_first;
+    dp_bucket_ready(c, 2 + (nb - 1 - b));   // this block's gradients are final
   }
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
@@ -981,10 +998,8 @@ static void wgrad_rows(frcnn_ctx* c, const bf16* dy, const bf16* x, int R, int n
 // gradient), while BatchNormalization / PReLU / Dropout and the criteria run per frame on its row slice -- in the
 // reference cnet sees the ROI batch of one image at a time (objective.lua:164 inside the per-image loop), so the batch
 // statistics, the running-statistics updates (in frame order) and the mean over the frame's rows stay per frame.
-static void run_cnet_train_frames(frcnn_ctx* c, int nf, const int* off, const int* R, const int* n_pos, const float* const* cnet_masks,
-                                  const uint64_t* seeds) {
+static void cnet_train_forward(frcnn_ctx* c, int nf, const int* off, const int* R, const float* const* cnet_masks, const uint64_t* seeds) {
   cudaStream_t st = c->stream;
-  const int bins = c->roi_kh * c->roi_kw;
   const int rows = off[nf - 1] + R[nf - 1];
   if (rows <= 0) return;
   // ---- cnet forward, training mode (objective.lua:164)
@@ -1011,6 +1026,14 @@ static void run_cnet_train_frames(frcnn_ctx* c, int nf, const int* off, const in
     }
     in = f.t_out;
   }
+}
+// ext_dreg / ext_dcls: gradients wrt cnet's two outputs supplied by the caller (cnet:backward(cinput, {crdelta, ccdelta}),
+// objective.lua:179) instead of the built-in criteria
+static void cnet_train_loss_bwd(frcnn_ctx* c, int nf, const int* off, const int* R, const int* n_pos, const float* ext_dreg = nullptr,
+                                const float* ext_dcls = nullptr) {
+  cudaStream_t st = c->stream;
+  const int rows = off[nf - 1] + R[nf - 1];
+  if (rows <= 0) return;
   // ---- detection-stage criteria + backward through the two output branches (objective.lua:166-179), per frame
   FcLayer& last = c->fcs.back();
   const int no = c->class_count + 5;
@@ -1024,9 +1047,17 @@ static void run_cnet_train_frames(frcnn_ctx* c, int nf, const int* off, const in
     cl.d_hidden = c->t_dhidden + (size_t)off[fr] * last.nout; cl.dz = c->t_dz + (size_t)off[fr] * no;
     cl.g_w_reg = G(c, c->p_reg_w); cl.g_b_reg = G(c, c->p_reg_b); cl.g_w_cls = G(c, c->p_cls_w); cl.g_b_cls = G(c, c->p_cls_b);
     cl.losses = nf == 1 ? c->losses_cur : c->losses_dev + 8 * fr;
+    cl.ext_dreg = ext_dreg ? ext_dreg + (size_t)off[fr] * 4 : nullptr;
+    cl.ext_dcls = ext_dcls ? ext_dcls + (size_t)off[fr] * (c->class_count + 1) : nullptr;
     launch_cnet_loss_bwd(cl, st);
     c->launches += 2;
   }
+}
+static void cnet_train_backward(frcnn_ctx* c, int nf, const int* off, const int* R) {
+  cudaStream_t st = c->stream;
+  const int bins = c->roi_kh * c->roi_kw;
+  const int rows = off[nf - 1] + R[nf - 1];
+  if (rows <= 0) return;
   // ---- cnet backward (objective.lua:179)
   const float* d_in = c->t_dhidden;
   for (int i = (int)c->fcs.size() - 1; i >= 0; --i) {
@@ -1059,6 +1090,12 @@ static void run_cnet_train_frames(frcnn_ctx* c, int nf, const int* off, const in
     gemm_rows(c, f.t_dy, f.w_dgrad, rows, f.nout, f.nin, d_prev);
     d_in = d_prev;
   }
+}
+static void run_cnet_train_frames(frcnn_ctx* c, int nf, const int* off, const int* R, const int* n_pos, const float* const* cnet_masks,
+                                  const uint64_t* seeds) {
+  cnet_train_forward(c, nf, off, R, cnet_masks, seeds);
+  cnet_train_loss_bwd(c, nf, off, R, n_pos);
+  cnet_train_backward(c, nf, off, R);
 }
 
 static void run_cnet_train(frcnn_ctx* c, int R, int n_pos, const float* const* cnet_masks, uint64_t seed) {
@@ -1139,6 +1176,7 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
     }
     c->losses_cur = c->losses_dev;
     run_cnet_train_frames(c, N, off.data(), Rn.data(), n_pos, cnet_masks, seeds);
+    dp_bucket_ready(c, 0);   // cnet's gradients are final: their all-reduce overlaps pnet:backward
     // ---- ROI-pool backward into delta_outputs[5] (objective.lua:182-185), kept as the fp32 NHWC block gradient
     for (int n = 0; n < N; ++n) {
       if (Rn[n] <= 0) continue;
@@ -1317,15 +1355,28 @@ static void run_decode(frcnn_ctx* c, const float* const* heads_dev, int N, int H
 }
 
 // Enqueues the whole Detector:detect pipeline (Detector.lua:31-136) plus the result copies on the ctx stream.
+static int detect_stop_after() {
+  // FRCNN_DETECT_STOP (measurement only: tools/stage_costs.sh): 1 = trunk, 2 = + anchor heads, 3 = + decode / NMS,
+  // 4 = + ROI pooling, 5 = + cnet; 0 / unset = the whole pipeline.  Winners are meaningless when set.
+  static const int v = getenv("FRCNN_DETECT_STOP") ? atoi(getenv("FRCNN_DETECT_STOP")) : 0;
+  return v;
+}
+
 static void enqueue_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int W) {
   cudaStream_t st = c->stream;
   const bool prof = c->profiling;
+  const int stop = detect_stop_after();
+  auto copy_back = [&]() {
+    if (prof) for (int i = 1; i <= 5; ++i) cudaEventRecord(c->ev[i], st);
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(c->h_ints, c->flags, (16 + 2 * (size_t)c->det_n) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  };
   if (prof) {
     conv_profile_begin(c);
     cudaEventRecord(c->ev[0], st);
   }
   do_pnet_forward(c, img_dev, N, H, W);
   if (prof) cudaEventRecord(c->ev[1], st);
+  if (stop == 1 || stop == 2) return copy_back();
   // --- Detector.lua:36-66
   const float* heads_dev[MAX_HEADS];
   for (int i = 0; i < MAX_HEADS; ++i) heads_dev[i] = c->heads[i].out;
@@ -1367,6 +1418,7 @@ static void enqueue_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int
     }
   }
   if (prof) cudaEventRecord(c->ev[2], st);
+  if (stop == 3) return copy_back();
   // --- Detector.lua:91-98: ROI pooling of every candidate
   RoiParams rp;
   rp.f16 = c->act_f16;
@@ -1378,9 +1430,11 @@ static void enqueue_detect(frcnn_ctx* c, const float* img_dev, int N, int H, int
   launch_roi_pool_nhwc(rp, N, c->sm_count, st);
   c->launches += 2;
   if (prof) cudaEventRecord(c->ev[3], st);
+  if (stop == 4) return copy_back();
   // --- Detector.lua:101: cnet
   run_cnet(c, c->roi_cap);
   if (prof) cudaEventRecord(c->ev[4], st);
+  if (stop == 5) return copy_back();
   // --- Detector.lua:106-122
   FinalizeParams fp;
   fp.cand_r = c->cand_r; fp.cand_logp = c->cand_logp; fp.cand_anchor = c->cand_anchor; fp.cap = c->cand_cap;
@@ -1571,6 +1625,110 @@ static const float* stage_frames(frcnn_ctx* c, const float* img, bool on_device,
   return c->d_img;
 }
 
+// ---------------------------------------------------------------------------------------------- data-parallel training
+// The one collective of the path (objective.lua:189,200 sum the per-image gradients and divide once): an
+// all-reduce (sum) of the flat gradient over the ranks.  NCCL is loaded at run time (dlopen: the library itself links
+// nothing but the CUDA runtime); one communicator rank per context.  The gradient is reduced IN PLACE in buckets, in the
+// order pnet:backward finishes them -- cnet, anchor networks, conv block 4 ... 1 -- on a side stream, so that all but the
+// last bucket travel over NVLink while the remaining weight gradients are still being computed.
+typedef struct { char internal[128]; } NcclUniqueId;
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(NcclUniqueId*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclUniqueId, int) = nullptr;
+  int (*CommInitAll)(void**, int, const int*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  int (*GetVersion)(int*) = nullptr;
+};
+static NcclApi& nccl() {
+  static NcclApi api;
+  if (api.handle) return api;
+  const char* names[] = {getenv("FRCNN_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n || !n[0]) continue;
+    api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  FRCNN_REQUIRE(api.handle != nullptr, FRCNN_E_NCCL, std::string("cannot load NCCL (libnccl.so.2; set FRCNN_NCCL_LIB): ") + (dlerror() ? dlerror() : ""));
+  auto sym = [&](const char* name) {
+    void* p = dlsym(api.handle, name);
+    FRCNN_REQUIRE(p != nullptr, FRCNN_E_NCCL, std::string("NCCL symbol missing: ") + name);
+    return p;
+  };
+  api.GetUniqueId = reinterpret_cast<int (*)(NcclUniqueId*)>(sym("ncclGetUniqueId"));
+  api.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclUniqueId, int)>(sym("ncclCommInitRank"));
+  api.CommInitAll = reinterpret_cast<int (*)(void**, int, const int*)>(sym("ncclCommInitAll"));
+  api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(sym("ncclAllReduce"));
+  api.GroupStart = reinterpret_cast<int (*)()>(sym("ncclGroupStart"));
+  api.GroupEnd = reinterpret_cast<int (*)()>(sym("ncclGroupEnd"));
+  api.CommDestroy = reinterpret_cast<int (*)(void*)>(sym("ncclCommDestroy"));
+  api.GetErrorString = reinterpret_cast<const char* (*)(int)>(sym("ncclGetErrorString"));
+  api.GetVersion = reinterpret_cast<int (*)(int*)>(sym("ncclGetVersion"));
+  return api;
+}
+#define FRCNN_NCCL_TRY(expr)                                                                                            \
+  do {                                                                                                                  \
+    int _r = (expr);                                                                                                    \
+    if (_r != 0) throw ::frcnn::Error{FRCNN_E_NCCL, std::string(#expr) + ": " + nccl().GetErrorString(_r)};             \
+  } while (0)
+static constexpr int NCCL_FLOAT = 7, NCCL_SUM = 0;
+
+// Buckets in completion order: 0 = cnet, 1 = anchor networks, 2.. = conv blocks, last block first.  [lo, hi] param indices.
+static int dp_bucket_count(const frcnn_ctx* c) { return 2 + (int)c->blocks.size(); }
+static void dp_bucket_range(const frcnn_ctx* c, int bucket, int* lo, int* hi) {
+  if (bucket == 0) {
+    *lo = c->fcs.front().p_w;
+    *hi = c->p_cls_b;
+  } else if (bucket == 1) {
+    *lo = c->heads.front().conv.p_w;
+    *hi = c->heads.back().p_b2;
+  } else {
+    const int b = (int)c->blocks.size() - 1 - (bucket - 2);
+    size_t first = 0;
+    for (int i = 0; i < b; ++i) first += c->blocks[i].conv_steps;
+    *lo = c->trunk[first].p_w;
+    *hi = c->trunk[first + c->blocks[b].conv_steps - 1].p_prelu;
+  }
+}
+static void dp_setup_streams(frcnn_ctx* c) {
+  if (c->dp_stream) return;
+  FRCNN_CUDA_TRY(cudaStreamCreateWithFlags(&c->dp_stream, cudaStreamNonBlocking));
+  FRCNN_CUDA_TRY(cudaEventCreateWithFlags(&c->dp_ready, cudaEventDisableTiming));
+  FRCNN_CUDA_TRY(cudaEventCreateWithFlags(&c->dp_done, cudaEventDisableTiming));
+  c->dp_bucket_sent.assign(dp_bucket_count(c), 0);
+}
+// Enqueues the all-reduce of one bucket on the side stream, ordered after everything enqueued so far on the context's
+// stream.  Gradient views that are adjacent in memory (nn.Module.flatten lays them out back to back) go out as one call.
+static void dp_send_bucket(frcnn_ctx* c, int bucket) {
+  int lo, hi;
+  dp_bucket_range(c, bucket, &lo, &hi);
+  FRCNN_CUDA_TRY(cudaEventRecord(c->dp_ready, c->stream));
+  FRCNN_CUDA_TRY(cudaStreamWaitEvent(c->dp_stream, c->dp_ready, 0));
+  int i = lo;
+  while (i <= hi) {
+    float* base = c->grads[i];
+    int64_t n = c->params[i].numel;
+    int j = i + 1;
+    while (j <= hi && c->grads[j] == base + n) {
+      n += c->params[j].numel;
+      ++j;
+    }
+    FRCNN_NCCL_TRY(nccl().AllReduce(base, base, (size_t)n, NCCL_FLOAT, NCCL_SUM, c->dp_comm, c->dp_stream));
+    c->dp_bytes += n * 4;
+    i = j;
+  }
+  c->dp_bucket_sent[bucket] = 1;
+}
+static void dp_bucket_ready(frcnn_ctx* c, int bucket) {
+  if (!c->dp_comm || !c->dp_overlap || c->dp_nranks <= 1) return;
+  if (bucket >= (int)c->dp_bucket_sent.size() || c->dp_bucket_sent[bucket]) return;
+  dp_send_bucket(c, bucket);
+}
+
 }  // namespace frcnn
 
 // =============================================================================================== C ABI
@@ -1690,6 +1848,16 @@ int frcnn_destroy(frcnn_ctx* c) {
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->conv_ev) cudaEventDestroy(e);
+  if (c->dp_comm) {
+    cudaStreamSynchronize(c->dp_stream);
+    try {
+      frcnn::nccl().CommDestroy(c->dp_comm);
+    } catch (...) {
+    }
+  }
+  if (c->dp_ready) cudaEventDestroy(c->dp_ready);
+  if (c->dp_done) cudaEventDestroy(c->dp_done);
+  if (c->dp_stream) cudaStreamDestroy(c->dp_stream);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   delete c;
   return FRCNN_OK;
@@ -1957,6 +2125,49 @@ int frcnn_cnet_train_step(frcnn_ctx* c, const float* x_dev, int R, int n_pos, co
   FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   losses_host[0] = lh[2];
   losses_host[1] = lh[3];
+  API_END(c)
+}
+
+int frcnn_cnet_forward_train(frcnn_ctx* c, const float* x_dev, int R, const float* const* masks_dev, uint64_t seed, float* reg_dev,
+                             float* cls_dev) {
+  API_BEGIN(c)
+  FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called first");
+  FRCNN_REQUIRE(x_dev && reg_dev && cls_dev && R >= 1, FRCNN_E_INVALID, "bad argument");
+  frcnn::ensure_objective_workspace(c, R);
+  const int bins = c->roi_kh * c->roi_kw;
+  const long total = (long)R * bins * c->feat_c;
+  const int blocks = (int)std::min<long>((total + 255) / 256, 148 * 16);
+  frcnn::pack_roi_rows_kernel<<<blocks, 256, 0, c->stream>>>(x_dev, c->t_rows, R, c->feat_c, bins, 0);
+  ++c->launches;
+  const int off = 0;
+  frcnn::cnet_train_forward(c, 1, &off, &R, masks_dev, &seed);
+  // the two output branches in fp32 on the stored hidden activations (model_utilities.lua:96-105)
+  const frcnn::FcLayer& last = c->fcs.back();
+  frcnn::launch_cnet_out(last.t_out32, frcnn::P(c, c->p_reg_w), frcnn::P(c, c->p_reg_b), frcnn::P(c, c->p_cls_w), frcnn::P(c, c->p_cls_b), reg_dev,
+                         cls_dev, R, nullptr, last.nout, c->class_count + 1, c->stream);
+  ++c->launches;
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  c->cnet_train_rows = R;
+  API_END(c)
+}
+
+int frcnn_cnet_backward(frcnn_ctx* c, const float* d_reg_dev, const float* d_cls_dev, float* dx_dev) {
+  API_BEGIN(c)
+  for (auto g : c->grads) FRCNN_REQUIRE(g != nullptr, FRCNN_E_STATE, "frcnn_bind_grads must be called first");
+  FRCNN_REQUIRE(c->cnet_train_rows > 0, FRCNN_E_STATE, "cnet:backward needs a preceding frcnn_cnet_forward_train on this context");
+  FRCNN_REQUIRE(d_reg_dev && d_cls_dev, FRCNN_E_INVALID, "null gradient");
+  const int R = c->cnet_train_rows, off = 0, n_pos = R;
+  frcnn::cnet_train_loss_bwd(c, 1, &off, &R, &n_pos, d_reg_dev, d_cls_dev);
+  frcnn::cnet_train_backward(c, 1, &off, &R);
+  if (dx_dev) {
+    const int bins = c->roi_kh * c->roi_kw;
+    const long total = (long)R * bins * c->feat_c;
+    const int blocks = (int)std::min<long>((total + 255) / 256, 148 * 16);
+    unpack_roi_rows_kernel<<<blocks, 256, 0, c->stream>>>(c->t_dx, dx_dev, R, c->feat_c, bins);
+    ++c->launches;
+  }
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  c->cnet_train_rows = 0;
   API_END(c)
 }
 
@@ -2465,7 +2676,8 @@ int frcnn_conv_bf16(frcnn_ctx* c, const uint16_t* x_dev, const float* w_dev, con
   REQUIRE_DEVICE(c);
   FRCNN_REQUIRE(x_dev && w_dev && out_dev, FRCNN_E_INVALID, "null argument");
   FRCNN_REQUIRE(bn == 0 || bn == 64 || bn == 128 || bn == 192 || bn == 256, FRCNN_E_INVALID, "bn must be 0, 64, 128, 192 or 256");
-  FRCNN_REQUIRE(((mt >= 0 && mt <= 2) || mt == 11 || mt == 12) && !(pool && splits > 1), FRCNN_E_INVALID, "bad mt / pool");
+  FRCNN_REQUIRE(((mt >= 0 && mt <= 2) || (mt > 10 && mt < 50 && (mt % 10 == 1 || mt % 10 == 2))) && !(pool && splits > 1), FRCNN_E_INVALID,
+                "bad mt / pool");
   const int ho = h + 2 * pad - k + 1, wo = w + 2 * pad - k + 1;
   FRCNN_REQUIRE(ho > 0 && wo > 0, FRCNN_E_INVALID, "input smaller than the kernel");
   const size_t wbytes = ((size_t)cout * cin * k * k * sizeof(frcnn::bf16) + 255) & ~size_t(255);
@@ -2509,6 +2721,121 @@ int frcnn_conv_bf16(frcnn_ctx* c, const uint16_t* x_dev, const float* w_dev, con
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   API_END(c)
+}
+
+// ---- data-parallel training ---------------------------------------------------------------------------------------
+int frcnn_dp_unique_id(char id_out[128]) {
+  try {
+    FRCNN_REQUIRE(id_out != nullptr, FRCNN_E_INVALID, "null id buffer");
+    frcnn::NcclUniqueId id;
+    FRCNN_NCCL_TRY(frcnn::nccl().GetUniqueId(&id));
+    memcpy(id_out, id.internal, 128);
+    return FRCNN_OK;
+  } catch (const frcnn::Error& e) {
+    frcnn::set_global_error(e.msg);
+    return e.code;
+  }
+}
+
+int frcnn_dp_init_rank(frcnn_ctx* c, const char id[128], int rank, int nranks) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(c->planned, FRCNN_E_STATE, "frcnn_model_plan must be called first");
+  FRCNN_REQUIRE(id != nullptr && nranks >= 1 && rank >= 0 && rank < nranks, FRCNN_E_INVALID, "bad rank / id");
+  FRCNN_REQUIRE(c->dp_comm == nullptr, FRCNN_E_STATE, "the context already belongs to a communicator");
+  frcnn::NcclUniqueId uid;
+  memcpy(uid.internal, id, 128);
+  FRCNN_NCCL_TRY(frcnn::nccl().CommInitRank(&c->dp_comm, nranks, uid, rank));
+  c->dp_rank = rank;
+  c->dp_nranks = nranks;
+  frcnn::dp_setup_streams(c);
+  API_END(c)
+}
+
+int frcnn_dp_init_all(frcnn_ctx* const* ctxs, int n) {
+  if (!ctxs || n < 1 || n > 64) return FRCNN_E_INVALID;
+  frcnn_ctx* c = ctxs[0];
+  API_BEGIN(c)
+  int devs[64];
+  void* comms[64];
+  for (int i = 0; i < n; ++i) {
+    FRCNN_REQUIRE(ctxs[i] && ctxs[i]->device >= 0 && ctxs[i]->planned && !ctxs[i]->dp_comm, FRCNN_E_STATE,
+                  "every context needs a device, a model plan and no communicator yet");
+    devs[i] = ctxs[i]->device;
+  }
+  FRCNN_NCCL_TRY(frcnn::nccl().CommInitAll(comms, n, devs));
+  for (int i = 0; i < n; ++i) {
+    FRCNN_CUDA_TRY(cudaSetDevice(ctxs[i]->device));
+    ctxs[i]->dp_comm = comms[i];
+    ctxs[i]->dp_rank = i;
+    ctxs[i]->dp_nranks = n;
+    frcnn::dp_setup_streams(ctxs[i]);
+  }
+  FRCNN_CUDA_TRY(cudaSetDevice(c->device));
+  API_END(c)
+}
+
+int frcnn_dp_set_overlap(frcnn_ctx* c, int enable) {
+  if (!c) return FRCNN_E_INVALID;
+  c->dp_overlap = enable != 0;
+  return FRCNN_OK;
+}
+
+int frcnn_dp_allreduce(frcnn_ctx* const* ctxs, int n, float* const* counters_dev, int n_counters) {
+  if (!ctxs || n < 1 || n > 64 || !ctxs[0]) return FRCNN_E_INVALID;
+  frcnn_ctx* c = ctxs[0];
+  API_BEGIN(c)
+  for (int i = 0; i < n; ++i) {
+    FRCNN_REQUIRE(ctxs[i] && ctxs[i]->dp_comm, FRCNN_E_STATE, "frcnn_dp_init_rank / frcnn_dp_init_all must be called first");
+    for (auto g : ctxs[i]->grads) FRCNN_REQUIRE(g != nullptr, FRCNN_E_STATE, "frcnn_bind_grads must be called first");
+  }
+  FRCNN_REQUIRE(n_counters >= 0 && (n_counters == 0 || counters_dev != nullptr), FRCNN_E_INVALID, "bad counters");
+  // one NCCL group over every context this thread drives (a single thread must not issue ungrouped collectives to
+  // several devices): whatever pnet:backward has not sent yet, plus the counters
+  FRCNN_NCCL_TRY(frcnn::nccl().GroupStart());
+  try {
+    for (int i = 0; i < n; ++i) {
+      frcnn_ctx* x = ctxs[i];
+      FRCNN_CUDA_TRY(cudaSetDevice(x->device));
+      for (int b = 0; b < frcnn::dp_bucket_count(x); ++b)
+        if (!x->dp_bucket_sent[b]) frcnn::dp_send_bucket(x, b);
+      if (n_counters > 0) {
+        FRCNN_CUDA_TRY(cudaEventRecord(x->dp_ready, x->stream));
+        FRCNN_CUDA_TRY(cudaStreamWaitEvent(x->dp_stream, x->dp_ready, 0));
+        FRCNN_NCCL_TRY(frcnn::nccl().AllReduce(counters_dev[i], counters_dev[i], (size_t)n_counters, frcnn::NCCL_FLOAT, frcnn::NCCL_SUM,
+                                               x->dp_comm, x->dp_stream));
+      }
+    }
+  } catch (...) {
+    frcnn::nccl().GroupEnd();
+    throw;
+  }
+  FRCNN_NCCL_TRY(frcnn::nccl().GroupEnd());
+  for (int i = 0; i < n; ++i) {
+    frcnn_ctx* x = ctxs[i];
+    FRCNN_CUDA_TRY(cudaSetDevice(x->device));
+    // the context's stream continues (optimiser step, next forward) only after the sums have arrived
+    FRCNN_CUDA_TRY(cudaEventRecord(x->dp_done, x->dp_stream));
+    FRCNN_CUDA_TRY(cudaStreamWaitEvent(x->stream, x->dp_done, 0));
+    std::fill(x->dp_bucket_sent.begin(), x->dp_bucket_sent.end(), 0);
+  }
+  FRCNN_CUDA_TRY(cudaSetDevice(c->device));
+  API_END(c)
+}
+
+int frcnn_dp_info(const frcnn_ctx* c, int* rank, int* nranks, int* nccl_version, int64_t* bytes_reduced) {
+  if (!c) return FRCNN_E_INVALID;
+  if (rank) *rank = c->dp_rank;
+  if (nranks) *nranks = c->dp_comm ? c->dp_nranks : 0;
+  if (bytes_reduced) *bytes_reduced = c->dp_bytes;
+  if (nccl_version) {
+    *nccl_version = 0;
+    try {
+      frcnn::nccl().GetVersion(nccl_version);
+    } catch (...) {
+    }
+  }
+  return FRCNN_OK;
 }
 
 }  // extern "C"

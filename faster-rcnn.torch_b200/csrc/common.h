@@ -100,6 +100,7 @@ struct ConvParams {
   int halo;                 // 1: launched with conv_halo_kernel (with wgrad: conv_wgrad_halo_kernel, MT = taps per unit)
   int pair;                 // 1: launched with conv_pair_kernel on CTA pairs (cta_group::2): a unit covers TWO CTA tiles stacked
                             // along H (cluster rank r computes rows [r, r + 1) * BH * MT of it); tiles_h counts pair tiles
+  int occ;                  // CTAs resident per SM the launch is sized for (1, or 2: halved shared memory / TMEM per CTA)
   int first_tma;            // first-layer kernel: eligible for conv_first_tma_kernel (16 x 8 tiles, Win % 4 == 0)
   int halo_desc;            // descriptor base-offset mode for the row-shifted start address (0: field left 0)
   const float* w2;          // EPI_HEAD: [18][256] weights of the 1x1 convolution (Torch layout)

@@ -50,7 +50,7 @@ static constexpr int A_SUB_BYTES = BLOCK_M * BLOCK_K * 2;    // 16 KB per 128-ro
 static constexpr int STAGE_TILE_BYTES = 128 * 128;           // epilogue staging: 128 px x 64 ch bf16
 static constexpr int MAX_BIAS = 512;
 static constexpr int SMEM_LIMIT = 227 * 1024;
-static constexpr int SMEM_FIXED = STAGE_TILE_BYTES + MAX_BIAS * 4 + 256 + 1024;
+static constexpr int SMEM_FIXED = STAGE_TILE_BYTES + MAX_BIAS * 4 + 512 + 1024;   // staging tile | bias | <= 63 mbarriers + TMEM slot | alignment slack
 
 __host__ __device__ constexpr int stage_bytes(int BN, int MT) { return MT * A_SUB_BYTES + BN * BLOCK_K * 2; }
 __host__ __device__ constexpr int conv_stages(int BN, int MT) {
@@ -548,6 +548,34 @@ __host__ __device__ constexpr int halo_tmem_cols(int BN, int MT) {
 static int halo_smem_bytes(int BN, int MT, int KMAX) {
   return halo_a_slots(MT, KMAX) * halo_a_slot(MT, KMAX) + halo_b_slots(BN, MT, KMAX) * BN * 128 + SMEM_FIXED + halo_extra(KMAX);
 }
+// OCC = 2: TWO CTAs resident per SM (half the shared memory, half the TMEM columns, <= 85 registers per thread).  A CTA
+// spends a third to a half of its life outside its MMA phase -- prologue, the latency of its first loads, the epilogue of
+// its last unit -- and with one CTA per SM the tensor pipe idles meanwhile (ncu, batch 1: pipe active 50-63 % of a CTA's
+// cycles).  A second resident CTA (another unit of the same layer, or a layer of another frame in flight) fills those
+// phases; the rings are shallower, which the co-resident CTA covers as well.
+__host__ __device__ constexpr int occ_smem_limit(int OCC) { return OCC == 2 ? 115712 : SMEM_LIMIT; }   // (228 KB - 2 x 1 KB reserved) / 2
+__host__ __device__ constexpr int occ_fixed(int OCC) { return OCC == 2 ? SMEM_FIXED - 1024 : SMEM_FIXED; }  // OCC 2: no alignment slack
+__host__ __device__ constexpr int occ_a_slots(int MT, int KMAX, int OCC) { return OCC == 2 ? 2 : halo_a_slots(MT, KMAX); }
+__host__ __device__ constexpr int occ_b_slots(int b_slot_bytes, int MT, int KMAX, int OCC, int cap) {
+  const int n = (occ_smem_limit(OCC) - occ_fixed(OCC) - halo_extra(KMAX) - occ_a_slots(MT, KMAX, OCC) * halo_a_slot(MT, KMAX)) / b_slot_bytes;
+  return n > cap ? cap : n;
+}
+__host__ __device__ constexpr int occ_acc_stages(int BN, int MT, int OCC) { return 2 * BN * MT <= 512 / OCC ? 2 : 1; }
+__host__ __device__ constexpr int occ_tmem_cols(int BN, int MT, int OCC) {
+  const int c = occ_acc_stages(BN, MT, OCC) * BN * MT;
+  return c <= 64 ? 64 : (c <= 128 ? 128 : (c <= 256 ? 256 : 512));
+}
+static int occ_smem_bytes(int b_slot_bytes, int MT, int KMAX, int OCC, int cap) {
+  return occ_a_slots(MT, KMAX, OCC) * halo_a_slot(MT, KMAX) + occ_b_slots(b_slot_bytes, MT, KMAX, OCC, cap) * b_slot_bytes + occ_fixed(OCC) +
+         halo_extra(KMAX);
+}
+__device__ __forceinline__ uint8_t* occ_smem_base(uint8_t* raw, int OCC) {
+  if (OCC == 2) {  // no slack to round up into: the dynamic shared memory window itself must be 1024-byte aligned
+    if ((ptx::smem_u32(raw) & 1023u) != 0u) __trap();
+    return raw;
+  }
+  return reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+}
 
 // Fused AnchorNetwork epilogue (model_utilities.lua:29-35): the k x k conv's 256 fp32 sums per pixel never leave the
 // SM -- bias + PReLU and the 1x1 convolution to 18 channels run on the CUDA cores straight out of TMEM, in fp32 with
@@ -635,20 +663,21 @@ __device__ __forceinline__ void epilogue_head(const ConvGroup& grp, float* w2s, 
   }
 }
 
-template <int BN, int MT, int KMAX>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+template <int BN, int MT, int KMAX, int OCC = 1>
+__global__ void __launch_bounds__(CONV_THREADS, OCC)
     conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGroup grp) {
-  constexpr int A_SLOT = halo_a_slot(MT, KMAX), A_SLOTS = halo_a_slots(MT, KMAX);
-  constexpr int B_SLOT = BN * 128, B_SLOTS = halo_b_slots(BN, MT, KMAX);
-  constexpr int ACC = halo_acc_stages(BN, MT);
-  constexpr int TMEM_COLS = halo_tmem_cols(BN, MT);
+  constexpr int A_SLOT = halo_a_slot(MT, KMAX), A_SLOTS = occ_a_slots(MT, KMAX, OCC);
+  constexpr int B_SLOT = BN * 128, B_SLOTS = occ_b_slots(B_SLOT, MT, KMAX, OCC, 8);
+  constexpr int ACC = occ_acc_stages(BN, MT, OCC);
+  constexpr int TMEM_COLS = occ_tmem_cols(BN, MT, OCC);
+  static_assert(TMEM_COLS <= 512 / OCC, "accumulators of all resident CTAs must fit the 512 TMEM columns");
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BN);
   constexpr bool HEAD = KMAX > HALO_MAXK;  // the fused anchor-head configuration: EPI_HEAD units of up to 4 convs
   static_assert(B_SLOTS >= 2, "weight ring too small");
   static_assert(!HEAD || (BN == HEAD_CM && MT == 1), "anchor heads: 256 hidden channels, one sub-tile");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = occ_smem_base(smem_raw, OCC);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + A_SLOTS * A_SLOT;
   uint8_t* tile_buf = smem_b + B_SLOTS * B_SLOT;   // bf16 epilogues: 16 KB staging tile; EPI_HEAD: w2 | partial sums
@@ -837,27 +866,20 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 //   * tcgen05.commit multicasts to empty_a / empty_b / tmem_full of both CTAs (same shared-memory offsets);
 //   * the peer's epilogue warps release the accumulator stage with a remote arrive on the leader's tmem_empty;
 //   * TMEM is allocated with cta_group::2 by the same warp of both CTAs; cluster barriers bracket the kernel.
-__host__ __device__ constexpr int pair_b_slots(int BN, int MT, int KMAX) {
-  return (SMEM_LIMIT - SMEM_FIXED - halo_extra(KMAX) - halo_a_slots(MT, KMAX) * halo_a_slot(MT, KMAX)) / (BN * 64) > 12
-             ? 12
-             : (SMEM_LIMIT - SMEM_FIXED - halo_extra(KMAX) - halo_a_slots(MT, KMAX) * halo_a_slot(MT, KMAX)) / (BN * 64);
-}
-static int pair_smem_bytes(int BN, int MT, int KMAX) {
-  return halo_a_slots(MT, KMAX) * halo_a_slot(MT, KMAX) + pair_b_slots(BN, MT, KMAX) * BN * 64 + SMEM_FIXED + halo_extra(KMAX);
-}
-
-template <int BN, int MT, int KMAX>
-__global__ void __launch_bounds__(CONV_THREADS, 1)
+template <int BN, int MT, int KMAX, int OCC = 1>
+__global__ void __launch_bounds__(CONV_THREADS, OCC)
     conv_pair_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGroup grp) {
-  constexpr int A_SLOT = halo_a_slot(MT, KMAX), A_SLOTS = halo_a_slots(MT, KMAX);
-  constexpr int B_SLOT = BN * 64, B_SLOTS = pair_b_slots(BN, MT, KMAX);   // half a weight box: BN / 2 rows of 128 bytes
-  constexpr int ACC = halo_acc_stages(BN, MT);
-  constexpr int TMEM_COLS = halo_tmem_cols(BN, MT);
+  constexpr int A_SLOT = halo_a_slot(MT, KMAX), A_SLOTS = occ_a_slots(MT, KMAX, OCC);
+  constexpr int B_SLOT = BN * 64, B_SLOTS = occ_b_slots(B_SLOT, MT, KMAX, OCC, 12);   // half a weight box: BN / 2 rows of 128 bytes
+  constexpr int ACC = occ_acc_stages(BN, MT, OCC);
+  constexpr int TMEM_COLS = occ_tmem_cols(BN, MT, OCC);
+  static_assert(TMEM_COLS <= 512 / OCC, "accumulators of all resident CTAs must fit the 512 TMEM columns");
   constexpr uint32_t IDESC = ptx::make_idesc_bf16(2 * BLOCK_M, BN);       // M = 256 over the pair
   static_assert(B_SLOTS >= 2 && BN % 16 == 0, "weight ring too small / N must be a multiple of 16 for cta_group::2");
+  static_assert((2 * A_SLOTS + 2 * B_SLOTS + 4) * 8 + 4 <= 512, "mbarrier area of SMEM_FIXED");
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = occ_smem_base(smem_raw, OCC);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + A_SLOTS * A_SLOT;
   uint8_t* tile_buf = smem_b + B_SLOTS * B_SLOT;
@@ -1779,7 +1801,9 @@ static bool halo_cfg_ok(int Cout, int BN, int MT) {
 }
 
 static void conv_prepare_halo(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
-                              int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int BN, int MT, int w_copies) {
+                              int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int BN, int MT, int w_copies,
+                              int occ = 1) {
+  FRCNN_REQUIRE(occ == 1 || (occ == 2 && BN * MT <= 256), FRCNN_E_INVALID, "conv: two CTAs per SM need BN x MT <= 256 TMEM columns");
   L->w_copies = w_copies;
   FRCNN_REQUIRE(halo_cfg_ok(Cout, BN, MT), FRCNN_E_INVALID, "conv (halo kernel): unsupported (BN, MT) for this Cout");
   L->BN = BN;
@@ -1810,16 +1834,18 @@ static void conv_prepare_halo(ConvLaunch* L, const bf16* in, const bf16* w_packe
   make_tmap_act(&L->tmA, in, N, Hin, Win, Cin, HALO_BW + KW - 1, HALO_BH * MT + KH - 1);
   make_tmap_weight(&L->tmB, w_packed, Cout, KH * KW * Cin, BN, w_copies);
   make_out_map(L, out);
+  p.occ = occ;
   const int total = p.n_tiles_m * p.n_tiles_n;
-  L->grid = total < num_sms ? total : num_sms;
+  L->grid = total < occ * num_sms ? total : occ * num_sms;
 }
 
 // conv_pair_kernel (cta_group::2): same tiling as the halo kernel, a unit = two CTA tiles stacked along H, the weight
 // box is half an N tile (each CTA of the pair loads BN / 2 rows)
 static void conv_prepare_pair(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
-                              int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int BN, int MT, int w_copies) {
+                              int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int BN, int MT, int w_copies,
+                              int occ = 1) {
   FRCNN_REQUIRE(halo_cfg_ok(Cout, BN, MT) && BN % 16 == 0, FRCNN_E_INVALID, "conv (pair kernel): unsupported (BN, MT) for this Cout");
-  conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, BN, MT, w_copies);
+  conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, BN, MT, w_copies, occ);
   ConvParams& p = L->p;
   p.pair = 1;
   p.tiles_h = (p.Hout + 2 * p.BH * MT - 1) / (2 * p.BH * MT);
@@ -1827,7 +1853,7 @@ static void conv_prepare_pair(ConvLaunch* L, const bf16* in, const bf16* w_packe
   make_tmap_weight(&L->tmB, w_packed, Cout, KH * KW * Cin, BN / 2, w_copies);
   L->tmOut = L->tmB;
   const int total = p.n_tiles_m * p.n_tiles_n;
-  const int pairs = std::max(1, num_sms / 2);
+  const int pairs = std::max(1, occ * num_sms / 2);
   L->grid = 2 * (total < pairs ? total : pairs);
 }
 
@@ -1884,21 +1910,37 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
     FRCNN_REQUIRE(!forced || eligible, FRCNN_E_INVALID, "conv: the halo kernel needs 2x2..3x3 filters and a bf16 epilogue");
     // CTA-pair kernel (cta_group::2): force_mt 21 / 22, or automatically (FRCNN_CONV_PAIR, see the selection rule below)
     const bool pair_ok = eligible && !f32 && Cout % 64 == 0;
-    if (pair_ok && (force_mt == 21 || force_mt == 22)) {
-      const int mt = force_mt - 20;
+    if (pair_ok && force_mt > 20) {
+      // 21 / 22: CTA pairs; 31 / 32: halo kernel with two CTAs per SM; 41 / 42: CTA pairs with two CTAs per SM
+      const int mt = force_mt % 10, kind = force_mt / 10;
+      FRCNN_REQUIRE((mt == 1 || mt == 2) && kind >= 2 && kind <= 4, FRCNN_E_INVALID, "conv: bad kernel selector");
       int bn = force_bn > 0 ? force_bn : (Cout % 256 == 0 ? 256 : (Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : 64)));
+      if (kind >= 3 && bn * mt > 256 && force_bn == 0) bn = Cout % 128 == 0 ? 128 : 64;
       FRCNN_REQUIRE(halo_cfg_ok(Cout, bn, mt), FRCNN_E_INVALID, "conv: no pair-kernel tile for this (Cout, bn, mt)");
-      conv_prepare_pair(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, bn, mt, w_copies);
+      if (kind == 3) conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, bn, mt, w_copies, 2);
+      else conv_prepare_pair(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, bn, mt, w_copies, kind == 4 ? 2 : 1);
       return;
     }
     FRCNN_REQUIRE(force_mt < 20, FRCNN_E_INVALID, "conv: the pair kernel needs 2x2..3x3 filters and a bf16 epilogue");
-    if (pair_ok && force_mt == 0 && force_bn == 0 && env_int("FRCNN_CONV_PAIR", 0)) {
-      const int bn = Cout % 256 == 0 ? 256 : (Cout % 192 == 0 ? 192 : (Cout % 128 == 0 ? 128 : 64));
-      const int mt = env_int("FRCNN_CONV_PAIR_MT", bn <= 128 ? 2 : 1);
-      if (halo_cfg_ok(Cout, bn, mt)) {
-        conv_prepare_pair(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, bn, mt, w_copies);
-        return;
+    // Automatic choice (FRCNN_CONV_DUO=0 restores the one-CTA-per-SM rule below).  Measured on B200
+    // (tools/bench_conv_layers.py, profiles/r2_conv_sweep.md): every trunk layer is at least as fast with TWO resident
+    // CTAs per SM (the tensor pipe of a lone CTA idles through its prologue, first-load latency and last epilogue), and
+    // kernels sized that way can share an SM with the kernels of the other frames in flight:
+    //   * wide layers with enough work for two waves of CTA pairs: conv_pair_kernel, BN = 256 / 192, M = 256 MMAs;
+    //   * otherwise conv_halo_kernel with BN = 128 (Cout = 128 layers; the wide layers at batch 1), or BN = 64.
+    if (pair_ok && force_mt == 0 && force_bn == 0 && env_int("FRCNN_CONV_DUO", 1)) {
+      const int Ho = Hin + 2 * padH - KH + 1, Wo = Win + 2 * padW - KW + 1;
+      const int wide = Cout % 256 == 0 ? 256 : (Cout % 192 == 0 ? 192 : 0);
+      if (wide) {
+        const long pair_ctas = 2L * N * ((Ho + 2 * HALO_BH - 1) / (2 * HALO_BH)) * ((Wo + HALO_BW - 1) / HALO_BW) * (Cout / wide);
+        if (pair_ctas >= 4L * num_sms || Cout % 128 != 0) {
+          conv_prepare_pair(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, wide, 1, w_copies, 2);
+          return;
+        }
       }
+      conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, Cout % 128 == 0 ? 128 : 64, 1,
+                        w_copies, 2);
+      return;
     }
     if (eligible && (forced || (force_mt == 0 && env_int("FRCNN_CONV_HALO", 1)))) {
       // Measured on B200 (tools/bench_conv_layers.py sweep, profiles/r1_conv_sweep.md): the halo kernel wins where the
@@ -2119,23 +2161,27 @@ static void launch_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cud
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
-template <int BN, int MT, int KMAX>
+template <int BN, int MT, int KMAX, int OCC = 1>
 static void launch_halo_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
   static DeviceOnce configured;
-  const int smem = halo_smem_bytes(BN, MT, KMAX);
+  const int smem = OCC == 2 ? occ_smem_bytes(BN * 128, MT, KMAX, OCC, 8) : halo_smem_bytes(BN, MT, KMAX);
   if (first_use_on_device(configured)) {
-    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, KMAX, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (OCC == 2)
+      FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<BN, MT, KMAX, OCC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
-  conv_halo_kernel<BN, MT, KMAX><<<grid, CONV_THREADS, smem, st>>>(maps, grp);
+  conv_halo_kernel<BN, MT, KMAX, OCC><<<grid, CONV_THREADS, smem, st>>>(maps, grp);
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
-template <int BN, int MT, int KMAX>
+template <int BN, int MT, int KMAX, int OCC = 1>
 static void launch_pair_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
   static DeviceOnce configured;
-  const int smem = pair_smem_bytes(BN, MT, KMAX);
+  const int smem = occ_smem_bytes(BN * 64, MT, KMAX, OCC, 12);
   if (first_use_on_device(configured)) {
-    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<BN, MT, KMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<BN, MT, KMAX, OCC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    if (OCC == 2)
+      FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_pair_kernel<BN, MT, KMAX, OCC>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid, 1, 1);
@@ -2149,9 +2195,20 @@ static void launch_pair_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  FRCNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_pair_kernel<BN, MT, KMAX>, maps, grp));
+  FRCNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_pair_kernel<BN, MT, KMAX, OCC>, maps, grp));
 }
-static void launch_pair_key(int BN, int MT, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+static void launch_pair_key(int BN, int MT, int occ, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+  if (occ == 2) {
+    switch (BN * 10 + MT) {
+      case 641: launch_pair_cfg<64, 1, HALO_MAXK, 2>(maps, grp, grid, st); break;
+      case 642: launch_pair_cfg<64, 2, HALO_MAXK, 2>(maps, grp, grid, st); break;
+      case 1281: launch_pair_cfg<128, 1, HALO_MAXK, 2>(maps, grp, grid, st); break;
+      case 1921: launch_pair_cfg<192, 1, HALO_MAXK, 2>(maps, grp, grid, st); break;
+      case 2561: launch_pair_cfg<256, 1, HALO_MAXK, 2>(maps, grp, grid, st); break;
+      default: throw Error{FRCNN_E_INVALID, "conv (pair kernel, 2 CTAs / SM): unsupported (BN, MT)"};
+    }
+    return;
+  }
   switch (BN * 10 + MT) {
     case 641: launch_pair_cfg<64, 1, HALO_MAXK>(maps, grp, grid, st); break;
     case 642: launch_pair_cfg<64, 2, HALO_MAXK>(maps, grp, grid, st); break;
@@ -2165,7 +2222,16 @@ static void launch_pair_key(int BN, int MT, const ConvMaps& maps, const ConvGrou
   }
 }
 
-static void launch_halo_key(int BN, int MT, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+static void launch_halo_key(int BN, int MT, int occ, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+  if (occ == 2) {
+    switch (BN * 10 + MT) {
+      case 641: launch_halo_cfg<64, 1, HALO_MAXK, 2>(maps, grp, grid, st); break;
+      case 1281: launch_halo_cfg<128, 1, HALO_MAXK, 2>(maps, grp, grid, st); break;
+      case 1921: launch_halo_cfg<192, 1, HALO_MAXK, 2>(maps, grp, grid, st); break;
+      default: throw Error{FRCNN_E_INVALID, "conv (halo kernel, 2 CTAs / SM): unsupported (BN, MT)"};
+    }
+    return;
+  }
   switch (BN * 10 + MT) {
     case 641: launch_halo_cfg<64, 1, HALO_MAXK>(maps, grp, grid, st); break;
     case 642: launch_halo_cfg<64, 2, HALO_MAXK>(maps, grp, grid, st); break;
@@ -2258,8 +2324,8 @@ void conv_launch(const ConvLaunch& L, cudaStream_t st) {
     maps.o[g] = L.tmOut;
   }
   if (L.p.wgrad && L.p.halo) launch_wgrad_halo_key(L.BN, maps, grp, L.grid, st);
-  else if (L.p.pair) launch_pair_key(L.BN, L.p.MT, maps, grp, L.grid, st);
-  else if (L.p.halo) launch_halo_key(L.BN, L.p.MT, maps, grp, L.grid, st);
+  else if (L.p.pair) launch_pair_key(L.BN, L.p.MT, L.p.occ, maps, grp, L.grid, st);
+  else if (L.p.halo) launch_halo_key(L.BN, L.p.MT, L.p.occ, maps, grp, L.grid, st);
   else launch_key(L.BN, L.p.MT, maps, grp, L.grid, st);
 }
 

@@ -293,7 +293,19 @@ __global__ void __launch_bounds__(256) cnet_loss_row_kernel(CnetLossParams p) {
     if (lane == 0) z[o] = s + (o < 4 ? p.b_reg[o] : p.b_cls[o - 4]);
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && p.ext_dreg && p.ext_dcls) {
+    // cnet:backward with the caller's output gradients: Linear(nin -> 4) takes d_reg as is; the class branch ends in
+    // nn.LogSoftMax, y = z - lse(z): dz_c = dy_c - softmax(z)_c * sum_j dy_j
+    for (int i = 0; i < 4; ++i) z[i] = p.ext_dreg[r * 4 + i];
+    float m = -INFINITY;
+    for (int c = 0; c < p.ncls; ++c) m = fmaxf(m, z[4 + c]);
+    float s = 0.f;
+    for (int c = 0; c < p.ncls; ++c) s += expf(z[4 + c] - m);
+    const float lse = m + logf(s);
+    float dsum = 0.f;
+    for (int c = 0; c < p.ncls; ++c) dsum += p.ext_dcls[(long)r * p.ncls + c];
+    for (int c = 0; c < p.ncls; ++c) z[4 + c] = p.ext_dcls[(long)r * p.ncls + c] - expf(z[4 + c] - lse) * dsum;
+  } else if (threadIdx.x == 0) {
     const bool pos = r < p.n_pos;
     float l_reg = 0.f;
     for (int i = 0; i < 4; ++i) {

@@ -95,6 +95,8 @@ struct CnetLossParams {      // objective.lua:166-177 on the two cnet outputs + 
   float* dz;                 // [R][ncls + 4] scratch: gradient wrt the branch outputs (4 reg, then ncls logits)
   float *g_w_reg, *g_b_reg, *g_w_cls, *g_b_cls;
   float* losses;             // [2] += 10 * SmoothL1 sum, [3] += mean NLL
+  const float* ext_dreg;     // optional [R][4]: gradient wrt the bbox output supplied by the caller (cnet:backward, objective.lua:179)
+  const float* ext_dcls;     // optional [R][ncls]: gradient wrt the LOG-SOFTMAX output; with both set no criterion is evaluated
 };
 void launch_cnet_loss_bwd(const CnetLossParams& p, cudaStream_t st);
 

@@ -80,8 +80,7 @@ class Model:
             self.param_names.append(ffi.string(name).decode())
             self.param_numel.append(int(numel[0]))
         self.pnet = _Net(self._pnet_forward, self._pnet_backward)
-        self.cnet = _Net(self._cnet_forward)
-        self.cnet._bwd = None
+        self.cnet = _Net(self._cnet_forward, self._cnet_backward)
         self.n_heads = len(anchor_nets)
         if self.host_only:
             return
@@ -343,15 +342,37 @@ class Model:
         check(self.ctx, lib().frcnn_train_batch(self.ctx, ffi.cast("const float*", x.data_ptr()), n, h, w, pp, n_pos, qq, n_neg, pm, sd, losses))
         return [dict(cls=losses[4 * i], reg=losses[4 * i + 1], creg=losses[4 * i + 2], ccls=losses[4 * i + 3]) for i in range(n)]
 
-    def _cnet_forward(self, x):
-        """cnet:forward(cinput) (Detector.lua:101): x [R][kh*kw*C] fp32 -> (bbox [R][4], log-softmax [R][classes+1])."""
+    def _cnet_forward(self, x, dropout_masks=None, seed=0):
+        """cnet:forward(cinput) (Detector.lua:101, objective.lua:164): x [R][kh*kw*C] fp32 -> (bbox [R][4], log-softmax
+        [R][classes+1]).  After cnet.training(): BatchNormalization batch statistics (running statistics updated), Dropout
+        masks drawn from `seed` or injected (`dropout_masks`: one [R][n] 0/1 tensor per class layer); the state
+        cnet.backward needs stays in the context."""
         x = x.to(self.device, torch.float32).contiguous()
         R = x.shape[0]
         reg = torch.empty((R, 4), dtype=torch.float32, device=self.device)
         cls = torch.empty((R, self.cfg["class_count"] + 1), dtype=torch.float32, device=self.device)
+        if self.cnet.train:
+            keep = [m.to(self.device, torch.float32).contiguous() for m in dropout_masks] if dropout_masks is not None else []
+            mp = ffi.new("const float*[]", [ffi.cast("const float*", m.data_ptr()) for m in keep]) if keep else ffi.NULL
+            check(self.ctx, lib().frcnn_cnet_forward_train(self.ctx, ffi.cast("const float*", x.data_ptr()), R, mp, seed,
+                                                           ffi.cast("float*", reg.data_ptr()), ffi.cast("float*", cls.data_ptr())))
+            torch.cuda.synchronize(self.device)  # `keep` / `x` may be released afterwards
+            return reg, cls
         check(self.ctx, lib().frcnn_cnet_forward(self.ctx, ffi.cast("const float*", x.data_ptr()), R,
                                                  ffi.cast("float*", reg.data_ptr()), ffi.cast("float*", cls.data_ptr())))
         return reg, cls
+
+    def _cnet_backward(self, cinput, deltas):
+        """cnet:backward(cinput, {crdelta, ccdelta}) (objective.lua:179) after a training-mode cnet.forward(cinput): returns
+        post_roi_delta [R][kh*kw*C]; parameter gradients accumulate in `self.gradient`."""
+        crdelta, ccdelta = deltas
+        dr = crdelta.to(self.device, torch.float32).contiguous()
+        dc = ccdelta.to(self.device, torch.float32).contiguous()
+        dx = torch.empty((dr.shape[0], cinput.shape[1]), dtype=torch.float32, device=self.device)
+        check(self.ctx, lib().frcnn_cnet_backward(self.ctx, ffi.cast("const float*", dr.data_ptr()),
+                                                  ffi.cast("const float*", dc.data_ptr()), ffi.cast("float*", dx.data_ptr())))
+        torch.cuda.synchronize(self.device)
+        return dx
 
     def cnet_train_step(self, x, n_pos, crtarget, cctarget, masks=None, seed=0):
         """cnet:forward (training) + detection-stage criteria + cnet:backward (objective.lua:164-179) on example rows

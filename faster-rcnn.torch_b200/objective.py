@@ -26,12 +26,50 @@ def allreduce_gradient(gradient, counters, dist=None):
     return gradient, buf[gradient.numel():].clone()
 
 
+def dp_init(model, dist):
+    """Forms the C library's NCCL communicator (frcnn_dp_init_rank) over the ranks of an initialised torch.distributed
+    group -- which is only used to ship rank 0's 128-byte NCCL id.  Returns the (device) counter buffer the all-reduce
+    carries next to the gradient."""
+    from ._lib import check, ffi, lib
+    L = lib()
+    idbuf = ffi.new("char[128]")
+    payload = [None]
+    if dist.get_rank() == 0:
+        check(None, L.frcnn_dp_unique_id(idbuf))
+        payload = [bytes(ffi.buffer(idbuf, 128))]
+    dist.broadcast_object_list(payload, src=0, device=model.device)
+    ffi.memmove(idbuf, payload[0], 128)
+    check(model.ctx, L.frcnn_dp_init_rank(model.ctx, idbuf, dist.get_rank(), dist.get_world_size()))
+    model._dp_counters = torch.zeros(8, dtype=torch.float32, device=model.device)
+    return model._dp_counters
+
+
+def dp_allreduce(model, counters):
+    """frcnn_dp_allreduce on this rank's context: the gradient buckets pnet:backward has not sent yet + the counters, in
+    place, on the library's side stream; returns the summed counters (host list)."""
+    from ._lib import check, ffi, lib
+    buf = model._dp_counters
+    buf[:len(counters)].copy_(torch.tensor(counters, dtype=torch.float32))
+    ctxs = ffi.new("frcnn_ctx*[]", [model.ctx])
+    ptrs = ffi.new("float*[]", [ffi.cast("float*", buf.data_ptr())])
+    check(model.ctx, lib().frcnn_dp_allreduce(ctxs, 1, ptrs, len(counters)))
+    return buf[:len(counters)].tolist()
+
+
 def create_objective(model, dist=None, defer_div=False, batched=True):
     """Returns lossAndGradient(batch, seed) -> (loss, gradient, stats); batch = list of dicts {img [3][H][W] tensor,
     positive [(anchor, roi)], negative [(anchor,)]} as BatchIterator:nextTraining yields them (this rank's share).
     batched: frames of equal size are processed by one frcnn_train_batch call (False: frame by frame, frcnn_train_image).
     defer_div: leave gradient:div(cls_count) (objective.lua:200) to the fused optimiser pass (optim.rmsprop_step's
     grad_div = stats['deferred_div'])."""
+
+    # With NCCL available the collective runs inside the C library (frcnn_dp_*: in place, bucketed, overlapped with
+    # pnet:backward); the torch.distributed path below remains for host-only groups (gloo tests).
+    use_lib_dp = (dist is not None and dist.is_initialized() and dist.get_world_size() > 1 and not model.host_only
+                  and dist.get_backend() == "nccl")
+    if use_lib_dp and getattr(model, "_dp_counters", None) is None:
+        dp_init(model, dist)
+    from ._lib import lib as _lib
 
     def lossAndGradient(batch, seed=0):
         model.zero_grad()                                   # gradient:zero()
@@ -44,6 +82,10 @@ def create_objective(model, dist=None, defer_div=False, batched=True):
         groups = {}
         for i, x in enumerate(batch):
             groups.setdefault(tuple(x["img"].shape), []).append(i)
+        if use_lib_dp:
+            # one size group = one frcnn_train_batch call = the step's only accumulation into the gradient: its buckets may
+            # leave as soon as the backward pass has finished them
+            _lib().frcnn_dp_set_overlap(model.ctx, 1 if (len(groups) == 1 and batched) else 0)
         for shape, idx in groups.items():
             dims = model.output_dims(shape[1], shape[2])
             ps = [clean_anchors(batch[i]["positive"], dims) for i in idx]
@@ -62,9 +104,12 @@ def create_objective(model, dist=None, defer_div=False, batched=True):
                 reg_count += len(p)
                 cls_count += len(p) + len(n)
                 ccls_count += 1
-        gradient, c = allreduce_gradient(model.gradient, [sums["cls"], sums["reg"], sums["creg"], sums["ccls"], cls_count,
-                                                           reg_count, ccls_count], dist)
-        c = c.tolist()
+        counters = [sums["cls"], sums["reg"], sums["creg"], sums["ccls"], cls_count, reg_count, ccls_count]
+        if use_lib_dp:
+            gradient, c = model.gradient, dp_allreduce(model, counters)
+        else:
+            gradient, c = allreduce_gradient(model.gradient, counters, dist)
+            c = c.tolist()
         if not defer_div:
             gradient.div_(max(c[4], 1.0))                    # gradient:div(cls_count)
         stats = dict(pcls=c[0] / max(c[4], 1.0), preg=c[1] / max(c[5], 1.0), dcls=c[3] / max(c[6], 1.0), dreg=c[2] / max(c[5], 1.0),

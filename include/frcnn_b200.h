@@ -179,6 +179,16 @@ int frcnn_cnet_train_step(frcnn_ctx* ctx, const float* x_dev, int R, int n_pos, 
                           const int32_t* cctarget_dev, const float* const* masks_dev, uint64_t seed, float* dx_dev,
                           float losses_host[2]);
 
+/* cnet:forward(cinput) in TRAINING mode (objective.lua:164: BatchNormalization batch statistics + running-statistics update,
+ * Dropout v2 masks drawn from `seed` or injected through masks_dev[layer] [R][n]) and, separately, cnet:backward(cinput,
+ * {crdelta, ccdelta}) (objective.lua:179) with the caller's gradients wrt the two outputs -- d_reg_dev [R][4] and d_cls_dev
+ * [R][class_count+1] (wrt the log-softmax output) -- for hosts that keep their own criteria (the unmodified objective.lua).
+ * The backward pass uses the state the forward call left in the context; dx_dev (optional) receives post_roi_delta
+ * [R][kh*kw*C]; parameter gradients are accumulated. */
+int frcnn_cnet_forward_train(frcnn_ctx* ctx, const float* x_dev, int R, const float* const* masks_dev, uint64_t seed,
+                             float* reg_dev, float* cls_dev);
+int frcnn_cnet_backward(frcnn_ctx* ctx, const float* d_reg_dev, const float* d_cls_dev, float* dx_dev);
+
 /* ---- RPN decode: replaces the per-anchor Lua loop Detector.lua:36-66 ------------------------------------- */
 /* heads_dev[i]: [18][hi][wi] fp32 of ONE image.  Writes the ordered match list (layer, y, x, aspect order) to
  * cand_host and its length to n_cand.  threshold = 0.95 in the reference (Detector.lua:54). */
@@ -311,12 +321,39 @@ int frcnn_sample_negative(frcnn_ctx* ctx, const double image_rect[4], const doub
 int frcnn_rmsprop_step(frcnn_ctx* ctx, float* weights_dev, float* gradient_dev, float* state_m_dev, int64_t n,
                        double grad_div, double lr, double alpha, double epsilon, double weight_decay);
 
+/* ---- data-parallel training: the gradient all-reduce of SURVEY 8e (objective.lua:189,200 sum the per-image gradients
+ *      into the flat `gradient` and divide once by the example count; with the frames of a batch sharded over GPUs the sum
+ *      runs over the ranks) ---------------------------------------------------------------------------------------------
+ * NCCL is loaded at run time (libnccl.so.2, or the path in FRCNN_NCCL_LIB); failures return FRCNN_E_NCCL.  One
+ * communicator rank per context.  Two ways to form the communicator:
+ *   one process per GPU (torchrun, MPI): rank 0 calls frcnn_dp_unique_id and distributes the 128 bytes by any means; every
+ *     rank calls frcnn_dp_init_rank on its context;
+ *   one process, several GPUs (a LuaJIT host is single-threaded, main.lua:52): frcnn_dp_init_all over one context per
+ *     device (ncclCommInitAll).
+ * frcnn_dp_allreduce sums IN PLACE, across the ranks, every gradient view bound with frcnn_bind_grads (adjacent views --
+ * nn.Module.flatten's layout -- go out as single calls) and `n_counters` floats of counters_dev[i] (the example / loss
+ * counters of objective.lua:196-200; NULL / 0 = none), for the `n` contexts this thread drives (n = 1 with one process per
+ * GPU), inside one NCCL group.  The work runs on a side stream ordered after the context's stream; the context's stream
+ * waits for the result, so the optimiser step may simply be enqueued next.  The caller then divides by the summed counter.
+ * With frcnn_dp_set_overlap(ctx, 1) (one process per GPU only) frcnn_train_batch / frcnn_pnet_backward send each bucket
+ * -- cnet, anchor networks, conv block 4 ... 1, the order in which the backward pass finishes them -- as soon as it is
+ * final, so that only the last bucket's transfer is exposed; the caller promises that the call is the step's last
+ * accumulation into the gradient.  frcnn_dp_allreduce then sends what is left and joins the streams. */
+int frcnn_dp_unique_id(char id_out[128]);
+int frcnn_dp_init_rank(frcnn_ctx* ctx, const char id[128], int rank, int nranks);
+int frcnn_dp_init_all(frcnn_ctx* const* ctxs, int n);
+int frcnn_dp_set_overlap(frcnn_ctx* ctx, int enable);
+int frcnn_dp_allreduce(frcnn_ctx* const* ctxs, int n, float* const* counters_dev, int n_counters);
+/* rank / size of the context's communicator (nranks = 0: none), the loaded NCCL's version, bytes all-reduced so far */
+int frcnn_dp_info(const frcnn_ctx* ctx, int* rank, int* nranks, int* nccl_version, int64_t* bytes_reduced);
+
 /* ---- low-level conv / GEMM entry (tests, roofline measurement) ---------------------------------------- */
 /* y = prelu(conv(x, w) + bias) * scale on NHWC bf16 activations (passed as uint16 bit patterns).
  * x_dev: [n][h][w][cin]; w_dev: fp32 Torch layout [cout][cin][k][k]; out_dev: [n][ho][wo][cout] bf16, or with
  * pool != 0 the 2x2 stride-2 ceil-mode max-pooled map [n][ceil(ho/2)][ceil(wo/2)][cout] (model_utilities.lua:23).
  * splits > 1 exercises the split-K fp32-atomic path; bn in {0 (auto), 64, 128, 192, 256}; mt in {0 (auto), 1, 2} =
- * 128-row sub-tiles per CTA of the tap-per-box kernel, 11 / 12 = the halo-tile kernel with 1 / 2 sub-tiles.  elapsed_ms (optional) receives the device time of `iters` back-to-back launches of
+ * 128-row sub-tiles per CTA of the tap-per-box kernel, 11 / 12 = the halo-tile kernel with 1 / 2 sub-tiles, 21 / 22 = the
+ * halo-tile kernel on CTA pairs (cta_group::2, M = 256 MMAs) with 1 / 2 sub-tiles per CTA.  elapsed_ms (optional) receives the device time of `iters` back-to-back launches of
  * the conv kernel alone. */
 int frcnn_conv_bf16(frcnn_ctx* ctx, const uint16_t* x_dev, const float* w_dev, const float* bias_dev,
                     const float* prelu_dev, float scale, int n, int h, int w, int cin, int cout, int k, int pad,

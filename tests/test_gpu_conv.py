@@ -102,6 +102,42 @@ def test_conv_halo_kernel(F, small_model, case, bn, mt, pool):
     _conv_case(F, small_model, *case, seed=sum(case) + mt, bn=bn, mt=mt, pool=pool)
 
 
+@pytest.mark.parametrize("pool", [False, True])
+@pytest.mark.parametrize("mt", [21, 22])
+@pytest.mark.parametrize("case,bn", [
+    ((1, 16, 16, 64, 64, 3, 1), 0), ((1, 29, 51, 128, 128, 3, 1), 128), ((2, 57, 100, 128, 256, 3, 1), 256),
+    ((1, 57, 99, 256, 384, 3, 1), 192), ((1, 57, 99, 256, 384, 3, 1), 128), ((1, 45, 77, 64, 128, 3, 1), 64),
+    ((1, 33, 20, 128, 256, 3, 0), 0), ((1, 40, 41, 64, 64, 2, 0), 0), ((4, 113, 200, 128, 256, 3, 1), 0),
+    ((1, 113, 200, 128, 256, 3, 1), 0), ((1, 225, 400, 64, 128, 3, 1), 0), ((1, 57, 100, 256, 384, 3, 1), 0),
+])
+def test_conv_pair_kernel(F, small_model, case, bn, mt, pool):
+    """conv_pair_kernel (mt = 21 / 22): the halo kernel on CTA pairs -- tcgen05.mma cta_group::2 with M = 256, each CTA of the
+    pair loading its own pixel tile and half of every weight box.  Same coverage as the halo kernel plus the headline
+    layer shapes: every tile width, ragged pair tiles (the second CTA's tile partly or wholly outside the map), several
+    units per pair (ring / accumulator phase wrap), pad 0, 2x2 filters, the fused pool."""
+    _conv_case(F, small_model, *case, seed=sum(case) + mt, bn=bn, mt=mt, pool=pool)
+
+
+@pytest.mark.parametrize("pool", [False, True])
+@pytest.mark.parametrize("case,bn,mt", [
+    ((1, 29, 51, 128, 128, 3, 1), 128, 31), ((1, 57, 99, 256, 384, 3, 1), 192, 31), ((1, 45, 77, 64, 128, 3, 1), 64, 31),
+    ((2, 57, 100, 128, 256, 3, 1), 256, 41), ((1, 57, 99, 256, 384, 3, 1), 192, 41), ((4, 113, 200, 128, 256, 3, 1), 0, 41),
+    ((1, 225, 400, 64, 128, 3, 1), 0, 41), ((1, 45, 77, 64, 128, 3, 1), 64, 42), ((1, 113, 200, 128, 256, 3, 1), 128, 31),
+])
+def test_conv_two_ctas_per_sm(F, small_model, case, bn, mt, pool):
+    """The halo kernel (mt = 31) and the CTA-pair kernel (mt = 41 / 42) sized for TWO resident CTAs per SM: half the shared
+    memory and TMEM columns per CTA, two-slot activation ring, <= 85 registers -- same arithmetic, shallower pipeline."""
+    _conv_case(F, small_model, *case, seed=sum(case) + mt, bn=bn, mt=mt, pool=pool)
+
+
+def test_conv_pair_equals_halo_kernel(F, small_model):
+    """Same products, same fp32 accumulation order per output (chunk-major, taps inside): the pair kernel's outputs are
+    bit-identical to the single-CTA halo kernel's."""
+    a, _ = _conv_case(F, small_model, 1, 57, 100, 128, 256, 3, 1, seed=5, mt=12)
+    b, _ = _conv_case(F, small_model, 1, 57, 100, 128, 256, 3, 1, seed=5, mt=22)
+    assert torch.equal(a, b)
+
+
 def test_conv_halo_equals_tap_kernel(F, small_model):
     """Both kernels accumulate the same products in fp32 in the same (chunk-major vs tap-major) grouping only up to
     fp32 rounding: outputs agree to one bf16 ulp, and exactly on small-integer data."""

@@ -233,6 +233,49 @@ def test_cnet_train_step_vs_autograd(F, small_model, R, n_pos):
         m.zero_grad()
 
 
+@pytest.mark.parametrize("R", [48, 130])
+def test_cnet_forward_train_and_backward_vs_autograd(F, small_model, R):
+    """The module slots objective.lua drives itself: cnet:training(); cnet:forward(cinput) (objective.lua:164) and
+    cnet:backward(cinput, {crdelta, ccdelta}) (objective.lua:179) with the CALLER's criteria.  Outputs of the training
+    forward within 2e-2 of autograd on identical (bf16-rounded) rows; post_roi_delta and parameter gradients within 3 %
+    relative L2 for arbitrary output gradients (incl. the LogSoftMax backward)."""
+    m = small_model
+    g = torch.Generator().manual_seed(100 + R)
+    x = OM.bf16_round(torch.randn(R, 13824, generator=g).abs())
+    masks = [(torch.rand(R, n, generator=g) > 0.5).float() for n in (1024, 512)]
+    p = {k: v.clone().requires_grad_(not k.endswith(("bn_mean", "bn_var"))) for k, v in m.oracle_params.items()}
+    xr = x.clone().requires_grad_(True)
+    crout, ccout = OM.cnet_forward(OM.VGG_SMALL, p, xr, train=True, dropout_masks={"fc1": masks[0], "fc2": masks[1]},
+                                   quant=OM.bf16_round, quant_heads=None)
+    d_reg = torch.randn(R, 4, generator=g)
+    d_cls = torch.randn(R, ccout.shape[1], generator=g) / R
+    torch.autograd.backward([crout, ccout], [d_reg, d_cls])
+    saved = m.weights.clone()
+    m.zero_grad()
+    m.cnet.training()
+    try:
+        reg, cls = m.cnet.forward(x.cuda(), dropout_masks=masks)
+        assert torch.allclose(reg.cpu(), crout.detach(), rtol=2e-2, atol=2e-2)
+        assert torch.allclose(cls.cpu(), ccout.detach(), rtol=2e-2, atol=2e-2)
+        dx = m.cnet.backward(x.cuda(), (d_reg, d_cls))
+
+        def rel(a, b):
+            return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+        assert rel(dx.cpu(), xr.grad) <= 0.03
+        for name in ("fc1.weight", "fc1.bn_weight", "fc1.bn_bias", "fc1.prelu", "fc2.weight", "fc2.bias", "fc2.prelu", "reg.weight",
+                     "reg.bias", "cls.weight", "cls.bias"):
+            gr = p[name].grad
+            assert rel(m.grads[name].cpu().reshape(gr.shape), gr) <= 0.03, name
+        with pytest.raises(F.FrcnnError) as e:   # the state of a forward is consumed by one backward
+            m.cnet.backward(x.cuda(), (d_reg, d_cls))
+        assert e.value.code == 4
+    finally:
+        m.cnet.evaluate()
+        m.weights.copy_(saved)
+        m.pack_weights()
+        m.zero_grad()
+
+
 def test_create_objective_matches_manual_loop(F, small_model):
     """lossAndGradient (objective.lua:45-218): zero, per-frame loop, gradient / cls_count, statistics."""
     from oracle import anchors as OA, objective as OO

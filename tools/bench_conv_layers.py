@@ -35,6 +35,8 @@ def main():
     rows = []
     for n in batches:
         for name, h, w, cin, cout, pool in LAYERS:
+            if os.environ.get("FRCNN_BENCH_LAYER") and os.environ["FRCNN_BENCH_LAYER"] != name:
+                continue
             x = torch.randn(n, h, w, cin, device="cuda").to(torch.bfloat16)
             wt = torch.randn(cout, cin, 3, 3, device="cuda") * 0.05
             b = torch.zeros(cout, device="cuda")
@@ -47,13 +49,14 @@ def main():
                 if forced[0] and cout % forced[0]:
                     continue
                 best = None
-                for rep in range(3):
+                for rep in range(int(os.environ.get("FRCNN_BENCH_REPS", "3"))):
                     rc = L.frcnn_conv_bf16(m.ctx, ffi.cast("const uint16_t*", x.data_ptr()), ffi.cast("const float*", wt.data_ptr()),
                                            ffi.cast("const float*", b.data_ptr()), ffi.cast("const float*", s.data_ptr()), 1.0, n, h, w,
-                                           cin, cout, 3, 1, 0, forced[0], forced[1], pool, ffi.cast("uint16_t*", out.data_ptr()), 20, ms)
+                                           cin, cout, 3, 1, 0, forced[0], forced[1], pool, ffi.cast("uint16_t*", out.data_ptr()),
+                                           int(os.environ.get("FRCNN_BENCH_ITERS", "20")), ms)
                     if rc != 0:
                         break
-                    us = ms[0] * 1000.0 / 20
+                    us = ms[0] * 1000.0 / int(os.environ.get("FRCNN_BENCH_ITERS", "20"))
                     best = us if best is None else min(best, us)
                 if best is None:
                     continue
