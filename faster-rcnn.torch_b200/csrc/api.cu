@@ -140,6 +140,7 @@ struct frcnn_ctx {
   std::vector<void*> ws_allocs;
   std::vector<bf16*> pool_out;   // per block
   std::vector<int> pool_h, pool_w;
+  HeadPlan head_plan;            // conv_head_kernel: the anchor networks of a frame batch in one launch (evaluate mode)
   int feat_h = 0, feat_w = 0;
 
   // detector workspace
@@ -589,6 +590,36 @@ static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
     conv_set_f32_output(&hd.conv.launch, hd.acc);
     conv_prepare_head(&hd.fused, c->pool_out[hd.input - 1], hd.conv.w_packed, N, ih, iw, hd.conv.cin, hd.kW, c->sm_count);
   }
+  // the fused anchor-network kernel (evaluate mode): unit schedule, slices of the split heads, arrival counters
+  {
+    HeadDesc hdesc[MAX_GROUP];
+    const int nh = (int)c->heads.size();
+    FRCNN_REQUIRE(nh <= MAX_GROUP, FRCNN_E_INVALID, "at most 4 anchor networks (Detector.lua:38)");
+    for (int i = 0; i < nh; ++i) {
+      Head& hd = c->heads[i];
+      hdesc[i] = HeadDesc{c->pool_out[hd.input - 1], hd.conv.w_packed, c->pool_h[hd.input - 1], c->pool_w[hd.input - 1], hd.conv.cin, hd.kW};
+    }
+    std::vector<int4> units;
+    std::vector<int> cta_off;
+    size_t slice_floats[MAX_GROUP];
+    int counter_ints[MAX_GROUP];
+    conv_head_plan(&c->head_plan, hdesc, nh, N, c->sm_count, &units, &cta_off, slice_floats, counter_ints);
+    int4* d_units = (int4*)dev_alloc(c->ws_allocs, units.size() * sizeof(int4));
+    int* d_off = (int*)dev_alloc(c->ws_allocs, cta_off.size() * sizeof(int));
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(d_units, units.data(), units.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(d_off, cta_off.data(), cta_off.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    c->head_plan.sched.units = d_units;
+    c->head_plan.sched.cta_off = d_off;
+    for (int i = 0; i < MAX_GROUP; ++i) {
+      c->head_plan.sched.slices[i] = slice_floats[i] ? (float*)dev_alloc(c->ws_allocs, slice_floats[i] * sizeof(float)) : nullptr;
+      c->head_plan.sched.counters[i] = nullptr;
+      if (counter_ints[i]) {
+        c->head_plan.sched.counters[i] = (int*)dev_alloc(c->ws_allocs, counter_ints[i] * sizeof(int));
+        FRCNN_CUDA_TRY(cudaMemsetAsync(c->head_plan.sched.counters[i], 0, counter_ints[i] * sizeof(int), c->stream));
+      }
+    }
+    FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));   // `units` / `cta_off` are stack vectors
+  }
   c->ws_n = N; c->ws_h = H; c->ws_w = W;
 }
 
@@ -694,6 +725,39 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
   // the other frames.  Latency schedule: one grouped split-K conv launch (every SM busy on this frame), heaviest
   // units first, then one grouped tail launch.
   if (detect_stop_after() == 1 && !train) return;
+  static const int old_heads = getenv("FRCNN_HEADS_OLD") ? atoi(getenv("FRCNN_HEADS_OLD")) : 0;   // A/B measurements only
+  if (!train && !old_heads) {
+    // evaluate mode, both schedules: conv_head_kernel (linear tiles, reduction split by filter rows with in-kernel fix-up)
+    HeadPlan& hp = c->head_plan;
+    for (size_t i = 0; i < c->heads.size(); ++i) {
+      Head& hd = c->heads[i];
+      ConvParams& p = hp.grp.p[i];
+      p.bias = P(c, hd.conv.p_b); p.prelu = P(c, hd.conv.p_prelu); p.w2 = P(c, hd.p_w2); p.b2 = P(c, hd.p_b2);
+      p.out = hd.out;
+      p.f16 = f16;
+    }
+    for (size_t i = c->heads.size(); i < (size_t)MAX_GROUP; ++i) hp.grp.p[i] = hp.grp.p[c->heads.size() - 1];
+    const bool prof = c->profiling;
+    if (prof) {
+      if ((int)c->conv_ev.size() < c->conv_ev_used + 2) {
+        cudaEvent_t a, b;
+        FRCNN_CUDA_TRY(cudaEventCreate(&a));
+        FRCNN_CUDA_TRY(cudaEventCreate(&b));
+        c->conv_ev.push_back(a);
+        c->conv_ev.push_back(b);
+      }
+      cudaEventRecord(c->conv_ev[c->conv_ev_used], c->stream);
+    }
+    conv_launch_heads(hp, c->stream);
+    ++c->launches;
+    if (prof) {
+      cudaEventRecord(c->conv_ev[c->conv_ev_used + 1], c->stream);
+      c->conv_ev_used += 2;
+      c->conv_flops += hp.flops;
+    }
+    FRCNN_CUDA_TRY(cudaGetLastError());
+    return;
+  }
   if (c->schedule == FRCNN_SCHED_THROUGHPUT && !train) {
     std::vector<const ConvLaunch*> order;
     for (auto& hd : c->heads) {
@@ -1280,6 +1344,7 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
     // machine on the latency schedule, a quarter of it on the throughput schedule (measured: 37 CTAs cost a single
     // frame nothing and leave the other SMs to the frames in flight; the 148-way TMA reduce-add contention goes away)
     f.launch.p.dyn_ctas = cnet_ctas(c);
+    f.launch.grid = std::min(f.launch.grid, f.launch.p.dyn_ctas);   // no idle CTAs: each would still claim a whole SM (TMEM, 200 KB)
     in = f.out_bf16;
   }
   // NMS workspace: segments = max(N images, N * classes)
@@ -1950,6 +2015,36 @@ int frcnn_feature_to_input_rect(const frcnn_ctx* cc, int which, const double rec
   return FRCNN_OK;
 }
 
+// the same with the optional layer_index argument of the Lua methods (Localizer.lua:41-42,69-70): only the first
+// `layer_index` layers take part (0 or #layers = all of them)
+int frcnn_input_to_feature_rect_upto(const frcnn_ctx* cc, int which, int layer_index, const double rect[4], double out[4]) {
+  frcnn_ctx* c = const_cast<frcnn_ctx*>(cc);
+  if (!c || !c->planned || which < 0 || which >= (int)c->loc.size() || !rect || !out) return FRCNN_E_INVALID;
+  const auto& L = c->loc[which];
+  if (layer_index < 0 || layer_index > (int)L.size()) return FRCNN_E_INVALID;
+  if (layer_index == 0 || layer_index == (int)L.size()) {
+    frcnn::input_to_feature(L, rect, out);
+  } else {
+    std::vector<std::array<int, 6>> part(L.begin(), L.begin() + layer_index);
+    frcnn::input_to_feature(part, rect, out);
+  }
+  return FRCNN_OK;
+}
+
+int frcnn_feature_to_input_rect_upto(const frcnn_ctx* cc, int which, int layer_index, const double rect[4], double out[4]) {
+  frcnn_ctx* c = const_cast<frcnn_ctx*>(cc);
+  if (!c || !c->planned || which < 0 || which >= (int)c->loc.size() || !rect || !out) return FRCNN_E_INVALID;
+  const auto& L = c->loc[which];
+  if (layer_index < 0 || layer_index > (int)L.size()) return FRCNN_E_INVALID;
+  if (layer_index == 0 || layer_index == (int)L.size()) {
+    frcnn::feature_to_input(L, rect, out);
+  } else {
+    std::vector<std::array<int, 6>> part(L.begin(), L.begin() + layer_index);
+    frcnn::feature_to_input(part, rect, out);
+  }
+  return FRCNN_OK;
+}
+
 int frcnn_anchors_build(frcnn_ctx* c, float* w_lut_host, float* h_lut_host) {
   if (!c || !c->planned || !w_lut_host || !h_lut_host) return FRCNN_E_INVALID;
   memcpy(w_lut_host, c->w_lut.data(), c->w_lut.size() * sizeof(float));
@@ -2552,7 +2647,11 @@ int frcnn_set_schedule(frcnn_ctx* c, int schedule) {
   if (c->schedule != schedule) {
     c->schedule = schedule;
     for (auto& f : c->fcs)
-      if (f.launch.p.m_limit) f.launch.p.dyn_ctas = frcnn::cnet_ctas(c);
+      if (f.launch.p.m_limit) {
+        f.launch.p.dyn_ctas = frcnn::cnet_ctas(c);
+        const int total = f.launch.p.n_tiles_m * f.launch.p.n_tiles_n * f.launch.p.splits;
+        f.launch.grid = std::min(std::min(total, c->sm_count), f.launch.p.dyn_ctas);
+      }
     ++c->ws_gen;  // a captured detect graph holds the other schedule's launches: re-capture
   }
   return FRCNN_OK;

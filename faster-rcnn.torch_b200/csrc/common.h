@@ -139,6 +139,35 @@ struct ConvMaps {
   CUtensorMap a[MAX_GROUP], b[MAX_GROUP], o[MAX_GROUP];
 };
 
+// Work schedule of conv_head_kernel (the four anchor networks in one launch): units = (head, image, 128-position tile,
+// filter-row range), dealt to the persistent CTAs by the host.  units[i] = {head | slice << 8 | n_slices << 16, image, tile,
+// kh0 | kh1 << 8}; CTA b processes units [cta_off[b], cta_off[b + 1]).
+struct HeadSched {
+  const int4* units;
+  const int* cta_off;
+  float* slices[MAX_GROUP];    // per head: [image][tile][slice][128][256] fp32 partial sums (split heads only)
+  int* counters[MAX_GROUP];    // per head: [image][tile] arrivals; zero between launches
+  int tiles[MAX_GROUP];        // tiles per image
+};
+// Builds the launch state of the fused anchor-network kernel for N frames of in_h x in_w (per head) and runs it.
+struct HeadPlan {
+  ConvMaps maps;
+  ConvGroup grp;
+  HeadSched sched;
+  int grid = 0;
+  int n_units = 0;
+  double flops = 0.0;
+};
+
+struct HeadDesc {
+  const bf16* in;        // NHWC 16-bit input map [N][Hin][Win][Cin]
+  const bf16* w_packed;  // [2][256][K][K][Cin] packed weights (bf16 | fp16 copies)
+  int Hin, Win, Cin, K;
+};
+void conv_head_plan(HeadPlan* P, const HeadDesc* heads, int n_heads, int N, int num_sms, std::vector<int4>* units_out,
+                    std::vector<int>* cta_off_out, size_t slice_floats[MAX_GROUP], int counter_ints[MAX_GROUP]);
+void conv_launch_heads(const HeadPlan& P, cudaStream_t st);
+
 // Host helpers (conv_igemm.cu)
 void conv_choose_tile(int Hout, int Wout, int* BW, int* BH);
 void make_tmap_act(CUtensorMap* m, const bf16* base, int N, int H, int W, int C, int BW, int BH);

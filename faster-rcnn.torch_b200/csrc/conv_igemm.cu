@@ -1054,6 +1054,319 @@ __global__ void __launch_bounds__(CONV_THREADS, OCC)
   }
 }
 
+// ------------------------------------------------------------------------------------------------- anchor networks
+// The four AnchorNetworks (model_utilities.lua:29-35: k x k valid conv to 256 channels -> PReLU -> 1 x 1 conv to 18) of a
+// frame in ONE launch, fused down to the 18-channel maps Detector.lua:47-49 reads.  What the halo-kernel version lost
+// (profiles/r1b_ncu_full_b1.md: 136 us, 0.13 of the tensor peak, 88 CTAs): 8 x 16 pixel tiles on 23..27-row maps waste
+// 16-34 % of every MMA; one CTA per tile makes the 7 x 7 head's 18 816-deep reduction a 78-135 us critical path.
+//   * LINEAR tiles: the input map is the 2-D matrix [N*Hin*Win pixels][Cin] and a tile is 128 CONSECUTIVE pixel positions
+//     p = y*Win + x.  For filter row kh the A operand of ALL kw taps is one slab of 128 + k - 1 consecutive rows starting at
+//     p0 + kh*Win (one TMA box {64 ch, 136 rows}); tap kw is the same slab read from row kw on (UMMA descriptor start
+//     + kw*128 B, canonical 8-row groups).  Positions whose window wraps around the row end (x > Win - k) produce
+//     garbage that is never stored: 4-12 % waste instead of 16-34 %.
+//   * K SPLIT BY FILTER ROWS with an in-kernel fix-up: a unit is (head, image, tile, kh range).  Split units write their
+//     fp32 partial sums [128][256] to a slice in L2; the unit that arrives LAST at the tile's counter sums the slices in
+//     ascending order (fixed order: the result does not depend on who is last), applies bias + PReLU + the 1 x 1 conv and
+//     stores.  Units are dealt to the persistent CTAs by a host-side longest-processing-time schedule.
+// Warp roles / pipeline as conv_halo_kernel: TMA producer, single-thread MMA issuer (M128 x N256 x K16), two
+// accumulator stages in TMEM, eight epilogue warps.
+static constexpr int HEADK_SLAB_ROWS = 136;                                  // 128 + (7 - 1), padded to a multiple of 8
+static constexpr int HEADK_A_SLOT = HEADK_SLAB_ROWS * 128;                   // 17 408 B = 17 KB
+static constexpr int HEADK_A_SLOTS = 3, HEADK_B_SLOTS = 4;
+static constexpr int HEADK_B_SLOT = HEAD_CM * 128;                           // 32 KB
+static constexpr int HEADK_SMEM = HEADK_A_SLOTS * HEADK_A_SLOT + HEADK_B_SLOTS * HEADK_B_SLOT + HEAD_SMEM + MAX_BIAS * 4 + 512 + 1024;
+
+__device__ __forceinline__ void headk_decode(const int4 u, int& head, int& s, int& nsl, int& img, int& tile, int& kh0, int& kh1) {
+  head = u.x & 0xff; s = (u.x >> 8) & 0xff; nsl = (u.x >> 16) & 0xff;
+  img = u.y; tile = u.z; kh0 = u.w & 0xff; kh1 = (u.w >> 8) & 0xff;
+}
+
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+    conv_head_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGroup grp, const HeadSched hs) {
+  constexpr int BN = HEAD_CM;
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BN);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + HEADK_A_SLOTS * HEADK_A_SLOT;
+  float* w2s = reinterpret_cast<float*>(smem_b + HEADK_B_SLOTS * HEADK_B_SLOT);
+  float* parts = w2s + HEAD_CM * HEAD_W2_PITCH;
+  float* sb = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(w2s) + HEAD_SMEM);
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(sb + MAX_BIAS);
+  uint64_t* empty_a = full_a + HEADK_A_SLOTS;
+  uint64_t* full_b = empty_a + HEADK_A_SLOTS;
+  uint64_t* empty_b = full_b + HEADK_B_SLOTS;
+  uint64_t* tmem_full = empty_b + HEADK_B_SLOTS;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  int* s_flag = reinterpret_cast<int*>(tmem_base_slot + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int u_begin = hs.cta_off[blockIdx.x], u_end = hs.cta_off[blockIdx.x + 1];
+
+  if (warp == 0 && lane == 0) {
+    for (int g = 0; g < grp.n; ++g) {
+      ptx::tma_prefetch_desc(&maps.a[g]);
+      ptx::tma_prefetch_desc(&maps.b[g]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < HEADK_A_SLOTS; ++i) {
+      ptx::mbar_init(&full_a[i], 1);
+      ptx::mbar_init(&empty_a[i], 1);
+    }
+    for (int i = 0; i < HEADK_B_SLOTS; ++i) {
+      ptx::mbar_init(&full_b[i], 1);
+      ptx::mbar_init(&empty_b[i], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], EPI_THREADS / 32);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_base_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer: per (kh, chunk) step one slab + k weight boxes.
+    // The slab of step i + 1 goes out BEFORE the weight boxes of step i (its own cursor, one step ahead): otherwise it
+    // would queue behind weight boxes that wait for ring slots, and every step would start with an exposed load latency.
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int a_ui = u_begin, a_kh = -1, a_c = 0;   // cursor of the slab ring
+      auto issue_a = [&]() {
+        while (a_ui < u_end) {
+          int g, s, nsl, img, tile, kh0, kh1;
+          headk_decode(hs.units[a_ui], g, s, nsl, img, tile, kh0, kh1);
+          const ConvParams& p = grp.p[g];
+          if (a_kh < 0) { a_kh = kh0; a_c = 0; }
+          if (a_kh >= kh1) { ++a_ui; a_kh = -1; continue; }
+          ptx::mbar_wait(&empty_a[as], aph ^ 1);
+          ptx::mbar_arrive_expect_tx(&full_a[as], HEADK_A_SLOT);
+          ptx::tma_load_2d(smem_a + as * HEADK_A_SLOT, &maps.a[g], &full_a[as], a_c * BLOCK_K,
+                           img * p.Hin * p.Win + tile * BLOCK_M + a_kh * p.Win);
+          if (++as == HEADK_A_SLOTS) {
+            as = 0;
+            aph ^= 1;
+          }
+          if (++a_c == p.cchunks) { a_c = 0; ++a_kh; }
+          return;
+        }
+      };
+      issue_a();
+      for (int ui = u_begin; ui < u_end; ++ui) {
+        int g, s, nsl, img, tile, kh0, kh1;
+        headk_decode(hs.units[ui], g, s, nsl, img, tile, kh0, kh1);
+        const ConvParams& p = grp.p[g];
+        for (int kh = kh0; kh < kh1; ++kh) {
+          for (int c = 0; c < p.cchunks; ++c) {
+            issue_a();   // the NEXT step's slab
+            for (int kw = 0; kw < p.KW; ++kw) {
+              ptx::mbar_wait(&empty_b[bs], bph ^ 1);
+              ptx::mbar_arrive_expect_tx(&full_b[bs], HEADK_B_SLOT);
+              ptx::tma_load_3d(smem_b + bs * HEADK_B_SLOT, &maps.b[g], &full_b[bs], ((kh * p.KW + kw) * p.cchunks + c) * BLOCK_K, 0, p.f16);
+              if (++bs == HEADK_B_SLOTS) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int seq = 0;
+      for (int ui = u_begin; ui < u_end; ++ui, ++seq) {
+        int g, s, nsl, img, tile, kh0, kh1;
+        headk_decode(hs.units[ui], g, s, nsl, img, tile, kh0, kh1);
+        const ConvParams& p = grp.p[g];
+        const uint32_t idesc = p.f16 ? ptx::idesc_to_f16(IDESC) : IDESC;
+        const int acc = seq & 1;
+        ptx::mbar_wait(&tmem_empty[acc], ((uint32_t)(seq >> 1) & 1u) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        uint32_t first = 0u;
+        for (int kh = kh0; kh < kh1; ++kh) {
+          for (int c = 0; c < p.cchunks; ++c) {
+            ptx::mbar_wait(&full_a[as], aph);
+            const uint32_t a_addr = ptx::smem_u32(smem_a + as * HEADK_A_SLOT);
+            for (int kw = 0; kw < p.KW; ++kw) {
+              ptx::mbar_wait(&full_b[bs], bph);
+              ptx::tc_fence_after();
+              // tap kw = the slab read from row kw on: start address + kw * 128 B, canonical 8-row groups (SBO 1024)
+              const uint64_t da = ptx::make_desc_k_sw128(a_addr + kw * 128);
+              const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + bs * HEADK_B_SLOT));
+#pragma unroll
+              for (int j = 0; j < BLOCK_K / 16; ++j) ptx::mma_bf16_ss(d_tmem, da + 2 * j, db + 2 * j, idesc, j > 0 ? 1u : first);
+              first = 1u;
+              ptx::mma_commit(&empty_b[bs]);
+              if (++bs == HEADK_B_SLOTS) {
+                bs = 0;
+                bph ^= 1;
+              }
+            }
+            ptx::mma_commit(&empty_a[as]);
+            if (++as == HEADK_A_SLOTS) {
+              as = 0;
+              aph ^= 1;
+            }
+          }
+        }
+        ptx::mma_commit(&tmem_full[acc]);
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue: thread = pixel row (TMEM lane), column half = ewarp >> 2
+    const int ewarp = warp - 4;
+    const int q = ewarp & 3, half = ewarp >> 2;
+    const int row = q * 32 + lane;
+    const int tid = ewarp * 32 + lane;
+    int cur = -1, seq = 0;
+    for (int ui = u_begin; ui < u_end; ++ui, ++seq) {
+      int g, s, nsl, img, tile, kh0, kh1;
+      headk_decode(hs.units[ui], g, s, nsl, img, tile, kh0, kh1);
+      const ConvParams& p = grp.p[g];
+      const int acc = seq & 1;
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + half * 128) + ((uint32_t)(q * 32) << 16);
+      const int tiles_img = hs.tiles[g];
+      const long tile_lin = (long)img * tiles_img + tile;
+      bool finish = true;
+      ptx::mbar_wait(&tmem_full[acc], (uint32_t)(seq >> 1) & 1u);
+      ptx::tc_fence_after();
+      if (nsl > 1) {
+        // ---- partial sums of this filter-row range -> slice s of the tile (plain 64-byte stores per thread and step)
+        float* sl = hs.slices[g] + ((tile_lin * nsl + s) * BLOCK_M + row) * BN + half * 128;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 16) {
+          uint32_t v[16];
+          ptx::tmem_ld_32x32b_x16(taddr + c0, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            __stcg(reinterpret_cast<uint4*>(sl + c0) + j, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);   // the accumulator stage is free for the next unit's MMAs
+        __threadfence();                                     // slice visible device-wide before the arrival is counted
+        ptx::named_bar_sync(1, EPI_THREADS);
+        if (tid == 0) {
+          int* cnt = hs.counters[g] + tile_lin;
+          const int old = atomicAdd(cnt, 1);
+          const int last = old == nsl - 1;
+          if (last) *cnt = 0;                                // every split has arrived: re-armed for the next launch
+          *s_flag = last;
+        }
+        ptx::named_bar_sync(1, EPI_THREADS);
+        finish = *s_flag != 0;
+        if (finish) __threadfence();
+      }
+      if (!finish) continue;
+      if (g != cur) {  // another head: its 1x1 weights [18][256] -> [256][20], hidden bias [256], output bias [18]
+        ptx::named_bar_sync(1, EPI_THREADS);
+        for (int i = tid; i < HEAD_CO * HEAD_CM; i += EPI_THREADS) {
+          const int o = i / HEAD_CM, c = i - o * HEAD_CM;
+          w2s[c * HEAD_W2_PITCH + o] = __ldg(p.w2 + i);
+        }
+        for (int i = tid; i < HEAD_CM; i += EPI_THREADS) sb[i] = __ldg(p.bias + i);
+        if (tid < HEAD_CO) sb[HEAD_CM + tid] = __ldg(p.b2 + tid);
+        ptx::named_bar_sync(1, EPI_THREADS);
+        cur = g;
+      }
+      const float slope = p.prelu ? __ldg(p.prelu) : 1.0f;
+      float o18[HEAD_CO];
+#pragma unroll
+      for (int o = 0; o < HEAD_CO; ++o) o18[o] = 0.f;
+      const float* sl0 = hs.slices[g] + ((tile_lin * nsl) * BLOCK_M + row) * BN + half * 128;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 16) {
+        float x[16];
+        if (nsl > 1) {
+          // the k x k sums: slices in ascending order (fixed summation order whoever finishes)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(sl0 + c0) + j);
+            x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+          }
+          for (int s2 = 1; s2 < nsl; ++s2) {
+            const float* slp = sl0 + (long)s2 * BLOCK_M * BN + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 t = __ldcg(reinterpret_cast<const float4*>(slp) + j);
+              x[4 * j] += t.x; x[4 * j + 1] += t.y; x[4 * j + 2] += t.z; x[4 * j + 3] += t.w;
+            }
+          }
+        } else {
+          uint32_t v[16];
+          ptx::tmem_ld_32x32b_x16(taddr + c0, v);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+        }
+        const float* wrow = w2s + (half * 128 + c0) * HEAD_W2_PITCH;
+        const float* brow = sb + half * 128 + c0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float h = x[j] + brow[j];
+          h = h > 0.f ? h : h * slope;
+          const float4* w4 = reinterpret_cast<const float4*>(wrow + j * HEAD_W2_PITCH);
+#pragma unroll
+          for (int gq = 0; gq < 5; ++gq) {
+            const float4 w = w4[gq];
+            o18[4 * gq] = fmaf(h, w.x, o18[4 * gq]);
+            o18[4 * gq + 1] = fmaf(h, w.y, o18[4 * gq + 1]);
+            if (gq < 4) {
+              o18[4 * gq + 2] = fmaf(h, w.z, o18[4 * gq + 2]);
+              o18[4 * gq + 3] = fmaf(h, w.w, o18[4 * gq + 3]);
+            }
+          }
+        }
+      }
+      if (nsl == 1) {
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      }
+      if (half == 1) {
+#pragma unroll
+        for (int o = 0; o < HEAD_CO; ++o) parts[row * HEAD_PART_PITCH + o] = o18[o];
+      }
+      ptx::named_bar_sync(1, EPI_THREADS);
+      if (half == 0) {
+        const int pp = tile * BLOCK_M + row;         // linear position on the INPUT grid
+        const int y = pp / p.Win, x = pp - y * p.Win;
+        if (y < p.Hout && x < p.Wout) {
+          const size_t HW = (size_t)p.Hout * p.Wout;
+          float* o_px = reinterpret_cast<float*>(p.out) + (size_t)img * HEAD_CO * HW + (size_t)y * p.Wout + x;
+#pragma unroll
+          for (int o = 0; o < HEAD_CO; ++o) o_px[o * HW] = (o18[o] + parts[row * HEAD_PART_PITCH + o]) + sb[HEAD_CM + o];
+        }
+      }
+      ptx::named_bar_sync(1, EPI_THREADS);  // `parts` may be overwritten by the next unit
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- weight gradient, tap groups
 // conv_igemm_kernel's weight-gradient mode makes one unit per filter tap: dY and X are re-read nine times and every
 // K step moves 16 KB + BN/64 x 8 KB through the SM's L2 port for 4 MMAs -- 94 to 188 B/clk against the ~50 B/clk the port
@@ -2347,6 +2660,108 @@ void conv_launch_group(const ConvLaunch* const* Ls, int n, int num_sms, cudaStre
     grp.unit_end[g] = total;
   }
   launch_key(Ls[0]->BN, 1, maps, grp, total < num_sms ? total : num_sms, st);
+}
+
+// ---- fused anchor-network kernel (conv_head_kernel): plan + launch
+// Fills P->grp / P->maps and the host-side unit schedule for `n_heads` anchor networks on N frames; the caller uploads
+// units / cta_off, allocates the slices and counters (sizes returned) and stores the device pointers in P->sched.
+void conv_head_plan(HeadPlan* P, const HeadDesc* heads, int n_heads, int N, int num_sms, std::vector<int4>* units_out,
+                    std::vector<int>* cta_off_out, size_t slice_floats[MAX_GROUP], int counter_ints[MAX_GROUP]) {
+  FRCNN_REQUIRE(n_heads >= 1 && n_heads <= MAX_GROUP && N >= 1 && N < 65536, FRCNN_E_INVALID, "anchor networks: 1..4 heads");
+  P->grp = ConvGroup();
+  P->grp.n = n_heads;
+  P->flops = 0.0;
+  struct U { int cost, head, img, tile, kh0, kh1, s, nsl; };
+  std::vector<U> units;
+  long total_cost = 0;
+  int tiles[MAX_GROUP] = {0, 0, 0, 0};
+  for (int g = 0; g < n_heads; ++g) {
+    const HeadDesc& h = heads[g];
+    FRCNN_REQUIRE(h.Cin % 64 == 0 && h.K >= 1 && h.K <= HEAD_MAXK && h.Hin >= h.K && h.Win >= h.K, FRCNN_E_INVALID,
+                  "anchor network: Cin % 64 == 0, kernel size <= 7, input at least as large as the kernel");
+    ConvParams& p = P->grp.p[g];
+    p = ConvParams();
+    p.N = N; p.Hin = h.Hin; p.Win = h.Win; p.Cin = h.Cin; p.Cout = HEAD_CM; p.KH = h.K; p.KW = h.K;
+    p.Hout = h.Hin - h.K + 1; p.Wout = h.Win - h.K + 1;
+    p.cchunks = h.Cin / 64; p.k_iters = h.K * h.K * p.cchunks; p.mode = EPI_HEAD; p.scale = 1.f; p.MT = 1; p.splits = 1;
+    // linear positions that carry a valid output: up to (Hout - 1) * Win + Wout - 1
+    tiles[g] = ((p.Hout - 1) * h.Win + p.Wout + BLOCK_M - 1) / BLOCK_M;
+    total_cost += (long)N * tiles[g] * p.k_iters;
+    P->flops += 2.0 * N * p.Hout * p.Wout * (double)HEAD_CM * h.K * h.K * h.Cin;
+    // the input map as a matrix [N * Hin * Win][Cin]: box {64 channels, 136 rows}
+    cuuint64_t dims[2] = {(cuuint64_t)h.Cin, (cuuint64_t)N * h.Hin * h.Win};
+    cuuint64_t strides[1] = {(cuuint64_t)h.Cin * 2};
+    cuuint32_t box[2] = {BLOCK_K, HEADK_SLAB_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = get_encode()(&P->maps.a[g], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<bf16*>(h.in), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    FRCNN_REQUIRE(r == CUDA_SUCCESS, FRCNN_E_CUDA, "cuTensorMapEncodeTiled(anchor network input) failed, CUresult " + std::to_string((int)r));
+    make_tmap_weight(&P->maps.b[g], h.w_packed, HEAD_CM, h.K * h.K * h.Cin, HEAD_CM, 2);
+    P->maps.o[g] = P->maps.b[g];
+  }
+  for (int g = n_heads; g < MAX_GROUP; ++g) {
+    P->grp.p[g] = P->grp.p[n_heads - 1];
+    P->maps.a[g] = P->maps.a[n_heads - 1];
+    P->maps.b[g] = P->maps.b[n_heads - 1];
+    P->maps.o[g] = P->maps.o[n_heads - 1];
+  }
+  // split a head's reduction by filter rows when one unsplit tile would be longer than a CTA's fair share of the launch
+  const long fair = std::max<long>(16, (total_cost + num_sms - 1) / num_sms);
+  for (int g = 0; g < n_heads; ++g) {
+    const ConvParams& p = P->grp.p[g];
+    int nsl = (int)std::min<long>(p.KH, (p.k_iters + fair - 1) / fair);
+    if (nsl < 1) nsl = 1;
+    const int row_cost = p.KW * p.cchunks;
+    slice_floats[g] = nsl > 1 ? (size_t)N * tiles[g] * nsl * BLOCK_M * HEAD_CM : 0;
+    counter_ints[g] = N * tiles[g];
+    P->sched.tiles[g] = tiles[g];
+    for (int n = 0; n < N; ++n)
+      for (int t = 0; t < tiles[g]; ++t)
+        for (int s = 0; s < nsl; ++s) {
+          const int kh0 = (int)((long)p.KH * s / nsl), kh1 = (int)((long)p.KH * (s + 1) / nsl);
+          // a split unit also pays for writing its slice; the fix-up itself lands on whichever unit arrives last
+          units.push_back(U{(kh1 - kh0) * row_cost + (nsl > 1 ? 4 : 0), g, n, t, kh0, kh1, s, nsl});
+        }
+  }
+  for (int g = n_heads; g < MAX_GROUP; ++g) { slice_floats[g] = 0; counter_ints[g] = 0; P->sched.tiles[g] = 0; }
+  // longest-processing-time schedule over the persistent CTAs (deterministic: stable sort, lowest CTA index on ties)
+  std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+  const int G = (int)std::min<size_t>((size_t)num_sms, units.size());
+  std::vector<long> load(G, 0);
+  std::vector<std::vector<int>> mine(G);
+  for (size_t i = 0; i < units.size(); ++i) {
+    int best = 0;
+    for (int b = 1; b < G; ++b)
+      if (load[b] < load[best]) best = b;
+    load[best] += units[i].cost;
+    mine[best].push_back((int)i);
+  }
+  units_out->clear();
+  cta_off_out->assign(G + 1, 0);
+  for (int b = 0; b < G; ++b) {
+    for (int i : mine[b]) {
+      const U& u = units[i];
+      units_out->push_back(make_int4(u.head | (u.s << 8) | (u.nsl << 16), u.img, u.tile, u.kh0 | (u.kh1 << 8)));
+    }
+    (*cta_off_out)[b + 1] = (int)units_out->size();
+  }
+  P->grid = G;
+  P->n_units = (int)units.size();
+}
+
+void conv_launch_heads(const HeadPlan& P, cudaStream_t st) {
+  static DeviceOnce configured;
+  if (first_use_on_device(configured)) {
+    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADK_SMEM));
+  }
+  for (int g = 0; g < P.grp.n; ++g) {
+    const ConvParams& p = P.grp.p[g];
+    FRCNN_REQUIRE(p.w2 && p.b2 && p.bias && p.out, FRCNN_E_STATE, "anchor networks: tail parameters / outputs not set");
+  }
+  FRCNN_REQUIRE(P.sched.units && P.sched.cta_off, FRCNN_E_STATE, "anchor networks: schedule not uploaded");
+  conv_head_kernel<<<P.grid, CONV_THREADS, HEADK_SMEM, st>>>(P.maps, P.grp, P.sched);
+  FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
 void conv_launch_head_group(const ConvLaunch* const* Ls, int n, int num_sms, cudaStream_t st) {

@@ -21,20 +21,17 @@ class Localizer:
         keys = ("kW", "kH", "dW", "dH", "padW", "padH")
         self.layers = [dict(zip(keys, [buf[6 * i + j] for j in range(6)])) for i in range(n[0])]
 
-    def inputToFeatureRect(self, rect, layer_index=None):
-        if layer_index is not None and layer_index != len(self.layers):
-            raise NotImplementedError("partial layer ranges are not used on the detection path")
+    def inputToFeatureRect(self, rect, layer_index=None):  # Localizer.lua:41-67
+        """layer_index (Localizer.lua:42): only the first layer_index layers; default: all of them."""
         src = ffi.new("double[4]", list(rect.unpack()))
         dst = ffi.new("double[4]")
-        check(self.model.ctx, lib().frcnn_input_to_feature_rect(self.model.ctx, self.which, src, dst))
+        check(self.model.ctx, lib().frcnn_input_to_feature_rect_upto(self.model.ctx, self.which, int(layer_index or 0), src, dst))
         return Rect(dst[0], dst[1], dst[2], dst[3])
 
-    def featureToInputRect(self, minX, minY, maxX, maxY, layer_index=None):
-        if layer_index is not None and layer_index != len(self.layers):
-            raise NotImplementedError("partial layer ranges are not used on the detection path")
+    def featureToInputRect(self, minX, minY, maxX, maxY, layer_index=None):  # Localizer.lua:69-79
         src = ffi.new("double[4]", [minX, minY, maxX, maxY])
         dst = ffi.new("double[4]")
-        check(self.model.ctx, lib().frcnn_feature_to_input_rect(self.model.ctx, self.which, src, dst))
+        check(self.model.ctx, lib().frcnn_feature_to_input_rect_upto(self.model.ctx, self.which, int(layer_index or 0), src, dst))
         return Rect(dst[0], dst[1], dst[2], dst[3])
 
 

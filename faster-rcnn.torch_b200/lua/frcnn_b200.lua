@@ -8,7 +8,10 @@
 -- Usage (main.lua stays unchanged except for three lines, see INTEGRATION.md):
 --   local b200 = require 'frcnn_b200'
 --   local model = load_model(cfg, opt.model, opt.restore, true)     -- main.lua:80-101, unchanged
---   b200.accelerate(model)                                          -- binds the flat weights, builds the plan
+--   b200.accelerate(model)                                          -- plan from the nn modules, binds weights + gradients,
+--                                                                   --   overrides pnet/cnet forward/backward (objective.lua,
+--                                                                   --   Detector.lua then run unmodified)
+--   create_objective = b200.create_objective                        -- optional: the fused per-batch objective
 --   local d = Detector(model)                                       -- lua/Detector.lua of this directory
 local ffi = require 'ffi'
 local M = {}
@@ -51,21 +54,99 @@ local function trunk_blocks(pnet, n_heads)
   local blocks, node = {}, pnet.outnode.children[n_heads + 1]
   while node and node.data.module do
     if torch.typename(node.data.module) == 'nn.Sequential' then table.insert(blocks, 1, node.data.module) end
-    node = node.children[1]
+    node = node.children and node.children[1]
   end
   return blocks
 end
 
 local function dev_ptr(t) return ffi.cast('const float*', t:data()) end
+local function dev_ptr_rw(t) return ffi.cast('float*', t:data()) end
 
--- Builds the plan from the model's own description tables (models/vgg_*.lua) and binds device pointers of the
--- learnable tensors -- views into the flat CudaTensor created by combine_and_flatten_parameters
--- (utilities.lua:136-147), so optimiser updates (main.lua:133) are seen after the next M.pack(model).
+-- The reference's model table is { cfg, layers, pnet, cnet } (model_utilities.lua:128-134): the anchor_nets / class_layers
+-- tables of models/vgg_*.lua are NOT kept, so they are read back from the nn modules themselves.
+--   anchor net i = pnet.outnode.children[i].data.module, an nn.Sequential { SpatialConvolution(k x k), PReLU,
+--   SpatialConvolution(1 x 1) } (model_utilities.lua:29-35) whose graph child is the conv block it reads (:51-53);
+--   class layers = the first nn.Sequential of cnet: Linear [, BatchNormalization], PReLU [, Dropout] (:80-92).
+local function derive_anchor_nets(pnet, blocks)
+  local nets, i = {}, 1
+  local n_out = #pnet.outnode.children
+  for i = 1, n_out - 1 do                                    -- the last output is the conv feature map itself (:55)
+    local node = pnet.outnode.children[i]
+    local seq = node.data.module
+    local conv = seq.modules[1]
+    assert(torch.typename(conv) == 'nn.SpatialConvolution' and conv.kW == conv.kH, 'unexpected AnchorNetwork layout')
+    local src, input = node.children[1].data.module, nil
+    for b, blk in ipairs(blocks) do if blk == src then input = b end end
+    assert(input, 'anchor network is not attached to a conv block output')
+    nets[i] = { kW = conv.kW, n = conv.nOutputPlane, input = input }
+  end
+  return nets
+end
+
+local function derive_class_layers(cnet)
+  local net = cnet:findModules('nn.Sequential')[1]
+  local layers = {}
+  for _, m in ipairs(net.modules) do
+    local t = torch.typename(m)
+    if t == 'nn.Linear' then layers[#layers + 1] = { n = m.weight:size(1), dropout = 0, batch_norm = false }
+    elseif t == 'nn.BatchNormalization' then layers[#layers].batch_norm = true
+    elseif t == 'nn.Dropout' then layers[#layers].dropout = m.p end
+  end
+  return layers
+end
+
+-- Parameter tensors in the library's bind order (frcnn_param_info): trunk convs (weight, bias, PReLU slope), anchor
+-- networks (conv weight, bias, slope, 1x1 weight, bias), class layers (Linear weight, bias [, BN weight, bias,
+-- running_mean, running_var], slope), Linear(n, 4), Linear(n, classes).  field = 'weight' / 'gradWeight'.
+local function walk_params(model, anchor_nets, class_layers, grads)
+  local W, B = grads and 'gradWeight' or 'weight', grads and 'gradBias' or 'bias'
+  local list, nh = {}, #anchor_nets
+  local function push(t) list[#list + 1] = t end
+  for _, seq in ipairs(trunk_blocks(model.pnet, nh)) do
+    local convs, prelus = seq:findModules('nn.SpatialConvolution'), seq:findModules('nn.PReLU')
+    for i = 1, #convs do push(convs[i][W]); push(convs[i][B]); push(prelus[i][W]) end
+  end
+  for i = 1, nh do
+    local seq = model.pnet.outnode.children[i].data.module
+    local c1, pr, c2 = seq.modules[1], seq.modules[2], seq.modules[3]
+    push(c1[W]); push(c1[B]); push(pr[W]); push(c2[W]); push(c2[B])
+  end
+  local lin = model.cnet:findModules('nn.Linear')
+  local bns = model.cnet:findModules('nn.BatchNormalization')
+  local prs = model.cnet:findModules('nn.PReLU')
+  local bi = 0
+  for i, l in ipairs(class_layers) do
+    push(lin[i][W]); push(lin[i][B])
+    if l.batch_norm then
+      bi = bi + 1
+      local bn = bns[bi]
+      push(bn[W]); push(bn[B])
+      if grads then
+        -- running statistics are not parameters in Torch: their gradient slots are never written by the library
+        model.b200.bn_dummy = model.b200.bn_dummy or torch.CudaTensor(bn.running_mean:nElement()):zero()
+        push(model.b200.bn_dummy); push(model.b200.bn_dummy)
+      else
+        push(bn.running_mean); push(bn.running_var)
+      end
+    end
+    push(prs[i][W])
+  end
+  -- the two output branches: Linear(n, 4) and Linear(n, classes) (model_utilities.lua:96-104)
+  local reg, cls = lin[#class_layers + 1], lin[#class_layers + 2]
+  if reg.weight:size(1) ~= 4 then reg, cls = cls, reg end
+  push(reg[W]); push(reg[B]); push(cls[W]); push(cls[B])
+  return list
+end
+
+-- Builds the plan from the model table alone and binds device pointers of the learnable tensors -- views into the
+-- flat CudaTensor created by combine_and_flatten_parameters (utilities.lua:136-147), so optimiser updates (main.lua:133)
+-- are seen after the next M.pack(model) -- then installs the module-slot overrides (M.install) so that the reference's
+-- objective.lua and Detector.lua run UNMODIFIED on the accelerated model.  Call after load_model (main.lua:114).
 function M.accelerate(model, anchor_nets, class_layers)
   local cfg, layers = model.cfg, model.layers
-  anchor_nets = anchor_nets or model.anchor_nets
-  class_layers = class_layers or model.class_layers
-  assert(anchor_nets and class_layers, 'pass the anchor_nets / class_layers tables of models/vgg_*.lua')
+  local n_out = #model.pnet.outnode.children
+  anchor_nets = anchor_nets or model.anchor_nets or derive_anchor_nets(model.pnet, trunk_blocks(model.pnet, n_out - 1))
+  class_layers = class_layers or model.class_layers or derive_class_layers(model.cnet)
   local ctx = M.create()
   local nb, nh, nf = #layers, #anchor_nets, #class_layers
   local blocks = ffi.new('frcnn_block_desc[?]', nb)
@@ -82,42 +163,150 @@ function M.accelerate(model, anchor_nets, class_layers)
   local scales = ffi.new('double[?]', #cfg.scales, cfg.scales)
   check(ctx, C.frcnn_model_plan(ctx, blocks, nb, heads, nh, fcs, nf, cfg.class_count, cfg.roi_pooling.kh, cfg.roi_pooling.kw,
                                 scales, #cfg.scales, -1))
-  -- parameter pointers in the library's bind order (frcnn_param_info): trunk convs, heads, cnet
-  local ptrs = {}
-  for _, seq in ipairs(trunk_blocks(model.pnet, nh)) do
-    local convs, prelus = seq:findModules('nn.SpatialConvolution'), seq:findModules('nn.PReLU')
-    for i = 1, #convs do
-      ptrs[#ptrs + 1] = dev_ptr(convs[i].weight); ptrs[#ptrs + 1] = dev_ptr(convs[i].bias); ptrs[#ptrs + 1] = dev_ptr(prelus[i].weight)
-    end
-  end
-  for i = 1, nh do
-    local seq = model.pnet.outnode.children[i].data.module   -- AnchorNetwork Sequential (model_utilities.lua:29-35)
-    local c1, pr, c2 = seq.modules[1], seq.modules[2], seq.modules[3]
-    for _, t in ipairs{c1.weight, c1.bias, pr.weight, c2.weight, c2.bias} do ptrs[#ptrs + 1] = dev_ptr(t) end
-  end
-  local lin = model.cnet:findModules('nn.Linear')
-  local bns = model.cnet:findModules('nn.BatchNormalization')
-  local prs = model.cnet:findModules('nn.PReLU')
-  local bi = 0
-  for i, l in ipairs(class_layers) do
-    ptrs[#ptrs + 1] = dev_ptr(lin[i].weight); ptrs[#ptrs + 1] = dev_ptr(lin[i].bias)
-    if l.batch_norm then
-      bi = bi + 1
-      local bn = bns[bi]
-      for _, t in ipairs{bn.weight, bn.bias, bn.running_mean, bn.running_var} do ptrs[#ptrs + 1] = dev_ptr(t) end
-    end
-    ptrs[#ptrs + 1] = dev_ptr(prs[i].weight)
-  end
-  -- the two output branches: Linear(n, 4) and Linear(n, classes) (model_utilities.lua:96-104)
-  local reg, cls = lin[nf + 1], lin[nf + 2]
-  if reg.weight:size(1) ~= 4 then reg, cls = cls, reg end
-  for _, t in ipairs{reg.weight, reg.bias, cls.weight, cls.bias} do ptrs[#ptrs + 1] = dev_ptr(t) end
-  assert(#ptrs == C.frcnn_param_count(ctx), 'parameter walk does not match the plan')
-  local arr = ffi.new('const float*[?]', #ptrs, ptrs)
-  check(ctx, C.frcnn_bind_params(ctx, arr, #ptrs))
-  model.b200 = { ctx = ctx, n_heads = nh }
+  model.b200 = { ctx = ctx, n_heads = nh, anchor_nets = anchor_nets, class_layers = class_layers }
+  local tensors = walk_params(model, anchor_nets, class_layers, false)
+  assert(#tensors == C.frcnn_param_count(ctx), 'parameter walk does not match the plan')
+  local arr = ffi.new('const float*[?]', #tensors)
+  for i, t in ipairs(tensors) do arr[i - 1] = dev_ptr(t) end
+  check(ctx, C.frcnn_bind_params(ctx, arr, #tensors))
   M.pack(model)
+  M.bind_grads(model)
+  M.install(model)
   return model
+end
+
+-- Binds the flat gradient views: the same walk over gradWeight / gradBias (views into the flat `gradient` CudaTensor of
+-- combine_and_flatten_parameters, main.lua:92).
+function M.bind_grads(model)
+  local ctx = model.b200.ctx
+  local tensors = walk_params(model, model.b200.anchor_nets, model.b200.class_layers, true)
+  local arr = ffi.new('float*[?]', #tensors)
+  for i, t in ipairs(tensors) do arr[i - 1] = dev_ptr_rw(t) end
+  check(ctx, C.frcnn_bind_grads(ctx, arr, #tensors))
+end
+
+-- Module-slot overrides.  nn modules are tables whose methods live in the class metatable, so an instance field shadows
+-- the class method: after this, pnet:forward / pnet:backward / cnet:forward / cnet:backward of THIS model run in the
+-- library, with the call shapes objective.lua:71,164,179,189 and Detector.lua:33,101 use.  :training() / :evaluate() stay
+-- nn.Module's (they set self.train, which selects the mode here); :cuda(), :parameters() are untouched.
+function M.install(model)
+  local ctx, nh = model.b200.ctx, model.b200.n_heads
+  local pnet, cnet = model.pnet, model.cnet
+  local dims = ffi.new('int[?]', 3 * (nh + 1))
+  local optrs = ffi.new('float*[?]', nh + 1)
+  local dptrs = ffi.new('const float*[?]', nh + 1)
+  local step = 0
+
+  pnet.forward = function(self, img)                            -- objective.lua:71, Detector.lua:33: img is a 3-D CudaTensor
+    local x = img:contiguous()
+    local h, w = x:size(2), x:size(3)
+    check(ctx, C.frcnn_pnet_output_dims(ctx, h, w, dims))
+    self.output = type(self.output) == 'table' and self.output or {}
+    for i = 0, nh do
+      self.output[i + 1] = self.output[i + 1] or torch.CudaTensor()
+      self.output[i + 1]:resize(dims[3 * i], dims[3 * i + 1], dims[3 * i + 2])
+      optrs[i] = self.output[i + 1]:data()
+    end
+    if self.train then
+      -- fresh SpatialDropout masks every call: the seed comes from Torch's global generator, as nn.SpatialDropout's does
+      step = step + 1
+      check(ctx, C.frcnn_pnet_forward_train(ctx, x:data(), 1, h, w, optrs, nil, torch.random()))
+      self.b200_input = x                                       -- pnet:backward re-reads the frame (first-layer wgrad)
+    else
+      check(ctx, C.frcnn_pnet_forward(ctx, x:data(), 1, h, w, optrs))
+    end
+    return self.output
+  end
+  pnet.updateOutput = pnet.forward
+
+  pnet.backward = function(self, img, delta_outputs)            -- objective.lua:189; the returned gradInput is unused there
+    for i = 0, nh do
+      local d = delta_outputs[i + 1]
+      dptrs[i] = d and d:contiguous():data() or nil
+    end
+    check(ctx, C.frcnn_pnet_backward(ctx, dptrs))
+    self.gradInput = self.gradInput or torch.CudaTensor()
+    return self.gradInput
+  end
+
+  cnet.forward = function(self, cinput)                         -- objective.lua:164, Detector.lua:101: R x (kh*kw*C)
+    local x = cinput:contiguous()
+    local R = x:size(1)
+    self.output = type(self.output) == 'table' and self.output or {}
+    self.output[1] = (self.output[1] or torch.CudaTensor()):resize(R, 4)
+    self.output[2] = (self.output[2] or torch.CudaTensor()):resize(R, model.cfg.class_count + 1)
+    if self.train then
+      check(ctx, C.frcnn_cnet_forward_train(ctx, x:data(), R, nil, torch.random(), self.output[1]:data(), self.output[2]:data()))
+    else
+      check(ctx, C.frcnn_cnet_forward(ctx, x:data(), R, self.output[1]:data(), self.output[2]:data()))
+    end
+    return self.output
+  end
+  cnet.updateOutput = cnet.forward
+
+  cnet.backward = function(self, cinput, deltas)                -- objective.lua:179: { crdelta, ccdelta } -> post_roi_delta
+    self.gradInput = (torch.isTensor(self.gradInput) and self.gradInput or torch.CudaTensor()):resize(cinput:size())
+    check(ctx, C.frcnn_cnet_backward(ctx, deltas[1]:contiguous():data(), deltas[2]:contiguous():data(), self.gradInput:data()))
+    return self.gradInput
+  end
+  return model
+end
+
+-- Drop-in for the global create_objective (objective.lua:15): same arguments, same returned closure
+-- lossAndGradient(w) -> loss, gradient, same statistics appended to `stats` -- but the per-image loop body
+-- (objective.lua:65-198: criteria per anchor, ROI pooling per example, cnet, pnet:backward) is ONE frcnn_train_batch call
+-- per group of equally sized frames.  Use: `create_objective = require('frcnn_b200').create_objective` before main.lua:120.
+function M.create_objective(model, weights, gradient, batch_iterator, stats)
+  local ctx = model.b200.ctx
+  local step = 0
+  local function cleanAnchors(examples, dims)                   -- objective.lua:32-43
+    local i = 1
+    while i <= #examples do
+      local a = examples[i][1]
+      if a.index[2] > dims[3 * (a.layer - 1) + 1] or a.index[3] > dims[3 * (a.layer - 1) + 2] then table.remove(examples, i) else i = i + 1 end
+    end
+  end
+  local dims = ffi.new('int[?]', 3 * (model.b200.n_heads + 1))
+  return function(w)
+    if w ~= weights then weights:copy(w) end
+    M.pack(model)                                               -- the optimiser has moved the weights since the last call
+    gradient:zero()
+    step = step + 1
+    local batch = batch_iterator:nextTraining()
+    local groups, order = {}, {}
+    for i, x in ipairs(batch) do                                -- frames of one size share a frcnn_train_batch call
+      local key = x.img:size(2) .. 'x' .. x.img:size(3)
+      if not groups[key] then groups[key] = {}; order[#order + 1] = key end
+      table.insert(groups[key], x)
+    end
+    local cls_loss, reg_loss, creg_loss, ccls_loss = 0, 0, 0, 0
+    local cls_count, reg_count, ccls_count = 0, 0, 0
+    for _, key in ipairs(order) do
+      local g = groups[key]
+      local n, h, w_ = #g, g[1].img:size(2), g[1].img:size(3)
+      check(ctx, C.frcnn_pnet_output_dims(ctx, h, w_, dims))
+      local imgs = torch.CudaTensor(n, 3, h, w_)
+      for i, x in ipairs(g) do
+        imgs[i]:copy(x.img)                                     -- objective.lua:66: x.img:cuda()
+        cleanAnchors(x.positive, dims); cleanAnchors(x.negative, dims)
+      end
+      local losses = M.train_batch(model, imgs, g, step)
+      for i, x in ipairs(g) do
+        cls_loss, reg_loss = cls_loss + losses[4 * i - 4], reg_loss + losses[4 * i - 3]
+        creg_loss, ccls_loss = creg_loss + losses[4 * i - 2], ccls_loss + losses[4 * i - 1]
+        reg_count = reg_count + #x.positive
+        cls_count = cls_count + #x.positive + #x.negative
+        ccls_count = ccls_count + 1
+      end
+    end
+    gradient:div(cls_count)                                     -- objective.lua:200
+    local pcls, preg = cls_loss / cls_count, reg_loss / reg_count
+    local dcls, dreg = ccls_loss / ccls_count, creg_loss / reg_count
+    print(string.format('prop: cls: %f (%d), reg: %f (%d); det: cls: %f, reg: %f', pcls, cls_count, preg, reg_count, dcls, dreg))
+    table.insert(stats.pcls, pcls); table.insert(stats.preg, preg)
+    table.insert(stats.dcls, dcls); table.insert(stats.dreg, dreg)
+    return pcls + preg, gradient
+  end
 end
 
 -- Call after every optimiser step / weights:copy (main.lua:97,133): re-packs fp32 -> bf16 tensor-core layouts.
@@ -142,14 +331,6 @@ function M.pnet_forward(model, img)
 end
 
 -- ---------------------------------------------------------------------------------------------- training
--- Binds the flat gradient views (same walk as accelerate, but over gradWeight / gradBias).  Call once after
--- combine_and_flatten_parameters (main.lua:92).
-function M.bind_grads(model, grad_ptrs)
-  local ctx = model.b200.ctx
-  local arr = ffi.new('float*[?]', #grad_ptrs, grad_ptrs)
-  check(ctx, C.frcnn_bind_grads(ctx, arr, #grad_ptrs))
-end
-
 -- The body of the per-image loop of lossAndGradient (objective.lua:65-198) as ONE call: positives = { {anchor, roi}, ... },
 -- negatives = { {anchor}, ... } exactly as BatchIterator:nextTraining yields them (after cleanAnchors).
 -- Returns cls_loss, reg_loss, creg_loss, ccls_loss of the frame; gradients accumulate in the flat gradient tensor.
@@ -174,6 +355,58 @@ function M.train_image(model, img, positives, negatives, seed)
   check(ctx, C.frcnn_train_image(ctx, img:data(), img:size(2), img:size(3), pos, #positives, neg, #negatives, nil, nil,
                                  seed or 0, losses))
   return losses[0], losses[1], losses[2], losses[3]
+end
+
+-- The same for a group of equally sized frames (frcnn_train_batch): imgs is an n x 3 x h x w CudaTensor, items[i] =
+-- { positive = {...}, negative = {...} } as BatchIterator:nextTraining yields them (cleaned).  Dropout seeds are drawn
+-- from Torch's global generator.  Returns a 0-based float[4 n] cdata: {cls, reg, creg, ccls} loss sums per frame.
+local function fill_example(e, anchor, roi)
+  e.anchor[0], e.anchor[1], e.anchor[2], e.anchor[3] = anchor.minX, anchor.minY, anchor.maxX, anchor.maxY
+  e.layer, e.aspect, e.y, e.x = anchor.layer, anchor.aspect, anchor.index[2], anchor.index[3]
+  if roi then
+    local r = roi.rect
+    e.roi[0], e.roi[1], e.roi[2], e.roi[3] = r.minX, r.minY, r.maxX, r.maxY
+    local t = Anchors.inputToAnchor(anchor, r)            -- FloatTensor(4), objective.lua:110
+    for k = 0, 3 do e.reg_target[k] = t[k + 1] end
+    e.class_index = roi.class_index
+  end
+end
+function M.train_batch(model, imgs, items, step)
+  local ctx, n = model.b200.ctx, #items
+  local pos_arr, neg_arr, keep = ffi.new('const frcnn_example*[?]', n), ffi.new('const frcnn_example*[?]', n), {}
+  local n_pos, n_neg, seeds = ffi.new('int[?]', n), ffi.new('int[?]', n), ffi.new('uint64_t[?]', n)
+  for i, x in ipairs(items) do
+    local pos = ffi.new('frcnn_example[?]', math.max(#x.positive, 1))
+    local neg = ffi.new('frcnn_example[?]', math.max(#x.negative, 1))
+    for k, ex in ipairs(x.positive) do fill_example(pos[k - 1], ex[1], ex[2]) end
+    for k, ex in ipairs(x.negative) do fill_example(neg[k - 1], ex[1], nil) end
+    keep[#keep + 1] = pos; keep[#keep + 1] = neg               -- keep the cdata alive across the call
+    pos_arr[i - 1], neg_arr[i - 1] = pos, neg
+    n_pos[i - 1], n_neg[i - 1] = #x.positive, #x.negative
+    seeds[i - 1] = torch.random()
+  end
+  local losses = ffi.new('float[?]', 4 * n)
+  check(ctx, C.frcnn_train_batch(ctx, imgs:data(), n, imgs:size(3), imgs:size(4), pos_arr, n_pos, neg_arr, n_neg, nil, seeds, losses))
+  return losses
+end
+
+-- Data-parallel training inside ONE LuaJIT process (main.lua:52 drives one device; here: one accelerated model per
+-- device): models = { model_on_gpu1, model_on_gpu2, ... }.  dp_init forms the NCCL communicator over their contexts,
+-- dp_allreduce sums the flat gradients (bound with bind_grads) and the given per-model counter tensors in place.
+function M.dp_init(models)
+  local n = #models
+  local ctxs = ffi.new('frcnn_ctx*[?]', n)
+  for i, m in ipairs(models) do ctxs[i - 1] = m.b200.ctx end
+  check(models[1].b200.ctx, C.frcnn_dp_init_all(ctxs, n))
+end
+function M.dp_allreduce(models, counters)       -- counters: optional list of small CudaTensors, one per model
+  local n = #models
+  local ctxs, ptrs = ffi.new('frcnn_ctx*[?]', n), ffi.new('float*[?]', n)
+  for i, m in ipairs(models) do
+    ctxs[i - 1] = m.b200.ctx
+    ptrs[i - 1] = counters and counters[i]:data() or nil
+  end
+  check(models[1].b200.ctx, C.frcnn_dp_allreduce(ctxs, n, counters and ptrs or nil, counters and counters[1]:nElement() or 0))
 end
 
 -- Anchors:findPositive (Anchors.lua:147-195) as one launch.  `anchors` is the reference's own Anchors object (its :get

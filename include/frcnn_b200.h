@@ -121,6 +121,10 @@ int frcnn_localizer_layers(const frcnn_ctx* ctx, int which, int* layers6, int ca
 int frcnn_input_to_feature_rect(const frcnn_ctx* ctx, int which, const double rect[4], double out[4]);
 /* Localizer:featureToInputRect (Localizer.lua:69-79) */
 int frcnn_feature_to_input_rect(const frcnn_ctx* ctx, int which, const double rect[4], double out[4]);
+/* The same with the Lua methods' optional `layer_index` argument (Localizer.lua:41-42,69-70): only the first
+ * layer_index layers of the localizer take part; 0 (or the layer count) = all. */
+int frcnn_input_to_feature_rect_upto(const frcnn_ctx* ctx, int which, int layer_index, const double rect[4], double out[4]);
+int frcnn_feature_to_input_rect_upto(const frcnn_ctx* ctx, int which, int layer_index, const double rect[4], double out[4]);
 /* Anchors.__init LUTs (Anchors.lua:15-57): w_lut/h_lut are [n_scales][3][200][2] fp32 */
 int frcnn_anchors_build(frcnn_ctx* ctx, float* w_lut_host, float* h_lut_host);
 

@@ -74,6 +74,26 @@ def stage_report(got_inter, got_winners, want_inter, want_winners):
         box_rel = max(box_rel, float(np.max(np.abs(np.array(a["r2"].unpack()) - np.array(b["r2"].unpack()))) / size))
         conf_abs = max(conf_abs, abs(float(a["confidence"]) - float(b["confidence"])))
     # winners that agree on the anchor but not on the class
+    # geometric agreement (independent of WHICH anchor of a cluster survived the bottom-edge-ordered greedy NMS): share of
+    # the fp32 winners that have a CUDA winner of the same class overlapping them with IoU >= 0.7, and vice versa
+    def iou(a, b):  # Rect.lua:126-141 on the unpacked corners (the two sides carry different Rect classes)
+        ax0, ay0, ax1, ay1 = a.unpack()
+        bx0, by0, bx1, by1 = b.unpack()
+        w, h = min(ax1, bx1) - max(ax0, bx0), min(ay1, by1) - max(ay0, by0)
+        i = w * h if w > 0 and h > 0 else 0.0
+        u = (ax1 - ax0) * (ay1 - ay0) + (bx1 - bx0) * (by1 - by0) - i
+        return i / u if u > 0 else 0.0
+
+    def covered(src, dst):
+        n = 0
+        for k, a in src.items():
+            for k2, b in dst.items():
+                if k2[0] == k[0] and iou(a["r2"], b["r2"]) >= 0.7:
+                    n += 1
+                    break
+        return n
+    cov_w = covered(ww, gw) / max(len(ww), 1) if ww else 1.0
+    cov_g = covered(gw, ww) / max(len(gw), 1) if gw else 1.0
     ga = {k[1:]: k[0] for k in gw}
     wa = {k[1:]: k[0] for k in ww}
     class_flips = sum(1 for k in set(ga) & set(wa) if ga[k] != wa[k])
@@ -81,7 +101,7 @@ def stage_report(got_inter, got_winners, want_inter, want_winners):
                 candidates=dict(cuda=len(gc), fp32=len(wc), jaccard=jaccard(gc, wc)),
                 winners=dict(cuda=len(gw), fp32=len(ww), common=len(common), jaccard=jaccard(gw, ww),
                              class_flips_on_common_anchor=class_flips, r2_max_rel_to_box=box_rel,
-                             confidence_max_abs=conf_abs))
+                             confidence_max_abs=conf_abs, fp32_covered_by_cuda=cov_w, cuda_covered_by_fp32=cov_g))
 
 
 def precision_report(desc, cfg, params, img, cuda_maps, cuda_winners, fp32_result=None, quant=None):

@@ -78,6 +78,10 @@ def test_host_geometry_equals_oracle(F, which):
         assert loc.inputToFeatureRect(F.Rect(*r)).unpack() == oloc.inputToFeatureRect(ORect(*r)).unpack()
         q = tuple(float(v) for v in rng.integers(0, 60, 4))
         assert loc.featureToInputRect(*q).unpack() == oloc.featureToInputRect(*q).unpack()
+        # the optional layer_index argument (Localizer.lua:41-42,69-70): only the first k layers take part
+        k = int(rng.integers(1, len(loc.layers) + 1))
+        assert loc.inputToFeatureRect(F.Rect(*r), k).unpack() == oloc.inputToFeatureRect(ORect(*r), k).unpack()
+        assert loc.featureToInputRect(*q, layer_index=k).unpack() == oloc.featureToInputRect(*q, layer_index=k).unpack()
     r = a.get(2, 3, 4, 5)
     o = oa.get(2, 3, 4, 5)
     assert r.unpack() == o.unpack() and r.index == o.index
@@ -129,3 +133,49 @@ def test_example_record_layout_matches_header():
     for name in ("anchor", "roi", "reg_target", "layer", "aspect", "y", "x", "class_index"):
         assert dt.fields[name][1] == ffi.offsetof("frcnn_example", name), name
     assert ffi.sizeof("frcnn_anchor_ref") == 16
+
+
+def test_lua_glue_binds_only_declared_symbols_with_the_declared_arity():
+    """The LuaJIT glue cannot run here (no Lua in the image), so it is checked statically against the header it cdef's:
+    every C.frcnn_* call names a declared function and passes as many arguments as the declaration has parameters; every
+    enum constant it reads exists."""
+    import glob
+    import os
+    import re
+    from frcnn_b200._lib import header_cdef
+    cdef = header_cdef()
+    decl = {}
+    for m in re.finditer(r"\b(?:int|int64_t|const char\*)\s+(frcnn_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", cdef, flags=re.S):
+        args = m.group(2).strip()
+        decl[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",")])
+    consts = set(re.findall(r"\b(FRCNN_[A-Z0-9_]+)\b", cdef))
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "faster-rcnn.torch_b200", "lua")
+    files = sorted(glob.glob(os.path.join(root, "*.lua")))
+    assert len(files) >= 3
+    calls = 0
+    for path in files:
+        src = open(path).read()
+        src = re.sub(r"--[^\n]*", "", src)  # comments
+        for m in re.finditer(r"\bC\.(FRCNN_[A-Z0-9_]+)", src):
+            assert m.group(1) in consts, (path, m.group(1))
+        for m in re.finditer(r"\bC\.(frcnn_[a-z0-9_]+)\s*(\()?", src):
+            name = m.group(1)
+            assert name in decl, "%s uses undeclared %s" % (os.path.basename(path), name)
+            if not m.group(2):
+                continue  # passed as a value (ffi.gc finaliser)
+            depth, i, n_args, any_arg = 1, m.end(), 1, False
+            while depth > 0:
+                ch = src[i]
+                if ch in "([{":
+                    depth += 1
+                elif ch in ")]}":
+                    depth -= 1
+                elif ch == "," and depth == 1:
+                    n_args += 1
+                if depth > 0 and not ch.isspace():
+                    any_arg = True
+                i += 1
+            n = n_args if any_arg else 0
+            assert n == decl[name], "%s: %s called with %d arguments, declared with %d" % (os.path.basename(path), name, n, decl[name])
+            calls += 1
+    assert calls >= 25
