@@ -136,7 +136,7 @@ struct frcnn_ctx {
   float thr_nms1 = 0.25f, thr_nms2 = 0.1f;
 
   // activation workspace for (N, H, W)
-  int ws_n = 0, ws_h = 0, ws_w = 0;
+  int ws_n = 0, ws_h = 0, ws_w = 0, ws_sched = -1;
   std::vector<void*> ws_allocs;
   std::vector<bf16*> pool_out;   // per block
   std::vector<int> pool_h, pool_w;
@@ -521,7 +521,8 @@ static void do_pack(frcnn_ctx* c) {
 
 // (re)builds the activation workspace and the prepared conv launches for an (N, H, W) input
 static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
-  if (c->ws_n == N && c->ws_h == H && c->ws_w == W) return;
+  if (c->ws_n == N && c->ws_h == H && c->ws_w == W && c->ws_sched == c->schedule) return;
+  c->ws_sched = c->schedule;   // the throughput schedule picks the trunk kernels by SM-time (conv_prepare, force_mt = -1)
   FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
   free_all(c->ws_allocs);
   free_all(c->tws_allocs);
@@ -552,7 +553,7 @@ static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
       } else {
         cv.in = cur;
         conv_prepare(&cv.launch, cur, cv.w_packed, N, h, w, cv.cin, cv.cout, cv.k, cv.k, cv.pad, cv.pad, mode, cv.out,
-                     c->sm_count, 0, 0, 0, 2);
+                     c->sm_count, 0, 0, c->schedule == FRCNN_SCHED_THROUGHPUT ? -1 : 0, 2);
       }
       cv.launch.p.scale = cv.scale;
       cur = cv.out;
@@ -617,6 +618,12 @@ static void ensure_pnet_workspace(frcnn_ctx* c, int N, int H, int W) {
         c->head_plan.sched.counters[i] = (int*)dev_alloc(c->ws_allocs, counter_ints[i] * sizeof(int));
         FRCNN_CUDA_TRY(cudaMemsetAsync(c->head_plan.sched.counters[i], 0, counter_ints[i] * sizeof(int), c->stream));
       }
+    }
+    c->head_plan.sched.trace = nullptr;
+    if (getenv("FRCNN_HEAD_TRACE")) {   // measurement only: per-unit globaltimer stamps, dumped after every launch
+      const size_t bytes = (size_t)c->head_plan.grid * 64 * sizeof(unsigned long long);
+      c->head_plan.sched.trace = (unsigned long long*)dev_alloc(c->ws_allocs, bytes);
+      FRCNN_CUDA_TRY(cudaMemsetAsync(c->head_plan.sched.trace, 0, bytes, c->stream));
     }
     FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));   // `units` / `cta_off` are stack vectors
   }
@@ -749,7 +756,17 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
       cudaEventRecord(c->conv_ev[c->conv_ev_used], c->stream);
     }
     conv_launch_heads(hp, c->stream);
-    ++c->launches;
+    c->launches += hp.fix.n > 0 ? 2 : 1;   // + head_fixup_kernel when a head's reduction is split
+    if (hp.sched.trace) {
+      std::vector<unsigned long long> t((size_t)hp.grid * 64);
+      FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+      FRCNN_CUDA_TRY(cudaMemcpy(t.data(), hp.sched.trace, t.size() * 8, cudaMemcpyDeviceToHost));
+      FRCNN_CUDA_TRY(cudaMemset(hp.sched.trace, 0, t.size() * 8));
+      if (FILE* f = fopen(getenv("FRCNN_HEAD_TRACE"), "wb")) {
+        fwrite(t.data(), 8, t.size(), f);
+        fclose(f);
+      }
+    }
     if (prof) {
       cudaEventRecord(c->conv_ev[c->conv_ev_used + 1], c->stream);
       c->conv_ev_used += 2;

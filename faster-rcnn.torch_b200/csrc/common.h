@@ -148,12 +148,22 @@ struct HeadSched {
   float* slices[MAX_GROUP];    // per head: [image][tile][slice][128][256] fp32 partial sums (split heads only)
   int* counters[MAX_GROUP];    // per head: [image][tile] arrivals; zero between launches
   int tiles[MAX_GROUP];        // tiles per image
+  unsigned long long* trace;   // measurement only (FRCNN_HEAD_TRACE): [cta][8 units][8] globaltimer stamps; nullptr = off
+};
+// head_fixup_kernel: the anchor networks whose reduction conv_head_kernel split by filter rows (slices summed in ascending
+// order + bias + PReLU + 1 x 1 conv).  Block b of head i handles 32 positions of tile b / 4.
+struct HeadFixArgs {
+  int n;                       // split heads
+  int head[MAX_GROUP];         // index into the ConvGroup
+  int nsl[MAX_GROUP];          // slices per tile
+  int block_end[MAX_GROUP];    // running block count
 };
 // Builds the launch state of the fused anchor-network kernel for N frames of in_h x in_w (per head) and runs it.
 struct HeadPlan {
   ConvMaps maps;
   ConvGroup grp;
   HeadSched sched;
+  HeadFixArgs fix;
   int grid = 0;
   int n_units = 0;
   double flops = 0.0;

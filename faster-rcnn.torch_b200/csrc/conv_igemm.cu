@@ -1058,33 +1058,50 @@ __global__ void __launch_bounds__(CONV_THREADS, OCC)
 // The four AnchorNetworks (model_utilities.lua:29-35: k x k valid conv to 256 channels -> PReLU -> 1 x 1 conv to 18) of a
 // frame in ONE launch, fused down to the 18-channel maps Detector.lua:47-49 reads.  What the halo-kernel version lost
 // (profiles/r1b_ncu_full_b1.md: 136 us, 0.13 of the tensor peak, 88 CTAs): 8 x 16 pixel tiles on 23..27-row maps waste
-// 16-34 % of every MMA; one CTA per tile makes the 7 x 7 head's 18 816-deep reduction a 78-135 us critical path.
+// 16-34 % of every MMA; one CTA per tile makes the 7 x 7 head's 18 816-deep reduction a 78-135 us critical path; and
+// every CTA streams the whole 256-filter weight tensor of its head through its SM's L2 port (32 KB per 512 MMA clocks =
+// 64 B/clk against the ~42 B/clk an SM gets when all 148 pull: the MMA phase ran at half speed).
 //   * LINEAR tiles: the input map is the 2-D matrix [N*Hin*Win pixels][Cin] and a tile is 128 CONSECUTIVE pixel positions
 //     p = y*Win + x.  For filter row kh the A operand of ALL kw taps is one slab of 128 + k - 1 consecutive rows starting at
 //     p0 + kh*Win (one TMA box {64 ch, 136 rows}); tap kw is the same slab read from row kw on (UMMA descriptor start
 //     + kw*128 B, canonical 8-row groups).  Positions whose window wraps around the row end (x > Win - k) produce
 //     garbage that is never stored: 4-12 % waste instead of 16-34 %.
-//   * K SPLIT BY FILTER ROWS with an in-kernel fix-up: a unit is (head, image, tile, kh range).  Split units write their
-//     fp32 partial sums [128][256] to a slice in L2; the unit that arrives LAST at the tile's counter sums the slices in
-//     ascending order (fixed order: the result does not depend on who is last), applies bias + PReLU + the 1 x 1 conv and
-//     stores.  Units are dealt to the persistent CTAs by a host-side longest-processing-time schedule.
-// Warp roles / pipeline as conv_halo_kernel: TMA producer, single-thread MMA issuer (M128 x N256 x K16), two
-// accumulator stages in TMEM, eight epilogue warps.
+//   * CTA PAIRS (cta_group::2, cluster {2,1,1}): a pair computes two neighbouring tiles with M = 256 MMAs; each CTA loads
+//     its own slab but only HALF of every weight box (128 of the 256 filters, 16 KB), the tensor core reads the other half
+//     from the peer's shared memory: weight ingress per SM halved.
+//   * K SPLIT BY FILTER ROWS with an in-kernel fix-up: a unit is (head, image, tile pair, kh range).  Split units write their
+//     fp32 partial sums to a slice in L2 ([column group of 4][128 rows][4]: a warp stores / loads 512 contiguous bytes); the
+//     CTA that arrives LAST at its tile's counter sums the slices in ascending order (fixed order: the result does not
+//     depend on who is last), applies bias + PReLU + the 1 x 1 conv and stores.  Units are dealt to the persistent pairs
+//     by a host-side longest-processing-time schedule.
+// Warp roles as conv_pair_kernel: TMA producer (both CTAs), single-thread MMA issuer (leader CTA, M256 x N256 x K16), two
+// accumulator stages in TMEM, eight epilogue warps per CTA.
 static constexpr int HEADK_SLAB_ROWS = 136;                                  // 128 + (7 - 1), padded to a multiple of 8
 static constexpr int HEADK_A_SLOT = HEADK_SLAB_ROWS * 128;                   // 17 408 B = 17 KB
-static constexpr int HEADK_A_SLOTS = 3, HEADK_B_SLOTS = 4;
-static constexpr int HEADK_B_SLOT = HEAD_CM * 128;                           // 32 KB
+static constexpr int HEADK_A_SLOTS = 3, HEADK_B_SLOTS = 8;
+static constexpr int HEADK_B_SLOT = (HEAD_CM / 2) * 128;                     // half a weight box: 128 filters x 128 B = 16 KB
 static constexpr int HEADK_SMEM = HEADK_A_SLOTS * HEADK_A_SLOT + HEADK_B_SLOTS * HEADK_B_SLOT + HEAD_SMEM + MAX_BIAS * 4 + 512 + 1024;
+static constexpr int HEADK_MAX_SLICES = HEAD_MAXK;                           // one slice per filter row at most
+static_assert(HEADK_SMEM <= 227 * 1024, "anchor-network kernel: shared memory");
+static_assert((2 * HEADK_A_SLOTS + 2 * HEADK_B_SLOTS + 4) * 8 + 8 <= 512, "anchor-network kernel: mbarrier area");
 
 __device__ __forceinline__ void headk_decode(const int4 u, int& head, int& s, int& nsl, int& img, int& tile, int& kh0, int& kh1) {
   head = u.x & 0xff; s = (u.x >> 8) & 0xff; nsl = (u.x >> 16) & 0xff;
   img = u.y; tile = u.z; kh0 = u.w & 0xff; kh1 = (u.w >> 8) & 0xff;
 }
 
+__device__ __forceinline__ unsigned long long headk_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define HEADK_TRACE(ui, k, v) \
+  do { if (hs.trace && (ui) - u_begin < 8) hs.trace[((size_t)blockIdx.x * 8 + ((ui) - u_begin)) * 8 + (k)] = (v); } while (0)
+
 __global__ void __launch_bounds__(CONV_THREADS, 1)
     conv_head_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGroup grp, const HeadSched hs) {
   constexpr int BN = HEAD_CM;
-  constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BN);
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(2 * BLOCK_M, BN);          // M = 256 over the pair
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -1103,7 +1120,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int u_begin = hs.cta_off[blockIdx.x], u_end = hs.cta_off[blockIdx.x + 1];
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int u_begin = hs.cta_off[pair], u_end = hs.cta_off[pair + 1];
+  if (threadIdx.x == 0 && hs.trace) hs.trace[((size_t)blockIdx.x * 8 + 7) * 8 + 7] = headk_now();
 
   if (warp == 0 && lane == 0) {
     for (int g = 0; g < grp.n; ++g) {
@@ -1122,24 +1143,27 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full[a], 1);
-      ptx::mbar_init(&tmem_empty[a], EPI_THREADS / 32);
+      ptx::mbar_init(&tmem_empty[a], 2 * (EPI_THREADS / 32));   // the epilogue warps of BOTH CTAs (used in the leader only)
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_base_slot, 512);
-    ptx::tmem_relinquish();
+    ptx::tmem_alloc_2cta(tmem_base_slot, 512);
+    ptx::tmem_relinquish_2cta();
   }
   ptx::tc_fence_before();
   __syncthreads();
+  ptx::cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them remotely
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer: per (kh, chunk) step one slab + k weight boxes.
-    // The slab of step i + 1 goes out BEFORE the weight boxes of step i (its own cursor, one step ahead): otherwise it
-    // would queue behind weight boxes that wait for ring slots, and every step would start with an exposed load latency.
+    // ------------------------------------------------------------ TMA producer (both CTAs): per (kh, chunk) step the CTA's
+    // own slab + its half of k weight boxes.  The slab of step i + 1 goes out BEFORE the weight boxes of step i (its own
+    // cursor, one step ahead): otherwise it would queue behind weight boxes that wait for ring slots.
     if (lane == 0) {
+      const uint32_t full_a_leader = ptx::mapa_shared(ptx::smem_u32(full_a), 0);
+      const uint32_t full_b_leader = ptx::mapa_shared(ptx::smem_u32(full_b), 0);
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int a_ui = u_begin, a_kh = -1, a_c = 0;   // cursor of the slab ring
@@ -1151,9 +1175,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
           if (a_kh < 0) { a_kh = kh0; a_c = 0; }
           if (a_kh >= kh1) { ++a_ui; a_kh = -1; continue; }
           ptx::mbar_wait(&empty_a[as], aph ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_a[as], HEADK_A_SLOT);
-          ptx::tma_load_2d(smem_a + as * HEADK_A_SLOT, &maps.a[g], &full_a[as], a_c * BLOCK_K,
-                           img * p.Hin * p.Win + tile * BLOCK_M + a_kh * p.Win);
+          if (leader) ptx::mbar_arrive_expect_tx(&full_a[as], 2 * HEADK_A_SLOT);
+          // rows past the end of the map (the odd tile of a pair, the last slab rows) are zero-filled by the TMA unit
+          ptx::tma_load_2d_2sm(smem_a + as * HEADK_A_SLOT, &maps.a[g], full_a_leader + (uint32_t)as * 8u, a_c * BLOCK_K,
+                               img * p.Hin * p.Win + (2 * tile + (int)rank) * BLOCK_M + a_kh * p.Win);
           if (++as == HEADK_A_SLOTS) {
             as = 0;
             aph ^= 1;
@@ -1167,13 +1192,15 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         int g, s, nsl, img, tile, kh0, kh1;
         headk_decode(hs.units[ui], g, s, nsl, img, tile, kh0, kh1);
         const ConvParams& p = grp.p[g];
+        HEADK_TRACE(ui, 6, headk_now());
         for (int kh = kh0; kh < kh1; ++kh) {
           for (int c = 0; c < p.cchunks; ++c) {
             issue_a();   // the NEXT step's slab
             for (int kw = 0; kw < p.KW; ++kw) {
               ptx::mbar_wait(&empty_b[bs], bph ^ 1);
-              ptx::mbar_arrive_expect_tx(&full_b[bs], HEADK_B_SLOT);
-              ptx::tma_load_3d(smem_b + bs * HEADK_B_SLOT, &maps.b[g], &full_b[bs], ((kh * p.KW + kw) * p.cchunks + c) * BLOCK_K, 0, p.f16);
+              if (leader) ptx::mbar_arrive_expect_tx(&full_b[bs], 2 * HEADK_B_SLOT);
+              ptx::tma_load_3d_2sm(smem_b + bs * HEADK_B_SLOT, &maps.b[g], full_b_leader + (uint32_t)bs * 8u,
+                                   ((kh * p.KW + kw) * p.cchunks + c) * BLOCK_K, (int)rank * (BN / 2), p.f16);
               if (++bs == HEADK_B_SLOTS) {
                 bs = 0;
                 bph ^= 1;
@@ -1184,8 +1211,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int seq = 0;
@@ -1195,8 +1222,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         const ConvParams& p = grp.p[g];
         const uint32_t idesc = p.f16 ? ptx::idesc_to_f16(IDESC) : IDESC;
         const int acc = seq & 1;
-        ptx::mbar_wait(&tmem_empty[acc], ((uint32_t)(seq >> 1) & 1u) ^ 1u);
+        ptx::mbar_wait_cluster(&tmem_empty[acc], ((uint32_t)(seq >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
+        HEADK_TRACE(ui, 0, headk_now());
+        HEADK_TRACE(ui, 5, (unsigned long long)(g | (s << 8) | (nsl << 16) | (tile << 24)));
         const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t first = 0u;
         for (int kh = kh0; kh < kh1; ++kh) {
@@ -1209,72 +1238,75 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
               // tap kw = the slab read from row kw on: start address + kw * 128 B, canonical 8-row groups (SBO 1024)
               const uint64_t da = ptx::make_desc_k_sw128(a_addr + kw * 128);
               const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + bs * HEADK_B_SLOT));
+              if (hs.trace && ui == u_begin && first == 0u) hs.trace[((size_t)blockIdx.x * 8 + 7) * 8 + 6] = headk_now();   // first operands landed
 #pragma unroll
-              for (int j = 0; j < BLOCK_K / 16; ++j) ptx::mma_bf16_ss(d_tmem, da + 2 * j, db + 2 * j, idesc, j > 0 ? 1u : first);
+              for (int j = 0; j < BLOCK_K / 16; ++j) ptx::mma_bf16_ss_2cta(d_tmem, da + 2 * j, db + 2 * j, idesc, j > 0 ? 1u : first);
               first = 1u;
-              ptx::mma_commit(&empty_b[bs]);
+              ptx::mma_commit_2cta(&empty_b[bs], 3);
               if (++bs == HEADK_B_SLOTS) {
                 bs = 0;
                 bph ^= 1;
               }
             }
-            ptx::mma_commit(&empty_a[as]);
+            ptx::mma_commit_2cta(&empty_a[as], 3);
             if (++as == HEADK_A_SLOTS) {
               as = 0;
               aph ^= 1;
             }
           }
         }
-        ptx::mma_commit(&tmem_full[acc]);
+        ptx::mma_commit_2cta(&tmem_full[acc], 3);
+        HEADK_TRACE(ui, 1, headk_now());
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue: thread = pixel row (TMEM lane), column half = ewarp >> 2
+    // ------------------------------------------------------------ epilogue (both CTAs, each on its own tile): thread = pixel
+    // row (TMEM lane), column half = ewarp >> 2
+    const uint32_t empty_leader = ptx::mapa_shared(ptx::smem_u32(tmem_empty), 0);
     const int ewarp = warp - 4;
     const int q = ewarp & 3, half = ewarp >> 2;
     const int row = q * 32 + lane;
     const int tid = ewarp * 32 + lane;
     int cur = -1, seq = 0;
     for (int ui = u_begin; ui < u_end; ++ui, ++seq) {
-      int g, s, nsl, img, tile, kh0, kh1;
-      headk_decode(hs.units[ui], g, s, nsl, img, tile, kh0, kh1);
+      int g, s, nsl, img, ptile, kh0, kh1;
+      headk_decode(hs.units[ui], g, s, nsl, img, ptile, kh0, kh1);
       const ConvParams& p = grp.p[g];
       const int acc = seq & 1;
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + half * 128) + ((uint32_t)(q * 32) << 16);
       const int tiles_img = hs.tiles[g];
+      const int tile = 2 * ptile + (int)rank;
       const long tile_lin = (long)img * tiles_img + tile;
-      bool finish = true;
       ptx::mbar_wait(&tmem_full[acc], (uint32_t)(seq >> 1) & 1u);
       ptx::tc_fence_after();
+      if (tid == 0) HEADK_TRACE(ui, 2, headk_now());
+      if (tile >= tiles_img) {
+        // the odd tile of the last pair: nothing to keep, only the accumulator stage to hand back
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(empty_leader + (uint32_t)acc * 8u);
+        continue;
+      }
+      // partial sums / fix-up layout of a slice: [64 column groups][128 rows][4 floats]
+      float* slice0 = hs.slices[g] + (tile_lin * nsl) * (long)(BLOCK_M * BN) + (long)(half * 32) * (BLOCK_M * 4) + row * 4;
       if (nsl > 1) {
-        // ---- partial sums of this filter-row range -> slice s of the tile (plain 64-byte stores per thread and step)
-        float* sl = hs.slices[g] + ((tile_lin * nsl + s) * BLOCK_M + row) * BN + half * 128;
-#pragma unroll 1
+        // ---- partial sums of this filter-row range -> slice s of the tile (a warp stores 512 contiguous bytes)
+        float* sl = slice0 + (long)s * (BLOCK_M * BN);
+#pragma unroll 2
         for (int c0 = 0; c0 < 128; c0 += 16) {
           uint32_t v[16];
           ptx::tmem_ld_32x32b_x16(taddr + c0, v);
           ptx::tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            __stcg(reinterpret_cast<uint4*>(sl + c0) + j, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+            __stcg(reinterpret_cast<uint4*>(sl + (c0 / 4 + j) * (BLOCK_M * 4)), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
         }
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);   // the accumulator stage is free for the next unit's MMAs
-        __threadfence();                                     // slice visible device-wide before the arrival is counted
-        ptx::named_bar_sync(1, EPI_THREADS);
-        if (tid == 0) {
-          int* cnt = hs.counters[g] + tile_lin;
-          const int old = atomicAdd(cnt, 1);
-          const int last = old == nsl - 1;
-          if (last) *cnt = 0;                                // every split has arrived: re-armed for the next launch
-          *s_flag = last;
-        }
-        ptx::named_bar_sync(1, EPI_THREADS);
-        finish = *s_flag != 0;
-        if (finish) __threadfence();
+        if (lane == 0) ptx::mbar_arrive_cluster(empty_leader + (uint32_t)acc * 8u);   // the stage is free for the next unit's MMAs
+        if (tid == 0) HEADK_TRACE(ui, 3, headk_now());
+        continue;   // head_fixup_kernel (next launch) sums the slices and applies the tail
       }
-      if (!finish) continue;
       if (g != cur) {  // another head: its 1x1 weights [18][256] -> [256][20], hidden bias [256], output bias [18]
         ptx::named_bar_sync(1, EPI_THREADS);
         for (int i = tid; i < HEAD_CO * HEAD_CM; i += EPI_THREADS) {
@@ -1287,59 +1319,37 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         cur = g;
       }
       const float slope = p.prelu ? __ldg(p.prelu) : 1.0f;
-      float o18[HEAD_CO];
+      // 18 outputs as 9 packed pairs: one FFMA2 per pair and hidden channel (each half rounds like a scalar fmaf)
+      float2 o9[HEAD_CO / 2];
 #pragma unroll
-      for (int o = 0; o < HEAD_CO; ++o) o18[o] = 0.f;
-      const float* sl0 = hs.slices[g] + ((tile_lin * nsl) * BLOCK_M + row) * BN + half * 128;
+      for (int o = 0; o < HEAD_CO / 2; ++o) o9[o] = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 16) {
-        float x[16];
-        if (nsl > 1) {
-          // the k x k sums: slices in ascending order (fixed summation order whoever finishes)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(sl0 + c0) + j);
-            x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
-          }
-          for (int s2 = 1; s2 < nsl; ++s2) {
-            const float* slp = sl0 + (long)s2 * BLOCK_M * BN + c0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 t = __ldcg(reinterpret_cast<const float4*>(slp) + j);
-              x[4 * j] += t.x; x[4 * j + 1] += t.y; x[4 * j + 2] += t.z; x[4 * j + 3] += t.w;
-            }
-          }
-        } else {
-          uint32_t v[16];
-          ptx::tmem_ld_32x32b_x16(taddr + c0, v);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
-        }
+        uint32_t v[16];
+        ptx::tmem_ld_32x32b_x16(taddr + c0, v);
+        ptx::tmem_ld_wait();
         const float* wrow = w2s + (half * 128 + c0) * HEAD_W2_PITCH;
         const float* brow = sb + half * 128 + c0;
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float h = x[j] + brow[j];
+          float h = __uint_as_float(v[j]) + brow[j];
           h = h > 0.f ? h : h * slope;
+          const float2 hh = make_float2(h, h);
           const float4* w4 = reinterpret_cast<const float4*>(wrow + j * HEAD_W2_PITCH);
 #pragma unroll
           for (int gq = 0; gq < 5; ++gq) {
             const float4 w = w4[gq];
-            o18[4 * gq] = fmaf(h, w.x, o18[4 * gq]);
-            o18[4 * gq + 1] = fmaf(h, w.y, o18[4 * gq + 1]);
-            if (gq < 4) {
-              o18[4 * gq + 2] = fmaf(h, w.z, o18[4 * gq + 2]);
-              o18[4 * gq + 3] = fmaf(h, w.w, o18[4 * gq + 3]);
-            }
+            o9[2 * gq] = __ffma2_rn(hh, make_float2(w.x, w.y), o9[2 * gq]);
+            if (gq < 4) o9[2 * gq + 1] = __ffma2_rn(hh, make_float2(w.z, w.w), o9[2 * gq + 1]);
           }
         }
       }
-      if (nsl == 1) {
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
-      }
+      float o18[HEAD_CO];
+#pragma unroll
+      for (int o = 0; o < HEAD_CO / 2; ++o) { o18[2 * o] = o9[o].x; o18[2 * o + 1] = o9[o].y; }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(empty_leader + (uint32_t)acc * 8u);
       if (half == 1) {
 #pragma unroll
         for (int o = 0; o < HEAD_CO; ++o) parts[row * HEAD_PART_PITCH + o] = o18[o];
@@ -1356,14 +1366,99 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         }
       }
       ptx::named_bar_sync(1, EPI_THREADS);  // `parts` may be overwritten by the next unit
+      if (tid == 0) HEADK_TRACE(ui, 4, headk_now());
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  ptx::cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the peer may still read its shared memory / barriers
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    ptx::tmem_dealloc_2cta(tmem_base, 512);
+  }
+  if (threadIdx.x == 0) HEADK_TRACE(u_begin, 7, headk_now());
+}
+
+// The tail of the anchor networks conv_head_kernel split by filter rows: sum of the slices in ascending order (fixed
+// summation order) + bias -> PReLU -> 1 x 1 conv to 18 channels (model_utilities.lua:32-33), fp32.  A block = 32 positions
+// of one 128-position tile: lane <-> position (the slice layout [column group][row][4] makes a warp's load 512 contiguous
+// bytes), warp <-> 32 of the 256 hidden channels; the eight partial 18-vectors of a position are added in warp order.
+__global__ void __launch_bounds__(256) head_fixup_kernel(const __grid_constant__ ConvGroup grp, const HeadSched hs, const HeadFixArgs fx) {
+  __shared__ __align__(16) float w2s[HEAD_CM * HEAD_W2_PITCH];
+  __shared__ float sb[HEAD_CM + HEAD_CO];
+  __shared__ float red[8][32][HEAD_PART_PITCH];
+  int hi = 0;
+  while (hi + 1 < fx.n && (int)blockIdx.x >= fx.block_end[hi]) ++hi;
+  const int g = fx.head[hi], nsl = fx.nsl[hi];
+  const int b = (int)blockIdx.x - (hi ? fx.block_end[hi - 1] : 0);
+  const ConvParams& p = grp.p[g];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < HEAD_CO * HEAD_CM; i += 256) {
+    const int o = i / HEAD_CM, c = i - o * HEAD_CM;
+    w2s[c * HEAD_W2_PITCH + o] = __ldg(p.w2 + i);
+  }
+  for (int i = tid; i < HEAD_CM; i += 256) sb[i] = __ldg(p.bias + i);
+  if (tid < HEAD_CO) sb[HEAD_CM + tid] = __ldg(p.b2 + tid);
+  __syncthreads();
+  const float slope = p.prelu ? __ldg(p.prelu) : 1.0f;
+  const long tile_lin = b >> 2;
+  const int row = (b & 3) * 32 + lane;
+  const float* slice0 = hs.slices[g] + (tile_lin * nsl) * (long)(BLOCK_M * HEAD_CM) + (long)(warp * 8) * (BLOCK_M * 4) + row * 4;
+  float2 o9[HEAD_CO / 2];
+#pragma unroll
+  for (int o = 0; o < HEAD_CO / 2; ++o) o9[o] = make_float2(0.f, 0.f);
+#pragma unroll 1
+  for (int cg = 0; cg < 8; cg += 2) {
+    float4 t[HEADK_MAX_SLICES][2];
+#pragma unroll
+    for (int s2 = 0; s2 < HEADK_MAX_SLICES; ++s2) {
+      if (s2 < nsl) {
+        const float* slp = slice0 + (long)s2 * (BLOCK_M * HEAD_CM) + cg * (BLOCK_M * 4);
+        t[s2][0] = __ldcg(reinterpret_cast<const float4*>(slp));
+        t[s2][1] = __ldcg(reinterpret_cast<const float4*>(slp + BLOCK_M * 4));
+      }
+    }
+    float x[8] = {t[0][0].x, t[0][0].y, t[0][0].z, t[0][0].w, t[0][1].x, t[0][1].y, t[0][1].z, t[0][1].w};
+#pragma unroll
+    for (int s2 = 1; s2 < HEADK_MAX_SLICES; ++s2) {
+      if (s2 < nsl) {
+        x[0] += t[s2][0].x; x[1] += t[s2][0].y; x[2] += t[s2][0].z; x[3] += t[s2][0].w;
+        x[4] += t[s2][1].x; x[5] += t[s2][1].y; x[6] += t[s2][1].z; x[7] += t[s2][1].w;
+      }
+    }
+    const int c0 = (warp * 8 + cg) * 4;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float h = x[j] + sb[c0 + j];
+      h = h > 0.f ? h : h * slope;
+      const float2 hh = make_float2(h, h);
+      const float4* w4 = reinterpret_cast<const float4*>(w2s + (c0 + j) * HEAD_W2_PITCH);
+#pragma unroll
+      for (int gq = 0; gq < 5; ++gq) {
+        const float4 w = w4[gq];
+        o9[2 * gq] = __ffma2_rn(hh, make_float2(w.x, w.y), o9[2 * gq]);
+        if (gq < 4) o9[2 * gq + 1] = __ffma2_rn(hh, make_float2(w.z, w.w), o9[2 * gq + 1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < HEAD_CO / 2; ++o) {
+    red[warp][lane][2 * o] = o9[o].x;
+    red[warp][lane][2 * o + 1] = o9[o].y;
+  }
+  __syncthreads();
+  const int img = (int)(tile_lin / hs.tiles[g]), tile = (int)(tile_lin - (long)img * hs.tiles[g]);
+  const size_t HW = (size_t)p.Hout * p.Wout;
+  for (int i = tid; i < 32 * HEAD_CO; i += 256) {
+    const int o = i >> 5, r = i & 31;
+    float v = red[0][r][o];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) v += red[w][r][o];
+    const int pp = tile * BLOCK_M + (b & 3) * 32 + r;   // linear position on the INPUT grid
+    const int y = pp / p.Win, x = pp - y * p.Win;
+    if (y < p.Hout && x < p.Wout)
+      reinterpret_cast<float*>(p.out)[((size_t)img * HEAD_CO + o) * HW + (size_t)y * p.Wout + x] = v + sb[HEAD_CM + o];
   }
 }
 
@@ -2241,6 +2336,13 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
     // kernels sized that way can share an SM with the kernels of the other frames in flight:
     //   * wide layers with enough work for two waves of CTA pairs: conv_pair_kernel, BN = 256 / 192, M = 256 MMAs;
     //   * otherwise conv_halo_kernel with BN = 128 (Cout = 128 layers; the wide layers at batch 1), or BN = 64.
+    //   * force_mt = -1 (the throughput schedule: several frames in flight, the SMs a launch leaves idle are filled by the
+    //     other frames' kernels, so a launch costs its SM-time = sum of CTA residencies, not its duration): wide layers
+    //     WITHOUT two waves of pairs run on conv_halo_kernel with the 256-pixel tile and ONE CTA per SM -- few, long-lived
+    //     CTAs amortise prologue / first-load latency / last epilogue (profiles/r2_conv_smtime.md: conv4_2 at batch 1
+    //     25.4 -> 13.1 SM-us although the launch alone takes 42 instead of 31 us).
+    const bool sm_time = force_mt == -1;
+    if (sm_time) force_mt = 0;
     if (pair_ok && force_mt == 0 && force_bn == 0 && env_int("FRCNN_CONV_DUO", 1)) {
       const int Ho = Hin + 2 * padH - KH + 1, Wo = Win + 2 * padW - KW + 1;
       const int wide = Cout % 256 == 0 ? 256 : (Cout % 192 == 0 ? 192 : 0);
@@ -2248,6 +2350,10 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
         const long pair_ctas = 2L * N * ((Ho + 2 * HALO_BH - 1) / (2 * HALO_BH)) * ((Wo + HALO_BW - 1) / HALO_BW) * (Cout / wide);
         if (pair_ctas >= 4L * num_sms || Cout % 128 != 0) {
           conv_prepare_pair(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, wide, 1, w_copies, 2);
+          return;
+        }
+        if (sm_time && halo_cfg_ok(Cout, wide, 2) && env_int("FRCNN_CONV_SMTIME", 1)) {
+          conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, wide, 2, w_copies, 1);
           return;
         }
       }
@@ -2671,9 +2777,9 @@ void conv_head_plan(HeadPlan* P, const HeadDesc* heads, int n_heads, int N, int 
   P->grp = ConvGroup();
   P->grp.n = n_heads;
   P->flops = 0.0;
+  P->fix = HeadFixArgs();
   struct U { int cost, head, img, tile, kh0, kh1, s, nsl; };
   std::vector<U> units;
-  long total_cost = 0;
   int tiles[MAX_GROUP] = {0, 0, 0, 0};
   for (int g = 0; g < n_heads; ++g) {
     const HeadDesc& h = heads[g];
@@ -2686,7 +2792,6 @@ void conv_head_plan(HeadPlan* P, const HeadDesc* heads, int n_heads, int N, int 
     p.cchunks = h.Cin / 64; p.k_iters = h.K * h.K * p.cchunks; p.mode = EPI_HEAD; p.scale = 1.f; p.MT = 1; p.splits = 1;
     // linear positions that carry a valid output: up to (Hout - 1) * Win + Wout - 1
     tiles[g] = ((p.Hout - 1) * h.Win + p.Wout + BLOCK_M - 1) / BLOCK_M;
-    total_cost += (long)N * tiles[g] * p.k_iters;
     P->flops += 2.0 * N * p.Hout * p.Wout * (double)HEAD_CM * h.K * h.K * h.Cin;
     // the input map as a matrix [N * Hin * Win][Cin]: box {64 channels, 136 rows}
     cuuint64_t dims[2] = {(cuuint64_t)h.Cin, (cuuint64_t)N * h.Hin * h.Win};
@@ -2697,7 +2802,7 @@ void conv_head_plan(HeadPlan* P, const HeadDesc* heads, int n_heads, int N, int 
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     FRCNN_REQUIRE(r == CUDA_SUCCESS, FRCNN_E_CUDA, "cuTensorMapEncodeTiled(anchor network input) failed, CUresult " + std::to_string((int)r));
-    make_tmap_weight(&P->maps.b[g], h.w_packed, HEAD_CM, h.K * h.K * h.Cin, HEAD_CM, 2);
+    make_tmap_weight(&P->maps.b[g], h.w_packed, HEAD_CM, h.K * h.K * h.Cin, HEAD_CM / 2, 2);   // half boxes: 128 filters per CTA of a pair
     P->maps.o[g] = P->maps.b[g];
   }
   for (int g = n_heads; g < MAX_GROUP; ++g) {
@@ -2706,28 +2811,43 @@ void conv_head_plan(HeadPlan* P, const HeadDesc* heads, int n_heads, int N, int 
     P->maps.b[g] = P->maps.b[n_heads - 1];
     P->maps.o[g] = P->maps.o[n_heads - 1];
   }
-  // split a head's reduction by filter rows when one unsplit tile would be longer than a CTA's fair share of the launch
-  const long fair = std::max<long>(16, (total_cost + num_sms - 1) / num_sms);
+  // units run on CTA pairs (two neighbouring tiles each).  A head's reduction is split by filter rows when one unsplit
+  // tile pair would be longer than a pair's fair share of the launch: the smallest number of slices whose longest slice
+  // stays within 1.25 fair shares (an uneven split -- 5 rows in 4 slices -- only adds fix-up work), else one per row
+  const int n_pairs_max = std::max(1, num_sms / 2);
+  long pair_cost = 0;
+  // the split count of a head must not depend on the batch size (batched == per-image results, bit for bit): the fair
+  // share is that of ONE frame on the whole machine
+  for (int g = 0; g < n_heads; ++g) pair_cost += (long)((tiles[g] + 1) / 2) * P->grp.p[g].k_iters;
+  const long fair = std::max<long>(16, (pair_cost + n_pairs_max - 1) / n_pairs_max);
   for (int g = 0; g < n_heads; ++g) {
     const ConvParams& p = P->grp.p[g];
-    int nsl = (int)std::min<long>(p.KH, (p.k_iters + fair - 1) / fair);
-    if (nsl < 1) nsl = 1;
     const int row_cost = p.KW * p.cchunks;
+    int nsl = p.KH;
+    for (int n = 1; n <= p.KH; ++n)
+      if ((long)((p.KH + n - 1) / n) * row_cost * 4 <= fair * 5) { nsl = n; break; }
     slice_floats[g] = nsl > 1 ? (size_t)N * tiles[g] * nsl * BLOCK_M * HEAD_CM : 0;
-    counter_ints[g] = N * tiles[g];
+    counter_ints[g] = 0;
     P->sched.tiles[g] = tiles[g];
+    if (nsl > 1) {
+      HeadFixArgs& fx = P->fix;
+      fx.head[fx.n] = g;
+      fx.nsl[fx.n] = nsl;
+      fx.block_end[fx.n] = (fx.n ? fx.block_end[fx.n - 1] : 0) + N * tiles[g] * 4;
+      ++fx.n;
+    }
     for (int n = 0; n < N; ++n)
-      for (int t = 0; t < tiles[g]; ++t)
+      for (int t = 0; t < (tiles[g] + 1) / 2; ++t)
         for (int s = 0; s < nsl; ++s) {
           const int kh0 = (int)((long)p.KH * s / nsl), kh1 = (int)((long)p.KH * (s + 1) / nsl);
-          // a split unit also pays for writing its slice; the fix-up itself lands on whichever unit arrives last
-          units.push_back(U{(kh1 - kh0) * row_cost + (nsl > 1 ? 4 : 0), g, n, t, kh0, kh1, s, nsl});
+          // every unit also pays for its epilogue (slice store, or bias + PReLU + 1 x 1 tail): ~8 reduction steps' worth
+          units.push_back(U{(kh1 - kh0) * row_cost + 8, g, n, t, kh0, kh1, s, nsl});
         }
   }
   for (int g = n_heads; g < MAX_GROUP; ++g) { slice_floats[g] = 0; counter_ints[g] = 0; P->sched.tiles[g] = 0; }
-  // longest-processing-time schedule over the persistent CTAs (deterministic: stable sort, lowest CTA index on ties)
+  // longest-processing-time schedule over the persistent pairs (deterministic: stable sort, lowest pair index on ties)
   std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
-  const int G = (int)std::min<size_t>((size_t)num_sms, units.size());
+  const int G = (int)std::min<size_t>((size_t)n_pairs_max, units.size());
   std::vector<long> load(G, 0);
   std::vector<std::vector<int>> mine(G);
   for (size_t i = 0; i < units.size(); ++i) {
@@ -2746,7 +2866,7 @@ void conv_head_plan(HeadPlan* P, const HeadDesc* heads, int n_heads, int N, int 
     }
     (*cta_off_out)[b + 1] = (int)units_out->size();
   }
-  P->grid = G;
+  P->grid = 2 * G;
   P->n_units = (int)units.size();
 }
 
@@ -2760,8 +2880,23 @@ void conv_launch_heads(const HeadPlan& P, cudaStream_t st) {
     FRCNN_REQUIRE(p.w2 && p.b2 && p.bias && p.out, FRCNN_E_STATE, "anchor networks: tail parameters / outputs not set");
   }
   FRCNN_REQUIRE(P.sched.units && P.sched.cta_off, FRCNN_E_STATE, "anchor networks: schedule not uploaded");
-  conv_head_kernel<<<P.grid, CONV_THREADS, HEADK_SMEM, st>>>(P.maps, P.grp, P.sched);
-  FRCNN_CUDA_TRY(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(P.grid, 1, 1);
+  cfg.blockDim = dim3(CONV_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = HEADK_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FRCNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_head_kernel, P.maps, P.grp, P.sched));
+  if (P.fix.n > 0) {
+    head_fixup_kernel<<<P.fix.block_end[P.fix.n - 1], 256, 0, st>>>(P.grp, P.sched, P.fix);
+    FRCNN_CUDA_TRY(cudaGetLastError());
+  }
 }
 
 void conv_launch_head_group(const ConvLaunch* const* Ls, int n, int num_sms, cudaStream_t st) {

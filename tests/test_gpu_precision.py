@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # drift apart even though 99 % of the matches agree; fp16 operands (11 bits) are the evaluate-mode default.
 # Measured values: profiles/r2_precision_*.json.
 BARS = {
-    "fp16": dict(head=(6e-3, 4e-3), feat=(2e-3, 4e-3), matches=0.99, candidates=0.85, winners=0.85, covered=0.90, r2=0.005),
+    "fp16": dict(head=(6e-3, 4e-3), feat=(2e-3, 4e-3), matches=0.99, candidates=0.75, winners=0.85, covered=0.90, r2=0.005),
     "bf16": dict(head=(4e-2, 2e-2), feat=(1e-2, 2e-2), matches=0.98, candidates=0.30, winners=0.20, covered=0.50, r2=0.03),
 }
 FRAME_SEEDS = {"small": (2, 3, 4, 5), "large": (2, 3, 4)}
