@@ -33,7 +33,9 @@ sys.path.insert(0, ROOT)
 _REAL_STDOUT = os.dup(1)
 os.dup2(2, 1)
 if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-    os.environ.setdefault("NCCL_DEBUG", "INFO")  # the driver reads the communicator's rank count from NCCL's own log
+    # the driver reads the communicator's rank count from NCCL's own log: INFO unless the caller asked for more
+    if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+        os.environ["NCCL_DEBUG"] = "INFO"
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -642,6 +644,21 @@ def bench_train(hs, model, steps, warmup, batch, with_cpu):
     clocks = hs.sampler.stop()
     launches = (m.launch_count() - l0) // max(state["step"], 1)
     ms_e2e, spread_e2e = hs.region(k_of(step_e2e), lambda: [step_e2e() for _ in range(3)])
+    collective = None
+    if hs.world > 1:
+        # what the gradient all-reduce costs a step: the same steps with the collective left out (every rank on its own)
+        local_objective = F.create_objective(m, None)
+
+        def step_local():
+            state["step"] += 1
+            local_objective(batch_list, seed=state["step"])
+
+        ms_local, _ = hs.region(k_of(step_local), lambda: [step_local() for _ in range(3)])
+        info = m.dp_info() if hasattr(m, "dp_info") else {}
+        collective = dict(kind="ncclAllReduce(sum, fp32) in place on the flat gradient + counters, bucketed cnet -> heads -> block 4..1, "
+                               "launched from inside pnet:backward as each bucket's last wgrad finishes (frcnn_dp_*)",
+                          bytes_per_step=int(m.gradient.numel() * 4 + 32), ms_per_step_with=ms / steps, ms_per_step_without=ms_local / steps,
+                          exposed_ms_per_step=(ms - ms_local) / steps, **info)
     total = hs.sum_over_ranks(float(B)) * steps
     fwd = conv_flops_per_image(desc, h, w)
     grad_bytes = int(m.gradient.numel() * 4)
@@ -662,6 +679,8 @@ def bench_train(hs, model, steps, warmup, batch, with_cpu):
                               peak_source=hs.pk["source"] + " bf16 sustained",
                               note="3 x forward conv FLOPs per frame over the whole step (every other kernel and the all-reduce in the "
                                    "denominator): lower bound of the tcgen05 kernels' own rate"))
+    if collective:
+        line["collective"] = collective
     if hs.rank == 0 and with_cpu and hs.world == 1:
         line["cpu_baseline"] = cpu_train(desc, cfg, params, h, w)
     m.close()

@@ -2461,6 +2461,30 @@ int frcnn_roi_pool_forward(frcnn_ctx* c, const float* fmap_dev, int C, int H, in
   API_END(c)
 }
 
+int frcnn_adaptive_maxpool_forward(frcnn_ctx* c, const float* x_dev, int C, int h, int w, int64_t stride_c, int64_t stride_h,
+                                   int64_t stride_w, int kh, int kw, float* out_dev, float* idx_dev) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(x_dev && out_dev && C >= 1 && kh >= 1 && kw >= 1, FRCNN_E_INVALID, "bad argument");
+  // an empty view is what extract_roi_pooling_input yields for a rect clipped to nothing; cunn raises on it
+  FRCNN_REQUIRE(h >= 1 && w >= 1, FRCNN_E_ROI_EMPTY, "adaptive max pooling of an empty view (objective.lua:11)");
+  frcnn::launch_adaptive_maxpool_fwd(x_dev, C, h, w, (long)stride_c, (long)stride_h, (long)stride_w, kh, kw, out_dev, idx_dev, c->stream);
+  ++c->launches;
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  API_END(c)
+}
+
+int frcnn_adaptive_maxpool_backward(frcnn_ctx* c, const float* dout_dev, const float* idx_dev, int C, int h, int w, int kh, int kw,
+                                    float* dx_dev) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(dout_dev && idx_dev && dx_dev && C >= 1 && h >= 1 && w >= 1 && kh >= 1 && kw >= 1, FRCNN_E_INVALID, "bad argument");
+  frcnn::launch_adaptive_maxpool_bwd(dout_dev, idx_dev, C, h, w, kh, kw, dx_dev, c->stream);
+  ++c->launches;
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  API_END(c)
+}
+
 int frcnn_cnet_forward(frcnn_ctx* c, const float* x_dev, int R, float* reg_dev, float* cls_dev) {
   API_BEGIN(c)
   FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called first");

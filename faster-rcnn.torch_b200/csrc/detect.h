@@ -62,6 +62,11 @@ void launch_roi_pool_nhwc(const RoiParams& p, int N, int num_sms, cudaStream_t s
 void launch_roi_pool_chw(const float* fmap, int C, int H, int W, const LocalizerDev& loc, const double* rects_dev, int R,
                          int kh, int kw, float* out, int32_t* argmax, int* status, cudaStream_t st);
 
+// nn.SpatialAdaptiveMaxPooling on a strided [C][h][w] view (the `amp` module of objective.lua:30 / Detector.lua:14)
+void launch_adaptive_maxpool_fwd(const float* x, int C, int h, int w, long sc, long sh, long sw, int kh, int kw, float* out,
+                                 float* idx, cudaStream_t st);
+void launch_adaptive_maxpool_bwd(const float* dout, const float* idx, int C, int h, int w, int kh, int kw, float* dx, cudaStream_t st);
+
 struct FinalizeParams {
   const double* cand_r;   // [N][cap][4]
   const float* cand_logp;

@@ -194,6 +194,52 @@ __global__ void __launch_bounds__(256) roi_pool_nhwc_kernel(RoiParams p) {
     reinterpret_cast<uint4*>(p.out)[(long)row * per_row + item] = m;
   }
 }
+// ------------------------------------------------------------------------------------------ the `amp` module slot
+// nn.SpatialAdaptiveMaxPooling(kw, kh):forward on a (possibly non-contiguous) [C][h][w] view, as objective.lua:118,138 and
+// Detector.lua:97 call it on the crop extract_roi_pooling_input returns: bin (by, bx) covers rows
+// [floor(by*h/kh), ceil((by+1)*h/kh)) and the same along x, the FIRST maximum in row-major order wins (strict >).  idx holds
+// the winner's position inside the view (y*w + x) as a float -- the module's `indices` field, which objective.lua only
+// clones and puts back (:119,139,183).
+__global__ void adaptive_maxpool_fwd_kernel(const float* __restrict__ x, int C, int h, int w, long sc, long sh, long sw, int kh, int kw,
+                                            float* __restrict__ out, float* __restrict__ idx) {
+  const long total = (long)C * kh * kw;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int bx = (int)(i % kw), by = (int)((i / kw) % kh), c = (int)(i / ((long)kw * kh));
+    const int ys = (by * h) / kh, ye = ((by + 1) * h + kh - 1) / kh;
+    const int xs = (bx * w) / kw, xe = ((bx + 1) * w + kw - 1) / kw;
+    float best = -INFINITY;
+    int arg = ys * w + xs;
+    for (int yy = ys; yy < ye; ++yy)
+      for (int xx = xs; xx < xe; ++xx) {
+        const float v = __ldg(x + c * sc + yy * sh + xx * sw);
+        if (v > best) { best = v; arg = yy * w + xx; }
+      }
+    out[i] = best;
+    if (idx) idx[i] = (float)arg;
+  }
+}
+// :backward -- gradInput [C][h][w] (contiguous, zeroed here) receives every output's gradient at its winner; bins overlap
+// when the view is smaller than the grid, hence the atomic (cunn does the same)
+__global__ void adaptive_maxpool_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ idx, int C, int h, int w, int kh,
+                                            int kw, float* __restrict__ dx) {
+  const long total = (long)C * kh * kw;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i / ((long)kw * kh));
+    const int arg = (int)idx[i];
+    if (arg >= 0 && arg < h * w) atomicAdd(dx + (long)c * h * w + arg, dout[i]);
+  }
+}
+void launch_adaptive_maxpool_fwd(const float* x, int C, int h, int w, long sc, long sh, long sw, int kh, int kw, float* out,
+                                 float* idx, cudaStream_t st) {
+  const long total = (long)C * kh * kw;
+  adaptive_maxpool_fwd_kernel<<<(int)std::min<long>((total + 255) / 256, 148 * 8), 256, 0, st>>>(x, C, h, w, sc, sh, sw, kh, kw, out, idx);
+}
+void launch_adaptive_maxpool_bwd(const float* dout, const float* idx, int C, int h, int w, int kh, int kw, float* dx, cudaStream_t st) {
+  const long total = (long)C * kh * kw;
+  cudaMemsetAsync(dx, 0, (size_t)C * h * w * sizeof(float), st);
+  adaptive_maxpool_bwd_kernel<<<(int)std::min<long>((total + 255) / 256, 148 * 8), 256, 0, st>>>(dout, idx, C, h, w, kh, kw, dx);
+}
+
 void launch_roi_pool_nhwc(const RoiParams& p, int N, int num_sms, cudaStream_t st) {
   roi_prepare_kernel<<<dim3((p.cap + 255) / 256, N), 256, 0, st>>>(p, N);
   roi_pool_nhwc_kernel<<<num_sms * 4, 256, 0, st>>>(p);

@@ -23,6 +23,50 @@ def extract_roi_pooling_input(model, rects, fmap):
     return out, arg
 
 
+def roi_pooling_view(localizer, input_rect, fmap):
+    """extract_roi_pooling_input exactly as objective.lua:5-13 returns it: the (non-contiguous) crop VIEW of the feature
+    map [C][H][W] and its 1-based inclusive index table {{}, {y1, y2}, {x1, x2}}."""
+    r = localizer.inputToFeatureRect(input_rect)
+    C, H, W = fmap.shape
+    r = r.clip(Rect(0, 0, W, H))
+    y1, y2 = int(min(r.minY + 1, r.maxY)), int(r.maxY)
+    x1, x2 = int(min(r.minX + 1, r.maxX)), int(r.maxX)
+    return fmap[:, y1 - 1:y2, x1 - 1:x2], ((), (y1, y2), (x1, x2))
+
+
+class SpatialAdaptiveMaxPooling:
+    """The `amp` module slot (nn.SpatialAdaptiveMaxPooling(kw, kh), objective.lua:30, Detector.lua:14) for callers that keep
+    the reference's per-ROI loop: forward on a strided [C][h][w] view, `indices` readable / assignable like the nn
+    module's field (objective.lua:119,139,183), backward -> gradInput [C][h][w]."""
+
+    def __init__(self, model, kw, kh):
+        self.model, self.kw, self.kh = model, kw, kh
+        self.indices = None
+        self.output = None
+        self.gradInput = None
+
+    def forward(self, x):
+        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 3
+        C, h, w = x.shape
+        self.output = torch.empty((C, self.kh, self.kw), dtype=torch.float32, device=x.device)
+        self.indices = torch.empty((C, self.kh, self.kw), dtype=torch.float32, device=x.device)
+        sc, sh, sw = x.stride()
+        check(self.model.ctx, lib().frcnn_adaptive_maxpool_forward(
+            self.model.ctx, ffi.cast("const float*", x.data_ptr()), C, h, w, sc, sh, sw, self.kh, self.kw,
+            ffi.cast("float*", self.output.data_ptr()), ffi.cast("float*", self.indices.data_ptr())))
+        return self.output
+
+    def backward(self, x, grad_output):
+        C, h, w = x.shape
+        g = grad_output.to(torch.float32).contiguous()
+        idx = self.indices.contiguous()
+        self.gradInput = torch.empty((C, h, w), dtype=torch.float32, device=x.device)
+        check(self.model.ctx, lib().frcnn_adaptive_maxpool_backward(
+            self.model.ctx, ffi.cast("const float*", g.data_ptr()), ffi.cast("const float*", idx.data_ptr()), C, h, w, self.kh,
+            self.kw, ffi.cast("float*", self.gradInput.data_ptr())))
+        return self.gradInput
+
+
 class Detector:
     def __init__(self, model):  # Detector.lua:8-15
         self.model = model

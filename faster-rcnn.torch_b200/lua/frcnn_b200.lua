@@ -172,6 +172,7 @@ function M.accelerate(model, anchor_nets, class_layers)
   M.pack(model)
   M.bind_grads(model)
   M.install(model)
+  M.install_amp(model)
   return model
 end
 
@@ -250,6 +251,51 @@ function M.install(model)
     return self.gradInput
   end
   return model
+end
+
+-- The `amp` slot.  objective.lua:30 and Detector.lua:14 build it themselves -- `nn.SpatialAdaptiveMaxPooling(kw, kh):cuda()`
+-- is a LOCAL of create_objective / a field set in Detector:__init -- so the constructor is what gets replaced:
+-- M.install_amp(model) swaps nn.SpatialAdaptiveMaxPooling for a class with the same surface (forward on the strided crop
+-- view extract_roi_pooling_input returns, `indices` readable / assignable, backward -> gradInput of the view's shape)
+-- whose updateOutput / updateGradInput are one library launch each.  M.uninstall_amp() puts cunn's class back.
+local B200Amp = nil
+local function amp_class()
+  if B200Amp then return B200Amp end
+  B200Amp = torch.class('nn.B200SpatialAdaptiveMaxPooling', 'nn.Module')
+  function B200Amp:__init(W, H)
+    nn.Module.__init(self)
+    self.W, self.H = W, H
+    self.indices = torch.Tensor()
+  end
+  function B200Amp:updateOutput(input)                            -- input: C x h x w view, any strides
+    local ctx = B200Amp.ctx
+    assert(input:dim() == 3, 'B200 amp: 3-D (C x h x w) input expected (objective.lua:118, Detector.lua:97)')
+    local nc, h, w = input:size(1), input:size(2), input:size(3)
+    self.output:resize(nc, self.H, self.W)
+    self.indices = self.indices:type(input:type()):resize(nc, self.H, self.W)
+    check(ctx, C.frcnn_adaptive_maxpool_forward(ctx, input:data(), nc, h, w, input:stride(1), input:stride(2), input:stride(3),
+                                                self.H, self.W, self.output:data(), self.indices:data()))
+    return self.output
+  end
+  function B200Amp:updateGradInput(input, gradOutput)
+    local ctx = B200Amp.ctx
+    local nc, h, w = input:size(1), input:size(2), input:size(3)
+    local g = gradOutput:contiguous()
+    self.gradInput:resize(nc, h, w)
+    check(ctx, C.frcnn_adaptive_maxpool_backward(ctx, g:data(), self.indices:contiguous():data(), nc, h, w, self.H, self.W,
+                                                 self.gradInput:data()))
+    return self.gradInput
+  end
+  return B200Amp
+end
+function M.install_amp(model)
+  local cls = amp_class()
+  cls.ctx = model.b200.ctx
+  M.cunn_amp = M.cunn_amp or nn.SpatialAdaptiveMaxPooling
+  nn.SpatialAdaptiveMaxPooling = cls
+end
+function M.uninstall_amp()
+  if M.cunn_amp then nn.SpatialAdaptiveMaxPooling = M.cunn_amp end
 end
 
 -- Drop-in for the global create_objective (objective.lua:15): same arguments, same returned closure

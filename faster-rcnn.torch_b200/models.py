@@ -394,6 +394,12 @@ class Model:
     def launch_count(self):
         return int(lib().frcnn_launch_count(self.ctx))
 
+    def dp_info(self):
+        """frcnn_dp_info: the context's NCCL communicator (nranks 0 = none), NCCL version, bytes all-reduced so far."""
+        r, n, v, b = ffi.new("int*"), ffi.new("int*"), ffi.new("int*"), ffi.new("int64_t*")
+        check(self.ctx, lib().frcnn_dp_info(self.ctx, r, n, v, b))
+        return dict(comm_rank=int(r[0]), comm_nranks=int(n[0]), nccl_version=int(v[0]), bytes_reduced=int(b[0]))
+
 
 def create_model(cfg, layers, anchor_nets, class_layers, **kw):  # model_utilities.lua:126-136
     return Model(cfg, layers, anchor_nets, class_layers, **kw)

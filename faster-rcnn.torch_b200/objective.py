@@ -86,6 +86,8 @@ def create_objective(model, dist=None, defer_div=False, batched=True):
             # one size group = one frcnn_train_batch call = the step's only accumulation into the gradient: its buckets may
             # leave as soon as the backward pass has finished them
             _lib().frcnn_dp_set_overlap(model.ctx, 1 if (len(groups) == 1 and batched) else 0)
+        elif getattr(model, "_dp_counters", None) is not None:
+            _lib().frcnn_dp_set_overlap(model.ctx, 0)       # a local objective on a context that owns a communicator
         for shape, idx in groups.items():
             dims = model.output_dims(shape[1], shape[2])
             ps = [clean_anchors(batch[i]["positive"], dims) for i in idx]

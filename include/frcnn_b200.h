@@ -223,6 +223,17 @@ int frcnn_nms_segmented_dev(frcnn_ctx* ctx, const float* boxes_dev, int64_t n_to
 int frcnn_roi_pool_forward(frcnn_ctx* ctx, const float* fmap_dev, int C, int H, int W, const double* rects_host, int R,
                            float* out_dev, int32_t* argmax_dev);
 
+/* The `amp` module itself, nn.SpatialAdaptiveMaxPooling(kw, kh) (objective.lua:30,118-119,138-139,183-184;
+ * Detector.lua:14,97), for callers that keep the reference's per-ROI loop: forward on a [C][h][w] view with element strides
+ * (stride_c, stride_h, stride_w) -- the crop extract_roi_pooling_input returns is a non-contiguous view of the feature map --
+ * writes out_dev [C][kh][kw] and, when idx_dev is non-NULL, the module's `indices` [C][kh][kw]: the winner's position
+ * y*w + x inside the view, stored as float (objective.lua only clones the field and puts it back).  Backward zero-fills
+ * dx_dev [C][h][w] (contiguous, the module's gradInput) and adds every output gradient at its winner. */
+int frcnn_adaptive_maxpool_forward(frcnn_ctx* ctx, const float* x_dev, int C, int h, int w, int64_t stride_c, int64_t stride_h,
+                                   int64_t stride_w, int kh, int kw, float* out_dev, float* idx_dev);
+int frcnn_adaptive_maxpool_backward(frcnn_ctx* ctx, const float* dout_dev, const float* idx_dev, int C, int h, int w, int kh,
+                                    int kw, float* dx_dev);
+
 /* ---- cnet: replaces cnet:forward (Detector.lua:101, objective.lua:164), evaluate mode ---------------------- */
 /* x_dev: [R][kh*kw*C] fp32 (reference ordering).  reg_dev: [R][4]; cls_dev: [R][class_count+1] log-softmax. */
 int frcnn_cnet_forward(frcnn_ctx* ctx, const float* x_dev, int R, float* reg_dev, float* cls_dev);

@@ -145,3 +145,43 @@ def test_cnet_forward(F, small_model, R):
         small_model.set_eval_precision("fp16")
     assert torch.allclose(reg_b.cpu(), reg_f, rtol=5e-2, atol=5e-2)
     assert torch.allclose(cls_b.cpu(), cls_f, rtol=5e-2, atol=5e-2)
+
+
+def test_amp_module_slot_on_strided_views(F, small_model):
+    """The `amp` slot the way objective.lua:118-119,183-184 and Detector.lua:96-97 use it: extract_roi_pooling_input
+    returns a NON-contiguous crop view, amp:forward pools it, amp.indices is cloned and put back, amp:backward returns
+    gradInput of the view's shape.  Values bit-exact vs the oracle's per-ROI restatement and vs the batched
+    frcnn_roi_pool_forward; winners = the first maximum in row-major order (ties included); backward = scatter-add at the
+    winners (overlapping bins of crops smaller than 6 x 6 accumulate)."""
+    rng = np.random.default_rng(11)
+    C, H, W = 384, 29, 50
+    fmap = torch.from_numpy(rng.integers(-3, 4, size=(C, H, W)).astype(np.float32))   # many ties
+    loc = F.Localizer(small_model, small_model.n_heads + 1)
+    oloc = OL.Localizer(OL.trunk_layer_info(OM.VGG_SMALL["layers"], 4))
+    amp = F.SpatialAdaptiveMaxPooling(small_model, 6, 6)
+    rects = [(100, 50, 300, 250), (0, 0, 800, 450), (790, 440, 800, 450), (0, 0, 16, 16), (333.3, 120.7, 390.2, 200.1), (5, 5, 40, 300)]
+    g = fmap.cuda()
+    batched, _ = F.extract_roi_pooling_input(small_model, [F.Rect(*r) for r in rects], g)
+    for k, r in enumerate(rects):
+        view, idx = F.roi_pooling_view(loc, F.Rect(*r), g)
+        assert not view.is_contiguous() or view.shape[2] == W
+        out = amp.forward(view)
+        want, ind, (y0, y1, x0, x1) = OD.roi_pool(fmap, ORect(*r), oloc)
+        assert idx[1] == (y0 + 1, y1) and idx[2] == (x0 + 1, x1)
+        assert torch.equal(out.cpu().reshape(-1), want.reshape(-1))
+        assert torch.equal(out.reshape(-1), batched[k])
+        ref, ref_idx = torch.nn.functional.adaptive_max_pool2d(view.cpu().contiguous(), (6, 6), return_indices=True)
+        assert torch.equal(out.cpu(), ref)
+        assert torch.equal(amp.indices.cpu().to(torch.int64), ref_idx)          # first maximum in row-major order
+        # objective.lua:119 / :183: indices cloned, other ROIs pooled in between, indices put back before backward
+        saved = amp.indices.clone()
+        amp.forward(F.roi_pooling_view(loc, F.Rect(10, 10, 200, 200), g)[0])
+        amp.indices = saved
+        dout = torch.from_numpy(rng.standard_normal((C, 6, 6)).astype(np.float32)).cuda()
+        gi = amp.backward(view, dout)
+        assert tuple(gi.shape) == tuple(view.shape)
+        want_gi = torch.zeros(view.shape, dtype=torch.float64).reshape(C, -1)
+        want_gi.scatter_add_(1, ref_idx.reshape(C, -1), dout.cpu().double().reshape(C, -1))
+        assert torch.allclose(gi.cpu().double().reshape(C, -1), want_gi, atol=1e-5)
+    with pytest.raises(F.FrcnnError):
+        amp.forward(g[:, 3:3, 2:9])     # an empty crop: cunn raises as well (SURVEY Q8)

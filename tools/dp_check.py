@@ -36,17 +36,24 @@ def main():
                           packed=(m.pack_examples(pos), m.pack_examples(neg))))
     local_only = F.create_objective(m, None, defer_div=True)           # no collective
     lib_dp = F.create_objective(m, dist, defer_div=True)               # frcnn_dp_allreduce (overlapped: one size group)
-    # ---- 1. equality with torch.distributed on identical per-rank gradients (fixed dropout seed)
-    local_only(batch, seed=7)
-    ref = m.gradient.clone()
-    dist.all_reduce(ref, op=dist.ReduceOp.SUM)
-    _, g, st = lib_dp(batch, seed=7)
-    same_overlap = bool(torch.equal(g, ref))
+    # ---- 1. equality with torch.distributed on IDENTICAL per-rank gradients.  The backward pass itself is not bit
+    # reproducible run to run (ROI-pool scatter atomics, TMA reduce-add split-K weight gradients), so the same local
+    # gradient buffer is reduced both ways: by torch.distributed on a clone, by the library in place.
     L = F.lib()
     local_only(batch, seed=7)
+    g0 = m.gradient.clone()
+    ref = g0.clone()
+    dist.all_reduce(ref, op=dist.ReduceOp.SUM)
     L.frcnn_dp_set_overlap(m.ctx, 0)
-    c = F.dp_allreduce(m, [0.0] * 7)
+    F.dp_allreduce(m, [0.0] * 7)
     same_plain = bool(torch.equal(m.gradient, ref))
+    # the overlapped path sends its buckets from inside the backward pass: a fresh backward, so it is compared with the
+    # reduced gradient of the other run to the run-to-run reproducibility of the backward pass itself
+    _, g, st = lib_dp(batch, seed=7)
+    rel = ((g - ref).norm() / ref.norm()).item()
+    local_only(batch, seed=7)
+    rel_rerun = ((m.gradient - g0).norm() / g0.norm()).item()
+    same_overlap = dict(rel_l2_vs_other_run=rel, rel_l2_of_two_local_runs=rel_rerun, ok=bool(rel <= 4 * rel_rerun + 1e-6))
     cnt = torch.tensor([float(sum(len(b["positive"]) + len(b["negative"]) for b in batch))], device="cuda")
     dist.all_reduce(cnt)
     counts_ok = abs(st["cls_count"] - cnt.item()) < 0.5
