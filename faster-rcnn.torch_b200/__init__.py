@@ -8,7 +8,7 @@ from ._lib import FrcnnError, declared_functions, ffi, lib  # noqa: F401
 from .rect import Rect  # noqa: F401
 from .geometry import Anchors, Localizer  # noqa: F401
 from .nms import nms, nms_segmented, nms_segmented_dev  # noqa: F401
-from .models import Model, create_model, duplo_cfg, imgnet_cfg, vgg_large, vgg_small  # noqa: F401
+from .models import Model, create_model, duplo_cfg, find_target_size, imgnet_cfg, vgg_large, vgg_small  # noqa: F401
 from .detector import Detector, DetectorPipeline, SpatialAdaptiveMaxPooling, extract_roi_pooling_input, roi_pooling_view  # noqa: F401
 from .shard import reduce_timing, shard_frames, shard_segments  # noqa: F401
 from .objective import allreduce_gradient, clean_anchors, create_objective, dp_allreduce, dp_init  # noqa: F401

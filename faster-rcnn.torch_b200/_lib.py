@@ -42,6 +42,10 @@ def lib():
             raise FrcnnError(-1, "libfrcnn_b200.so is not built; run `python __graft_entry__.py build` "
                                  "(this package has no CPU or PyTorch fallback)")
         _lib = ffi.dlopen(LIB_PATH)
+        # resolve every entry point now: cffi builds accessors lazily under a non-reentrant lock, and a finaliser
+        # (Model.__del__ -> frcnn_destroy) that runs inside another cffi call would otherwise deadlock on it
+        for name in declared_functions():
+            getattr(_lib, name)
     return _lib
 
 

@@ -2547,6 +2547,35 @@ int frcnn_set_detect_thresholds(frcnn_ctx* c, double fg_prob, float nms_proposal
   return FRCNN_OK;
 }
 
+int frcnn_find_target_size(int orig_w, int orig_h, double target_smaller_side, double max_pixel_size, int* w_out, int* h_out) {
+  if (orig_w < 1 || orig_h < 1 || !w_out || !h_out) return FRCNN_E_INVALID;
+  double w, h;   // Lua numbers are doubles; math.floor(x + 0.5)
+  if (orig_h < orig_w) {
+    w = std::min((double)orig_w * target_smaller_side / (double)orig_h, max_pixel_size);
+    h = floor((double)orig_h * w / (double)orig_w + 0.5);
+    w = floor(w + 0.5);
+  } else {
+    h = std::min((double)orig_h * target_smaller_side / (double)orig_w, max_pixel_size);
+    w = floor((double)orig_w * h / (double)orig_h + 0.5);
+    h = floor(h + 0.5);
+  }
+  if (!(w >= 1 && h >= 1)) return FRCNN_E_INVALID;   // utilities.lua:201 asserts
+  *w_out = (int)w;
+  *h_out = (int)h;
+  return FRCNN_OK;
+}
+
+int frcnn_scale_frame(frcnn_ctx* c, const float* src_dev, int ch, int src_h, int src_w, float* dst_dev, int dst_h, int dst_w) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(src_dev && dst_dev && ch >= 1 && src_h >= 1 && src_w >= 1 && dst_h >= 1 && dst_w >= 1, FRCNN_E_INVALID, "bad argument");
+  float* tmp = (float*)frcnn::ensure_scratch(c, (size_t)ch * src_h * dst_w * sizeof(float) + 256);
+  frcnn::launch_scale_image(src_dev, ch, src_h, src_w, tmp, dst_dev, dst_h, dst_w, c->stream);
+  c->launches += 2;
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  API_END(c)
+}
+
 int frcnn_normalize_frame(frcnn_ctx* c, float* img_dev, int h, int w, int rgb2yuv, int centering, int scaling, int contrastive_width) {
   API_BEGIN(c)
   REQUIRE_DEVICE(c);

@@ -251,6 +251,7 @@ void launch_normalize_frame(float* img, int H, int W, int rgb2yuv, int centering
                             float threshold, double* scratch, float* plane_tmp, cudaStream_t st);
 
 // ------------------------------------------------------------------ optimiser (optim_kernels.cu)
+void launch_scale_image(const float* src, int C, int sh, int sw, float* tmp, float* dst, int dh, int dw, cudaStream_t st);
 void launch_rmsprop_step(float* w, float* g, float* m, long n, double grad_div, double lr, double alpha, double eps, double wd,
                          int num_sms, cudaStream_t st);
 

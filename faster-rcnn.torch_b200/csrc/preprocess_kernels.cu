@@ -147,4 +147,65 @@ void launch_normalize_frame(float* img, int H, int W, int rgb2yuv, int centering
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------- resize
+// image.scale(img, w, h) in its default 'bilinear' mode (BatchIterator.lua:49-52, utilities.lua:188-204): torch/image's
+// Main_scaleLinear_rowcol applied along the rows, then along the columns.  Enlarging an axis = linear interpolation with
+// scale (src - 1) / (dst - 1), the last sample copied; shrinking = the mean of the source interval [di * s, (di + 1) * s) with
+// fractional end weights.  One thread per output sample walks its interval in the C loop's order with individually
+// rounded fp32 operations (no FMA contraction), so the result equals the restated loop bit for bit.
+__device__ __forceinline__ float scale_sample(const float* __restrict__ src, long stride, int src_len, int dst_len, int di) {
+  if (dst_len > src_len) {
+    if (src_len == 1 || di == dst_len - 1) return src[(long)(src_len - 1) * stride];
+    const float scale = __fdiv_rn((float)(src_len - 1), (float)(dst_len - 1));
+    float si_f = __fmul_rn((float)di, scale);
+    const int si_i = (int)si_f;
+    si_f = __fsub_rn(si_f, (float)si_i);
+    return __fadd_rn(__fmul_rn(__fsub_rn(1.f, si_f), src[(long)si_i * stride]), __fmul_rn(si_f, src[(long)(si_i + 1) * stride]));
+  }
+  if (dst_len < src_len) {
+    const float scale = __fdiv_rn((float)src_len, (float)dst_len);
+    float si0_f = __fmul_rn((float)di, scale);          // what the loop carries over from the previous sample
+    const int si0_i = (int)si0_f;
+    si0_f = __fsub_rn(si0_f, (float)si0_i);
+    float si1_f = __fmul_rn((float)(di + 1), scale);
+    const int si1_i = (int)si1_f;
+    si1_f = __fsub_rn(si1_f, (float)si1_i);
+    float acc = __fmul_rn(__fsub_rn(1.f, si0_f), src[(long)si0_i * stride]);
+    float n = __fsub_rn(1.f, si0_f);
+    for (int si = si0_i + 1; si < si1_i; ++si) {
+      acc = __fadd_rn(acc, src[(long)si * stride]);
+      n = __fadd_rn(n, 1.f);
+    }
+    if (si1_i < src_len) {
+      acc = __fadd_rn(acc, __fmul_rn(si1_f, src[(long)si1_i * stride]));
+      n = __fadd_rn(n, si1_f);
+    }
+    return __fdiv_rn(acc, n);
+  }
+  return src[(long)di * stride];
+}
+// pass 1: [C][sh][sw] -> [C][sh][dw]; pass 2: [C][sh][dw] -> [C][dh][dw]
+__global__ void scale_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, long planes_rows, int sw, int dw) {
+  const long total = planes_rows * dw;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long row = i / dw;
+    const int x = (int)(i - row * dw);
+    dst[i] = scale_sample(src + row * sw, 1, sw, dw, x);
+  }
+}
+__global__ void scale_cols_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int sh, int dh, int dw) {
+  const long total = (long)C * dh * dw;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % dw);
+    const int y = (int)((i / dw) % dh);
+    const int c = (int)(i / ((long)dw * dh));
+    dst[i] = scale_sample(src + (long)c * sh * dw + x, dw, sh, dh, y);
+  }
+}
+void launch_scale_image(const float* src, int C, int sh, int sw, float* tmp, float* dst, int dh, int dw, cudaStream_t st) {
+  const long t1 = (long)C * sh * dw, t2 = (long)C * dh * dw;
+  scale_rows_kernel<<<(int)std::min<long>((t1 + 255) / 256, 148 * 16), 256, 0, st>>>(src, tmp, (long)C * sh, sw, dw);
+  scale_cols_kernel<<<(int)std::min<long>((t2 + 255) / 256, 148 * 16), 256, 0, st>>>(tmp, dst, C, sh, dh, dw);
+}
+
 }  // namespace frcnn

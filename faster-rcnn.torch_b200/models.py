@@ -172,6 +172,15 @@ class Model:
             self.pack_weights()
         return stats
 
+    def scale_frame(self, img, width, height):
+        """image.scale(img, width, height) ('bilinear') on the GPU: [C][h][w] fp32 CUDA tensor -> [C][height][width]
+        (BatchIterator.lua:49-52; frcnn_scale_frame)."""
+        img = img.to(torch.float32).contiguous()
+        out = torch.empty((img.shape[0], int(height), int(width)), dtype=torch.float32, device=img.device)
+        check(self.ctx, lib().frcnn_scale_frame(self.ctx, ffi.cast("const float*", img.data_ptr()), img.shape[0], img.shape[1],
+                                                img.shape[2], ffi.cast("float*", out.data_ptr()), int(height), int(width)))
+        return out
+
     def normalize_frame(self, img, rgb2yuv=False, centering=True, scaling=True, contrastive_width=7):
         """The frame normalisation of BatchIterator:processImage / load_image (BatchIterator.lua:146-161,
         utilities.lua:211-212) on the GPU, in place on a [3][H][W] fp32 CUDA tensor (frcnn_normalize_frame)."""
@@ -399,6 +408,12 @@ class Model:
         r, n, v, b = ffi.new("int*"), ffi.new("int*"), ffi.new("int*"), ffi.new("int64_t*")
         check(self.ctx, lib().frcnn_dp_info(self.ctx, r, n, v, b))
         return dict(comm_rank=int(r[0]), comm_nranks=int(n[0]), nccl_version=int(v[0]), bytes_reduced=int(b[0]))
+
+
+def find_target_size(orig_w, orig_h, target_smaller_side, max_pixel_size):  # utilities.lua:188-204
+    w, h = ffi.new("int*"), ffi.new("int*")
+    check(None, lib().frcnn_find_target_size(int(orig_w), int(orig_h), float(target_smaller_side), float(max_pixel_size), w, h))
+    return int(w[0]), int(h[0])
 
 
 def create_model(cfg, layers, anchor_nets, class_layers, **kw):  # model_utilities.lua:126-136

@@ -300,6 +300,16 @@ int frcnn_last_conv_profile(const frcnn_ctx* ctx, float* ms, double* flops, int*
 int frcnn_normalize_frame(frcnn_ctx* ctx, float* img_dev, int h, int w, int rgb2yuv, int centering, int scaling,
                           int contrastive_width);
 
+/* find_target_size (utilities.lua:188-204): the frame size BatchIterator:processImage / main.lua:199 resize to.  Host only. */
+int frcnn_find_target_size(int orig_w, int orig_h, double target_smaller_side, double max_pixel_size, int* w, int* h);
+/* image.scale(img, dst_w, dst_h), default 'bilinear' mode (BatchIterator.lua:49-52, main.lua:200): src_dev [c][src_h][src_w]
+ * fp32 -> dst_dev [c][dst_h][dst_w].  Rows first, then columns; enlarging an axis interpolates linearly with scale
+ * (src - 1) / (dst - 1), shrinking averages the source interval with fractional end weights (torch/image's
+ * Main_scaleLinear_rowcol, un-vendored: restated in oracle/preprocess.py, bit-exact against that restatement, parity
+ * unpinned).  src_dev may be the frame still in page-locked host memory mapped into the device (the copy then rides in
+ * the first pass). */
+int frcnn_scale_frame(frcnn_ctx* ctx, const float* src_dev, int c, int src_h, int src_w, float* dst_dev, int dst_h, int dst_w);
+
 /* ---- anchor labelling: replaces Anchors:findPositive / Anchors:sampleNegative (Anchors.lua:147-235; called per
  *      training image by BatchIterator.lua:200-225) -- SURVEY 8f row 1 ------------------------------------------ */
 typedef struct frcnn_anchor_ref {

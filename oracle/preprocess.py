@@ -70,3 +70,71 @@ def normalize_frame(img, rgb_to_yuv=False, centering=True, scaling=True, contras
     if contrastive_width:
         x[0] = contrastive_normalization(x[0], contrastive_width)
     return x
+
+
+# ---------------------------------------------------------------------------------------------- resize
+def find_target_size(orig_w, orig_h, target_smaller_side, max_pixel_size):
+    """utilities.lua:188-204 (Lua numbers are doubles; math.floor(x + 0.5))."""
+    import math
+    if orig_h < orig_w:
+        w = min(orig_w * target_smaller_side / orig_h, max_pixel_size)
+        h = math.floor(orig_h * w / orig_w + 0.5)
+        w = math.floor(w + 0.5)
+    else:
+        h = min(orig_h * target_smaller_side / orig_w, max_pixel_size)
+        w = math.floor(orig_w * h / orig_h + 0.5)
+        h = math.floor(h + 0.5)
+    assert w >= 1 and h >= 1
+    return int(w), int(h)
+
+
+def _scale_linear_1d(src, dst_len):
+    """image's Main_scaleLinear_rowcol along the LAST axis of a float32 array (torch/image generic/image.c, 2015; un-vendored,
+    restated from the published source -- PARITY UNPINNED): enlarging = linear interpolation between the two neighbours with
+    scale (src_len - 1) / (dst_len - 1), the last sample copied; shrinking = the mean of the source interval
+    [di * scale, (di + 1) * scale) with fractional weights at both ends, scale = src_len / dst_len; float32 arithmetic in
+    the C loop's order."""
+    f32 = np.float32
+    src = np.ascontiguousarray(src, dtype=f32)
+    src_len = src.shape[-1]
+    dst = np.empty(src.shape[:-1] + (dst_len,), dtype=f32)
+    if dst_len > src_len:
+        if src_len == 1:
+            dst[...] = src
+            return dst
+        scale = f32(src_len - 1) / f32(dst_len - 1)
+        for di in range(dst_len - 1):
+            si_f = f32(di) * scale
+            si_i = int(si_f)
+            si_f = f32(si_f - f32(si_i))
+            dst[..., di] = f32(1) * (f32(1) - si_f) * src[..., si_i] + si_f * src[..., si_i + 1]
+        dst[..., dst_len - 1] = src[..., src_len - 1]
+    elif dst_len < src_len:
+        scale = f32(src_len) / f32(dst_len)
+        si0_i, si0_f = 0, f32(0)
+        for di in range(dst_len):
+            si1_f = f32(di + 1) * scale
+            si1_i = int(si1_f)
+            si1_f = f32(si1_f - f32(si1_i))
+            acc = (f32(1) - si0_f) * src[..., si0_i]
+            n = f32(1) - si0_f
+            for si in range(si0_i + 1, si1_i):
+                acc = acc + src[..., si]
+                n = f32(n + f32(1))
+            if si1_i < src_len:
+                acc = acc + si1_f * src[..., si1_i]
+                n = f32(n + si1_f)
+            dst[..., di] = acc / n
+            si0_i, si0_f = si1_i, si1_f
+    else:
+        dst[...] = src
+    return dst
+
+
+def scale_image(img, width, height):
+    """image.scale(img, width, height) in its default 'bilinear' mode on a [C][H][W] float32 array: rows first (width) into
+    a [C][H][width] temporary, then columns (BatchIterator.lua:49-52 via transform_example)."""
+    a = np.asarray(img, dtype=np.float32)
+    tmp = _scale_linear_1d(a, int(width))
+    out = _scale_linear_1d(np.swapaxes(tmp, -1, -2), int(height))
+    return np.ascontiguousarray(np.swapaxes(out, -1, -2))

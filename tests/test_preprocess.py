@@ -46,3 +46,37 @@ def test_gpu_normalize_frame(F, small_model, h, w, yuv):
     got2 = small_model.normalize_frame(img.clone().cuda(), rgb2yuv=yuv, contrastive_width=0).cpu()
     want2 = OP.normalize_frame(img, rgb_to_yuv=yuv, contrastive_width=0)
     assert (got2 - want2).abs().max().item() <= 2e-6 * max(want2.abs().max().item(), 1.0)
+
+
+def test_find_target_size_host_equals_oracle():
+    import frcnn_b200 as F
+    for (w, h) in [(1280, 720), (720, 1280), (800, 450), (500, 375), (333, 500), (4000, 600), (600, 4000), (17, 17), (1, 1), (1000, 999)]:
+        for tss, mps in [(450, 1000), (480, 1000), (600, 800)]:
+            assert F.find_target_size(w, h, tss, mps) == OP.find_target_size(w, h, tss, mps)
+    assert OP.find_target_size(1280, 720, 450, 1000) == (800, 450)        # the headline frame size
+    assert OP.find_target_size(4000, 600, 450, 1000) == (1000, 150)       # max_pixel_size caps the long side
+
+
+def test_oracle_scale_known_answers():
+    # enlarging 3 -> 5 samples: scale (3-1)/(5-1) = 0.5 -> positions 0, .5, 1, 1.5 and the last sample copied
+    a = np.array([[0.0, 2.0, 6.0]], dtype=np.float32)
+    assert np.array_equal(OP._scale_linear_1d(a, 5), np.array([[0.0, 1.0, 2.0, 4.0, 6.0]], dtype=np.float32))
+    # shrinking 6 -> 4: intervals of 1.5 samples with fractional end weights
+    b = np.arange(6, dtype=np.float32)[None]
+    want = [(0 + 0.5 * 1) / 1.5, (0.5 * 1 + 2) / 1.5, (3 + 0.5 * 4) / 1.5, (0.5 * 4 + 5) / 1.5]
+    assert np.allclose(OP._scale_linear_1d(b, 4), np.array([want], dtype=np.float32), rtol=1e-6)
+    c = np.random.default_rng(0).uniform(0, 1, (3, 9, 7)).astype(np.float32)
+    assert np.array_equal(OP.scale_image(c, 7, 9), c)                      # same size: a copy
+    assert OP.scale_image(c, 12, 4).shape == (3, 4, 12)
+    assert abs(float(OP.scale_image(np.full((1, 20, 30), 0.25, np.float32), 11, 47).max()) - 0.25) < 1e-6
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sh,sw,dh,dw", [(720, 1280, 450, 800), (375, 500, 450, 600), (100, 60, 37, 91), (5, 1, 9, 4), (64, 64, 64, 64)])
+def test_gpu_scale_frame_bit_exact_vs_restatement(F, small_model, sh, sw, dh, dw):
+    rng = np.random.default_rng(sh * 7 + dw)
+    img = rng.uniform(0, 1, (3, sh, sw)).astype(np.float32)
+    want = OP.scale_image(img, dw, dh)
+    got = small_model.scale_frame(torch.from_numpy(img).cuda(), dw, dh).cpu().numpy()
+    assert got.shape == want.shape
+    assert np.array_equal(got, want)
