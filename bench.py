@@ -626,12 +626,25 @@ def bench_train(hs, model, steps, warmup, batch, with_cpu):
         loss, _, _ = objective(batch_list, seed=state["step"])
         state["loss"] = loss
 
+    prefetch = F.FramePrefetcher(device=hs.local, depth=2 * B)
+
+    def upload_next():
+        for hf in host_frames:
+            prefetch.submit(hf)
+
     def step_e2e():
-        # objective.lua:66: img = batch[i].img:cuda() -- every frame of the step comes from page-locked host memory; the
-        # loss scalars come back (the objective reads them on the host)
-        for b, hf in zip(batch_list, host_frames):
-            b["img"].copy_(hf, non_blocking=True)
+        # objective.lua:66: img = batch[i].img:cuda() -- every frame of the step comes from page-locked host memory (one
+        # asynchronous copy per frame on the prefetcher's stream, enqueued one step ahead: BatchIterator's job); the loss
+        # scalars come back (the objective reads them on the host)
+        if prefetch.pending() == 0:
+            upload_next()
+        old = [b["img"] for b in batch_list]
+        for b in batch_list:
+            b["img"] = prefetch.get()
+        upload_next()                      # the NEXT step's frames go up while this step computes
         step()
+        for t in old:
+            prefetch.recycle(t)
 
     def k_of(fn):
         def run():
@@ -671,14 +684,16 @@ def bench_train(hs, model, steps, warmup, batch, with_cpu):
                 spread=spread, clocks=clocks, gpu_launches=int(launches * steps),
                 e2e=dict(value=total / (ms_e2e * 1e-3), unit="images/s", h2d_bytes_per_step=int(B * 3 * h * w * 4 + B * 256 * 96),
                          d2h_bytes_per_step=int(B * 16 + 28), spread=spread_e2e,
-                         note="lossAndGradient with every frame copied from page-locked host memory inside the step (objective.lua:66) "
-                              "plus the example records; the loss sums and counters come back"),
+                         note="lossAndGradient with every frame copied from page-locked host memory inside the timed region (objective.lua:66; "
+                              "FramePrefetcher: asynchronous copies on a side stream, one step ahead) plus the example records; the loss "
+                              "sums and counters come back"),
                 roofline=dict(bound="tensor", kernel="conv_igemm_kernel / conv_halo_kernel / conv_wgrad_halo_kernel (fwd + dgrad + wgrad launches of a step)",
                               achieved=3 * fwd * B / (ms / steps * 1e-3) / 1e12, peak=hs.pk["bf16_sustained"], unit="TFLOP/s",
                               frac=3 * fwd * B / (ms / steps * 1e-3) / 1e12 / hs.pk["bf16_sustained"], traffic=None,
                               peak_source=hs.pk["source"] + " bf16 sustained",
                               note="3 x forward conv FLOPs per frame over the whole step (every other kernel and the all-reduce in the "
                                    "denominator): lower bound of the tcgen05 kernels' own rate"))
+    prefetch.close()
     if collective:
         line["collective"] = collective
     if hs.rank == 0 and with_cpu and hs.world == 1:

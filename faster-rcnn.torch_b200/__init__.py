@@ -13,4 +13,5 @@ from .detector import Detector, DetectorPipeline, SpatialAdaptiveMaxPooling, ext
 from .shard import reduce_timing, shard_frames, shard_segments  # noqa: F401
 from .objective import allreduce_gradient, clean_anchors, create_objective, dp_allreduce, dp_init  # noqa: F401
 from .optim import rmsprop, rmsprop_step  # noqa: F401
+from .batch_iterator import FramePrefetcher  # noqa: F401
 from . import t7  # noqa: F401,E402  (Torch7 .t7 snapshots: utilities.lua:113-134)

@@ -104,8 +104,10 @@ struct frcnn_ctx {
   int feat_c = 0;
   std::vector<std::vector<std::array<int, 6>>> loc;  // heads..., ROI
   std::vector<float> w_lut, h_lut;
+  std::vector<double> cen_x, cen_y;   // [scale][200] cell centres (Anchors.lua:40-41,49-50): the findNearby bins
   float* d_w_lut = nullptr;
   float* d_h_lut = nullptr;
+  double* d_cen = nullptr;            // cen_x | cen_y
   LocalizerDev roi_loc;
 
   // training (pnet:backward): gradient views, per-block winners / gradient accumulators, two scratch gradient maps
@@ -325,6 +327,8 @@ static void build_luts(frcnn_ctx* c) {
   const int S = (int)c->scales.size();
   c->w_lut.assign((size_t)S * 3 * LUT_EXTENT * 2, 0.f);
   c->h_lut.assign((size_t)S * 3 * LUT_EXTENT * 2, 0.f);
+  c->cen_x.assign((size_t)S * LUT_EXTENT, 0.0);
+  c->cen_y.assign((size_t)S * LUT_EXTENT, 0.0);
   for (int i = 0; i < S; ++i) {
     const double s = c->scales[i];
     const double a = s / sqrt(2.0);
@@ -334,6 +338,7 @@ static void build_luts(frcnn_ctx* c) {
         double in[4] = {0, (double)(y - 1), 0, (double)y}, r[4];
         feature_to_input(c->loc[i], in, r);
         const double cy = (r[1] + r[3]) / 2;
+        c->cen_y[(size_t)i * LUT_EXTENT + (y - 1)] = cy;
         const double mn = cy - asp[j][1] * 0.5;  // Rect.fromCenterWidthHeight (Rect.lua:30-36)
         c->h_lut[(((size_t)i * 3 + j) * LUT_EXTENT + (y - 1)) * 2 + 0] = (float)mn;
         c->h_lut[(((size_t)i * 3 + j) * LUT_EXTENT + (y - 1)) * 2 + 1] = (float)(mn + asp[j][1]);
@@ -342,6 +347,7 @@ static void build_luts(frcnn_ctx* c) {
         double in[4] = {(double)(x - 1), 0, (double)x, 0}, r[4];
         feature_to_input(c->loc[i], in, r);
         const double cx = (r[0] + r[2]) / 2;
+        c->cen_x[(size_t)i * LUT_EXTENT + (x - 1)] = cx;
         const double mn = cx - asp[j][0] * 0.5;
         c->w_lut[(((size_t)i * 3 + j) * LUT_EXTENT + (x - 1)) * 2 + 0] = (float)mn;
         c->w_lut[(((size_t)i * 3 + j) * LUT_EXTENT + (x - 1)) * 2 + 1] = (float)(mn + asp[j][0]);
@@ -474,6 +480,9 @@ static void ensure_luts_dev(frcnn_ctx* c) {
   FRCNN_CUDA_TRY(cudaMalloc(&c->d_h_lut, c->h_lut.size() * sizeof(float)));
   FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_w_lut, c->w_lut.data(), c->w_lut.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
   FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_h_lut, c->h_lut.data(), c->h_lut.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  FRCNN_CUDA_TRY(cudaMalloc(&c->d_cen, (c->cen_x.size() + c->cen_y.size()) * sizeof(double)));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_cen, c->cen_x.data(), c->cen_x.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(c->d_cen + c->cen_x.size(), c->cen_y.data(), c->cen_y.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
 }
 
@@ -1921,6 +1930,7 @@ int frcnn_destroy(frcnn_ctx* c) {
   for (auto& f : c->fcs) if (f.w_packed) cudaFree(f.w_packed);
   if (c->d_w_lut) cudaFree(c->d_w_lut);
   if (c->d_h_lut) cudaFree(c->d_h_lut);
+  if (c->d_cen) cudaFree(c->d_cen);
   if (c->scratch) cudaFree(c->scratch);
   if (c->nms_stage) cudaFree(c->nms_stage);
   if (c->d_img) cudaFree(c->d_img);
@@ -2655,6 +2665,51 @@ int frcnn_find_positive(frcnn_ctx* c, const double* rois_host, int n_rois, const
     }
     FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
     *n_out = at;
+  }
+  API_END(c)
+}
+
+int frcnn_find_nearby_negative(frcnn_ctx* c, const frcnn_anchor_ref* pos_host, int n_pos, double neg_threshold,
+                               frcnn_anchor_ref* out_host, int* out_pos_host, int cap, int* n_out) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(n_out && cap >= 0 && n_pos >= 0 && (n_pos == 0 || pos_host), FRCNN_E_INVALID, "bad argument");
+  *n_out = 0;
+  if (n_pos > 0) {
+    frcnn::ensure_luts_dev(c);
+    const int n_scales = (int)c->w_lut.size() / (3 * frcnn::LUT_CELLS * 2);
+    for (int i = 0; i < n_pos; ++i)
+      FRCNN_REQUIRE(pos_host[i].layer >= 1 && pos_host[i].layer <= n_scales && pos_host[i].aspect >= 1 && pos_host[i].aspect <= 3 &&
+                        pos_host[i].y >= 1 && pos_host[i].y <= frcnn::LUT_CELLS && pos_host[i].x >= 1 && pos_host[i].x <= frcnn::LUT_CELLS,
+                    FRCNN_E_INVALID, "find_nearby: anchor index out of the LUT range");
+    const size_t b_pos = ((size_t)n_pos * sizeof(frcnn_anchor_ref) + 255) & ~size_t(255);
+    const size_t b_out = ((size_t)cap * sizeof(frcnn_anchor_ref) + 255) & ~size_t(255);
+    const size_t b_idx = ((size_t)cap * sizeof(int) + 255) & ~size_t(255);
+    uint8_t* mem = (uint8_t*)frcnn::ensure_scratch(c, b_pos + b_out + b_idx + 256);
+    frcnn::FindNearbyParams p;
+    p.w_lut = c->d_w_lut; p.h_lut = c->d_h_lut; p.n_scales = n_scales;
+    p.cen_x = c->d_cen; p.cen_y = c->d_cen + c->cen_x.size();
+    p.pos = (const frcnn_anchor_ref*)mem;
+    p.n_pos = n_pos;
+    p.neg_threshold = neg_threshold;
+    p.out = (frcnn_anchor_ref*)(mem + b_pos);
+    p.out_pos = (int*)(mem + b_pos + b_out);
+    p.cap = cap;
+    p.result = (int*)(mem + b_pos + b_out + b_idx);
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(mem, pos_host, (size_t)n_pos * sizeof(frcnn_anchor_ref), cudaMemcpyHostToDevice, c->stream));
+    frcnn::launch_find_nearby(p, c->stream);
+    ++c->launches;
+    int total = 0;
+    FRCNN_CUDA_TRY(cudaMemcpyAsync(&total, p.result, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    FRCNN_REQUIRE(total <= cap, FRCNN_E_OVERFLOW, "find_nearby: more entries than the output capacity");
+    FRCNN_REQUIRE(total == 0 || (out_host && out_pos_host), FRCNN_E_INVALID, "null output");
+    if (total > 0) {
+      FRCNN_CUDA_TRY(cudaMemcpyAsync(out_host, p.out, (size_t)total * sizeof(frcnn_anchor_ref), cudaMemcpyDeviceToHost, c->stream));
+      FRCNN_CUDA_TRY(cudaMemcpyAsync(out_pos_host, p.out_pos, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
+    *n_out = total;
   }
   API_END(c)
 }

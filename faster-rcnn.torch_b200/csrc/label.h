@@ -40,4 +40,19 @@ struct SampleNegativeParams {
 };
 void launch_sample_negative(const SampleNegativeParams& p, cudaStream_t st);
 
+// Anchors:findNearby + the nearby-aversion filter of BatchIterator.lua:206-217
+struct FindNearbyParams {
+  const float *w_lut, *h_lut;   // [n_scales][3][200][2]
+  const double *cen_x, *cen_y;  // [n_scales][200] cell centres (Anchors.lua:40-41,49-50), doubles
+  int n_scales;
+  const frcnn_anchor_ref* pos;  // [n_pos] the positive anchors p[1]
+  int n_pos;
+  double neg_threshold;
+  frcnn_anchor_ref* out;        // [cap]
+  int* out_pos;                 // [cap] 0-based index of the positive each entry belongs to
+  int cap;
+  int* result;                  // {n_out (may exceed cap: only cap are written)}
+};
+void launch_find_nearby(const FindNearbyParams& p, cudaStream_t st);
+
 }  // namespace frcnn

@@ -366,4 +366,66 @@ void launch_sample_negative(const SampleNegativeParams& p, cudaStream_t st) {
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------- findNearby
+// BatchIterator.lua:206-217 (cfg.nearby_aversion): for every positive anchor p, Anchors:findNearby(p:center()) -- the
+// anchors whose cell centre shares p's 16-pixel bin on both axes (Anchors.lua:22-30,69-84), in the order the Lua tables
+// yield them: (scale, aspect, y cell, x cell) ascending -- kept when Rect.IoU(p, a) < negative_threshold.  One CTA, a thread
+// per positive, ordered output through a block scan (positives in list order, at most 4 x 3 x 2 x 2 entries each).
+static constexpr int NEARBY_BIN = 16;   // Anchors.lua:5
+static constexpr int NEARBY_MAX = 64;   // per positive and (scale, aspect): cells per bin along an axis are <= 16 / stride
+
+__device__ __forceinline__ void anchor_rect(const float* w_lut, const float* h_lut, int ij, int y, int x, double r[4]) {
+  const float* w = w_lut + ((size_t)ij * LUT_CELLS + (x - 1)) * 2;
+  const float* h = h_lut + ((size_t)ij * LUT_CELLS + (y - 1)) * 2;
+  r[0] = (double)w[0]; r[1] = (double)h[0]; r[2] = (double)w[1]; r[3] = (double)h[1];
+}
+
+template <bool WRITE>
+__device__ __forceinline__ int nearby_of(const FindNearbyParams& p, int pi, frcnn_anchor_ref* out, int* out_pos, int at) {
+  const frcnn_anchor_ref a = p.pos[pi];
+  double pr[4];
+  anchor_rect(p.w_lut, p.h_lut, (a.layer - 1) * 3 + (a.aspect - 1), a.y, a.x, pr);
+  const double cx = (pr[0] + pr[2]) / 2, cy = (pr[1] + pr[3]) / 2;     // Rect:center (Rect.lua:65-67)
+  const double bx = floor(cx / NEARBY_BIN), by = floor(cy / NEARBY_BIN);
+  int n = 0;
+  for (int i = 0; i < p.n_scales; ++i) {
+    const double* ceny = p.cen_y + (size_t)i * LUT_CELLS;
+    const double* cenx = p.cen_x + (size_t)i * LUT_CELLS;
+    for (int j = 0; j < 3; ++j) {
+      for (int vy = 1; vy <= LUT_CELLS; ++vy) {
+        if (floor(ceny[vy - 1] / NEARBY_BIN) != by) continue;
+        for (int vx = 1; vx <= LUT_CELLS; ++vx) {
+          if (floor(cenx[vx - 1] / NEARBY_BIN) != bx) continue;
+          double r[4];
+          anchor_rect(p.w_lut, p.h_lut, i * 3 + j, vy, vx, r);
+          if (rect_iou(pr, r[0], r[1], r[2], r[3]) < p.neg_threshold) {
+            if (WRITE && at + n < p.cap) {
+              out[at + n] = frcnn_anchor_ref{i + 1, j + 1, vy, vx};
+              out_pos[at + n] = pi;
+            }
+            ++n;
+          }
+        }
+      }
+    }
+  }
+  return n;
+}
+
+__global__ void __launch_bounds__(LB_THREADS) find_nearby_kernel(FindNearbyParams p) {
+  __shared__ int warp_buf[LB_THREADS / 32];
+  int base = 0;
+  for (int p0 = 0; p0 < p.n_pos; p0 += LB_THREADS) {
+    const int pi = p0 + (int)threadIdx.x;
+    const int mine = pi < p.n_pos ? nearby_of<false>(p, pi, nullptr, nullptr, 0) : 0;
+    int total;
+    const int at = block_excl_sum(mine, warp_buf, total);
+    if (pi < p.n_pos && mine) nearby_of<true>(p, pi, p.out, p.out_pos, base + at);
+    base += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) p.result[0] = base;
+}
+void launch_find_nearby(const FindNearbyParams& p, cudaStream_t st) { find_nearby_kernel<<<1, LB_THREADS, 0, st>>>(p); }
+
 }  // namespace frcnn

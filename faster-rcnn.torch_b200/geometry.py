@@ -121,6 +121,22 @@ class Anchors:
             break
         return [(self.get(out[i].layer, out[i].aspect, out[i].y, out[i].x), roi_list[out_roi[i]]) for i in range(n_out[0])]
 
+    def nearbyNegative(self, positive, neg_threshold):  # BatchIterator.lua:206-217 (before shuffle_n)
+        """The nearby-aversion candidates of the positives [(anchor_rect, roi), ...]: findNearby(p:center()) filtered by
+        Rect.IoU(p, a) < neg_threshold, in the reference's order, as one launch (frcnn_find_nearby_negative).  Returns
+        [(anchor_rect,), ...] like the `nearby_negative` table."""
+        n = len(positive)
+        if n == 0:
+            return []
+        pos = ffi.new("frcnn_anchor_ref[]", n)
+        for i, p in enumerate(positive):
+            a = p[0]
+            pos[i].layer, pos[i].aspect, pos[i].y, pos[i].x = a.layer, a.aspect, a.index[1], a.index[2]
+        cap = 64 * n
+        out, out_pos, n_out = ffi.new("frcnn_anchor_ref[]", cap), ffi.new("int[]", cap), ffi.new("int*")
+        check(self.model.ctx, lib().frcnn_find_nearby_negative(self.model.ctx, pos, n, neg_threshold, out, out_pos, cap, n_out))
+        return [(self.get(out[i].layer, out[i].aspect, out[i].y, out[i].x),) for i in range(n_out[0])]
+
     def sampleNegative(self, image_rect, roi_list, neg_threshold, count, rnd, retry=0, return_retry=False):  # Anchors.lua:197-235
         """`rnd`: numpy uint32 array of torch.random() values, three per trial (the RNG contract: the caller owns the
         generator).  Returns ([(anchor_rect,), ...], trials consumed, finished[, retry]); `retry` continues a loop whose

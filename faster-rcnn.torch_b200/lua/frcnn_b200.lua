@@ -477,6 +477,24 @@ function M.find_positive(model, anchors, roi_list, clip_rect, pos_threshold, neg
   return matches
 end
 
+-- The nearby-aversion candidates of BatchIterator.lua:206-217 (before shuffle_n) as one launch: positives =
+-- { {anchor_rect, roi}, ... }; returns { {anchor_rect}, ... } in the reference's order.
+function M.find_nearby_negative(model, anchors, positives, neg_threshold)
+  local ctx, n = model.b200.ctx, #positives
+  if n == 0 then return {} end
+  local pos = ffi.new('frcnn_anchor_ref[?]', n)
+  for i, p in ipairs(positives) do
+    local a = p[1]
+    pos[i - 1].layer, pos[i - 1].aspect, pos[i - 1].y, pos[i - 1].x = a.layer, a.aspect, a.index[2], a.index[3]
+  end
+  local cap = 64 * n
+  local out, out_pos, cnt = ffi.new('frcnn_anchor_ref[?]', cap), ffi.new('int[?]', cap), ffi.new('int[1]')
+  check(ctx, C.frcnn_find_nearby_negative(ctx, pos, n, neg_threshold, out, out_pos, cap, cnt))
+  local found = {}
+  for i = 0, cnt[0] - 1 do found[i + 1] = { anchors:get(out[i].layer, out[i].aspect, out[i].y, out[i].x) } end
+  return found
+end
+
 -- Anchors:sampleNegative (Anchors.lua:197-235).  The generator stays in Lua: three torch.random() values per trial are
 -- drawn here and handed over.  The reference consumes exactly three values per trial it runs, so the generator is put
 -- back and advanced by 3 * used afterwards: the Lua random stream stays identical to the reference's.  If the drawn

@@ -323,6 +323,12 @@ typedef struct frcnn_anchor_ref {
 int frcnn_find_positive(frcnn_ctx* ctx, const double* rois_host, int n_rois, const double* clip_host,
                         double pos_threshold, double neg_threshold, int include_best, frcnn_anchor_ref* out_host,
                         int* out_roi_host, int cap, int* n_out);
+/* The nearby-aversion list of BatchIterator.lua:206-217 (before shuffle_n): for every positive anchor p (in list order)
+ * Anchors:findNearby(p:center()) (Anchors.lua:69-84: the anchors whose cell centre falls into p's 16-pixel bin on both axes,
+ * in the order of the Lua bin tables = scale, aspect, y cell, x cell ascending), kept when Rect.IoU(p, a) < neg_threshold.
+ * out_pos_host[k] = 0-based index of the positive entry k belongs to. */
+int frcnn_find_nearby_negative(frcnn_ctx* ctx, const frcnn_anchor_ref* pos_host, int n_pos, double neg_threshold,
+                               frcnn_anchor_ref* out_host, int* out_pos_host, int cap, int* n_out);
 /* Anchors:sampleNegative(image_rect, roi_list, neg_threshold, count).  The reference draws three torch.random()
  * values per trial (range, x, y); the caller supplies that stream: rnd_host holds 3 * n_trials uint32 values.  Returns
  * the accepted anchors in order, how many trials the loop consumed (so the caller can keep its generator in step) and

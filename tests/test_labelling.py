@@ -137,3 +137,28 @@ def test_gpu_sample_negative_continued_stream(F, small_model):
     assert part == [] and used == 300 and not finished and retry == 300
     part, used, finished, retry = ga.sampleNegative(img, rois, -1.0, 5, rnd[3 * 300:3 * 900], retry=retry, return_retry=True)
     assert part == [] and used == 200 and finished
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n,thr", [(0, 4, 0.3), (1, 8, 0.25), (2, 8, 0.9), (3, 2, 0.0)])
+def test_gpu_nearby_negative_bit_exact(F, small_model, seed, n, thr):
+    """cfg.nearby_aversion (BatchIterator.lua:206-217): for every positive anchor, Anchors:findNearby(center) filtered by
+    Rect.IoU(p, a) < negative_threshold -- the device list equals the restated Lua loops entry for entry, in order."""
+    oa = _oracle_anchors()
+    ga = F.Anchors(small_model)
+    positive = oa.findPositive(_rois(seed, n), Rect(0, 0, 800, 450), 0.6, 0.3, True)
+    assert len(positive) > 0
+    want = []
+    for p in positive:
+        cx, cy = p[0].center()
+        for a in oa.findNearby(cx, cy):
+            if Rect.IoU(p[0], a) < thr:
+                want.append(a)
+    got = ga.nearbyNegative(positive, thr)
+    assert [_ref(a) for (a,) in got] == [_ref(a) for a in want]
+    if thr >= 0.25:
+        assert len(want) > 0
+    # the host mirror's own findNearby agrees with the oracle's bins
+    for p in positive[:20]:
+        cx, cy = p[0].center()
+        assert [_ref(a) for a in ga.findNearby(cx, cy)] == [_ref(a) for a in oa.findNearby(cx, cy)]

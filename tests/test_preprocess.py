@@ -80,3 +80,33 @@ def test_gpu_scale_frame_bit_exact_vs_restatement(F, small_model, sh, sw, dh, dw
     got = small_model.scale_frame(torch.from_numpy(img).cuda(), dw, dh).cpu().numpy()
     assert got.shape == want.shape
     assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_frame_prefetcher_pipeline(F, small_model):
+    """The asynchronous upload + resize + normalise pipeline (side stream, events) yields, in submission order, exactly what
+    the same library calls yield synchronously; a consumer on another stream sees complete frames."""
+    rng = np.random.default_rng(5)
+    frames = [torch.from_numpy(rng.uniform(0, 1, (3, 360 + 40 * i, 640)).astype(np.float32)).pin_memory() for i in range(5)]
+    norm = dict(rgb2yuv=True, centering=True, scaling=True, contrastive_width=7)
+    pf = F.FramePrefetcher(device=0, depth=2, target_smaller_side=450, max_pixel_size=1000, normalization=norm)
+    try:
+        want = []
+        for f in frames:
+            w, h = F.find_target_size(f.shape[2], f.shape[1], 450, 1000)
+            x = small_model.scale_frame(f.cuda(), w, h)
+            want.append(small_model.normalize_frame(x, rgb2yuv=True).clone())
+        got = []
+        pf.submit(frames[0])
+        pf.submit(frames[1])
+        for i in range(len(frames)):
+            x = pf.get()
+            got.append((x.sum() * 0 + x).clone())          # consumed on the current stream, after the event
+            if i + 2 < len(frames):
+                pf.submit(frames[i + 2])
+        torch.cuda.synchronize()
+        for g, wnt in zip(got, want):
+            assert g.shape == wnt.shape and torch.equal(g, wnt)
+        assert pf.pending() == 0
+    finally:
+        pf.close()
