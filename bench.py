@@ -626,11 +626,11 @@ def bench_train(hs, model, steps, warmup, batch, with_cpu):
         loss, _, _ = objective(batch_list, seed=state["step"])
         state["loss"] = loss
 
-    prefetch = F.FramePrefetcher(device=hs.local, depth=2 * B)
+    prefetch = F.FramePrefetcher(device=hs.local, depth=2)
+    host_stack = torch.stack(host_frames).pin_memory()    # the step's frames, page-locked, one asynchronous copy
 
     def upload_next():
-        for hf in host_frames:
-            prefetch.submit(hf)
+        prefetch.submit(host_stack)
 
     def step_e2e():
         # objective.lua:66: img = batch[i].img:cuda() -- every frame of the step comes from page-locked host memory (one
@@ -638,13 +638,14 @@ def bench_train(hs, model, steps, warmup, batch, with_cpu):
         # scalars come back (the objective reads them on the host)
         if prefetch.pending() == 0:
             upload_next()
-        old = [b["img"] for b in batch_list]
-        for b in batch_list:
-            b["img"] = prefetch.get()
+        stack = prefetch.get()
+        for i, b in enumerate(batch_list):
+            b["img"] = stack[i]
         upload_next()                      # the NEXT step's frames go up while this step computes
         step()
-        for t in old:
-            prefetch.recycle(t)
+        if state.get("stack") is not None:
+            prefetch.recycle(state["stack"])
+        state["stack"] = stack
 
     def k_of(fn):
         def run():

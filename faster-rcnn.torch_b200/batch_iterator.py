@@ -57,9 +57,19 @@ class FramePrefetcher:
         self._free.setdefault(tuple(t.shape), []).append((t, ev))
 
     def submit(self, host_frame):
-        """host_frame: [3][h][w] fp32 CPU tensor (page-locked for a truly asynchronous copy).  Returns immediately."""
-        assert host_frame.dtype == torch.float32 and host_frame.dim() == 3
+        """host_frame: [3][h][w] fp32 CPU tensor (page-locked for a truly asynchronous copy), or a stack [n][3][h][w] of
+        frames that need no resize / normalisation (one copy for the whole stack).  Returns immediately."""
+        assert host_frame.dtype == torch.float32 and host_frame.dim() in (3, 4)
         L = lib()
+        if host_frame.dim() == 4:
+            assert not self.target and not self.norm, "stacks are uploaded as they are"
+            with torch.cuda.stream(self.stream):
+                raw = self._buffer(host_frame.shape)
+                raw.copy_(host_frame, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+            self._queue.append((raw, ev, None, host_frame))
+            return
         with torch.cuda.stream(self.stream):
             raw = self._buffer(host_frame.shape)
             raw.copy_(host_frame, non_blocking=True)

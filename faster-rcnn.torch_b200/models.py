@@ -347,7 +347,9 @@ class Model:
             keep = [m.to(self.device, torch.float32).reshape(n, -1).contiguous() for m in pnet_masks]
             pm = ffi.new("const float*[]", [ffi.cast("const float*", t.data_ptr()) for t in keep])
         losses = ffi.new("float[]", 4 * n)
-        torch.cuda.synchronize(self.device)
+        # the library's stream must see what torch's current stream produced (the frame stack); NOT a device-wide
+        # synchronize: uploads of the next step's frames on a prefetcher's stream keep running
+        torch.cuda.current_stream(self.device).synchronize()
         check(self.ctx, lib().frcnn_train_batch(self.ctx, ffi.cast("const float*", x.data_ptr()), n, h, w, pp, n_pos, qq, n_neg, pm, sd, losses))
         return [dict(cls=losses[4 * i], reg=losses[4 * i + 1], creg=losses[4 * i + 2], ccls=losses[4 * i + 3]) for i in range(n)]
 
