@@ -2557,6 +2557,22 @@ int frcnn_set_detect_thresholds(frcnn_ctx* c, double fg_prob, float nms_proposal
   return FRCNN_OK;
 }
 
+int frcnn_block_output(frcnn_ctx* c, int block, float* out_dev, int* dims3) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(c->planned && c->ws_n > 0, FRCNN_E_STATE, "no pnet forward has run on this context");
+  FRCNN_REQUIRE(block >= 1 && block <= (int)c->blocks.size() && dims3, FRCNN_E_INVALID, "bad block index");
+  const int C = c->blocks[block - 1].filters, h = c->pool_h[block - 1], w = c->pool_w[block - 1];
+  dims3[0] = C; dims3[1] = h; dims3[2] = w;
+  if (out_dev) {
+    // training forwards store bf16 activations; evaluate-mode forwards the context's operand format
+    frcnn::launch_nhwc_bf16_to_chw_f32(c->pool_out[block - 1], out_dev, c->ws_n, h, w, C, c->stream, c->act_f16);
+    ++c->launches;
+    FRCNN_CUDA_TRY(cudaGetLastError());
+  }
+  API_END(c)
+}
+
 int frcnn_find_target_size(int orig_w, int orig_h, double target_smaller_side, double max_pixel_size, int* w_out, int* h_out) {
   if (orig_w < 1 || orig_h < 1 || !w_out || !h_out) return FRCNN_E_INVALID;
   double w, h;   // Lua numbers are doubles; math.floor(x + 0.5)

@@ -405,6 +405,18 @@ class Model:
     def launch_count(self):
         return int(lib().frcnn_launch_count(self.ctx))
 
+    def block_outputs(self, n=1):
+        """Diagnostic: the pooled output of every conv block of the last pnet forward over `n` frames, fp32 [n][C][h][w]
+        (frcnn_block_output)."""
+        outs, d = [], ffi.new("int[3]")
+        for b in range(1, len(self.layers) + 1):
+            check(self.ctx, lib().frcnn_block_output(self.ctx, b, ffi.NULL, d))
+            t = torch.empty((n, d[0], d[1], d[2]), dtype=torch.float32, device=self.device)
+            check(self.ctx, lib().frcnn_block_output(self.ctx, b, ffi.cast("float*", t.data_ptr()), d))
+            outs.append(t)
+        torch.cuda.synchronize(self.device)
+        return outs
+
     def dp_info(self):
         """frcnn_dp_info: the context's NCCL communicator (nranks 0 = none), NCCL version, bytes all-reduced so far."""
         r, n, v, b = ffi.new("int*"), ffi.new("int*"), ffi.new("int*"), ffi.new("int64_t*")

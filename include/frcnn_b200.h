@@ -378,6 +378,10 @@ int frcnn_dp_allreduce(frcnn_ctx* const* ctxs, int n, float* const* counters_dev
 /* rank / size of the context's communicator (nranks = 0: none), the loaded NCCL's version, bytes all-reduced so far */
 int frcnn_dp_info(const frcnn_ctx* ctx, int* rank, int* nranks, int* nccl_version, int64_t* bytes_reduced);
 
+/* Diagnostic (training parity tests): the pooled output of conv block `block` (1-based) of the LAST pnet forward on this
+ * context as fp32 [n][C][h][w] (Torch layout); dims3 receives {C, h, w}.  out_dev may be NULL to query the shape. */
+int frcnn_block_output(frcnn_ctx* ctx, int block, float* out_dev, int* dims3);
+
 /* ---- low-level conv / GEMM entry (tests, roofline measurement) ---------------------------------------- */
 /* y = prelu(conv(x, w) + bias) * scale on NHWC bf16 activations (passed as uint16 bit patterns).
  * x_dev: [n][h][w][cin]; w_dev: fp32 Torch layout [cout][cin][k][k]; out_dev: [n][ho][wo][cout] bf16, or with

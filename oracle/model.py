@@ -111,14 +111,17 @@ def prelu(x, slope):
 
 
 def pnet_forward(desc, p, img, train=False, dropout_masks=None, dropout_eval_scale=None, quant=None, act_quant=None,
-                 tail_quant="same"):
+                 tail_quant="same", inject_blocks=None):
     """create_proposal_net forward (model_utilities.lua:3-58). img: [3][H][W] fp32 (single image, no batch
     dim, as Detector.lua:33).  Returns [o1..o4 (18xhxw), o5 (CxH/16xW/16)].
     `quant`, if given, is applied to every conv input and weight (e.g. bf16 round trip) -- used by the
     kernel-level tests to separate operand quantisation from accumulation-order effects.  `act_quant` is applied
     to every trunk activation where the CUDA path stores it (after PReLU / dropout, BEFORE the pool), so that
     pooling winners and PReLU signs are decided on the same values; `tail_quant` overrides `quant` for the 1x1
-    convs of the anchor heads (the CUDA path keeps them in fp32: pass None)."""
+    convs of the anchor heads (the CUDA path keeps them in fp32: pass None).  `inject_blocks` ("same forward" mode of the
+    training parity tests): the pooled output of every conv block as ANOTHER implementation computed it ([C][h][w] each);
+    the forward value of the block output becomes that tensor while the derivative stays this graph's (straight-through),
+    so rounding flips of PReLU signs / pooling winners do not compound from block to block."""
     q = quant or (lambda t: t)
     aq = act_quant or (lambda t: t)
     tq = q if tail_quant == "same" else (tail_quant or (lambda t: t))
@@ -137,6 +140,8 @@ def pnet_forward(desc, p, img, train=False, dropout_masks=None, dropout_eval_sca
                     x = x * s
             x = aq(x)
         x = F.max_pool2d(x, 2, 2, ceil_mode=True)  # model_utilities.lua:23
+        if inject_blocks is not None:
+            x = x + (inject_blocks[bi].reshape(x.shape).to(x.dtype) - x).detach()
         block_out.append(x)
     outs = []
     for hi, a in enumerate(desc["anchor_nets"]):

@@ -27,7 +27,7 @@ def clean_anchors(examples, dims):
 
 
 def loss_and_gradient_image(desc, cfg, params, img, positives, negatives, dropout_masks=None, cnet_masks=None,
-                            quant=None, act_quant=None, tail_quant="same", cnet_quant=None):
+                            quant=None, act_quant=None, tail_quant="same", cnet_quant=None, inject_blocks=None):
     """One iteration of the per-image loop of lossAndGradient (objective.lua:65-198).
     positives: list of (anchor Rect with .layer/.aspect/.index, roi dict{rect, class_index}); negatives: list of
     (anchor,).  Returns (losses dict, grads dict name -> tensor, intermediates)."""
@@ -36,7 +36,7 @@ def loss_and_gradient_image(desc, cfg, params, img, positives, negatives, dropou
     bgclass = cfg["class_count"] + 1
     localizer = Localizer(trunk_layer_info(desc["layers"], len(desc["layers"])))
     outputs = M.pnet_forward(desc, p, img, train=True, dropout_masks=dropout_masks, quant=quant, act_quant=act_quant,
-                             tail_quant=tail_quant)
+                             tail_quant=tail_quant, inject_blocks=inject_blocks)
     dims = [tuple(o.shape) for o in outputs]
     positives = clean_anchors(positives, dims)
     negatives = clean_anchors(negatives, dims)
