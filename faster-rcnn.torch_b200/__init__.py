@@ -12,6 +12,6 @@ from .models import Model, create_model, duplo_cfg, find_target_size, imgnet_cfg
 from .detector import Detector, DetectorPipeline, SpatialAdaptiveMaxPooling, extract_roi_pooling_input, roi_pooling_view  # noqa: F401
 from .shard import reduce_timing, shard_frames, shard_segments  # noqa: F401
 from .objective import allreduce_gradient, clean_anchors, create_objective, dp_allreduce, dp_init  # noqa: F401
-from .optim import rmsprop, rmsprop_step  # noqa: F401
+from .optim import rmsprop, rmsprop_step, sync_running_stats  # noqa: F401
 from .batch_iterator import FramePrefetcher  # noqa: F401
 from . import t7  # noqa: F401,E402  (Torch7 .t7 snapshots: utilities.lua:113-134)

@@ -399,7 +399,7 @@ function M.train_image(model, img, positives, negatives, seed)
   for i, x in ipairs(negatives) do fill(neg[i - 1], x[1], nil) end
   local losses = ffi.new('float[4]')
   check(ctx, C.frcnn_train_image(ctx, img:data(), img:size(2), img:size(3), pos, #positives, neg, #negatives, nil, nil,
-                                 seed or 0, losses))
+                                 seed or torch.random(), losses))   -- fresh masks every call, like nn.SpatialDropout
   return losses[0], losses[1], losses[2], losses[3]
 end
 

@@ -71,7 +71,16 @@ def create_objective(model, dist=None, defer_div=False, batched=True):
         dp_init(model, dist)
     from ._lib import lib as _lib
 
-    def lossAndGradient(batch, seed=0):
+    counter = dict(step=0)
+    rank = dist.get_rank() if (dist is not None and dist.is_initialized()) else 0
+
+    def lossAndGradient(batch, seed=None):
+        # the reference draws fresh SpatialDropout / Dropout masks from the global generator on every forward: without an
+        # explicit seed every call gets a new one, and every rank / frame its own (seed mixes step, rank and frame index)
+        counter["step"] += 1
+        if seed is None:
+            seed = counter["step"]
+        frame0 = rank * len(batch)
         model.zero_grad()                                   # gradient:zero()
         model.pnet.training()
         model.cnet.training()
@@ -93,13 +102,16 @@ def create_objective(model, dist=None, defer_div=False, batched=True):
             ps = [clean_anchors(batch[i]["positive"], dims) for i in idx]
             ns = [clean_anchors(batch[i]["negative"], dims) for i in idx]
             packed = None
-            if all("packed" in batch[i] for i in idx):   # example records marshalled once by the caller (BatchIterator)
+            # example records marshalled once by the caller (BatchIterator) -- only usable when cleanAnchors
+            # (objective.lua:32-43) dropped nothing: the records are index-aligned with the uncleaned lists
+            if all("packed" in batch[i] for i in idx) and all(len(p) == len(batch[i]["positive"]) and len(q) == len(batch[i]["negative"])
+                                                              for p, q, i in zip(ps, ns, idx)):
                 packed = [batch[i]["packed"] for i in idx]
             if len(idx) == 1 and not batched:
-                all_losses = [model.train_image(batch[idx[0]]["img"], ps[0], ns[0], seed=seed * 1000003 + idx[0])]
+                all_losses = [model.train_image(batch[idx[0]]["img"], ps[0], ns[0], seed=seed * 1000003 + frame0 + idx[0])]
             else:
-                all_losses = model.train_batch([batch[i]["img"] for i in idx], ps, ns, seeds=[seed * 1000003 + i for i in idx],
-                                               packed=packed)
+                all_losses = model.train_batch([batch[i]["img"] for i in idx], ps, ns,
+                                               seeds=[seed * 1000003 + frame0 + i for i in idx], packed=packed)
             for losses, p, n in zip(all_losses, ps, ns):
                 for k in sums:
                     sums[k] += losses[k]
