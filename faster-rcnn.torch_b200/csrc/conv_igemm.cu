@@ -1929,8 +1929,12 @@ static constexpr int FT_PATCH_PITCH = 2944;  // 24 floats x 10 rows x 3 planes =
 // The layer is paced by the latency of one tile's trip through an epilogue warp (TMEM load, activation, staging,
 // pooling, store: ~3600 clocks), not by instruction issue: FOUR accumulator stages, each drained by its own four warps.
 static constexpr int FT_ACC = 4;
+// The input patches are tiny (2.9 KB each, 30 row segments of 96 B): with the patch ring as deep as the A ring (6) an SM had
+// 17 KB in flight against a DRAM round trip of more than a microsecond -- the layer ran at 0.8 TB/s (profiles/
+// r1b_ncu_full_b1.md).  The rings are decoupled: FT_PATCH_STAGES patches in flight, FT_A_STAGES im2col tiles.
+static constexpr int FT_PATCH_STAGES = 20, FT_A_STAGES = 4;
 static constexpr int FT_THREADS = 384 + FT_ACC * 128;   // 8 gather warps, MMA / TMEM / TMA / spare, 4 epilogue warps per stage
-static constexpr int FT_SMEM = FIRST_STAGES * A_SUB_BYTES + FIRST_STAGES * FT_PATCH_PITCH + FIRST_BN * 128 + FT_ACC * 4 * 4096 +
+static constexpr int FT_SMEM = FT_A_STAGES * A_SUB_BYTES + FT_PATCH_STAGES * FT_PATCH_PITCH + FIRST_BN * 128 + FT_ACC * 4 * 4096 +
                                MAX_BIAS * 4 + 512 + 1024;
 
 __global__ void __launch_bounds__(FT_THREADS, 1)
@@ -1942,15 +1946,15 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + FIRST_STAGES * A_SUB_BYTES;
+  uint8_t* smem_b = smem + FT_A_STAGES * A_SUB_BYTES;
   uint8_t* patches = smem_b + BN * 128;
-  uint8_t* tile_buf = patches + FIRST_STAGES * FT_PATCH_PITCH;  // 16 warps x 4 KB
+  uint8_t* tile_buf = patches + FT_PATCH_STAGES * FT_PATCH_PITCH;  // 16 warps x 4 KB
   float* sbias = reinterpret_cast<float*>(tile_buf + FT_ACC * 4 * 4096);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
-  uint64_t* empty_bar = full_bar + FIRST_STAGES;
-  uint64_t* patch_full = empty_bar + FIRST_STAGES;
-  uint64_t* patch_empty = patch_full + FIRST_STAGES;
-  uint64_t* tmem_full = patch_empty + FIRST_STAGES;
+  uint64_t* empty_bar = full_bar + FT_A_STAGES;
+  uint64_t* patch_full = empty_bar + FT_A_STAGES;
+  uint64_t* patch_empty = patch_full + FT_PATCH_STAGES;
+  uint64_t* tmem_full = patch_empty + FT_PATCH_STAGES;
   uint64_t* tmem_empty = tmem_full + FT_ACC;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + FT_ACC);
 
@@ -1960,9 +1964,11 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
 
   if (warp == 8 && lane == 0) {
     ptx::tma_prefetch_desc(&tmImg);
-    for (int s = 0; s < FIRST_STAGES; ++s) {
+    for (int s = 0; s < FT_A_STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 4);
       ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < FT_PATCH_STAGES; ++s) {
       ptx::mbar_init(&patch_full[s], 1);
       ptx::mbar_init(&patch_empty[s], 4);   // the four warps of the gathering group
     }
@@ -2003,11 +2009,13 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
     const int sw = row & 7;
     int local = group;
     for (int tile = blockIdx.x + group * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, local += 2) {
-      const int stage = local % FIRST_STAGES;
-      const uint32_t phase = (uint32_t)(local / FIRST_STAGES) & 1u;
-      ptx::mbar_wait(&patch_full[stage], phase);
+      const int stage = local % FT_A_STAGES;
+      const uint32_t phase = (uint32_t)(local / FT_A_STAGES) & 1u;
+      const int pstage = local % FT_PATCH_STAGES;
+      const uint32_t pphase = (uint32_t)(local / FT_PATCH_STAGES) & 1u;
+      ptx::mbar_wait(&patch_full[pstage], pphase);
       constexpr int pw = FT_PATCH_W;
-      const float* pt = reinterpret_cast<const float*>(patches + stage * FT_PATCH_PITCH) + dy * pw + dx + (FT_PATCH_X0 - 1);
+      const float* pt = reinterpret_cast<const float*>(patches + pstage * FT_PATCH_PITCH) + dy * pw + dx + (FT_PATCH_X0 - 1);
       float v[27];
 #pragma unroll
       for (int c = 0; c < 3; ++c)
@@ -2016,7 +2024,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
 #pragma unroll
           for (int kw = 0; kw < 3; ++kw) v[c * 9 + kh * 3 + kw] = pt[(c * FT_PATCH_H + kh) * pw + kw];
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&patch_empty[stage]);
+      if (lane == 0) ptx::mbar_arrive(&patch_empty[pstage]);
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 13; ++j) o[j] = ptx::pack_op16x2(v[2 * j], v[2 * j + 1], p.f16);
@@ -2048,7 +2056,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
         ptx::mma_bf16_ss(tmem_base + acc * BN, da + 2, db + 2, idesc, 1u);
         ptx::mma_commit(&empty_bar[stage]);
         ptx::mma_commit(&tmem_full[acc]);
-        if (++stage == FIRST_STAGES) {
+        if (++stage == FT_A_STAGES) {
           stage = 0;
           phase ^= 1;
         }
@@ -2068,7 +2076,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
         ptx::mbar_wait(&patch_empty[stage], phase ^ 1);
         ptx::mbar_arrive_expect_tx(&patch_full[stage], FT_PATCH_BYTES);
         ptx::tma_load_4d(patches + stage * FT_PATCH_PITCH, &tmImg, &patch_full[stage], t.w0 - FT_PATCH_X0, t.h0 - p.padH, 0, t.n_img);
-        if (++stage == FIRST_STAGES) {
+        if (++stage == FT_PATCH_STAGES) {
           stage = 0;
           phase ^= 1;
         }

@@ -118,4 +118,46 @@ want, trials = oa.sampleNegative(img, rois, 0.3, 128, rnd)
 cpu_s = time.perf_counter() - t0
 print(json.dumps({"row": "sample_negative (128 of 8 boxes)", "trials": int(used), "call_ms": round(gpu_s * 1e3, 4),
                   "cpu_baseline": {"ms": round(cpu_s * 1e3, 1), "kind": "port", "cores": 1, "sample": "oracle restatement, same random stream"}}))
+
+# ---- nearby-aversion candidates (Anchors:findNearby per positive anchor, BatchIterator.lua:206-217)
+positive = oa.findPositive(rois, img, 0.6, 0.3, True)
+ts = []
+for it in range(23):
+    t0 = time.perf_counter()
+    got = ga.nearbyNegative(positive, 0.3)
+    if it >= 3:
+        ts.append(time.perf_counter() - t0)
+gpu_s = float(np.median(ts))
+t0 = time.perf_counter()
+want = []
+for pz in positive:
+    cx, cy = pz[0].center()
+    want += [a for a in oa.findNearby(cx, cy) if Rect.IoU(pz[0], a) < 0.3]
+cpu_s = time.perf_counter() - t0
+print(json.dumps({"row": "find_nearby_negative (%d positives)" % len(positive), "entries": len(got), "call_ms": round(gpu_s * 1e3, 4),
+                  "note": "host call incl. marshalling of the positives and building the returned anchor rects in Python",
+                  "cpu_baseline": {"ms": round(cpu_s * 1e3, 1), "kind": "port", "cores": 1, "sample": "oracle restatement of the Lua loops", "entries": len(want)}}))
+
+# ---- resize (image.scale 'bilinear', BatchIterator.lua:49-52): 1280x720 -> 800x450
+src = torch.rand(3, 720, 1280)
+sd = src.cuda()
+evs = []
+for it in range(13):
+    flush.fill_(1)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    o = m.scale_frame(sd, 800, 450)
+    b.record()
+    torch.cuda.synchronize()
+    if it >= 3:
+        evs.append(a.elapsed_time(b))
+ms = float(np.median(evs))
+t0 = time.perf_counter()
+OP.scale_image(src.numpy(), 800, 450)
+cpu_s = time.perf_counter() - t0
+ab = src.numel() * 4 + 3 * 450 * 800 * 4 + 2 * 3 * 720 * 800 * 4     # source read, result written, row-pass temporary written + read
+print(json.dumps({"row": "scale_frame (image.scale bilinear) 1280x720 -> 800x450", "ms": round(ms, 4), "launches": 2, "algorithmic_bytes": int(ab),
+                  "roofline": {"bound": "hbm", "achieved": round(ab / (ms * 1e-3) / 1e9, 1), "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                               "frac": round(ab / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], 4)},
+                  "cpu_baseline": {"ms": round(cpu_s * 1e3, 1), "kind": "port", "cores": 1, "sample": "numpy restatement of Main_scaleLinear_rowcol, same frame"}}))
 m.close()
