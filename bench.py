@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--nms-n", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=6,
+    ap.add_argument("--in-flight", type=int, default=12,
                     help="detect: frames (steps) in flight, one library context each (1 = every step synchronous)")
     ap.add_argument("--schedule", default="throughput", choices=["throughput", "latency"],
                     help="detect: launch schedule of the in-flight contexts (frcnn_set_schedule)")

@@ -1932,7 +1932,7 @@ static constexpr int FT_ACC = 4;
 // The input patches are tiny (2.9 KB each, 30 row segments of 96 B): with the patch ring as deep as the A ring (6) an SM had
 // 17 KB in flight against a DRAM round trip of more than a microsecond -- the layer ran at 0.8 TB/s (profiles/
 // r1b_ncu_full_b1.md).  The rings are decoupled: FT_PATCH_STAGES patches in flight, FT_A_STAGES im2col tiles.
-static constexpr int FT_PATCH_STAGES = 20, FT_A_STAGES = 4;
+static constexpr int FT_PATCH_STAGES = 16, FT_A_STAGES = 6;
 static constexpr int FT_THREADS = 384 + FT_ACC * 128;   // 8 gather warps, MMA / TMEM / TMA / spare, 4 epilogue warps per stage
 static constexpr int FT_SMEM = FT_A_STAGES * A_SUB_BYTES + FT_PATCH_STAGES * FT_PATCH_PITCH + FIRST_BN * 128 + FT_ACC * 4 * 4096 +
                                MAX_BIAS * 4 + 512 + 1024;
