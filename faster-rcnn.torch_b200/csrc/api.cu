@@ -2916,7 +2916,7 @@ int frcnn_conv_bf16(frcnn_ctx* c, const uint16_t* x_dev, const float* w_dev, con
   REQUIRE_DEVICE(c);
   FRCNN_REQUIRE(x_dev && w_dev && out_dev, FRCNN_E_INVALID, "null argument");
   FRCNN_REQUIRE(bn == 0 || bn == 64 || bn == 128 || bn == 192 || bn == 256, FRCNN_E_INVALID, "bn must be 0, 64, 128, 192 or 256");
-  FRCNN_REQUIRE(((mt >= 0 && mt <= 2) || (mt > 10 && mt < 50 && (mt % 10 == 1 || mt % 10 == 2))) && !(pool && splits > 1), FRCNN_E_INVALID,
+  FRCNN_REQUIRE(((mt >= 0 && mt <= 2) || (mt > 10 && mt < 50 && (mt % 10 == 1 || mt % 10 == 2)) || mt == 51 || mt == 61) && !(pool && splits > 1), FRCNN_E_INVALID,
                 "bad mt / pool");
   const int ho = h + 2 * pad - k + 1, wo = w + 2 * pad - k + 1;
   FRCNN_REQUIRE(ho > 0 && wo > 0, FRCNN_E_INVALID, "input smaller than the kernel");
@@ -2960,6 +2960,24 @@ int frcnn_conv_bf16(frcnn_ctx* c, const uint16_t* x_dev, const float* w_dev, con
   if (elapsed_ms) FRCNN_CUDA_TRY(cudaEventElapsedTime(elapsed_ms, e0, e1));
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  if (const char* path = getenv("FRCNN_CONV_TRACE")) {
+    // measurement only: one more launch with per-CTA / per-unit globaltimer stamps (conv_halo_kernel), dumped to `path`
+    const size_t words = (size_t)L.grid * 64;
+    unsigned long long* d_trace = nullptr;
+    FRCNN_CUDA_TRY(cudaMalloc(&d_trace, words * 8));
+    FRCNN_CUDA_TRY(cudaMemset(d_trace, 0, words * 8));
+    L.p.trace = d_trace;
+    frcnn::conv_launch(L, c->stream);
+    FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<unsigned long long> t(words);
+    FRCNN_CUDA_TRY(cudaMemcpy(t.data(), d_trace, words * 8, cudaMemcpyDeviceToHost));
+    cudaFree(d_trace);
+    L.p.trace = nullptr;
+    if (FILE* f = fopen(path, "wb")) {
+      fwrite(t.data(), 8, t.size(), f);
+      fclose(f);
+    }
+  }
   API_END(c)
 }
 

@@ -98,9 +98,12 @@ struct ConvParams {
   // {64 ch, BW + KW - 1, BH * MT + KH - 1} = the CTA tile plus its halo; tap (kh, kw) is a row offset of the UMMA
   // descriptor into that box.  BW = 8 (one 8-row descriptor group per tile row), BH = 16.
   int halo;                 // 1: launched with conv_halo_kernel (with wgrad: conv_wgrad_halo_kernel, MT = taps per unit)
+  int swap;                 // 1: conv_halo_kernel<128, 2, 3, 1, SWAP>: filters on the M side, 256 pixels on the N side (epilogue_swap)
   int pair;                 // 1: launched with conv_pair_kernel on CTA pairs (cta_group::2): a unit covers TWO CTA tiles stacked
                             // along H (cluster rank r computes rows [r, r + 1) * BH * MT of it); tiles_h counts pair tiles
-  int occ;                  // CTAs resident per SM the launch is sized for (1, or 2: halved shared memory / TMEM per CTA)
+  int occ;                  // CTAs resident per SM the launch is sized for (1, or 2: halved shared memory / TMEM per CTA; 3: conv_pair_bres_kernel)
+  unsigned long long* trace; // measurement only (FRCNN_CONV_TRACE): per-CTA / per-unit globaltimer stamps of conv_halo_kernel; nullptr = off
+  int a_slots;              // conv_pair_bres_kernel: depth of the activation ring (what the resident weights leave room for)
   int first_tma;            // first-layer kernel: eligible for conv_first_tma_kernel (16 x 8 tiles, Win % 4 == 0)
   int halo_desc;            // descriptor base-offset mode for the row-shifted start address (0: field left 0)
   const float* w2;          // EPI_HEAD: [18][256] weights of the 1x1 convolution (Torch layout)

@@ -143,6 +143,15 @@ __device__ __forceinline__ bool next_unit(const ConvGroup& grp, const GroupSched
 // pixel) and the chunk-wise reads (8 lanes = one 128-byte pixel segment) are bank-conflict free.  Output leaves
 // the SM as fully coalesced 128-byte segments written with plain 16-byte st.global by all 256 threads.
 static constexpr int EPI_THREADS = 256;
+__device__ __forceinline__ unsigned long long conv_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// trace layout: [cta][8 units][8 stamps]; unit slot 7 stamp 7 = CTA start, stamp 6 = CTA end
+#define CONV_TRACE(P, local, k) \
+  do { if ((P).trace && (local) < 7) (P).trace[((size_t)blockIdx.x * 8 + (local)) * 8 + (k)] = conv_now(); } while (0)
+
 template <int BN, int MT, int ACC = 2>
 __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtensorMap* tmOuts, uint8_t* tile_buf,
                                               const float* sbias, uint32_t tmem_base, uint64_t* tmem_full,
@@ -178,6 +187,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
     const float k_pos = p.scale;
     ptx::mbar_wait(&tmem_full[acc], acc_phase);
     ptx::tc_fence_after();
+    if (tid == 0) CONV_TRACE(p, seq - 1, 3);
     // weight-gradient tap groups (conv_wgrad_halo_kernel): sub-tile mt is filter tap t.w0 + mt of the same Cout rows
     const int mt_count = (p.wgrad && p.halo) ? min(MT, p.KH * p.KW - t.w0) : MT;
 #pragma unroll 1
@@ -333,6 +343,7 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
       if (empty_leader_addr) ptx::mbar_arrive_cluster(empty_leader_addr + (uint32_t)acc * 8u);
       else ptx::mbar_arrive(&tmem_empty[acc]);
     }
+    if (tid == 0) CONV_TRACE(p, seq - 1, 4);
   }
   if (store_thread) ptx::tma_store_wait_all();
 }
@@ -663,7 +674,141 @@ __device__ __forceinline__ void epilogue_head(const ConvGroup& grp, float* w2s, 
   }
 }
 
-template <int BN, int MT, int KMAX, int OCC = 1>
+// ------------------------------------------------------------------------------------------------- swapped operands
+// Epilogue of conv_halo_kernel<128, 2, 3, 1, SWAP = true>.  Measured on B200 (tools/micro/mma_issue_bench.cu): one
+// tcgen05.mma with M = 128 and shared-memory operands takes ~130 clocks per K16 step WHATEVER N is (64, 128 or 256) -- the
+// 4 KB A tile is read at 32 B/clk -- so an N = 128 tile (Cout = 128: conv2_x; 3 x 128 = 384: conv4_x) runs the tensor
+// pipe at half rate.  With the operands swapped the 128 filters are the M side (A = the weight box) and 256 pixels (an
+// 8 x 32 halo tile, tap = descriptor offset exactly as before) the N side: the same instruction does twice the work.
+// The accumulator then holds D[filter][pixel]: TMEM lane = output channel, column = pixel y * 8 + x of the tile.
+//   thread <-> channel: bias / PReLU slope / dropout mask are per-thread scalars; the 2 x 2 max-pool windows (columns
+//   j, j + 1, j + 8, j + 9) lie in the thread's own registers; values go through the 16 KB staging tile transposed
+//   ([pixel][128 channels], 2-byte stores: a warp writes 64 contiguous bytes) and leave as 16-byte coalesced stores.
+// Warp e covers lane quarter (e & 3) = channels, column half (e >> 2) = tile rows [16 half, 16 half + 16).
+__device__ __forceinline__ void epilogue_swap(const ConvGroup& grp, uint8_t* tile_buf, const float* sbias, uint32_t tmem_base,
+                                              uint64_t* tmem_full, uint64_t* tmem_empty, const GroupSched& sc, int ewarp, int lane) {
+  constexpr int BN = 128;                 // filters per unit (the M side)
+  const int q = ewarp & 3, half = ewarp >> 2;
+  const int ch = q * 32 + lane;           // TMEM lane == output channel within the unit's filter tile
+  const int tid = ewarp * 32 + lane;
+  const uint32_t tile_addr = ptx::smem_u32(tile_buf);
+  const int total_units = grp.unit_end[grp.n - 1];
+  const ConvParams& p = grp.p[0];
+  const float slope = p.prelu ? __ldg(p.prelu) : 1.0f;
+  const float k_neg = (slope - 1.0f) * p.scale, k_pos = p.scale;
+  const int Hp = (p.Hout + 1) >> 1, Wp = (p.Wout + 1) >> 1;
+  int seq = 0;
+  for (int unit = blockIdx.x; unit < total_units; unit += gridDim.x) {
+    int gi;
+    TileCoord t;
+    if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+    const int acc = seq & 1;
+    const uint32_t acc_phase = (uint32_t)(seq >> 1) & 1u;
+    ++seq;
+    const int cg = t.n0 + ch;             // global output channel
+    const float bias = sbias[cg];
+    const float mask = p.chan_scale ? __ldg(p.chan_scale + (size_t)t.n_img * p.Cout + cg) : 1.0f;
+    ptx::mbar_wait(&tmem_full[acc], acc_phase);
+    ptx::tc_fence_after();
+    if (tid == 0) CONV_TRACE(p, seq - 1, 3);
+    const uint32_t taddr = tmem_base + (uint32_t)(acc * 256 + half * 128) + ((uint32_t)(q * 32) << 16);
+    if (p.mode == EPI_POOL) {
+      // ---- 2 x 2 ceil-mode max pool in registers: chunk k = tile rows 4k .. 4k + 3 of this half -> 2 x 4 pooled pixels
+      bf16* out_img = reinterpret_cast<bf16*>(p.out) + (size_t)t.n_img * Hp * Wp * p.Cout;
+      const uint16_t ninf = p.f16 ? (uint16_t)0xFC00u : (uint16_t)0xFF80u;
+      ptx::named_bar_sync(1, EPI_THREADS);   // the previous unit's staging reads are done
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(taddr + k * 32, v);
+        ptx::tmem_ld_wait();
+        uint16_t r[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int y = half * 16 + k * 4 + (i >> 3), x = i & 7;
+          const float a = __uint_as_float(v[i]) + bias;
+          const float o = fmaf(fminf(a, 0.f), k_neg, a * k_pos) * mask;
+          const bool valid = (t.h0 + y < p.Hout) && (t.w0 + x < p.Wout);
+          r[i] = valid ? ptx::float_to_op16(o, p.f16) : ninf;   // outside the map: never wins a window
+        }
+#pragma unroll
+        for (int py = 0; py < 2; ++py) {
+#pragma unroll
+          for (int px = 0; px < 4; ++px) {
+            const int i00 = (2 * py) * 8 + 2 * px;
+            // winner = first maximum in window scan order, decided on the rounded values (as nn.SpatialMaxPooling would
+            // on the stored activations)
+            float best = ptx::op16_to_float(r[i00], p.f16);
+            uint16_t bv = r[i00];
+            uint32_t arg = 0;
+            const float fb = ptx::op16_to_float(r[i00 + 1], p.f16), fc = ptx::op16_to_float(r[i00 + 8], p.f16), fd = ptx::op16_to_float(r[i00 + 9], p.f16);
+            if (fb > best) { best = fb; bv = r[i00 + 1]; arg = 1; }
+            if (fc > best) { best = fc; bv = r[i00 + 8]; arg = 2; }
+            if (fd > best) { best = fd; bv = r[i00 + 9]; arg = 3; }
+            const int ppy = half * 8 + k * 2 + py;                  // pooled row / column inside the tile (16 x 4)
+            const int prow = ppy * 4 + px;                          // staging row
+            *reinterpret_cast<uint16_t*>(tile_buf + prow * 256 + ch * 2) = bv;
+            if (p.pool_arg) {
+              const int ph = (t.h0 >> 1) + ppy, pw = (t.w0 >> 1) + px;
+              if (ph < Hp && pw < Wp) p.pool_arg[(((size_t)t.n_img * Hp + ph) * Wp + pw) * p.Cout + cg] = (uint8_t)arg;
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);   // all TMEM reads done: the stage goes back before the stores
+      ptx::named_bar_sync(1, EPI_THREADS);
+      // 64 pooled pixels x 256 bytes: 16-byte coalesced stores
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int idx = it * EPI_THREADS + tid;
+        const int prow = idx >> 4, c16 = idx & 15;
+        const int ph = (t.h0 >> 1) + (prow >> 2), pw = (t.w0 >> 1) + (prow & 3);
+        if (ph < Hp && pw < Wp && !(p.dbg & 1)) {
+          const uint4 val = ptx::ld_shared_v4(tile_addr + prow * 256 + c16 * 16);
+          *reinterpret_cast<uint4*>(out_img + ((size_t)ph * Wp + pw) * p.Cout + t.n0 + c16 * 8) = val;
+        }
+      }
+    } else {
+      // ---- EPI_STORE: four staging passes of 64 pixels (chunk k of both column halves)
+      bf16* out_img = reinterpret_cast<bf16*>(p.out) + (size_t)t.n_img * p.Hout * p.Wout * p.Cout;
+#pragma unroll 1
+      for (int k = 0; k < 4; ++k) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(taddr + k * 32, v);
+        ptx::tmem_ld_wait();
+        if (k == 3) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+        }
+        ptx::named_bar_sync(1, EPI_THREADS);   // the previous pass's staging reads are done
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float a = __uint_as_float(v[i]) + bias;
+          const float o = fmaf(fminf(a, 0.f), k_neg, a * k_pos) * mask;
+          *reinterpret_cast<uint16_t*>(tile_buf + (half * 32 + i) * 256 + ch * 2) = ptx::float_to_op16(o, p.f16);
+        }
+        ptx::named_bar_sync(1, EPI_THREADS);
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int idx = it * EPI_THREADS + tid;
+          const int srow = idx >> 4, c16 = idx & 15;
+          const int hf = srow >> 5, i = srow & 31;
+          const int hh = t.h0 + hf * 16 + k * 4 + (i >> 3), ww = t.w0 + (i & 7);
+          if (hh < p.Hout && ww < p.Wout && !(p.dbg & 1)) {
+            const uint4 val = ptx::ld_shared_v4(tile_addr + srow * 256 + c16 * 16);
+            *reinterpret_cast<uint4*>(out_img + ((size_t)hh * p.Wout + ww) * p.Cout + t.n0 + c16 * 8) = val;
+          }
+        }
+      }
+    }
+    if (tid == 0) CONV_TRACE(p, seq - 1, 4);
+  }
+}
+
+template <int BN, int MT, int KMAX, int OCC = 1, bool SWAP = false>
 __global__ void __launch_bounds__(CONV_THREADS, OCC)
     conv_halo_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGroup grp) {
   constexpr int A_SLOT = halo_a_slot(MT, KMAX), A_SLOTS = occ_a_slots(MT, KMAX, OCC);
@@ -671,7 +816,9 @@ __global__ void __launch_bounds__(CONV_THREADS, OCC)
   constexpr int ACC = occ_acc_stages(BN, MT, OCC);
   constexpr int TMEM_COLS = occ_tmem_cols(BN, MT, OCC);
   static_assert(TMEM_COLS <= 512 / OCC, "accumulators of all resident CTAs must fit the 512 TMEM columns");
-  constexpr uint32_t IDESC = ptx::make_idesc_bf16(BLOCK_M, BN);
+  // SWAP: the weight box is the A operand (M = BN = 128 filters), the 8 x 32-pixel halo tile the B operand (N = 256)
+  static_assert(!SWAP || (BN == 128 && MT == 2 && OCC == 1 && KMAX == HALO_MAXK), "swapped operands: 128 filters x 256 pixels");
+  constexpr uint32_t IDESC = SWAP ? ptx::make_idesc_bf16(BLOCK_M, 256) : ptx::make_idesc_bf16(BLOCK_M, BN);
   constexpr bool HEAD = KMAX > HALO_MAXK;  // the fused anchor-head configuration: EPI_HEAD units of up to 4 convs
   static_assert(B_SLOTS >= 2, "weight ring too small");
   static_assert(!HEAD || (BN == HEAD_CM && MT == 1), "anchor heads: 256 hidden channels, one sub-tile");
@@ -691,6 +838,7 @@ __global__ void __launch_bounds__(CONV_THREADS, OCC)
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
+  if (threadIdx.x == 0 && grp.p[0].trace) grp.p[0].trace[((size_t)blockIdx.x * 8 + 7) * 8 + 7] = conv_now();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_units = grp.unit_end[grp.n - 1];
@@ -784,7 +932,7 @@ __global__ void __launch_bounds__(CONV_THREADS, OCC)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (true) {   // the WHOLE warp, converged: one elected lane issues (ptx::mma_bf16_ss_w)
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int seq = 0;
@@ -801,6 +949,7 @@ __global__ void __launch_bounds__(CONV_THREADS, OCC)
         ++seq;
         ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
+        if (lane == 0) CONV_TRACE(p, seq - 1, 0);
         const uint32_t d_tmem = tmem_base + acc * BN * MT;
         for (int c = 0; c < p.cchunks; ++c) {
           ptx::mbar_wait(&full_a[as], aph);
@@ -809,30 +958,48 @@ __global__ void __launch_bounds__(CONV_THREADS, OCC)
             for (int kw = 0; kw < p.KW; ++kw) {
               ptx::mbar_wait(&full_b[bs], bph);
               ptx::tc_fence_after();
+              if (c == 0 && kh == 0 && kw == 0) CONV_TRACE(p, seq - 1, 1);
               const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + bs * B_SLOT));
               const uint32_t first = (c == 0 && kh == 0 && kw == 0) ? 0u : 1u;
+              // consecutive tcgen05.mma into the SAME accumulator serialise on its read-modify-write (measured: ~190 clocks
+              // per dependent K16 step whatever N is): the sub-tiles' accumulators alternate instruction by instruction
+              if constexpr (SWAP) {
+                // A = the weight box (canonical K-major tile), B = the pixel tile read from the halo box at the tap's row
+                // offset: 32 groups of 8 rows (one tile row each), SBO = halo pitch
+                const int row0 = kh * PW + kw;
+                const uint64_t dpx = ptx::make_desc_k_sw128_sbo(a_addr + row0 * 128, sbo, p.halo_desc ? (uint32_t)row0 : 0u);
+#pragma unroll
+                for (int j = 0; j < BLOCK_K / 16; ++j)
+                  if (!(p.dbg & 4)) ptx::mma_bf16_ss_w(d_tmem, db + 2 * j, dpx + 2 * j, idesc, j > 0 ? 1u : first);
+              } else {
+              uint64_t da[MT];
 #pragma unroll
               for (int mt = 0; mt < MT; ++mt) {
                 const int row0 = (mt * HALO_BH + kh) * PW + kw;  // first 128-byte row of this tap's operand
-                const uint64_t da = ptx::make_desc_k_sw128_sbo(a_addr + row0 * 128, sbo, p.halo_desc ? (uint32_t)row0 : 0u);
-#pragma unroll
-                for (int j = 0; j < BLOCK_K / 16; ++j)
-                  if (!(p.dbg & 4)) ptx::mma_bf16_ss(d_tmem + mt * BN, da + 2 * j, db + 2 * j, idesc, j > 0 ? 1u : first);
+                da[mt] = ptx::make_desc_k_sw128_sbo(a_addr + row0 * 128, sbo, p.halo_desc ? (uint32_t)row0 : 0u);
               }
-              ptx::mma_commit(&empty_b[bs]);
+#pragma unroll
+              for (int j = 0; j < BLOCK_K / 16; ++j) {
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+                  if (!(p.dbg & 4)) ptx::mma_bf16_ss_w(d_tmem + mt * BN, da[mt] + 2 * j, db + 2 * j, idesc, j > 0 ? 1u : first);
+              }
+              }
+              ptx::mma_commit_w(&empty_b[bs]);
               if (++bs == B_SLOTS) {
                 bs = 0;
                 bph ^= 1;
               }
             }
           }
-          ptx::mma_commit(&empty_a[as]);
+          ptx::mma_commit_w(&empty_a[as]);
           if (++as == A_SLOTS) {
             as = 0;
             aph ^= 1;
           }
         }
-        ptx::mma_commit(&tmem_full[acc]);
+        ptx::mma_commit_w(&tmem_full[acc]);
+        if (lane == 0) CONV_TRACE(p, seq - 1, 2);
       }
     }
   } else if (warp >= 4) {
@@ -840,6 +1007,8 @@ __global__ void __launch_bounds__(CONV_THREADS, OCC)
       float* w2s = reinterpret_cast<float*>(tile_buf);
       float* parts = w2s + HEAD_CM * HEAD_W2_PITCH;
       epilogue_head<ACC>(grp, w2s, parts, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 4, lane);
+    } else if constexpr (SWAP) {
+      epilogue_swap(grp, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 4, lane);
     } else {
       epilogue_loop<BN, MT, ACC>(grp, maps.o, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 4, lane);
     }
@@ -851,6 +1020,7 @@ __global__ void __launch_bounds__(CONV_THREADS, OCC)
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 0 && grp.p[0].trace) grp.p[0].trace[((size_t)blockIdx.x * 8 + 7) * 8 + 6] = conv_now();
 }
 
 // ------------------------------------------------------------------------------------------------- halo kernel on CTA pairs
@@ -989,7 +1159,7 @@ __global__ void __launch_bounds__(CONV_THREADS, OCC)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    if (leader) {   // the WHOLE warp, converged: one elected lane issues
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int seq = 0;
@@ -1022,22 +1192,22 @@ __global__ void __launch_bounds__(CONV_THREADS, OCC)
                 const uint64_t da = ptx::make_desc_k_sw128_sbo(a_addr + row0 * 128, sbo, 0u);
 #pragma unroll
                 for (int j = 0; j < BLOCK_K / 16; ++j)
-                  if (!(p.dbg & 4)) ptx::mma_bf16_ss_2cta(d_tmem + mt * BN, da + 2 * j, db + 2 * j, idesc, j > 0 ? 1u : first);
+                  if (!(p.dbg & 4)) ptx::mma_bf16_ss_2cta_w(d_tmem + mt * BN, da + 2 * j, db + 2 * j, idesc, j > 0 ? 1u : first);
               }
-              ptx::mma_commit_2cta(&empty_b[bs], 3);
+              ptx::mma_commit_2cta_w(&empty_b[bs], 3);
               if (++bs == B_SLOTS) {
                 bs = 0;
                 bph ^= 1;
               }
             }
           }
-          ptx::mma_commit_2cta(&empty_a[as], 3);
+          ptx::mma_commit_2cta_w(&empty_a[as], 3);
           if (++as == A_SLOTS) {
             as = 0;
             aph ^= 1;
           }
         }
-        ptx::mma_commit_2cta(&tmem_full[acc], 3);
+        ptx::mma_commit_2cta_w(&tmem_full[acc], 3);
       }
     }
   } else if (warp >= 4) {
@@ -1052,6 +1222,221 @@ __global__ void __launch_bounds__(CONV_THREADS, OCC)
     ptx::tc_fence_after();
     ptx::tmem_dealloc_2cta(tmem_base, TMEM_COLS);
   }
+}
+
+// ------------------------------------------------------------------------------------------------- CTA pairs, weights resident
+// conv_pair_kernel for the narrow layers (Cout = 128: conv2_x) with the WHOLE weight tensor of the layer resident in the
+// pair's shared memory.  What bounds those layers (profiles/r2_ncu_full_b1.md: tensor pipe active 30-43 % of a CTA's cycles):
+// one M128 x N128 x K16 MMA reads 8 KB of operands in 64 clocks = the entire 128 B/clk shared-memory bandwidth, while the
+// weight boxes streaming through the ring (16 KB per 256 MMA clocks) and the A boxes write into the same memory.  Here
+//   * each CTA of a pair keeps its 64-filter half of ALL taps x channel chunks (9 x Cin / 64 boxes of 8 KB: 72 KB for
+//     conv2_1, 144 KB for conv2_2), loaded once while the first unit runs -- no weight traffic afterwards;
+//   * the M = 256 pair MMA reads 4 KB (A) + 2 KB (B half) per SM and K16 step: 96 B/clk;
+//   * only the pixel halo boxes (23 KB per 64-channel chunk and 36 MMAs) keep arriving.
+// One CTA per SM (214 KB), persistent over ~10 units, two accumulator stages.  Requires 9 * Cin / 64 <= 18 boxes.
+static constexpr int BRES_MAX_BOXES = 18, BRES_MAX_A_SLOTS = 6;
+static int bres_a_slots(int BN, int boxes) {
+  const int n = (SMEM_LIMIT - SMEM_FIXED - boxes * BN * 64) / halo_a_slot(1, HALO_MAXK);
+  return n > BRES_MAX_A_SLOTS ? BRES_MAX_A_SLOTS : n;
+}
+static int bres_smem_bytes(int BN, int boxes) { return bres_a_slots(BN, boxes) * halo_a_slot(1, HALO_MAXK) + boxes * BN * 64 + SMEM_FIXED; }
+template <int BN>
+__global__ void __launch_bounds__(CONV_THREADS, 1)
+    conv_pair_bres_kernel(const __grid_constant__ ConvMaps maps, const __grid_constant__ ConvGroup grp) {
+  constexpr int MT = 1, KMAX = HALO_MAXK, OCC = 1;
+  constexpr int A_SLOT = halo_a_slot(MT, KMAX), A_SLOTS_MAX = BRES_MAX_A_SLOTS;
+  const int A_SLOTS = grp.p[0].a_slots;   // what the resident weights leave room for (2 .. BRES_MAX_A_SLOTS)
+  constexpr int B_SLOT = BN * 64, B_SLOTS = BRES_MAX_BOXES;   // half a weight box: BN / 2 rows of 128 bytes; ALL boxes resident
+  constexpr int ACC = occ_acc_stages(BN, MT, OCC);
+  constexpr int TMEM_COLS = occ_tmem_cols(BN, MT, OCC);
+  constexpr uint32_t IDESC = ptx::make_idesc_bf16(2 * BLOCK_M, BN);       // M = 256 over the pair
+  static_assert(B_SLOTS >= 2 && BN % 16 == 0, "weight ring too small / N must be a multiple of 16 for cta_group::2");
+  static_assert((2 * A_SLOTS_MAX + 2 * B_SLOTS + 4) * 8 + 4 <= 512, "mbarrier area of SMEM_FIXED");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = occ_smem_base(smem_raw, OCC);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + A_SLOTS * A_SLOT;
+  uint8_t* tile_buf = smem_b + grp.p[0].KH * grp.p[0].KW * grp.p[0].cchunks * B_SLOT;   // only the boxes the layer has
+  float* sbias = reinterpret_cast<float*>(tile_buf + STAGE_TILE_BYTES);
+  uint64_t* full_a = reinterpret_cast<uint64_t*>(sbias + MAX_BIAS);
+  uint64_t* empty_a = full_a + A_SLOTS_MAX;
+  uint64_t* full_b = empty_a + A_SLOTS_MAX;
+  uint64_t* empty_b = full_b + B_SLOTS;
+  uint64_t* tmem_full = empty_b + B_SLOTS;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  if (threadIdx.x == 0 && grp.p[0].trace) grp.p[0].trace[((size_t)blockIdx.x * 8 + 7) * 8 + 7] = conv_now();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_units = grp.unit_end[grp.n - 1];
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  GroupSched sc;
+  make_sched(grp, BN, sc);
+
+  if (warp == 0 && lane == 0) {
+    for (int g = 0; g < grp.n; ++g) {
+      ptx::tma_prefetch_desc(&maps.a[g]);
+      ptx::tma_prefetch_desc(&maps.b[g]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < A_SLOTS; ++s) {
+      ptx::mbar_init(&full_a[s], 1);
+      ptx::mbar_init(&empty_a[s], 1);
+    }
+    for (int s = 0; s < B_SLOTS; ++s) {
+      ptx::mbar_init(&full_b[s], 1);
+      ptx::mbar_init(&empty_b[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full[a], 1);
+      ptx::mbar_init(&tmem_empty[a], 2 * (EPI_THREADS / 32));   // the epilogue warps of BOTH CTAs (used in the leader only)
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc_2cta(tmem_base_slot, TMEM_COLS);
+    ptx::tmem_relinquish_2cta();
+  }
+  {
+    const ConvParams& p0 = grp.p[0];
+    for (int i = threadIdx.x; i < MAX_BIAS; i += blockDim.x) sbias[i] = (p0.bias && i < p0.Cout) ? p0.bias[i] : 0.f;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them remotely
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+  const int u0 = unit_first(grp), ustride = unit_stride(grp);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs): own A box, half of every B box
+    if (lane == 0) {
+      const uint32_t full_a_leader = ptx::mapa_shared(ptx::smem_u32(full_a), 0);
+      const uint32_t full_b_leader = ptx::mapa_shared(ptx::smem_u32(full_b), 0);
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int ua = u0, ca = 0;  // cursor of the A ring: one chunk ahead of the weight ring
+      auto issue_a = [&]() {
+        int ga;
+        TileCoord ta;
+        while (ua < total_units && !next_unit(grp, sc, ua, BN, ga, ta)) ua += ustride;
+        if (ua >= total_units) return;
+        const ConvParams& pa = grp.p[ga];
+        const uint32_t a_tx = (uint32_t)((HALO_BW + pa.KW - 1) * (HALO_BH * MT + pa.KH - 1)) * 128u;
+        if (pa.dbg & 8) { if (++ca == pa.cchunks) { ca = 0; ua += ustride; } return; }   // measurement: no pixel loads at all
+        ptx::mbar_wait(&empty_a[as], aph ^ 1);
+        if (leader) ptx::mbar_arrive_expect_tx(&full_a[as], 2 * a_tx);
+        ptx::tma_load_4d_2sm(smem_a + as * A_SLOT, &maps.a[ga], full_a_leader + (uint32_t)as * 8u, ca * BLOCK_K, ta.w0 - pa.padW,
+                             ta.h0 - pa.padH, ta.n_img);
+        if (++as == A_SLOTS) {
+          as = 0;
+          aph ^= 1;
+        }
+        if (++ca == pa.cchunks) {
+          ca = 0;
+          ua += ustride;
+        }
+      };
+      issue_a();
+      bool weights_loaded = false;
+      for (int unit = u0; unit < total_units; unit += ustride) {
+        int gi;
+        TileCoord t;
+        if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+        const ConvParams& p = grp.p[gi];
+        const int taps = p.KH * p.KW;
+        for (int c = 0; c < p.cchunks; ++c) {
+          if (!weights_loaded) {
+            // the CTA's first unit: every weight box of its filter half goes into its own slot, in consumption order,
+            // and STAYS there (one N tile: the boxes are the same for every later unit)
+            for (int tap = 0; tap < taps; ++tap) {
+              const int slot = c * taps + tap;
+              if (leader) ptx::mbar_arrive_expect_tx(&full_b[slot], 2 * B_SLOT);
+              ptx::tma_load_3d_2sm(smem_b + slot * B_SLOT, &maps.b[gi], full_b_leader + (uint32_t)slot * 8u, (tap * p.cchunks + c) * BLOCK_K,
+                                   t.n0 + (int)rank * (BN / 2), p.f16);
+              if (tap == 0) issue_a();
+            }
+          } else {
+            issue_a();
+          }
+        }
+        weights_loaded = true;
+      }
+      (void)bs; (void)bph;
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader) {   // the WHOLE warp, converged: one elected lane issues
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int seq = 0;
+      bool weights_ready = false;
+      for (int unit = u0; unit < total_units; unit += ustride) {
+        int gi;
+        TileCoord t;
+        if (!next_unit(grp, sc, unit, BN, gi, t)) continue;
+        const ConvParams& p = grp.p[gi];
+        const int taps = p.KH * p.KW;
+        const int PW = HALO_BW + p.KW - 1;  // halo pitch, pixels
+        const uint32_t sbo = (uint32_t)PW * 128u;
+        const uint32_t idesc = p.f16 ? ptx::idesc_to_f16(IDESC) : IDESC;
+        const int acc = ACC == 2 ? (seq & 1) : 0;
+        const uint32_t acc_phase = (uint32_t)(ACC == 2 ? (seq >> 1) : seq) & 1u;
+        ++seq;
+        ptx::mbar_wait_cluster(&tmem_empty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        if (lane == 0) CONV_TRACE(p, seq - 1, 0);
+        const uint32_t d_tmem = tmem_base + acc * BN * MT;
+        for (int c = 0; c < p.cchunks; ++c) {
+          if (!(p.dbg & 8)) ptx::mbar_wait(&full_a[as], aph);
+          const uint32_t a_addr = ptx::smem_u32(smem_a + as * A_SLOT);
+          for (int kh = 0; kh < p.KH; ++kh) {
+            for (int kw = 0; kw < p.KW; ++kw) {
+              const int slot = c * taps + kh * p.KW + kw;
+              if (!weights_ready) ptx::mbar_wait(&full_b[slot], 0u);
+              ptx::tc_fence_after();
+              if (slot == 0) CONV_TRACE(p, seq - 1, 1);
+              const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + ((p.dbg & 16) ? 0 : slot) * B_SLOT));
+              const uint32_t first = (c == 0 && kh == 0 && kw == 0) ? 0u : 1u;
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const int row0 = (mt * HALO_BH + kh) * PW + kw;  // first 128-byte row of this tap's operand
+                const uint64_t da = (p.dbg & 32) ? ptx::make_desc_k_sw128(a_addr) : ptx::make_desc_k_sw128_sbo(a_addr + row0 * 128, sbo, 0u);
+#pragma unroll
+                for (int j = 0; j < BLOCK_K / 16; ++j)
+                  if (!(p.dbg & 4)) ptx::mma_bf16_ss_2cta_w(d_tmem + mt * BN, da + 2 * j, db + 2 * j, idesc, j > 0 ? 1u : first);
+              }
+            }
+          }
+          if (!(p.dbg & 8)) ptx::mma_commit_2cta_w(&empty_a[as], 3);
+          if (++as == A_SLOTS) {
+            as = 0;
+            aph ^= 1;
+          }
+        }
+        ptx::mma_commit_2cta_w(&tmem_full[acc], 3);
+        if (lane == 0) CONV_TRACE(p, seq - 1, 2);
+        weights_ready = true;
+      }
+      (void)bs; (void)bph;
+    }
+  } else if (warp >= 4) {
+    const uint32_t empty_leader = ptx::mapa_shared(ptx::smem_u32(tmem_empty), 0);
+    epilogue_loop<BN, MT, ACC>(grp, maps.o, tile_buf, sbias, tmem_base, tmem_full, tmem_empty, sc, warp - 4, lane, empty_leader);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the peer may still read its shared memory / barriers
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2cta(tmem_base, TMEM_COLS);
+  }
+  if (threadIdx.x == 0 && grp.p[0].trace) grp.p[0].trace[((size_t)blockIdx.x * 8 + 7) * 8 + 6] = conv_now();
 }
 
 // ------------------------------------------------------------------------------------------------- anchor networks
@@ -1212,7 +1597,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    if (leader) {   // the WHOLE warp, converged: one elected lane issues
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       int seq = 0;
@@ -1224,8 +1609,8 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
         const int acc = seq & 1;
         ptx::mbar_wait_cluster(&tmem_empty[acc], ((uint32_t)(seq >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
-        HEADK_TRACE(ui, 0, headk_now());
-        HEADK_TRACE(ui, 5, (unsigned long long)(g | (s << 8) | (nsl << 16) | (tile << 24)));
+        if (lane == 0) HEADK_TRACE(ui, 0, headk_now());
+        if (lane == 0) HEADK_TRACE(ui, 5, (unsigned long long)(g | (s << 8) | (nsl << 16) | (tile << 24)));
         const uint32_t d_tmem = tmem_base + acc * BN;
         uint32_t first = 0u;
         for (int kh = kh0; kh < kh1; ++kh) {
@@ -1238,25 +1623,25 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
               // tap kw = the slab read from row kw on: start address + kw * 128 B, canonical 8-row groups (SBO 1024)
               const uint64_t da = ptx::make_desc_k_sw128(a_addr + kw * 128);
               const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + bs * HEADK_B_SLOT));
-              if (hs.trace && ui == u_begin && first == 0u) hs.trace[((size_t)blockIdx.x * 8 + 7) * 8 + 6] = headk_now();   // first operands landed
+              if (lane == 0 && hs.trace && ui == u_begin && first == 0u) hs.trace[((size_t)blockIdx.x * 8 + 7) * 8 + 6] = headk_now();   // first operands landed
 #pragma unroll
-              for (int j = 0; j < BLOCK_K / 16; ++j) ptx::mma_bf16_ss_2cta(d_tmem, da + 2 * j, db + 2 * j, idesc, j > 0 ? 1u : first);
+              for (int j = 0; j < BLOCK_K / 16; ++j) ptx::mma_bf16_ss_2cta_w(d_tmem, da + 2 * j, db + 2 * j, idesc, j > 0 ? 1u : first);
               first = 1u;
-              ptx::mma_commit_2cta(&empty_b[bs], 3);
+              ptx::mma_commit_2cta_w(&empty_b[bs], 3);
               if (++bs == HEADK_B_SLOTS) {
                 bs = 0;
                 bph ^= 1;
               }
             }
-            ptx::mma_commit_2cta(&empty_a[as], 3);
+            ptx::mma_commit_2cta_w(&empty_a[as], 3);
             if (++as == HEADK_A_SLOTS) {
               as = 0;
               aph ^= 1;
             }
           }
         }
-        ptx::mma_commit_2cta(&tmem_full[acc], 3);
-        HEADK_TRACE(ui, 1, headk_now());
+        ptx::mma_commit_2cta_w(&tmem_full[acc], 3);
+        if (lane == 0) HEADK_TRACE(ui, 1, headk_now());
       }
     }
   } else if (warp >= 4) {
@@ -2273,6 +2658,26 @@ static void conv_prepare_pair(ConvLaunch* L, const bf16* in, const bf16* w_packe
   L->grid = 2 * (total < pairs ? total : pairs);
 }
 
+// conv_pair_bres_kernel: one N tile (BN == Cout), all 9 * Cin / 64 half boxes resident
+static bool bres_ok(int Cin, int Cout, int BN, int KH, int KW) {
+  return (BN == 64 || BN == 128) && Cout % BN == 0 && KH == 3 && KW == 3 && KH * KW * (Cin / 64) <= BRES_MAX_BOXES &&
+         bres_a_slots(BN, KH * KW * (Cin / 64)) >= 2;
+}
+static void conv_prepare_pair_bres(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int Cout,
+                                   int KH, int KW, int padH, int padW, int mode, bf16* out, int num_sms, int BN, int w_copies) {
+  FRCNN_REQUIRE(bres_ok(Cin, Cout, BN, KH, KW), FRCNN_E_INVALID, "conv (pair kernel, resident weights): 3x3, N tile 64 / 128, at most 18 weight boxes");
+  conv_prepare_pair(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, BN, 1, w_copies, 1);
+  // a pair keeps the weights of ONE N tile: units are enumerated N-tile-fastest and dealt round-robin, so the pair count
+  // must be a multiple of the N tile count for every pair to stay on its tile
+  const int ntn = L->p.n_tiles_n;
+  int pairs = L->grid / 2;
+  if (pairs > ntn) pairs -= pairs % ntn;
+  L->grid = 2 * pairs;
+  FRCNN_REQUIRE(pairs % ntn == 0 || pairs < ntn, FRCNN_E_INVALID, "conv (pair kernel, resident weights): pair count / N tile mismatch");
+  L->p.occ = 3;
+  L->p.a_slots = bres_a_slots(BN, KH * KW * (Cin / 64));
+}
+
 void conv_prepare_head(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, int Hin, int Win, int Cin, int K, int num_sms) {
   FRCNN_REQUIRE(Cin % 64 == 0 && K >= 1 && K <= HEAD_MAXK, FRCNN_E_INVALID, "fused anchor head: Cin % 64 == 0, kernel size <= 7");
   FRCNN_REQUIRE(Hin >= K && Win >= K, FRCNN_E_INVALID, "fused anchor head: input smaller than the kernel");
@@ -2326,6 +2731,17 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
     FRCNN_REQUIRE(!forced || eligible, FRCNN_E_INVALID, "conv: the halo kernel needs 2x2..3x3 filters and a bf16 epilogue");
     // CTA-pair kernel (cta_group::2): force_mt 21 / 22, or automatically (FRCNN_CONV_PAIR, see the selection rule below)
     const bool pair_ok = eligible && !f32 && Cout % 64 == 0;
+    if (pair_ok && force_mt == 61) {   // swapped operands: 128 filters (M) x 256 pixels (N)
+      FRCNN_REQUIRE(Cout % 128 == 0 && KH == 3 && KW == 3, FRCNN_E_INVALID, "conv (swapped operands): 3x3, Cout a multiple of 128");
+      conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, 128, 2, w_copies, 1);
+      L->p.swap = 1;
+      return;
+    }
+    if (pair_ok && force_mt == 51) {   // CTA pairs with the layer's weights resident in shared memory
+      conv_prepare_pair_bres(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms,
+                             force_bn > 0 ? force_bn : (Cout % 128 == 0 ? 128 : 64), w_copies);
+      return;
+    }
     if (pair_ok && force_mt > 20) {
       // 21 / 22: CTA pairs; 31 / 32: halo kernel with two CTAs per SM; 41 / 42: CTA pairs with two CTAs per SM
       const int mt = force_mt % 10, kind = force_mt / 10;
@@ -2601,6 +3017,16 @@ static void launch_halo_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid
   FRCNN_CUDA_TRY(cudaGetLastError());
 }
 
+static void launch_swap_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+  static DeviceOnce configured;
+  const int smem = halo_smem_bytes(128, 2, HALO_MAXK);
+  if (first_use_on_device(configured)) {
+    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_halo_kernel<128, 2, HALO_MAXK, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  }
+  conv_halo_kernel<128, 2, HALO_MAXK, 1, true><<<grid, CONV_THREADS, smem, st>>>(maps, grp);
+  FRCNN_CUDA_TRY(cudaGetLastError());
+}
+
 template <int BN, int MT, int KMAX, int OCC = 1>
 static void launch_pair_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
   static DeviceOnce configured;
@@ -2624,7 +3050,36 @@ static void launch_pair_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid
   cfg.numAttrs = 1;
   FRCNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_pair_kernel<BN, MT, KMAX, OCC>, maps, grp));
 }
+template <int BN>
+static void launch_pair_bres_cfg(const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+  static DeviceOnce configured;
+  const int smem = bres_smem_bytes(BN, grp.p[0].KH * grp.p[0].KW * grp.p[0].cchunks);
+  if (first_use_on_device(configured)) {
+    FRCNN_CUDA_TRY(cudaFuncSetAttribute(conv_pair_bres_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(CONV_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  FRCNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, conv_pair_bres_kernel<BN>, maps, grp));
+}
 static void launch_pair_key(int BN, int MT, int occ, const ConvMaps& maps, const ConvGroup& grp, int grid, cudaStream_t st) {
+  if (occ == 3) {   // weights resident (conv_pair_bres_kernel)
+    switch (BN) {
+      case 64: launch_pair_bres_cfg<64>(maps, grp, grid, st); break;
+      case 128: launch_pair_bres_cfg<128>(maps, grp, grid, st); break;
+      default: throw Error{FRCNN_E_INVALID, "conv (pair kernel, resident weights): BN = 64 or 128"};
+    }
+    return;
+  }
   if (occ == 2) {
     switch (BN * 10 + MT) {
       case 641: launch_pair_cfg<64, 1, HALO_MAXK, 2>(maps, grp, grid, st); break;
@@ -2751,6 +3206,7 @@ void conv_launch(const ConvLaunch& L, cudaStream_t st) {
     maps.o[g] = L.tmOut;
   }
   if (L.p.wgrad && L.p.halo) launch_wgrad_halo_key(L.BN, maps, grp, L.grid, st);
+  else if (L.p.swap) launch_swap_cfg(maps, grp, L.grid, st);
   else if (L.p.pair) launch_pair_key(L.BN, L.p.MT, L.p.occ, maps, grp, L.grid, st);
   else if (L.p.halo) launch_halo_key(L.BN, L.p.MT, L.p.occ, maps, grp, L.grid, st);
   else launch_key(L.BN, L.p.MT, maps, grp, L.grid, st);

@@ -152,6 +152,28 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// The same for a CONVERGED warp: all 32 lanes execute the call with identical arguments, one elected lane issues.  Measured
+// (tools/micro/, profiles/r2_mma_issue.md): wrapping the whole issue loop in `if (lane == 0)` makes every operand a
+// per-thread value in divergent code, and nvcc moves them into the uniform registers UTCHMMA wants with an ELECT / R2UR x 7 /
+// BRA.U.ANY waterfall per instruction -- ~150-190 clocks per tcgen05.mma, more than the 128 clocks an M128 x N256 x K16 step
+// takes.  With the warp converged the operands are warp-uniform and no waterfall is generated.
+__device__ __forceinline__ void mma_bf16_ss_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i <-> lane base+i).
 __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t* v) {
   asm volatile(
@@ -245,6 +267,24 @@ __device__ __forceinline__ void mma_bf16_ss_2cta(uint32_t tmem_d, uint64_t desc_
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// converged-warp variants (see mma_bf16_ss_w)
+__device__ __forceinline__ void mma_bf16_ss_2cta_w(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_2cta_w(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "h"(cta_mask)
       : "memory");
 }
 // arrives on the barrier at this shared-memory offset in every CTA of `cta_mask` once the MMAs issued so far have completed

@@ -130,6 +130,36 @@ def test_conv_two_ctas_per_sm(F, small_model, case, bn, mt, pool):
     _conv_case(F, small_model, *case, seed=sum(case) + mt, bn=bn, mt=mt, pool=pool)
 
 
+@pytest.mark.parametrize("pool", [False, True])
+@pytest.mark.parametrize("case", [
+    (1, 16, 16, 64, 64, 3, 1), (1, 29, 51, 128, 128, 3, 1), (1, 45, 77, 64, 128, 3, 1), (1, 225, 400, 64, 128, 3, 1),
+    (1, 225, 400, 128, 128, 3, 1), (8, 113, 200, 128, 128, 3, 1), (1, 33, 20, 128, 64, 3, 0), (3, 61, 96, 64, 128, 3, 1),
+])
+def test_conv_pair_resident_weights(F, small_model, case, pool):
+    """conv_pair_bres_kernel (mt = 51): CTA pairs with every weight box of the layer resident in shared memory (loaded while
+    the pair's first unit runs, reused by all later units) -- the Cout = 64 / 128 layers (conv2_x at their real sizes, many
+    units per pair, ragged pair tiles, pad 0, the fused pool); bit-identical to the streaming pair kernel."""
+    a, _ = _conv_case(F, small_model, *case, seed=sum(case) + 51, bn=0, mt=51, pool=pool)
+    b, _ = _conv_case(F, small_model, *case, seed=sum(case) + 51, bn=case[4], mt=21, pool=pool)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("pool", [False, True])
+@pytest.mark.parametrize("case", [
+    (1, 16, 16, 64, 128, 3, 1), (1, 29, 51, 128, 128, 3, 1), (1, 45, 77, 64, 128, 3, 1), (1, 225, 400, 64, 128, 3, 1),
+    (1, 225, 400, 128, 128, 3, 1), (2, 57, 100, 256, 384, 3, 1), (1, 57, 99, 384, 384, 3, 1), (1, 33, 20, 128, 256, 3, 0),
+    (3, 61, 96, 64, 128, 3, 1), (1, 113, 200, 128, 256, 3, 1),
+])
+def test_conv_swapped_operands(F, small_model, case, pool):
+    """conv_halo_kernel<128, 2, 3, 1, SWAP> (mt = 61): the 128-filter weight box as the MMA's A operand, an 8 x 32-pixel halo
+    tile as its 256-wide B operand, accumulator lanes = output channels, pooling in registers, transposed staging.  Same
+    products in the same K order as the halo kernel: bit-identical outputs (ragged tiles, several filter tiles, pad 0,
+    the fused pool, the headline conv2_x / conv4_x shapes)."""
+    a, _ = _conv_case(F, small_model, *case, seed=sum(case) + 61, bn=0, mt=61, pool=pool)
+    b, _ = _conv_case(F, small_model, *case, seed=sum(case) + 61, bn=128, mt=12, pool=pool)
+    assert torch.equal(a, b)
+
+
 def test_conv_pair_equals_halo_kernel(F, small_model):
     """Same products, same fp32 accumulation order per output (chunk-major, taps inside): the pair kernel's outputs are
     bit-identical to the single-CTA halo kernel's."""

@@ -19,7 +19,7 @@ LAYERS = [("conv2_1", 225, 400, 64, 128, 0), ("conv2_2+pool", 225, 400, 128, 128
 LARGE = [("conv1_2+pool", 600, 1000, 64, 64, 1), ("conv2_2+pool", 300, 500, 128, 128, 1), ("conv3_3+pool", 150, 250, 256, 256, 1),
          ("conv4_1", 75, 125, 256, 512, 0), ("conv4_3+pool", 75, 125, 512, 512, 1)]
 KINDS = {1: "tap x1", 2: "tap x2", 11: "halo x1", 12: "halo x2", 21: "pair x1", 22: "pair x2", 31: "halo x1 occ2", 32: "halo x2 occ2",
-         41: "pair x1 occ2", 42: "pair x2 occ2"}
+         41: "pair x1 occ2", 42: "pair x2 occ2", 51: "pair resident-B", 61: "swap 128x256"}
 
 
 def run():
