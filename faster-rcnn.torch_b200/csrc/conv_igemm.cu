@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (true) {   // the WHOLE warp, converged: one elected lane issues (ptx::mma_bf16_ss_w)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
             const uint64_t db = ptx::make_desc_mn_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES), 8192);
 #pragma unroll
             for (int j = 0; j < BLOCK_K / 16; ++j)
-              ptx::mma_bf16_ss(d_tmem, da + (uint64_t)(j * 2048 >> 4), db + (uint64_t)(j * 2048 >> 4), IDESC_MN, (k > t.k_begin || j > 0) ? 1u : 0u);
+              ptx::mma_bf16_ss_w(d_tmem, da + (uint64_t)(j * 2048 >> 4), db + (uint64_t)(j * 2048 >> 4), IDESC_MN, (k > t.k_begin || j > 0) ? 1u : 0u);
           } else {
             const uint64_t da = ptx::make_desc_k_sw128(ptx::smem_u32(smem_a + stage * A_STAGE_BYTES));
             const uint64_t db = ptx::make_desc_k_sw128(ptx::smem_u32(smem_b + stage * B_STAGE_BYTES));
@@ -496,13 +496,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
                 // +32 bytes along K inside the 128-byte swizzle row = +2 in the (addr >> 4) field; the second
                 // 128-row sub-tile starts 16 KB further
                 if (!(grp.p[gi].dbg & 4))
-                  ptx::mma_bf16_ss(d_tmem + mt * BN, da + 2 * j + mt * (A_SUB_BYTES >> 4), db + 2 * j, idesc,
+                  ptx::mma_bf16_ss_w(d_tmem + mt * BN, da + 2 * j + mt * (A_SUB_BYTES >> 4), db + 2 * j, idesc,
                                    (k > t.k_begin || j > 0) ? 1u : 0u);
               }
             }
           }
-          ptx::mma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (k == t.k_end - 1) ptx::mma_commit(&tmem_full[acc]);
+          ptx::mma_commit_w(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (k == t.k_end - 1) ptx::mma_commit_w(&tmem_full[acc]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -1947,7 +1947,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (true) {   // the WHOLE warp, converged: one elected lane issues (ptx::mma_bf16_ss_w)
       int stage = 0;
       uint32_t phase = 0;
       int seq = 0;
@@ -1975,11 +1975,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
             for (int j = 0; j < BLOCK_K / 16; ++j) {
               // K step j = patch rows 2j, 2j + 1: A rows [16j, 16j + 16) contiguous; X rows (kh + 2j) * PW + kw of the halo box
               const uint64_t db = ptx::make_desc_mn_sw128_sbo(b_addr + (uint32_t)(((kh + 2 * j) * PW + kw) * 128), B_ATOM, sbo);
-              ptx::mma_bf16_ss(tmem_base + ti * BN, da + (uint64_t)(j * 2048 >> 4), db, IDESC_MN, (k > t.k_begin || j > 0) ? 1u : 0u);
+              ptx::mma_bf16_ss_w(tmem_base + ti * BN, da + (uint64_t)(j * 2048 >> 4), db, IDESC_MN, (k > t.k_begin || j > 0) ? 1u : 0u);
             }
           }
-          ptx::mma_commit(&empty_bar[stage]);
-          if (k == t.k_end - 1) ptx::mma_commit(&tmem_full[0]);
+          ptx::mma_commit_w(&empty_bar[stage]);
+          if (k == t.k_end - 1) ptx::mma_commit_w(&tmem_full[0]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
