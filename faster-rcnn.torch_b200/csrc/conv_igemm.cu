@@ -152,6 +152,119 @@ __device__ __forceinline__ unsigned long long conv_now() {
 #define CONV_TRACE(P, local, k) \
   do { if ((P).trace && (local) < 7) (P).trace[((size_t)blockIdx.x * 8 + (local)) * 8 + (k)] = conv_now(); } while (0)
 
+// Warp-local bf16 epilogue of one 128-pixel sub-tile of the halo kernels (tile 8 wide x 16 tall: a warp's 32 TMEM lanes are
+// four complete tile rows, so every 2 x 2 pooling window and every output row lies inside ONE warp).  The CTA-wide version
+// below needs two 256-thread barriers per 64 channels; its per-tile latency chain (TMEM load -> activation -> staging ->
+// barrier -> read-back -> store, ~2 us per 128 x 128 tile) paced the narrow layers even with two accumulator stages.  Here
+// every warp drains its lane quarter (q) and channel half (hf) on its own, 32 channels per pass, through a private 2 KB
+// staging area (32 rows x 64 B, 16-byte chunks XOR-swizzled by (row >> 1) & 3), with __syncwarp only.
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_warp(const ConvParams& p, const TileCoord& t, int hbase, uint32_t taddr_mt, uint8_t* tile_buf,
+                                                   uint32_t bias_addr, int ewarp, int lane, float k_neg, float k_pos) {
+  const int q = ewarp & 3, hf = ewarp >> 2;
+  const int row = q * 32 + lane;
+  const int dy = row >> 3, dx = row & 7;
+  const bool valid = (hbase + dy < p.Hout) && (t.w0 + dx < p.Wout);
+  const uint32_t st = ptx::smem_u32(tile_buf) + ewarp * 2048;
+  const uint32_t my_row = st + lane * 64;
+  const int sw = (lane >> 1) & 3;
+  const int Hp = (p.Hout + 1) >> 1, Wp = (p.Wout + 1) >> 1;
+  constexpr int PASSES = BN / 64;            // 32-channel passes per warp: channels [hf * BN / 2, (hf + 1) * BN / 2)
+#pragma unroll 1
+  for (int ps = 0; ps < PASSES; ++ps) {
+    const int col = hf * (BN / 2) + ps * 32;  // first accumulator column = channel offset inside the N tile
+    const int cbase = t.n0 + col;
+    uint32_t o[16];
+    {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(taddr_mt + col, v);
+      const uint32_t baddr = bias_addr + (uint32_t)cbase * 4u;
+      uint4 bq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) bq[j] = ptx::ld_shared_v4(baddr + j * 16);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x0 = __uint_as_float(v[4 * j]) + __uint_as_float(bq[j].x);
+        const float x1 = __uint_as_float(v[4 * j + 1]) + __uint_as_float(bq[j].y);
+        const float x2 = __uint_as_float(v[4 * j + 2]) + __uint_as_float(bq[j].z);
+        const float x3 = __uint_as_float(v[4 * j + 3]) + __uint_as_float(bq[j].w);
+        float y0 = fmaf(fminf(x0, 0.f), k_neg, x0 * k_pos);
+        float y1 = fmaf(fminf(x1, 0.f), k_neg, x1 * k_pos);
+        float y2 = fmaf(fminf(x2, 0.f), k_neg, x2 * k_pos);
+        float y3 = fmaf(fminf(x3, 0.f), k_neg, x3 * k_pos);
+        if (p.chan_scale) {  // training: SpatialDropout mask of this image's channels
+          const float4 m = __ldg(reinterpret_cast<const float4*>(p.chan_scale + (size_t)t.n_img * p.Cout + cbase) + j);
+          y0 *= m.x; y1 *= m.y; y2 *= m.z; y3 *= m.w;
+        }
+        o[2 * j] = ptx::pack_op16x2(y0, y1, p.f16);
+        o[2 * j + 1] = ptx::pack_op16x2(y2, y3, p.f16);
+      }
+    }
+    if (p.mode == EPI_POOL && !valid) {
+      const uint32_t ninf = p.f16 ? 0xFC00FC00u : 0xFF80FF80u;  // -inf: outside the map, never wins a ceil-mode window
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = ninf;
+    }
+    __syncwarp();   // the previous pass's staging reads are done
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ptx::st_shared_v4(my_row + ((c ^ sw) << 4), o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+    __syncwarp();
+    if (cbase >= p.Cout || (p.dbg & 1)) continue;
+    if (p.mode == EPI_POOL) {
+      // this warp's 4 tile rows x 8 pixels = 2 x 4 pooled pixels x 4 chunks of 8 channels: one item per lane
+      bf16* out_img = reinterpret_cast<bf16*>(p.out) + (size_t)t.n_img * Hp * Wp * p.Cout;
+      const int pp = lane >> 2, c = lane & 3;
+      const int ppy = pp >> 2, ppx = pp & 3;
+      const int ph = ((hbase + q * 4) >> 1) + ppy, pw = (t.w0 >> 1) + ppx;
+      if (ph < Hp && pw < Wp) {
+        const int r00 = (2 * ppy) * 8 + 2 * ppx, r01 = r00 + 1, r10 = r00 + 8, r11 = r10 + 1;
+        uint4 a = ptx::ld_shared_v4(st + r00 * 64 + ((c ^ ((r00 >> 1) & 3)) << 4));
+        const uint4 b = ptx::ld_shared_v4(st + r01 * 64 + ((c ^ ((r01 >> 1) & 3)) << 4));
+        const uint4 cc = ptx::ld_shared_v4(st + r10 * 64 + ((c ^ ((r10 >> 1) & 3)) << 4));
+        const uint4 d = ptx::ld_shared_v4(st + r11 * 64 + ((c ^ ((r11 >> 1) & 3)) << 4));
+        if (p.pool_arg) {
+          // training (bf16): remember the winner (first maximum in window scan order, as nn.SpatialMaxPooling)
+          const bf16* ea = reinterpret_cast<const bf16*>(&a);
+          const bf16* eb = reinterpret_cast<const bf16*>(&b);
+          const bf16* ec = reinterpret_cast<const bf16*>(&cc);
+          const bf16* ed = reinterpret_cast<const bf16*>(&d);
+          uint32_t lo = 0, hi = 0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            float best = __bfloat162float(ea[e]);
+            uint32_t arg = 0;
+            const float vb = __bfloat162float(eb[e]), vc = __bfloat162float(ec[e]), vd = __bfloat162float(ed[e]);
+            if (vb > best) { best = vb; arg = 1; }
+            if (vc > best) { best = vc; arg = 2; }
+            if (vd > best) { best = vd; arg = 3; }
+            if (e < 4) lo |= arg << (8 * e); else hi |= arg << (8 * (e - 4));
+          }
+          *reinterpret_cast<uint2*>(p.pool_arg + (((size_t)t.n_img * Hp + ph) * Wp + pw) * p.Cout + cbase + c * 8) = make_uint2(lo, hi);
+        }
+        a.x = ptx::max4_op16x2(a.x, b.x, cc.x, d.x, p.f16);
+        a.y = ptx::max4_op16x2(a.y, b.y, cc.y, d.y, p.f16);
+        a.z = ptx::max4_op16x2(a.z, b.z, cc.z, d.z, p.f16);
+        a.w = ptx::max4_op16x2(a.w, b.w, cc.w, d.w, p.f16);
+        *reinterpret_cast<uint4*>(out_img + ((size_t)ph * Wp + pw) * p.Cout + cbase + c * 8) = a;
+      }
+    } else {
+      bf16* out_img = reinterpret_cast<bf16*>(p.out) + (size_t)t.n_img * p.Hout * p.Wout * p.Cout;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int idx = it * 32 + lane;
+        const int lr = idx >> 2, c = idx & 3;
+        const int r = q * 32 + lr;
+        const int hh = hbase + (r >> 3), ww = t.w0 + (r & 7);
+        if (hh < p.Hout && ww < p.Wout) {
+          const uint4 val = ptx::ld_shared_v4(st + lr * 64 + ((c ^ ((lr >> 1) & 3)) << 4));
+          *reinterpret_cast<uint4*>(out_img + ((size_t)hh * p.Wout + ww) * p.Cout + cbase + c * 8) = val;
+        }
+      }
+    }
+  }
+}
+
 template <int BN, int MT, int ACC = 2>
 __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtensorMap* tmOuts, uint8_t* tile_buf,
                                               const float* sbias, uint32_t tmem_base, uint64_t* tmem_full,
@@ -238,6 +351,9 @@ __device__ __forceinline__ void epilogue_loop(const ConvGroup& grp, const CUtens
             }
           }
         }
+      } else if (p.halo && !p.wgrad && p.bw_shift == 3 && BN % 64 == 0 && !(p.dbg & 64)) {
+        // 8 x 16-pixel halo tiles: every warp on its own (no CTA-wide barriers)
+        epilogue_tile_warp<BN>(p, t, hbase, taddr, tile_buf, bias_addr, ewarp, lane, k_neg, k_pos);
       } else {
         const int Hp = (p.Hout + 1) >> 1, Wp = (p.Wout + 1) >> 1;
         bf16* out_img = reinterpret_cast<bf16*>(p.out) +
