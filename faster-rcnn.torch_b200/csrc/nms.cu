@@ -696,7 +696,7 @@ __device__ void cta_filter(const NmsState& st, int s, const float* __restrict__ 
   __syncthreads();
 }
 
-enum { NMS_PH_SORT_SELECT = 0, NMS_PH_RESOLVE_LOOP = 1, NMS_PH_FUSED = 2 };
+enum { NMS_PH_SORT_SELECT = 0, NMS_PH_RESOLVE_LOOP = 1, NMS_PH_FUSED = 2, NMS_PH_RESOLVE_SELECT = 3 };
 
 // development aid (FRCNN_NMS_PROF=1): phase time stamps of CTA 0, printed by the host after the launch
 __device__ long long g_nms_prof[64];
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(1024) nms_cta_kernel(NmsCtaArgs a) {
     prof_on = a.prof > 1000 ? (len0 > 4) : ((int)blockIdx.x == a.prof - 1);
   }
   prof_mark(prof_on, ps);
-  if (PHASE != NMS_PH_RESOLVE_LOOP) {
+  if (PHASE != NMS_PH_RESOLVE_LOOP && PHASE != NMS_PH_RESOLVE_SELECT) {
     if (threadIdx.x == 0) {
       if (a.seg_counts) {
         st.seg_beg[s] = s * a.seg_stride;
@@ -763,6 +763,13 @@ __global__ void __launch_bounds__(1024) nms_cta_kernel(NmsCtaArgs a) {
     prof_mark(prof_on, ps);
     cta_filter(st, s, a.boxes, a.row_stride, a.thr, nk);
     prof_mark(prof_on, ps);
+    if (PHASE == NMS_PH_RESOLVE_SELECT) {
+      // segments that can hold more than NMS_B boxes: the SECOND round's selection is made here and its 1024 x 1024
+      // suppression matrix goes to all SMs as well (next launch); the in-CTA matrix of the loop below took 136 us at
+      // 2 377 matches (vgg_large) on this one CTA
+      cta_select(st, s, a.boxes, a.row_stride, &sel);
+      return;
+    }
   }
   // further rounds (rare: more than NMS_B candidates survive the first round's keepers) stay inside the CTA
   for (;;) {
@@ -873,6 +880,7 @@ int nms_run(NmsWorkspace* ws, const float* boxes_dev, int row_stride, int n_seg,
       FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_cta_kernel<NMS_PH_SORT_SELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_CTA_MAX * 8));
       FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_cta_kernel<NMS_PH_RESOLVE_LOOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, mask_bytes));
       FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_cta_kernel<NMS_PH_FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, mask_bytes));
+      FRCNN_CUDA_TRY(cudaFuncSetAttribute(nms_cta_kernel<NMS_PH_RESOLVE_SELECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, mask_bytes));
     }
     int n2 = 1;
     while (n2 < max_seg_len) n2 <<= 1;
@@ -891,10 +899,19 @@ int nms_run(NmsWorkspace* ws, const float* boxes_dev, int row_stride, int n_seg,
     nms_cta_kernel<NMS_PH_SORT_SELECT><<<n_seg, 1024, n2 * 8, st_>>>(a);
     if (prof) nms_prof_dump("phase0 sort|select", st_);
     nms_mask_kernel<<<dim3(NMS_B * NMS_ROW_WORDS / 256, n_seg), 256, 0, st_>>>(st, thr);
+    int launched = 3;
+    static const int two_rounds = getenv("FRCNN_NMS_TWO_ROUNDS") ? atoi(getenv("FRCNN_NMS_TWO_ROUNDS")) : 1;
+    if (max_seg_len > NMS_B && two_rounds) {
+      // a second round is possible: its matrix on all SMs too (two more launches; a no-op when the round is empty)
+      nms_cta_kernel<NMS_PH_RESOLVE_SELECT><<<n_seg, 1024, mask_bytes, st_>>>(a);
+      if (prof) nms_prof_dump("phase1a load_mask|resolve|filter|select", st_);
+      nms_mask_kernel<<<dim3(NMS_B * NMS_ROW_WORDS / 256, n_seg), 256, 0, st_>>>(st, thr);
+      launched += 2;
+    }
     nms_cta_kernel<NMS_PH_RESOLVE_LOOP><<<n_seg, 1024, mask_bytes, st_>>>(a);
     FRCNN_CUDA_TRY(cudaGetLastError());
     if (prof) nms_prof_dump("phase1 load_mask|resolve|filter|select|mask|resolve|filter|select...", st_);
-    return 3;
+    return launched;
   } else {
     FRCNN_REQUIRE(n_seg <= 256, FRCNN_E_INVALID, "nms: at most 256 segments in the large-N path");
     FRCNN_REQUIRE(ws->seg_counts == nullptr, FRCNN_E_INVALID, "nms: device-side segment counts need the CTA-level path");
