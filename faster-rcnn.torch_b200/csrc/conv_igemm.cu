@@ -1586,6 +1586,7 @@ static constexpr int HEADK_MAX_SLICES = HEAD_MAXK;                           // 
 static_assert(HEADK_SMEM <= 227 * 1024, "anchor-network kernel: shared memory");
 static_assert((2 * HEADK_A_SLOTS + 2 * HEADK_B_SLOTS + 4) * 8 + 8 <= 512, "anchor-network kernel: mbarrier area");
 
+// u.x bit 24: the unit stores its fp32 sums as a slice even when it is the only one (the tail then runs in head_fixup_kernel)
 __device__ __forceinline__ void headk_decode(const int4 u, int& head, int& s, int& nsl, int& img, int& tile, int& kh0, int& kh1) {
   head = u.x & 0xff; s = (u.x >> 8) & 0xff; nsl = (u.x >> 16) & 0xff;
   img = u.y; tile = u.z; kh0 = u.w & 0xff; kh1 = (u.w >> 8) & 0xff;
@@ -1790,7 +1791,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1)
       }
       // partial sums / fix-up layout of a slice: [64 column groups][128 rows][4 floats]
       float* slice0 = hs.slices[g] + (tile_lin * nsl) * (long)(BLOCK_M * BN) + (long)(half * 32) * (BLOCK_M * 4) + row * 4;
-      if (nsl > 1) {
+      if (nsl > 1 || ((hs.units[ui].x >> 24) & 1)) {
         // ---- partial sums of this filter-row range -> slice s of the tile (a warp stores 512 contiguous bytes)
         float* sl = slice0 + (long)s * (BLOCK_M * BN);
 #pragma unroll 2
@@ -3406,10 +3407,15 @@ void conv_head_plan(HeadPlan* P, const HeadDesc* heads, int n_heads, int N, int 
     int nsl = p.KH;
     for (int n = 1; n <= p.KH; ++n)
       if ((long)((p.KH + n - 1) / n) * row_cost * 4 <= fair * 5) { nsl = n; break; }
-    slice_floats[g] = nsl > 1 ? (size_t)N * tiles[g] * nsl * BLOCK_M * HEAD_CM : 0;
+    // FRCNN_HEAD_TAIL=1 (measurement): the tail of EVERY head runs in head_fixup_kernel (a unit then ends with its slice store
+    // instead of the ~15 us in-epilogue tail).  Measured slower with frames in flight (4 829 vs 4 975 img/s: the fix-up
+    // kernel's 292 blocks cost 14.5 SM-us against 8 saved), so the default keeps the tail of unsplit units in their epilogue.
+    static const int tail_kernel = getenv("FRCNN_HEAD_TAIL") ? atoi(getenv("FRCNN_HEAD_TAIL")) : 0;
+    const bool sliced = nsl > 1 || tail_kernel;
+    slice_floats[g] = sliced ? (size_t)N * tiles[g] * nsl * BLOCK_M * HEAD_CM : 0;
     counter_ints[g] = 0;
     P->sched.tiles[g] = tiles[g];
-    if (nsl > 1) {
+    if (sliced) {
       HeadFixArgs& fx = P->fix;
       fx.head[fx.n] = g;
       fx.nsl[fx.n] = nsl;
@@ -3421,7 +3427,7 @@ void conv_head_plan(HeadPlan* P, const HeadDesc* heads, int n_heads, int N, int 
         for (int s = 0; s < nsl; ++s) {
           const int kh0 = (int)((long)p.KH * s / nsl), kh1 = (int)((long)p.KH * (s + 1) / nsl);
           // every unit also pays for its epilogue (slice store, or bias + PReLU + 1 x 1 tail): ~8 reduction steps' worth
-          units.push_back(U{(kh1 - kh0) * row_cost + 8, g, n, t, kh0, kh1, s, nsl});
+          units.push_back(U{(kh1 - kh0) * row_cost + 8, g | (sliced ? (1 << 24) : 0), n, t, kh0, kh1, s, nsl});
         }
   }
   for (int g = n_heads; g < MAX_GROUP; ++g) { slice_floats[g] = 0; counter_ints[g] = 0; P->sched.tiles[g] = 0; }
