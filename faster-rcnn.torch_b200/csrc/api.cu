@@ -1391,6 +1391,13 @@ static void ensure_det_workspace(frcnn_ctx* c, int N, int min_rows) {
   c->roi_cap = R;
 }
 
+// grid sizing of the small cnet kernels: the typical live row count (the grid-stride loops cover more); FRCNN_CNET_GRID_ROWS
+// overrides it for measurements
+static int env_rows() {
+  static const int v = getenv("FRCNN_CNET_GRID_ROWS") ? atoi(getenv("FRCNN_CNET_GRID_ROWS")) : 128;
+  return v;
+}
+
 // cnet on rows [0, *roi_total) of roi_out (bf16, [bins][C] order)
 static void run_cnet(frcnn_ctx* c, int rows_max) {
   for (size_t i = 0; i < c->fcs.size(); ++i) {
@@ -1400,7 +1407,7 @@ static void run_cnet(frcnn_ctx* c, int rows_max) {
     const ConvParams& fp = f.launch.p;
     const FcSlices sl = {fp.k_iters, fp.splits, fp.n_tiles_n, fp.dyn_ctas};
     launch_fc_tail(f.acc, P(c, f.p_b), P(c, f.p_bn_w), P(c, f.p_bn_b), P(c, f.p_bn_mean), P(c, f.p_bn_var), P(c, f.p_prelu),
-                   f.out_bf16, f.out_f32, rows_max, c->flags + 2, f.nout, c->stream, &sl, 512, c->eval_f16);
+                   f.out_bf16, f.out_f32, rows_max, c->flags + 2, f.nout, c->stream, &sl, env_rows(), c->eval_f16);
     ++c->launches;
   }
   const FcLayer& last = c->fcs.back();
