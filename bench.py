@@ -469,7 +469,7 @@ def bench_detect(hs, model, steps, warmup, batch, with_cpu, headline):
         rows = summ.get("full_%s_b%d" % (model, B))
         if rows and (h, w) == ((450, 800) if model == "vgg_small" else (600, 1000)):
             traffic = sum(r["dram_mb"] for r in rows) * 1e6
-            traffic_src = "profiles/r2_ncu_full_%s_b%d.md (dram__bytes_read.sum + dram__bytes_write.sum over %d tcgen05 launches)" % (model, B, len(rows))
+            traffic_src = "profiles/r2_ncu_full_b%d.md (dram__bytes_read.sum + dram__bytes_write.sum over the %d tcgen05 launches of one %s step)" % (B, len(rows), model)
     except Exception:
         pass
     total_frames = hs.sum_over_ranks(float(B)) * steps
