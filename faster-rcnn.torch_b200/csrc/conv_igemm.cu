@@ -17,9 +17,11 @@
 // layout -- and is consumed by four tcgen05.mma (M=128, N=BN, K=16) per 64-channel chunk and 128-row sub-tile.
 // MT = 2 halves the weight traffic per MAC for the narrow (Cout <= 128) layers, which are L2->SM bandwidth bound.
 //
-// Kernel structure (persistent, warp-specialised, 384 threads, 1 CTA / SM):
+// Kernel structure (persistent, warp-specialised, 384 threads, 1 or 2 CTAs / SM):
 //   warp 0    TMA producer   (one elected lane)        smem ring: full[s] / empty[s] mbarriers
-//   warp 1    MMA issuer     (one elected lane)        TMEM accumulators double-buffered: tmem_full / tmem_empty
+//   warp 1    MMA issuer     (the whole warp converged, one lane elected inside the asm: ptx::mma_bf16_ss_w -- a loop wrapped
+//             in `if (lane == 0)` costs ~130 clocks of operand waterfall per tcgen05.mma, profiles/r2_mma_issue.md)
+//                                                      TMEM accumulators double-buffered: tmem_full / tmem_empty
 //   warp 2    TMEM allocator
 //   warps 4-11 epilogue: tcgen05.ld 32x32b -> bias (smem) + PReLU + scale -> bf16 -> swizzled smem tile
 //             [-> 2x2 max pool in smem] -> coalesced 16-byte global stores (borders clipped);
@@ -27,8 +29,14 @@
 //
 // Kernels of this file (all share the warp roles and, except the first-layer ones, epilogue_loop):
 //   conv_igemm_kernel<BN, MT>        one TMA box per filter tap (any k x k, GEMMs, split-K, weight-gradient mode)
-//   conv_halo_kernel<BN, MT, KMAX>   tile + halo in ONE box per 64-channel chunk, taps = row-shifted UMMA descriptors
-//                                    (the wide 3x3 layers; KMAX = 7: the fused anchor heads with epilogue_head)
+//   conv_halo_kernel<BN, MT, KMAX, OCC, SWAP>   tile + halo in ONE box per 64-channel chunk, taps = row-shifted UMMA
+//                                    descriptors (the trunk's 3x3 layers; OCC = 2: two CTAs per SM; KMAX = 7: the fused
+//                                    anchor heads of the training forward with epilogue_head; SWAP: filters as the M side
+//                                    -- a measured, unselected variant); 8 x 16 tiles use the warp-local epilogue_tile_warp
+//   conv_pair_kernel<BN, MT, KMAX, OCC>   the halo kernel on CTA pairs (cta_group::2, M = 256, half weight boxes per CTA)
+//   conv_pair_bres_kernel<BN>        CTA pairs with the layer's weights resident in shared memory (measured, unselected)
+//   conv_head_kernel + head_fixup_kernel   the four anchor networks of evaluate mode in one launch: linear 128-position
+//                                    tiles on CTA pairs, reduction split by filter rows, tail in the epilogue / fix-up
 //   conv_wgrad_halo_kernel<BN, T>    weight gradient, T filter taps per unit sharing one dY box and one X halo box
 //   conv_first_kernel                the 3-channel first layer: the A operand (K = 27 padded to 32) is built in shared
 //                                    memory by producer warps straight from the fp32 NCHW frame (any frame)

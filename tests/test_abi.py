@@ -85,8 +85,10 @@ def test_host_geometry_equals_oracle(F, which):
     r = a.get(2, 3, 4, 5)
     o = oa.get(2, 3, 4, 5)
     assert r.unpack() == o.unpack() and r.index == o.index
-    assert m.output_dims(450, 800)[:2] == ([(18, 55, 98), (18, 27, 48)] if which == "small" else
-                                           [(18, 55, 98), (18, 27, 48)])
+    # head geometry is identical for the two models; the feature map carries the last block's filters
+    assert m.output_dims(450, 800)[:2] == [(18, 55, 98), (18, 27, 48)]
+    assert m.output_dims(450, 800)[4] == ((384, 29, 50) if which == "small" else (512, 29, 50))
+    assert m.output_dims(600, 1000)[:4] == [(18, 73, 123), (18, 36, 61), (18, 34, 59), (18, 32, 57)]
     m.close()
 
 
