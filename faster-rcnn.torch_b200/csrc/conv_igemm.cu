@@ -2895,16 +2895,41 @@ void conv_prepare(ConvLaunch* L, const bf16* in, const bf16* w_packed, int N, in
     if (pair_ok && force_mt == 0 && force_bn == 0 && env_int("FRCNN_CONV_DUO", 1)) {
       const int Ho = Hin + 2 * padH - KH + 1, Wo = Win + 2 * padW - KW + 1;
       const int wide = Cout % 256 == 0 ? 256 : (Cout % 192 == 0 ? 192 : 0);
+      // Re-measured after the issue-rate fix (converged-warp tcgen05.mma issue; profiles/r2_conv_smtime2_*.md):
+      //   * swapped operands (filters as M, 256 pixels as N) win where the reduction is short or the N tile would be 192:
+      //     the first conv of block 2 (Cin = 64: 19.5 instead of 21.9 SM-us at batch 1, 123 instead of 135 us at batch 8)
+      //     and the Cout = 384 layers once there are two waves of units (conv4_x at batch 8: 65 / 92 instead of 72 / 96 us);
+      //   * Cout = 256 layers with two waves of pairs: CTA pairs with ONE CTA per SM (87 / 146 us at batch 8 against 98 / 156
+      //     with two per SM: the deeper rings matter more than the overlap now that the MMA phase is shorter);
+      //   * Cout = 64 (vgg_large conv1_2): CTA pairs with 256-pixel tiles, two per SM (65 instead of 73 SM-us).
+      const bool swap_ok = KH == 3 && KW == 3 && Cout % 128 == 0 && env_int("FRCNN_CONV_SWAP", 1);
+      auto prepare_swap = [&]() {
+        conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, 128, 2, w_copies, 1);
+        L->p.swap = 1;
+      };
+      if (swap_ok && Cin == 64) {
+        prepare_swap();
+        return;
+      }
       if (wide) {
         const long pair_ctas = 2L * N * ((Ho + 2 * HALO_BH - 1) / (2 * HALO_BH)) * ((Wo + HALO_BW - 1) / HALO_BW) * (Cout / wide);
         if (pair_ctas >= 4L * num_sms || Cout % 128 != 0) {
-          conv_prepare_pair(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, wide, 1, w_copies, 2);
+          if (wide == 192 && swap_ok) prepare_swap();
+          else conv_prepare_pair(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, wide, 1, w_copies, wide == 256 ? 1 : 2);
           return;
         }
         if (sm_time && halo_cfg_ok(Cout, wide, 2) && env_int("FRCNN_CONV_SMTIME", 1)) {
           conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, wide, 2, w_copies, 1);
           return;
         }
+        if (wide == 192 && swap_ok) {   // latency schedule, few units: 22 / 31 us alone against 25 / 31 with two CTAs per SM
+          prepare_swap();
+          return;
+        }
+      }
+      if (Cout == 64 && halo_cfg_ok(Cout, 64, 2)) {
+        conv_prepare_pair(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, 64, 2, w_copies, 2);
+        return;
       }
       conv_prepare_halo(L, in, w_packed, N, Hin, Win, Cin, Cout, KH, KW, padH, padW, mode, out, num_sms, Cout % 128 == 0 ? 128 : 64, 1,
                         w_copies, 2);

@@ -2,7 +2,7 @@
 (what a frame costs when the SMs a launch leaves idle are filled by the other frames in flight), next to the isolated
 duration.  Two passes on the GPU box:
     ncu --metrics gpu__time_duration.sum,sm__cycles_active.avg,sm__cycles_elapsed.max --clock-control none --csv \
-        --log-file gpurun_out/sweep_smtime.csv -k regex:'conv_(halo|igemm|pair)_kernel' python tools/sweep_smtime.py run [batch]
+        --log-file gpurun_out/sweep_smtime.csv -k regex:'conv_(halo|igemm|pair|pair_bres)_kernel' python tools/sweep_smtime.py run [batch]
     python tools/sweep_smtime.py join gpurun_out/sweep_smtime.csv gpurun_out/sweep_smtime_order.jsonl
 `run` launches every configuration exactly once (in the order it logs), `join` pairs the ncu rows with that log."""
 import csv
