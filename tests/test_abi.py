@@ -181,3 +181,28 @@ def test_lua_glue_binds_only_declared_symbols_with_the_declared_arity():
             assert n == decl[name], "%s: %s called with %d arguments, declared with %d" % (os.path.basename(path), name, n, decl[name])
             calls += 1
     assert calls >= 25
+
+
+def test_lua_glue_installs_the_module_slot_overrides():
+    """accelerate(model) must leave objective.lua / Detector.lua runnable unmodified: the glue derives the plan
+    from the nn modules, binds weights and gradients, and installs pnet / cnet forward + backward and the `amp` class.
+    Static check of the Lua source (no Lua in this image)."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "faster-rcnn.torch_b200", "lua")
+    src = open(os.path.join(root, "frcnn_b200.lua")).read()
+    code = re.sub(r"--[^\n]*", "", src)
+    for slot in ("pnet.forward", "pnet.backward", "cnet.forward", "cnet.backward", "pnet.updateOutput", "cnet.updateOutput"):
+        assert re.search(r"\b%s\s*=" % re.escape(slot), code), slot
+    acc = code[code.index("function M.accelerate"):]
+    acc = acc[:acc.index("\nend")]
+    for call in ("derive_anchor_nets", "derive_class_layers", "frcnn_model_plan", "frcnn_bind_params", "M.pack(model)", "M.bind_grads(model)",
+                 "M.install(model)", "M.install_amp(model)"):
+        assert call in acc, call
+    assert "nn.SpatialAdaptiveMaxPooling = cls" in code and "updateGradInput" in code and "self.indices" in code
+    # the calls the reference's own files make on those slots, by the lines SURVEY 8b lists
+    for fn in ("frcnn_pnet_forward_train", "frcnn_pnet_forward", "frcnn_pnet_backward", "frcnn_cnet_forward_train", "frcnn_cnet_forward",
+               "frcnn_cnet_backward", "frcnn_adaptive_maxpool_forward", "frcnn_adaptive_maxpool_backward", "frcnn_train_batch",
+               "frcnn_dp_init_all", "frcnn_dp_allreduce", "frcnn_find_positive", "frcnn_sample_negative", "frcnn_find_nearby_negative",
+               "frcnn_rmsprop_step", "frcnn_detect_begin", "frcnn_detect_end"):
+        assert "C.%s(" % fn in code, fn
