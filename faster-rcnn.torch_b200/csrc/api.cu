@@ -2883,6 +2883,32 @@ int frcnn_conv_wgrad_bf16(frcnn_ctx* c, const uint16_t* x_dev, const uint16_t* d
   API_END(c)
 }
 
+int frcnn_conv_first_wgrad(frcnn_ctx* c, const uint16_t* dy_dev, const float* img_dev, int n, int h, int w, int pad,
+                           float* dw_dev, int iters, float* elapsed_ms) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_REQUIRE(dy_dev && img_dev && dw_dev, FRCNN_E_INVALID, "null argument");
+  FRCNN_REQUIRE(n > 0 && h > 0 && w > 0 && pad >= 0 && pad <= 1, FRCNN_E_INVALID, "bad shape");
+  if (iters < 1) iters = 1;
+  cudaEvent_t e0, e1;
+  FRCNN_CUDA_TRY(cudaEventCreate(&e0));
+  FRCNN_CUDA_TRY(cudaEventCreate(&e1));
+  FRCNN_CUDA_TRY(cudaEventRecord(e0, c->stream));
+  for (int i = 0; i < iters; ++i) {
+    frcnn::launch_first_wgrad((const frcnn::bf16*)dy_dev, img_dev, dw_dev, n, h, w, pad, c->sm_count, c->stream);
+    ++c->launches;
+  }
+  FRCNN_CUDA_TRY(cudaEventRecord(e1, c->stream));
+  FRCNN_CUDA_TRY(cudaGetLastError());
+  FRCNN_CUDA_TRY(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  FRCNN_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  if (elapsed_ms) *elapsed_ms = ms / iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  API_END(c)
+}
+
 int frcnn_conv_first(frcnn_ctx* c, const float* img_dev, const float* w_dev, const float* bias_dev, const float* prelu_dev,
                      float scale, int n, int h, int w, int cout, int pad, int pool, uint16_t* out_dev, int iters, float* elapsed_ms) {
   API_BEGIN(c)

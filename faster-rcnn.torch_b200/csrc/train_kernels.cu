@@ -253,82 +253,154 @@ void launch_head_tail_bwd(const HeadTailBwd& H, int num_sms, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------ first-layer wgrad
+// Ampere-style asynchronous copies (LDGSTS): src_bytes = 0 zero-fills the destination, which is how the out-of-frame
+// pixels of a border tile become zeros without a branch around the copy.
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Warp-level tensor-core pieces of the first-layer weight gradient: the GEMM is [64 co] x [27 -> 32 taps] with K = pixels,
+// far too narrow in M and N for a tcgen05 tile to pay for its TMEM round trip, and HBM-bound (one read of dY) once the
+// products leave the fp32 pipe.
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_m16n8k16_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// two fp32 values -> a bf16 pair (hi) and the bf16 pair of what the rounding dropped (lo): hi + lo carries 16 mantissa
+// bits of the frame, so the products match the fp32 FMA version to ~2^-17 instead of 2^-9
+__device__ __forceinline__ void split_bf16x2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(v0 - __uint_as_float(hi << 16), v1 - __uint_as_float(hi & 0xffff0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+constexpr int FW_CO = 64, FW_TH = 8, FW_TW = 32;
+constexpr int FW_D_BYTES = FW_TH * FW_TW * FW_CO * 2;                      // 32 KB gradient tile
+constexpr int FW_PITCH = 40, FW_CPITCH = (FW_TH + 2) * FW_PITCH;           // frame patch: [3][10][40] floats, 34 columns used
+constexpr int FW_IMG_STRIDE = 1280;                                        // floats per stage (3 * 400 rounded up)
+constexpr int FW_SMEM = 2 * FW_D_BYTES + 2 * FW_IMG_STRIDE * (int)sizeof(float);   // two stages: 74 KB, two CTAs per SM
+
 // dW[co][c][kh][kw] += sum over pixels of dpre[n][h][w][co] * img[n][c][h + kh - pad][w + kw - pad] for the 3-channel
-// first convolution (K = 27 is too narrow for the tensor-core wgrad).  Persistent CTAs over 8 x 32 pixel tiles: the
-// gradient tile [256 px][64 co] and the (8+2) x (32+2) x 3 image patch are staged in shared memory, thread <-> (co,
-// tap group) accumulates its 7 taps in registers across all its tiles, one atomic per accumulator at the end.
-__global__ void __launch_bounds__(256) first_wgrad_kernel(const bf16* __restrict__ dpre, const float* __restrict__ img,
-                                                          float* __restrict__ dw, int N, int H, int W, int pad) {
-  // thread <-> (8 output channels, 7 of the 27 taps, one of 8 interleaved pixel subsets): per pixel ONE 16-byte
-  // gradient read + 7 image reads feed 56 FMAs into a register tile (the one-channel-per-thread version issued
-  // 8 shared-memory loads per 7 FMAs and ran at the LDS rate)
-  constexpr int CO = 64, TAPS = 27, TG = 4, PER = 7, TH = 8, TW = 32, PS = 8;
-  __shared__ __align__(16) bf16 s_d[TH * TW][CO];        // 32 KB
-  __shared__ float s_img[3][TH + 2][TW + 2];
-  const int cg = threadIdx.x & 7, tg = (threadIdx.x >> 3) & 3, ps = threadIdx.x >> 5;
-  int t_off[PER];
+// first convolution.  Persistent CTAs over 8 x 32 pixel tiles, two shared-memory stages filled by cp.async (the next
+// tile lands while this one is consumed).  Warp w owns tile row w = two K-steps of 16 pixels: A = dY^T fragments come
+// out of the [px][co] tile with ldmatrix.trans (16-byte chunks XOR-swizzled by px & 7, so the eight row addresses of a
+// matrix hit eight different bank groups), B = the frame at 32 tap offsets, split hi/lo in registers; 64 co x 32 taps
+// accumulate in 64 registers per thread over all the CTA's tiles, then warps -> shared -> one global atomic per entry.
+__global__ void __launch_bounds__(256, 2) first_wgrad_kernel(const bf16* __restrict__ dpre, const float* __restrict__ img,
+                                                             float* __restrict__ dw, int N, int H, int W, int pad) {
+  constexpr int CO = FW_CO, TAPS = 27, TH = FW_TH, TW = FW_TW;
+  extern __shared__ __align__(128) unsigned char fw_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  int toff[4];
 #pragma unroll
-  for (int j = 0; j < PER; ++j) {
-    const int tap = min(tg + j * TG, TAPS - 1);
-    t_off[j] = ((tap / 9) * (TH + 2) + (tap % 9) / 3) * (TW + 2) + tap % 3;
+  for (int nt = 0; nt < 4; ++nt) {
+    const int tap = min(nt * 8 + g, TAPS - 1);     // taps 27..31 are padding: computed on a valid address, never stored
+    toff[nt] = (tap / 9) * FW_CPITCH + ((tap % 9) / 3) * FW_PITCH + tap % 3 + 2 * t;
   }
-  float acc[8][PER];
+  float acc[4][4][4];
 #pragma unroll
-  for (int e = 0; e < 8; ++e)
+  for (int m = 0; m < 4; ++m)
 #pragma unroll
-    for (int j = 0; j < PER; ++j) acc[e][j] = 0.f;
-  const float* simg = &s_img[0][0][0];
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[m][nt][e] = 0.f;
   const int tiles_w = (W + TW - 1) / TW, tiles_h = (H + TH - 1) / TH;
-  const long total_tiles = (long)N * tiles_h * tiles_w;
+  const int total_tiles = N * tiles_h * tiles_w;
   const long plane = (long)H * W;
-  for (long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    const int tw = (int)(tile % tiles_w);
-    const long r = tile / tiles_w;
-    const int th = (int)(r % tiles_h), n = (int)(r / tiles_h);
+
+  auto stage = [&](int tile, int b) {
+    const int tw = tile % tiles_w;
+    const int r = tile / tiles_w;
+    const int th = r % tiles_h, n = r / tiles_h;
     const int h0 = th * TH, w0 = tw * TW;
-    __syncthreads();
+    unsigned char* sd = fw_smem + b * FW_D_BYTES;
+    float* si = reinterpret_cast<float*>(fw_smem + 2 * FW_D_BYTES) + b * FW_IMG_STRIDE;
     // gradient tile: 256 px x 128 B, 16-byte vectors
     for (int i = threadIdx.x; i < TH * TW * 8; i += 256) {
       const int px = i >> 3, c8 = i & 7;
       const int h = h0 + px / TW, w = w0 + px % TW;
-      uint4 v = make_uint4(0, 0, 0, 0);
-      if (h < H && w < W) v = *reinterpret_cast<const uint4*>(dpre + (((long)n * H + h) * W + w) * CO + c8 * 8);
-      *reinterpret_cast<uint4*>(&s_d[px][c8 * 8]) = v;
+      const bool in = h < H && w < W;
+      cp_async_16(sd + px * (CO * 2) + ((c8 ^ (px & 7)) << 4), in ? dpre + (((long)n * H + h) * W + w) * CO + c8 * 8 : dpre, in ? 16 : 0);
     }
     for (int i = threadIdx.x; i < 3 * (TH + 2) * (TW + 2); i += 256) {
       const int c = i / ((TH + 2) * (TW + 2)), rr = i % ((TH + 2) * (TW + 2));
-      const int yy = h0 + rr / (TW + 2) - pad, xx = w0 + rr % (TW + 2) - pad;
-      s_img[c][rr / (TW + 2)][rr % (TW + 2)] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(img + ((long)n * 3 + c) * plane + (long)yy * W + xx) : 0.f;
+      const int py = rr / (TW + 2), pxx = rr % (TW + 2);
+      const int yy = h0 + py - pad, xx = w0 + pxx - pad;
+      const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      cp_async_4(si + c * FW_CPITCH + py * FW_PITCH + pxx, in ? img + ((long)n * 3 + c) * plane + (long)yy * W + xx : img, in ? 4 : 0);
     }
+    cp_async_commit();
+  };
+
+  // ldmatrix row of this lane: matrix j = lane / 8 covers pixels (j / 2) * 8 .. + 7 and channel chunk 2 m + (j & 1)
+  const int a_px = ((lane >> 4) << 3) + (lane & 7), a_ch = (lane >> 3) & 1, a_sw = lane & 7;
+  int b = 0;
+  if ((int)blockIdx.x < total_tiles) stage(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, b ^= 1) {
+    const int nxt = tile + gridDim.x;
+    if (nxt < total_tiles) { stage(nxt, b ^ 1); cp_async_wait<1>(); } else cp_async_wait<0>();
     __syncthreads();
-#pragma unroll 2
-    for (int px = ps; px < TH * TW; px += PS) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(&s_d[px][cg * 8]);
-      const bf16* d8 = reinterpret_cast<const bf16*>(&raw);
-      const int base = (px / TW) * (TW + 2) + (px % TW);
-      float iv[PER];
+    const uint32_t sd = (uint32_t)__cvta_generic_to_shared(fw_smem + b * FW_D_BYTES);
+    const float* simg = reinterpret_cast<const float*>(fw_smem + 2 * FW_D_BYTES) + b * FW_IMG_STRIDE + warp * FW_PITCH;
 #pragma unroll
-      for (int j = 0; j < PER; ++j) iv[j] = simg[base + t_off[j]];
+    for (int half = 0; half < 2; ++half) {
+      uint32_t bh[4][2], bl[4][2];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float d = __bfloat162float(d8[e]);
+      for (int nt = 0; nt < 4; ++nt) {
+        const float* s = simg + half * 16 + toff[nt];     // B[k][n]: k = 2t, 2t+1 (reg 0) and 2t+8, 2t+9 (reg 1), n = g
+        split_bf16x2(s[0], s[1], bh[nt][0], bl[nt][0]);
+        split_bf16x2(s[8], s[9], bh[nt][1], bl[nt][1]);
+      }
+      const uint32_t row = sd + (warp * 32 + half * 16 + a_px) * (CO * 2);
 #pragma unroll
-        for (int j = 0; j < PER; ++j) acc[e][j] = fmaf(d, iv[j], acc[e][j]);
+      for (int m = 0; m < 4; ++m) {
+        uint32_t a[4];
+        ldmatrix_x4_trans(a, row + (((2 * m + a_ch) ^ a_sw) << 4));
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          mma_m16n8k16_bf16(acc[m][nt], a, bh[nt][0], bh[nt][1]);
+          mma_m16n8k16_bf16(acc[m][nt], a, bl[nt][0], bl[nt][1]);
+        }
       }
     }
+    __syncthreads();   // stage b is refilled by the next iteration's copies
   }
+  // D fragment: rows co = 16 m + g (+8), columns tap = 8 nt + 2t (+1)
+  float* s_out = reinterpret_cast<float*>(fw_smem);
+  for (int i = threadIdx.x; i < CO * 32; i += 256) s_out[i] = 0.f;
+  __syncthreads();
 #pragma unroll
-  for (int e = 0; e < 8; ++e)
+  for (int m = 0; m < 4; ++m)
 #pragma unroll
-    for (int j = 0; j < PER; ++j) {
-      const int tap = tg + j * TG;
-      if (tap < TAPS && acc[e][j] != 0.f) atomicAdd(dw + (cg * 8 + e) * TAPS + tap, acc[e][j]);  // Torch layout [co][c][kh][kw]
-    }
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int co = m * 16 + g + (e >> 1) * 8, tap = nt * 8 + 2 * t + (e & 1);
+        if (tap < TAPS && acc[m][nt][e] != 0.f) atomicAdd(&s_out[co * 32 + tap], acc[m][nt][e]);
+      }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CO * TAPS; i += 256) {   // Torch layout [co][c][kh][kw]
+    const float v = s_out[(i / TAPS) * 32 + i % TAPS];
+    if (v != 0.f) atomicAdd(dw + i, v);
+  }
 }
 void launch_first_wgrad(const bf16* dpre, const float* img, float* dw, int N, int H, int W, int pad, int num_sms, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(first_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM); attr = true; }
   const long tiles = (long)N * ((H + 7) / 8) * ((W + 31) / 32);
-  const int grid = (int)std::min<long>(tiles, (long)num_sms * 4);
-  first_wgrad_kernel<<<grid, 256, 0, st>>>(dpre, img, dw, N, H, W, pad);
+  // the kernel indexes tiles in 32 bits: 2^31 tiles would be a 70 TB gradient tensor
+  const int grid = (int)std::min<long>(tiles, (long)num_sms * 2);
+  first_wgrad_kernel<<<grid, 256, FW_SMEM, st>>>(dpre, img, dw, N, H, W, pad);
 }
 
 // ------------------------------------------------------------------------------------------ misc

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 export PYTHONUNBUFFERED=1
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 1200 --csv --log-file gpurun_out/launches_train_b8.csv python bench.py --workload train --batch 8 --steps 1 --warmup 1 > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -c 2500 --csv --log-file gpurun_out/launches_train_b8.csv python bench.py --workload train --batch 8 --steps 1 --warmup 1 > /dev/null 2>&1
 python - <<'PY'
 import csv, re, collections
 lines=[l for l in open('gpurun_out/launches_train_b8.csv') if not l.startswith('==')]
