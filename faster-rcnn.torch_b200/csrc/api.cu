@@ -69,7 +69,7 @@ struct FcLayer {
   ConvLaunch launch;
   float dropout = 0.f;
   // training buffers for up to cw_rows example rows
-  float *t_acc = nullptr, *t_pre = nullptr, *t_xhat = nullptr, *t_rstd = nullptr, *t_mask = nullptr, *t_din = nullptr, *t_out32 = nullptr;
+  float *t_acc = nullptr, *t_pre = nullptr, *t_xhat = nullptr, *t_rstd = nullptr, *t_stat = nullptr, *t_mask = nullptr, *t_din = nullptr, *t_out32 = nullptr;
   bf16 *t_out = nullptr, *t_dy = nullptr, *w_dgrad = nullptr;
   float* dw_taps = nullptr;
   long dgrad_gen = -1;
@@ -1039,6 +1039,7 @@ static void ensure_objective_workspace(frcnn_ctx* c, int rows) {
     f.t_pre = (float*)dev_alloc(A, rn * sizeof(float));
     f.t_xhat = f.bn ? (float*)dev_alloc(A, rn * sizeof(float)) : nullptr;
     f.t_rstd = (float*)dev_alloc(A, (size_t)NF * f.nout * sizeof(float));   // BatchNorm 1/std of every frame's ROI batch
+    f.t_stat = (float*)dev_alloc(A, (size_t)NF * 2 * f.nout * sizeof(float));   // and its mean / unbiased variance
     f.t_mask = (float*)dev_alloc(A, rn * sizeof(float));
     f.t_din = (float*)dev_alloc(A, rn * sizeof(float));
     f.t_out32 = (float*)dev_alloc(A, rn * sizeof(float));
@@ -1085,86 +1086,83 @@ static void wgrad_rows(frcnn_ctx* c, const bf16* dy, const bf16* x, int R, int n
 // nf frames stored back to back in c->t_rows ([rows][bins][C] bf16; frame f = rows [off[f], off[f] + R[f])) with targets
 // c->crtarget / c->cctarget; leaves d(loss)/d(rows) in c->t_dx and adds frame f's losses to c->losses_dev[8 f + 2..3].
 // Stage-wise over the frames: every Linear layer is ONE tensor-core GEMM over all rows (forward, data gradient, weight
-// gradient), while BatchNormalization / PReLU / Dropout and the criteria run per frame on its row slice -- in the
-// reference cnet sees the ROI batch of one image at a time (objective.lua:164 inside the per-image loop), so the batch
-// statistics, the running-statistics updates (in frame order) and the mean over the frame's rows stay per frame.
-static void cnet_train_forward(frcnn_ctx* c, int nf, const int* off, const int* R, const float* const* cnet_masks, const uint64_t* seeds) {
+// gradient), and BatchNormalization / PReLU / Dropout and the criteria are ONE launch each with the frame on blockIdx.y
+// (or looked up from the row) -- in the reference cnet sees the ROI batch of one image at a time (objective.lua:164
+// inside the per-image loop), so the batch statistics, the running-statistics updates (in frame order) and the mean
+// over the frame's rows stay per frame inside those launches.
+static FrameList make_frames(int nf, const int* off, const int* R, const int* n_pos) {
+  FrameList fl;
+  memset(&fl, 0, sizeof(fl));
+  fl.nf = nf;
+  for (int f = 0; f < nf; ++f) { fl.off[f] = off[f]; fl.R[f] = R[f]; fl.n_pos[f] = n_pos ? n_pos[f] : 0; }
+  return fl;
+}
+static void cnet_train_forward(frcnn_ctx* c, const FrameList& fl, const float* const* cnet_masks, const uint64_t* seeds) {
   cudaStream_t st = c->stream;
-  const int rows = off[nf - 1] + R[nf - 1];
+  const int rows = fl.rows();
   if (rows <= 0) return;
+  FrameSeeds fs;
+  for (int f = 0; f < fl.nf; ++f) fs.seed[f] = seeds[f];
   // ---- cnet forward, training mode (objective.lua:164)
   const bf16* in = c->t_rows;
   for (size_t i = 0; i < c->fcs.size(); ++i) {
     FcLayer& f = c->fcs[i];
     gemm_rows(c, in, f.w_packed, rows, f.nin, f.nout, f.t_acc);
-    for (int fr = 0; fr < nf; ++fr) {
-      if (R[fr] <= 0) continue;
-      const size_t o = (size_t)off[fr] * f.nout;
-      if (cnet_masks && cnet_masks[i]) {
-        FRCNN_CUDA_TRY(cudaMemcpyAsync(f.t_mask + o, cnet_masks[i], (size_t)R[fr] * f.nout * sizeof(float), cudaMemcpyDeviceToDevice, st));
-      } else {
-        launch_dropout_mask(f.t_mask + o, R[fr] * f.nout, f.dropout, seeds[fr], 100u + (uint32_t)i, st);
-      }
-      FcTrainFwd ff;
-      ff.acc = f.t_acc + o; ff.bias = P(c, f.p_b); ff.bn_w = P(c, f.p_bn_w); ff.bn_b = P(c, f.p_bn_b); ff.prelu = P(c, f.p_prelu);
-      ff.bn_mean = const_cast<float*>(P(c, f.p_bn_mean)); ff.bn_var = const_cast<float*>(P(c, f.p_bn_var));
-      ff.mask = f.t_mask + o; ff.keep_scale = f.dropout > 0.f ? 1.f / (1.f - f.dropout) : 1.f;
-      ff.pre = f.t_pre + o; ff.xhat = f.t_xhat ? f.t_xhat + o : nullptr; ff.rstd = f.t_rstd + (size_t)fr * f.nout;
-      ff.out_bf16 = f.t_out + o; ff.out_f32 = f.t_out32 + o; ff.R = R[fr]; ff.n = f.nout;
-      launch_fc_train_fwd(ff, st);
-      c->launches += 2;
+    if (cnet_masks && cnet_masks[i]) {   // explicit masks: single-frame (test) facility
+      FRCNN_CUDA_TRY(cudaMemcpyAsync(f.t_mask, cnet_masks[i], (size_t)rows * f.nout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+      launch_dropout_mask_frames(f.t_mask, fl, f.nout, f.dropout, fs, 100u + (uint32_t)i, st);
     }
+    FcTrainFwd ff;
+    ff.acc = f.t_acc; ff.bias = P(c, f.p_b); ff.bn_w = P(c, f.p_bn_w); ff.bn_b = P(c, f.p_bn_b); ff.prelu = P(c, f.p_prelu);
+    ff.bn_mean = const_cast<float*>(P(c, f.p_bn_mean)); ff.bn_var = const_cast<float*>(P(c, f.p_bn_var));
+    ff.mask = f.t_mask; ff.keep_scale = f.dropout > 0.f ? 1.f / (1.f - f.dropout) : 1.f;
+    ff.pre = f.t_pre; ff.xhat = f.t_xhat; ff.rstd = f.t_rstd; ff.stat = f.t_stat;
+    ff.out_bf16 = f.t_out; ff.out_f32 = f.t_out32; ff.n = f.nout;
+    launch_fc_train_fwd(ff, fl, st);
+    c->launches += 2 + ((f.bn && fl.nf > 1) ? 1 : 0);
     in = f.t_out;
   }
 }
 // ext_dreg / ext_dcls: gradients wrt cnet's two outputs supplied by the caller (cnet:backward(cinput, {crdelta, ccdelta}),
 // objective.lua:179) instead of the built-in criteria
-static void cnet_train_loss_bwd(frcnn_ctx* c, int nf, const int* off, const int* R, const int* n_pos, const float* ext_dreg = nullptr,
-                                const float* ext_dcls = nullptr) {
-  cudaStream_t st = c->stream;
-  const int rows = off[nf - 1] + R[nf - 1];
-  if (rows <= 0) return;
-  // ---- detection-stage criteria + backward through the two output branches (objective.lua:166-179), per frame
+static void cnet_train_loss_bwd(frcnn_ctx* c, const FrameList& fl, const float* ext_dreg = nullptr, const float* ext_dcls = nullptr) {
+  if (fl.rows() <= 0) return;
+  // ---- detection-stage criteria + backward through the two output branches (objective.lua:166-179): one launch over
+  // the rows of all frames, each row averaged over ITS frame's ROI batch
   FcLayer& last = c->fcs.back();
-  const int no = c->class_count + 5;
-  for (int fr = 0; fr < nf; ++fr) {
-    if (R[fr] <= 0) continue;
-    CnetLossParams cl;
-    cl.hidden = last.t_out32 + (size_t)off[fr] * last.nout;
-    cl.w_reg = P(c, c->p_reg_w); cl.b_reg = P(c, c->p_reg_b); cl.w_cls = P(c, c->p_cls_w); cl.b_cls = P(c, c->p_cls_b);
-    cl.crtarget = c->crtarget + (size_t)off[fr] * 4; cl.cctarget = c->cctarget + off[fr];
-    cl.R = R[fr]; cl.n_pos = n_pos[fr]; cl.nin = last.nout; cl.ncls = c->class_count + 1;
-    cl.d_hidden = c->t_dhidden + (size_t)off[fr] * last.nout; cl.dz = c->t_dz + (size_t)off[fr] * no;
-    cl.g_w_reg = G(c, c->p_reg_w); cl.g_b_reg = G(c, c->p_reg_b); cl.g_w_cls = G(c, c->p_cls_w); cl.g_b_cls = G(c, c->p_cls_b);
-    cl.losses = nf == 1 ? c->losses_cur : c->losses_dev + 8 * fr;
-    cl.ext_dreg = ext_dreg ? ext_dreg + (size_t)off[fr] * 4 : nullptr;
-    cl.ext_dcls = ext_dcls ? ext_dcls + (size_t)off[fr] * (c->class_count + 1) : nullptr;
-    launch_cnet_loss_bwd(cl, st);
-    c->launches += 2;
-  }
+  CnetLossParams cl;
+  cl.hidden = last.t_out32;
+  cl.w_reg = P(c, c->p_reg_w); cl.b_reg = P(c, c->p_reg_b); cl.w_cls = P(c, c->p_cls_w); cl.b_cls = P(c, c->p_cls_b);
+  cl.crtarget = c->crtarget; cl.cctarget = c->cctarget;
+  cl.nin = last.nout; cl.ncls = c->class_count + 1;
+  cl.d_hidden = c->t_dhidden; cl.dz = c->t_dz;
+  cl.g_w_reg = G(c, c->p_reg_w); cl.g_b_reg = G(c, c->p_reg_b); cl.g_w_cls = G(c, c->p_cls_w); cl.g_b_cls = G(c, c->p_cls_b);
+  cl.losses = fl.nf == 1 ? c->losses_cur : c->losses_dev;
+  cl.loss_stride = fl.nf == 1 ? 0 : 8;
+  cl.ext_dreg = ext_dreg;
+  cl.ext_dcls = ext_dcls;
+  launch_cnet_loss_bwd(cl, fl, c->stream);
+  c->launches += 2;
 }
-static void cnet_train_backward(frcnn_ctx* c, int nf, const int* off, const int* R) {
+static void cnet_train_backward(frcnn_ctx* c, const FrameList& fl) {
   cudaStream_t st = c->stream;
   const int bins = c->roi_kh * c->roi_kw;
-  const int rows = off[nf - 1] + R[nf - 1];
+  const int rows = fl.rows();
   if (rows <= 0) return;
   // ---- cnet backward (objective.lua:179)
   const float* d_in = c->t_dhidden;
   for (int i = (int)c->fcs.size() - 1; i >= 0; --i) {
     FcLayer& f = c->fcs[i];
-    for (int fr = 0; fr < nf; ++fr) {
-      if (R[fr] <= 0) continue;
-      const size_t o = (size_t)off[fr] * f.nout;
-      FcTrainBwd fb;
-      fb.d_in = d_in + o; fb.pre = f.t_pre + o; fb.xhat = f.t_xhat ? f.t_xhat + o : nullptr; fb.rstd = f.t_rstd + (size_t)fr * f.nout;
-      fb.bn_w = P(c, f.p_bn_w); fb.prelu = P(c, f.p_prelu);
-      fb.mask = f.t_mask + o; fb.keep_scale = f.dropout > 0.f ? 1.f / (1.f - f.dropout) : 1.f;
-      fb.d_out_bf16 = f.t_dy + o;
-      fb.g_bias = G(c, f.p_b); fb.g_bn_w = G(c, f.p_bn_w); fb.g_bn_b = G(c, f.p_bn_b); fb.g_prelu = G(c, f.p_prelu);
-      fb.R = R[fr]; fb.n = f.nout;
-      launch_fc_train_bwd(fb, st);
-      ++c->launches;
-    }
+    FcTrainBwd fb;
+    fb.d_in = d_in; fb.pre = f.t_pre; fb.xhat = f.t_xhat; fb.rstd = f.t_rstd;
+    fb.bn_w = P(c, f.p_bn_w); fb.prelu = P(c, f.p_prelu);
+    fb.mask = f.t_mask; fb.keep_scale = f.dropout > 0.f ? 1.f / (1.f - f.dropout) : 1.f;
+    fb.d_out_bf16 = f.t_dy;
+    fb.g_bias = G(c, f.p_b); fb.g_bn_w = G(c, f.p_bn_w); fb.g_bn_b = G(c, f.p_bn_b); fb.g_prelu = G(c, f.p_prelu);
+    fb.n = f.nout;
+    launch_fc_train_bwd(fb, fl, st);
+    ++c->launches;
     const bf16* x_in = i == 0 ? c->t_rows : c->fcs[i - 1].t_out;
     // weight gradient over ALL rows: one fp32 TMA reduce-add GEMM into dw_taps, transposed into Torch's layout
     wgrad_rows(c, f.t_dy, x_in, rows, f.nin, f.nout, f.dw_taps, true);
@@ -1181,16 +1179,15 @@ static void cnet_train_backward(frcnn_ctx* c, int nf, const int* off, const int*
     d_in = d_prev;
   }
 }
-static void run_cnet_train_frames(frcnn_ctx* c, int nf, const int* off, const int* R, const int* n_pos, const float* const* cnet_masks,
-                                  const uint64_t* seeds) {
-  cnet_train_forward(c, nf, off, R, cnet_masks, seeds);
-  cnet_train_loss_bwd(c, nf, off, R, n_pos);
-  cnet_train_backward(c, nf, off, R);
+static void run_cnet_train_frames(frcnn_ctx* c, const FrameList& fl, const float* const* cnet_masks, const uint64_t* seeds) {
+  cnet_train_forward(c, fl, cnet_masks, seeds);
+  cnet_train_loss_bwd(c, fl);
+  cnet_train_backward(c, fl);
 }
 
 static void run_cnet_train(frcnn_ctx* c, int R, int n_pos, const float* const* cnet_masks, uint64_t seed) {
   const int off = 0;
-  run_cnet_train_frames(c, 1, &off, &R, &n_pos, cnet_masks, &seed);
+  run_cnet_train_frames(c, make_frames(1, &off, &R, &n_pos), cnet_masks, &seed);
 }
 
 // The per-image loop of lossAndGradient (objective.lua:65-198) for N frames of one size: pnet forward (training) and
@@ -1217,6 +1214,12 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
   ensure_pnet_workspace(c, N, H, W);
   ensure_train_workspace(c, N, H, W);
   ensure_objective_workspace(c, rows);
+  const FrameList fl = make_frames(N, off.data(), Rn.data(), n_pos);
+  FrameList per_frame;   // "one row per frame": the SpatialDropout masks
+  memset(&per_frame, 0, sizeof(per_frame));
+  per_frame.nf = N;
+  FrameSeeds fs;
+  for (int n = 0; n < N; ++n) { per_frame.off[n] = n; per_frame.R[n] = 1; fs.seed[n] = seeds[n]; }
   // ---- pnet forward, training mode (objective.lua:60,71)
   int mi = 0;
   for (auto& cv : c->trunk) {
@@ -1224,7 +1227,7 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
     if (pnet_masks && pnet_masks[mi]) {
       FRCNN_CUDA_TRY(cudaMemcpyAsync(cv.mask, pnet_masks[mi], (size_t)N * cv.cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
     } else {
-      for (int n = 0; n < N; ++n) launch_dropout_mask(cv.mask + (size_t)n * cv.cout, cv.cout, cv.dropout, seeds[n], (uint32_t)mi, st);
+      launch_dropout_mask_frames(cv.mask, per_frame, cv.cout, cv.dropout, fs, (uint32_t)mi, st);   // one draw per (frame, channel)
     }
     ++mi;
   }
@@ -1245,35 +1248,26 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
       if (n_neg[n]) memcpy(&ex[off[n] + n_pos[n]], neg[n], (size_t)n_neg[n] * sizeof(ExampleDev));
     }
     FRCNN_CUDA_TRY(cudaMemcpyAsync(c->ex_dev, ex.data(), (size_t)rows * sizeof(ExampleDev), cudaMemcpyHostToDevice, st));
-    for (int n = 0; n < N; ++n) {
-      if (Rn[n] <= 0) continue;
-      // ---- RPN criteria on the listed anchors (objective.lua:91-140)
-      RpnLossParams lp;
-      lp.ex = c->ex_dev + off[n]; lp.n_pos = n_pos[n]; lp.n_neg = n_neg[n];
-      for (int i = 0; i < MAX_HEADS; ++i) {
-        const size_t per = (size_t)18 * c->heads[i].hh * c->heads[i].hw;
-        lp.out[i] = c->heads[i].out + n * per; lp.d_out[i] = c->head_dout[i] + n * per; lp.hh[i] = c->heads[i].hh; lp.hw[i] = c->heads[i].hw;
-      }
-      lp.crtarget = c->crtarget + (size_t)off[n] * 4; lp.cctarget = c->cctarget + off[n]; lp.bg_class = c->class_count;
-      lp.rects = c->ex_rects + (size_t)off[n] * 4;
-      lp.losses = c->losses_dev + 8 * n; lp.status = c->t_status;
-      launch_rpn_loss(lp, st);
-      // ---- ROI pooling of ground-truth rects / negative anchors (objective.lua:117-119,137-139)
-      launch_roi_pool_train(c->pool_out.back() + n * fmap_elems, c->feat_h, c->feat_w, c->feat_c, c->roi_kh, c->roi_kw, c->roi_loc,
-                            c->ex_rects + (size_t)off[n] * 4, Rn[n], c->t_rows + (size_t)off[n] * feat, c->t_argmax + (size_t)off[n] * feat,
-                            c->t_status + 1, st);
-      c->launches += 2;
+    // ---- RPN criteria on the listed anchors (objective.lua:91-140), all frames in one launch
+    RpnLossParams lp;
+    lp.ex = c->ex_dev;
+    for (int i = 0; i < MAX_HEADS; ++i) {
+      lp.out[i] = c->heads[i].out; lp.d_out[i] = c->head_dout[i]; lp.hh[i] = c->heads[i].hh; lp.hw[i] = c->heads[i].hw;
     }
+    lp.crtarget = c->crtarget; lp.cctarget = c->cctarget; lp.bg_class = c->class_count;
+    lp.rects = c->ex_rects;
+    lp.losses = c->losses_dev; lp.status = c->t_status;
+    launch_rpn_loss(lp, fl, st);
+    // ---- ROI pooling of ground-truth rects / negative anchors (objective.lua:117-119,137-139)
+    launch_roi_pool_train(c->pool_out.back(), c->feat_h, c->feat_w, c->feat_c, c->roi_kh, c->roi_kw, c->roi_loc, c->ex_rects, fl,
+                          c->t_rows, c->t_argmax, c->t_status + 1, st);
+    c->launches += 2;
     c->losses_cur = c->losses_dev;
-    run_cnet_train_frames(c, N, off.data(), Rn.data(), n_pos, cnet_masks, seeds);
+    run_cnet_train_frames(c, fl, cnet_masks, seeds);
     dp_bucket_ready(c, 0);   // cnet's gradients are final: their all-reduce overlaps pnet:backward
     // ---- ROI-pool backward into delta_outputs[5] (objective.lua:182-185), kept as the fp32 NHWC block gradient
-    for (int n = 0; n < N; ++n) {
-      if (Rn[n] <= 0) continue;
-      launch_roi_pool_bwd(c->t_dx + (size_t)off[n] * feat, c->t_argmax + (size_t)off[n] * feat, Rn[n], bins, c->feat_c,
-                          c->dblock.back() + n * fmap_elems, st);
-      ++c->launches;
-    }
+    launch_roi_pool_bwd(c->t_dx, c->t_argmax, fl, bins, c->feat_c, c->dblock.back(), (long)fmap_elems, st);
+    ++c->launches;
   }
   c->losses_cur = c->losses_dev;
   // ---- pnet backward (objective.lua:189), all frames at once
@@ -2269,7 +2263,7 @@ int frcnn_cnet_forward_train(frcnn_ctx* c, const float* x_dev, int R, const floa
   frcnn::pack_roi_rows_kernel<<<blocks, 256, 0, c->stream>>>(x_dev, c->t_rows, R, c->feat_c, bins, 0);
   ++c->launches;
   const int off = 0;
-  frcnn::cnet_train_forward(c, 1, &off, &R, masks_dev, &seed);
+  frcnn::cnet_train_forward(c, frcnn::make_frames(1, &off, &R, nullptr), masks_dev, &seed);
   // the two output branches in fp32 on the stored hidden activations (model_utilities.lua:96-105)
   const frcnn::FcLayer& last = c->fcs.back();
   frcnn::launch_cnet_out(last.t_out32, frcnn::P(c, c->p_reg_w), frcnn::P(c, c->p_reg_b), frcnn::P(c, c->p_cls_w), frcnn::P(c, c->p_cls_b), reg_dev,
@@ -2286,8 +2280,9 @@ int frcnn_cnet_backward(frcnn_ctx* c, const float* d_reg_dev, const float* d_cls
   FRCNN_REQUIRE(c->cnet_train_rows > 0, FRCNN_E_STATE, "cnet:backward needs a preceding frcnn_cnet_forward_train on this context");
   FRCNN_REQUIRE(d_reg_dev && d_cls_dev, FRCNN_E_INVALID, "null gradient");
   const int R = c->cnet_train_rows, off = 0, n_pos = R;
-  frcnn::cnet_train_loss_bwd(c, 1, &off, &R, &n_pos, d_reg_dev, d_cls_dev);
-  frcnn::cnet_train_backward(c, 1, &off, &R);
+  const frcnn::FrameList fl = frcnn::make_frames(1, &off, &R, &n_pos);
+  frcnn::cnet_train_loss_bwd(c, fl, d_reg_dev, d_cls_dev);
+  frcnn::cnet_train_backward(c, fl);
   if (dx_dev) {
     const int bins = c->roi_kh * c->roi_kw;
     const long total = (long)R * bins * c->feat_c;

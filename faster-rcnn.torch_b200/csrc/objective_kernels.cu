@@ -21,13 +21,16 @@ __device__ __forceinline__ float smooth_l1_grad(float d) { return fminf(fmaxf(d,
 // 2 = negative), 10 * SmoothL1(sum) on the 4 regression outputs of the positives, deltas ADDED into delta_outputs
 // (an anchor may be listed twice), detection-stage targets: class index / background and
 // Anchors.inputToAnchor(Anchors.anchorToInput(anchor, reg_out), roi.rect) in double (Anchors.lua:237-252).
-__global__ void rpn_loss_kernel(RpnLossParams p) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  const int R = p.n_pos + p.n_neg;
+__global__ void rpn_loss_kernel(RpnLossParams p, FrameList fl) {
+  // blockIdx.y = frame: its examples, its slice of the anchor-network outputs, its loss slots
+  const int fr = blockIdx.y;
+  const int local = blockIdx.x * blockDim.x + threadIdx.x;
+  const int R = fl.R[fr];
+  const int e = fl.off[fr] + local;                // row of the batch
   float l_cls = 0.f, l_reg = 0.f;
-  if (e < R) {
+  if (local < R) {
     const ExampleDev& x = p.ex[e];
-    const bool pos = e < p.n_pos;
+    const bool pos = local < fl.n_pos[fr];
     const int l = x.layer - 1, a = x.aspect - 1, yy = x.y - 1, xx = x.x - 1;
     bool ok = l >= 0 && l < MAX_HEADS && a >= 0 && a < 3;
     if (ok) ok = yy >= 0 && yy < p.hh[l] && xx >= 0 && xx < p.hw[l];
@@ -39,7 +42,7 @@ __global__ void rpn_loss_kernel(RpnLossParams p) {
       atomicExch(p.status, 1);
     } else {
       const long plane = (long)p.hh[l] * p.hw[l];
-      const long base = (long)(a * 6) * plane + (long)yy * p.hw[l] + xx;
+      const long base = ((long)fr * 18 + a * 6) * plane + (long)yy * p.hw[l] + xx;
       const float* v = p.out[l] + base;
       float* d = p.d_out[l] + base;
       const float v1 = v[0], v2 = v[plane];
@@ -75,23 +78,24 @@ __global__ void rpn_loss_kernel(RpnLossParams p) {
   l_cls = wsum(l_cls);
   l_reg = wsum(l_reg);
   if ((threadIdx.x & 31) == 0) {
-    if (l_cls != 0.f) atomicAdd(p.losses + 0, l_cls);
-    if (l_reg != 0.f) atomicAdd(p.losses + 1, l_reg);
+    if (l_cls != 0.f) atomicAdd(p.losses + 8 * fr + 0, l_cls);
+    if (l_reg != 0.f) atomicAdd(p.losses + 8 * fr + 1, l_reg);
   }
 }
-void launch_rpn_loss(const RpnLossParams& p, cudaStream_t st) {
-  const int R = p.n_pos + p.n_neg;
-  if (R > 0) rpn_loss_kernel<<<cdiv(R, 128), 128, 0, st>>>(p);
+void launch_rpn_loss(const RpnLossParams& p, const FrameList& fl, cudaStream_t st) {
+  const int R = fl.max_R();
+  if (R > 0) rpn_loss_kernel<<<dim3(cdiv(R, 128), fl.nf), 128, 0, st>>>(p, fl);
 }
 
 // ------------------------------------------------------------------------------------------ training ROI pooling
 __global__ void __launch_bounds__(256) roi_pool_train_kernel(const bf16* __restrict__ fmap, int FH, int FW, int C, int kh, int kw,
-                                                             LocalizerDev loc, const double* __restrict__ rects, bf16* __restrict__ out,
-                                                             int* __restrict__ argmax, int* status) {
+                                                             LocalizerDev loc, const double* __restrict__ rects, FrameList fl,
+                                                             bf16* __restrict__ out, int* __restrict__ argmax, int* status) {
   // CTA <-> ROI (the double-precision crop of extract_roi_pooling_input is evaluated once per ROI); thread <-> (bin, 8
   // channels): 16-byte feature reads, 16-byte row writes.  output [row][bin][C]
   __shared__ int s_rect[5];
   const int r = blockIdx.x;
+  fmap += (long)frame_of_row(fl, r) * FH * FW * C;   // the feature map of the row's frame
   if (threadIdx.x == 0) {
     const double* q = rects + (long)r * 4;
     int y0, y1, x0, x1;
@@ -139,27 +143,47 @@ __global__ void __launch_bounds__(256) roi_pool_train_kernel(const bf16* __restr
   }
 }
 void launch_roi_pool_train(const bf16* fmap, int FH, int FW, int C, int kh, int kw, const LocalizerDev& loc, const double* rects_dev,
-                           int R, bf16* out, int* argmax, int* status, cudaStream_t st) {
+                           const FrameList& fl, bf16* out, int* argmax, int* status, cudaStream_t st) {
   FRCNN_REQUIRE(C % 8 == 0, FRCNN_E_INVALID, "training ROI pooling: channel count must be a multiple of 8");
-  if (R > 0) roi_pool_train_kernel<<<R, 256, 0, st>>>(fmap, FH, FW, C, kh, kw, loc, rects_dev, out, argmax, status);
+  const int R = fl.rows();
+  if (R > 0) roi_pool_train_kernel<<<R, 256, 0, st>>>(fmap, FH, FW, C, kh, kw, loc, rects_dev, fl, out, argmax, status);
 }
 
-__global__ void roi_pool_bwd_kernel(const float* __restrict__ d_rows, const int* __restrict__ argmax, long total, int C,
-                                    float* __restrict__ dfeat) {
+__global__ void roi_pool_bwd_kernel(const float* __restrict__ d_rows, const int* __restrict__ argmax, FrameList fl, int feat, int C,
+                                    float* __restrict__ dfeat, long fmap_elems) {
+  const int fr = blockIdx.y;
+  const long first = (long)fl.off[fr] * feat, total = (long)fl.R[fr] * feat;
+  d_rows += first;
+  argmax += first;
+  dfeat += fr * fmap_elems;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const float d = d_rows[i];
     if (d != 0.f) atomicAdd(dfeat + (long)argmax[i] * C + (int)(i % C), d);  // ROIs overlap: atomics
   }
 }
-void launch_roi_pool_bwd(const float* d_rows, const int* argmax, int R, int bins, int C, float* dfeat, cudaStream_t st) {
-  const long total = (long)R * bins * C;
-  if (total > 0) roi_pool_bwd_kernel<<<(int)std::min<long>(cdiv(total, 256), 148 * 16), 256, 0, st>>>(d_rows, argmax, total, C, dfeat);
+void launch_roi_pool_bwd(const float* d_rows, const int* argmax, const FrameList& fl, int bins, int C, float* dfeat, long fmap_elems,
+                         cudaStream_t st) {
+  const long total = (long)fl.max_R() * bins * C;   // (feat = bins * C is a multiple of C, so i % C is the channel in every frame)
+  if (total <= 0) return;
+  const int bx = (int)std::min<long>(cdiv(total, 256), std::max(148 * 16 / fl.nf, 148));
+  roi_pool_bwd_kernel<<<dim3(bx, fl.nf), 256, 0, st>>>(d_rows, argmax, fl, bins * C, C, dfeat, fmap_elems);
 }
 
 // ------------------------------------------------------------------------------------------ cnet chains
 // One CTA = 32 feature columns x all R rows (32 x 8 threads: threadIdx.x = column, threadIdx.y strides the rows).
-__global__ void __launch_bounds__(256) fc_train_fwd_kernel(FcTrainFwd p) {
+__global__ void __launch_bounds__(256) fc_train_fwd_kernel(FcTrainFwd p, FrameList fl) {
+  // blockIdx.y = frame: BatchNormalization sees the ROI batch of ONE image (objective.lua:164 inside the per-image loop)
   __shared__ float s_a[8][33], s_b[8][33];
+  const int fr = blockIdx.y, R = fl.R[fr];
+  if (R <= 0) return;
+  {
+    const long o = (long)fl.off[fr] * p.n;
+    p.acc += o; p.mask += o; p.pre += o;
+    if (p.xhat) p.xhat += o;
+    if (p.out_bf16) p.out_bf16 += o;
+    if (p.out_f32) p.out_f32 += o;
+    p.rstd += (long)fr * p.n;
+  }
   const int col = blockIdx.x * 32 + threadIdx.x;
   const bool live = col < p.n;
   const float bias = live ? p.bias[col] : 0.f;
@@ -169,7 +193,7 @@ __global__ void __launch_bounds__(256) fc_train_fwd_kernel(FcTrainFwd p) {
     // updated with momentum 0.1 (unbiased variance)
     float s = 0.f, ss = 0.f;
     if (live)
-      for (int r = threadIdx.y; r < p.R; r += 8) {
+      for (int r = threadIdx.y; r < R; r += 8) {
         const float x = p.acc[(long)r * p.n + col] + bias;
         s += x;
         ss += x * x;
@@ -179,23 +203,28 @@ __global__ void __launch_bounds__(256) fc_train_fwd_kernel(FcTrainFwd p) {
     __syncthreads();
     s = 0.f; ss = 0.f;
     for (int k = 0; k < 8; ++k) { s += s_a[k][threadIdx.x]; ss += s_b[k][threadIdx.x]; }
-    mean = s / p.R;
-    float var = ss / p.R - mean * mean;
+    mean = s / R;
+    float var = ss / R - mean * mean;
     var = fmaxf(var, 0.f);
     rstd = rsqrtf(var + 1e-5f);
     if (live && threadIdx.y == 0) {
       p.rstd[col] = rstd;
       if (p.bn_mean) {
-        const float unbiased = p.R > 1 ? var * p.R / (p.R - 1) : var;
-        p.bn_mean[col] = 0.9f * p.bn_mean[col] + 0.1f * mean;
-        p.bn_var[col] = 0.9f * p.bn_var[col] + 0.1f * unbiased;
+        const float unbiased = R > 1 ? var * R / (R - 1) : var;
+        if (fl.nf == 1) {
+          p.bn_mean[col] = 0.9f * p.bn_mean[col] + 0.1f * mean;
+          p.bn_var[col] = 0.9f * p.bn_var[col] + 0.1f * unbiased;
+        } else {   // the momentum recursion runs in frame order: bn_running_kernel, after this launch
+          p.stat[((long)fr * 2 + 0) * p.n + col] = mean;
+          p.stat[((long)fr * 2 + 1) * p.n + col] = unbiased;
+        }
       }
     }
   }
   if (!live) return;
   const float slope = p.prelu[0];
   const float g = p.bn_w ? p.bn_w[col] : 1.f, b = p.bn_w ? p.bn_b[col] : 0.f;
-  for (int r = threadIdx.y; r < p.R; r += 8) {
+  for (int r = threadIdx.y; r < R; r += 8) {
     const long i = (long)r * p.n + col;
     float x = p.acc[i] + bias;
     if (p.bn_w) {
@@ -210,19 +239,43 @@ __global__ void __launch_bounds__(256) fc_train_fwd_kernel(FcTrainFwd p) {
     if (p.out_f32) p.out_f32[i] = a;
   }
 }
-void launch_fc_train_fwd(const FcTrainFwd& p, cudaStream_t st) {
-  fc_train_fwd_kernel<<<cdiv(p.n, 32), dim3(32, 8), 0, st>>>(p);
+// running statistics of nn.BatchNormalization, momentum 0.1, one update per frame in frame order (what the per-image
+// loop of the reference does to them)
+__global__ void bn_running_kernel(const float* __restrict__ stat, float* __restrict__ bn_mean, float* __restrict__ bn_var, int n, FrameList fl) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= n) return;
+  float m = bn_mean[col], v = bn_var[col];
+  for (int fr = 0; fr < fl.nf; ++fr) {
+    if (fl.R[fr] <= 0) continue;
+    m = 0.9f * m + 0.1f * stat[((long)fr * 2 + 0) * n + col];
+    v = 0.9f * v + 0.1f * stat[((long)fr * 2 + 1) * n + col];
+  }
+  bn_mean[col] = m;
+  bn_var[col] = v;
+}
+void launch_fc_train_fwd(const FcTrainFwd& p, const FrameList& fl, cudaStream_t st) {
+  if (fl.max_R() <= 0) return;
+  fc_train_fwd_kernel<<<dim3(cdiv(p.n, 32), fl.nf), dim3(32, 8), 0, st>>>(p, fl);
+  if (p.bn_w && p.bn_mean && fl.nf > 1) bn_running_kernel<<<cdiv(p.n, 128), 128, 0, st>>>(p.stat, p.bn_mean, p.bn_var, p.n, fl);
 }
 
-__global__ void __launch_bounds__(256) fc_train_bwd_kernel(FcTrainBwd p) {
+__global__ void __launch_bounds__(256) fc_train_bwd_kernel(FcTrainBwd p, FrameList fl) {
   __shared__ float s_a[8][33], s_b[8][33], s_c[8][33];
+  const int fr = blockIdx.y, R = fl.R[fr];
+  if (R <= 0) return;
+  {
+    const long o = (long)fl.off[fr] * p.n;
+    p.d_in += o; p.pre += o; p.mask += o; p.d_out_bf16 += o;
+    if (p.xhat) p.xhat += o;
+    p.rstd += (long)fr * p.n;
+  }
   const int col = blockIdx.x * 32 + threadIdx.x;
   const bool live = col < p.n;
   const float slope = p.prelu[0];
   // pass 1: d wrt the PReLU input (= BN output), column sums for bias / BN parameter gradients, slope gradient
   float sum_d = 0.f, sum_dx = 0.f, ds = 0.f;
   if (live)
-    for (int r = threadIdx.y; r < p.R; r += 8) {
+    for (int r = threadIdx.y; r < R; r += 8) {
       const long i = (long)r * p.n + col;
       const float x = p.pre[i];
       const float da = p.d_in[i] * p.mask[i] * p.keep_scale;
@@ -255,12 +308,12 @@ __global__ void __launch_bounds__(256) fc_train_bwd_kernel(FcTrainBwd p) {
     }
   }
   float col_dx = 0.f;
-  for (int r = threadIdx.y; r < p.R; r += 8) {
+  for (int r = threadIdx.y; r < R; r += 8) {
     const long i = (long)r * p.n + col;
     const float x = p.pre[i];
     const float da = p.d_in[i] * p.mask[i] * p.keep_scale;
     float d = x > 0.f ? da : da * slope;
-    if (p.xhat) d = g * rstd * (d - sum_d / p.R - p.xhat[i] * sum_dx / p.R);   // BatchNorm backward, batch statistics
+    if (p.xhat) d = g * rstd * (d - sum_d / R - p.xhat[i] * sum_dx / R);   // BatchNorm backward, batch statistics
     col_dx += d;
     p.d_out_bf16[i] = __float2bfloat16_rn(d);
   }
@@ -270,15 +323,17 @@ __global__ void __launch_bounds__(256) fc_train_bwd_kernel(FcTrainBwd p) {
     atomicAdd(p.g_bias + col, col_dx);
   }
 }
-void launch_fc_train_bwd(const FcTrainBwd& p, cudaStream_t st) {
-  fc_train_bwd_kernel<<<cdiv(p.n, 32), dim3(32, 8), 0, st>>>(p);
+void launch_fc_train_bwd(const FcTrainBwd& p, const FrameList& fl, cudaStream_t st) {
+  if (fl.max_R() <= 0) return;
+  fc_train_bwd_kernel<<<dim3(cdiv(p.n, 32), fl.nf), dim3(32, 8), 0, st>>>(p, fl);
 }
 
 // objective.lua:166-177 + backward through Linear(nin -> 4) and Linear(nin -> ncls) + LogSoftMax.
 // kernel 1: one CTA per row: outputs, losses, dz, d_hidden.  kernel 2: one CTA per output neuron: weight gradients.
-__global__ void __launch_bounds__(256) cnet_loss_row_kernel(CnetLossParams p) {
+__global__ void __launch_bounds__(256) cnet_loss_row_kernel(CnetLossParams p, FrameList fl) {
   extern __shared__ float sh[];  // [nin] hidden, [ncls + 4] outputs -> dz
-  const int r = blockIdx.x;
+  const int r = blockIdx.x;      // row of the batch; the criteria average over the rows of its frame
+  const int fr = frame_of_row(fl, r), R = fl.R[fr];
   float* h = sh;
   float* z = sh + p.nin;
   for (int i = threadIdx.x; i < p.nin; i += blockDim.x) h[i] = p.hidden[(long)r * p.nin + i];
@@ -306,7 +361,7 @@ __global__ void __launch_bounds__(256) cnet_loss_row_kernel(CnetLossParams p) {
     for (int c = 0; c < p.ncls; ++c) dsum += p.ext_dcls[(long)r * p.ncls + c];
     for (int c = 0; c < p.ncls; ++c) z[4 + c] = p.ext_dcls[(long)r * p.ncls + c] - expf(z[4 + c] - lse) * dsum;
   } else if (threadIdx.x == 0) {
-    const bool pos = r < p.n_pos;
+    const bool pos = r - fl.off[fr] < fl.n_pos[fr];
     float l_reg = 0.f;
     for (int i = 0; i < 4; ++i) {
       const float out = pos ? z[i] : 0.f;                       // crout of the negatives is zeroed (objective.lua:170)
@@ -320,10 +375,11 @@ __global__ void __launch_bounds__(256) cnet_loss_row_kernel(CnetLossParams p) {
     for (int c = 0; c < p.ncls; ++c) s += expf(z[4 + c] - m);
     const float lse = m + logf(s);
     const int t = p.cctarget[r];
-    const float l_cls = (lse - z[4 + t]) / p.R;                  // ClassNLLCriterion, sizeAverage
-    for (int c = 0; c < p.ncls; ++c) z[4 + c] = (expf(z[4 + c] - lse) - (c == t ? 1.f : 0.f)) / p.R;
-    if (l_reg != 0.f) atomicAdd(p.losses + 2, l_reg);
-    atomicAdd(p.losses + 3, l_cls);
+    const float l_cls = (lse - z[4 + t]) / R;                    // ClassNLLCriterion, sizeAverage
+    for (int c = 0; c < p.ncls; ++c) z[4 + c] = (expf(z[4 + c] - lse) - (c == t ? 1.f : 0.f)) / R;
+    float* losses = p.losses + (long)p.loss_stride * fr;
+    if (l_reg != 0.f) atomicAdd(losses + 2, l_reg);
+    atomicAdd(losses + 3, l_cls);
   }
   __syncthreads();
   for (int o = threadIdx.x; o < no; o += blockDim.x) p.dz[(long)r * no + o] = z[o];
@@ -334,10 +390,13 @@ __global__ void __launch_bounds__(256) cnet_loss_row_kernel(CnetLossParams p) {
     p.d_hidden[(long)r * p.nin + k] = d;
   }
 }
-__global__ void __launch_bounds__(256) cnet_loss_wgrad_kernel(CnetLossParams p) {
-  // CTA <-> (output o, 64 weights of its row); thread <-> (weight, one of 4 interleaved row groups): the R-long sums
-  // are four independent chains per weight instead of one (the serial chain paced this kernel), combined in fixed order
+__global__ void __launch_bounds__(256) cnet_loss_wgrad_kernel(CnetLossParams p, int rows, int rows_per) {
+  // CTA <-> (output o, 64 weights of its row, a slice of the batch's rows: dz already carries every frame's 1 / R, so
+  // the sum runs over the rows of ALL frames); thread <-> (weight, one of 4 interleaved row groups): four independent
+  // chains per weight instead of one (the serial chain paced this kernel), combined in fixed order, one atomic per
+  // weight and slice
   const int o = blockIdx.x, kc = blockIdx.y, no = p.ncls + 4;
+  const int r0 = blockIdx.z * rows_per, r1 = min(rows, r0 + rows_per);
   const int kl = threadIdx.x & 63, rg = threadIdx.x >> 6;
   const int k = kc * 64 + kl;
   __shared__ float part[4][64];
@@ -345,29 +404,29 @@ __global__ void __launch_bounds__(256) cnet_loss_wgrad_kernel(CnetLossParams p) 
   float* gw = o < 4 ? p.g_w_reg + (long)o * p.nin : p.g_w_cls + (long)(o - 4) * p.nin;
   float s = 0.f;
   if (k < p.nin)
-    for (int r = rg; r < p.R; r += 4) s += p.dz[(long)r * no + o] * p.hidden[(long)r * p.nin + k];
+    for (int r = r0 + rg; r < r1; r += 4) s += p.dz[(long)r * no + o] * p.hidden[(long)r * p.nin + k];
   part[rg][kl] = s;
   if (kc == 0) {
     float b = 0.f;
-    for (int r = threadIdx.x; r < p.R; r += 256) b += p.dz[(long)r * no + o];
+    for (int r = r0 + threadIdx.x; r < r1; r += 256) b += p.dz[(long)r * no + o];
     bpart[threadIdx.x] = b;
   }
   __syncthreads();
-  if (rg == 0 && k < p.nin) gw[k] += (part[0][kl] + part[1][kl]) + (part[2][kl] + part[3][kl]);
+  if (rg == 0 && k < p.nin) atomicAdd(gw + k, (part[0][kl] + part[1][kl]) + (part[2][kl] + part[3][kl]));
   if (kc == 0) {
     for (int off = 128; off > 0; off >>= 1) {
       if ((int)threadIdx.x < off) bpart[threadIdx.x] += bpart[threadIdx.x + off];
       __syncthreads();
     }
-    if (threadIdx.x == 0) {
-      if (o < 4) p.g_b_reg[o] += bpart[0]; else p.g_b_cls[o - 4] += bpart[0];
-    }
+    if (threadIdx.x == 0) atomicAdd(o < 4 ? p.g_b_reg + o : p.g_b_cls + (o - 4), bpart[0]);
   }
 }
-void launch_cnet_loss_bwd(const CnetLossParams& p, cudaStream_t st) {
-  if (p.R <= 0) return;
-  cnet_loss_row_kernel<<<p.R, 256, (p.nin + p.ncls + 4) * sizeof(float), st>>>(p);
-  cnet_loss_wgrad_kernel<<<dim3(p.ncls + 4, (p.nin + 63) / 64), 256, 0, st>>>(p);
+void launch_cnet_loss_bwd(const CnetLossParams& p, const FrameList& fl, cudaStream_t st) {
+  const int rows = fl.rows();
+  if (rows <= 0) return;
+  cnet_loss_row_kernel<<<rows, 256, (p.nin + p.ncls + 4) * sizeof(float), st>>>(p, fl);
+  const int slices = std::min(16, cdiv(rows, 256));
+  cnet_loss_wgrad_kernel<<<dim3(p.ncls + 4, (p.nin + 63) / 64, slices), 256, 0, st>>>(p, rows, cdiv(rows, slices));
 }
 
 // ------------------------------------------------------------------------------------------ fc weight layouts

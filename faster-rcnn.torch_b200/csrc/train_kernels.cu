@@ -33,6 +33,23 @@ __global__ void dropout_mask_kernel(float* __restrict__ mask, int n, float p, ui
 void launch_dropout_mask(float* mask, int n, float p, uint64_t seed, uint32_t layer, cudaStream_t st) {
   dropout_mask_kernel<<<cdiv(n, 256), 256, 0, st>>>(mask, n, p, seed, layer);
 }
+// the same draws for every frame of a batch in one launch (blockIdx.y = frame, the index restarts at 0 in each frame)
+__global__ void dropout_mask_frames_kernel(float* __restrict__ mask, FrameList fl, int per_row, float p, FrameSeeds seeds, uint32_t layer) {
+  const int fr = blockIdx.y;
+  const long n = (long)fl.R[fr] * per_row;
+  float* m = mask + (long)fl.off[fr] * per_row;
+  const uint64_t seed = seeds.seed[fr];
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const float u = (mix32(seed * 0x9E3779B97F4A7C15ull + ((uint64_t)layer << 32) + (uint64_t)i) >> 8) * (1.0f / 16777216.0f);
+    m[i] = u >= p ? 1.0f : 0.0f;
+  }
+}
+void launch_dropout_mask_frames(float* mask, const FrameList& fl, int per_row, float p, const FrameSeeds& seeds, uint32_t layer,
+                                cudaStream_t st) {
+  const long n = (long)fl.max_R() * per_row;
+  if (n <= 0) return;
+  dropout_mask_frames_kernel<<<dim3((unsigned)std::min<long>(cdiv(n, 256), 4096), fl.nf), 256, 0, st>>>(mask, fl, per_row, p, seeds, layer);
+}
 
 // ------------------------------------------------------------------------------------------ pooled conv backward
 // Backward of [PReLU -> SpatialDropout mask -> MaxPool 2x2 ceil] given the gradient wrt the POOLED output: only the
