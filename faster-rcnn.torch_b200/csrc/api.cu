@@ -56,6 +56,8 @@ struct Head {
   ConvLaunch fused;          // throughput schedule: k x k conv + tail in one unsplit halo-kernel unit (EPI_HEAD)
   int hh = 0, hw = 0;
   bf16* dpre = nullptr;      // training: [N][hh][hw][n] gradient wrt the k x k conv's pre-activation output
+  bf16* w_rows = nullptr;    // sparse backward: [k * k * cin][n] filter as the operand of the listed-pixel GEMM
+  long rows_gen = -1;        // weights generation w_rows was packed from
 };
 
 struct FcLayer {
@@ -126,6 +128,13 @@ struct frcnn_ctx {
   long cw_gen = -1;                // pnet workspace generation they were sized against
   float* losses_cur = nullptr;     // the 8-float loss slot of the frame being processed
   std::vector<ExampleDev> ex_host; // host staging of a batch's example records
+  // sparse anchor-head backward of lossAndGradient: per head the unique pixels its listed anchors sit on
+  std::vector<int> hl_host;        // the lists back to back (staging, alive until the next call)
+  int* hl_dev = nullptr;           // [rows capacity]
+  int hl_off[MAX_HEADS] = {0}, hl_count[MAX_HEADS] = {0};
+  bf16* hs_d = nullptr;            // [rows][256] compact pre-activation gradients of one head
+  bf16* hs_x = nullptr;            // [rows][max k*k*cin] gathered input windows
+  float* hs_g = nullptr;           // [rows][max k*k*cin] listed-pixel data gradients before the scatter
   std::vector<void*> cw_allocs;
   ExampleDev* ex_dev = nullptr;
   double* ex_rects = nullptr;
@@ -943,7 +952,11 @@ static void zero_block_grads(frcnn_ctx* c) {
 }
 
 // keep_block_grads: the caller has already zeroed the per-block gradient maps and added the ROI-pool gradients
-static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out, bool keep_block_grads = false) {
+static void gemm_rows(frcnn_ctx* c, const bf16* a, const bf16* w, int R, int nin, int nout, float* out);
+static void wgrad_rows(frcnn_ctx* c, const bf16* dy, const bf16* x, int R, int nin, int nout, float* dw, bool zero);
+// sparse_heads: the caller (lossAndGradient) has listed, per head, the pixels delta_outputs can be non-zero at
+// (c->hl_dev / hl_off / hl_count): the head convolutions' backward runs on those pixels only
+static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out, bool keep_block_grads = false, bool sparse_heads = false) {
   FRCNN_REQUIRE(c->train_ready, FRCNN_E_STATE, "pnet:backward needs a preceding training-mode forward on this context");
   for (auto g : c->grads) FRCNN_REQUIRE(g != nullptr, FRCNN_E_STATE, "frcnn_bind_grads must be called before the backward pass");
   const int N = c->ws_n, nb = (int)c->blocks.size();
@@ -969,6 +982,29 @@ static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out, bool keep_
     hb.bias = P(c, hd.conv.p_b); hb.prelu = P(c, hd.conv.p_prelu); hb.w2 = P(c, hd.p_w2);
     hb.dpre = hd.dpre;
     hb.dw2 = G(c, hd.p_w2); hb.db2 = G(c, hd.p_b2); hb.db1 = G(c, hd.conv.p_b); hb.dslope = G(c, hd.conv.p_prelu);
+    if (sparse_heads) {
+      const int M = c->hl_count[i];
+      if (M == 0) continue;               // no listed anchor on this head: all its gradients are zero
+      ConvLayer& cv = hd.conv;
+      const int* list = c->hl_dev + c->hl_off[i];
+      const int kkc = cv.k * cv.k * cv.cin;
+      hb.list = list; hb.M = M; hb.dpre = c->hs_d;
+      launch_head_tail_bwd(hb, c->sm_count, st);
+      // weight gradient: dW[co][tap][ci] = dpre[M][co]^T x windows[M][tap][ci]
+      launch_head_gather_rows(c->pool_out[hd.input - 1], list, M, hd.hh, hd.hw, cv.hin, cv.win, cv.cin, cv.k, c->hs_x, st);
+      wgrad_rows(c, c->hs_d, c->hs_x, M, kkc, cv.cout, cv.dw_taps, true);
+      launch_wgrad_finish(cv.dw_taps, G(c, cv.p_w), cv.cout, cv.cin, cv.k, cv.k, st);
+      // data gradient: G[M][tap][ci] = dpre[M][co] x W, scattered onto the windows
+      if (hd.rows_gen != c->weights_gen) {
+        launch_pack_head_weight_rows(P(c, cv.p_w), hd.w_rows, cv.cout, cv.cin, cv.k, st);
+        hd.rows_gen = c->weights_gen;
+        ++c->launches;
+      }
+      gemm_rows(c, c->hs_d, hd.w_rows, M, cv.cout, kkc, c->hs_g);
+      launch_head_scatter_rows(c->hs_g, list, M, hd.hh, hd.hw, cv.hin, cv.win, cv.cin, cv.k, c->dblock[hd.input - 1], st);
+      c->launches += 4;
+      continue;
+    }
     launch_head_tail_bwd(hb, c->sm_count, st);
     ++c->launches;
     run_wgrad(c, hd.conv);
@@ -996,10 +1032,8 @@ static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out, bool keep_
         // gradient wrt the previous conv's output (bf16, gscratch[1]) -> its pre-activation gradient, which becomes
         // the next iteration's dy in gscratch[0]
         ConvLayer& prev = c->trunk[li - 1];
-        launch_prelu_bwd(c->gscratch[1], prev.out, P(c, prev.p_prelu), prev.dropout > 0.f ? prev.mask : nullptr, G(c, prev.p_b),
-                         G(c, prev.p_prelu), N, prev.hout, prev.wout, prev.cout, c->sm_count, st);
-        FRCNN_CUDA_TRY(cudaMemcpyAsync(c->gscratch[0], c->gscratch[1], (size_t)N * prev.hout * prev.wout * prev.cout * sizeof(bf16),
-                                       cudaMemcpyDeviceToDevice, st));
+        launch_prelu_bwd(c->gscratch[1], c->gscratch[0], prev.out, P(c, prev.p_prelu), prev.dropout > 0.f ? prev.mask : nullptr,
+                         G(c, prev.p_b), G(c, prev.p_prelu), N, prev.hout, prev.wout, prev.cout, c->sm_count, st);
         ++c->launches;
       }
     }
@@ -1051,6 +1085,17 @@ static void ensure_objective_workspace(frcnn_ctx* c, int rows) {
   }
   c->head_dout.clear();
   for (auto& hd : c->heads) c->head_dout.push_back((float*)dev_alloc(A, (size_t)NF * 18 * hd.hh * hd.hw * sizeof(float)));
+  size_t max_kkc = 0;
+  for (auto& hd : c->heads) {
+    const size_t kkc = (size_t)hd.conv.k * hd.conv.k * hd.conv.cin;
+    max_kkc = std::max(max_kkc, kkc);
+    hd.w_rows = (bf16*)dev_alloc(A, kkc * hd.n * sizeof(bf16));
+    hd.rows_gen = -1;
+  }
+  c->hl_dev = (int*)dev_alloc(A, (size_t)R * sizeof(int));
+  c->hs_d = (bf16*)dev_alloc(A, (size_t)R * 256 * sizeof(bf16));
+  c->hs_x = (bf16*)dev_alloc(A, (size_t)R * max_kkc * sizeof(bf16));
+  c->hs_g = (float*)dev_alloc(A, (size_t)R * max_kkc * sizeof(float));
   c->cw_rows = R;
   c->cw_n = NF;
   c->cw_gen = c->ws_gen;
@@ -1074,7 +1119,7 @@ static void gemm_rows(frcnn_ctx* c, const bf16* a, const bf16* w, int R, int nin
   ++c->launches;
 }
 // dW[nout][nin] (fp32 taps buffer, zeroed here) = dy[R][nout]^T x[R][nin]
-static void wgrad_rows(frcnn_ctx* c, const bf16* dy, const bf16* x, int R, int nin, int nout, float* dw, bool zero = true) {
+static void wgrad_rows(frcnn_ctx* c, const bf16* dy, const bf16* x, int R, int nin, int nout, float* dw, bool zero) {
   if (zero) FRCNN_CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)nin * nout * sizeof(float), c->stream));
   ConvLaunch L;
   conv_wgrad_prepare(&L, dy, x, dw, 1, 1, R, nin, nout, 1, 1, 0, 0, c->sm_count);
@@ -1215,6 +1260,10 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
   ensure_train_workspace(c, N, H, W);
   ensure_objective_workspace(c, rows);
   const FrameList fl = make_frames(N, off.data(), Rn.data(), n_pos);
+  // FRCNN_HEAD_SPARSE=0: dense anchor-head backward (the path pnet:backward with caller-supplied deltas always takes)
+  const char* hs_env = getenv("FRCNN_HEAD_SPARSE");
+  const bool sparse_heads = !(hs_env && atoi(hs_env) == 0);
+  for (int l = 0; l < MAX_HEADS; ++l) c->hl_count[l] = 0;
   FrameList per_frame;   // "one row per frame": the SpatialDropout masks
   memset(&per_frame, 0, sizeof(per_frame));
   per_frame.nf = N;
@@ -1248,6 +1297,33 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
       if (n_neg[n]) memcpy(&ex[off[n] + n_pos[n]], neg[n], (size_t)n_neg[n] * sizeof(ExampleDev));
     }
     FRCNN_CUDA_TRY(cudaMemcpyAsync(c->ex_dev, ex.data(), (size_t)rows * sizeof(ExampleDev), cudaMemcpyHostToDevice, st));
+    if (sparse_heads) {
+      // the pixels of every head that carry a listed anchor (several aspects / examples may share one): the only places
+      // delta_outputs is written (objective.lua:102-103,131); records that index outside their map are skipped here and
+      // reported by rpn_loss_kernel's status flag
+      std::vector<int> per_head[MAX_HEADS];
+      const int nh = (int)c->heads.size();
+      for (int n = 0; n < N; ++n)
+        for (int e = off[n]; e < off[n] + Rn[n]; ++e) {
+          const ExampleDev& x = ex[e];
+          const int l = x.layer - 1, a = x.aspect - 1, yy = x.y - 1, xx = x.x - 1;
+          if (l < 0 || l >= nh || a < 0 || a >= 3) continue;
+          const Head& hd = c->heads[l];
+          if (yy < 0 || yy >= hd.hh || xx < 0 || xx >= hd.hw) continue;
+          per_head[l].push_back((n * hd.hh + yy) * hd.hw + xx);
+        }
+      c->hl_host.clear();
+      for (int l = 0; l < MAX_HEADS; ++l) {
+        auto& v = per_head[l];
+        std::sort(v.begin(), v.end());
+        v.erase(std::unique(v.begin(), v.end()), v.end());
+        c->hl_off[l] = (int)c->hl_host.size();
+        c->hl_count[l] = (int)v.size();
+        c->hl_host.insert(c->hl_host.end(), v.begin(), v.end());
+      }
+      if (!c->hl_host.empty())
+        FRCNN_CUDA_TRY(cudaMemcpyAsync(c->hl_dev, c->hl_host.data(), c->hl_host.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
     // ---- RPN criteria on the listed anchors (objective.lua:91-140), all frames in one launch
     RpnLossParams lp;
     lp.ex = c->ex_dev;
@@ -1273,7 +1349,7 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
   // ---- pnet backward (objective.lua:189), all frames at once
   std::vector<const float*> d_out(c->heads.size() + 1, nullptr);
   for (size_t i = 0; i < c->heads.size(); ++i) d_out[i] = c->head_dout[i];
-  do_pnet_backward(c, d_out.data(), true);
+  do_pnet_backward(c, d_out.data(), true, sparse_heads);
   std::vector<float> lh((size_t)N * 8);
   int sh[4];
   FRCNN_CUDA_TRY(cudaMemcpyAsync(lh.data(), c->losses_dev, (size_t)N * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -459,11 +459,13 @@ __global__ void __launch_bounds__(256) wgrad_finish_fc_kernel(const float* __res
       continue;
     }
     __syncthreads();
-    for (long k = threadIdx.x; k < K; k += blockDim.x) srow[k] = dw[o * K + k];
+    // one pad word per C-long bin row: consecutive threads read consecutive bins of one channel, C (a multiple of 32)
+    // words apart -- the same bank without the pad
+    for (long k = threadIdx.x; k < K; k += blockDim.x) srow[k + k / C] = dw[o * K + k];
     __syncthreads();
     for (long d = threadIdx.x; d < K; d += blockDim.x) {
       const int c = (int)(d / bins), b = (int)(d - (long)c * bins);
-      grad[o * K + d] += srow[(long)b * C + c];
+      grad[o * K + d] += srow[(long)b * (C + 1) + c];
     }
   }
 }
@@ -472,7 +474,7 @@ void launch_wgrad_finish_fc(const float* dw, float* grad, int nout, int C, int b
   if (first_use_on_device(configured)) {
     cudaFuncSetAttribute(wgrad_finish_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
   }
-  const size_t smem = permute ? (size_t)C * bins * sizeof(float) : 0;
+  const size_t smem = permute ? (size_t)(C + 1) * bins * sizeof(float) : 0;
   FRCNN_REQUIRE(smem <= 96 * 1024, FRCNN_E_INVALID, "fc row too long for the transposing gradient accumulation");
   wgrad_finish_fc_kernel<<<std::min(nout, 148 * 4), 256, smem, st>>>(dw, grad, nout, C, bins, permute);
 }

@@ -30,7 +30,7 @@ void launch_dropout_mask_frames(float* mask, const FrameList& fl, int per_row, f
                                 cudaStream_t st);
 void launch_unpool_prelu_bwd(const float* g, const uint8_t* arg, const bf16* yp, const float* slope, const float* mask, bf16* dpre,
                              float* dbias, float* dslope, int N, int H, int W, int C, int num_sms, cudaStream_t st);
-void launch_prelu_bwd(bf16* d, const bf16* y, const float* slope, const float* mask, float* dbias, float* dslope, int N, int H, int W,
+void launch_prelu_bwd(const bf16* d, bf16* out, const bf16* y, const float* slope, const float* mask, float* dbias, float* dslope, int N, int H, int W,
                       int C, int num_sms, cudaStream_t st);
 
 struct HeadTailBwd {
@@ -42,8 +42,21 @@ struct HeadTailBwd {
   const float *bias, *prelu, *w2;
   bf16* dpre;           // [npix][256] gradient wrt the k x k conv's pre-activation output
   float *dw2, *db2, *db1, *dslope;
+  const int* list = nullptr;   // sparse form: the M pixels (flat n * HW + y * hw + x, unique) that can carry gradient;
+  int M = 0;                   // dpre is then the COMPACT [M][256] matrix, row r = pixel list[r]
 };
 void launch_head_tail_bwd(const HeadTailBwd& H, int num_sms, cudaStream_t st);
+// Sparse anchor-head backward (lossAndGradient lists <= 256 anchors per frame, objective.lua:91-140, so delta_outputs is
+// zero at all but M pixels of a head): the k x k conv's data and weight gradients become two small GEMMs over the M
+// listed pixels instead of two dense convolutions over the map.
+//   rows   [M][k*k*Cin] bf16 = the input windows of the listed pixels (im2col rows, tap-major then channel)
+//   w_rows [k*k*Cin][Cout] bf16 = the filter as the GEMM operand of  G[M][k*k*Cin] = dpre[M][Cout] x W
+//   scatter: dx[n][y + ty][x + tx][ci] += G[r][(ty * k + tx) * Cin + ci]
+void launch_pack_head_weight_rows(const float* w, bf16* out, int Cout, int Cin, int K, cudaStream_t st);
+void launch_head_gather_rows(const bf16* x, const int* list, int M, int hh, int hw, int Hin, int Win, int Cin, int K, bf16* rows,
+                             cudaStream_t st);
+void launch_head_scatter_rows(const float* g, const int* list, int M, int hh, int hw, int Hin, int Win, int Cin, int K, float* dx,
+                              cudaStream_t st);
 void launch_first_wgrad(const bf16* dpre, const float* img, float* dw, int N, int H, int W, int pad, int num_sms, cudaStream_t st);
 void launch_add_chw_to_nhwc(const float* src, float* dst, int N, int H, int W, int C, cudaStream_t st);
 void launch_check_slopes(const float* const* slopes_dev, int n, int* flag, cudaStream_t st);

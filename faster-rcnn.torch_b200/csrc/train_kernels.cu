@@ -147,9 +147,10 @@ void launch_unpool_prelu_bwd(const float* g, const uint8_t* arg, const bf16* yp,
 }
 
 // ------------------------------------------------------------------------------------------ plain conv backward
-// Backward of [PReLU -> mask] for a conv that is not followed by the pool: dpre = dy * mask * (y < 0 ? slope : 1), in
-// place on the bf16 gradient tensor produced by the next conv's dgrad.  thread <-> (pixel, 8 channels).
-__global__ void __launch_bounds__(256) prelu_bwd_kernel(bf16* __restrict__ d, const bf16* __restrict__ y, const float* __restrict__ slope_p,
+// Backward of [PReLU -> mask] for a conv that is not followed by the pool: dpre = dy * mask * (y < 0 ? slope : 1), from
+// the bf16 gradient tensor produced by the next conv's dgrad (d) into the tensor the previous conv's backward reads
+// (out; may alias d).  thread <-> (pixel, 8 channels).
+__global__ void __launch_bounds__(256) prelu_bwd_kernel(const bf16* d, bf16* out, const bf16* __restrict__ y, const float* __restrict__ slope_p,
                                                         const float* __restrict__ mask, float* __restrict__ dbias,
                                                         float* __restrict__ dslope, long npix_per_img, int N, int C) {
   extern __shared__ float sb[];
@@ -167,7 +168,7 @@ __global__ void __launch_bounds__(256) prelu_bwd_kernel(bf16* __restrict__ d, co
     const int c8 = c8_fixed;
     const long pix = i / cv;
     const int n = (int)(pix / npix_per_img);
-    uint4 d8 = reinterpret_cast<uint4*>(d)[i];
+    uint4 d8 = reinterpret_cast<const uint4*>(d)[i];
     const uint4 y8 = reinterpret_cast<const uint4*>(y)[i];
     bf16* de = reinterpret_cast<bf16*>(&d8);
     const bf16* ye = reinterpret_cast<const bf16*>(&y8);
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(256) prelu_bwd_kernel(bf16* __restrict__ d, co
       bacc[e] += v;
       de[e] = __float2bfloat16_rn(v);
     }
-    reinterpret_cast<uint4*>(d)[i] = d8;
+    reinterpret_cast<uint4*>(out)[i] = d8;
   }
 #pragma unroll
   for (int e = 0; e < 8; ++e)
@@ -198,11 +199,11 @@ __global__ void __launch_bounds__(256) prelu_bwd_kernel(bf16* __restrict__ d, co
     if (t != 0.f) atomicAdd(dslope, t);
   }
 }
-void launch_prelu_bwd(bf16* d, const bf16* y, const float* slope, const float* mask, float* dbias, float* dslope, int N, int H, int W,
+void launch_prelu_bwd(const bf16* d, bf16* out, const bf16* y, const float* slope, const float* mask, float* dbias, float* dslope, int N, int H, int W,
                       int C, int num_sms, cudaStream_t st) {
   const long total = (long)N * H * W * (C / 8);
   const int blocks = channel_stable_grid(total, C / 8, num_sms);
-  prelu_bwd_kernel<<<blocks, 256, C * sizeof(float), st>>>(d, y, slope, mask, dbias, dslope, (long)H * W, N, C);
+  prelu_bwd_kernel<<<blocks, 256, C * sizeof(float), st>>>(d, out, y, slope, mask, dbias, dslope, (long)H * W, N, C);
 }
 
 // ------------------------------------------------------------------------------------------ anchor-head tail backward
@@ -263,10 +264,127 @@ __global__ void __launch_bounds__(256) head_tail_bwd_kernel(HeadTailBwd H) {
     if (lane == 0 && ds != 0.f) atomicAdd(H.dslope, ds);
   }
 }
+// The same backward on a pixel list (sparse form).  Every listed pixel carries gradient, so the per-element atomics of
+// the kernel above (18 x 256 addresses hit by every pixel) would serialise in L2: here thread <-> channel keeps its
+// column of dw2, its bias and slope partials in registers over the CTA's pixels and issues one atomic per address at
+// the end.  Per pixel the arithmetic (and its order) is the dense kernel's: adding the zero terms it skips changes nothing.
+__global__ void __launch_bounds__(256) head_tail_bwd_list_kernel(HeadTailBwd H) {
+  constexpr int CO = 18, CM = 256;
+  __shared__ float s_dout[CO];
+  __shared__ float s_red[CM / 32];
+  const int c = threadIdx.x;
+  float w2c[CO], acc[CO];
+#pragma unroll
+  for (int o = 0; o < CO; ++o) { w2c[o] = H.w2[o * CM + c]; acc[o] = 0.f; }
+  const float bias = H.bias[c], slope = H.prelu[0];
+  float db1 = 0.f, db2 = 0.f, ds = 0.f;
+  for (int it = blockIdx.x; it < H.M; it += gridDim.x) {
+    const long pix = H.list[it];
+    const long n = pix / H.HW, hw = pix - n * H.HW;
+    __syncthreads();   // the previous pixel's readers of s_dout are done
+    if (c < CO) {
+      const float dv = H.d_out[(n * CO + c) * H.HW + hw];
+      s_dout[c] = dv;
+      db2 += dv;
+    }
+    __syncthreads();
+    float h = bias;
+    for (int s = 0; s < H.splits; ++s) h += H.ws[(size_t)s * H.slice_stride + pix * CM + c];
+    const float a = h > 0.f ? h : h * slope;
+    float dA = 0.f;
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+      const float d = s_dout[o];
+      dA += d * w2c[o];
+      acc[o] += d * a;
+    }
+    const float dp = h > 0.f ? dA : dA * slope;
+    if (!(h > 0.f)) ds += dA * h;
+    db1 += dp;
+    H.dpre[(long)it * CM + c] = __float2bfloat16_rn(dp);
+  }
+#pragma unroll
+  for (int o = 0; o < CO; ++o)
+    if (acc[o] != 0.f) atomicAdd(H.dw2 + o * CM + c, acc[o]);
+  if (db1 != 0.f) atomicAdd(H.db1 + c, db1);
+  if (c < CO && db2 != 0.f) atomicAdd(H.db2 + c, db2);
+  ds = warp_sum(ds);
+  if ((c & 31) == 0) s_red[c >> 5] = ds;
+  __syncthreads();
+  if (c == 0) {
+    float t = 0.f;
+    for (int i = 0; i < CM / 32; ++i) t += s_red[i];
+    if (t != 0.f) atomicAdd(H.dslope, t);
+  }
+}
 void launch_head_tail_bwd(const HeadTailBwd& H, int num_sms, cudaStream_t st) {
+  if (H.list) {
+    if (H.M > 0) head_tail_bwd_list_kernel<<<std::min(H.M, 4 * num_sms), 256, 0, st>>>(H);
+    return;
+  }
   const int smem = 19 * 256 * sizeof(float);
+  if (H.npix <= 0) return;
   const int blocks = (int)std::min<long>(cdiv(H.npix, 8), (long)num_sms * 4);
   head_tail_bwd_kernel<<<blocks, 256, smem, st>>>(H);
+}
+
+// ------------------------------------------------------------------------------------------ sparse anchor-head backward
+__global__ void pack_head_weight_rows_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int taps) {
+  const long total = (long)Cout * Cin * taps;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % Cout);
+    const long r = i / Cout;
+    const int ci = (int)(r % Cin), t = (int)(r / Cin);
+    out[i] = __float2bfloat16_rn(w[((long)co * Cin + ci) * taps + t]);   // Torch layout [co][ci][kh][kw]
+  }
+}
+void launch_pack_head_weight_rows(const float* w, bf16* out, int Cout, int Cin, int K, cudaStream_t st) {
+  const long total = (long)Cout * Cin * K * K;
+  pack_head_weight_rows_kernel<<<(int)std::min<long>(cdiv(total, 256), 148 * 8), 256, 0, st>>>(w, out, Cout, Cin, K * K);
+}
+// item <-> (listed pixel, filter tap, 8 channels): one 16-byte copy
+__global__ void head_gather_rows_kernel(const bf16* __restrict__ x, const int* __restrict__ list, int M, int hh, int hw, int Hin, int Win,
+                                        int Cin, int K, bf16* __restrict__ rows) {
+  const int cv = Cin >> 3, taps = K * K;
+  const long total = (long)M * taps * cv;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const long q = i / cv;
+    const int t = (int)(q % taps), r = (int)(q / taps);
+    const int pix = list[r];
+    const int n = pix / (hh * hw), rem = pix - n * hh * hw;
+    const int y = rem / hw + t / K, xx = rem % hw + t % K;
+    const uint4 v = *reinterpret_cast<const uint4*>(x + (((long)n * Hin + y) * Win + xx) * Cin + c8 * 8);
+    *reinterpret_cast<uint4*>(rows + ((long)r * taps + t) * Cin + c8 * 8) = v;
+  }
+}
+void launch_head_gather_rows(const bf16* x, const int* list, int M, int hh, int hw, int Hin, int Win, int Cin, int K, bf16* rows,
+                             cudaStream_t st) {
+  const long total = (long)M * K * K * (Cin / 8);
+  if (total <= 0) return;
+  head_gather_rows_kernel<<<(int)std::min<long>(cdiv(total, 256), 148 * 16), 256, 0, st>>>(x, list, M, hh, hw, Hin, Win, Cin, K, rows);
+}
+// item <-> (listed pixel, filter tap, 4 channels): one 16-byte vector reduction (windows of listed pixels overlap)
+__global__ void head_scatter_rows_kernel(const float* __restrict__ g, const int* __restrict__ list, int M, int hh, int hw, int Hin,
+                                         int Win, int Cin, int K, float* __restrict__ dx) {
+  const int cv = Cin >> 2, taps = K * K;
+  const long total = (long)M * taps * cv;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % cv);
+    const long q = i / cv;
+    const int t = (int)(q % taps), r = (int)(q / taps);
+    const int pix = list[r];
+    const int n = pix / (hh * hw), rem = pix - n * hh * hw;
+    const int y = rem / hw + t / K, xx = rem % hw + t % K;
+    const float4 v = *reinterpret_cast<const float4*>(g + ((long)r * taps + t) * Cin + c4 * 4);
+    atomicAdd(reinterpret_cast<float4*>(dx + (((long)n * Hin + y) * Win + xx) * Cin + c4 * 4), v);
+  }
+}
+void launch_head_scatter_rows(const float* g, const int* list, int M, int hh, int hw, int Hin, int Win, int Cin, int K, float* dx,
+                              cudaStream_t st) {
+  const long total = (long)M * K * K * (Cin / 4);
+  if (total <= 0) return;
+  head_scatter_rows_kernel<<<(int)std::min<long>(cdiv(total, 256), 148 * 16), 256, 0, st>>>(g, list, M, hh, hw, Hin, Win, Cin, K, dx);
 }
 
 // ------------------------------------------------------------------------------------------ first-layer wgrad

@@ -431,3 +431,63 @@ def test_train_batch_equals_frame_by_frame(F, small_model, h, w, counts):
         m.zero_grad()
         m.pnet.evaluate()
         m.cnet.evaluate()
+
+
+@pytest.mark.parametrize("h,w,counts", [(122, 192, [(10, 14), (0, 0), (3, 30)]), (450, 800, [(128, 128)] * 2)])
+def test_sparse_head_backward_equals_dense(F, small_model, h, w, counts, monkeypatch):
+    """lossAndGradient runs the anchor heads' backward on the listed pixels only (two small GEMMs + gather / scatter);
+    FRCNN_HEAD_SPARSE=0 takes the dense convolutions pnet:backward uses for arbitrary deltas.  Same products, different
+    fp32 summation order: the anchor-head filters' gradients agree to 1e-5 relative L2 (measured 5e-8), the losses are
+    identical; everything downstream of the block gradients passes through bf16 gradient maps and atomic reductions
+    whose order varies from run to run (dense against dense: 4e-3 on the whole gradient, tools/sparse_check.py), so the
+    trunk filters and the whole gradient get the batch test's 2e-2.  An anchor listed twice exercises the
+    de-duplication of the pixel list."""
+    from oracle import anchors as OA, objective as OO
+    m = small_model
+    cfg = OM.CFG_DUPLO
+    dims = m.output_dims(h, w)
+    oa = OA.Anchors(OM.VGG_SMALL["layers"], OM.VGG_SMALL["anchor_nets"], cfg["scales"])
+    frames, P, Q = [], [], []
+    for s, (np_, nn_) in enumerate(counts):
+        pos, neg, _ = OO.synthetic_examples(oa, dims, w, h, max(np_, 1), max(nn_, 1), 3, cfg["class_count"], seed=70 + s)
+        pos, neg = OO.clean_anchors(pos, dims), OO.clean_anchors(neg, dims)
+        pos, neg = pos[:np_], neg[:nn_]
+        if len(pos) > 2:
+            pos = pos + pos[:2]            # the same anchor listed twice: its deltas add up, its pixel is listed once
+        frames.append(OM.synthetic_frame(h, w, seed=80 + s).cuda())
+        P.append(pos)
+        Q.append(neg)
+    seeds = list(range(3, 3 + len(counts)))
+    saved = m.weights.clone()
+    try:
+        m.pnet.training(); m.cnet.training()
+        out = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("FRCNN_HEAD_SPARSE", mode)
+            m.weights.copy_(saved)
+            m.pack_weights()
+            m.zero_grad()
+            losses = m.train_batch(frames, P, Q, seeds=seeds)
+            out[mode] = (m.gradient.clone(), losses)
+        gs, gd = out["1"][0], out["0"][0]
+        assert ((gs - gd).norm() / gd.norm()).item() < 2e-2
+        for a, b in zip(out["1"][1], out["0"][1]):
+            for k in a:
+                assert a[k] == pytest.approx(b[k], rel=1e-5, abs=1e-6)
+        # the anchor-head filters and the trunk filters their data gradient flows into, each on its own
+        off = 0
+        for name, numel in zip(m.param_names, m.param_numel):
+            a, b = gs[off:off + numel], gd[off:off + numel]
+            off += numel
+            if name.endswith("_conv.weight") or name in ("b1_c1.weight", "b2_c2.weight", "b3_c2.weight", "b4_c2.weight"):
+                if b.norm().item() == 0.0:
+                    assert a.norm().item() == 0.0, name      # a head without listed anchors
+                else:
+                    bar = 1e-5 if name.endswith("_conv.weight") else 2e-2
+                    assert ((a - b).norm() / b.norm()).item() < bar, name
+    finally:
+        m.weights.copy_(saved)
+        m.pack_weights()
+        m.zero_grad()
+        m.pnet.evaluate()
+        m.cnet.evaluate()
