@@ -133,7 +133,9 @@ struct frcnn_ctx {
   int* hl_dev = nullptr;           // [rows capacity]
   int hl_off[MAX_HEADS] = {0}, hl_count[MAX_HEADS] = {0};
   bf16* hs_d = nullptr;            // [rows][256] compact pre-activation gradients of one head
-  bf16* hs_x = nullptr;            // [rows][max k*k*cin] gathered input windows
+  bf16* hs_x = nullptr;            // [rows][max k*k*cin] gathered input windows, the heads' row blocks back to back
+  float* hs_h = nullptr;           // [rows][256] conv outputs of the listed pixels (forward), heads back to back
+  bool hs_forward = false;         // this step's anchor-network forward ran on the listed pixels (hs_x / hs_h are valid)
   float* hs_g = nullptr;           // [rows][max k*k*cin] listed-pixel data gradients before the scatter
   std::vector<void*> cw_allocs;
   ExampleDev* ex_dev = nullptr;
@@ -719,7 +721,8 @@ static void run_conv(frcnn_ctx* c, ConvLayer& cv) {
 static void ensure_train_workspace(frcnn_ctx* c, int N, int H, int W);
 static int detect_stop_after();
 
-static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, int W, bool train = false) {
+// skip_heads: lossAndGradient evaluates the anchor networks on the listed pixels only (sparse_head_forward)
+static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, int W, bool train = false, bool skip_heads = false) {
   FRCNN_REQUIRE(c->packed, FRCNN_E_STATE, "frcnn_pack_weights must be called before the forward pass");
   FRCNN_REQUIRE(N >= 1 && H >= 16 && W >= 16, FRCNN_E_INVALID, "bad input size");
   ensure_pnet_workspace(c, N, H, W);
@@ -750,6 +753,10 @@ static void do_pnet_forward(frcnn_ctx* c, const float* img_dev, int N, int H, in
   // the other frames.  Latency schedule: one grouped split-K conv launch (every SM busy on this frame), heaviest
   // units first, then one grouped tail launch.
   if (detect_stop_after() == 1 && !train) return;
+  if (skip_heads) {
+    FRCNN_CUDA_TRY(cudaGetLastError());
+    return;
+  }
   static const int old_heads = getenv("FRCNN_HEADS_OLD") ? atoi(getenv("FRCNN_HEADS_OLD")) : 0;   // A/B measurements only
   if (!train && !old_heads) {
     // evaluate mode, both schedules: conv_head_kernel (linear tiles, reduction split by filter rows with in-kernel fix-up)
@@ -953,6 +960,36 @@ static void zero_block_grads(frcnn_ctx* c) {
 
 // keep_block_grads: the caller has already zeroed the per-block gradient maps and added the ROI-pool gradients
 static void gemm_rows(frcnn_ctx* c, const bf16* a, const bf16* w, int R, int nin, int nout, float* out);
+// element offset of head i's block of gathered windows in c->hs_x (the heads' [M][k*k*cin] blocks back to back)
+static size_t head_rows_offset(const frcnn_ctx* c, int i) {
+  size_t o = 0;
+  for (int j = 0; j < i; ++j) o += (size_t)c->hl_count[j] * c->heads[j].conv.k * c->heads[j].conv.k * c->heads[j].conv.cin;
+  return o;
+}
+// The anchor networks on the listed pixels only (lossAndGradient reads their outputs nowhere else, objective.lua:96-131):
+// gather the k x k windows, one tensor-core GEMM per head against the packed forward filters, tail on the M rows.
+static void sparse_head_forward(frcnn_ctx* c) {
+  cudaStream_t st = c->stream;
+  for (size_t i = 0; i < c->heads.size(); ++i) {
+    const int M = c->hl_count[i];
+    if (M == 0) continue;
+    Head& hd = c->heads[i];
+    ConvLayer& cv = hd.conv;
+    const int* list = c->hl_dev + c->hl_off[i];
+    const int kkc = cv.k * cv.k * cv.cin;
+    bf16* windows = c->hs_x + head_rows_offset(c, (int)i);
+    float* hpre = c->hs_h + (size_t)c->hl_off[i] * 256;
+    launch_head_gather_rows(c->pool_out[hd.input - 1], list, M, hd.hh, hd.hw, cv.hin, cv.win, cv.cin, cv.k, windows, st);
+    gemm_rows(c, windows, cv.w_packed, M, kkc, cv.cout, hpre);
+    HeadTailList t;
+    t.hpre = hpre; t.list = list; t.M = M; t.HW = hd.hh * hd.hw;
+    t.bias = P(c, cv.p_b); t.prelu = P(c, cv.p_prelu); t.w2 = P(c, hd.p_w2); t.b2 = P(c, hd.p_b2);
+    t.out = hd.out;
+    launch_head_tail_list(t, st);
+    c->launches += 2;
+  }
+  c->hs_forward = true;
+}
 static void wgrad_rows(frcnn_ctx* c, const bf16* dy, const bf16* x, int R, int nin, int nout, float* dw, bool zero);
 // sparse_heads: the caller (lossAndGradient) has listed, per head, the pixels delta_outputs can be non-zero at
 // (c->hl_dev / hl_off / hl_count): the head convolutions' backward runs on those pixels only
@@ -989,10 +1026,17 @@ static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out, bool keep_
       const int* list = c->hl_dev + c->hl_off[i];
       const int kkc = cv.k * cv.k * cv.cin;
       hb.list = list; hb.M = M; hb.dpre = c->hs_d;
+      const bf16* windows = c->hs_x;
+      if (c->hs_forward) {   // the forward left this head's windows and conv outputs behind
+        windows = c->hs_x + head_rows_offset(c, i);
+        hb.ws = c->hs_h + (size_t)c->hl_off[i] * 256;
+        hb.ws_compact = 1;
+      }
       launch_head_tail_bwd(hb, c->sm_count, st);
       // weight gradient: dW[co][tap][ci] = dpre[M][co]^T x windows[M][tap][ci]
-      launch_head_gather_rows(c->pool_out[hd.input - 1], list, M, hd.hh, hd.hw, cv.hin, cv.win, cv.cin, cv.k, c->hs_x, st);
-      wgrad_rows(c, c->hs_d, c->hs_x, M, kkc, cv.cout, cv.dw_taps, true);
+      if (!c->hs_forward)
+        launch_head_gather_rows(c->pool_out[hd.input - 1], list, M, hd.hh, hd.hw, cv.hin, cv.win, cv.cin, cv.k, c->hs_x, st);
+      wgrad_rows(c, c->hs_d, windows, M, kkc, cv.cout, cv.dw_taps, true);
       launch_wgrad_finish(cv.dw_taps, G(c, cv.p_w), cv.cout, cv.cin, cv.k, cv.k, st);
       // data gradient: G[M][tap][ci] = dpre[M][co] x W, scattered onto the windows
       if (hd.rows_gen != c->weights_gen) {
@@ -1095,6 +1139,7 @@ static void ensure_objective_workspace(frcnn_ctx* c, int rows) {
   c->hl_dev = (int*)dev_alloc(A, (size_t)R * sizeof(int));
   c->hs_d = (bf16*)dev_alloc(A, (size_t)R * 256 * sizeof(bf16));
   c->hs_x = (bf16*)dev_alloc(A, (size_t)R * max_kkc * sizeof(bf16));
+  c->hs_h = (float*)dev_alloc(A, (size_t)R * 256 * sizeof(float));
   c->hs_g = (float*)dev_alloc(A, (size_t)R * max_kkc * sizeof(float));
   c->cw_rows = R;
   c->cw_n = NF;
@@ -1280,7 +1325,8 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
     }
     ++mi;
   }
-  do_pnet_forward(c, img_dev, N, H, W, true);
+  c->hs_forward = false;
+  do_pnet_forward(c, img_dev, N, H, W, true, sparse_heads);
   FRCNN_CUDA_TRY(cudaMemsetAsync(c->losses_dev, 0, (size_t)N * 8 * sizeof(float), st));
   FRCNN_CUDA_TRY(cudaMemsetAsync(c->t_status, 0, 4 * sizeof(int), st));
   for (size_t i = 0; i < c->heads.size(); ++i)
@@ -1323,6 +1369,7 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
       }
       if (!c->hl_host.empty())
         FRCNN_CUDA_TRY(cudaMemcpyAsync(c->hl_dev, c->hl_host.data(), c->hl_host.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+      sparse_head_forward(c);
     }
     // ---- RPN criteria on the listed anchors (objective.lua:91-140), all frames in one launch
     RpnLossParams lp;
@@ -1350,6 +1397,8 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
   std::vector<const float*> d_out(c->heads.size() + 1, nullptr);
   for (size_t i = 0; i < c->heads.size(); ++i) d_out[i] = c->head_dout[i];
   do_pnet_backward(c, d_out.data(), true, sparse_heads);
+  if (sparse_heads) c->train_ready = false;   // the dense head activations of this forward do not exist: a later
+                                              // pnet:backward must follow its own pnet:forward
   std::vector<float> lh((size_t)N * 8);
   int sh[4];
   FRCNN_CUDA_TRY(cudaMemcpyAsync(lh.data(), c->losses_dev, (size_t)N * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -44,6 +44,7 @@ struct HeadTailBwd {
   float *dw2, *db2, *db1, *dslope;
   const int* list = nullptr;   // sparse form: the M pixels (flat n * HW + y * hw + x, unique) that can carry gradient;
   int M = 0;                   // dpre is then the COMPACT [M][256] matrix, row r = pixel list[r]
+  int ws_compact = 0;          // sparse forward: ws is the compact [M][256] conv output of the listed pixels (one slice)
 };
 void launch_head_tail_bwd(const HeadTailBwd& H, int num_sms, cudaStream_t st);
 // Sparse anchor-head backward (lossAndGradient lists <= 256 anchors per frame, objective.lua:91-140, so delta_outputs is
@@ -52,6 +53,16 @@ void launch_head_tail_bwd(const HeadTailBwd& H, int num_sms, cudaStream_t st);
 //   rows   [M][k*k*Cin] bf16 = the input windows of the listed pixels (im2col rows, tap-major then channel)
 //   w_rows [k*k*Cin][Cout] bf16 = the filter as the GEMM operand of  G[M][k*k*Cin] = dpre[M][Cout] x W
 //   scatter: dx[n][y + ty][x + tx][ci] += G[r][(ty * k + tx) * Cin + ci]
+// forward tail of the listed pixels: out[n][o][y][x] = b2[o] + sum_c w2[o][c] * PReLU(hpre[r][c] + bias[c]), written at
+// the listed pixels only (the criteria read nothing else, objective.lua:96-131)
+struct HeadTailList {
+  const float* hpre;   // [M][256] conv output of the listed pixels (no bias)
+  const int* list;
+  int M, HW;
+  const float *bias, *prelu, *w2, *b2;
+  float* out;          // [N][18][HW]
+};
+void launch_head_tail_list(const HeadTailList& H, cudaStream_t st);
 void launch_pack_head_weight_rows(const float* w, bf16* out, int Cout, int Cin, int K, cudaStream_t st);
 void launch_head_gather_rows(const bf16* x, const int* list, int M, int hh, int hw, int Hin, int Win, int Cin, int K, bf16* rows,
                              cudaStream_t st);

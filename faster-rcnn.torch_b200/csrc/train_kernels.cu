@@ -289,7 +289,9 @@ __global__ void __launch_bounds__(256) head_tail_bwd_list_kernel(HeadTailBwd H) 
     }
     __syncthreads();
     float h = bias;
-    for (int s = 0; s < H.splits; ++s) h += H.ws[(size_t)s * H.slice_stride + pix * CM + c];
+    if (H.ws_compact) h += H.ws[(long)it * CM + c];
+    else
+      for (int s = 0; s < H.splits; ++s) h += H.ws[(size_t)s * H.slice_stride + pix * CM + c];
     const float a = h > 0.f ? h : h * slope;
     float dA = 0.f;
 #pragma unroll
@@ -328,7 +330,35 @@ void launch_head_tail_bwd(const HeadTailBwd& H, int num_sms, cudaStream_t st) {
   head_tail_bwd_kernel<<<blocks, 256, smem, st>>>(H);
 }
 
-// ------------------------------------------------------------------------------------------ sparse anchor-head backward
+// ------------------------------------------------------------------------------------------ sparse anchor-head passes
+// CTA <-> listed pixel, thread <-> channel: 18 dot products over the 256 activations, reduced warp -> CTA
+__global__ void __launch_bounds__(256) head_tail_list_kernel(HeadTailList H) {
+  constexpr int CO = 18, CM = 256;
+  __shared__ float s_part[CM / 32][CO];
+  const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
+  const float bias = H.bias[c], slope = H.prelu[0];
+  for (int it = blockIdx.x; it < H.M; it += gridDim.x) {
+    const long pix = H.list[it];
+    const long n = pix / H.HW, hw = pix - n * H.HW;
+    const float h = bias + H.hpre[(long)it * CM + c];
+    const float a = h > 0.f ? h : h * slope;
+    __syncthreads();   // the previous pixel's partial sums have been consumed
+#pragma unroll
+    for (int o = 0; o < CO; ++o) {
+      const float v = warp_sum(a * H.w2[o * CM + c]);
+      if (lane == 0) s_part[warp][o] = v;
+    }
+    __syncthreads();
+    if (c < CO) {
+      float v = H.b2[c];
+      for (int w = 0; w < CM / 32; ++w) v += s_part[w][c];
+      H.out[(n * CO + c) * H.HW + hw] = v;
+    }
+  }
+}
+void launch_head_tail_list(const HeadTailList& H, cudaStream_t st) {
+  if (H.M > 0) head_tail_list_kernel<<<H.M, 256, 0, st>>>(H);
+}
 __global__ void pack_head_weight_rows_kernel(const float* __restrict__ w, bf16* __restrict__ out, int Cout, int Cin, int taps) {
   const long total = (long)Cout * Cin * taps;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {

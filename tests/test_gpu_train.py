@@ -435,10 +435,10 @@ def test_train_batch_equals_frame_by_frame(F, small_model, h, w, counts):
 
 @pytest.mark.parametrize("h,w,counts", [(122, 192, [(10, 14), (0, 0), (3, 30)]), (450, 800, [(128, 128)] * 2)])
 def test_sparse_head_backward_equals_dense(F, small_model, h, w, counts, monkeypatch):
-    """lossAndGradient runs the anchor heads' backward on the listed pixels only (two small GEMMs + gather / scatter);
-    FRCNN_HEAD_SPARSE=0 takes the dense convolutions pnet:backward uses for arbitrary deltas.  Same products, different
-    fp32 summation order: the anchor-head filters' gradients agree to 1e-5 relative L2 (measured 5e-8), the losses are
-    identical; everything downstream of the block gradients passes through bf16 gradient maps and atomic reductions
+    """lossAndGradient runs the anchor heads -- forward and backward -- on the listed pixels only (gather, small
+    GEMMs, scatter); FRCNN_HEAD_SPARSE=0 takes the dense convolutions pnet:forward / pnet:backward use for whole maps and
+    arbitrary deltas.  Same products, different fp32 summation order: the anchor-head filters' gradients agree to 2e-4
+    relative L2 (measured 4e-5: a few bf16 roundings of the pre-activation gradient flip), the losses to 1e-5; everything downstream of the block gradients passes through bf16 gradient maps and atomic reductions
     whose order varies from run to run (dense against dense: 4e-3 on the whole gradient, tools/sparse_check.py), so the
     trunk filters and the whole gradient get the batch test's 2e-2.  An anchor listed twice exercises the
     de-duplication of the pixel list."""
@@ -483,7 +483,7 @@ def test_sparse_head_backward_equals_dense(F, small_model, h, w, counts, monkeyp
                 if b.norm().item() == 0.0:
                     assert a.norm().item() == 0.0, name      # a head without listed anchors
                 else:
-                    bar = 1e-5 if name.endswith("_conv.weight") else 2e-2
+                    bar = 2e-4 if name.endswith("_conv.weight") else 2e-2
                     assert ((a - b).norm() / b.norm()).item() < bar, name
     finally:
         m.weights.copy_(saved)
