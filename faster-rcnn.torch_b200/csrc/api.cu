@@ -212,6 +212,8 @@ struct frcnn_ctx {
   NmsWorkspace nms;
   int nms_cap_total = 0, nms_cap_seg = 0;
   // pinned host staging
+  float* h_loss = nullptr;         // page-locked [64 * 8 losses | 4 status ints]: lossAndGradient's early read-back
+  cudaEvent_t loss_ev = nullptr;   // recorded behind that read-back
   int* h_ints = nullptr;           // [16]
   frcnn_detection* h_det = nullptr;
   int h_det_cap = 0;
@@ -1393,17 +1395,28 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
     ++c->launches;
   }
   c->losses_cur = c->losses_dev;
+  // The losses and the status flags are final here, before pnet:backward: they go to page-locked memory behind an event,
+  // and the call returns on THAT event -- the caller's host work between two steps (cleanAnchors, marshalling) then
+  // overlaps the backward pass instead of leaving the GPU idle.  The gradient accumulation is still ordered on the
+  // context's stream (FRCNN_TRAIN_SYNC=1: wait for the whole step, the round-1 behaviour).
+  if (!c->h_loss) {
+    FRCNN_CUDA_TRY(cudaMallocHost(&c->h_loss, (size_t)(MAX_TRAIN_FRAMES * 8 + 4) * sizeof(float)));
+    FRCNN_CUDA_TRY(cudaEventCreateWithFlags(&c->loss_ev, cudaEventDisableTiming));
+  }
+  float* lh = c->h_loss;
+  int* sh = reinterpret_cast<int*>(c->h_loss + MAX_TRAIN_FRAMES * 8);
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(lh, c->losses_dev, (size_t)N * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  FRCNN_CUDA_TRY(cudaMemcpyAsync(sh, c->t_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  FRCNN_CUDA_TRY(cudaEventRecord(c->loss_ev, st));
   // ---- pnet backward (objective.lua:189), all frames at once
   std::vector<const float*> d_out(c->heads.size() + 1, nullptr);
   for (size_t i = 0; i < c->heads.size(); ++i) d_out[i] = c->head_dout[i];
   do_pnet_backward(c, d_out.data(), true, sparse_heads);
   if (sparse_heads) c->train_ready = false;   // the dense head activations of this forward do not exist: a later
                                               // pnet:backward must follow its own pnet:forward
-  std::vector<float> lh((size_t)N * 8);
-  int sh[4];
-  FRCNN_CUDA_TRY(cudaMemcpyAsync(lh.data(), c->losses_dev, (size_t)N * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
-  FRCNN_CUDA_TRY(cudaMemcpyAsync(sh, c->t_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-  FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
+  const char* ts_env = getenv("FRCNN_TRAIN_SYNC");
+  if (ts_env && atoi(ts_env) != 0) FRCNN_CUDA_TRY(cudaStreamSynchronize(st));
+  else FRCNN_CUDA_TRY(cudaEventSynchronize(c->loss_ev));
   for (int n = 0; n < N; ++n)
     for (int i = 0; i < 4; ++i) losses_host[4 * n + i] = lh[8 * n + i];
   FRCNN_REQUIRE(sh[0] == 0, FRCNN_E_INVALID, "an example indexes outside its anchor map: apply cleanAnchors first (objective.lua:32-43)");
@@ -2063,6 +2076,8 @@ int frcnn_destroy(frcnn_ctx* c) {
   if (c->h_ints) cudaFreeHost(c->h_ints);
   if (c->h_det) cudaFreeHost(c->h_det);
   if (c->h_img) cudaFreeHost(c->h_img);
+  if (c->h_loss) cudaFreeHost(c->h_loss);
+  if (c->loss_ev) cudaEventDestroy(c->loss_ev);
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   for (auto& e : c->ev) if (e) cudaEventDestroy(e);
   for (auto& e : c->conv_ev) cudaEventDestroy(e);
@@ -2336,6 +2351,13 @@ __global__ void unpack_roi_rows_kernel(const float* __restrict__ x, float* __res
     int b = k / C, cc = k - b * C;
     out[r * (long)C * bins + (long)cc * bins + b] = x[i];
   }
+}
+
+int frcnn_synchronize(frcnn_ctx* c) {
+  API_BEGIN(c)
+  REQUIRE_DEVICE(c);
+  FRCNN_CUDA_TRY(cudaStreamSynchronize(c->stream));
+  API_END(c)
 }
 
 int frcnn_train_batch(frcnn_ctx* c, const float* img_dev, int n, int h, int w, const frcnn_example* const* pos_host, const int* n_pos,

@@ -262,6 +262,12 @@ class Model:
     def zero_grad(self):
         self.gradient.zero_()
 
+    def synchronize(self):
+        """Waits for the context's stream: train_image / train_batch return when the losses are on the host, while the
+        backward pass may still be accumulating into `self.gradient` (torch ops on the default stream are ordered behind
+        it anyway; this is for host-side readers and timing)."""
+        check(self.ctx, lib().frcnn_synchronize(self.ctx))
+
     def train_image(self, img, positives, negatives, pnet_masks=None, cnet_masks=None, seed=0):
         """The body of the per-image loop of lossAndGradient (objective.lua:65-198) for one frame: forward, criteria,
         backward; gradients accumulate into `self.gradient`.  positives: [(anchor, roi)], negatives: [(anchor,)] as

@@ -169,10 +169,16 @@ int frcnn_train_image(frcnn_ctx* ctx, const float* img_dev, int h, int w, const 
  * once over the whole batch, the per-image stages (criteria, ROI pooling, cnet with its per-image BatchNorm statistics,
  * objective.lua:91-185) frame by frame in between; one host synchronisation.  pos_host / neg_host: n pointers to the
  * frames' example lists, n_pos / n_neg their lengths, seeds one per frame, losses_host [n][4].  Gradients accumulate
- * exactly as n calls of frcnn_train_image would (same sums; the tensor-core reductions differ in order). */
+ * exactly as n calls of frcnn_train_image would (same sums; the tensor-core reductions differ in order).
+ * Both calls return as soon as the losses are on the host (they are final before pnet:backward starts); the gradient
+ * accumulation may still be running on the context's stream.  Work queued on that stream, or on the legacy default
+ * stream (Torch's; it synchronises with the context's blocking stream), is ordered behind it as in any CUDA program;
+ * a host-side reader of the gradient calls frcnn_synchronize first.  FRCNN_TRAIN_SYNC=1 waits for the whole step. */
 int frcnn_train_batch(frcnn_ctx* ctx, const float* img_dev, int n, int h, int w, const frcnn_example* const* pos_host,
                       const int* n_pos, const frcnn_example* const* neg_host, const int* n_neg,
                       const float* const* pnet_masks_dev, const uint64_t* seeds, float* losses_host);
+/* Blocks until everything queued on the context's stream has finished (cutorch.synchronize() for this context). */
+int frcnn_synchronize(frcnn_ctx* ctx);
 
 /* cnet:forward(cinput) in training mode + the detection-stage criteria + cnet:backward (objective.lua:164-179).
  * x_dev: [R][kh*kw*C] fp32 (reference ordering), the first n_pos rows are positives; crtarget_dev [R][4];
