@@ -75,13 +75,14 @@ void launch_pack_conv_weight_dgrad(const float* w, bf16* out, int Cout, int Cin,
 }
 
 __global__ void wgrad_finish_kernel(const float* __restrict__ dw, float* __restrict__ grad, int Cout, int Cin, int taps) {
-  long total = (long)Cout * Cin * taps;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    int t = i % taps;
-    long r = i / taps;
-    int ci = r % Cin;
-    int co = r / Cin;
-    grad[i] += dw[((long)co * taps + t) * Cin + ci];
+  // (a filter bank has far fewer than 2^31 weights: 32-bit index arithmetic)
+  const int total = Cout * Cin * taps;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int t = i % taps;
+    const int r = i / taps;
+    const int ci = r % Cin;
+    const int co = r / Cin;
+    grad[i] += dw[(co * taps + t) * Cin + ci];
   }
 }
 void launch_wgrad_finish(const float* dw_taps, float* grad, int Cout, int Cin, int KH, int KW, cudaStream_t st) {

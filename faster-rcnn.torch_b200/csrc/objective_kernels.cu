@@ -156,15 +156,17 @@ __global__ void roi_pool_bwd_kernel(const float* __restrict__ d_rows, const int*
   d_rows += first;
   argmax += first;
   dfeat += fr * fmap_elems;
+  // (the launcher keeps a frame's element count below 2^31: 32-bit modulo instead of a 64-bit one per element)
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const float d = d_rows[i];
-    if (d != 0.f) atomicAdd(dfeat + (long)argmax[i] * C + (int)(i % C), d);  // ROIs overlap: atomics
+    if (d != 0.f) atomicAdd(dfeat + (long)argmax[i] * C + (int)((unsigned)i % (unsigned)C), d);  // ROIs overlap: atomics
   }
 }
 void launch_roi_pool_bwd(const float* d_rows, const int* argmax, const FrameList& fl, int bins, int C, float* dfeat, long fmap_elems,
                          cudaStream_t st) {
   const long total = (long)fl.max_R() * bins * C;   // (feat = bins * C is a multiple of C, so i % C is the channel in every frame)
   if (total <= 0) return;
+  FRCNN_REQUIRE(total < 0x7fffffffL, FRCNN_E_INVALID, "ROI-pool backward: more than 2^31 pooled elements in one frame");
   const int bx = (int)std::min<long>(cdiv(total, 256), std::max(148 * 16 / fl.nf, 148));
   roi_pool_bwd_kernel<<<dim3(bx, fl.nf), 256, 0, st>>>(d_rows, argmax, fl, bins * C, C, dfeat, fmap_elems);
 }
@@ -452,20 +454,22 @@ void launch_pack_fc_weight_dgrad(const float* w, bf16* out, int nout, int C, int
 __global__ void __launch_bounds__(256) wgrad_finish_fc_kernel(const float* __restrict__ dw, float* __restrict__ grad, int nout, int C,
                                                               int bins, int permute) {
   extern __shared__ float srow[];
-  const long K = (long)C * bins;
+  const int K = C * bins;   // 32-bit index arithmetic throughout: the 64-bit divisions of the first version cost more than the traffic
   for (int o = blockIdx.x; o < nout; o += gridDim.x) {
+    const float* src = dw + (long)o * K;
+    float* dst = grad + (long)o * K;
     if (!permute) {
-      for (long k = threadIdx.x; k < K; k += blockDim.x) grad[o * K + k] += dw[o * K + k];
+      for (int k = threadIdx.x; k < K; k += blockDim.x) dst[k] += src[k];
       continue;
     }
     __syncthreads();
     // one pad word per C-long bin row: consecutive threads read consecutive bins of one channel, C (a multiple of 32)
     // words apart -- the same bank without the pad
-    for (long k = threadIdx.x; k < K; k += blockDim.x) srow[k + k / C] = dw[o * K + k];
+    for (int k = threadIdx.x; k < K; k += blockDim.x) srow[k + k / C] = src[k];
     __syncthreads();
-    for (long d = threadIdx.x; d < K; d += blockDim.x) {
-      const int c = (int)(d / bins), b = (int)(d - (long)c * bins);
-      grad[o * K + d] += srow[(long)b * (C + 1) + c];
+    for (int d = threadIdx.x; d < K; d += blockDim.x) {
+      const int c = d / bins, b = d - c * bins;
+      dst[d] += srow[b * (C + 1) + c];
     }
   }
 }

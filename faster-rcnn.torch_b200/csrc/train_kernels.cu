@@ -55,7 +55,9 @@ void launch_dropout_mask_frames(float* mask, const FrameList& fl, int per_row, f
 // Backward of [PReLU -> SpatialDropout mask -> MaxPool 2x2 ceil] given the gradient wrt the POOLED output: only the
 // winner of every window receives gradient; its pre-activation sign is the sign of the pooled value.
 // g: fp32 [N][Hp][Wp][C]; arg: winners; yp: pooled activations; dpre: bf16 [N][H][W][C] (every element written).
-// thread <-> (pooled pixel, 8 channels).
+// thread <-> (pooled pixel, 8 channels).  I = index type: 32-bit whenever the item count allows (a 64-bit division costs
+// ~100 instructions; three of them per 16-byte item made these streaming kernels issue-bound).
+template <typename I>
 __global__ void __launch_bounds__(256) unpool_prelu_bwd_kernel(const float* __restrict__ g, const uint8_t* __restrict__ arg,
                                                                const bf16* __restrict__ yp, const float* __restrict__ slope_p,
                                                                const float* __restrict__ mask, bf16* __restrict__ dpre,
@@ -68,20 +70,20 @@ __global__ void __launch_bounds__(256) unpool_prelu_bwd_kernel(const float* __re
   const int Hp = (H + 1) >> 1, Wp = (W + 1) >> 1, cv = C >> 3;
   const float slope = slope_p[0];
   const float inv_slope = 1.0f / slope;
-  const long total = (long)N * Hp * Wp * cv;
+  const I total = (I)N * Hp * Wp * cv;
   float ds = 0.f;
   // the launcher makes the grid stride a multiple of C / 8, so a thread keeps its 8 channels over all iterations and
   // the bias-gradient partials live in registers (one shared-memory atomic per channel and thread at the end, not
   // one per element: the shared atomics paced this kernel)
   float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int c8_fixed = (int)((blockIdx.x * (long)blockDim.x + threadIdx.x) % cv);
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  for (I i = (I)blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * (I)blockDim.x) {
     const int c8 = c8_fixed;
-    long r = i / cv;
-    const int pw = (int)(r % Wp);
-    r /= Wp;
-    const int ph = (int)(r % Hp);
-    const int n = (int)(r / Hp);
+    I r = i / (I)cv;
+    const int pw = (int)(r % (I)Wp);
+    r /= (I)Wp;
+    const int ph = (int)(r % (I)Hp);
+    const int n = (int)(r / (I)Hp);
     const long pbase = (((long)n * Hp + ph) * Wp + pw) * C + c8 * 8;
     const float4 g0 = *reinterpret_cast<const float4*>(g + pbase), g1 = *reinterpret_cast<const float4*>(g + pbase + 4);
     const uint2 a8 = *reinterpret_cast<const uint2*>(arg + pbase);
@@ -143,13 +145,17 @@ void launch_unpool_prelu_bwd(const float* g, const uint8_t* arg, const bf16* yp,
                              float* dbias, float* dslope, int N, int H, int W, int C, int num_sms, cudaStream_t st) {
   const long total = (long)N * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
   const int blocks = channel_stable_grid(total, C / 8, num_sms);
-  unpool_prelu_bwd_kernel<<<blocks, 256, C * sizeof(float), st>>>(g, arg, yp, slope, mask, dpre, dbias, dslope, N, H, W, C);
+  if (total + (long)blocks * 256 < 0x7fffffffL)
+    unpool_prelu_bwd_kernel<int><<<blocks, 256, C * sizeof(float), st>>>(g, arg, yp, slope, mask, dpre, dbias, dslope, N, H, W, C);
+  else
+    unpool_prelu_bwd_kernel<long><<<blocks, 256, C * sizeof(float), st>>>(g, arg, yp, slope, mask, dpre, dbias, dslope, N, H, W, C);
 }
 
 // ------------------------------------------------------------------------------------------ plain conv backward
 // Backward of [PReLU -> mask] for a conv that is not followed by the pool: dpre = dy * mask * (y < 0 ? slope : 1), from
 // the bf16 gradient tensor produced by the next conv's dgrad (d) into the tensor the previous conv's backward reads
 // (out; may alias d).  thread <-> (pixel, 8 channels).
+template <typename I>
 __global__ void __launch_bounds__(256) prelu_bwd_kernel(const bf16* d, bf16* out, const bf16* __restrict__ y, const float* __restrict__ slope_p,
                                                         const float* __restrict__ mask, float* __restrict__ dbias,
                                                         float* __restrict__ dslope, long npix_per_img, int N, int C) {
@@ -160,14 +166,13 @@ __global__ void __launch_bounds__(256) prelu_bwd_kernel(const bf16* d, bf16* out
   const int cv = C >> 3;
   const float slope = slope_p[0];
   const float inv_slope = 1.0f / slope;
-  const long total = (long)N * npix_per_img * cv;
+  const I total = (I)N * (I)npix_per_img * cv;
   float ds = 0.f;
   float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // see unpool_prelu_bwd_kernel
   const int c8_fixed = (int)((blockIdx.x * (long)blockDim.x + threadIdx.x) % cv);
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  for (I i = (I)blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * (I)blockDim.x) {
     const int c8 = c8_fixed;
-    const long pix = i / cv;
-    const int n = (int)(pix / npix_per_img);
+    const int n = mask ? (int)((i / (I)cv) / (I)npix_per_img) : 0;   // only the dropout mask is per frame
     uint4 d8 = reinterpret_cast<const uint4*>(d)[i];
     const uint4 y8 = reinterpret_cast<const uint4*>(y)[i];
     bf16* de = reinterpret_cast<bf16*>(&d8);
@@ -203,7 +208,10 @@ void launch_prelu_bwd(const bf16* d, bf16* out, const bf16* y, const float* slop
                       int C, int num_sms, cudaStream_t st) {
   const long total = (long)N * H * W * (C / 8);
   const int blocks = channel_stable_grid(total, C / 8, num_sms);
-  prelu_bwd_kernel<<<blocks, 256, C * sizeof(float), st>>>(d, out, y, slope, mask, dbias, dslope, (long)H * W, N, C);
+  if (total + (long)blocks * 256 < 0x7fffffffL)
+    prelu_bwd_kernel<int><<<blocks, 256, C * sizeof(float), st>>>(d, out, y, slope, mask, dbias, dslope, (long)H * W, N, C);
+  else
+    prelu_bwd_kernel<long><<<blocks, 256, C * sizeof(float), st>>>(d, out, y, slope, mask, dbias, dslope, (long)H * W, N, C);
 }
 
 // ------------------------------------------------------------------------------------------ anchor-head tail backward
@@ -373,14 +381,15 @@ void launch_pack_head_weight_rows(const float* w, bf16* out, int Cout, int Cin, 
   pack_head_weight_rows_kernel<<<(int)std::min<long>(cdiv(total, 256), 148 * 8), 256, 0, st>>>(w, out, Cout, Cin, K * K);
 }
 // item <-> (listed pixel, filter tap, 8 channels): one 16-byte copy
+template <typename I>
 __global__ void head_gather_rows_kernel(const bf16* __restrict__ x, const int* __restrict__ list, int M, int hh, int hw, int Hin, int Win,
                                         int Cin, int K, bf16* __restrict__ rows) {
   const int cv = Cin >> 3, taps = K * K;
-  const long total = (long)M * taps * cv;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cv);
-    const long q = i / cv;
-    const int t = (int)(q % taps), r = (int)(q / taps);
+  const I total = (I)M * taps * cv;
+  for (I i = (I)blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * (I)blockDim.x) {
+    const int c8 = (int)(i % (I)cv);
+    const I q = i / (I)cv;
+    const int t = (int)(q % (I)taps), r = (int)(q / (I)taps);
     const int pix = list[r];
     const int n = pix / (hh * hw), rem = pix - n * hh * hw;
     const int y = rem / hw + t / K, xx = rem % hw + t % K;
@@ -392,17 +401,20 @@ void launch_head_gather_rows(const bf16* x, const int* list, int M, int hh, int 
                              cudaStream_t st) {
   const long total = (long)M * K * K * (Cin / 8);
   if (total <= 0) return;
-  head_gather_rows_kernel<<<(int)std::min<long>(cdiv(total, 256), 148 * 16), 256, 0, st>>>(x, list, M, hh, hw, Hin, Win, Cin, K, rows);
+  const int blocks = (int)std::min<long>(cdiv(total, 256), 148 * 16);
+  if (total + (long)blocks * 256 < 0x7fffffffL) head_gather_rows_kernel<int><<<blocks, 256, 0, st>>>(x, list, M, hh, hw, Hin, Win, Cin, K, rows);
+  else head_gather_rows_kernel<long><<<blocks, 256, 0, st>>>(x, list, M, hh, hw, Hin, Win, Cin, K, rows);
 }
 // item <-> (listed pixel, filter tap, 4 channels): one 16-byte vector reduction (windows of listed pixels overlap)
+template <typename I>
 __global__ void head_scatter_rows_kernel(const float* __restrict__ g, const int* __restrict__ list, int M, int hh, int hw, int Hin,
                                          int Win, int Cin, int K, float* __restrict__ dx) {
   const int cv = Cin >> 2, taps = K * K;
-  const long total = (long)M * taps * cv;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % cv);
-    const long q = i / cv;
-    const int t = (int)(q % taps), r = (int)(q / taps);
+  const I total = (I)M * taps * cv;
+  for (I i = (I)blockIdx.x * (I)blockDim.x + threadIdx.x; i < total; i += (I)gridDim.x * (I)blockDim.x) {
+    const int c4 = (int)(i % (I)cv);
+    const I q = i / (I)cv;
+    const int t = (int)(q % (I)taps), r = (int)(q / (I)taps);
     const int pix = list[r];
     const int n = pix / (hh * hw), rem = pix - n * hh * hw;
     const int y = rem / hw + t / K, xx = rem % hw + t % K;
@@ -414,7 +426,9 @@ void launch_head_scatter_rows(const float* g, const int* list, int M, int hh, in
                               cudaStream_t st) {
   const long total = (long)M * K * K * (Cin / 4);
   if (total <= 0) return;
-  head_scatter_rows_kernel<<<(int)std::min<long>(cdiv(total, 256), 148 * 16), 256, 0, st>>>(g, list, M, hh, hw, Hin, Win, Cin, K, dx);
+  const int blocks = (int)std::min<long>(cdiv(total, 256), 148 * 16);
+  if (total + (long)blocks * 256 < 0x7fffffffL) head_scatter_rows_kernel<int><<<blocks, 256, 0, st>>>(g, list, M, hh, hw, Hin, Win, Cin, K, dx);
+  else head_scatter_rows_kernel<long><<<blocks, 256, 0, st>>>(g, list, M, hh, hw, Hin, Win, Cin, K, dx);
 }
 
 // ------------------------------------------------------------------------------------------ first-layer wgrad
