@@ -56,12 +56,13 @@ def dp_allreduce(model, counters):
     return buf[:len(counters)].tolist()
 
 
-def create_objective(model, dist=None, defer_div=False, batched=True):
+def create_objective(model, dist=None, defer_div=False, batched=True, rank=None):
     """Returns lossAndGradient(batch, seed) -> (loss, gradient, stats); batch = list of dicts {img [3][H][W] tensor,
     positive [(anchor, roi)], negative [(anchor,)]} as BatchIterator:nextTraining yields them (this rank's share).
     batched: frames of equal size are processed by one frcnn_train_batch call (False: frame by frame, frcnn_train_image).
     defer_div: leave gradient:div(cls_count) (objective.lua:200) to the fused optimiser pass (optim.rmsprop_step's
-    grad_div = stats['deferred_div'])."""
+    grad_div = stats['deferred_div']).  rank: the rank the dropout seeds are derived from (default: dist's rank, 0 without
+    a group) -- a local objective that must draw the masks of a given rank passes it here."""
 
     # With NCCL available the collective runs inside the C library (frcnn_dp_*: in place, bucketed, overlapped with
     # pnet:backward); the torch.distributed path below remains for host-only groups (gloo tests).
@@ -72,7 +73,8 @@ def create_objective(model, dist=None, defer_div=False, batched=True):
     from ._lib import lib as _lib
 
     counter = dict(step=0)
-    rank = dist.get_rank() if (dist is not None and dist.is_initialized()) else 0
+    if rank is None:
+        rank = dist.get_rank() if (dist is not None and dist.is_initialized()) else 0
 
     def lossAndGradient(batch, seed=None):
         # the reference draws fresh SpatialDropout / Dropout masks from the global generator on every forward: without an

@@ -34,7 +34,7 @@ def main():
         pos, neg = F.clean_anchors(pos, dims), F.clean_anchors(neg, dims)
         batch.append(dict(img=OM.synthetic_frame(h, w, seed=100 * rank + s).cuda(), positive=pos, negative=neg,
                           packed=(m.pack_examples(pos), m.pack_examples(neg))))
-    local_only = F.create_objective(m, None, defer_div=True)           # no collective
+    local_only = F.create_objective(m, None, defer_div=True, rank=rank)   # no collective; this rank's dropout seeds
     lib_dp = F.create_objective(m, dist, defer_div=True)               # frcnn_dp_allreduce (overlapped: one size group)
     # ---- 1. equality with torch.distributed on IDENTICAL per-rank gradients.  The backward pass itself is not bit
     # reproducible run to run (ROI-pool scatter atomics, TMA reduce-add split-K weight gradients), so the same local
