@@ -48,6 +48,10 @@ class Model:
     def __init__(self, cfg, layers, anchor_nets, class_layers, device=0, dropout_eval_scale=-1.0, stream=None):
         self.cfg, self.layers, self.anchor_nets, self.class_layers = cfg, layers, anchor_nets, class_layers
         self._ctor = dict(device=device, dropout_eval_scale=dropout_eval_scale)
+        # a caller-supplied stream is not ordered with torch's default stream: the training calls, which return before the
+        # backward pass has finished, are followed by a synchronize() then (the library's own stream is a blocking one,
+        # which the legacy default stream waits for implicitly)
+        self._foreign_stream = bool(stream)
         self.host_only = device == -1  # plan + Localizer / Anchors geometry only; no compute entry point works
         if not self.host_only and not torch.cuda.is_available():
             # fail loudly: the product has no CPU path
@@ -310,6 +314,8 @@ class Model:
         torch.cuda.synchronize(self.device)
         check(self.ctx, lib().frcnn_train_image(self.ctx, ffi.cast("const float*", x.data_ptr()), h, w, pos, len(positives), neg,
                                                 len(negatives), pm, cm, seed, losses))
+        if self._foreign_stream:
+            self.synchronize()      # `keep` (the injected masks) is released on return
         return dict(cls=losses[0], reg=losses[1], creg=losses[2], ccls=losses[3])
 
     # frcnn_example as a numpy record: the example lists are marshalled with array operations, not per-field cffi writes
@@ -357,6 +363,8 @@ class Model:
         # synchronize: uploads of the next step's frames on a prefetcher's stream keep running
         torch.cuda.current_stream(self.device).synchronize()
         check(self.ctx, lib().frcnn_train_batch(self.ctx, ffi.cast("const float*", x.data_ptr()), n, h, w, pp, n_pos, qq, n_neg, pm, sd, losses))
+        if self._foreign_stream:
+            self.synchronize()
         return [dict(cls=losses[4 * i], reg=losses[4 * i + 1], creg=losses[4 * i + 2], ccls=losses[4 * i + 3]) for i in range(n)]
 
     def _cnet_forward(self, x, dropout_masks=None, seed=0):
