@@ -1068,6 +1068,8 @@ static void do_pnet_backward(frcnn_ctx* c, const float* const* d_out, bool keep_
     for (size_t li = li_end; li-- > li_first;) {
       ConvLayer& cv = c->trunk[li];
       if (cv.first) {
+        FRCNN_REQUIRE(cv.k == 3 && cv.pad == 1 && cv.cout == 64, FRCNN_E_INVALID,
+                      "training: the first convolution must be 3 -> 64 channels, 3x3, padding 1 (both reference models)");
         launch_first_wgrad(c->gscratch[0], c->train_img, G(c, cv.p_w), N, cv.hin, cv.win, cv.pad, c->sm_count, st);
         ++c->launches;
         break;
@@ -3030,7 +3032,8 @@ int frcnn_conv_first_wgrad(frcnn_ctx* c, const uint16_t* dy_dev, const float* im
   API_BEGIN(c)
   REQUIRE_DEVICE(c);
   FRCNN_REQUIRE(dy_dev && img_dev && dw_dev, FRCNN_E_INVALID, "null argument");
-  FRCNN_REQUIRE(n > 0 && h > 0 && w > 0 && pad >= 0 && pad <= 1, FRCNN_E_INVALID, "bad shape");
+  // the kernel indexes dy and the frame with the same (h, w): a 3 x 3 filter with padding 1, as both reference models have
+  FRCNN_REQUIRE(n > 0 && h > 0 && w > 0 && pad == 1, FRCNN_E_INVALID, "first-layer wgrad: 3x3 filter, padding 1");
   if (iters < 1) iters = 1;
   cudaEvent_t e0, e1;
   FRCNN_CUDA_TRY(cudaEventCreate(&e0));

@@ -412,7 +412,8 @@ int frcnn_conv_first(frcnn_ctx* ctx, const float* img_dev, const float* w_dev, c
                      const float* prelu_dev, float scale, int n, int h, int w, int cout, int pad, int pool,
                      uint16_t* out_dev, int iters, float* elapsed_ms);
 /* Its weight gradient (accGradParameters of the first nn.SpatialConvolution inside pnet:backward, objective.lua:189):
- * dw_dev [64][3][3][3] fp32 += sum over pixels of dy_dev [n][h][w][64] (bf16, NHWC) x the padded frame.  Warp-level
+ * dw_dev [64][3][3][3] fp32 += sum over pixels of dy_dev [n][h][w][64] (bf16, NHWC) x the padded frame (pad = 1: the
+ * output has the frame's size, as in both reference models; anything else is rejected).  Warp-level
  * tensor-core kernel with the frame split hi/lo, so the frame enters at 16 mantissa bits. */
 int frcnn_conv_first_wgrad(frcnn_ctx* ctx, const uint16_t* dy_dev, const float* img_dev, int n, int h, int w, int pad,
                            float* dw_dev, int iters, float* elapsed_ms);
