@@ -355,6 +355,13 @@ function M.create_objective(model, weights, gradient, batch_iterator, stats)
   end
 end
 
+-- frcnn_train_image / frcnn_train_batch return when the losses are on the host; the backward pass may still be adding
+-- into the gradient on the context's stream.  cutorch work on the default stream is ordered behind it (the context's
+-- stream is a blocking one), so lossAndGradient above needs nothing; a host-side reader (gradient:float(), timing) calls this.
+function M.synchronize(model)
+  check(model.b200.ctx, C.frcnn_synchronize(model.b200.ctx))
+end
+
 -- Call after every optimiser step / weights:copy (main.lua:97,133): re-packs fp32 -> bf16 tensor-core layouts.
 function M.pack(model)
   cutorch.synchronize()
