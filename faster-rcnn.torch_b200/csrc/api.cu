@@ -1336,7 +1336,7 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
   for (size_t i = 0; i < c->heads.size(); ++i)
     FRCNN_CUDA_TRY(cudaMemsetAsync(c->head_dout[i], 0, (size_t)N * 18 * c->heads[i].hh * c->heads[i].hw * sizeof(float), st));
   zero_block_grads(c);
-  const int bins = c->roi_kh * c->roi_kw, feat = bins * c->feat_c;
+  const int bins = c->roi_kh * c->roi_kw;
   const size_t fmap_elems = (size_t)c->feat_h * c->feat_w * c->feat_c;
   if (rows > 0) {
     // all example records of the batch in one upload (frame f = rows [off[f], off[f] + R[f]): positives, then negatives)
