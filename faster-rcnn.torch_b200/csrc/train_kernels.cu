@@ -574,8 +574,8 @@ __global__ void __launch_bounds__(256, 2) first_wgrad_kernel(const bf16* __restr
   }
 }
 void launch_first_wgrad(const bf16* dpre, const float* img, float* dw, int N, int H, int W, int pad, int num_sms, cudaStream_t st) {
-  static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(first_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM); attr = true; }
+  static DeviceOnce configured;   // function attributes are per device: one process may drive several (frcnn_dp_init_all)
+  if (first_use_on_device(configured)) cudaFuncSetAttribute(first_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FW_SMEM);
   const long tiles = (long)N * ((H + 7) / 8) * ((W + 31) / 32);
   // the kernel indexes tiles in 32 bits: 2^31 tiles would be a 70 TB gradient tensor
   const int grid = (int)std::min<long>(tiles, (long)num_sms * 2);
