@@ -85,3 +85,38 @@ def test_host_loop_deferred_division_and_default_rank(F):
     assert torch.allclose(grad, torch.ones(6)) and stats["deferred_div"] == 4.0      # the optimiser pass divides
     assert m.calls[0]["seeds"] == [1000003]                                           # rank 0 without a process group
     assert m.calls[0]["packed"] == [("P2", "N2")]
+
+
+def _dp_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import frcnn_b200 as F
+    m = _StubModel()
+    # this rank's share of the batch: rank 0 two frames, rank 1 two frames with other example counts
+    batch = [_frame(64, 96, 1 + rank, 2), _frame(64, 96, 2, 1 + 2 * rank)]
+    obj = F.create_objective(m, dist)
+    loss, grad, stats = obj(batch, seed=3)
+    torch.save(dict(loss=loss, grad=grad.clone(), stats=stats, seeds=m.calls[0]["seeds"]), out % rank)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_host_loop_two_ranks_gloo(tmp_path):
+    """World size 2 on CPU (gloo): every rank runs its share, ONE all-reduce carries the flat gradient and the seven
+    counters, both ranks end with the same gradient divided by the GLOBAL cls_count, and the dropout seeds are disjoint
+    across ranks (rank * len(batch) + frame index)."""
+    import os
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "r%d.pt")
+    mp.spawn(_dp_worker, args=(2, 33100 + os.getpid() % 2000, out), nprocs=2, join=True)
+    r0, r1 = torch.load(out % 0, weights_only=False), torch.load(out % 1, weights_only=False)
+    # stub gradient: +2 per rank (one call of two frames) -> 4 after the sum; cls_count = (1+2 + 2+1) + (2+2 + 2+3) = 15
+    assert r0["stats"]["cls_count"] == 15 and r1["stats"]["cls_count"] == 15
+    assert r0["stats"]["reg_count"] == 3 + 4
+    assert torch.allclose(r0["grad"], torch.full((6,), 4.0 / 15)) and torch.equal(r0["grad"], r1["grad"])
+    assert r0["loss"] == r1["loss"]
+    base = 3 * 1000003
+    assert r0["seeds"] == [base + 0, base + 1] and r1["seeds"] == [base + 2, base + 3]
