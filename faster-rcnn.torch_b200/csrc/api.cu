@@ -1195,7 +1195,7 @@ static void cnet_train_forward(frcnn_ctx* c, const FrameList& fl, const float* c
   cudaStream_t st = c->stream;
   const int rows = fl.rows();
   if (rows <= 0) return;
-  FrameSeeds fs;
+  FrameSeeds fs = {};
   for (int f = 0; f < fl.nf; ++f) fs.seed[f] = seeds[f];
   // ---- cnet forward, training mode (objective.lua:164)
   const bf16* in = c->t_rows;
@@ -1316,7 +1316,7 @@ static void do_train_batch(frcnn_ctx* c, const float* img_dev, int N, int H, int
   FrameList per_frame;   // "one row per frame": the SpatialDropout masks
   memset(&per_frame, 0, sizeof(per_frame));
   per_frame.nf = N;
-  FrameSeeds fs;
+  FrameSeeds fs = {};
   for (int n = 0; n < N; ++n) { per_frame.off[n] = n; per_frame.R[n] = 1; fs.seed[n] = seeds[n]; }
   // ---- pnet forward, training mode (objective.lua:60,71)
   int mi = 0;
